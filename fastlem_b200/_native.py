@@ -1,0 +1,189 @@
+"""ctypes binding of include/fastlem_b200.h.
+
+The product library is fastlem_b200/_lib/libfastlem_b200.so (nvcc, sm_100a).  There is no CPU fallback:
+if the library is missing, or no CUDA device can be opened, this module raises.  (tests/ may pass an
+explicit path to the FL_EMU host build to check solver logic on the CPU tier; nothing else does.)
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libfastlem_b200.so")
+
+UNTIL_STABLE = 0xFFFFFFFF
+OK, E_INVALID, E_STATE, E_CUDA, E_NOMEM = 0, -1, -2, -3, -4
+
+STAGE = dict(receivers=0, receivers_initial=1, labels_initial=2, labels=3, depth=4, drainage_area=5,
+             response_time=6, elevation=7, flood_rank=8)
+_STAGE_DTYPE = {0: np.uint32, 1: np.uint32, 2: np.uint32, 3: np.uint32, 4: np.uint32, 5: np.float64,
+                6: np.float64, 7: np.float64, 8: np.uint32}
+
+# every symbol include/fastlem_b200.h declares
+SYMBOLS = ["fastlem_create", "fastlem_destroy", "fastlem_last_error", "fastlem_set_graph",
+           "fastlem_set_parameters", "fastlem_generate", "fastlem_run", "fastlem_download",
+           "fastlem_set_option", "fastlem_get_stats", "fastlem_debug_fetch", "fastlem_version",
+           "fastlem_host_initial_elevations"]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("iterations", ctypes.c_uint32), ("lake_iterations", ctypes.c_uint32),
+                ("depth_first", ctypes.c_uint32), ("depth_last", ctypes.c_uint32),
+                ("kernel_launches", ctypes.c_uint64), ("ms_run", ctypes.c_double), ("ms_upload", ctypes.c_double),
+                ("ms_flood_rank", ctypes.c_double), ("ms_download", ctypes.c_double),
+                ("ms_receivers", ctypes.c_double), ("ms_labels", ctypes.c_double), ("ms_lakes", ctypes.c_double),
+                ("ms_order", ctypes.c_double), ("ms_area", ctypes.c_double), ("ms_elevation", ctypes.c_double),
+                ("n_receivers", ctypes.c_uint64), ("n_labels", ctypes.c_uint64), ("n_lakes", ctypes.c_uint64),
+                ("n_order", ctypes.c_uint64), ("n_area", ctypes.c_uint64), ("n_elevation", ctypes.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class FastlemError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"fastlem_b200 error {code}: {msg}")
+        self.code = code
+
+
+_libs = {}
+
+
+def load(path=None):
+    path = path or LIB_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise ImportError(
+            f"fastlem_b200: native library not found at {path}. Build it with `python -m fastlem_b200.build` "
+            "(needs nvcc). There is no CPU fallback.")
+    lib = ctypes.CDLL(path)
+    vp, u32, u32p, f64p = ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32), \
+        ctypes.POINTER(ctypes.c_double)
+    lib.fastlem_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int]
+    lib.fastlem_destroy.argtypes = [vp]
+    lib.fastlem_destroy.restype = None
+    lib.fastlem_last_error.argtypes = [vp]
+    lib.fastlem_last_error.restype = ctypes.c_char_p
+    lib.fastlem_set_graph.argtypes = [vp, u32, u32p, u32p, f64p, f64p]
+    lib.fastlem_set_parameters.argtypes = [vp, f64p, f64p, f64p, f64p, u32p, u32]
+    lib.fastlem_generate.argtypes = [vp, u32, f64p, u32p]
+    lib.fastlem_run.argtypes = [vp, u32, u32p]
+    lib.fastlem_download.argtypes = [vp, f64p]
+    lib.fastlem_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int64]
+    lib.fastlem_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    lib.fastlem_debug_fetch.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t]
+    lib.fastlem_version.restype = ctypes.c_char_p
+    lib.fastlem_host_initial_elevations.argtypes = [u32, f64p, f64p]
+    lib.fastlem_host_initial_elevations.restype = None
+    _libs[path] = lib
+    return lib
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(ctypes.POINTER(t))
+
+
+class Context:
+    """One fastlem_ctx.  Keeps the numpy arrays it handed to the library alive (the C ABI borrows the graph)."""
+
+    def __init__(self, device=0, lib_path=None):
+        self._lib = load(lib_path)
+        self._h = ctypes.c_void_p()
+        rc = self._lib.fastlem_create(ctypes.byref(self._h), int(device))
+        if rc != OK:
+            self._h = None
+            raise FastlemError(rc, f"cannot create context on CUDA device {device} (no CPU fallback)")
+        self._keep = {}
+        self.n = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fastlem_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise FastlemError(rc, self._lib.fastlem_last_error(self._h).decode())
+
+    def version(self):
+        return self._lib.fastlem_version().decode()
+
+    def set_option(self, name, value):
+        self._ck(self._lib.fastlem_set_option(self._h, name.encode(), int(value)))
+
+    def set_graph(self, row_ptr, col, dist, areas):
+        rp, c, d, a = _u32(row_ptr), _u32(col), _f64(dist), _f64(areas)
+        n = rp.size - 1
+        if a.size != n or c.size != d.size:
+            raise ValueError("set_graph: inconsistent array sizes")
+        self._keep["graph"] = (rp, c, d, a)
+        self._ck(self._lib.fastlem_set_graph(self._h, n, _p(rp, ctypes.c_uint32), _p(c, ctypes.c_uint32),
+                                             _p(d, ctypes.c_double), _p(a, ctypes.c_double)))
+        self.n = n
+
+    def set_parameters(self, initial_elevation, erodibility, uplift_rate, tan_max_slope, outlets):
+        e0, k, u = _f64(initial_elevation), _f64(erodibility), _f64(uplift_rate)
+        t = None if tan_max_slope is None else _f64(tan_max_slope)
+        o = _u32(outlets)
+        for arr in (e0, k, u) + (() if t is None else (t,)):
+            if arr.size != self.n:
+                raise ValueError("set_parameters: parameter arrays must have one entry per site")
+        self._keep["params"] = (e0, k, u, t, o)
+        self._ck(self._lib.fastlem_set_parameters(self._h, _p(e0, ctypes.c_double), _p(k, ctypes.c_double),
+                                                  _p(u, ctypes.c_double), _p(t, ctypes.c_double),
+                                                  _p(o, ctypes.c_uint32), o.size))
+
+    def generate(self, max_iteration=None, out=None):
+        out = np.empty(self.n, dtype=np.float64) if out is None else out
+        it = ctypes.c_uint32(0)
+        mi = UNTIL_STABLE if max_iteration is None else int(max_iteration)
+        self._ck(self._lib.fastlem_generate(self._h, mi, _p(out, ctypes.c_double), ctypes.byref(it)))
+        return out, it.value
+
+    def run(self, max_iteration=None):
+        it = ctypes.c_uint32(0)
+        mi = UNTIL_STABLE if max_iteration is None else int(max_iteration)
+        self._ck(self._lib.fastlem_run(self._h, mi, ctypes.byref(it)))
+        return it.value
+
+    def download(self, out=None):
+        out = np.empty(self.n, dtype=np.float64) if out is None else out
+        self._ck(self._lib.fastlem_download(self._h, _p(out, ctypes.c_double)))
+        return out
+
+    def stats(self):
+        s = Stats()
+        self._ck(self._lib.fastlem_get_stats(self._h, ctypes.byref(s)))
+        return s.as_dict()
+
+    def fetch(self, stage):
+        code = STAGE[stage] if isinstance(stage, str) else int(stage)
+        out = np.empty(self.n, dtype=_STAGE_DTYPE[code])
+        self._ck(self._lib.fastlem_debug_fetch(self._h, code, out.ctypes.data_as(ctypes.c_void_p), out.nbytes))
+        return out
+
+
+def host_initial_elevations(base_elevation, lib_path=None):
+    """generator.rs:134-138 on the host: base + StdRng::seed_from_u64(0).gen::<f64>() * f64::EPSILON."""
+    base = _f64(base_elevation)
+    out = np.empty_like(base)
+    load(lib_path).fastlem_host_initial_elevations(base.size, _p(base, ctypes.c_double), _p(out, ctypes.c_double))
+    return out

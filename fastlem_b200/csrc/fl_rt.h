@@ -1,0 +1,150 @@
+// fl_rt.h -- thin runtime layer under the solver.
+//
+// Normal build (nvcc, sm_100a): CUDA runtime, real kernels, CUB.
+// FL_EMU build (g++ -DFL_EMU): the SAME kernel bodies and the SAME host orchestration run serially on
+// the host, one "thread" after another.  The emu build exists only so that the CPU-only test tier
+// (pytest -m "not gpu") can check the solver's logic against the oracle before GPU time is spent;
+// it is built into tests/_emu/, never shipped, and the product loader (fastlem_b200/_native.py)
+// never looks for it.  Kernels that need block-level cooperation are not available under FL_EMU.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#ifdef FL_EMU
+// ------------------------------------------------------------------------------------------------
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define FL_DEVICE_BUILD 0
+
+struct fl_dim3 {
+    unsigned x, y, z;
+    fl_dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+typedef fl_dim3 dim3;
+extern thread_local fl_dim3 threadIdx, blockIdx, blockDim, gridDim;
+
+typedef int cudaStream_t;
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
+
+struct fl_event { std::chrono::steady_clock::time_point t; };
+typedef fl_event* cudaEvent_t;
+
+template <class T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
+template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
+template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <class T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
+inline void __threadfence() {}
+inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
+inline int __ffsll(long long x) { return __builtin_ffsll(x); }
+
+template <class F> inline void fl_emu_launch(unsigned grid, unsigned block, F&& f) {
+    gridDim = fl_dim3(grid);
+    blockDim = fl_dim3(block);
+    for (unsigned b = 0; b < grid; ++b) {
+        blockIdx = fl_dim3(b);
+        for (unsigned t = 0; t < block; ++t) {
+            threadIdx = fl_dim3(t);
+            f();
+        }
+    }
+}
+#define FL_LAUNCH(kernel, grid, block, stream, ...) \
+    do { (void)(stream); fl_emu_launch((grid), (block), [&] { kernel(__VA_ARGS__); }); } while (0)
+
+inline cudaError_t fl_set_device(int) { return 0; }
+inline cudaError_t fl_stream_create(cudaStream_t* s) { *s = 0; return 0; }
+inline cudaError_t fl_stream_destroy(cudaStream_t) { return 0; }
+inline cudaError_t fl_stream_sync(cudaStream_t) { return 0; }
+inline cudaError_t fl_malloc(void** p, size_t bytes) { *p = std::malloc(bytes ? bytes : 1); return *p ? 0 : 2; }
+inline cudaError_t fl_free(void* p) { std::free(p); return 0; }
+inline cudaError_t fl_malloc_host(void** p, size_t bytes) { *p = std::malloc(bytes ? bytes : 1); return *p ? 0 : 2; }
+inline cudaError_t fl_free_host(void* p) { std::free(p); return 0; }
+inline cudaError_t fl_h2d(void* d, const void* h, size_t bytes, cudaStream_t) { std::memcpy(d, h, bytes); return 0; }
+inline cudaError_t fl_d2h(void* h, const void* d, size_t bytes, cudaStream_t) { std::memcpy(h, d, bytes); return 0; }
+inline cudaError_t fl_d2d(void* d, const void* s, size_t bytes, cudaStream_t) { std::memcpy(d, s, bytes); return 0; }
+inline cudaError_t fl_memset(void* d, int v, size_t bytes, cudaStream_t) { std::memset(d, v, bytes); return 0; }
+inline cudaError_t fl_event_create(cudaEvent_t* e) { *e = new fl_event; return 0; }
+inline cudaError_t fl_event_destroy(cudaEvent_t e) { delete e; return 0; }
+inline cudaError_t fl_event_record(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return 0; }
+inline cudaError_t fl_event_sync(cudaEvent_t) { return 0; }
+inline cudaError_t fl_event_elapsed(float* ms, cudaEvent_t a, cudaEvent_t b) {
+    *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+    return 0;
+}
+inline cudaError_t fl_last_error() { return 0; }
+inline int fl_sm_count() { return 4; }
+
+// stable LSD sort of (key,value) pairs on the low `end_bit` bits, like cub::DeviceRadixSort::SortPairs
+inline cudaError_t fl_sort_pairs(void*, size_t& temp_bytes, const uint32_t* kin, uint32_t* kout, const uint32_t* vin,
+                                 uint32_t* vout, uint32_t n, int end_bit, cudaStream_t, bool query) {
+    if (query) { temp_bytes = 1; return 0; }
+    std::vector<uint32_t> idx(n);
+    for (uint32_t i = 0; i < n; ++i) idx[i] = i;
+    uint32_t mask = end_bit >= 32 ? 0xFFFFFFFFu : ((1u << end_bit) - 1u);
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return (kin[a] & mask) < (kin[b] & mask); });
+    for (uint32_t i = 0; i < n; ++i) { kout[i] = kin[idx[i]]; vout[i] = vin[idx[i]]; }
+    return 0;
+}
+
+#else
+// ------------------------------------------------------------------------------------------------
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#define FL_DEVICE_BUILD 1
+
+#define FL_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+
+inline cudaError_t fl_set_device(int d) { return cudaSetDevice(d); }
+inline cudaError_t fl_stream_create(cudaStream_t* s) { return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); }
+inline cudaError_t fl_stream_destroy(cudaStream_t s) { return cudaStreamDestroy(s); }
+inline cudaError_t fl_stream_sync(cudaStream_t s) { return cudaStreamSynchronize(s); }
+inline cudaError_t fl_malloc(void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 1); }
+inline cudaError_t fl_free(void* p) { return cudaFree(p); }
+inline cudaError_t fl_malloc_host(void** p, size_t bytes) { return cudaMallocHost(p, bytes ? bytes : 1); }
+inline cudaError_t fl_free_host(void* p) { return cudaFreeHost(p); }
+inline cudaError_t fl_h2d(void* d, const void* h, size_t bytes, cudaStream_t s) {
+    return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s);
+}
+inline cudaError_t fl_d2h(void* h, const void* d, size_t bytes, cudaStream_t s) {
+    return cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s);
+}
+inline cudaError_t fl_d2d(void* d, const void* s_, size_t bytes, cudaStream_t s) {
+    return cudaMemcpyAsync(d, s_, bytes, cudaMemcpyDeviceToDevice, s);
+}
+inline cudaError_t fl_memset(void* d, int v, size_t bytes, cudaStream_t s) { return cudaMemsetAsync(d, v, bytes, s); }
+inline cudaError_t fl_event_create(cudaEvent_t* e) { return cudaEventCreate(e); }
+inline cudaError_t fl_event_destroy(cudaEvent_t e) { return cudaEventDestroy(e); }
+inline cudaError_t fl_event_record(cudaEvent_t e, cudaStream_t s) { return cudaEventRecord(e, s); }
+inline cudaError_t fl_event_sync(cudaEvent_t e) { return cudaEventSynchronize(e); }
+inline cudaError_t fl_event_elapsed(float* ms, cudaEvent_t a, cudaEvent_t b) { return cudaEventElapsedTime(ms, a, b); }
+inline cudaError_t fl_last_error() { return cudaGetLastError(); }
+inline int fl_sm_count() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+inline cudaError_t fl_sort_pairs(void* temp, size_t& temp_bytes, const uint32_t* kin, uint32_t* kout,
+                                 const uint32_t* vin, uint32_t* vout, uint32_t n, int end_bit, cudaStream_t s,
+                                 bool query) {
+    return cub::DeviceRadixSort::SortPairs(query ? nullptr : temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, end_bit,
+                                           s);
+}
+#endif

@@ -1,0 +1,135 @@
+/* fastlem_b200.h -- C ABI of the B200-native terrain solve.
+ *
+ * Drop-in boundary for ONE path of TadaTeruki/fastlem 0.1.4: the body of
+ * `TerrainGenerator::generate()` (reference src/lem/generator.rs:90-213, with
+ * src/lem/stream_tree.rs:72-243 and src/lem/drainage_basin.rs:13-46 underneath).
+ * The reference has no FFI of its own; these are the entry points a Rust shim inside
+ * `generate()` binds (see INTEGRATION.md for the `extern "C"` block and the packing code).
+ *
+ * Conventions
+ *   - every function returns FASTLEM_OK (0) or a negative FASTLEM_E_* code; nothing throws
+ *     across the boundary; `fastlem_last_error` gives the text of the last failure on a ctx.
+ *   - plain pointers and sizes only; all arrays are HOST memory owned by the caller.
+ *   - one ctx per generate() call (or reused across calls); a ctx owns its CUDA stream and
+ *     device buffers and has no global mutable state, so independent ctxs may be used from
+ *     different threads concurrently (TerrainGenerator is Clone and has no interior
+ *     mutability, generator.rs:36).  A single ctx must not be used from two threads at once.
+ *   - node indices and CSR offsets are uint32 (the reference uses usize): n < 2^32-1, D < 2^32.
+ *   - there is NO CPU fallback: without a CUDA device `fastlem_create` fails with
+ *     FASTLEM_E_CUDA.
+ */
+#ifndef FASTLEM_B200_H
+#define FASTLEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fastlem_ctx fastlem_ctx;
+
+enum {
+    FASTLEM_OK = 0,
+    FASTLEM_E_INVALID = -1,  /* bad argument (null pointer, index out of range, ...) */
+    FASTLEM_E_STATE = -2,    /* call order: graph / parameters not set (generator.rs:91-116 analogues) */
+    FASTLEM_E_CUDA = -3,     /* CUDA runtime failure, or no device */
+    FASTLEM_E_NOMEM = -4
+};
+
+/* Sentinel for "max_iteration not set" (generator.rs:140: max_iteration.unwrap_or(u32::MAX)). */
+#define FASTLEM_UNTIL_STABLE 0xFFFFFFFFu
+
+/* Creates a context on CUDA device `device_ordinal`. */
+int fastlem_create(fastlem_ctx** out, int device_ordinal);
+void fastlem_destroy(fastlem_ctx* ctx);
+const char* fastlem_last_error(const fastlem_ctx* ctx);
+
+/* The model, as `generate()` reads it through trait Model (src/core/traits.rs:13-20):
+ *   n        = model.num()                                   (generator.rs:99-105)
+ *   row_ptr  = n+1 offsets; row i = graph.neighbors_of(i) IN ITERATION ORDER -- the order is
+ *              semantically significant (receiver tie-break stream_tree.rs:122-133, BFS order
+ *              drainage_basin.rs:23, lake connection stream_tree.rs:204-236)
+ *   col/dist = neighbour index and edge attribute (length) per slot
+ *   areas    = model.areas()
+ * The graph must be simple and symmetric with equal lengths in both directions (what
+ * terrain-graph's add_edge produces).  The arrays are copied to HBM before this returns, but the
+ * pointers must stay valid until the ctx is destroyed or the graph is replaced: the flood order of
+ * lake removal (a function of graph + outlets only) is computed from them on first use.
+ */
+int fastlem_set_graph(fastlem_ctx* ctx, uint32_t n, const uint32_t* row_ptr, const uint32_t* col,
+                      const double* dist, const double* areas);
+
+/* Per-site parameters, flattened from Vec<TopographicalParameters> (src/core/parameters.rs:24-30):
+ *   initial_elevation = base_elevation[i] + rng.gen::<f64>() * f64::EPSILON  (generator.rs:134-138;
+ *                       the shim keeps calling `rand`, so the noise stream stays the crate's own)
+ *   erodibility, uplift_rate
+ *   tan_max_slope     = tan(max_slope) per site, NaN where max_slope is None; NULL if None everywhere
+ *                       (generator.rs:194 evaluates max_slope.tan(); done once on the host)
+ *   outlets           = generator.rs:120-132: indices with is_outlet in ascending order, or
+ *                       model.default_outlets() if there is none, in that order.
+ */
+int fastlem_set_parameters(fastlem_ctx* ctx, const double* initial_elevation, const double* erodibility,
+                           const double* uplift_rate, const double* tan_max_slope, const uint32_t* outlets,
+                           uint32_t n_outlets);
+
+/* The loop of generator.rs:140-210: runs until no elevation changes or `max_iteration` bodies have
+ * run (FASTLEM_UNTIL_STABLE = not set).  Entirely on the device.  Writes the final elevations (n
+ * doubles, host) and the number of loop bodies executed.  May be called again: every call restarts
+ * from the uploaded initial elevations.
+ */
+int fastlem_generate(fastlem_ctx* ctx, uint32_t max_iteration, double* elevations_out, uint32_t* iterations_done);
+
+/* fastlem_generate split in two, so a caller can keep results on the device (bench, ensembles):
+ * `fastlem_run` leaves the elevations in HBM, `fastlem_download` copies them out. */
+int fastlem_run(fastlem_ctx* ctx, uint32_t max_iteration, uint32_t* iterations_done);
+int fastlem_download(fastlem_ctx* ctx, double* elevations_out);
+
+/* Options (all default 0): "profile" = 1 records CUDA events around every stage and fills the ms_*
+ * fields of fastlem_stats; "keep_stages" = 1 keeps the pre-lake-removal receivers/labels of the last
+ * iteration for fastlem_debug_fetch; "sweep" selects the tree-sweep implementation. */
+int fastlem_set_option(fastlem_ctx* ctx, const char* name, int64_t value);
+
+typedef struct fastlem_stats {
+    uint32_t iterations;       /* loop bodies executed by the last run */
+    uint32_t lake_iterations;  /* of which ran lake removal (stream_tree.rs:91-96) */
+    uint32_t depth_first;      /* stream-tree depth (levels) in the first / last iteration */
+    uint32_t depth_last;
+    uint64_t kernel_launches;  /* kernels of this library launched by the last run */
+    double ms_run;             /* device time of the last fastlem_run, CUDA events */
+    double ms_upload;          /* host->device copies of set_graph + set_parameters (wall clock) */
+    double ms_flood_rank;      /* one-off flood-order computation (wall clock; 0 if never needed) */
+    double ms_download;
+    /* "profile"=1 only: summed over the iterations of the last run */
+    double ms_receivers, ms_labels, ms_lakes, ms_order, ms_area, ms_elevation;
+    uint64_t n_receivers, n_labels, n_lakes, n_order, n_area, n_elevation; /* launches per stage */
+} fastlem_stats;
+int fastlem_get_stats(const fastlem_ctx* ctx, fastlem_stats* out);
+
+/* Stage dumps of the LAST iteration executed, for parity tests.  `bytes` must equal the size of the
+ * stage array (n * 4 for uint32 stages, n * 8 for double stages). */
+enum {
+    FASTLEM_STAGE_RECEIVERS = 0,         /* u32: stream_tree.next after lake removal */
+    FASTLEM_STAGE_RECEIVERS_INITIAL = 1, /* u32: next before lake removal ("keep_stages") */
+    FASTLEM_STAGE_LABELS_INITIAL = 2,    /* u32: subroot of find_roots_with_lakes ("keep_stages") */
+    FASTLEM_STAGE_LABELS = 3,            /* u32: root of the final forest */
+    FASTLEM_STAGE_DEPTH = 4,             /* u32: depth in the final forest, 0xFFFFFFFF if unreached */
+    FASTLEM_STAGE_DRAINAGE_AREA = 5,     /* f64 */
+    FASTLEM_STAGE_RESPONSE_TIME = 6,     /* f64 */
+    FASTLEM_STAGE_ELEVATION = 7,         /* f64 */
+    FASTLEM_STAGE_FLOOD_RANK = 8         /* u32: pop order of the lake flood (0xFFFFFFFF = never popped / not computed) */
+};
+int fastlem_debug_fetch(fastlem_ctx* ctx, int stage, void* out, size_t bytes);
+
+/* Host utility for the C++/Python mirrors of TerrainGenerator (NOT needed by the Rust shim, which keeps
+ * using the `rand` crate): generator.rs:134-138, out[i] = base[i] + StdRng::seed_from_u64(0).gen::<f64>() * EPSILON. */
+void fastlem_host_initial_elevations(uint32_t n, const double* base_elevation, double* out);
+
+/* Library identification: "fastlem_b200 <version> sm_100a" (or "... emu" for the test-only host build). */
+const char* fastlem_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTLEM_B200_H */
