@@ -1,0 +1,231 @@
+"""fastlem_b200 -- B200-native `TerrainGenerator::generate()` for TadaTeruki/fastlem.
+
+Python host-side mirror of the reference's public interface for the one path this package replaces
+(the C++ mirror with the same names is fastlem_b200/host/fastlem.hpp; the Rust shim is in INTEGRATION.md):
+
+    reference (Rust)                                     here
+    ---------------------------------------------------  ------------------------------------------
+    core::parameters::TopographicalParameters            TopographicalParameters   (parameters.rs:24-69)
+    models::surface::sites::Site2D                       Site2D                    (sites.rs)
+    models::surface::model::TerrainModel2D (trait Model) TerrainModel2D            (model.rs:41-69, traits.rs:13-20)
+    models::surface::terrain::Terrain2D                  Terrain2D                 (terrain.rs:8-39)
+    lem::generator::TerrainGenerator                     TerrainGenerator          (generator.rs:36-213)
+    lem::generator::GenerationError                      GenerationError + variants (generator.rs:18-26)
+
+`generate()` packs the model into the C ABI's boundary format and runs the whole loop on the GPU through
+include/fastlem_b200.h.  There is no CPU implementation in this package.
+"""
+import math
+
+import numpy as np
+
+from . import _native
+
+__all__ = ["Site2D", "TopographicalParameters", "ParameterArrays", "TerrainModel2D", "Terrain2D",
+           "TerrainGenerator", "GenerationError", "InvalidNumberOfParameters", "ParametersNotSet", "ModelNotSet"]
+
+
+class GenerationError(Exception):
+    """generator.rs:18-26"""
+
+
+class InvalidNumberOfParameters(GenerationError):
+    def __init__(self):
+        super().__init__("The number of topographical parameters must be equal to the number of sites")
+
+
+class ParametersNotSet(GenerationError):
+    def __init__(self):
+        super().__init__("You must set topographical parameters before generating terrain")
+
+
+class ModelNotSet(GenerationError):
+    def __init__(self):
+        super().__init__("You must set `TerrainModel` before generating terrain")
+
+
+class Site2D:
+    __slots__ = ("x", "y")
+
+    def __init__(self, x=0.0, y=0.0):
+        self.x, self.y = float(x), float(y)
+
+    def distance(self, other):
+        return math.sqrt(self.squared_distance(other))
+
+    def squared_distance(self, other):
+        return (self.x - other.x) ** 2 + (self.y - other.y) ** 2
+
+
+class TopographicalParameters:
+    """parameters.rs:24-69: defaults 0 / 1 / 1 / False / None, chained setters."""
+    __slots__ = ("base_elevation", "erodibility", "uplift_rate", "is_outlet", "max_slope")
+
+    def __init__(self):
+        self.base_elevation = 0.0
+        self.erodibility = 1.0
+        self.uplift_rate = 1.0
+        self.is_outlet = False
+        self.max_slope = None
+
+    @classmethod
+    def default(cls):
+        return cls()
+
+    def set_base_elevation(self, v):
+        self.base_elevation = float(v)
+        return self
+
+    def set_erodibility(self, v):
+        self.erodibility = float(v)
+        return self
+
+    def set_uplift_rate(self, v):
+        self.uplift_rate = float(v)
+        return self
+
+    def set_is_outlet(self, v):
+        self.is_outlet = bool(v)
+        return self
+
+    def set_max_slope(self, v):
+        self.max_slope = None if v is None else float(v)
+        return self
+
+
+class ParameterArrays:
+    """Structure-of-arrays form of Vec<TopographicalParameters> for large models (what the C ABI takes).
+    max_slope: radians, NaN = None (or None for "None everywhere")."""
+
+    def __init__(self, base_elevation, erodibility, uplift_rate, is_outlet=None, max_slope=None):
+        self.base_elevation = np.ascontiguousarray(base_elevation, dtype=np.float64)
+        self.erodibility = np.ascontiguousarray(erodibility, dtype=np.float64)
+        self.uplift_rate = np.ascontiguousarray(uplift_rate, dtype=np.float64)
+        n = self.base_elevation.size
+        self.is_outlet = np.zeros(n, dtype=bool) if is_outlet is None else np.ascontiguousarray(is_outlet, dtype=bool)
+        self.max_slope = None if max_slope is None else np.ascontiguousarray(max_slope, dtype=np.float64)
+
+    def __len__(self):
+        return self.base_elevation.size
+
+    @classmethod
+    def from_list(cls, params):
+        n = len(params)
+        ms = None
+        if any(p.max_slope is not None for p in params):
+            ms = np.array([np.nan if p.max_slope is None else p.max_slope for p in params], dtype=np.float64)
+        return cls(np.fromiter((p.base_elevation for p in params), np.float64, n),
+                   np.fromiter((p.erodibility for p in params), np.float64, n),
+                   np.fromiter((p.uplift_rate for p in params), np.float64, n),
+                   np.fromiter((p.is_outlet for p in params), bool, n), ms)
+
+
+class TerrainModel2D:
+    """model.rs:18-69.  The graph is held as the CSR the C ABI takes: row i = graph.neighbors_of(i) in order."""
+
+    def __init__(self, sites, areas, row_ptr, col, dist, default_outlets):
+        self._sites = np.ascontiguousarray(sites, dtype=np.float64).reshape(-1, 2)
+        self._areas = np.ascontiguousarray(areas, dtype=np.float64)
+        self._row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint32)
+        self._col = np.ascontiguousarray(col, dtype=np.uint32)
+        self._dist = np.ascontiguousarray(dist, dtype=np.float64)
+        self._default_outlets = np.ascontiguousarray(default_outlets, dtype=np.uint32)
+
+    @classmethod
+    def from_workload(cls, m):
+        return cls(m["sites"], m["areas"], m["row_ptr"], m["col"], m["dist"], m["default_outlets"])
+
+    def num(self):  # model.rs:42-44: graph.order()
+        return self._row_ptr.size - 1
+
+    def sites(self):
+        return self._sites
+
+    def areas(self):
+        return self._areas
+
+    def default_outlets(self):
+        return self._default_outlets
+
+    def graph(self):
+        return self._row_ptr, self._col, self._dist
+
+    def create_terrain_from_result(self, elevations):  # model.rs:62-68
+        return Terrain2D(self._sites.copy(), np.array(elevations, dtype=np.float64, copy=True))
+
+
+class Terrain2D:
+    """terrain.rs:8-39."""
+
+    def __init__(self, sites, elevations):
+        self._sites, self._elevations = sites, elevations
+
+    def sites(self):
+        return self._sites
+
+    def elevations(self):
+        return self._elevations
+
+    def get_elevation(self, site):
+        raise NotImplementedError("natural-neighbour interpolation (terrain.rs:36-38) is outside the generate() path; "
+                                  "see DESIGN.md, scope row f1")
+
+
+class TerrainGenerator:
+    """generator.rs:36-213: builder + generate()."""
+
+    def __init__(self):
+        self._model = None
+        self._parameters = None
+        self._max_iteration = None
+        self.device = 0
+        self._lib_path = None  # tests only
+        self.last_stats = None
+        self.last_iterations = None
+
+    @classmethod
+    def default(cls):
+        return cls()
+
+    def set_model(self, model):
+        self._model = model
+        return self
+
+    def set_parameters(self, parameters):
+        self._parameters = parameters
+        return self
+
+    def set_max_iteration(self, max_iteration):
+        self._max_iteration = int(max_iteration)
+        return self
+
+    def set_device(self, ordinal):
+        self.device = int(ordinal)
+        return self
+
+    def generate(self):
+        model = self._model
+        if model is None:  # generator.rs:91-97
+            raise ModelNotSet()
+        num = model.num()
+        if self._parameters is None:  # generator.rs:107-116
+            raise ParametersNotSet()
+        if len(self._parameters) != num:
+            raise InvalidNumberOfParameters()
+        p = self._parameters if isinstance(self._parameters, ParameterArrays) else \
+            ParameterArrays.from_list(self._parameters)
+        # generator.rs:120-132
+        outlets = np.nonzero(p.is_outlet)[0].astype(np.uint32)
+        if outlets.size == 0:
+            outlets = model.default_outlets()
+        # generator.rs:134-138
+        initial = _native.host_initial_elevations(p.base_elevation, self._lib_path)
+        tan = None if p.max_slope is None else np.tan(p.max_slope)  # generator.rs:194, NaN stays NaN
+        row_ptr, col, dist = model.graph()
+        with _native.Context(self.device, self._lib_path) as ctx:
+            ctx.set_graph(row_ptr, col, dist, model.areas())
+            ctx.set_parameters(initial, p.erodibility, p.uplift_rate, tan, outlets)
+            elevations, it = ctx.generate(self._max_iteration)
+            self.last_stats = ctx.stats()
+            self.last_iterations = it
+        return model.create_terrain_from_result(elevations)  # generator.rs:212

@@ -22,7 +22,7 @@ _STAGE_DTYPE = {0: np.uint32, 1: np.uint32, 2: np.uint32, 3: np.uint32, 4: np.ui
 
 # every symbol include/fastlem_b200.h declares
 SYMBOLS = ["fastlem_create", "fastlem_destroy", "fastlem_last_error", "fastlem_set_graph",
-           "fastlem_set_parameters", "fastlem_generate", "fastlem_run", "fastlem_download",
+           "fastlem_set_parameters", "fastlem_generate", "fastlem_run", "fastlem_download", "fastlem_download_to_device",
            "fastlem_set_option", "fastlem_get_stats", "fastlem_debug_fetch", "fastlem_version",
            "fastlem_host_initial_elevations"]
 
@@ -71,6 +71,7 @@ def load(path=None):
     lib.fastlem_generate.argtypes = [vp, u32, f64p, u32p]
     lib.fastlem_run.argtypes = [vp, u32, u32p]
     lib.fastlem_download.argtypes = [vp, f64p]
+    lib.fastlem_download_to_device.argtypes = [vp, vp]
     lib.fastlem_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int64]
     lib.fastlem_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.fastlem_debug_fetch.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t]
@@ -168,6 +169,10 @@ class Context:
         out = np.empty(self.n, dtype=np.float64) if out is None else out
         self._ck(self._lib.fastlem_download(self._h, _p(out, ctypes.c_double)))
         return out
+
+    def download_to_device(self, device_ptr):
+        """Copy the elevations into a device buffer (e.g. torch_tensor.data_ptr()) of n float64 on this device."""
+        self._ck(self._lib.fastlem_download_to_device(self._h, ctypes.c_void_p(int(device_ptr))))
 
     def stats(self):
         s = Stats()

@@ -484,6 +484,15 @@ int fastlem_download(fastlem_ctx* c, double* elevations_out) {
     return FASTLEM_OK;
 }
 
+int fastlem_download_to_device(fastlem_ctx* c, double* device_out) {
+    if (!c || !device_out) return FASTLEM_E_INVALID;
+    if (!c->has_graph || !c->has_params) return fail(c, FASTLEM_E_STATE, "download: nothing to download");
+    FL_CK(fl_set_device(c->device));
+    FL_CK(fl_d2d(device_out, c->d_elev, sizeof(double) * c->n, c->stream));
+    FL_CK(fl_stream_sync(c->stream));
+    return FASTLEM_OK;
+}
+
 int fastlem_generate(fastlem_ctx* c, uint32_t max_iteration, double* elevations_out, uint32_t* iterations_done) {
     if (!c || !elevations_out) return FASTLEM_E_INVALID;
     int rc = fastlem_run(c, max_iteration, iterations_done);

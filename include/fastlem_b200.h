@@ -85,6 +85,9 @@ int fastlem_generate(fastlem_ctx* ctx, uint32_t max_iteration, double* elevation
  * `fastlem_run` leaves the elevations in HBM, `fastlem_download` copies them out. */
 int fastlem_run(fastlem_ctx* ctx, uint32_t max_iteration, uint32_t* iterations_done);
 int fastlem_download(fastlem_ctx* ctx, double* elevations_out);
+/* Same as fastlem_download, but into a caller-owned DEVICE buffer of n doubles on the ctx's device
+ * (used to hand an ensemble member's result to an NCCL gather without a host round trip). */
+int fastlem_download_to_device(fastlem_ctx* ctx, double* device_elevations_out);
 
 /* Options (all default 0): "profile" = 1 records CUDA events around every stage and fills the ms_*
  * fields of fastlem_stats; "keep_stages" = 1 keeps the pre-lake-removal receivers/labels of the last

@@ -1,0 +1,70 @@
+"""CPU tier: the solver's host orchestration and kernel bodies, compiled serially for the host (-DFL_EMU),
+against the oracle.  This checks LOGIC before GPU time is spent; the GPU tier (test_gpu_parity.py) is the
+parity gate proper."""
+import numpy as np
+import pytest
+
+import helpers
+from scenarios import SMALL, scenario
+
+
+def _ctx(emu_lib, **opts):
+    from fastlem_b200 import _native
+    ctx = _native.Context(0, emu_lib)
+    assert ctx.version().endswith("emu")
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    return ctx
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_first_iteration_stages(oracle, emu_lib, name):
+    m, p, outlets, initial, _ = scenario(name)
+    with _ctx(emu_lib) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        _, exact = helpers.check_first_iteration(ctx, oracle, m, p, outlets, initial)
+        assert exact
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_generate(oracle, emu_lib, name):
+    m, p, outlets, initial, max_iteration = scenario(name)
+    with _ctx(emu_lib) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
+
+
+@pytest.mark.parametrize("path", helpers.golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_golden(emu_lib, path):
+    with _ctx(emu_lib) as ctx:
+        helpers.check_against_golden(ctx, path)
+
+
+@pytest.mark.parametrize("k", [0, 1, 3])
+def test_max_iteration(oracle, emu_lib, k):
+    m, p, outlets, initial, _ = scenario("uniform")
+    with _ctx(emu_lib) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        e, it = ctx.generate(k)
+        ref, ref_it = oracle.generate(m, p["erodibility"], p["uplift"], None, outlets, initial, k)
+        assert it == ref_it == k
+        assert np.array_equal(e, ref)
+        if k == 0:
+            assert np.array_equal(e, initial)  # generator.rs:140: zero bodies -> the noise comes back
+
+
+def test_flood_rank_matches_oracle(oracle, emu_lib):
+    for name in ("uniform", "lattice", "lattice_regular", "advanced", "disconnected"):
+        m, p, outlets, initial, _ = scenario(name)
+        with _ctx(emu_lib) as ctx:
+            helpers.load_ctx(ctx, m, p, outlets, initial)
+            assert np.array_equal(ctx.fetch("flood_rank"), oracle.flood_order(m, outlets)), name
+
+
+def test_rerun_restarts_from_initial(emu_lib):
+    m, p, outlets, initial, _ = scenario("uniform", 800)
+    with _ctx(emu_lib) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        a, ita = ctx.generate()
+        b, itb = ctx.generate()
+        assert ita == itb and np.array_equal(a, b)

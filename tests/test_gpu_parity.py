@@ -1,0 +1,137 @@
+"""GPU tier (-m gpu): the parity gate.  Everything goes through the C ABI of the nvcc-built product library
+(fastlem_b200/_lib/libfastlem_b200.so) and is compared with the CPU oracle on identical inputs.
+
+Bars (north_star): receivers, basin labels, lake connection and traversal membership bit-exact; drainage
+areas, response times and elevations within 1e-9 relative (helpers.REL_TOL) -- in practice the CUDA path
+reproduces them bit for bit, which the tests also record.
+"""
+import numpy as np
+import pytest
+
+import helpers
+from scenarios import SMALL, scenario
+
+pytestmark = pytest.mark.gpu
+
+
+def test_library_is_the_cuda_build(gpu_ctx_factory):
+    with gpu_ctx_factory() as ctx:
+        assert ctx.version().endswith("sm_100a")
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_first_iteration_stages(oracle, gpu_ctx_factory, name):
+    m, p, outlets, initial, _ = scenario(name)
+    with gpu_ctx_factory() as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        _, exact = helpers.check_first_iteration(ctx, oracle, m, p, outlets, initial)
+        assert exact, "f64 stages are within tolerance but not bit-identical"
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_generate_to_convergence(oracle, gpu_ctx_factory, name):
+    m, p, outlets, initial, max_iteration = scenario(name)
+    with gpu_ctx_factory() as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
+
+
+@pytest.mark.parametrize("path", helpers.golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_golden_vectors(gpu_ctx_factory, path):
+    with gpu_ctx_factory() as ctx:
+        helpers.check_against_golden(ctx, path)
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 5])
+def test_max_iteration(oracle, gpu_ctx_factory, k):
+    m, p, outlets, initial, _ = scenario("uniform")
+    with gpu_ctx_factory() as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        e, it = ctx.generate(k)
+        ref, ref_it = oracle.generate(m, p["erodibility"], p["uplift"], None, outlets, initial, k)
+        assert it == ref_it == k
+        assert np.array_equal(e, ref)
+
+
+def test_c1_landscape_evolution_as_shipped(oracle, gpu_ctx_factory):
+    """BASELINE config C1: examples/landscape_evolution.rs (30 000 sites, relaxate_sites(1), k = 1, hull outlets)."""
+    m, p, outlets, initial, _ = scenario("rust_sites", 30000)
+    with gpu_ctx_factory() as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        helpers.check_first_iteration(ctx, oracle, m, p, outlets, initial)
+        assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, None)
+
+
+def test_c3_style_advanced_200k(oracle, gpu_ctx_factory):
+    """terrain_generation_advanced-style (noise erodibility + ocean-mask outlets) at 200k sites, to convergence."""
+    m, p, outlets, initial, _ = scenario("advanced", 200000)
+    with gpu_ctx_factory() as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, None)
+
+
+def test_c7_nonuniform_uplift_lakes_every_iteration(oracle, gpu_ctx_factory):
+    m, p, outlets, initial, _ = scenario("uplift", 100000)
+    with gpu_ctx_factory() as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, 50)
+        assert ctx.stats()["lake_iterations"] > 1
+
+
+def test_c2_one_million_sites(oracle, gpu_ctx_factory):
+    """BASELINE config C2 (1M random sites, uniform erodibility, hull outlets): the oracle is too slow to
+    converge here (~10 min), so compare the first iterations against it, then check size-independent
+    properties of the converged GPU result."""
+    m, p, outlets, initial, _ = scenario("uniform", 1000000)
+    n = m["n"]
+    with gpu_ctx_factory() as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        ref, _ = helpers.check_first_iteration(ctx, oracle, m, p, outlets, initial)
+        assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, 3)
+        e, it = ctx.generate()
+        recv = ctx.fetch("receivers").astype(np.int64)
+        A = ctx.fetch("drainage_area")
+        depth = ctx.fetch("depth")
+        labels = ctx.fetch("labels").astype(np.int64)
+        e2, it2 = ctx.generate()
+    assert it == it2 and np.array_equal(e, e2), "deterministic"
+    is_outlet = np.zeros(n, dtype=bool)
+    is_outlet[outlets] = True
+    # converged forest: every site drains to an outlet, elevation strictly increases upstream (uniform uplift)
+    assert (depth != 0xFFFFFFFF).all()
+    assert is_outlet[labels].all()
+    non_out = ~is_outlet
+    assert (recv[non_out] != np.arange(n)[non_out]).all()
+    assert (e[non_out] > e[recv[non_out]]).all()
+    assert np.array_equal(e[is_outlet], initial[is_outlet]), "outlets keep base + noise (generator.rs:177-179)"
+    # conservation: the outlets' drainage areas add up to the total cell area
+    assert abs(A[is_outlet].sum() - m["areas"].sum()) <= 1e-9 * m["areas"].sum()
+    # fixed point: one more body from the converged field changes nothing (checked with the oracle)
+    nxt = oracle.iterate_once(m, p["erodibility"], p["uplift"], None, outlets, e)
+    assert not nxt["changed"]
+    assert np.array_equal(nxt["next"], recv)
+
+
+def test_host_mirror_on_gpu(oracle, product_lib):
+    import fastlem_b200 as fl
+    m, p, outlets, initial, _ = scenario("max_slope")
+    params = [fl.TopographicalParameters.default().set_max_slope(3.14 * 0.1) for _ in range(m["n"])]
+    gen = fl.TerrainGenerator.default().set_model(fl.TerrainModel2D.from_workload(m)).set_parameters(params)
+    terrain = gen.generate()
+    ref, ref_it = oracle.generate(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, initial)
+    assert gen.last_iterations == ref_it
+    assert np.array_equal(terrain.elevations(), ref)
+
+
+def test_two_contexts_are_independent(oracle, gpu_ctx_factory):
+    a = scenario("uniform")
+    b = scenario("advanced")
+    with gpu_ctx_factory() as ca, gpu_ctx_factory() as cb:
+        helpers.load_ctx(ca, a[0], a[1], a[2], a[3])
+        helpers.load_ctx(cb, b[0], b[1], b[2], b[3])
+        ea, _ = ca.generate()
+        eb, _ = cb.generate()
+        ea2, _ = ca.generate()
+    assert np.array_equal(ea, ea2)
+    assert np.array_equal(ea, oracle.generate(a[0], a[1]["erodibility"], a[1]["uplift"], None, a[2], a[3])[0])
+    assert np.array_equal(eb, oracle.generate(b[0], b[1]["erodibility"], b[1]["uplift"], None, b[2], b[3])[0])
