@@ -35,7 +35,9 @@ class Stats(ctypes.Structure):
                 ("ms_receivers", ctypes.c_double), ("ms_labels", ctypes.c_double), ("ms_lakes", ctypes.c_double),
                 ("ms_order", ctypes.c_double), ("ms_area", ctypes.c_double), ("ms_elevation", ctypes.c_double),
                 ("n_receivers", ctypes.c_uint64), ("n_labels", ctypes.c_uint64), ("n_lakes", ctypes.c_uint64),
-                ("n_order", ctypes.c_uint64), ("n_area", ctypes.c_uint64), ("n_elevation", ctypes.c_uint64)]
+                ("n_order", ctypes.c_uint64), ("n_area", ctypes.c_uint64), ("n_elevation", ctypes.c_uint64),
+                ("rebuilds", ctypes.c_uint32), ("path_levels", ctypes.c_uint32), ("paths", ctypes.c_uint32),
+                ("reserved", ctypes.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

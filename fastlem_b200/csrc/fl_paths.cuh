@@ -1,0 +1,435 @@
+// fl_paths.cuh -- path-decomposed tree sweeps ("sweep" >= 1).
+//
+// Why: both tree sweeps of an iteration are chains of NON-associative double additions whose order the
+// reference fixes (generator.rs:154-174): A[j] = ((a_j + A[c_k]) + ...) + A[c_1] bottom-up and
+// rt_i = rt_recv + t_i top-down.  Bit-exact results therefore need depth-many dependent additions
+// (~800 .. 5000 levels at 1M sites).  Level-synchronous launches pay a kernel launch per level; here the
+// forest is cut into PATHS (a node continues into one chosen "heavy" child), every path is laid out
+// contiguously in memory, and one thread walks a whole path with the running value in a register.  Paths
+// nest only O(log N) deep when the heavy child is the one with the largest drainage area, so a sweep is
+// ~20 rounds instead of ~1000 levels.  The additions themselves are performed in exactly the reference order.
+//
+// The layout is a renumbering of the sites: internal id = position.  Position q+1 is the heavy child of q
+// inside a path.  Adjacency ORDER per row is preserved by the renumbering, so every tie-break of the
+// reference (first slot wins, children in reverse slot order) is unaffected.
+#pragma once
+#include "fl_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// static per-graph table: rev[s] = slot of i inside adj(col[s]) (first match), 255 if >= 255 / absent
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rev_slots(uint32_t n, const uint32_t* __restrict__ row_ptr,
+                                                    const uint32_t* __restrict__ col, uint8_t* __restrict__ rev) {
+    uint32_t i = FL_TID;
+    if (i >= n) return;
+    const uint32_t s1 = row_ptr[i + 1];
+    for (uint32_t s = row_ptr[i]; s < s1; ++s) {
+        const uint32_t j = col[s];
+        const uint32_t t0 = row_ptr[j], t1 = row_ptr[j + 1];
+        uint32_t r = 255;
+        for (uint32_t t = t0; t < t1; ++t)
+            if (col[t] == i) { r = (t - t0) < 255u ? (t - t0) : 255u; break; }
+        rev[s] = (uint8_t)r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 (stream_tree.rs:109-137) + child registration: the chosen receiver gets bit `slot of i in its row`
+// set in its child mask, so parents can later enumerate children in adjacency order without rescanning
+// their neighbours.  Rows longer than 32 ignore the mask and rescan (fl_children_rev).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_receivers_mask(uint32_t n, const uint32_t* __restrict__ row_ptr,
+                                                         const uint32_t* __restrict__ col,
+                                                         const double* __restrict__ dist,
+                                                         const uint8_t* __restrict__ rev,
+                                                         const double* __restrict__ elev,
+                                                         const uint8_t* __restrict__ is_outlet,
+                                                         uint32_t* __restrict__ recv, double* __restrict__ drecv,
+                                                         uint32_t* cmask, uint32_t* __restrict__ flags) {
+    uint32_t i = FL_TID;
+    if (i >= n) return;
+    uint32_t best = i, best_s = FL_NONE;
+    double best_d = 1.0;
+    if (!is_outlet[i]) {
+        const double ei = elev[i];
+        double steepest = 0.0;
+        const uint32_t s1 = row_ptr[i + 1];
+        for (uint32_t s = row_ptr[i]; s < s1; ++s) {
+            const uint32_t j = col[s];
+            const double ej = elev[j];
+            if (ei > ej) {
+                const double d = dist[s];
+                const double slope = (ei - ej) / d;
+                if (slope > steepest) {
+                    steepest = slope;
+                    best = j;
+                    best_d = d;
+                    best_s = s;
+                }
+            }
+        }
+        if (best == i) atomicOr(&flags[FL_FLAG_LAKE], 1u);
+    }
+    recv[i] = best;
+    drecv[i] = best_d;
+    if (best_s != FL_NONE) {
+        const uint32_t r = rev[best_s];
+        if (r < 32u) atomicOr(&cmask[best], 1u << r);
+    }
+}
+
+// child masks from scratch (after lake removal rewrote receivers)
+__global__ void __launch_bounds__(256) k_childmask(uint32_t n, const uint32_t* __restrict__ row_ptr,
+                                                    const uint32_t* __restrict__ col, const uint8_t* __restrict__ rev,
+                                                    const uint32_t* __restrict__ recv, uint32_t* cmask) {
+    uint32_t i = FL_TID;
+    if (i >= n) return;
+    const uint32_t p = recv[i];
+    if (p == i) return;
+    const uint32_t s1 = row_ptr[i + 1];
+    for (uint32_t s = row_ptr[i]; s < s1; ++s)
+        if (col[s] == p) {
+            const uint32_t r = rev[s];
+            if (r < 32u) atomicOr(&cmask[p], 1u << r);
+            return;
+        }
+}
+
+// children of q in REVERSE adjacency order (the order generator.rs:154-159 adds them in)
+template <class F>
+__device__ __forceinline__ void fl_children_rev(uint32_t q, const uint32_t* __restrict__ row_ptr,
+                                                const uint32_t* __restrict__ col, const uint32_t* __restrict__ recv,
+                                                const uint32_t* __restrict__ cmask, F&& f) {
+    const uint32_t s0 = row_ptr[q];
+    const uint32_t deg = row_ptr[q + 1] - s0;
+    if (deg <= 32u) {
+        uint32_t m = cmask[q];
+        while (m) {
+            const uint32_t b = 31u - (uint32_t)__clz((int)m);
+            m ^= 1u << b;
+            f(col[s0 + b]);
+        }
+    } else {
+        for (uint32_t s = deg; s-- > 0;) {
+            const uint32_t c = col[s0 + s];
+            if (c != q && recv[c] == q) f(c);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout rebuild, step 1: heavy child = child with the largest weight (previous drainage area); the
+// first such child in reverse adjacency order wins.  Any choice is CORRECT; it only shapes the paths.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_heavy(uint32_t n, const uint32_t* __restrict__ row_ptr,
+                                                const uint32_t* __restrict__ col, const uint32_t* __restrict__ recv,
+                                                const uint32_t* __restrict__ cmask, const double* __restrict__ weight,
+                                                uint32_t* __restrict__ heavy) {
+    uint32_t q = FL_TID;
+    if (q >= n) return;
+    uint32_t best = FL_NONE;
+    double bw = 0.0;
+    fl_children_rev(q, row_ptr, col, recv, cmask, [&](uint32_t c) {
+        const double w = weight[c];
+        if (best == FL_NONE || w > bw) { best = c; bw = w; }
+    });
+    heavy[q] = best;
+}
+
+// step 2: chain pointers for list ranking along paths: up = parent if I am its heavy child, else myself
+__global__ void __launch_bounds__(256) k_chain_init(uint32_t n, const uint32_t* __restrict__ recv,
+                                                     const uint32_t* __restrict__ heavy,
+                                                     unsigned long long* __restrict__ pd) {
+    uint32_t c = FL_TID;
+    if (c >= n) return;
+    const uint32_t p = recv[c];
+    const bool chained = (p != c) && (heavy[p] == c);
+    pd[c] = chained ? ((unsigned long long)p | (1ull << 32)) : (unsigned long long)c;
+}
+
+// step 3: path length, written by the path's last node (no heavy child): plen[head] = pos + 1
+__global__ void __launch_bounds__(256) k_path_len(uint32_t n, const uint32_t* __restrict__ heavy,
+                                                   const unsigned long long* __restrict__ pd,
+                                                   uint32_t* __restrict__ plen) {
+    uint32_t c = FL_TID;
+    if (c >= n) return;
+    if (heavy[c] != FL_NONE) return;
+    const unsigned long long a = pd[c];
+    plen[(uint32_t)a] = (uint32_t)(a >> 32) + 1u;
+}
+
+// step 4: nesting level of each path = number of path switches between its head and the tree root.
+// Jump table over path heads: head -> head of the parent's path.
+__global__ void __launch_bounds__(256) k_nest_init(uint32_t n, const uint32_t* __restrict__ recv,
+                                                    const unsigned long long* __restrict__ pd,
+                                                    unsigned long long* __restrict__ pd2) {
+    uint32_t q = FL_TID;
+    if (q >= n) return;
+    const uint32_t head = (uint32_t)pd[q];
+    if (head != q) { pd2[q] = (unsigned long long)q; return; }  // not a head: idle entry
+    const uint32_t p = recv[q];
+    if (p == q) { pd2[q] = (unsigned long long)q; return; }  // tree root: level 0
+    pd2[q] = (unsigned long long)(uint32_t)pd[p] | (1ull << 32);
+}
+
+// step 5: sort keys: level for heads, FL_NONE for everything else
+__global__ void __launch_bounds__(256) k_path_keys(uint32_t n, const unsigned long long* __restrict__ pd,
+                                                    const unsigned long long* __restrict__ pd2,
+                                                    uint32_t* __restrict__ keys, uint32_t* __restrict__ ids,
+                                                    uint32_t* flags) {
+    uint32_t q = FL_TID;
+    if (q >= n) return;
+    ids[q] = q;
+    if ((uint32_t)pd[q] == q) {
+        const uint32_t level = (uint32_t)(pd2[q] >> 32);
+        keys[q] = level;
+        if (level > 0) atomicMax(&flags[FL_FLAG_MAXDEPTH], level);
+    } else {
+        keys[q] = FL_NONE;
+    }
+}
+
+// step 6: per sorted path k: its length and the inverse map head -> k
+__global__ void __launch_bounds__(256) k_path_gather(uint32_t npaths, const uint32_t* __restrict__ hlist,
+                                                      const uint32_t* __restrict__ plen,
+                                                      uint32_t* __restrict__ len_sorted,
+                                                      uint32_t* __restrict__ hrank) {
+    uint32_t k = FL_TID;
+    if (k >= npaths) return;
+    const uint32_t h = hlist[k];
+    len_sorted[k] = plen[h];
+    hrank[h] = k;
+}
+
+// step 7: new position of every node = start of its path + position in the path
+__global__ void __launch_bounds__(256) k_newpos(uint32_t n, const unsigned long long* __restrict__ pd,
+                                                 const uint32_t* __restrict__ hrank,
+                                                 const uint32_t* __restrict__ starts, uint32_t* __restrict__ newpos) {
+    uint32_t q = FL_TID;
+    if (q >= n) return;
+    const unsigned long long a = pd[q];
+    newpos[q] = starts[hrank[(uint32_t)a]] + (uint32_t)(a >> 32);
+}
+
+// ------------------------------------------------------------------------------------------------
+// renumbering
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_deg_scatter(uint32_t n, const uint32_t* __restrict__ row_ptr,
+                                                      const uint32_t* __restrict__ newpos,
+                                                      uint32_t* __restrict__ deg_new) {
+    uint32_t q = FL_TID;
+    if (q >= n) return;
+    deg_new[newpos[q]] = row_ptr[q + 1] - row_ptr[q];
+}
+
+__global__ void __launch_bounds__(256) k_permute_rows(uint32_t n, const uint32_t* __restrict__ row_ptr,
+                                                       const uint32_t* __restrict__ col,
+                                                       const double* __restrict__ dist,
+                                                       const uint8_t* __restrict__ rev,
+                                                       const uint32_t* __restrict__ newpos,
+                                                       const uint32_t* __restrict__ row_ptr_new,
+                                                       uint32_t* __restrict__ col_new, double* __restrict__ dist_new,
+                                                       uint8_t* __restrict__ rev_new) {
+    uint32_t q = FL_TID;
+    if (q >= n) return;
+    const uint32_t s0 = row_ptr[q], deg = row_ptr[q + 1] - s0;
+    const uint32_t t0 = row_ptr_new[newpos[q]];
+    for (uint32_t k = 0; k < deg; ++k) {
+        col_new[t0 + k] = newpos[col[s0 + k]];
+        dist_new[t0 + k] = dist[s0 + k];
+        rev_new[t0 + k] = rev[s0 + k];
+    }
+}
+
+struct FlNodeArrays {
+    // f64 per-node arrays (tan may be null)
+    const double *areas, *erod, *uplift, *tan, *elev, *drecv;
+    double *areas_n, *erod_n, *uplift_n, *tan_n, *elev_n, *drecv_n;
+    // u32
+    const uint32_t *recv, *cmask, *rank, *orig_of;
+    uint32_t *recv_n, *cmask_n, *rank_n, *orig_of_n;
+    const uint8_t* is_outlet;
+    uint8_t* is_outlet_n;
+};
+
+__global__ void __launch_bounds__(256) k_permute_nodes(uint32_t n, const uint32_t* __restrict__ newpos,
+                                                        FlNodeArrays a) {
+    uint32_t q = FL_TID;
+    if (q >= n) return;
+    const uint32_t p = newpos[q];
+    a.areas_n[p] = a.areas[q];
+    a.erod_n[p] = a.erod[q];
+    a.uplift_n[p] = a.uplift[q];
+    if (a.tan) a.tan_n[p] = a.tan[q];
+    a.elev_n[p] = a.elev[q];
+    a.drecv_n[p] = a.drecv[q];
+    a.recv_n[p] = newpos[a.recv[q]];
+    a.cmask_n[p] = a.cmask[q];
+    if (a.rank) a.rank_n[p] = a.rank[q];
+    a.orig_of_n[p] = a.orig_of[q];
+    a.is_outlet_n[p] = a.is_outlet[q];
+}
+
+__global__ void __launch_bounds__(256) k_rank_inverse(uint32_t n, const uint32_t* __restrict__ rank,
+                                                       uint32_t* __restrict__ rank_to_node) {
+    uint32_t q = FL_TID;
+    if (q >= n) return;
+    const uint32_t t = rank[q];
+    if (t != FL_NONE) rank_to_node[t] = q;
+}
+
+__global__ void __launch_bounds__(256) k_iota(uint32_t n, uint32_t* __restrict__ a) {
+    uint32_t q = FL_TID;
+    if (q < n) a[q] = q;
+}
+
+// out[orig_of[q]] = in[q]  (results back in the caller's numbering)
+__global__ void __launch_bounds__(256) k_unpermute_f64(uint32_t n, const uint32_t* __restrict__ orig_of,
+                                                        const double* __restrict__ in, double* __restrict__ out) {
+    uint32_t q = FL_TID;
+    if (q < n) out[orig_of[q]] = in[q];
+}
+
+// same for arrays whose VALUES are node ids (receivers, labels); FL_NONE stays
+__global__ void __launch_bounds__(256) k_unpermute_ids(uint32_t n, const uint32_t* __restrict__ orig_of,
+                                                        const uint32_t* __restrict__ in, uint32_t* __restrict__ out) {
+    uint32_t q = FL_TID;
+    if (q >= n) return;
+    const uint32_t v = in[q];
+    out[orig_of[q]] = (v == FL_NONE) ? FL_NONE : orig_of[v];
+}
+
+__global__ void __launch_bounds__(256) k_unpermute_u32(uint32_t n, const uint32_t* __restrict__ orig_of,
+                                                        const uint32_t* __restrict__ in, uint32_t* __restrict__ out) {
+    uint32_t q = FL_TID;
+    if (q < n) out[orig_of[q]] = in[q];
+}
+
+__global__ void __launch_bounds__(256) k_gather_u32(uint32_t n, const uint32_t* __restrict__ orig_of,
+                                                     const uint32_t* __restrict__ src, uint32_t* __restrict__ dst) {
+    uint32_t q = FL_TID;
+    if (q < n) dst[q] = src[orig_of[q]];
+}
+
+// debug stages: label / depth of the final forest; depth FL_NONE where the root is not an outlet
+__global__ void __launch_bounds__(256) k_labels_depth(uint32_t n, const unsigned long long* __restrict__ pd,
+                                                       const uint8_t* __restrict__ is_outlet,
+                                                       uint32_t* __restrict__ label, uint32_t* __restrict__ depth) {
+    uint32_t q = FL_TID;
+    if (q >= n) return;
+    const unsigned long long a = pd[q];
+    label[q] = (uint32_t)a;
+    depth[q] = is_outlet[(uint32_t)a] ? (uint32_t)(a >> 32) : FL_NONE;
+}
+
+// debug stages: value where the site is visited, the loop's initial value (areas / 0.0) elsewhere
+__global__ void __launch_bounds__(256) k_stage_value(uint32_t n, const uint32_t* __restrict__ depth,
+                                                      const double* __restrict__ val,
+                                                      const double* __restrict__ fallback, double* __restrict__ out) {
+    uint32_t q = FL_TID;
+    if (q >= n) return;
+    out[q] = depth[q] != FL_NONE ? val[q] : (fallback ? fallback[q] : 0.0);
+}
+
+// in[int] <- src[orig]  (parameters / initial elevations into the current numbering)
+__global__ void __launch_bounds__(256) k_gather_f64(uint32_t n, const uint32_t* __restrict__ orig_of,
+                                                     const double* __restrict__ src, double* __restrict__ dst) {
+    uint32_t q = FL_TID;
+    if (q < n) dst[q] = src[orig_of[q]];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 on paths (generator.rs:154-159): one thread per path, bottom (tail) to top (head); `x` carries the
+// heavy child's finished area in a register.  Children other than q+1 are heads of deeper-nested paths,
+// finished in an earlier round.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_area_paths(uint32_t begin, uint32_t count,
+                                                     const uint32_t* __restrict__ seg_head,
+                                                     const uint32_t* __restrict__ seg_len,
+                                                     const uint32_t* __restrict__ row_ptr,
+                                                     const uint32_t* __restrict__ col,
+                                                     const uint32_t* __restrict__ recv,
+                                                     const uint32_t* __restrict__ cmask,
+                                                     const double* __restrict__ areas, double* A) {
+    uint32_t t = FL_TID;
+    if (t >= count) return;
+    const uint32_t h = seg_head[begin + t];
+    const uint32_t last = h + seg_len[begin + t] - 1u;
+    double x = 0.0;
+    for (uint32_t q = last;; --q) {
+        double a = areas[q];
+        const bool has_chain = q < last;
+        fl_children_rev(q, row_ptr, col, recv, cmask, [&](uint32_t c) {
+            a += (has_chain && c == q + 1u) ? x : A[c];
+        });
+        A[q] = a;
+        x = a;
+        if (q == h) break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5 on paths (generator.rs:162-203): one thread per path, head to tail; response time and the new
+// elevation of the receiver travel down the path in registers.
+//   rt_i = 0.0 + (rt_recv + 1.0 / (k_i * sqrt(A_i)) * d_i);  z = e_out + u_i * max(rt_i - rt_out, 0.0)
+// root_of[q] = root of q's tree (FL_NONE if that root is not an outlet: such trees are never visited).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_elev_paths(uint32_t begin, uint32_t count,
+                                                     const uint32_t* __restrict__ seg_head,
+                                                     const uint32_t* __restrict__ seg_len,
+                                                     const uint32_t* __restrict__ recv,
+                                                     const double* __restrict__ drecv, const double* __restrict__ A,
+                                                     const double* __restrict__ erod,
+                                                     const double* __restrict__ uplift,
+                                                     const double* __restrict__ tan_slope,
+                                                     const uint8_t* __restrict__ is_outlet, double* elev, double* rt,
+                                                     uint32_t* root_of, uint32_t* __restrict__ flags) {
+    uint32_t t = FL_TID;
+    if (t >= count) return;
+    const uint32_t h = seg_head[begin + t];
+    const uint32_t last = h + seg_len[begin + t] - 1u;
+    const uint32_t p = recv[h];
+    const bool is_root = (p == h);
+    uint32_t root;
+    double rt_prev, z_prev, e_out, rt_out;
+    if (is_root) {
+        root = is_outlet[h] ? h : FL_NONE;
+        rt_prev = 0.0;
+        z_prev = elev[h];  // has_edge(i,i) is false -> the clamp compares with the site's own old elevation
+        e_out = elev[h];
+        rt_out = 0.0;  // set below from the root's own response time
+    } else {
+        root = root_of[p];
+        rt_prev = rt[p];
+        z_prev = elev[p];  // receiver already holds its NEW elevation
+        e_out = root != FL_NONE ? elev[root] : 0.0;
+        rt_out = root != FL_NONE ? rt[root] : 0.0;
+    }
+    if (root == FL_NONE) {
+        for (uint32_t q = h; q <= last; ++q) root_of[q] = FL_NONE;
+        return;
+    }
+    bool changed = false;
+    for (uint32_t q = h; q <= last; ++q) {
+        const double d = drecv[q];
+        const double celerity = erod[q] * sqrt(A[q]);
+        const double rti = 0.0 + (rt_prev + 1.0 / celerity * d);
+        if (is_root && q == h) rt_out = rti;
+        double z = e_out + uplift[q] * fmax(rti - rt_out, 0.0);
+        if (tan_slope) {
+            const double ms = tan_slope[q];
+            if (ms == ms) {
+                const double slope = (z - z_prev) / d;
+                if (slope > ms) z = z_prev + ms * d;
+            }
+        }
+        changed |= (z != elev[q]);
+        if (is_root && q == h) e_out = z;  // later sites read elevations[outlet] after the outlet's own update
+        elev[q] = z;
+        rt[q] = rti;
+        root_of[q] = root;
+        rt_prev = rti;
+        z_prev = z;
+    }
+    if (changed) flags[FL_FLAG_CHANGED] = 1u;
+}

@@ -48,6 +48,8 @@ template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return 
 template <class T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
 template <class T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
+template <class T> inline T atomicAnd(T* p, T v) { T o = *p; *p = o & v; return o; }
+inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 inline void __threadfence() {}
 inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
@@ -102,10 +104,19 @@ inline cudaError_t fl_sort_pairs(void*, size_t& temp_bytes, const uint32_t* kin,
     return 0;
 }
 
+inline cudaError_t fl_exclusive_sum(void*, size_t& temp_bytes, const uint32_t* in, uint32_t* out, uint32_t n,
+                                    cudaStream_t, bool query) {
+    if (query) { temp_bytes = 1; return 0; }
+    uint32_t acc = 0;
+    for (uint32_t i = 0; i < n; ++i) { uint32_t v = in[i]; out[i] = acc; acc += v; }
+    return 0;
+}
+
 #else
 // ------------------------------------------------------------------------------------------------
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #define FL_DEVICE_BUILD 1
 
 #define FL_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
@@ -146,5 +157,10 @@ inline cudaError_t fl_sort_pairs(void* temp, size_t& temp_bytes, const uint32_t*
                                  bool query) {
     return cub::DeviceRadixSort::SortPairs(query ? nullptr : temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, end_bit,
                                            s);
+}
+
+inline cudaError_t fl_exclusive_sum(void* temp, size_t& temp_bytes, const uint32_t* in, uint32_t* out, uint32_t n,
+                                    cudaStream_t s, bool query) {
+    return cub::DeviceScan::ExclusiveSum(query ? nullptr : temp, temp_bytes, in, out, (int)n, s);
 }
 #endif

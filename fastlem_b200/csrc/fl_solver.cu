@@ -3,16 +3,23 @@
 //
 // Compiled by nvcc for sm_100a (product) or, with -DFL_EMU, by g++ as a serial host emulation used only
 // by the CPU test tier (see fl_rt.h).
+//
+// Two sweep implementations (option "sweep"):
+//   0  level-synchronous: nodes sorted by tree depth, one launch per level and sweep (simple; launch bound)
+//   1  path-decomposed  : fl_paths.cuh -- the sites are renumbered so that every heavy path is contiguous and
+//                         one thread walks a path; ~20 rounds per sweep instead of ~1000 levels (default)
 #include "../../include/fastlem_b200.h"
 
 #include <chrono>
 #include <cmath>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "fl_flood.h"
 #include "fl_kernels.cuh"
+#include "fl_paths.cuh"
 
 #ifdef FL_EMU
 thread_local fl_dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -26,6 +33,25 @@ double wall_ms() {
 
 enum Stage { ST_RECV = 0, ST_LABEL, ST_LAKE, ST_ORDER, ST_AREA, ST_ELEV, ST_COUNT };
 
+// One numbering of the sites and everything stored in it.
+struct Layout {
+    uint32_t* row_ptr = nullptr;
+    uint32_t* col = nullptr;
+    double* dist = nullptr;
+    uint8_t* rev = nullptr;
+    double* areas = nullptr;
+    double* erod = nullptr;
+    double* uplift = nullptr;
+    double* tan = nullptr;  // null = max_slope None everywhere
+    uint8_t* is_outlet = nullptr;
+    uint32_t* rank = nullptr;     // flood order, valid when ctx.rank_ready
+    uint32_t* orig_of = nullptr;  // this numbering -> the caller's
+    double* elev = nullptr;
+    double* drecv = nullptr;
+    uint32_t* recv = nullptr;
+    uint32_t* cmask = nullptr;
+};
+
 }  // namespace
 
 struct fastlem_ctx {
@@ -33,64 +59,66 @@ struct fastlem_ctx {
     cudaStream_t stream = 0;
     bool stream_ok = false;
     std::string err;
+    std::vector<void**> owned;  // every device allocation, for free_all
 
-    // model (device)
     uint32_t n = 0, nnz = 0;
-    bool has_graph = false, has_params = false;
-    uint32_t* d_row_ptr = nullptr;
-    uint32_t* d_col = nullptr;
-    double* d_dist = nullptr;
-    double* d_areas = nullptr;
+    bool has_graph = false, has_params = false, has_tan = false;
     // borrowed host pointers (flood order is computed from them on first use)
     const uint32_t* h_row_ptr = nullptr;
     const uint32_t* h_col = nullptr;
     const double* h_dist = nullptr;
-
-    // parameters (device)
-    double* d_init = nullptr;
-    double* d_erod = nullptr;
-    double* d_uplift = nullptr;
-    double* d_tan = nullptr;  // null = None everywhere
-    uint8_t* d_is_outlet = nullptr;
     std::vector<uint32_t> outlets;
 
-    // flood order (static per graph+outlets), lazily built
-    bool rank_ready = false;
-    uint32_t* d_rank = nullptr;
-    uint32_t* d_rank_to_node = nullptr;
+    Layout orig;    // the caller's numbering: static inputs only (+ rank)
+    Layout lay[2];  // working numberings (double buffer for renumbering)
+    int cur = 0;
+    double* d_init = nullptr;  // initial elevations, caller's numbering
 
-    // state
-    double* d_elev = nullptr;
-    uint32_t* d_recv = nullptr;
-    double* d_drecv = nullptr;
+    bool rank_ready = false;
+    bool layout_valid = false;           // lay[cur] holds a complete numbering (set by reset_layout)
+    uint32_t* d_rank_to_node = nullptr;  // current numbering
+
+    // per-iteration state (current numbering)
     unsigned long long* d_pd = nullptr;
+    unsigned long long* d_pd2 = nullptr;
     unsigned long long* d_lake_key = nullptr;
     uint32_t* d_label = nullptr;
-    uint32_t* d_depth = nullptr;
+    uint32_t* d_depth = nullptr;  // also: sort keys
     uint32_t* d_ids = nullptr;
-    uint32_t* d_sorted_depth = nullptr;
-    uint32_t* d_order = nullptr;
-    uint32_t* d_offs = nullptr;  // n+2
+    uint32_t* d_sorted = nullptr;
+    uint32_t* d_order = nullptr;  // level order (sweep 0) / sorted path heads (sweep 1)
+    uint32_t* d_offs = nullptr;   // n+2
     double* d_A = nullptr;
     double* d_rt = nullptr;
-    uint32_t* d_flags = nullptr;
-    uint32_t* h_flags = nullptr;  // pinned
-    uint32_t* h_offs = nullptr;   // pinned, n+2
-    void* d_sort_tmp = nullptr;
-    size_t sort_tmp_bytes = 0;
-    // keep_stages
+    uint32_t* d_root_of = nullptr;
+    // path layout
+    uint32_t* d_heavy = nullptr;
+    uint32_t* d_plen = nullptr;
+    uint32_t* d_len_sorted = nullptr;
+    uint32_t* d_hrank = nullptr;
+    uint32_t* d_seg_head = nullptr;  // n+1
+    uint32_t* d_newpos = nullptr;
+    uint32_t* d_deg_new = nullptr;  // n+1
+    uint32_t n_levels = 0, n_paths = 0;
+    // scratch in the caller's numbering (download, debug fetch, kept stages)
+    double* d_out_f64 = nullptr;
+    uint32_t* d_out_u32 = nullptr;
     uint32_t* d_recv0 = nullptr;
     uint32_t* d_label0 = nullptr;
     bool stages_valid = false;
 
-    // options
+    uint32_t* d_flags = nullptr;
+    uint32_t* h_flags = nullptr;  // pinned
+    uint32_t* h_offs = nullptr;   // pinned, n+2
+    void* d_tmp = nullptr;        // CUB temp storage (sort / scan)
+    size_t tmp_bytes = 0;
+
     bool opt_profile = false, opt_keep = false;
-    int64_t opt_sweep = 0;
+    int64_t opt_sweep = 1;
 
     fastlem_stats stats{};
     cudaEvent_t ev[ST_COUNT + 1] = {};
     cudaEvent_t ev_run[2] = {};
-    bool ev_ok = false;
 };
 
 namespace {
@@ -100,176 +128,327 @@ int fail(fastlem_ctx* c, int code, const std::string& msg) {
     return code;
 }
 
-#define FL_CK(expr)                                                                                          \
-    do {                                                                                                     \
-        cudaError_t e__ = (expr);                                                                            \
-        if (e__ != cudaSuccess)                                                                              \
-            return fail(c, FASTLEM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));             \
+#define FL_CK(expr)                                                                              \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return fail(c, FASTLEM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+#define FL_RC(expr)          \
+    do {                     \
+        int rc__ = (expr);   \
+        if (rc__) return rc__; \
     } while (0)
 
-template <class T> void dfree(T*& p) {
-    if (p) fl_free(p);
-    p = nullptr;
-}
-
-template <class T> cudaError_t dalloc(T*& p, size_t count) {
-    dfree(p);
+template <class T> cudaError_t dalloc(fastlem_ctx* c, T*& p, size_t count) {
+    if (p) { fl_free(p); p = nullptr; }
     void* v = nullptr;
     cudaError_t e = fl_malloc(&v, count * sizeof(T));
     p = (T*)v;
+    bool known = false;
+    for (void** q : c->owned) known = known || (q == (void**)&p);
+    if (!known) c->owned.push_back((void**)&p);
     return e;
 }
 
-void free_graph(fastlem_ctx* c) {
-    dfree(c->d_row_ptr); dfree(c->d_col); dfree(c->d_dist); dfree(c->d_areas);
-    dfree(c->d_init); dfree(c->d_erod); dfree(c->d_uplift); dfree(c->d_tan); dfree(c->d_is_outlet);
-    dfree(c->d_rank); dfree(c->d_rank_to_node);
-    dfree(c->d_elev); dfree(c->d_recv); dfree(c->d_drecv); dfree(c->d_pd); dfree(c->d_lake_key);
-    dfree(c->d_label); dfree(c->d_depth); dfree(c->d_ids); dfree(c->d_sorted_depth); dfree(c->d_order);
-    dfree(c->d_offs); dfree(c->d_A); dfree(c->d_rt); dfree(c->d_recv0); dfree(c->d_label0);
-    if (c->d_sort_tmp) fl_free(c->d_sort_tmp);
-    c->d_sort_tmp = nullptr;
+void free_all(fastlem_ctx* c) {
+    for (void** q : c->owned)
+        if (*q) { fl_free(*q); *q = nullptr; }
+    c->owned.clear();
     if (c->h_offs) fl_free_host(c->h_offs);
     c->h_offs = nullptr;
-    c->has_graph = c->has_params = c->rank_ready = c->stages_valid = false;
+    c->has_graph = c->has_params = c->rank_ready = c->stages_valid = c->has_tan = c->layout_valid = false;
 }
 
-inline unsigned blocks_for(uint32_t count) { return (count + 255u) / 256u; }
+inline unsigned blocks_for(uint32_t count, unsigned block = 256) { return (count + block - 1u) / block; }
+inline Layout& L_(fastlem_ctx* c) { return c->lay[c->cur]; }
 
-// lazily compute + upload the flood order (fl_flood.cpp)
-int ensure_rank(fastlem_ctx* c) {
-    if (c->rank_ready) return FASTLEM_OK;
-    double t0 = wall_ms();
-    const uint32_t n = c->n;
-    std::vector<uint32_t> rank(n), inv(n, FL_NONE);
-    fl_flood_rank(n, c->h_row_ptr, c->h_col, c->h_dist, c->outlets.data(), (uint32_t)c->outlets.size(), rank.data());
-    for (uint32_t i = 0; i < n; ++i)
-        if (rank[i] != FL_NONE) inv[rank[i]] = i;
-    FL_CK(dalloc(c->d_rank, n));
-    FL_CK(dalloc(c->d_rank_to_node, n));
-    FL_CK(fl_h2d(c->d_rank, rank.data(), sizeof(uint32_t) * n, c->stream));
-    FL_CK(fl_h2d(c->d_rank_to_node, inv.data(), sizeof(uint32_t) * n, c->stream));
-    FL_CK(fl_stream_sync(c->stream));
-    c->rank_ready = true;
-    c->stats.ms_flood_rank = wall_ms() - t0;
-    return FASTLEM_OK;
-}
-
-// K2 driver: pointer jumping until stable; leaves (root, depth) pairs in d_pd
-int run_jump(fastlem_ctx* c) {
-    const uint32_t n = c->n;
-    const unsigned g = blocks_for(n);
-    FL_LAUNCH(k_jump_init, g, 256, c->stream, n, c->d_recv, c->d_pd);
-    c->stats.kernel_launches++; c->stats.n_labels++;
-    for (int round = 0; round < 40; ++round) {
-        FL_CK(fl_memset(c->d_flags + FL_FLAG_JUMP, 0, sizeof(uint32_t), c->stream));
-        FL_LAUNCH(k_jump, g, 256, c->stream, n, c->d_pd, c->d_flags);
-        c->stats.kernel_launches++; c->stats.n_labels++;
-        FL_CK(fl_d2h(c->h_flags, c->d_flags, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
-        FL_CK(fl_stream_sync(c->stream));
-        if (!c->h_flags[FL_FLAG_JUMP]) return FASTLEM_OK;
-    }
-    return fail(c, FASTLEM_E_STATE, "pointer jumping did not converge (cycle in receivers?)");
-}
+#define LAUNCH_N(kernel, count, ...)                                                  \
+    do {                                                                              \
+        if ((count) > 0) {                                                            \
+            FL_LAUNCH(kernel, blocks_for(count), 256, c->stream, __VA_ARGS__);        \
+            c->stats.kernel_launches++;                                               \
+        }                                                                             \
+    } while (0)
 
 int stage_mark(fastlem_ctx* c, int k) {
     if (c->opt_profile) FL_CK(fl_event_record(c->ev[k], c->stream));
     return FASTLEM_OK;
 }
 
-// one loop body of generator.rs:140-210; *changed_out = the `changed` flag
-int iterate(fastlem_ctx* c, bool first, bool* changed_out) {
-    const uint32_t n = c->n;
-    const unsigned g = blocks_for(n);
-    int rc;
-    FL_CK(fl_memset(c->d_flags, 0, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
-    if ((rc = stage_mark(c, 0))) return rc;
-
-    // K1 receivers
-    FL_LAUNCH(k_receivers, g, 256, c->stream, n, c->d_row_ptr, c->d_col, c->d_dist, c->d_elev, c->d_is_outlet,
-              c->d_recv, c->d_drecv, c->d_flags);
-    c->stats.kernel_launches++; c->stats.n_receivers++;
-    if ((rc = stage_mark(c, 1))) return rc;
-
-    // K2 labels (+ depth)
-    if ((rc = run_jump(c))) return rc;
-    const bool has_lake = c->h_flags[FL_FLAG_LAKE] != 0;
-    if ((rc = stage_mark(c, 2))) return rc;
-
-    // K3 lake connection
-    c->stages_valid = false;
-    if (has_lake) {
-        if ((rc = ensure_rank(c))) return rc;
-        FL_LAUNCH(k_labels_only, g, 256, c->stream, n, c->d_pd, c->d_label);
-        c->stats.kernel_launches++;
-        if (c->opt_keep) {
-            FL_CK(fl_d2d(c->d_recv0, c->d_recv, sizeof(uint32_t) * n, c->stream));
-            FL_CK(fl_d2d(c->d_label0, c->d_label, sizeof(uint32_t) * n, c->stream));
-            c->stages_valid = true;
-        }
-        FL_CK(fl_memset(c->d_lake_key, 0xFF, sizeof(unsigned long long) * n, c->stream));
-        FL_LAUNCH(k_lake_min, g, 256, c->stream, n, c->d_row_ptr, c->d_col, c->d_label, c->d_is_outlet, c->d_rank,
-                  c->d_lake_key);
-        FL_LAUNCH(k_lake_reverse, g, 256, c->stream, n, c->d_row_ptr, c->d_col, c->d_dist, c->d_is_outlet,
-                  c->d_rank_to_node, c->d_lake_key, c->d_label, c->d_recv, c->d_drecv);
-        c->stats.kernel_launches += 2; c->stats.n_lakes += 3;
-        c->stats.lake_iterations++;
-        if ((rc = run_jump(c))) return rc;
-    }
-    if ((rc = stage_mark(c, 3))) return rc;
-
-    // ordering: sort nodes by depth
-    FL_LAUNCH(k_labels_finalize, g, 256, c->stream, n, c->d_pd, c->d_is_outlet, c->d_areas, c->d_label, c->d_depth,
-              c->d_ids, c->d_A, c->d_rt);
-    FL_CK(fl_sort_pairs(c->d_sort_tmp, c->sort_tmp_bytes, c->d_depth, c->d_sorted_depth, c->d_ids, c->d_order, n, 32,
-                        c->stream, false));
-    FL_CK(fl_memset(c->d_flags + FL_FLAG_MAXDEPTH, 0xFF, sizeof(uint32_t), c->stream));
-    FL_LAUNCH(k_level_offsets, g, 256, c->stream, n, c->d_sorted_depth, c->d_offs, c->d_flags);
-    c->stats.kernel_launches += 3; c->stats.n_order += 3;
+int read_flags(fastlem_ctx* c) {
     FL_CK(fl_d2h(c->h_flags, c->d_flags, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
     FL_CK(fl_stream_sync(c->stream));
+    return FASTLEM_OK;
+}
+
+// pointer jumping on a packed (pointer, distance) table until stable
+int jump_loop(fastlem_ctx* c, unsigned long long* pd) {
+    const uint32_t n = c->n;
+    for (int round = 0; round < 48; ++round) {
+        FL_CK(fl_memset(c->d_flags + FL_FLAG_JUMP, 0, sizeof(uint32_t), c->stream));
+        LAUNCH_N(k_jump, n, n, pd, c->d_flags);
+        c->stats.n_labels++;
+        FL_RC(read_flags(c));
+        if (!c->h_flags[FL_FLAG_JUMP]) return FASTLEM_OK;
+    }
+    return fail(c, FASTLEM_E_STATE, "pointer jumping did not converge (cycle in receivers?)");
+}
+
+// K2: (root, depth) of every node in the receiver forest -> d_pd
+int run_labels(fastlem_ctx* c) {
+    LAUNCH_N(k_jump_init, c->n, c->n, L_(c).recv, c->d_pd);
+    return jump_loop(c, c->d_pd);
+}
+
+// flood order (fl_flood.cpp): computed once per (graph, outlets) in the caller's numbering
+int ensure_rank(fastlem_ctx* c) {
+    if (c->rank_ready) return FASTLEM_OK;
+    double t0 = wall_ms();
+    const uint32_t n = c->n;
+    std::vector<uint32_t> rank(n);
+    fl_flood_rank(n, c->h_row_ptr, c->h_col, c->h_dist, c->outlets.data(), (uint32_t)c->outlets.size(), rank.data());
+    FL_CK(fl_h2d(c->orig.rank, rank.data(), sizeof(uint32_t) * n, c->stream));
+    FL_CK(fl_stream_sync(c->stream));
+    if (c->layout_valid) {  // into the current numbering (otherwise reset_layout does it at the next run)
+        Layout& L = L_(c);
+        LAUNCH_N(k_gather_u32, n, n, L.orig_of, c->orig.rank, L.rank);
+        FL_CK(fl_memset(c->d_rank_to_node, 0xFF, sizeof(uint32_t) * n, c->stream));
+        LAUNCH_N(k_rank_inverse, n, n, L.rank, c->d_rank_to_node);
+    }
+    c->rank_ready = true;
+    c->stats.ms_flood_rank = wall_ms() - t0;
+    return FASTLEM_OK;
+}
+
+// K3: connect every lake basin and reverse its in-basin path (labels must be in d_pd)
+int run_lakes(fastlem_ctx* c) {
+    const uint32_t n = c->n;
+    Layout& L = L_(c);
+    FL_RC(ensure_rank(c));
+    LAUNCH_N(k_labels_only, n, n, c->d_pd, c->d_label);
+    if (c->opt_keep) {
+        LAUNCH_N(k_unpermute_ids, n, n, L.orig_of, L.recv, c->d_recv0);
+        LAUNCH_N(k_unpermute_ids, n, n, L.orig_of, c->d_label, c->d_label0);
+        c->stages_valid = true;
+    }
+    FL_CK(fl_memset(c->d_lake_key, 0xFF, sizeof(unsigned long long) * n, c->stream));
+    LAUNCH_N(k_lake_min, n, n, L.row_ptr, L.col, c->d_label, L.is_outlet, L.rank, c->d_lake_key);
+    LAUNCH_N(k_lake_reverse, n, n, L.row_ptr, L.col, L.dist, L.is_outlet, c->d_rank_to_node, c->d_lake_key, c->d_label,
+             L.recv, L.drecv);
+    c->stats.n_lakes += 3;
+    c->stats.lake_iterations++;
+    return FASTLEM_OK;
+}
+
+int profile_accumulate(fastlem_ctx* c) {
+    if (!c->opt_profile) return FASTLEM_OK;
+    double* acc[ST_COUNT] = {&c->stats.ms_receivers, &c->stats.ms_labels, &c->stats.ms_lakes,
+                             &c->stats.ms_order,     &c->stats.ms_area,   &c->stats.ms_elevation};
+    for (int k = 0; k < ST_COUNT; ++k) {
+        float ms = 0.f;
+        FL_CK(fl_event_elapsed(&ms, c->ev[k], c->ev[k + 1]));
+        *acc[k] += ms;
+    }
+    return FASTLEM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sweep 0: one loop body of generator.rs:140-210, level-synchronous
+// ------------------------------------------------------------------------------------------------
+int iterate_levels(fastlem_ctx* c, bool first, bool* changed_out) {
+    const uint32_t n = c->n;
+    Layout& L = L_(c);
+    FL_CK(fl_memset(c->d_flags, 0, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
+    FL_RC(stage_mark(c, 0));
+
+    LAUNCH_N(k_receivers, n, n, L.row_ptr, L.col, L.dist, L.elev, L.is_outlet, L.recv, L.drecv, c->d_flags);
+    c->stats.n_receivers++;
+    FL_RC(stage_mark(c, 1));
+
+    FL_RC(run_labels(c));
+    const bool has_lake = c->h_flags[FL_FLAG_LAKE] != 0;
+    FL_RC(stage_mark(c, 2));
+
+    c->stages_valid = false;
+    if (has_lake) {
+        FL_RC(run_lakes(c));
+        FL_RC(run_labels(c));
+    }
+    FL_RC(stage_mark(c, 3));
+
+    // ordering: sort nodes by depth
+    LAUNCH_N(k_labels_finalize, n, n, c->d_pd, L.is_outlet, L.areas, c->d_label, c->d_depth, c->d_ids, c->d_A, c->d_rt);
+    FL_CK(fl_sort_pairs(c->d_tmp, c->tmp_bytes, c->d_depth, c->d_sorted, c->d_ids, c->d_order, n, 32, c->stream, false));
+    FL_CK(fl_memset(c->d_flags + FL_FLAG_MAXDEPTH, 0xFF, sizeof(uint32_t), c->stream));
+    LAUNCH_N(k_level_offsets, n, n, c->d_sorted, c->d_offs, c->d_flags);
+    c->stats.n_order += 3;
+    FL_RC(read_flags(c));
     const uint32_t maxd = c->h_flags[FL_FLAG_MAXDEPTH];
-    if ((rc = stage_mark(c, 4))) return rc;
+    FL_RC(stage_mark(c, 4));
     if (maxd != FL_NONE) {
         FL_CK(fl_d2h(c->h_offs, c->d_offs, sizeof(uint32_t) * ((size_t)maxd + 2), c->stream));
         FL_CK(fl_stream_sync(c->stream));
         if (first) c->stats.depth_first = maxd + 1;
         c->stats.depth_last = maxd + 1;
-
-        // K4 drainage area: deepest level first
-        for (uint32_t lv = maxd + 1; lv-- > 0;) {
+        for (uint32_t lv = maxd + 1; lv-- > 0;) {  // K4: deepest level first
             const uint32_t b = c->h_offs[lv], cnt = c->h_offs[lv + 1] - b;
-            FL_LAUNCH(k_area_level, blocks_for(cnt), 256, c->stream, b, cnt, c->d_order, c->d_row_ptr, c->d_col,
-                      c->d_recv, c->d_areas, c->d_A);
+            LAUNCH_N(k_area_level, cnt, b, cnt, c->d_order, L.row_ptr, L.col, L.recv, L.areas, c->d_A);
         }
-        c->stats.kernel_launches += maxd + 1; c->stats.n_area += maxd + 1;
-        if ((rc = stage_mark(c, 5))) return rc;
-
-        // K5 response time + elevation: roots first
-        for (uint32_t lv = 0; lv <= maxd; ++lv) {
+        c->stats.n_area += maxd + 1;
+        FL_RC(stage_mark(c, 5));
+        for (uint32_t lv = 0; lv <= maxd; ++lv) {  // K5: roots first
             const uint32_t b = c->h_offs[lv], cnt = c->h_offs[lv + 1] - b;
-            FL_LAUNCH(k_elev_level, blocks_for(cnt), 256, c->stream, b, cnt, (int)lv, c->d_order, c->d_recv, c->d_label,
-                      c->d_drecv, c->d_A, c->d_erod, c->d_uplift, c->d_tan, c->d_elev, c->d_rt, c->d_flags);
+            LAUNCH_N(k_elev_level, cnt, b, cnt, (int)lv, c->d_order, L.recv, c->d_label, L.drecv, c->d_A, L.erod,
+                     L.uplift, L.tan, L.elev, c->d_rt, c->d_flags);
         }
-        c->stats.kernel_launches += maxd + 1; c->stats.n_elevation += maxd + 1;
+        c->stats.n_elevation += maxd + 1;
     } else {
-        if ((rc = stage_mark(c, 5))) return rc;
+        FL_RC(stage_mark(c, 5));
     }
-    if ((rc = stage_mark(c, 6))) return rc;
-    FL_CK(fl_d2h(c->h_flags, c->d_flags, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
-    FL_CK(fl_stream_sync(c->stream));
+    FL_RC(stage_mark(c, 6));
+    FL_RC(read_flags(c));
     FL_CK(fl_last_error());
     *changed_out = c->h_flags[FL_FLAG_CHANGED] != 0;
+    return profile_accumulate(c);
+}
 
-    if (c->opt_profile) {
-        double* acc[ST_COUNT] = {&c->stats.ms_receivers, &c->stats.ms_labels, &c->stats.ms_lakes,
-                                 &c->stats.ms_order,     &c->stats.ms_area,   &c->stats.ms_elevation};
-        for (int k = 0; k < ST_COUNT; ++k) {
-            float ms = 0.f;
-            FL_CK(fl_event_elapsed(&ms, c->ev[k], c->ev[k + 1]));
-            *acc[k] += ms;
-        }
+// ------------------------------------------------------------------------------------------------
+// sweep 1: renumber the sites so that the heavy paths of the CURRENT receiver forest are contiguous
+// (fl_paths.cuh).  `weight` ranks the children of a node (previous drainage areas).
+// ------------------------------------------------------------------------------------------------
+int rebuild_layout(fastlem_ctx* c, const double* weight) {
+    const uint32_t n = c->n;
+    Layout& L = c->lay[c->cur];
+    Layout& M = c->lay[c->cur ^ 1];
+
+    LAUNCH_N(k_heavy, n, n, L.row_ptr, L.col, L.recv, L.cmask, weight, c->d_heavy);
+    LAUNCH_N(k_chain_init, n, n, L.recv, c->d_heavy, c->d_pd);
+    FL_RC(jump_loop(c, c->d_pd));  // -> (path head, position in path)
+    LAUNCH_N(k_path_len, n, n, c->d_heavy, c->d_pd, c->d_plen);
+    LAUNCH_N(k_nest_init, n, n, L.recv, c->d_pd, c->d_pd2);
+    FL_RC(jump_loop(c, c->d_pd2));  // -> (root path head, nesting level)
+    FL_CK(fl_memset(c->d_flags + FL_FLAG_MAXDEPTH, 0, sizeof(uint32_t), c->stream));
+    LAUNCH_N(k_path_keys, n, n, c->d_pd, c->d_pd2, c->d_depth, c->d_ids, c->d_flags);
+    FL_RC(read_flags(c));
+    const uint32_t max_level = c->h_flags[FL_FLAG_MAXDEPTH];
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) <= (unsigned long long)max_level + 1ull) ++bits;  // FL_NONE sorts last
+    FL_CK(fl_sort_pairs(c->d_tmp, c->tmp_bytes, c->d_depth, c->d_sorted, c->d_ids, c->d_order, n, bits, c->stream,
+                        false));
+    FL_CK(fl_memset(c->d_flags + FL_FLAG_MAXDEPTH, 0xFF, sizeof(uint32_t), c->stream));
+    LAUNCH_N(k_level_offsets, n, n, c->d_sorted, c->d_offs, c->d_flags);
+    FL_RC(read_flags(c));
+    if (c->h_flags[FL_FLAG_MAXDEPTH] != max_level) return fail(c, FASTLEM_E_STATE, "layout: level bookkeeping broke");
+    c->n_levels = max_level + 1;
+    c->n_paths = c->h_flags[FL_FLAG_REACHED];
+    FL_CK(fl_d2h(c->h_offs, c->d_offs, sizeof(uint32_t) * ((size_t)c->n_levels + 1), c->stream));
+
+    LAUNCH_N(k_path_gather, c->n_paths, c->n_paths, c->d_order, c->d_plen, c->d_len_sorted, c->d_hrank);
+    FL_CK(fl_exclusive_sum(c->d_tmp, c->tmp_bytes, c->d_len_sorted, c->d_seg_head, c->n_paths, c->stream, false));
+    LAUNCH_N(k_newpos, n, n, c->d_pd, c->d_hrank, c->d_seg_head, c->d_newpos);
+
+    // renumber everything: L -> M
+    FL_CK(fl_memset(c->d_deg_new + n, 0, sizeof(uint32_t), c->stream));
+    LAUNCH_N(k_deg_scatter, n, n, L.row_ptr, c->d_newpos, c->d_deg_new);
+    FL_CK(fl_exclusive_sum(c->d_tmp, c->tmp_bytes, c->d_deg_new, M.row_ptr, n + 1, c->stream, false));
+    LAUNCH_N(k_permute_rows, n, n, L.row_ptr, L.col, L.dist, L.rev, c->d_newpos, M.row_ptr, M.col, M.dist, M.rev);
+    FlNodeArrays a;
+    a.areas = L.areas; a.erod = L.erod; a.uplift = L.uplift; a.tan = c->has_tan ? L.tan : nullptr;
+    a.elev = L.elev; a.drecv = L.drecv;
+    a.areas_n = M.areas; a.erod_n = M.erod; a.uplift_n = M.uplift; a.tan_n = M.tan; a.elev_n = M.elev;
+    a.drecv_n = M.drecv;
+    a.recv = L.recv; a.cmask = L.cmask; a.rank = c->rank_ready ? L.rank : nullptr; a.orig_of = L.orig_of;
+    a.recv_n = M.recv; a.cmask_n = M.cmask; a.rank_n = M.rank; a.orig_of_n = M.orig_of;
+    a.is_outlet = L.is_outlet; a.is_outlet_n = M.is_outlet;
+    LAUNCH_N(k_permute_nodes, n, n, c->d_newpos, a);
+    c->cur ^= 1;
+    if (c->rank_ready) LAUNCH_N(k_rank_inverse, n, n, M.rank, c->d_rank_to_node);
+    FL_CK(fl_stream_sync(c->stream));  // h_offs
+    c->stats.n_order += 14;
+    c->stats.rebuilds++;
+    c->stats.path_levels = c->n_levels;
+    c->stats.paths = c->n_paths;
+    return FASTLEM_OK;
+}
+
+int iterate_paths(fastlem_ctx* c, bool* changed_out) {
+    const uint32_t n = c->n;
+    FL_CK(fl_memset(c->d_flags, 0, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
+    FL_CK(fl_memset(L_(c).cmask, 0, sizeof(uint32_t) * n, c->stream));
+    FL_RC(stage_mark(c, 0));
+    {
+        Layout& L = L_(c);
+        LAUNCH_N(k_receivers_mask, n, n, L.row_ptr, L.col, L.dist, L.rev, L.elev, L.is_outlet, L.recv, L.drecv, L.cmask,
+                 c->d_flags);
+        c->stats.n_receivers++;
     }
+    FL_RC(stage_mark(c, 1));
+    FL_RC(read_flags(c));
+    const bool has_lake = c->h_flags[FL_FLAG_LAKE] != 0;
+    FL_RC(stage_mark(c, 2));
+    c->stages_valid = false;
+    if (has_lake) {
+        Layout& L = L_(c);
+        FL_RC(run_labels(c));
+        FL_RC(run_lakes(c));
+        FL_CK(fl_memset(L.cmask, 0, sizeof(uint32_t) * n, c->stream));
+        LAUNCH_N(k_childmask, n, n, L.row_ptr, L.col, L.rev, L.recv, L.cmask);
+    }
+    FL_RC(stage_mark(c, 3));
+
+    FL_RC(rebuild_layout(c, c->d_A));
+    FL_RC(stage_mark(c, 4));
+
+    Layout& L = L_(c);
+    for (uint32_t lv = c->n_levels; lv-- > 0;) {  // K4: innermost paths first
+        const uint32_t b = c->h_offs[lv], cnt = c->h_offs[lv + 1] - b;
+        if (!cnt) continue;
+        FL_LAUNCH(k_area_paths, blocks_for(cnt, 128), 128, c->stream, b, cnt, c->d_seg_head, c->d_len_sorted, L.row_ptr,
+                  L.col, L.recv, L.cmask, L.areas, c->d_A);
+    }
+    c->stats.kernel_launches += c->n_levels; c->stats.n_area += c->n_levels;
+    FL_RC(stage_mark(c, 5));
+    for (uint32_t lv = 0; lv < c->n_levels; ++lv) {  // K5: root paths first
+        const uint32_t b = c->h_offs[lv], cnt = c->h_offs[lv + 1] - b;
+        if (!cnt) continue;
+        FL_LAUNCH(k_elev_paths, blocks_for(cnt, 128), 128, c->stream, b, cnt, c->d_seg_head, c->d_len_sorted, L.recv,
+                  L.drecv, c->d_A, L.erod, L.uplift, c->has_tan ? L.tan : nullptr, L.is_outlet, L.elev, c->d_rt,
+                  c->d_root_of, c->d_flags);
+    }
+    c->stats.kernel_launches += c->n_levels; c->stats.n_elevation += c->n_levels;
+    FL_RC(stage_mark(c, 6));
+    FL_RC(read_flags(c));
+    FL_CK(fl_last_error());
+    *changed_out = c->h_flags[FL_FLAG_CHANGED] != 0;
+    return profile_accumulate(c);
+}
+
+// start of a run: working numbering = the caller's
+int reset_layout(fastlem_ctx* c) {
+    const uint32_t n = c->n, nnz = c->nnz;
+    c->cur = 0;
+    Layout& L = c->lay[0];
+    const Layout& O = c->orig;
+    FL_CK(fl_d2d(L.row_ptr, O.row_ptr, sizeof(uint32_t) * ((size_t)n + 1), c->stream));
+    if (nnz) {
+        FL_CK(fl_d2d(L.col, O.col, sizeof(uint32_t) * nnz, c->stream));
+        FL_CK(fl_d2d(L.dist, O.dist, sizeof(double) * nnz, c->stream));
+        FL_CK(fl_d2d(L.rev, O.rev, nnz, c->stream));
+    }
+    FL_CK(fl_d2d(L.areas, O.areas, sizeof(double) * n, c->stream));
+    FL_CK(fl_d2d(L.erod, O.erod, sizeof(double) * n, c->stream));
+    FL_CK(fl_d2d(L.uplift, O.uplift, sizeof(double) * n, c->stream));
+    if (c->has_tan) FL_CK(fl_d2d(L.tan, O.tan, sizeof(double) * n, c->stream));
+    FL_CK(fl_d2d(L.is_outlet, O.is_outlet, n, c->stream));
+    FL_CK(fl_d2d(L.elev, c->d_init, sizeof(double) * n, c->stream));
+    LAUNCH_N(k_iota, n, n, L.orig_of);
+    if (c->rank_ready) {
+        FL_CK(fl_d2d(L.rank, O.rank, sizeof(uint32_t) * n, c->stream));
+        FL_CK(fl_memset(c->d_rank_to_node, 0xFF, sizeof(uint32_t) * n, c->stream));
+        LAUNCH_N(k_rank_inverse, n, n, L.rank, c->d_rank_to_node);
+    }
+    c->layout_valid = true;
     return FASTLEM_OK;
 }
 
@@ -279,9 +458,9 @@ extern "C" {
 
 const char* fastlem_version(void) {
 #ifdef FL_EMU
-    return "fastlem_b200 0.1.0 emu";
+    return "fastlem_b200 0.2.0 emu";
 #else
-    return "fastlem_b200 0.1.0 sm_100a";
+    return "fastlem_b200 0.2.0 sm_100a";
 #endif
 }
 
@@ -311,7 +490,9 @@ int fastlem_create(fastlem_ctx** out, int device_ordinal) {
     bool ok = true;
     for (int k = 0; k <= ST_COUNT; ++k) ok = ok && fl_event_create(&c->ev[k]) == cudaSuccess;
     for (int k = 0; k < 2; ++k) ok = ok && fl_event_create(&c->ev_run[k]) == cudaSuccess;
-    c->ev_ok = ok;
+    void* fl = nullptr;
+    ok = ok && fl_malloc(&fl, sizeof(uint32_t) * FL_N_FLAGS) == cudaSuccess;
+    c->d_flags = (uint32_t*)fl;
     if (!ok) {
         fastlem_destroy(c);
         return FASTLEM_E_CUDA;
@@ -323,8 +504,9 @@ int fastlem_create(fastlem_ctx** out, int device_ordinal) {
 void fastlem_destroy(fastlem_ctx* c) {
     if (!c) return;
     fl_set_device(c->device);
-    free_graph(c);
-    dfree(c->d_flags);
+    free_all(c);
+    if (c->d_tmp) fl_free(c->d_tmp);
+    if (c->d_flags) fl_free(c->d_flags);
     if (c->h_flags) fl_free_host(c->h_flags);
     for (int k = 0; k <= ST_COUNT; ++k)
         if (c->ev[k]) fl_event_destroy(c->ev[k]);
@@ -341,8 +523,10 @@ int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
     std::string s(name);
     if (s == "profile") c->opt_profile = value != 0;
     else if (s == "keep_stages") c->opt_keep = value != 0;
-    else if (s == "sweep") c->opt_sweep = value;
-    else return fail(c, FASTLEM_E_INVALID, "unknown option: " + s);
+    else if (s == "sweep") {
+        if (value < 0 || value > 1) return fail(c, FASTLEM_E_INVALID, "option sweep: 0 (levels) or 1 (paths)");
+        c->opt_sweep = value;
+    } else return fail(c, FASTLEM_E_INVALID, "unknown option: " + s);
     return FASTLEM_OK;
 }
 
@@ -350,7 +534,7 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
                       const double* areas) {
     if (!c) return FASTLEM_E_INVALID;
     if (!row_ptr || !areas) return fail(c, FASTLEM_E_INVALID, "set_graph: null pointer");
-    if (n == 0 || n >= FL_NONE) return fail(c, FASTLEM_E_INVALID, "set_graph: n must be in [1, 2^32-2]");
+    if (n == 0 || n >= FL_NONE - 1) return fail(c, FASTLEM_E_INVALID, "set_graph: n must be in [1, 2^32-3]");
     if (row_ptr[0] != 0) return fail(c, FASTLEM_E_INVALID, "set_graph: row_ptr[0] must be 0");
     for (uint32_t i = 0; i < n; ++i)
         if (row_ptr[i + 1] < row_ptr[i]) return fail(c, FASTLEM_E_INVALID, "set_graph: row_ptr must be non-decreasing");
@@ -360,45 +544,75 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
         if (col[s] >= n) return fail(c, FASTLEM_E_INVALID, "set_graph: neighbour index out of range");
     FL_CK(fl_set_device(c->device));
     double t0 = wall_ms();
-    free_graph(c);
+    free_all(c);
     c->n = n;
     c->nnz = nnz;
     c->h_row_ptr = row_ptr; c->h_col = col; c->h_dist = dist;
-    FL_CK(dalloc(c->d_row_ptr, (size_t)n + 1));
-    FL_CK(dalloc(c->d_col, nnz));
-    FL_CK(dalloc(c->d_dist, nnz));
-    FL_CK(dalloc(c->d_areas, n));
-    FL_CK(fl_h2d(c->d_row_ptr, row_ptr, sizeof(uint32_t) * ((size_t)n + 1), c->stream));
-    if (nnz) {
-        FL_CK(fl_h2d(c->d_col, col, sizeof(uint32_t) * nnz, c->stream));
-        FL_CK(fl_h2d(c->d_dist, dist, sizeof(double) * nnz, c->stream));
+    const size_t n1 = (size_t)n + 1;
+    Layout* sets[3] = {&c->orig, &c->lay[0], &c->lay[1]};
+    for (Layout* S : sets) {
+        FL_CK(dalloc(c, S->row_ptr, n1));
+        FL_CK(dalloc(c, S->col, nnz));
+        FL_CK(dalloc(c, S->dist, nnz));
+        FL_CK(dalloc(c, S->rev, nnz));
+        FL_CK(dalloc(c, S->areas, n));
+        FL_CK(dalloc(c, S->erod, n));
+        FL_CK(dalloc(c, S->uplift, n));
+        FL_CK(dalloc(c, S->is_outlet, n));
+        FL_CK(dalloc(c, S->rank, n));
     }
-    FL_CK(fl_h2d(c->d_areas, areas, sizeof(double) * n, c->stream));
-    // state buffers
-    FL_CK(dalloc(c->d_elev, n));
-    FL_CK(dalloc(c->d_recv, n));
-    FL_CK(dalloc(c->d_drecv, n));
-    FL_CK(dalloc(c->d_pd, n));
-    FL_CK(dalloc(c->d_lake_key, n));
-    FL_CK(dalloc(c->d_label, n));
-    FL_CK(dalloc(c->d_depth, n));
-    FL_CK(dalloc(c->d_ids, n));
-    FL_CK(dalloc(c->d_sorted_depth, n));
-    FL_CK(dalloc(c->d_order, n));
-    FL_CK(dalloc(c->d_offs, (size_t)n + 2));
-    FL_CK(dalloc(c->d_A, n));
-    FL_CK(dalloc(c->d_rt, n));
-    FL_CK(dalloc(c->d_recv0, n));
-    FL_CK(dalloc(c->d_label0, n));
-    if (!c->d_flags) FL_CK(dalloc(c->d_flags, FL_N_FLAGS));
+    for (int k = 0; k < 2; ++k) {
+        Layout& S = c->lay[k];
+        FL_CK(dalloc(c, S.orig_of, n));
+        FL_CK(dalloc(c, S.elev, n));
+        FL_CK(dalloc(c, S.drecv, n));
+        FL_CK(dalloc(c, S.recv, n));
+        FL_CK(dalloc(c, S.cmask, n));
+    }
+    FL_CK(fl_h2d(c->orig.row_ptr, row_ptr, sizeof(uint32_t) * n1, c->stream));
+    if (nnz) {
+        FL_CK(fl_h2d(c->orig.col, col, sizeof(uint32_t) * nnz, c->stream));
+        FL_CK(fl_h2d(c->orig.dist, dist, sizeof(double) * nnz, c->stream));
+    }
+    FL_CK(fl_h2d(c->orig.areas, areas, sizeof(double) * n, c->stream));
+    LAUNCH_N(k_rev_slots, n, n, c->orig.row_ptr, c->orig.col, c->orig.rev);
+    FL_CK(dalloc(c, c->d_init, n));
+    FL_CK(dalloc(c, c->d_rank_to_node, n));
+    FL_CK(dalloc(c, c->d_pd, n));
+    FL_CK(dalloc(c, c->d_pd2, n));
+    FL_CK(dalloc(c, c->d_lake_key, n));
+    FL_CK(dalloc(c, c->d_label, n));
+    FL_CK(dalloc(c, c->d_depth, n));
+    FL_CK(dalloc(c, c->d_ids, n));
+    FL_CK(dalloc(c, c->d_sorted, n));
+    FL_CK(dalloc(c, c->d_order, n));
+    FL_CK(dalloc(c, c->d_offs, (size_t)n + 2));
+    FL_CK(dalloc(c, c->d_A, n));
+    FL_CK(dalloc(c, c->d_rt, n));
+    FL_CK(dalloc(c, c->d_root_of, n));
+    FL_CK(dalloc(c, c->d_heavy, n));
+    FL_CK(dalloc(c, c->d_plen, n));
+    FL_CK(dalloc(c, c->d_len_sorted, n));
+    FL_CK(dalloc(c, c->d_hrank, n));
+    FL_CK(dalloc(c, c->d_seg_head, n1));
+    FL_CK(dalloc(c, c->d_newpos, n));
+    FL_CK(dalloc(c, c->d_deg_new, n1));
+    FL_CK(dalloc(c, c->d_out_f64, n));
+    FL_CK(dalloc(c, c->d_out_u32, n));
+    FL_CK(dalloc(c, c->d_recv0, n));
+    FL_CK(dalloc(c, c->d_label0, n));
     void* ho = nullptr;
     FL_CK(fl_malloc_host(&ho, sizeof(uint32_t) * ((size_t)n + 2)));
     c->h_offs = (uint32_t*)ho;
-    c->sort_tmp_bytes = 0;
-    FL_CK(fl_sort_pairs(nullptr, c->sort_tmp_bytes, c->d_depth, c->d_sorted_depth, c->d_ids, c->d_order, n, 32,
-                        c->stream, true));
-    FL_CK(fl_malloc(&c->d_sort_tmp, c->sort_tmp_bytes));
+    // CUB temp storage: the larger of the sort and the scan
+    size_t sort_bytes = 0, scan_bytes = 0;
+    FL_CK(fl_sort_pairs(nullptr, sort_bytes, c->d_depth, c->d_sorted, c->d_ids, c->d_order, n, 32, c->stream, true));
+    FL_CK(fl_exclusive_sum(nullptr, scan_bytes, c->d_deg_new, c->d_seg_head, n + 1, c->stream, true));
+    if (c->d_tmp) { fl_free(c->d_tmp); c->d_tmp = nullptr; }
+    c->tmp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+    FL_CK(fl_malloc(&c->d_tmp, c->tmp_bytes));
     FL_CK(fl_stream_sync(c->stream));
+    FL_CK(fl_last_error());
     c->has_graph = true;
     c->stats = fastlem_stats{};
     c->stats.ms_upload = wall_ms() - t0;
@@ -417,23 +631,22 @@ int fastlem_set_parameters(fastlem_ctx* c, const double* initial_elevation, cons
         if (outlets[k] >= n) return fail(c, FASTLEM_E_INVALID, "set_parameters: outlet index out of range");
     FL_CK(fl_set_device(c->device));
     double t0 = wall_ms();
-    FL_CK(dalloc(c->d_init, n));
-    FL_CK(dalloc(c->d_erod, n));
-    FL_CK(dalloc(c->d_uplift, n));
-    FL_CK(dalloc(c->d_is_outlet, n));
     FL_CK(fl_h2d(c->d_init, initial_elevation, sizeof(double) * n, c->stream));
-    FL_CK(fl_h2d(c->d_erod, erodibility, sizeof(double) * n, c->stream));
-    FL_CK(fl_h2d(c->d_uplift, uplift_rate, sizeof(double) * n, c->stream));
-    if (tan_max_slope) {
-        FL_CK(dalloc(c->d_tan, n));
-        FL_CK(fl_h2d(c->d_tan, tan_max_slope, sizeof(double) * n, c->stream));
-    } else {
-        dfree(c->d_tan);
+    FL_CK(fl_h2d(c->orig.erod, erodibility, sizeof(double) * n, c->stream));
+    FL_CK(fl_h2d(c->orig.uplift, uplift_rate, sizeof(double) * n, c->stream));
+    c->has_tan = tan_max_slope != nullptr;
+    if (c->has_tan) {
+        if (!c->orig.tan) {
+            FL_CK(dalloc(c, c->orig.tan, n));
+            FL_CK(dalloc(c, c->lay[0].tan, n));
+            FL_CK(dalloc(c, c->lay[1].tan, n));
+        }
+        FL_CK(fl_h2d(c->orig.tan, tan_max_slope, sizeof(double) * n, c->stream));
     }
     // stream_tree.rs:101-107 outlet table (static across iterations, so built once)
     std::vector<uint8_t> table(n, 0);
     for (uint32_t k = 0; k < n_outlets; ++k) table[outlets[k]] = 1;
-    FL_CK(fl_h2d(c->d_is_outlet, table.data(), n, c->stream));
+    FL_CK(fl_h2d(c->orig.is_outlet, table.data(), n, c->stream));
     FL_CK(fl_stream_sync(c->stream));
     c->outlets.assign(outlets, outlets + n_outlets);
     c->rank_ready = false;
@@ -447,19 +660,20 @@ int fastlem_run(fastlem_ctx* c, uint32_t max_iteration, uint32_t* iterations_don
     if (!c->has_graph) return fail(c, FASTLEM_E_STATE, "run: model not set (ModelNotSet)");
     if (!c->has_params) return fail(c, FASTLEM_E_STATE, "run: parameters not set (ParametersNotSet)");
     FL_CK(fl_set_device(c->device));
-    const uint32_t n = c->n;
     // reset per-run stats, keep the one-off ones
     double up = c->stats.ms_upload, fr = c->stats.ms_flood_rank;
     c->stats = fastlem_stats{};
     c->stats.ms_upload = up;
     c->stats.ms_flood_rank = fr;
     FL_CK(fl_event_record(c->ev_run[0], c->stream));
-    FL_CK(fl_d2d(c->d_elev, c->d_init, sizeof(double) * n, c->stream));
+    FL_RC(reset_layout(c));
     uint32_t it = 0;
     while (it < max_iteration) {
         bool changed = false;
-        int rc = iterate(c, it == 0, &changed);
-        if (rc) return rc;
+        // The first body runs level-synchronously: it yields the drainage areas that rank the heavy
+        // children of the path layout from the second body on.
+        if (c->opt_sweep == 0 || it == 0) FL_RC(iterate_levels(c, it == 0, &changed));
+        else FL_RC(iterate_paths(c, &changed));
         ++it;
         if (!changed) break;
     }
@@ -473,23 +687,24 @@ int fastlem_run(fastlem_ctx* c, uint32_t max_iteration, uint32_t* iterations_don
     return FASTLEM_OK;
 }
 
-int fastlem_download(fastlem_ctx* c, double* elevations_out) {
-    if (!c || !elevations_out) return FASTLEM_E_INVALID;
-    if (!c->has_graph || !c->has_params) return fail(c, FASTLEM_E_STATE, "download: nothing to download");
+int fastlem_download_to_device(fastlem_ctx* c, double* device_out) {
+    if (!c || !device_out) return FASTLEM_E_INVALID;
+    if (!c->layout_valid) return fail(c, FASTLEM_E_STATE, "download: nothing to download (no run yet)");
     FL_CK(fl_set_device(c->device));
-    double t0 = wall_ms();
-    FL_CK(fl_d2h(elevations_out, c->d_elev, sizeof(double) * c->n, c->stream));
+    LAUNCH_N(k_unpermute_f64, c->n, c->n, L_(c).orig_of, L_(c).elev, device_out);
     FL_CK(fl_stream_sync(c->stream));
-    c->stats.ms_download = wall_ms() - t0;
     return FASTLEM_OK;
 }
 
-int fastlem_download_to_device(fastlem_ctx* c, double* device_out) {
-    if (!c || !device_out) return FASTLEM_E_INVALID;
-    if (!c->has_graph || !c->has_params) return fail(c, FASTLEM_E_STATE, "download: nothing to download");
+int fastlem_download(fastlem_ctx* c, double* elevations_out) {
+    if (!c || !elevations_out) return FASTLEM_E_INVALID;
+    if (!c->layout_valid) return fail(c, FASTLEM_E_STATE, "download: nothing to download (no run yet)");
     FL_CK(fl_set_device(c->device));
-    FL_CK(fl_d2d(device_out, c->d_elev, sizeof(double) * c->n, c->stream));
+    double t0 = wall_ms();
+    LAUNCH_N(k_unpermute_f64, c->n, c->n, L_(c).orig_of, L_(c).elev, c->d_out_f64);
+    FL_CK(fl_d2h(elevations_out, c->d_out_f64, sizeof(double) * c->n, c->stream));
     FL_CK(fl_stream_sync(c->stream));
+    c->stats.ms_download = wall_ms() - t0;
     return FASTLEM_OK;
 }
 
@@ -510,28 +725,66 @@ int fastlem_debug_fetch(fastlem_ctx* c, int stage, void* out, size_t bytes) {
     if (!c || !out) return FASTLEM_E_INVALID;
     if (!c->has_graph || !c->has_params) return fail(c, FASTLEM_E_STATE, "debug_fetch: no run yet");
     FL_CK(fl_set_device(c->device));
-    const size_t n = c->n;
+    const uint32_t n = c->n;
+    if (!c->layout_valid && stage != FASTLEM_STAGE_FLOOD_RANK)
+        return fail(c, FASTLEM_E_STATE, "debug_fetch: no run yet");
+    Layout& L = L_(c);
+    const bool is_f64 = stage == FASTLEM_STAGE_DRAINAGE_AREA || stage == FASTLEM_STAGE_RESPONSE_TIME ||
+                        stage == FASTLEM_STAGE_ELEVATION;
+    if (bytes != (size_t)n * (is_f64 ? 8 : 4)) return fail(c, FASTLEM_E_INVALID, "debug_fetch: wrong buffer size");
+    const uint64_t launches_before = c->stats.kernel_launches;
     const void* src = nullptr;
-    size_t want = 0;
     switch (stage) {
-        case FASTLEM_STAGE_RECEIVERS: src = c->d_recv; want = n * 4; break;
-        case FASTLEM_STAGE_RECEIVERS_INITIAL: src = c->stages_valid ? c->d_recv0 : c->d_recv; want = n * 4; break;
-        case FASTLEM_STAGE_LABELS_INITIAL: src = c->stages_valid ? c->d_label0 : c->d_label; want = n * 4; break;
-        case FASTLEM_STAGE_LABELS: src = c->d_label; want = n * 4; break;
-        case FASTLEM_STAGE_DEPTH: src = c->d_depth; want = n * 4; break;
-        case FASTLEM_STAGE_DRAINAGE_AREA: src = c->d_A; want = n * 8; break;
-        case FASTLEM_STAGE_RESPONSE_TIME: src = c->d_rt; want = n * 8; break;
-        case FASTLEM_STAGE_ELEVATION: src = c->d_elev; want = n * 8; break;
-        case FASTLEM_STAGE_FLOOD_RANK: {
-            int rc = ensure_rank(c);
-            if (rc) return rc;
-            src = c->d_rank; want = n * 4; break;
+        case FASTLEM_STAGE_RECEIVERS:
+            LAUNCH_N(k_unpermute_ids, n, n, L.orig_of, L.recv, c->d_out_u32);
+            src = c->d_out_u32;
+            break;
+        case FASTLEM_STAGE_RECEIVERS_INITIAL:
+            if (c->stages_valid) src = c->d_recv0;
+            else { LAUNCH_N(k_unpermute_ids, n, n, L.orig_of, L.recv, c->d_out_u32); src = c->d_out_u32; }
+            break;
+        case FASTLEM_STAGE_LABELS_INITIAL:
+            if (c->stages_valid) { src = c->d_label0; break; }
+            // no lake removal happened: the initial labels are the final ones
+            // fall through
+        case FASTLEM_STAGE_LABELS:
+        case FASTLEM_STAGE_DEPTH:
+        case FASTLEM_STAGE_DRAINAGE_AREA:
+        case FASTLEM_STAGE_RESPONSE_TIME: {
+            // (root, depth) of the final forest, recomputed here so both sweeps share one definition
+            FL_RC(run_labels(c));
+            LAUNCH_N(k_labels_depth, n, n, c->d_pd, L.is_outlet, c->d_label, c->d_depth);
+            if (stage == FASTLEM_STAGE_DEPTH) {
+                LAUNCH_N(k_unpermute_u32, n, n, L.orig_of, c->d_depth, c->d_out_u32);
+                src = c->d_out_u32;
+            } else if (stage == FASTLEM_STAGE_DRAINAGE_AREA || stage == FASTLEM_STAGE_RESPONSE_TIME) {
+                // sites outside every outlet's basin keep the loop's initial values (generator.rs:144-145)
+                const bool area = stage == FASTLEM_STAGE_DRAINAGE_AREA;
+                LAUNCH_N(k_stage_value, n, n, c->d_depth, area ? c->d_A : c->d_rt, area ? L.areas : nullptr,
+                         c->d_out_f64 /*scratch*/);
+                // d_out_f64 is in the current numbering here; unpermute through d_A-sized scratch d_rt? use d_pd as scratch
+                LAUNCH_N(k_unpermute_f64, n, n, L.orig_of, c->d_out_f64, (double*)c->d_pd2);
+                src = c->d_pd2;
+            } else {
+                LAUNCH_N(k_unpermute_ids, n, n, L.orig_of, c->d_label, c->d_out_u32);
+                src = c->d_out_u32;
+            }
+            break;
         }
+        case FASTLEM_STAGE_ELEVATION:
+            LAUNCH_N(k_unpermute_f64, n, n, L.orig_of, L.elev, c->d_out_f64);
+            src = c->d_out_f64;
+            break;
+        case FASTLEM_STAGE_FLOOD_RANK:
+            FL_RC(ensure_rank(c));
+            src = c->orig.rank;
+            break;
         default: return fail(c, FASTLEM_E_INVALID, "debug_fetch: unknown stage");
     }
-    if (bytes != want) return fail(c, FASTLEM_E_INVALID, "debug_fetch: wrong buffer size");
-    FL_CK(fl_d2h(out, src, want, c->stream));
+    FL_CK(fl_d2h(out, src, bytes, c->stream));
     FL_CK(fl_stream_sync(c->stream));
+    FL_CK(fl_last_error());
+    c->stats.kernel_launches = launches_before;  // debug traffic is not part of the run
     return FASTLEM_OK;
 }
 

@@ -91,7 +91,8 @@ int fastlem_download_to_device(fastlem_ctx* ctx, double* device_elevations_out);
 
 /* Options (all default 0): "profile" = 1 records CUDA events around every stage and fills the ms_*
  * fields of fastlem_stats; "keep_stages" = 1 keeps the pre-lake-removal receivers/labels of the last
- * iteration for fastlem_debug_fetch; "sweep" selects the tree-sweep implementation. */
+ * iteration for fastlem_debug_fetch; "sweep" selects the tree-sweep implementation: 0 = one launch per
+ * tree level, 1 = path-decomposed (default). */
 int fastlem_set_option(fastlem_ctx* ctx, const char* name, int64_t value);
 
 typedef struct fastlem_stats {
@@ -107,6 +108,11 @@ typedef struct fastlem_stats {
     /* "profile"=1 only: summed over the iterations of the last run */
     double ms_receivers, ms_labels, ms_lakes, ms_order, ms_area, ms_elevation;
     uint64_t n_receivers, n_labels, n_lakes, n_order, n_area, n_elevation; /* launches per stage */
+    /* "sweep"=1: path layout of the last iteration */
+    uint32_t rebuilds;    /* layout rebuilds (site renumberings) during the last run */
+    uint32_t path_levels; /* nesting depth of the path decomposition = rounds per sweep */
+    uint32_t paths;       /* number of paths */
+    uint32_t reserved;
 } fastlem_stats;
 int fastlem_get_stats(const fastlem_ctx* ctx, fastlem_stats* out);
 

@@ -96,6 +96,25 @@ def scenario(name, n=None):
                  default_outlets=a["default_outlets"],
                  sites=np.concatenate([a["sites"], b["sites"] + 200.0]))
         return _finish(m, W.uniform_params(m["n"]))
+    if name == "hub":  # one site adjacent to 60 others: rows longer than the 32-bit child mask
+        base = _delaunay(n or 900, seed=21)
+        nn = base["n"]
+        rp = base["row_ptr"].astype(np.int64)
+        rows = [list(zip(base["col"][rp[i]:rp[i + 1]].tolist(), base["dist"][rp[i]:rp[i + 1]].tolist()))
+                for i in range(nn)]
+        hub = nn // 2
+        rng = np.random.default_rng(3)
+        have = {j for j, _ in rows[hub]} | {hub}
+        extra = [int(j) for j in rng.permutation(nn) if int(j) not in have][:60]
+        for j in extra:  # add_edge(hub, j, w): append to both lists
+            w = float(np.hypot(*(base["sites"][hub] - base["sites"][j])))
+            rows[hub].append((j, w))
+            rows[j].append((hub, w))
+        m = dict(base)
+        m["row_ptr"] = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.uint32)
+        m["col"] = np.array([j for r in rows for j, _ in r], dtype=np.uint32)
+        m["dist"] = np.array([w for r in rows for _, w in r], dtype=np.float64)
+        return _finish(m, W.uniform_params(nn))
     if name == "tiny_chain":  # 0 - 1 - 2 - 3, outlet 0
         m = dict(n=4, row_ptr=np.array([0, 1, 3, 5, 6], dtype=np.uint32),
                  col=np.array([1, 0, 2, 1, 3, 2], dtype=np.uint32),
@@ -111,5 +130,5 @@ def scenario(name, n=None):
 
 
 SMALL = ["uniform", "rust_sites", "max_slope", "mixed_slope", "uplift", "advanced", "plateau", "base_field",
-         "lattice", "lattice_regular", "single_outlet", "interior_outlets", "disconnected", "tiny_chain",
+         "lattice", "lattice_regular", "single_outlet", "interior_outlets", "disconnected", "hub", "tiny_chain",
          "isolated_nodes"]

@@ -17,6 +17,9 @@ def _ctx(emu_lib, **opts):
     return ctx
 
 
+SWEEPS = [0, 1]
+
+
 @pytest.mark.parametrize("name", SMALL)
 def test_first_iteration_stages(oracle, emu_lib, name):
     m, p, outlets, initial, _ = scenario(name)
@@ -26,17 +29,43 @@ def test_first_iteration_stages(oracle, emu_lib, name):
         assert exact
 
 
+@pytest.mark.parametrize("sweep", SWEEPS)
 @pytest.mark.parametrize("name", SMALL)
-def test_generate(oracle, emu_lib, name):
+def test_generate(oracle, emu_lib, name, sweep):
     m, p, outlets, initial, max_iteration = scenario(name)
-    with _ctx(emu_lib) as ctx:
+    with _ctx(emu_lib, sweep=sweep) as ctx:
         helpers.load_ctx(ctx, m, p, outlets, initial)
         assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
+        if sweep == 1 and ctx.stats()["iterations"] > 1:
+            assert ctx.stats()["rebuilds"] >= 1
 
 
+@pytest.mark.parametrize("name", ["uniform", "max_slope", "uplift", "disconnected", "hub", "interior_outlets"])
+def test_stages_after_several_iterations_on_paths(oracle, emu_lib, name):
+    """Stage dumps in the path layout (renumbered sites) map back to the caller's numbering."""
+    m, p, outlets, initial, _ = scenario(name)
+    k = 4
+    e = initial.copy()
+    for _ in range(k - 1):
+        e = oracle.iterate_once(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, e)["elevations"]
+    ref = oracle.iterate_once(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, e)
+    with _ctx(emu_lib, sweep=1, keep_stages=1) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        out, it = ctx.generate(k)
+        assert it == k
+        assert np.array_equal(out, ref["elevations"], equal_nan=True)
+        assert np.array_equal(ctx.fetch("receivers"), ref["next"])
+        assert np.array_equal(ctx.fetch("receivers_initial"), ref["next_initial"])
+        assert np.array_equal(ctx.fetch("labels_initial"), ref["subroot"])
+        assert np.array_equal(ctx.fetch("depth") != 0xFFFFFFFF, ref["order"] != oracle.NONE)
+        assert np.array_equal(ctx.fetch("drainage_area"), ref["drainage"])
+        assert np.array_equal(ctx.fetch("response_time"), ref["response"])
+
+
+@pytest.mark.parametrize("sweep", SWEEPS)
 @pytest.mark.parametrize("path", helpers.golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
-def test_golden(emu_lib, path):
-    with _ctx(emu_lib) as ctx:
+def test_golden(emu_lib, path, sweep):
+    with _ctx(emu_lib, sweep=sweep) as ctx:
         helpers.check_against_golden(ctx, path)
 
 

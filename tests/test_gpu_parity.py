@@ -28,17 +28,19 @@ def test_first_iteration_stages(oracle, gpu_ctx_factory, name):
         assert exact, "f64 stages are within tolerance but not bit-identical"
 
 
+@pytest.mark.parametrize("sweep", [0, 1])
 @pytest.mark.parametrize("name", SMALL)
-def test_generate_to_convergence(oracle, gpu_ctx_factory, name):
+def test_generate_to_convergence(oracle, gpu_ctx_factory, name, sweep):
     m, p, outlets, initial, max_iteration = scenario(name)
-    with gpu_ctx_factory() as ctx:
+    with gpu_ctx_factory(sweep=sweep) as ctx:
         helpers.load_ctx(ctx, m, p, outlets, initial)
         assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
 
 
+@pytest.mark.parametrize("sweep", [0, 1])
 @pytest.mark.parametrize("path", helpers.golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
-def test_golden_vectors(gpu_ctx_factory, path):
-    with gpu_ctx_factory() as ctx:
+def test_golden_vectors(gpu_ctx_factory, path, sweep):
+    with gpu_ctx_factory(sweep=sweep) as ctx:
         helpers.check_against_golden(ctx, path)
 
 
@@ -51,6 +53,28 @@ def test_max_iteration(oracle, gpu_ctx_factory, k):
         ref, ref_it = oracle.generate(m, p["erodibility"], p["uplift"], None, outlets, initial, k)
         assert it == ref_it == k
         assert np.array_equal(e, ref)
+
+
+@pytest.mark.parametrize("name", ["uniform", "max_slope", "uplift", "disconnected", "hub", "interior_outlets"])
+def test_stages_after_several_iterations_on_paths(oracle, gpu_ctx_factory, name):
+    """Stage dumps in the path layout (renumbered sites) map back to the caller's numbering."""
+    m, p, outlets, initial, _ = scenario(name)
+    k = 4
+    e = initial.copy()
+    for _ in range(k - 1):
+        e = oracle.iterate_once(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, e)["elevations"]
+    ref = oracle.iterate_once(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, e)
+    with gpu_ctx_factory(sweep=1, keep_stages=1) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        out, it = ctx.generate(k)
+        assert it == k
+        assert np.array_equal(out, ref["elevations"], equal_nan=True)
+        assert np.array_equal(ctx.fetch("receivers"), ref["next"])
+        assert np.array_equal(ctx.fetch("receivers_initial"), ref["next_initial"])
+        assert np.array_equal(ctx.fetch("labels_initial"), ref["subroot"])
+        assert np.array_equal(ctx.fetch("depth") != 0xFFFFFFFF, ref["order"] != oracle.NONE)
+        assert np.array_equal(ctx.fetch("drainage_area"), ref["drainage"])
+        assert np.array_equal(ctx.fetch("response_time"), ref["response"])
 
 
 def test_c1_landscape_evolution_as_shipped(oracle, gpu_ctx_factory):
