@@ -15,6 +15,8 @@
 #pragma once
 #include "fl_kernels.cuh"
 
+#define FL_LONG_PATH 32u  // paths at least this long go to the warp kernels ("sweep" = 2)
+
 // ------------------------------------------------------------------------------------------------
 // static per-graph table: rev[s] = slot of i inside adj(col[s]) (first match), 255 if >= 255 / absent
 // ------------------------------------------------------------------------------------------------
@@ -172,9 +174,11 @@ __global__ void __launch_bounds__(256) k_nest_init(uint32_t n, const uint32_t* _
     pd2[q] = (unsigned long long)(uint32_t)pd[p] | (1ull << 32);
 }
 
-// step 5: sort keys: level for heads, FL_NONE for everything else
+// step 5: sort keys for path heads (FL_NONE for everything else): the nesting level, or with `split`
+// (level * 2 + (path shorter than FL_LONG_PATH)) so that the long paths of a level come first.
 __global__ void __launch_bounds__(256) k_path_keys(uint32_t n, const unsigned long long* __restrict__ pd,
                                                     const unsigned long long* __restrict__ pd2,
+                                                    const uint32_t* __restrict__ plen, int split,
                                                     uint32_t* __restrict__ keys, uint32_t* __restrict__ ids,
                                                     uint32_t* flags) {
     uint32_t q = FL_TID;
@@ -182,8 +186,9 @@ __global__ void __launch_bounds__(256) k_path_keys(uint32_t n, const unsigned lo
     ids[q] = q;
     if ((uint32_t)pd[q] == q) {
         const uint32_t level = (uint32_t)(pd2[q] >> 32);
-        keys[q] = level;
-        if (level > 0) atomicMax(&flags[FL_FLAG_MAXDEPTH], level);
+        const uint32_t key = split ? (level * 2u + (plen[q] < FL_LONG_PATH ? 1u : 0u)) : level;
+        keys[q] = key;
+        if (key > 0) atomicMax(&flags[FL_FLAG_MAXDEPTH], key);
     } else {
         keys[q] = FL_NONE;
     }
@@ -433,3 +438,188 @@ __global__ void __launch_bounds__(128) k_elev_paths(uint32_t begin, uint32_t cou
     }
     if (changed) flags[FL_FLAG_CHANGED] = 1u;
 }
+
+// ================================================================================================
+// Long paths: one WARP per path ("sweep" = 2).  A single thread walking a 1000-site path pays a DRAM/L2
+// round trip per site (~3 us); here the 32 lanes fetch a 32-site chunk of the path together (coalesced,
+// the path is contiguous), every lane prepares its own site's order-independent part, and only the truly
+// sequential double additions run as a 32-step chain over warp shuffles -- in exactly the reference order.
+// ================================================================================================
+
+#ifndef FL_EMU
+#define FL_FULL 0xFFFFFFFFu
+
+__device__ __forceinline__ double fl_shfl(double v, int src) { return __shfl_sync(FL_FULL, v, src); }
+
+// t-th child (0-based) of q AFTER the chain child q+1 in reverse adjacency order (rare overflow path)
+__device__ double fl_post_child_value(uint32_t q, uint32_t t, const uint32_t* __restrict__ row_ptr,
+                                      const uint32_t* __restrict__ col, const uint32_t* __restrict__ recv,
+                                      const uint32_t* __restrict__ cmask, const double* A) {
+    bool seen = false;
+    uint32_t k = 0;
+    double out = 0.0;
+    fl_children_rev(q, row_ptr, col, recv, cmask, [&](uint32_t c) {
+        if (c == q + 1u) { seen = true; return; }
+        if (seen) { if (k == t) out = A[c]; ++k; }
+    });
+    return out;
+}
+
+// K4, warp per long path.  For site q with chain child q+1:
+//   A[q] = ((pre_q + A[q+1]) + post_1) + post_2 ...   pre_q = a_q + children before the chain child (reverse
+//   adjacency order), post_* = children after it.  pre/post are gathered by lane (parallel), the chain
+//   x -> A[q] runs over the lanes in order.
+__global__ void __launch_bounds__(128) k_area_paths_warp(uint32_t begin, uint32_t count,
+                                                          const uint32_t* __restrict__ seg_head,
+                                                          const uint32_t* __restrict__ seg_len,
+                                                          const uint32_t* __restrict__ row_ptr,
+                                                          const uint32_t* __restrict__ col,
+                                                          const uint32_t* __restrict__ recv,
+                                                          const uint32_t* __restrict__ cmask,
+                                                          const double* __restrict__ areas, double* A) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= count) return;
+    const uint32_t h = seg_head[begin + w];
+    const uint32_t last = h + seg_len[begin + w] - 1u;
+    double x = 0.0;
+    for (long long top = last; top >= (long long)h; top -= 32) {
+        const long long qq = top - lane;
+        const bool active = qq >= (long long)h;
+        const uint32_t q = (uint32_t)qq;
+        const bool has_chain = active && q < last;
+        double pre = 0.0, p1 = 0.0, p2 = 0.0;
+        uint32_t np = 0;
+        if (active) {
+            pre = areas[q];
+            bool seen = false;
+            fl_children_rev(q, row_ptr, col, recv, cmask, [&](uint32_t c) {
+                if (has_chain && c == q + 1u) { seen = true; return; }
+                const double v = A[c];
+                if (!seen) pre += v;
+                else { if (np == 0) p1 = v; else if (np == 1) p2 = v; ++np; }
+            });
+        }
+        const int nact = (int)((top - (long long)h + 1) < 32 ? (top - (long long)h + 1) : 32);
+        double mine = 0.0;
+        for (int k = 0; k < nact; ++k) {
+            const double pre_k = fl_shfl(pre, k);
+            const double p1_k = fl_shfl(p1, k);
+            const double p2_k = fl_shfl(p2, k);
+            const uint32_t np_k = __shfl_sync(FL_FULL, np, k);
+            const int hc_k = __shfl_sync(FL_FULL, (int)has_chain, k);
+            double y = hc_k ? (pre_k + x) : pre_k;
+            if (np_k >= 1) y += p1_k;
+            if (np_k >= 2) y += p2_k;
+            for (uint32_t t = 2; t < np_k; ++t) {  // more than two children after the chain child: rare
+                double v = 0.0;
+                if (lane == k) v = fl_post_child_value(q, t, row_ptr, col, recv, cmask, A);
+                y += fl_shfl(v, k);
+            }
+            x = y;
+            if (lane == k) mine = y;
+        }
+        if (active) A[q] = mine;
+    }
+}
+
+// K5, warp per long path (generator.rs:162-203).  t_q = 1/(k_q*sqrt(A_q))*d_q is per-lane work; the response
+// time chain rt_q = 0.0 + (rt_{q-1} + t_q) and (only with max_slope) the clamp chain run over the lanes.
+__global__ void __launch_bounds__(128) k_elev_paths_warp(uint32_t begin, uint32_t count,
+                                                          const uint32_t* __restrict__ seg_head,
+                                                          const uint32_t* __restrict__ seg_len,
+                                                          const uint32_t* __restrict__ recv,
+                                                          const double* __restrict__ drecv,
+                                                          const double* __restrict__ A,
+                                                          const double* __restrict__ erod,
+                                                          const double* __restrict__ uplift,
+                                                          const double* __restrict__ tan_slope,
+                                                          const uint8_t* __restrict__ is_outlet, double* elev,
+                                                          double* rt, uint32_t* root_of,
+                                                          uint32_t* __restrict__ flags) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= count) return;
+    const uint32_t h = seg_head[begin + w];
+    const uint32_t last = h + seg_len[begin + w] - 1u;
+    const uint32_t p = recv[h];
+    uint32_t root, first = h;
+    double rt_prev, z_prev, e_out, rt_out;
+    bool changed = false;
+    if (p == h) {  // tree root: handled by every lane redundantly (uniform), written by lane 0
+        if (!is_outlet[h]) {
+            for (uint32_t q = h + lane; q <= last; q += 32) root_of[q] = FL_NONE;
+            return;
+        }
+        root = h;
+        const double e_old = elev[h];
+        const double rti = 0.0 + (0.0 + 1.0 / (erod[h] * sqrt(A[h])) * drecv[h]);
+        double z = e_old + uplift[h] * fmax(rti - rti, 0.0);
+        if (tan_slope) {
+            const double ms = tan_slope[h];
+            if (ms == ms) {
+                const double d = drecv[h];
+                const double slope = (z - e_old) / d;
+                if (slope > ms) z = e_old + ms * d;
+            }
+        }
+        changed = (z != e_old);
+        __syncwarp();
+        if (lane == 0) { elev[h] = z; rt[h] = rti; root_of[h] = h; }
+        rt_prev = rti; z_prev = z; e_out = z; rt_out = rti;
+        first = h + 1u;
+    } else {
+        root = root_of[p];
+        if (root == FL_NONE) {
+            for (uint32_t q = h + lane; q <= last; q += 32) root_of[q] = FL_NONE;
+            return;
+        }
+        rt_prev = rt[p];
+        z_prev = elev[p];
+        e_out = elev[root];
+        rt_out = rt[root];
+    }
+    for (uint32_t base = first; base <= last; base += 32) {
+        const uint32_t q = base + lane;
+        const bool active = q <= last;
+        double t = 0.0, u = 0.0, zold = 0.0, d = 1.0, ms = 0.0;
+        if (active) {
+            d = drecv[q];
+            t = 1.0 / (erod[q] * sqrt(A[q])) * d;
+            u = uplift[q];
+            zold = elev[q];
+            if (tan_slope) ms = tan_slope[q];
+        }
+        const int nact = (int)((last - base + 1u) < 32u ? (last - base + 1u) : 32u);
+        double my_rt = 0.0;
+        for (int k = 0; k < nact; ++k) {
+            const double t_k = fl_shfl(t, k);
+            rt_prev = 0.0 + (rt_prev + t_k);
+            if (lane == k) my_rt = rt_prev;
+        }
+        double z = e_out + u * fmax(my_rt - rt_out, 0.0);
+        if (tan_slope) {
+            double my_z = z;
+            for (int k = 0; k < nact; ++k) {
+                double z_k = fl_shfl(z, k);
+                const double ms_k = fl_shfl(ms, k);
+                const double d_k = fl_shfl(d, k);
+                if (ms_k == ms_k) {
+                    const double slope = (z_k - z_prev) / d_k;
+                    if (slope > ms_k) z_k = z_prev + ms_k * d_k;
+                }
+                z_prev = z_k;
+                if (lane == k) my_z = z_k;
+            }
+            z = my_z;
+        }
+        if (active) {
+            changed |= (z != zold);
+            elev[q] = z;
+            rt[q] = my_rt;
+            root_of[q] = root;
+        }
+    }
+    if (changed) flags[FL_FLAG_CHANGED] = 1u;
+}
+#endif  // !FL_EMU

@@ -7,7 +7,8 @@
 // Two sweep implementations (option "sweep"):
 //   0  level-synchronous: nodes sorted by tree depth, one launch per level and sweep (simple; launch bound)
 //   1  path-decomposed  : fl_paths.cuh -- the sites are renumbered so that every heavy path is contiguous and
-//                         one thread walks a path; ~20 rounds per sweep instead of ~1000 levels (default)
+//                         one thread walks a path; ~20 rounds per sweep instead of ~1000 levels
+//   2  as 1, and paths of >= FL_LONG_PATH sites are walked by a whole warp (default)
 #include "../../include/fastlem_b200.h"
 
 #include <chrono>
@@ -99,7 +100,7 @@ struct fastlem_ctx {
     uint32_t* d_seg_head = nullptr;  // n+1
     uint32_t* d_newpos = nullptr;
     uint32_t* d_deg_new = nullptr;  // n+1
-    uint32_t n_levels = 0, n_paths = 0;
+    uint32_t n_levels = 0, n_groups = 0, n_paths = 0;  // groups = (level, long/short) buckets of the path list
     // scratch in the caller's numbering (download, debug fetch, kept stages)
     double* d_out_f64 = nullptr;
     uint32_t* d_out_u32 = nullptr;
@@ -114,7 +115,7 @@ struct fastlem_ctx {
     size_t tmp_bytes = 0;
 
     bool opt_profile = false, opt_keep = false;
-    int64_t opt_sweep = 1;
+    int64_t opt_sweep = 2;
 
     fastlem_stats stats{};
     cudaEvent_t ev[ST_COUNT + 1] = {};
@@ -182,13 +183,17 @@ int read_flags(fastlem_ctx* c) {
     return FASTLEM_OK;
 }
 
-// pointer jumping on a packed (pointer, distance) table until stable
+// pointer jumping on a packed (pointer, distance) table until stable.  Rounds go out in batches of three
+// with one flag read-back per batch (the flag is cleared before the batch's last round only, so it tells
+// whether that round still changed anything).
 int jump_loop(fastlem_ctx* c, unsigned long long* pd) {
     const uint32_t n = c->n;
-    for (int round = 0; round < 48; ++round) {
+    for (int batch = 0; batch < 24; ++batch) {
+        LAUNCH_N(k_jump, n, n, pd, c->d_flags);
+        LAUNCH_N(k_jump, n, n, pd, c->d_flags);
         FL_CK(fl_memset(c->d_flags + FL_FLAG_JUMP, 0, sizeof(uint32_t), c->stream));
         LAUNCH_N(k_jump, n, n, pd, c->d_flags);
-        c->stats.n_labels++;
+        c->stats.n_labels += 3;
         FL_RC(read_flags(c));
         if (!c->h_flags[FL_FLAG_JUMP]) return FASTLEM_OK;
     }
@@ -329,20 +334,23 @@ int rebuild_layout(fastlem_ctx* c, const double* weight) {
     LAUNCH_N(k_nest_init, n, n, L.recv, c->d_pd, c->d_pd2);
     FL_RC(jump_loop(c, c->d_pd2));  // -> (root path head, nesting level)
     FL_CK(fl_memset(c->d_flags + FL_FLAG_MAXDEPTH, 0, sizeof(uint32_t), c->stream));
-    LAUNCH_N(k_path_keys, n, n, c->d_pd, c->d_pd2, c->d_depth, c->d_ids, c->d_flags);
+    const int split = c->opt_sweep >= 2 ? 1 : 0;
+    LAUNCH_N(k_path_keys, n, n, c->d_pd, c->d_pd2, c->d_plen, split, c->d_depth, c->d_ids, c->d_flags);
     FL_RC(read_flags(c));
-    const uint32_t max_level = c->h_flags[FL_FLAG_MAXDEPTH];
+    const uint32_t max_key = c->h_flags[FL_FLAG_MAXDEPTH];
     int bits = 1;
-    while (bits < 32 && (1ull << bits) <= (unsigned long long)max_level + 1ull) ++bits;  // FL_NONE sorts last
+    while (bits < 32 && (1ull << bits) <= (unsigned long long)max_key + 1ull) ++bits;  // FL_NONE sorts last
     FL_CK(fl_sort_pairs(c->d_tmp, c->tmp_bytes, c->d_depth, c->d_sorted, c->d_ids, c->d_order, n, bits, c->stream,
                         false));
     FL_CK(fl_memset(c->d_flags + FL_FLAG_MAXDEPTH, 0xFF, sizeof(uint32_t), c->stream));
+    FL_CK(fl_memset(c->d_offs, 0xFF, sizeof(uint32_t) * ((size_t)max_key + 2), c->stream));
     LAUNCH_N(k_level_offsets, n, n, c->d_sorted, c->d_offs, c->d_flags);
     FL_RC(read_flags(c));
-    if (c->h_flags[FL_FLAG_MAXDEPTH] != max_level) return fail(c, FASTLEM_E_STATE, "layout: level bookkeeping broke");
-    c->n_levels = max_level + 1;
+    if (c->h_flags[FL_FLAG_MAXDEPTH] != max_key) return fail(c, FASTLEM_E_STATE, "layout: level bookkeeping broke");
+    c->n_groups = max_key + 1;
+    c->n_levels = split ? (max_key / 2 + 1) : (max_key + 1);
     c->n_paths = c->h_flags[FL_FLAG_REACHED];
-    FL_CK(fl_d2h(c->h_offs, c->d_offs, sizeof(uint32_t) * ((size_t)c->n_levels + 1), c->stream));
+    FL_CK(fl_d2h(c->h_offs, c->d_offs, sizeof(uint32_t) * ((size_t)c->n_groups + 1), c->stream));
 
     LAUNCH_N(k_path_gather, c->n_paths, c->n_paths, c->d_order, c->d_plen, c->d_len_sorted, c->d_hrank);
     FL_CK(fl_exclusive_sum(c->d_tmp, c->tmp_bytes, c->d_len_sorted, c->d_seg_head, c->n_paths, c->stream, false));
@@ -365,6 +373,8 @@ int rebuild_layout(fastlem_ctx* c, const double* weight) {
     c->cur ^= 1;
     if (c->rank_ready) LAUNCH_N(k_rank_inverse, n, n, M.rank, c->d_rank_to_node);
     FL_CK(fl_stream_sync(c->stream));  // h_offs
+    for (uint32_t g = c->n_groups; g-- > 0;)  // keys that do not occur (e.g. a level without long paths)
+        if (c->h_offs[g] == FL_NONE) c->h_offs[g] = c->h_offs[g + 1];
     c->stats.n_order += 14;
     c->stats.rebuilds++;
     c->stats.path_levels = c->n_levels;
@@ -401,22 +411,42 @@ int iterate_paths(fastlem_ctx* c, bool* changed_out) {
     FL_RC(stage_mark(c, 4));
 
     Layout& L = L_(c);
-    for (uint32_t lv = c->n_levels; lv-- > 0;) {  // K4: innermost paths first
-        const uint32_t b = c->h_offs[lv], cnt = c->h_offs[lv + 1] - b;
+    const bool split = c->opt_sweep >= 2;
+    uint32_t launched = 0;
+    for (uint32_t g = c->n_groups; g-- > 0;) {  // K4: innermost paths first
+        const uint32_t b = c->h_offs[g], cnt = c->h_offs[g + 1] - b;
         if (!cnt) continue;
+        ++launched;
+#ifndef FL_EMU
+        if (split && (g & 1u) == 0) {
+            FL_LAUNCH(k_area_paths_warp, blocks_for(cnt * 32u, 128), 128, c->stream, b, cnt, c->d_seg_head,
+                      c->d_len_sorted, L.row_ptr, L.col, L.recv, L.cmask, L.areas, c->d_A);
+            continue;
+        }
+#endif
         FL_LAUNCH(k_area_paths, blocks_for(cnt, 128), 128, c->stream, b, cnt, c->d_seg_head, c->d_len_sorted, L.row_ptr,
                   L.col, L.recv, L.cmask, L.areas, c->d_A);
     }
-    c->stats.kernel_launches += c->n_levels; c->stats.n_area += c->n_levels;
+    c->stats.kernel_launches += launched; c->stats.n_area += launched;
     FL_RC(stage_mark(c, 5));
-    for (uint32_t lv = 0; lv < c->n_levels; ++lv) {  // K5: root paths first
-        const uint32_t b = c->h_offs[lv], cnt = c->h_offs[lv + 1] - b;
+    launched = 0;
+    for (uint32_t g = 0; g < c->n_groups; ++g) {  // K5: root paths first
+        const uint32_t b = c->h_offs[g], cnt = c->h_offs[g + 1] - b;
         if (!cnt) continue;
+        ++launched;
+#ifndef FL_EMU
+        if (split && (g & 1u) == 0) {
+            FL_LAUNCH(k_elev_paths_warp, blocks_for(cnt * 32u, 128), 128, c->stream, b, cnt, c->d_seg_head,
+                      c->d_len_sorted, L.recv, L.drecv, c->d_A, L.erod, L.uplift, c->has_tan ? L.tan : nullptr,
+                      L.is_outlet, L.elev, c->d_rt, c->d_root_of, c->d_flags);
+            continue;
+        }
+#endif
         FL_LAUNCH(k_elev_paths, blocks_for(cnt, 128), 128, c->stream, b, cnt, c->d_seg_head, c->d_len_sorted, L.recv,
                   L.drecv, c->d_A, L.erod, L.uplift, c->has_tan ? L.tan : nullptr, L.is_outlet, L.elev, c->d_rt,
                   c->d_root_of, c->d_flags);
     }
-    c->stats.kernel_launches += c->n_levels; c->stats.n_elevation += c->n_levels;
+    c->stats.kernel_launches += launched; c->stats.n_elevation += launched;
     FL_RC(stage_mark(c, 6));
     FL_RC(read_flags(c));
     FL_CK(fl_last_error());
@@ -524,7 +554,8 @@ int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
     if (s == "profile") c->opt_profile = value != 0;
     else if (s == "keep_stages") c->opt_keep = value != 0;
     else if (s == "sweep") {
-        if (value < 0 || value > 1) return fail(c, FASTLEM_E_INVALID, "option sweep: 0 (levels) or 1 (paths)");
+        if (value < 0 || value > 2)
+            return fail(c, FASTLEM_E_INVALID, "option sweep: 0 (levels), 1 (paths, thread per path), 2 (paths, warp per long path)");
         c->opt_sweep = value;
     } else return fail(c, FASTLEM_E_INVALID, "unknown option: " + s);
     return FASTLEM_OK;

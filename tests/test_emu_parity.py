@@ -17,7 +17,7 @@ def _ctx(emu_lib, **opts):
     return ctx
 
 
-SWEEPS = [0, 1]
+SWEEPS = [0, 1, 2]
 
 
 @pytest.mark.parametrize("name", SMALL)

@@ -28,7 +28,7 @@ def test_first_iteration_stages(oracle, gpu_ctx_factory, name):
         assert exact, "f64 stages are within tolerance but not bit-identical"
 
 
-@pytest.mark.parametrize("sweep", [0, 1])
+@pytest.mark.parametrize("sweep", [0, 1, 2])
 @pytest.mark.parametrize("name", SMALL)
 def test_generate_to_convergence(oracle, gpu_ctx_factory, name, sweep):
     m, p, outlets, initial, max_iteration = scenario(name)
@@ -37,7 +37,7 @@ def test_generate_to_convergence(oracle, gpu_ctx_factory, name, sweep):
         assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
 
 
-@pytest.mark.parametrize("sweep", [0, 1])
+@pytest.mark.parametrize("sweep", [0, 1, 2])
 @pytest.mark.parametrize("path", helpers.golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
 def test_golden_vectors(gpu_ctx_factory, path, sweep):
     with gpu_ctx_factory(sweep=sweep) as ctx:
@@ -55,8 +55,9 @@ def test_max_iteration(oracle, gpu_ctx_factory, k):
         assert np.array_equal(e, ref)
 
 
+@pytest.mark.parametrize("sweep", [1, 2])
 @pytest.mark.parametrize("name", ["uniform", "max_slope", "uplift", "disconnected", "hub", "interior_outlets"])
-def test_stages_after_several_iterations_on_paths(oracle, gpu_ctx_factory, name):
+def test_stages_after_several_iterations_on_paths(oracle, gpu_ctx_factory, name, sweep):
     """Stage dumps in the path layout (renumbered sites) map back to the caller's numbering."""
     m, p, outlets, initial, _ = scenario(name)
     k = 4
@@ -64,7 +65,7 @@ def test_stages_after_several_iterations_on_paths(oracle, gpu_ctx_factory, name)
     for _ in range(k - 1):
         e = oracle.iterate_once(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, e)["elevations"]
     ref = oracle.iterate_once(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, e)
-    with gpu_ctx_factory(sweep=1, keep_stages=1) as ctx:
+    with gpu_ctx_factory(sweep=sweep, keep_stages=1) as ctx:
         helpers.load_ctx(ctx, m, p, outlets, initial)
         out, it = ctx.generate(k)
         assert it == k
@@ -83,6 +84,14 @@ def test_c1_landscape_evolution_as_shipped(oracle, gpu_ctx_factory):
     with gpu_ctx_factory() as ctx:
         helpers.load_ctx(ctx, m, p, outlets, initial)
         helpers.check_first_iteration(ctx, oracle, m, p, outlets, initial)
+        assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, None)
+
+
+def test_max_slope_100k_long_paths(oracle, gpu_ctx_factory):
+    """The clamp chain of the warp-per-path kernel on long paths (tests/landscape_evolution.rs scenario, larger)."""
+    m, p, outlets, initial, _ = scenario("max_slope", 100000)
+    with gpu_ctx_factory() as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
         assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, None)
 
 
