@@ -623,3 +623,266 @@ __global__ void __launch_bounds__(128) k_elev_paths_warp(uint32_t begin, uint32_
     if (changed) flags[FL_FLAG_CHANGED] = 1u;
 }
 #endif  // !FL_EMU
+
+// ================================================================================================
+// "sweep" = 3: dataflow sweeps on DYNAMIC segments.
+//
+// A segment is a maximal run of positions q, q+1, ... with recv[q+1] == q (a chain that is contiguous in the
+// current numbering).  Right after a layout rebuild the segments are exactly the heavy paths; when receivers
+// change in later iterations a chain simply breaks into shorter segments -- nothing else has to be updated,
+// so the numbering can be kept for many iterations and is rebuilt only when it has degraded.
+//
+// K4 (drainage area) runs as ONE launch without any level structure:
+//   * every leaf starts a scan that climbs its segment with the running area in a register;
+//   * a scan that finishes a segment head h (A[h] final) reports to the parent site p = recv[h];
+//     the LAST child of p to report ("last arriver") gathers p's non-chain children in reverse adjacency
+//     order into   pre  = a_p + (children before the chain child)   and   post1, post2 (children after it),
+//     then either resumes the scan that is waiting at p or leaves the values for the scan still to come;
+//   * nobody ever spins: a thread either continues with work that is ready or exits.
+// The additions are the reference's, in the reference's order (generator.rs:154-159).
+// It also yields, per segment head, the nesting height (longest chain of segment hand-offs below it), which
+// orders the top-down sweep exactly for the CURRENT forest.
+// ================================================================================================
+#define FL_ST_COUNT_MASK 0x00FFFFFFu
+#define FL_ST_NP_SHIFT 24
+#define FL_ST_NP_MASK 0x0F000000u
+#define FL_ST_PRE_READY 0x40000000u
+#define FL_ST_SCAN_ARRIVED 0x80000000u
+
+#ifdef FL_EMU
+template <class T> __device__ __forceinline__ T fl_ld_cg(const T* p) { return *p; }
+#else
+template <class T> __device__ __forceinline__ T fl_ld_cg(const T* p) { return __ldcg(p); }
+#endif
+
+struct FlFlow {
+    uint32_t n;
+    const uint32_t* row_ptr;
+    const uint32_t* col;
+    const uint32_t* recv;
+    const uint32_t* cmask;
+    const double* areas;
+    double* A;
+    uint32_t* state;  // zeroed before the launch
+    double* pre;
+    double* post1;
+    double* post2;
+    double* xbuf;     // running area handed over at a waiting site
+    uint32_t* hbuf;   // running nesting height handed over with it
+    uint32_t* hgt;    // out: nesting height for segment heads, FL_NONE elsewhere
+    uint32_t* hpre;   // max height over the non-chain children of a site (+1), written with pre
+    uint32_t* flags;
+};
+
+// non-chain children of p, reverse adjacency order -> pre / posts; returns np (15 = more than two posts)
+__device__ __forceinline__ uint32_t fl_gather_lights(const FlFlow& f, uint32_t p, bool has_chain, double& pre,
+                                                     double& p1, double& p2, uint32_t& hmax) {
+    pre = f.areas[p];
+    p1 = 0.0; p2 = 0.0;
+    uint32_t np = 0;
+    bool seen = false;
+    hmax = 0;
+    const uint32_t s0 = f.row_ptr[p];
+    uint32_t m = f.cmask[p];
+    while (m) {
+        const uint32_t b = 31u - (uint32_t)__clz((int)m);
+        m ^= 1u << b;
+        const uint32_t c = f.col[s0 + b];
+        if (has_chain && c == p + 1u) { seen = true; continue; }
+        const double v = fl_ld_cg(&f.A[c]);
+        const uint32_t hc = fl_ld_cg(&f.hgt[c]) + 1u;
+        if (hc > hmax) hmax = hc;
+        if (!seen) pre += v;
+        else { if (np == 0) p1 = v; else if (np == 1) p2 = v; ++np; }
+    }
+    return np > 2 ? 15u : np;
+}
+
+// slow path for np == 15: add every post child in order
+__device__ double fl_add_posts(const FlFlow& f, uint32_t p, double y) {
+    bool seen = false;
+    const uint32_t s0 = f.row_ptr[p];
+    uint32_t m = f.cmask[p];
+    while (m) {
+        const uint32_t b = 31u - (uint32_t)__clz((int)m);
+        m ^= 1u << b;
+        const uint32_t c = f.col[s0 + b];
+        if (c == p + 1u) { seen = true; continue; }
+        if (seen) y += fl_ld_cg(&f.A[c]);
+    }
+    return y;
+}
+
+__global__ void __launch_bounds__(256) k_area_flow(FlFlow f) {
+    const uint32_t q0 = FL_TID;
+    if (q0 >= f.n) return;
+    // only leaves start a scan (no children at all)
+    if (f.cmask[q0] != 0u) return;
+    uint32_t cur = q0;
+    double x = 0.0;       // finished area of the chain child (valid when has_chain)
+    uint32_t hrun = 0;    // nesting height accumulated along this segment
+    bool has_chain = false;
+    // `resume`: pre/posts of `cur` already in registers (we are the last arriver continuing the scan)
+    bool resume = false;
+    double pre = 0.0, p1 = 0.0, p2 = 0.0;
+    uint32_t np = 0, hp = 0;
+    for (;;) {
+        double y;
+        const uint32_t m = f.cmask[cur];
+        const uint32_t nchild = (uint32_t)__popc(m);
+        const uint32_t nlight = nchild - (has_chain ? 1u : 0u);
+        if (nlight == 0u) {
+            y = has_chain ? (f.areas[cur] + x) : f.areas[cur];
+        } else {
+            if (!resume) {
+                uint32_t s = fl_ld_cg(&f.state[cur]);
+                if (!(s & FL_ST_PRE_READY)) {
+                    f.xbuf[cur] = x;
+                    f.hbuf[cur] = hrun;
+                    __threadfence();
+                    s = atomicOr(&f.state[cur], FL_ST_SCAN_ARRIVED);
+                    if (!(s & FL_ST_PRE_READY)) return;  // the last arriver of `cur` takes over
+                }
+                __threadfence();
+                np = (s & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT;
+                pre = fl_ld_cg(&f.pre[cur]);
+                hp = fl_ld_cg(&f.hpre[cur]);
+                if (np >= 1u) p1 = fl_ld_cg(&f.post1[cur]);
+                if (np >= 2u) p2 = fl_ld_cg(&f.post2[cur]);
+            }
+            resume = false;
+            y = has_chain ? (pre + x) : pre;
+            if (np == 15u) y = fl_add_posts(f, cur, y);
+            else {
+                if (np >= 1u) y += p1;
+                if (np >= 2u) y += p2;
+            }
+            if (hp > hrun) hrun = hp;
+        }
+        f.A[cur] = y;
+        const uint32_t p = f.recv[cur];
+        if (cur > 0u && p == cur - 1u) {  // chained: climb
+            f.hgt[cur] = FL_NONE;
+            x = y;
+            has_chain = true;
+            cur = cur - 1u;
+            continue;
+        }
+        // `cur` is a segment head
+        f.hgt[cur] = hrun;
+        if (p == cur) {  // tree root: its segment has the largest nesting height of the tree
+            if (hrun > 0u) atomicMax(&f.flags[FL_FLAG_MAXDEPTH], hrun);
+            return;
+        }
+        __threadfence();       // publish A[cur], hgt[cur]
+        const uint32_t arrived = (atomicAdd(&f.state[p], 1u) & FL_ST_COUNT_MASK) + 1u;
+        const bool p_has_chain = (p + 1u < f.n) && (f.recv[p + 1u] == p);
+        const uint32_t p_lights = (uint32_t)__popc(f.cmask[p]) - (p_has_chain ? 1u : 0u);
+        if (arrived < p_lights) return;
+        // last arriver at p
+        __threadfence();
+        np = fl_gather_lights(f, p, p_has_chain, pre, p1, p2, hp);
+        if (!p_has_chain) {  // p ends its segment: nobody scans into it, start the scan here
+            cur = p; has_chain = false; x = 0.0; hrun = 0; resume = true;
+            continue;
+        }
+        f.pre[p] = pre;
+        f.hpre[p] = hp;
+        if (np >= 1u && np != 15u) f.post1[p] = p1;
+        if (np >= 2u && np != 15u) f.post2[p] = p2;
+        __threadfence();
+        const uint32_t old = atomicOr(&f.state[p], FL_ST_PRE_READY | (np << FL_ST_NP_SHIFT));
+        if (!(old & FL_ST_SCAN_ARRIVED)) return;  // the scan below p has not arrived yet; it will pick these up
+        __threadfence();
+        x = fl_ld_cg(&f.xbuf[p]);
+        hrun = fl_ld_cg(&f.hbuf[p]);
+        cur = p; has_chain = true; resume = true;
+    }
+}
+
+// K5 on dynamic segments: one thread per segment head, walks while recv[q+1] == q
+__global__ void __launch_bounds__(128) k_elev_flow(uint32_t begin, uint32_t count, uint32_t n,
+                                                    const uint32_t* __restrict__ heads,
+                                                    const uint32_t* __restrict__ recv,
+                                                    const double* __restrict__ drecv, const double* __restrict__ A,
+                                                    const double* __restrict__ erod,
+                                                    const double* __restrict__ uplift,
+                                                    const double* __restrict__ tan_slope,
+                                                    const uint8_t* __restrict__ is_outlet, double* elev, double* rt,
+                                                    uint32_t* root_of, uint32_t* __restrict__ flags) {
+    uint32_t t = FL_TID;
+    if (t >= count) return;
+    const uint32_t h = heads[begin + t];
+    const uint32_t p = recv[h];
+    const bool is_root = (p == h);
+    uint32_t root;
+    double rt_prev, z_prev, e_out, rt_out;
+    if (is_root) {
+        root = is_outlet[h] ? h : FL_NONE;
+        rt_prev = 0.0;
+        z_prev = elev[h];
+        e_out = elev[h];
+        rt_out = 0.0;
+    } else {
+        root = root_of[p];
+        rt_prev = rt[p];
+        z_prev = elev[p];
+        e_out = root != FL_NONE ? elev[root] : 0.0;
+        rt_out = root != FL_NONE ? rt[root] : 0.0;
+    }
+    bool changed = false;
+    for (uint32_t q = h;; ++q) {
+        if (root == FL_NONE) {
+            root_of[q] = FL_NONE;
+        } else {
+            const double d = drecv[q];
+            const double celerity = erod[q] * sqrt(A[q]);
+            const double rti = 0.0 + (rt_prev + 1.0 / celerity * d);
+            if (is_root && q == h) rt_out = rti;
+            double z = e_out + uplift[q] * fmax(rti - rt_out, 0.0);
+            if (tan_slope) {
+                const double ms = tan_slope[q];
+                if (ms == ms) {
+                    const double slope = (z - z_prev) / d;
+                    if (slope > ms) z = z_prev + ms * d;
+                }
+            }
+            changed |= (z != elev[q]);
+            if (is_root && q == h) e_out = z;
+            elev[q] = z;
+            rt[q] = rti;
+            root_of[q] = root;
+            rt_prev = rti;
+            z_prev = z;
+        }
+        if (q + 1u >= n || recv[q + 1u] != q) break;
+    }
+    if (changed) flags[FL_FLAG_CHANGED] = 1u;
+}
+
+// keys for sorting segment heads by descending nesting height: key = maxh - hgt (heads), FL_NONE otherwise
+__global__ void __launch_bounds__(256) k_flow_sort_keys(uint32_t n, const uint32_t* __restrict__ hgt, uint32_t maxh,
+                                                         uint32_t* __restrict__ keys) {
+    uint32_t q = FL_TID;
+    if (q >= n) return;
+    const uint32_t h = hgt[q];
+    keys[q] = (h == FL_NONE) ? FL_NONE : (maxh - h);
+}
+
+// layout rebuild on dynamic segments: exclusive scan input = path length at heads (in index order), 0 elsewhere
+__global__ void __launch_bounds__(256) k_head_lengths(uint32_t n, const unsigned long long* __restrict__ pd,
+                                                       const uint32_t* __restrict__ plen,
+                                                       uint32_t* __restrict__ out) {
+    uint32_t q = FL_TID;
+    if (q >= n) return;
+    out[q] = ((uint32_t)pd[q] == q) ? plen[q] : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_newpos_direct(uint32_t n, const unsigned long long* __restrict__ pd,
+                                                        const uint32_t* __restrict__ starts,
+                                                        uint32_t* __restrict__ newpos) {
+    uint32_t q = FL_TID;
+    if (q >= n) return;
+    const unsigned long long a = pd[q];
+    newpos[q] = starts[(uint32_t)a] + (uint32_t)(a >> 32);
+}

@@ -52,6 +52,7 @@ template <class T> inline T atomicAnd(T* p, T v) { T o = *p; *p = o & v; return 
 inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 inline void __threadfence() {}
 inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
 inline int __ffsll(long long x) { return __builtin_ffsll(x); }
 

@@ -101,6 +101,20 @@ struct fastlem_ctx {
     uint32_t* d_newpos = nullptr;
     uint32_t* d_deg_new = nullptr;  // n+1
     uint32_t n_levels = 0, n_groups = 0, n_paths = 0;  // groups = (level, long/short) buckets of the path list
+    // dataflow sweeps (sweep 3)
+    uint32_t* d_state = nullptr;
+    double* d_pre = nullptr;
+    double* d_post1 = nullptr;
+    double* d_post2 = nullptr;
+    double* d_xbuf = nullptr;
+    uint32_t* d_hbuf = nullptr;
+    uint32_t* d_hgt = nullptr;
+    uint32_t* d_hpre = nullptr;
+    uint32_t* d_iota = nullptr;
+    uint32_t max_degree = 0;
+    uint32_t segs_at_rebuild = 0, maxh_at_rebuild = 0;
+    bool need_rebuild = true;
+    int64_t opt_rebuild_every = 0;  // 0 = adaptive
     // scratch in the caller's numbering (download, debug fetch, kept stages)
     double* d_out_f64 = nullptr;
     uint32_t* d_out_u32 = nullptr;
@@ -115,7 +129,7 @@ struct fastlem_ctx {
     size_t tmp_bytes = 0;
 
     bool opt_profile = false, opt_keep = false;
-    int64_t opt_sweep = 2;
+    int64_t opt_sweep = 3;
 
     fastlem_stats stats{};
     cudaEvent_t ev[ST_COUNT + 1] = {};
@@ -454,6 +468,128 @@ int iterate_paths(fastlem_ctx* c, bool* changed_out) {
     return profile_accumulate(c);
 }
 
+// ------------------------------------------------------------------------------------------------
+// sweep 3: dataflow sweeps on dynamic segments (fl_paths.cuh).  The numbering is rebuilt only when it
+// has degraded; segments are whatever chains are contiguous in the current numbering.
+// ------------------------------------------------------------------------------------------------
+int rebuild_layout_flow(fastlem_ctx* c, const double* weight) {
+    const uint32_t n = c->n;
+    Layout& L = c->lay[c->cur];
+    Layout& M = c->lay[c->cur ^ 1];
+    LAUNCH_N(k_heavy, n, n, L.row_ptr, L.col, L.recv, L.cmask, weight, c->d_heavy);
+    LAUNCH_N(k_chain_init, n, n, L.recv, c->d_heavy, c->d_pd);
+    FL_RC(jump_loop(c, c->d_pd));  // -> (path head, position in path)
+    LAUNCH_N(k_path_len, n, n, c->d_heavy, c->d_pd, c->d_plen);
+    // paths keep the order of their heads; start = exclusive scan of the lengths stored at the heads
+    LAUNCH_N(k_head_lengths, n, n, c->d_pd, c->d_plen, c->d_len_sorted);
+    FL_CK(fl_exclusive_sum(c->d_tmp, c->tmp_bytes, c->d_len_sorted, c->d_seg_head, n, c->stream, false));
+    LAUNCH_N(k_newpos_direct, n, n, c->d_pd, c->d_seg_head, c->d_newpos);
+    FL_CK(fl_memset(c->d_deg_new + n, 0, sizeof(uint32_t), c->stream));
+    LAUNCH_N(k_deg_scatter, n, n, L.row_ptr, c->d_newpos, c->d_deg_new);
+    FL_CK(fl_exclusive_sum(c->d_tmp, c->tmp_bytes, c->d_deg_new, M.row_ptr, n + 1, c->stream, false));
+    LAUNCH_N(k_permute_rows, n, n, L.row_ptr, L.col, L.dist, L.rev, c->d_newpos, M.row_ptr, M.col, M.dist, M.rev);
+    FlNodeArrays a;
+    a.areas = L.areas; a.erod = L.erod; a.uplift = L.uplift; a.tan = c->has_tan ? L.tan : nullptr;
+    a.elev = L.elev; a.drecv = L.drecv;
+    a.areas_n = M.areas; a.erod_n = M.erod; a.uplift_n = M.uplift; a.tan_n = M.tan; a.elev_n = M.elev;
+    a.drecv_n = M.drecv;
+    a.recv = L.recv; a.cmask = L.cmask; a.rank = c->rank_ready ? L.rank : nullptr; a.orig_of = L.orig_of;
+    a.recv_n = M.recv; a.cmask_n = M.cmask; a.rank_n = M.rank; a.orig_of_n = M.orig_of;
+    a.is_outlet = L.is_outlet; a.is_outlet_n = M.is_outlet;
+    LAUNCH_N(k_permute_nodes, n, n, c->d_newpos, a);
+    c->cur ^= 1;
+    if (c->rank_ready) LAUNCH_N(k_rank_inverse, n, n, M.rank, c->d_rank_to_node);
+    c->stats.n_order += 10;
+    c->stats.rebuilds++;
+    return FASTLEM_OK;
+}
+
+int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
+    const uint32_t n = c->n;
+    FL_CK(fl_memset(c->d_flags, 0, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
+    FL_CK(fl_memset(L_(c).cmask, 0, sizeof(uint32_t) * n, c->stream));
+    FL_RC(stage_mark(c, 0));
+    {
+        Layout& L = L_(c);
+        LAUNCH_N(k_receivers_mask, n, n, L.row_ptr, L.col, L.dist, L.rev, L.elev, L.is_outlet, L.recv, L.drecv, L.cmask,
+                 c->d_flags);
+        c->stats.n_receivers++;
+    }
+    FL_RC(stage_mark(c, 1));
+    FL_RC(read_flags(c));
+    const bool has_lake = c->h_flags[FL_FLAG_LAKE] != 0;
+    FL_RC(stage_mark(c, 2));
+    c->stages_valid = false;
+    if (has_lake) {
+        Layout& L = L_(c);
+        FL_RC(run_labels(c));
+        FL_RC(run_lakes(c));
+        FL_CK(fl_memset(L.cmask, 0, sizeof(uint32_t) * n, c->stream));
+        LAUNCH_N(k_childmask, n, n, L.row_ptr, L.col, L.rev, L.recv, L.cmask);
+    }
+    FL_RC(stage_mark(c, 3));
+
+    const bool periodic = c->opt_rebuild_every > 0 && (it % (uint32_t)c->opt_rebuild_every) == 0;
+    const bool rebuilt = c->need_rebuild || periodic || c->opt_rebuild_every == 1;
+    if (rebuilt) FL_RC(rebuild_layout_flow(c, c->d_A));
+    c->need_rebuild = false;
+    Layout& L = L_(c);
+
+    // K4: one dataflow launch
+    FL_CK(fl_memset(c->d_state, 0, sizeof(uint32_t) * n, c->stream));
+    FlFlow f;
+    f.n = n; f.row_ptr = L.row_ptr; f.col = L.col; f.recv = L.recv; f.cmask = L.cmask; f.areas = L.areas;
+    f.A = c->d_A; f.state = c->d_state; f.pre = c->d_pre; f.post1 = c->d_post1; f.post2 = c->d_post2;
+    f.xbuf = c->d_xbuf; f.hbuf = c->d_hbuf; f.hgt = c->d_hgt; f.hpre = c->d_hpre; f.flags = c->d_flags;
+    LAUNCH_N(k_area_flow, n, f);
+    c->stats.n_area++;
+    FL_RC(stage_mark(c, 4));
+
+    // order the segment heads by descending nesting height (exact for the current forest)
+    FL_RC(read_flags(c));
+    const uint32_t maxh = c->h_flags[FL_FLAG_MAXDEPTH];
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) <= (unsigned long long)maxh + 1ull) ++bits;
+    LAUNCH_N(k_flow_sort_keys, n, n, c->d_hgt, maxh, c->d_depth);
+    FL_CK(fl_sort_pairs(c->d_tmp, c->tmp_bytes, c->d_depth, c->d_sorted, c->d_iota, c->d_order, n, bits, c->stream,
+                        false));
+    FL_CK(fl_memset(c->d_flags + FL_FLAG_MAXDEPTH, 0xFF, sizeof(uint32_t), c->stream));
+    FL_CK(fl_memset(c->d_offs, 0xFF, sizeof(uint32_t) * ((size_t)maxh + 2), c->stream));
+    LAUNCH_N(k_level_offsets, n, n, c->d_sorted, c->d_offs, c->d_flags);
+    FL_CK(fl_d2h(c->h_offs, c->d_offs, sizeof(uint32_t) * ((size_t)maxh + 2), c->stream));
+    FL_RC(read_flags(c));
+    if (c->h_flags[FL_FLAG_MAXDEPTH] != maxh) return fail(c, FASTLEM_E_STATE, "flow: height bookkeeping broke");
+    const uint32_t n_heads = c->h_flags[FL_FLAG_REACHED];
+    for (uint32_t g = maxh + 1; g-- > 0;)
+        if (c->h_offs[g] == FL_NONE) c->h_offs[g] = c->h_offs[g + 1];
+    c->stats.n_order += 3;
+    c->stats.path_levels = maxh + 1;
+    c->stats.paths = n_heads;
+    if (rebuilt) { c->segs_at_rebuild = n_heads; c->maxh_at_rebuild = maxh; }
+    else if (c->opt_rebuild_every == 0 &&
+             ((unsigned long long)n_heads * 100ull > (unsigned long long)c->segs_at_rebuild * 104ull ||
+              maxh > c->maxh_at_rebuild + c->maxh_at_rebuild / 2 + 2))
+        c->need_rebuild = true;  // the numbering has degraded: renumber in the next iteration
+    FL_RC(stage_mark(c, 5));
+
+    // K5: one launch per nesting height, outermost segments first
+    uint32_t launched = 0;
+    for (uint32_t g = 0; g <= maxh; ++g) {
+        const uint32_t b = c->h_offs[g], cnt = c->h_offs[g + 1] - b;
+        if (!cnt) continue;
+        ++launched;
+        FL_LAUNCH(k_elev_flow, blocks_for(cnt, 128), 128, c->stream, b, cnt, n, c->d_order, L.recv, L.drecv, c->d_A,
+                  L.erod, L.uplift, c->has_tan ? L.tan : nullptr, L.is_outlet, L.elev, c->d_rt, c->d_root_of,
+                  c->d_flags);
+    }
+    c->stats.kernel_launches += launched; c->stats.n_elevation += launched;
+    FL_RC(stage_mark(c, 6));
+    FL_RC(read_flags(c));
+    FL_CK(fl_last_error());
+    *changed_out = c->h_flags[FL_FLAG_CHANGED] != 0;
+    return profile_accumulate(c);
+}
+
 // start of a run: working numbering = the caller's
 int reset_layout(fastlem_ctx* c) {
     const uint32_t n = c->n, nnz = c->nnz;
@@ -554,9 +690,13 @@ int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
     if (s == "profile") c->opt_profile = value != 0;
     else if (s == "keep_stages") c->opt_keep = value != 0;
     else if (s == "sweep") {
-        if (value < 0 || value > 2)
-            return fail(c, FASTLEM_E_INVALID, "option sweep: 0 (levels), 1 (paths, thread per path), 2 (paths, warp per long path)");
+        if (value < 0 || value > 3)
+            return fail(c, FASTLEM_E_INVALID,
+                        "option sweep: 0 (levels), 1 (paths, thread per path), 2 (paths, warp per long path), 3 (dataflow)");
         c->opt_sweep = value;
+    } else if (s == "rebuild_every") {
+        if (value < 0) return fail(c, FASTLEM_E_INVALID, "option rebuild_every: 0 (adaptive) or a positive period");
+        c->opt_rebuild_every = value;
     } else return fail(c, FASTLEM_E_INVALID, "unknown option: " + s);
     return FASTLEM_OK;
 }
@@ -628,6 +768,21 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     FL_CK(dalloc(c, c->d_seg_head, n1));
     FL_CK(dalloc(c, c->d_newpos, n));
     FL_CK(dalloc(c, c->d_deg_new, n1));
+    FL_CK(dalloc(c, c->d_state, n));
+    FL_CK(dalloc(c, c->d_pre, n));
+    FL_CK(dalloc(c, c->d_post1, n));
+    FL_CK(dalloc(c, c->d_post2, n));
+    FL_CK(dalloc(c, c->d_xbuf, n));
+    FL_CK(dalloc(c, c->d_hbuf, n));
+    FL_CK(dalloc(c, c->d_hgt, n));
+    FL_CK(dalloc(c, c->d_hpre, n));
+    FL_CK(dalloc(c, c->d_iota, n));
+    LAUNCH_N(k_iota, n, n, c->d_iota);
+    c->max_degree = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t d = row_ptr[i + 1] - row_ptr[i];
+        if (d > c->max_degree) c->max_degree = d;
+    }
     FL_CK(dalloc(c, c->d_out_f64, n));
     FL_CK(dalloc(c, c->d_out_u32, n));
     FL_CK(dalloc(c, c->d_recv0, n));
@@ -698,12 +853,14 @@ int fastlem_run(fastlem_ctx* c, uint32_t max_iteration, uint32_t* iterations_don
     c->stats.ms_flood_rank = fr;
     FL_CK(fl_event_record(c->ev_run[0], c->stream));
     FL_RC(reset_layout(c));
+    c->need_rebuild = true;
     uint32_t it = 0;
     while (it < max_iteration) {
         bool changed = false;
         // The first body runs level-synchronously: it yields the drainage areas that rank the heavy
         // children of the path layout from the second body on.
         if (c->opt_sweep == 0 || it == 0) FL_RC(iterate_levels(c, it == 0, &changed));
+        else if (c->opt_sweep == 3 && c->max_degree <= 32) FL_RC(iterate_flow(c, it, &changed));
         else FL_RC(iterate_paths(c, &changed));
         ++it;
         if (!changed) break;

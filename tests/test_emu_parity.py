@@ -17,7 +17,7 @@ def _ctx(emu_lib, **opts):
     return ctx
 
 
-SWEEPS = [0, 1, 2]
+SWEEPS = [0, 1, 2, 3]
 
 
 @pytest.mark.parametrize("name", SMALL)
@@ -40,8 +40,9 @@ def test_generate(oracle, emu_lib, name, sweep):
             assert ctx.stats()["rebuilds"] >= 1
 
 
+@pytest.mark.parametrize("sweep", [1, 3])
 @pytest.mark.parametrize("name", ["uniform", "max_slope", "uplift", "disconnected", "hub", "interior_outlets"])
-def test_stages_after_several_iterations_on_paths(oracle, emu_lib, name):
+def test_stages_after_several_iterations_on_paths(oracle, emu_lib, name, sweep):
     """Stage dumps in the path layout (renumbered sites) map back to the caller's numbering."""
     m, p, outlets, initial, _ = scenario(name)
     k = 4
@@ -49,7 +50,7 @@ def test_stages_after_several_iterations_on_paths(oracle, emu_lib, name):
     for _ in range(k - 1):
         e = oracle.iterate_once(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, e)["elevations"]
     ref = oracle.iterate_once(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, e)
-    with _ctx(emu_lib, sweep=1, keep_stages=1) as ctx:
+    with _ctx(emu_lib, sweep=sweep, keep_stages=1) as ctx:
         helpers.load_ctx(ctx, m, p, outlets, initial)
         out, it = ctx.generate(k)
         assert it == k
@@ -67,6 +68,17 @@ def test_stages_after_several_iterations_on_paths(oracle, emu_lib, name):
 def test_golden(emu_lib, path, sweep):
     with _ctx(emu_lib, sweep=sweep) as ctx:
         helpers.check_against_golden(ctx, path)
+
+
+@pytest.mark.parametrize("every", [0, 1, 3, 1000])
+@pytest.mark.parametrize("name", ["uniform", "max_slope", "uplift", "advanced", "disconnected", "lattice_regular"])
+def test_dataflow_sweeps_on_stale_numbering(oracle, emu_lib, name, every):
+    """sweep 3 keeps a site numbering for several iterations; segments are whatever chains are still contiguous.
+    rebuild_every: 0 adaptive, 1 every iteration, 3 every third, 1000 never after the first."""
+    m, p, outlets, initial, max_iteration = scenario(name)
+    with _ctx(emu_lib, sweep=3, rebuild_every=every) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
 
 
 @pytest.mark.parametrize("k", [0, 1, 3])

@@ -28,7 +28,7 @@ def test_first_iteration_stages(oracle, gpu_ctx_factory, name):
         assert exact, "f64 stages are within tolerance but not bit-identical"
 
 
-@pytest.mark.parametrize("sweep", [0, 1, 2])
+@pytest.mark.parametrize("sweep", [0, 1, 2, 3])
 @pytest.mark.parametrize("name", SMALL)
 def test_generate_to_convergence(oracle, gpu_ctx_factory, name, sweep):
     m, p, outlets, initial, max_iteration = scenario(name)
@@ -37,11 +37,34 @@ def test_generate_to_convergence(oracle, gpu_ctx_factory, name, sweep):
         assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
 
 
-@pytest.mark.parametrize("sweep", [0, 1, 2])
+@pytest.mark.parametrize("sweep", [0, 1, 2, 3])
 @pytest.mark.parametrize("path", helpers.golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
 def test_golden_vectors(gpu_ctx_factory, path, sweep):
     with gpu_ctx_factory(sweep=sweep) as ctx:
         helpers.check_against_golden(ctx, path)
+
+
+@pytest.mark.parametrize("every", [0, 1, 3, 1000])
+@pytest.mark.parametrize("name", ["uniform", "max_slope", "uplift", "advanced", "disconnected", "lattice_regular"])
+def test_dataflow_sweeps_on_stale_numbering(oracle, gpu_ctx_factory, name, every):
+    """sweep 3 keeps a site numbering for several iterations; segments are whatever chains are still contiguous.
+    rebuild_every: 0 adaptive, 1 every iteration, 3 every third, 1000 never after the first."""
+    m, p, outlets, initial, max_iteration = scenario(name)
+    with gpu_ctx_factory(sweep=3, rebuild_every=every) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
+
+
+@pytest.mark.parametrize("n", [30000, 200000])
+def test_dataflow_sweeps_repeatable_at_size(oracle, gpu_ctx_factory, n):
+    """The dataflow kernel's hand-offs race differently from run to run; results must not."""
+    m, p, outlets, initial, _ = scenario("uniform", n)
+    ref, ref_it = oracle.generate(m, p["erodibility"], p["uplift"], None, outlets, initial)
+    with gpu_ctx_factory(sweep=3) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        for _ in range(3):
+            e, it = ctx.generate()
+            assert it == ref_it and np.array_equal(e, ref)
 
 
 @pytest.mark.parametrize("k", [0, 1, 2, 5])
@@ -55,7 +78,7 @@ def test_max_iteration(oracle, gpu_ctx_factory, k):
         assert np.array_equal(e, ref)
 
 
-@pytest.mark.parametrize("sweep", [1, 2])
+@pytest.mark.parametrize("sweep", [1, 2, 3])
 @pytest.mark.parametrize("name", ["uniform", "max_slope", "uplift", "disconnected", "hub", "interior_outlets"])
 def test_stages_after_several_iterations_on_paths(oracle, gpu_ctx_factory, name, sweep):
     """Stage dumps in the path layout (renumbered sites) map back to the caller's numbering."""
