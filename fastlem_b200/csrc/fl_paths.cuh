@@ -651,9 +651,17 @@ __global__ void __launch_bounds__(128) k_elev_paths_warp(uint32_t begin, uint32_
 
 #ifdef FL_EMU
 template <class T> __device__ __forceinline__ T fl_ld_cg(const T* p) { return *p; }
+__device__ __forceinline__ uint32_t fl_ld_acquire(const uint32_t* p) { return *p; }
 #else
 template <class T> __device__ __forceinline__ T fl_ld_cg(const T* p) { return __ldcg(p); }
+// acquire load: later loads of this thread (pre / posts) are ordered after it
+__device__ __forceinline__ uint32_t fl_ld_acquire(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 #endif
+#define FL_BATCH 8
 
 struct FlFlow {
     uint32_t n;
@@ -727,59 +735,129 @@ __global__ void __launch_bounds__(256) k_area_flow(FlFlow f) {
     double pre = 0.0, p1 = 0.0, p2 = 0.0;
     uint32_t np = 0, hp = 0;
     for (;;) {
-        double y;
-        const uint32_t m = f.cmask[cur];
-        const uint32_t nchild = (uint32_t)__popc(m);
-        const uint32_t nlight = nchild - (has_chain ? 1u : 0u);
-        if (nlight == 0u) {
-            y = has_chain ? (f.areas[cur] + x) : f.areas[cur];
-        } else {
-            if (!resume) {
-                uint32_t s = fl_ld_cg(&f.state[cur]);
-                if (!(s & FL_ST_PRE_READY)) {
-                    f.xbuf[cur] = x;
-                    f.hbuf[cur] = hrun;
-                    __threadfence();
-                    s = atomicOr(&f.state[cur], FL_ST_SCAN_ARRIVED);
-                    if (!(s & FL_ST_PRE_READY)) return;  // the last arriver of `cur` takes over
+        double y = 0.0;
+        uint32_t p = FL_NONE;
+        bool at_head = false;
+        // ---- fast path: up to FL_BATCH consecutive sites of the chain, every load issued up front ----
+        if (!resume) {
+            const uint32_t nb = cur + 1u < (uint32_t)FL_BATCH ? cur + 1u : (uint32_t)FL_BATCH;
+            uint32_t cm[FL_BATCH], rc[FL_BATCH], st[FL_BATCH], hq[FL_BATCH];
+            double ar[FL_BATCH], pr[FL_BATCH], q1[FL_BATCH], q2[FL_BATCH];
+#pragma unroll
+            for (int k = 0; k < FL_BATCH; ++k) {
+                cm[k] = 0u; rc[k] = FL_NONE; ar[k] = 0.0;
+                if ((uint32_t)k < nb) { cm[k] = f.cmask[cur - k]; rc[k] = f.recv[cur - k]; ar[k] = f.areas[cur - k]; }
+            }
+#pragma unroll
+            for (int k = 0; k < FL_BATCH; ++k) {
+                st[k] = 0u;
+                const uint32_t nl = (uint32_t)__popc(cm[k]) - ((k > 0 || has_chain) ? 1u : 0u);
+                if ((uint32_t)k < nb && cm[k] != 0u && nl > 0u) st[k] = fl_ld_acquire(&f.state[cur - k]);
+            }
+#pragma unroll
+            for (int k = 0; k < FL_BATCH; ++k) {
+                pr[k] = 0.0; q1[k] = 0.0; q2[k] = 0.0; hq[k] = 0u;
+                if (st[k] & FL_ST_PRE_READY) {
+                    const uint32_t npk = (st[k] & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT;
+                    pr[k] = fl_ld_cg(&f.pre[cur - k]);
+                    hq[k] = fl_ld_cg(&f.hpre[cur - k]);
+                    if (npk >= 1u && npk != 15u) q1[k] = fl_ld_cg(&f.post1[cur - k]);
+                    if (npk >= 2u && npk != 15u) q2[k] = fl_ld_cg(&f.post2[cur - k]);
                 }
-                __threadfence();
-                np = (s & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT;
-                pre = fl_ld_cg(&f.pre[cur]);
-                hp = fl_ld_cg(&f.hpre[cur]);
-                if (np >= 1u) p1 = fl_ld_cg(&f.post1[cur]);
-                if (np >= 2u) p2 = fl_ld_cg(&f.post2[cur]);
             }
-            resume = false;
-            y = has_chain ? (pre + x) : pre;
-            if (np == 15u) y = fl_add_posts(f, cur, y);
-            else {
-                if (np >= 1u) y += p1;
-                if (np >= 2u) y += p2;
+            uint32_t done = 0;  // sites of the batch finished and climbed past
+#pragma unroll
+            for (int k = 0; k < FL_BATCH; ++k) {
+                if (!at_head && done == (uint32_t)k && (uint32_t)k < nb) {
+                    const uint32_t idx = cur - k;
+                    const bool hc = (k > 0) || has_chain;
+                    const uint32_t nl = (uint32_t)__popc(cm[k]) - (hc ? 1u : 0u);
+                    bool ok = true;
+                    if (nl == 0u) {
+                        y = hc ? (ar[k] + x) : ar[k];
+                    } else if (st[k] & FL_ST_PRE_READY) {
+                        const uint32_t npk = (st[k] & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT;
+                        y = hc ? (pr[k] + x) : pr[k];
+                        if (npk == 15u) y = fl_add_posts(f, idx, y);
+                        else {
+                            if (npk >= 1u) y += q1[k];
+                            if (npk >= 2u) y += q2[k];
+                        }
+                        if (hq[k] > hrun) hrun = hq[k];
+                    } else {
+                        ok = false;  // children of idx still running: take the hand-off path below
+                    }
+                    if (ok) {
+                        f.A[idx] = y;
+                        if (idx > 0u && rc[k] == idx - 1u) {
+                            f.hgt[idx] = FL_NONE;
+                            x = y;
+                            done = (uint32_t)k + 1u;
+                        } else {
+                            at_head = true;
+                            p = rc[k];
+                        }
+                    }
+                }
             }
-            if (hp > hrun) hrun = hp;
+            if (done > 0u) has_chain = true;
+            cur -= done;
+            if (!at_head && done == nb) continue;  // whole batch climbed: next batch
         }
-        f.A[cur] = y;
-        const uint32_t p = f.recv[cur];
-        if (cur > 0u && p == cur - 1u) {  // chained: climb
-            f.hgt[cur] = FL_NONE;
-            x = y;
-            has_chain = true;
-            cur = cur - 1u;
-            continue;
+        if (!at_head) {
+            // ---- general path for one site: wait for / take over from its children ----
+            const uint32_t m = f.cmask[cur];
+            const uint32_t nlight = (uint32_t)__popc(m) - (has_chain ? 1u : 0u);
+            if (nlight == 0u) {
+                y = has_chain ? (f.areas[cur] + x) : f.areas[cur];
+            } else {
+                if (!resume) {
+                    uint32_t s = fl_ld_acquire(&f.state[cur]);
+                    if (!(s & FL_ST_PRE_READY)) {
+                        f.xbuf[cur] = x;
+                        f.hbuf[cur] = hrun;
+                        __threadfence();
+                        s = atomicOr(&f.state[cur], FL_ST_SCAN_ARRIVED);
+                        if (!(s & FL_ST_PRE_READY)) return;  // the last arriver of `cur` takes over
+                    }
+                    __threadfence();
+                    np = (s & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT;
+                    pre = fl_ld_cg(&f.pre[cur]);
+                    hp = fl_ld_cg(&f.hpre[cur]);
+                    if (np >= 1u && np != 15u) p1 = fl_ld_cg(&f.post1[cur]);
+                    if (np >= 2u && np != 15u) p2 = fl_ld_cg(&f.post2[cur]);
+                }
+                resume = false;
+                y = has_chain ? (pre + x) : pre;
+                if (np == 15u) y = fl_add_posts(f, cur, y);
+                else {
+                    if (np >= 1u) y += p1;
+                    if (np >= 2u) y += p2;
+                }
+                if (hp > hrun) hrun = hp;
+            }
+            f.A[cur] = y;
+            p = f.recv[cur];
+            if (cur > 0u && p == cur - 1u) {  // chained: climb
+                f.hgt[cur] = FL_NONE;
+                x = y;
+                has_chain = true;
+                cur = cur - 1u;
+                continue;
+            }
         }
-        // `cur` is a segment head
+        // ---- `cur` is a segment head with final area y; p = recv[cur] ----
         f.hgt[cur] = hrun;
         if (p == cur) {  // tree root: its segment has the largest nesting height of the tree
             if (hrun > 0u) atomicMax(&f.flags[FL_FLAG_MAXDEPTH], hrun);
             return;
         }
-        __threadfence();       // publish A[cur], hgt[cur]
+        __threadfence();  // publish A[cur], hgt[cur]
         const uint32_t arrived = (atomicAdd(&f.state[p], 1u) & FL_ST_COUNT_MASK) + 1u;
         const bool p_has_chain = (p + 1u < f.n) && (f.recv[p + 1u] == p);
         const uint32_t p_lights = (uint32_t)__popc(f.cmask[p]) - (p_has_chain ? 1u : 0u);
         if (arrived < p_lights) return;
-        // last arriver at p
+        // last arriver at p: gather p's non-chain children
         __threadfence();
         np = fl_gather_lights(f, p, p_has_chain, pre, p1, p2, hp);
         if (!p_has_chain) {  // p ends its segment: nobody scans into it, start the scan here
@@ -800,64 +878,109 @@ __global__ void __launch_bounds__(256) k_area_flow(FlFlow f) {
     }
 }
 
-// K5 on dynamic segments: one thread per segment head, walks while recv[q+1] == q
-__global__ void __launch_bounds__(128) k_elev_flow(uint32_t begin, uint32_t count, uint32_t n,
-                                                    const uint32_t* __restrict__ heads,
-                                                    const uint32_t* __restrict__ recv,
-                                                    const double* __restrict__ drecv, const double* __restrict__ A,
-                                                    const double* __restrict__ erod,
-                                                    const double* __restrict__ uplift,
-                                                    const double* __restrict__ tan_slope,
-                                                    const uint8_t* __restrict__ is_outlet, double* elev, double* rt,
-                                                    uint32_t* root_of, uint32_t* __restrict__ flags) {
+// K5 on dynamic segments: one thread per segment head, walks while recv[q+1] == q.  Sites are taken in
+// batches (4, then 8): all loads of a batch are issued together and the per-site celerity terms
+// t = 1/(k*sqrt(A))*d are computed side by side, so that only the running additions are serial.
+struct FlElev {
+    uint32_t n;
+    const uint32_t* recv;
+    const double* drecv;
+    const double* A;
+    const double* erod;
+    const double* uplift;
+    const double* tan_slope;  // may be null
+    const uint8_t* is_outlet;
+    double* elev;
+    double* rt;
+    uint32_t* root_of;
+    uint32_t* flags;
+};
+
+template <int B>
+__device__ __forceinline__ bool fl_elev_batch(const FlElev& e, uint32_t& q, uint32_t h, bool is_root, uint32_t root,
+                                              double& rt_prev, double& z_prev, double& e_out, double& rt_out,
+                                              bool& changed) {
+    // returns true when the segment ended inside this batch
+    const uint32_t nb = e.n - q < (uint32_t)B ? e.n - q : (uint32_t)B;
+    double d[B], t[B], up[B], eo[B], ms[B];
+    uint32_t nx[B];
+#pragma unroll
+    for (int k = 0; k < B; ++k) {
+        d[k] = 1.0; t[k] = 1.0; up[k] = 0.0; eo[k] = 0.0; ms[k] = 0.0; nx[k] = FL_NONE;
+        if ((uint32_t)k < nb) {
+            const uint32_t i = q + k;
+            d[k] = e.drecv[i];
+            t[k] = e.erod[i] * sqrt(e.A[i]);
+            up[k] = e.uplift[i];
+            eo[k] = e.elev[i];
+            if (e.tan_slope) ms[k] = e.tan_slope[i];
+            nx[k] = (i + 1u < e.n) ? e.recv[i + 1u] : FL_NONE;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < B; ++k) t[k] = 1.0 / t[k] * d[k];
+    bool ended = false;
+#pragma unroll
+    for (int k = 0; k < B; ++k) {
+        if (!ended && (uint32_t)k < nb) {
+            const uint32_t i = q + k;
+            const double rti = 0.0 + (rt_prev + t[k]);
+            if (is_root && i == h) rt_out = rti;
+            double z = e_out + up[k] * fmax(rti - rt_out, 0.0);
+            if (e.tan_slope) {
+                if (ms[k] == ms[k]) {
+                    const double slope = (z - z_prev) / d[k];
+                    if (slope > ms[k]) z = z_prev + ms[k] * d[k];
+                }
+            }
+            changed |= (z != eo[k]);
+            if (is_root && i == h) e_out = z;
+            e.elev[i] = z;
+            e.rt[i] = rti;
+            e.root_of[i] = root;
+            rt_prev = rti;
+            z_prev = z;
+            if (nx[k] != i) ended = true;
+        }
+    }
+    q += nb;
+    return ended || q >= e.n;
+}
+
+__global__ void __launch_bounds__(128) k_elev_flow(uint32_t begin, uint32_t count,
+                                                    const uint32_t* __restrict__ heads, FlElev e) {
     uint32_t t = FL_TID;
     if (t >= count) return;
     const uint32_t h = heads[begin + t];
-    const uint32_t p = recv[h];
+    const uint32_t p = e.recv[h];
     const bool is_root = (p == h);
     uint32_t root;
     double rt_prev, z_prev, e_out, rt_out;
     if (is_root) {
-        root = is_outlet[h] ? h : FL_NONE;
+        root = e.is_outlet[h] ? h : FL_NONE;
         rt_prev = 0.0;
-        z_prev = elev[h];
-        e_out = elev[h];
+        z_prev = e.elev[h];  // has_edge(i,i) is false: the clamp compares with the site's own old elevation
+        e_out = e.elev[h];
         rt_out = 0.0;
     } else {
-        root = root_of[p];
-        rt_prev = rt[p];
-        z_prev = elev[p];
-        e_out = root != FL_NONE ? elev[root] : 0.0;
-        rt_out = root != FL_NONE ? rt[root] : 0.0;
+        root = e.root_of[p];
+        rt_prev = e.rt[p];
+        z_prev = e.elev[p];  // the receiver already holds its NEW elevation
+        e_out = root != FL_NONE ? e.elev[root] : 0.0;
+        rt_out = root != FL_NONE ? e.rt[root] : 0.0;
+    }
+    if (root == FL_NONE) {  // tree without outlet: never visited (generator.rs:149)
+        for (uint32_t q = h;; ++q) {
+            e.root_of[q] = FL_NONE;
+            if (q + 1u >= e.n || e.recv[q + 1u] != q) break;
+        }
+        return;
     }
     bool changed = false;
-    for (uint32_t q = h;; ++q) {
-        if (root == FL_NONE) {
-            root_of[q] = FL_NONE;
-        } else {
-            const double d = drecv[q];
-            const double celerity = erod[q] * sqrt(A[q]);
-            const double rti = 0.0 + (rt_prev + 1.0 / celerity * d);
-            if (is_root && q == h) rt_out = rti;
-            double z = e_out + uplift[q] * fmax(rti - rt_out, 0.0);
-            if (tan_slope) {
-                const double ms = tan_slope[q];
-                if (ms == ms) {
-                    const double slope = (z - z_prev) / d;
-                    if (slope > ms) z = z_prev + ms * d;
-                }
-            }
-            changed |= (z != elev[q]);
-            if (is_root && q == h) e_out = z;
-            elev[q] = z;
-            rt[q] = rti;
-            root_of[q] = root;
-            rt_prev = rti;
-            z_prev = z;
-        }
-        if (q + 1u >= n || recv[q + 1u] != q) break;
-    }
-    if (changed) flags[FL_FLAG_CHANGED] = 1u;
+    uint32_t q = h;
+    if (!fl_elev_batch<4>(e, q, h, is_root, root, rt_prev, z_prev, e_out, rt_out, changed))
+        while (!fl_elev_batch<8>(e, q, h, is_root, root, rt_prev, z_prev, e_out, rt_out, changed)) {}
+    if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
 }
 
 // keys for sorting segment heads by descending nesting height: key = maxh - hgt (heads), FL_NONE otherwise

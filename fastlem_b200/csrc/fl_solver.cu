@@ -573,14 +573,16 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     FL_RC(stage_mark(c, 5));
 
     // K5: one launch per nesting height, outermost segments first
+    FlElev e;
+    e.n = n; e.recv = L.recv; e.drecv = L.drecv; e.A = c->d_A; e.erod = L.erod; e.uplift = L.uplift;
+    e.tan_slope = c->has_tan ? L.tan : nullptr; e.is_outlet = L.is_outlet; e.elev = L.elev; e.rt = c->d_rt;
+    e.root_of = c->d_root_of; e.flags = c->d_flags;
     uint32_t launched = 0;
     for (uint32_t g = 0; g <= maxh; ++g) {
         const uint32_t b = c->h_offs[g], cnt = c->h_offs[g + 1] - b;
         if (!cnt) continue;
         ++launched;
-        FL_LAUNCH(k_elev_flow, blocks_for(cnt, 128), 128, c->stream, b, cnt, n, c->d_order, L.recv, L.drecv, c->d_A,
-                  L.erod, L.uplift, c->has_tan ? L.tan : nullptr, L.is_outlet, L.elev, c->d_rt, c->d_root_of,
-                  c->d_flags);
+        FL_LAUNCH(k_elev_flow, blocks_for(cnt, 128), 128, c->stream, b, cnt, c->d_order, e);
     }
     c->stats.kernel_launches += launched; c->stats.n_elevation += launched;
     FL_RC(stage_mark(c, 6));
