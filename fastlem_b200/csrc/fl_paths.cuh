@@ -661,6 +661,16 @@ __device__ __forceinline__ uint32_t fl_ld_acquire(const uint32_t* p) {
     return v;
 }
 #endif
+// relaxed (pipelinable) load of a flag word; order later loads with one __threadfence() per batch
+#ifdef FL_EMU
+__device__ __forceinline__ uint32_t fl_ld_relaxed(const uint32_t* p) { return *p; }
+#else
+__device__ __forceinline__ uint32_t fl_ld_relaxed(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+#endif
 #define FL_BATCH 8
 
 struct FlFlow {
@@ -752,7 +762,13 @@ __global__ void __launch_bounds__(256) k_area_flow(FlFlow f) {
             for (int k = 0; k < FL_BATCH; ++k) {
                 st[k] = 0u;
                 const uint32_t nl = (uint32_t)__popc(cm[k]) - ((k > 0 || has_chain) ? 1u : 0u);
-                if ((uint32_t)k < nb && cm[k] != 0u && nl > 0u) st[k] = fl_ld_acquire(&f.state[cur - k]);
+                if ((uint32_t)k < nb && cm[k] != 0u && nl > 0u) st[k] = fl_ld_relaxed(&f.state[cur - k]);
+            }
+            {
+                uint32_t any = 0u;
+#pragma unroll
+                for (int k = 0; k < FL_BATCH; ++k) any |= st[k];
+                if (any & FL_ST_PRE_READY) __threadfence();  // acquire: pre/posts are read after the flags
             }
 #pragma unroll
             for (int k = 0; k < FL_BATCH; ++k) {
@@ -885,6 +901,7 @@ struct FlElev {
     uint32_t n;
     const uint32_t* recv;
     const double* drecv;
+    const double* tcel;  // 1/(k*sqrt(A))*d per site (k_celerity_term)
     const double* A;
     const double* erod;
     const double* uplift;
@@ -895,6 +912,17 @@ struct FlElev {
     uint32_t* root_of;
     uint32_t* flags;
 };
+
+// generator.rs:172-173: celerity = k_i * A_i^0.5;  term = 1.0 / celerity * d_i  (fully parallel; the
+// division and square root stay out of the serial scans)
+__global__ void __launch_bounds__(256) k_celerity_term(uint32_t n, const double* __restrict__ erod,
+                                                        const double* __restrict__ A,
+                                                        const double* __restrict__ drecv, double* __restrict__ tcel) {
+    uint32_t q = FL_TID;
+    if (q >= n) return;
+    const double celerity = erod[q] * sqrt(A[q]);
+    tcel[q] = 1.0 / celerity * drecv[q];
+}
 
 template <int B>
 __device__ __forceinline__ bool fl_elev_batch(const FlElev& e, uint32_t& q, uint32_t h, bool is_root, uint32_t root,
@@ -909,16 +937,14 @@ __device__ __forceinline__ bool fl_elev_batch(const FlElev& e, uint32_t& q, uint
         d[k] = 1.0; t[k] = 1.0; up[k] = 0.0; eo[k] = 0.0; ms[k] = 0.0; nx[k] = FL_NONE;
         if ((uint32_t)k < nb) {
             const uint32_t i = q + k;
-            d[k] = e.drecv[i];
-            t[k] = e.erod[i] * sqrt(e.A[i]);
+            if (e.tan_slope) d[k] = e.drecv[i];
+            t[k] = e.tcel[i];
             up[k] = e.uplift[i];
             eo[k] = e.elev[i];
             if (e.tan_slope) ms[k] = e.tan_slope[i];
             nx[k] = (i + 1u < e.n) ? e.recv[i + 1u] : FL_NONE;
         }
     }
-#pragma unroll
-    for (int k = 0; k < B; ++k) t[k] = 1.0 / t[k] * d[k];
     bool ended = false;
 #pragma unroll
     for (int k = 0; k < B; ++k) {

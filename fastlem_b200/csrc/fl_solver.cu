@@ -574,7 +574,8 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
 
     // K5: one launch per nesting height, outermost segments first
     FlElev e;
-    e.n = n; e.recv = L.recv; e.drecv = L.drecv; e.A = c->d_A; e.erod = L.erod; e.uplift = L.uplift;
+    LAUNCH_N(k_celerity_term, n, n, L.erod, c->d_A, L.drecv, c->d_pre);  // d_pre is free again after K4
+    e.n = n; e.recv = L.recv; e.drecv = L.drecv; e.tcel = c->d_pre; e.A = c->d_A; e.erod = L.erod; e.uplift = L.uplift;
     e.tan_slope = c->has_tan ? L.tan : nullptr; e.is_outlet = L.is_outlet; e.elev = L.elev; e.rt = c->d_rt;
     e.root_of = c->d_root_of; e.flags = c->d_flags;
     uint32_t launched = 0;
