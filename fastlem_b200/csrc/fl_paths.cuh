@@ -16,6 +16,10 @@
 #include "fl_kernels.cuh"
 
 #define FL_LONG_PATH 32u  // paths at least this long go to the warp kernels ("sweep" = 2)
+#ifndef FL_EMU
+#define FL_FULL 0xFFFFFFFFu
+__device__ __forceinline__ double fl_shfl(double v, int src) { return __shfl_sync(FL_FULL, v, src); }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // static per-graph table: rev[s] = slot of i inside adj(col[s]) (first match), 255 if >= 255 / absent
@@ -447,10 +451,6 @@ __global__ void __launch_bounds__(128) k_elev_paths(uint32_t begin, uint32_t cou
 // ================================================================================================
 
 #ifndef FL_EMU
-#define FL_FULL 0xFFFFFFFFu
-
-__device__ __forceinline__ double fl_shfl(double v, int src) { return __shfl_sync(FL_FULL, v, src); }
-
 // t-th child (0-based) of q AFTER the chain child q+1 in reverse adjacency order (rare overflow path)
 __device__ double fl_post_child_value(uint32_t q, uint32_t t, const uint32_t* __restrict__ row_ptr,
                                       const uint32_t* __restrict__ col, const uint32_t* __restrict__ recv,
@@ -690,6 +690,9 @@ struct FlFlow {
     uint32_t* hgt;    // out: nesting height for segment heads, FL_NONE elsewhere
     uint32_t* hpre;   // max height over the non-chain children of a site (+1), written with pre
     uint32_t* flags;
+    uint32_t* parked;    // sites where a long scan was parked for the warp-level pass
+    uint32_t* counters;  // [0] = number of parked scans, [1] = next one to take
+    uint32_t park_after; // a thread parks its scan after climbing this many sites in a row (0 = never)
 };
 
 // non-chain children of p, reverse adjacency order -> pre / posts; returns np (15 = more than two posts)
@@ -731,15 +734,10 @@ __device__ double fl_add_posts(const FlFlow& f, uint32_t p, double y) {
     return y;
 }
 
-__global__ void __launch_bounds__(256) k_area_flow(FlFlow f) {
-    const uint32_t q0 = FL_TID;
-    if (q0 >= f.n) return;
-    // only leaves start a scan (no children at all)
-    if (f.cmask[q0] != 0u) return;
-    uint32_t cur = q0;
-    double x = 0.0;       // finished area of the chain child (valid when has_chain)
-    uint32_t hrun = 0;    // nesting height accumulated along this segment
-    bool has_chain = false;
+// One thread follows one flow: climb, report to the parent, possibly take over as last arriver, ...
+__device__ void fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t hrun, bool has_chain, bool may_park) {
+    // x: finished area of the chain child (valid when has_chain); hrun: nesting height along this segment
+    uint32_t climbed = 0;  // sites climbed through the fast path without a break
     // `resume`: pre/posts of `cur` already in registers (we are the last arriver continuing the scan)
     bool resume = false;
     double pre = 0.0, p1 = 0.0, p2 = 0.0;
@@ -818,7 +816,18 @@ __global__ void __launch_bounds__(256) k_area_flow(FlFlow f) {
             }
             if (done > 0u) has_chain = true;
             cur -= done;
-            if (!at_head && done == nb) continue;  // whole batch climbed: next batch
+            if (!at_head && done == nb) {  // whole batch climbed
+                climbed += done;
+                if (may_park && f.park_after != 0u && climbed >= f.park_after) {
+                    // a long chain: leave it to the warp-level pass (k_area_flow_long)
+                    f.xbuf[cur] = x;
+                    f.hbuf[cur] = hrun;
+                    f.parked[atomicAdd(&f.counters[0], 1u)] = cur;
+                    return;
+                }
+                continue;  // next batch
+            }
+            climbed = 0;
         }
         if (!at_head) {
             // ---- general path for one site: wait for / take over from its children ----
@@ -892,6 +901,213 @@ __global__ void __launch_bounds__(256) k_area_flow(FlFlow f) {
         hrun = fl_ld_cg(&f.hbuf[p]);
         cur = p; has_chain = true; resume = true;
     }
+}
+
+// pass 1: every leaf starts a thread-level flow
+__global__ void __launch_bounds__(256) k_area_flow(FlFlow f) {
+    const uint32_t q0 = FL_TID;
+    if (q0 >= f.n) return;
+    if (f.cmask[q0] != 0u) return;  // only leaves (no children at all) start a scan
+    fl_flow_thread(f, q0, 0.0, 0u, false, true);
+}
+
+#ifndef FL_EMU
+__device__ __forceinline__ uint32_t fl_warp_max(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t w = __shfl_xor_sync(FL_FULL, v, o);
+        v = w > v ? w : v;
+    }
+    return v;
+}
+
+// One WARP follows one flow.  All lanes hold identical copies of the flow state; a 32-site window of the
+// chain is fetched by the lanes together, the additions run as a chain over shuffles.
+__device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t hrun, bool has_chain) {
+    const int lane = threadIdx.x & 31;
+    bool resume = false;
+    double pre = 0.0, p1 = 0.0, p2 = 0.0;
+    uint32_t np = 0, hp = 0;
+    for (;;) {
+        double y = 0.0;
+        uint32_t p = FL_NONE;
+        bool at_head = false;
+        if (!resume) {
+            const long long li = (long long)cur - lane;
+            const bool valid = li >= 0;
+            const uint32_t idx = (uint32_t)li;
+            uint32_t cm = 0u, rc = FL_NONE;
+            double ar = 0.0;
+            if (valid) { cm = f.cmask[idx]; rc = f.recv[idx]; ar = f.areas[idx]; }
+            const uint32_t rc_up = __shfl_up_sync(FL_FULL, rc, 1);
+            const bool link = valid && (lane == 0 || rc_up == idx);
+            const uint32_t linkmask = __ballot_sync(FL_FULL, link);
+            const uint32_t nchain = linkmask == FL_FULL ? 32u : (uint32_t)__ffs((int)~linkmask) - 1u;
+            const bool hc = (lane > 0) || has_chain;
+            const bool inwin = (uint32_t)lane < nchain;
+            const uint32_t nl = inwin ? (uint32_t)__popc(cm) - (hc ? 1u : 0u) : 0u;
+            uint32_t st = 0u;
+            if (inwin && nl > 0u) st = fl_ld_relaxed(&f.state[idx]);
+            const bool ready = inwin && (nl == 0u || (st & FL_ST_PRE_READY));
+            const uint32_t readymask = __ballot_sync(FL_FULL, ready);
+            const uint32_t nproc = readymask == FL_FULL ? 32u : (uint32_t)__ffs((int)~readymask) - 1u;
+            const bool mine_lit = (uint32_t)lane < nproc && nl > 0u;
+            if (__ballot_sync(FL_FULL, mine_lit)) __threadfence();  // acquire before reading pre/posts
+            double b = ar, q1 = 0.0, q2 = 0.0;
+            uint32_t npk = 0u, hq = 0u;
+            if (mine_lit) {
+                npk = (st & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT;
+                b = fl_ld_cg(&f.pre[idx]);
+                hq = fl_ld_cg(&f.hpre[idx]);
+                if (npk >= 1u && npk != 15u) q1 = fl_ld_cg(&f.post1[idx]);
+                if (npk >= 2u && npk != 15u) q2 = fl_ld_cg(&f.post2[idx]);
+            }
+            double mine = 0.0;
+            for (uint32_t k = 0; k < nproc; ++k) {
+                const double bk = fl_shfl(b, (int)k);
+                const double q1k = fl_shfl(q1, (int)k);
+                const double q2k = fl_shfl(q2, (int)k);
+                const uint32_t npk_k = __shfl_sync(FL_FULL, npk, (int)k);
+                double yy = ((k > 0u) || has_chain) ? (bk + x) : bk;
+                if (npk_k == 15u) {
+                    double v = 0.0;
+                    if ((uint32_t)lane == k) v = fl_add_posts(f, idx, yy);
+                    __syncwarp();
+                    yy = fl_shfl(v, (int)k);
+                } else {
+                    if (npk_k >= 1u) yy += q1k;
+                    if (npk_k >= 2u) yy += q2k;
+                }
+                x = yy;
+                if ((uint32_t)lane == k) mine = yy;
+            }
+            const uint32_t hw = fl_warp_max((uint32_t)lane < nproc ? hq : 0u);
+            if (hw > hrun) hrun = hw;
+            const bool climbs = valid && idx > 0u && rc == idx - 1u;
+            if ((uint32_t)lane < nproc) {
+                f.A[idx] = mine;
+                if (climbs) f.hgt[idx] = FL_NONE;
+            }
+            if (nproc > 0u) {
+                const int lastl = (int)nproc - 1;
+                const int last_climbs = __shfl_sync(FL_FULL, (int)climbs, lastl);
+                if (!last_climbs) {
+                    at_head = true;
+                    y = fl_shfl(mine, lastl);
+                    p = __shfl_sync(FL_FULL, rc, lastl);
+                    cur -= (uint32_t)lastl;
+                } else {
+                    has_chain = true;
+                    cur -= nproc;
+                    if (nproc == 32u) continue;  // whole window climbed
+                }
+            }
+        }
+        if (!at_head) {
+            // general path for the single site `cur` (uniform across the warp; lane 0 does the side effects)
+            const uint32_t nlight = (uint32_t)__popc(f.cmask[cur]) - (has_chain ? 1u : 0u);
+            if (nlight == 0u) {
+                y = has_chain ? (f.areas[cur] + x) : f.areas[cur];
+            } else {
+                if (!resume) {
+                    uint32_t sv = 0u;
+                    if (lane == 0) {
+                        sv = fl_ld_acquire(&f.state[cur]);
+                        if (!(sv & FL_ST_PRE_READY)) {
+                            f.xbuf[cur] = x;
+                            f.hbuf[cur] = hrun;
+                            __threadfence();
+                            sv = atomicOr(&f.state[cur], FL_ST_SCAN_ARRIVED);
+                        }
+                    }
+                    sv = __shfl_sync(FL_FULL, sv, 0);
+                    if (!(sv & FL_ST_PRE_READY)) return;  // the last arriver of `cur` takes over
+                    __threadfence();
+                    np = (sv & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT;
+                    pre = fl_ld_cg(&f.pre[cur]);
+                    hp = fl_ld_cg(&f.hpre[cur]);
+                    if (np >= 1u && np != 15u) p1 = fl_ld_cg(&f.post1[cur]);
+                    if (np >= 2u && np != 15u) p2 = fl_ld_cg(&f.post2[cur]);
+                }
+                resume = false;
+                y = has_chain ? (pre + x) : pre;
+                if (np == 15u) y = fl_add_posts(f, cur, y);
+                else {
+                    if (np >= 1u) y += p1;
+                    if (np >= 2u) y += p2;
+                }
+                if (hp > hrun) hrun = hp;
+            }
+            if (lane == 0) f.A[cur] = y;
+            p = f.recv[cur];
+            if (cur > 0u && p == cur - 1u) {
+                if (lane == 0) f.hgt[cur] = FL_NONE;
+                x = y;
+                has_chain = true;
+                cur = cur - 1u;
+                continue;
+            }
+        }
+        // `cur` is a segment head with final area y
+        if (lane == 0) f.hgt[cur] = hrun;
+        if (p == cur) {
+            if (lane == 0 && hrun > 0u) atomicMax(&f.flags[FL_FLAG_MAXDEPTH], hrun);
+            return;
+        }
+        uint32_t arrived = 0u;
+        if (lane == 0) {
+            __threadfence();
+            arrived = (atomicAdd(&f.state[p], 1u) & FL_ST_COUNT_MASK) + 1u;
+        }
+        arrived = __shfl_sync(FL_FULL, arrived, 0);
+        const bool p_has_chain = (p + 1u < f.n) && (f.recv[p + 1u] == p);
+        const uint32_t p_lights = (uint32_t)__popc(f.cmask[p]) - (p_has_chain ? 1u : 0u);
+        if (arrived < p_lights) return;
+        __threadfence();
+        np = fl_gather_lights(f, p, p_has_chain, pre, p1, p2, hp);  // uniform addresses: every lane, same values
+        if (!p_has_chain) {
+            cur = p; has_chain = false; x = 0.0; hrun = 0; resume = true;
+            continue;
+        }
+        uint32_t old = 0u;
+        if (lane == 0) {
+            f.pre[p] = pre;
+            f.hpre[p] = hp;
+            if (np >= 1u && np != 15u) f.post1[p] = p1;
+            if (np >= 2u && np != 15u) f.post2[p] = p2;
+            __threadfence();
+            old = atomicOr(&f.state[p], FL_ST_PRE_READY | (np << FL_ST_NP_SHIFT));
+        }
+        old = __shfl_sync(FL_FULL, old, 0);
+        if (!(old & FL_ST_SCAN_ARRIVED)) return;
+        __threadfence();
+        x = fl_ld_cg(&f.xbuf[p]);
+        hrun = fl_ld_cg(&f.hbuf[p]);
+        cur = p; has_chain = true; resume = true;
+    }
+}
+#endif
+
+// pass 2: the parked (long) scans.  Persistent: every warp (emulation: thread) takes parked scans until none is left.
+__global__ void __launch_bounds__(256) k_area_flow_long(FlFlow f) {
+#ifdef FL_EMU
+    for (;;) {
+        const uint32_t i = atomicAdd(&f.counters[1], 1u);
+        if (i >= f.counters[0]) return;
+        const uint32_t cur = f.parked[i];
+        fl_flow_thread(f, cur, f.xbuf[cur], f.hbuf[cur], true, false);
+    }
+#else
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t i = 0u;
+        if (lane == 0) i = atomicAdd(&f.counters[1], 1u);
+        i = __shfl_sync(FL_FULL, i, 0);
+        if (i >= fl_ld_cg(&f.counters[0])) return;
+        const uint32_t cur = f.parked[i];
+        fl_flow_warp(f, cur, fl_ld_cg(&f.xbuf[cur]), fl_ld_cg(&f.hbuf[cur]), true);
+    }
+#endif
 }
 
 // K5 on dynamic segments: one thread per segment head, walks while recv[q+1] == q.  Sites are taken in
@@ -973,39 +1189,123 @@ __device__ __forceinline__ bool fl_elev_batch(const FlElev& e, uint32_t& q, uint
     return ended || q >= e.n;
 }
 
+#ifndef FL_EMU
+// rest of a long segment, walked by the whole warp: 32-site windows, shuffle chains.  Returns "changed".
+__device__ bool fl_elev_warp(const FlElev& e, uint32_t q, uint32_t root, double rt_prev, double z_prev, double e_out,
+                             double rt_out) {
+    const int lane = threadIdx.x & 31;
+    bool changed = false;
+    for (;;) {
+        const uint32_t i = q + (uint32_t)lane;
+        const bool valid = i < e.n;
+        double t = 0.0, up = 0.0, eold = 0.0, ms = 0.0, d = 1.0;
+        uint32_t nx = FL_NONE;
+        if (valid) {
+            t = e.tcel[i];
+            up = e.uplift[i];
+            eold = e.elev[i];
+            nx = (i + 1u < e.n) ? e.recv[i + 1u] : FL_NONE;
+            if (e.tan_slope) { ms = e.tan_slope[i]; d = e.drecv[i]; }
+        }
+        const uint32_t endmask = __ballot_sync(FL_FULL, !valid || nx != i);
+        uint32_t nproc = 32u;
+        if (endmask) {
+            const int el = __ffs((int)endmask) - 1;
+            const int el_valid = __shfl_sync(FL_FULL, (int)valid, el);
+            nproc = (uint32_t)el + (el_valid ? 1u : 0u);
+        }
+        double my_rt = 0.0;
+        for (uint32_t k = 0; k < nproc; ++k) {
+            const double tk = fl_shfl(t, (int)k);
+            rt_prev = 0.0 + (rt_prev + tk);
+            if ((uint32_t)lane == k) my_rt = rt_prev;
+        }
+        double z = e_out + up * fmax(my_rt - rt_out, 0.0);
+        if (e.tan_slope) {
+            double my_z = z;
+            for (uint32_t k = 0; k < nproc; ++k) {
+                double zk = fl_shfl(z, (int)k);
+                const double msk = fl_shfl(ms, (int)k);
+                const double dk = fl_shfl(d, (int)k);
+                if (msk == msk) {
+                    const double slope = (zk - z_prev) / dk;
+                    if (slope > msk) zk = z_prev + msk * dk;
+                }
+                z_prev = zk;
+                if ((uint32_t)lane == k) my_z = zk;
+            }
+            z = my_z;
+        }
+        if ((uint32_t)lane < nproc) {
+            changed |= (z != eold);
+            e.elev[i] = z;
+            e.rt[i] = my_rt;
+            e.root_of[i] = root;
+        }
+        q += nproc;
+        if (endmask) break;
+    }
+    return __ballot_sync(FL_FULL, changed) != 0u;
+}
+#endif
+
+// One thread per segment head for the first 12 sites; segments that go on are finished by the whole warp,
+// one after the other (GPU) -- or by the same thread (emulation).
 __global__ void __launch_bounds__(128) k_elev_flow(uint32_t begin, uint32_t count,
                                                     const uint32_t* __restrict__ heads, FlElev e) {
-    uint32_t t = FL_TID;
-    if (t >= count) return;
-    const uint32_t h = heads[begin + t];
-    const uint32_t p = e.recv[h];
-    const bool is_root = (p == h);
-    uint32_t root;
-    double rt_prev, z_prev, e_out, rt_out;
-    if (is_root) {
-        root = e.is_outlet[h] ? h : FL_NONE;
-        rt_prev = 0.0;
-        z_prev = e.elev[h];  // has_edge(i,i) is false: the clamp compares with the site's own old elevation
-        e_out = e.elev[h];
-        rt_out = 0.0;
-    } else {
-        root = e.root_of[p];
-        rt_prev = e.rt[p];
-        z_prev = e.elev[p];  // the receiver already holds its NEW elevation
-        e_out = root != FL_NONE ? e.elev[root] : 0.0;
-        rt_out = root != FL_NONE ? e.rt[root] : 0.0;
-    }
-    if (root == FL_NONE) {  // tree without outlet: never visited (generator.rs:149)
-        for (uint32_t q = h;; ++q) {
-            e.root_of[q] = FL_NONE;
-            if (q + 1u >= e.n || e.recv[q + 1u] != q) break;
+    const uint32_t t = FL_TID;
+    const bool active = t < count;
+    bool changed = false, longseg = false;
+    uint32_t q = 0, root = FL_NONE;
+    double rt_prev = 0.0, z_prev = 0.0, e_out = 0.0, rt_out = 0.0;
+    if (active) {
+        const uint32_t h = heads[begin + t];
+        const uint32_t p = e.recv[h];
+        const bool is_root = (p == h);
+        if (is_root) {
+            root = e.is_outlet[h] ? h : FL_NONE;
+            rt_prev = 0.0;
+            z_prev = e.elev[h];  // has_edge(i,i) is false: the clamp compares with the site's own old elevation
+            e_out = e.elev[h];
+            rt_out = 0.0;
+        } else {
+            root = e.root_of[p];
+            rt_prev = e.rt[p];
+            z_prev = e.elev[p];  // the receiver already holds its NEW elevation
+            e_out = root != FL_NONE ? e.elev[root] : 0.0;
+            rt_out = root != FL_NONE ? e.rt[root] : 0.0;
         }
-        return;
+        if (root == FL_NONE) {  // tree without outlet: never visited (generator.rs:149)
+            for (uint32_t r = h;; ++r) {
+                e.root_of[r] = FL_NONE;
+                if (r + 1u >= e.n || e.recv[r + 1u] != r) break;
+            }
+        } else {
+            q = h;
+            bool ended = fl_elev_batch<4>(e, q, h, is_root, root, rt_prev, z_prev, e_out, rt_out, changed);
+            if (!ended) ended = fl_elev_batch<8>(e, q, h, is_root, root, rt_prev, z_prev, e_out, rt_out, changed);
+            longseg = !ended;
+#ifdef FL_EMU
+            if (longseg) while (!fl_elev_batch<8>(e, q, h, false, root, rt_prev, z_prev, e_out, rt_out, changed)) {}
+#endif
+        }
     }
-    bool changed = false;
-    uint32_t q = h;
-    if (!fl_elev_batch<4>(e, q, h, is_root, root, rt_prev, z_prev, e_out, rt_out, changed))
-        while (!fl_elev_batch<8>(e, q, h, is_root, root, rt_prev, z_prev, e_out, rt_out, changed)) {}
+#ifndef FL_EMU
+    uint32_t todo = __ballot_sync(FL_FULL, longseg);
+    const int lane = threadIdx.x & 31;
+    while (todo) {
+        const int src = __ffs((int)todo) - 1;
+        todo &= todo - 1u;
+        const uint32_t q_s = __shfl_sync(FL_FULL, q, src);
+        const uint32_t root_s = __shfl_sync(FL_FULL, root, src);
+        const double rtp_s = fl_shfl(rt_prev, src);
+        const double zp_s = fl_shfl(z_prev, src);
+        const double eo_s = fl_shfl(e_out, src);
+        const double ro_s = fl_shfl(rt_out, src);
+        const bool ch = fl_elev_warp(e, q_s, root_s, rtp_s, zp_s, eo_s, ro_s);
+        if (lane == src) changed |= ch;
+    }
+#endif
     if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
 }
 

@@ -111,6 +111,9 @@ struct fastlem_ctx {
     uint32_t* d_hgt = nullptr;
     uint32_t* d_hpre = nullptr;
     uint32_t* d_iota = nullptr;
+    uint32_t* d_parked = nullptr;
+    int sm_count = 148;
+    int64_t opt_park_after = 16;
     uint32_t max_degree = 0;
     uint32_t segs_at_rebuild = 0, maxh_at_rebuild = 0;
     bool need_rebuild = true;
@@ -541,8 +544,13 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     f.n = n; f.row_ptr = L.row_ptr; f.col = L.col; f.recv = L.recv; f.cmask = L.cmask; f.areas = L.areas;
     f.A = c->d_A; f.state = c->d_state; f.pre = c->d_pre; f.post1 = c->d_post1; f.post2 = c->d_post2;
     f.xbuf = c->d_xbuf; f.hbuf = c->d_hbuf; f.hgt = c->d_hgt; f.hpre = c->d_hpre; f.flags = c->d_flags;
+    f.parked = c->d_parked; f.counters = c->d_flags + FL_FLAG_PARKED; f.park_after = (uint32_t)c->opt_park_after;
     LAUNCH_N(k_area_flow, n, f);
-    c->stats.n_area++;
+    if (f.park_after) {  // pass 2: long chains, one warp each (persistent grid)
+        FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 4u, 256, c->stream, f);
+        c->stats.kernel_launches++;
+    }
+    c->stats.n_area += 2;
     FL_RC(stage_mark(c, 4));
 
     // order the segment heads by descending nesting height (exact for the current forest)
@@ -697,6 +705,9 @@ int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
             return fail(c, FASTLEM_E_INVALID,
                         "option sweep: 0 (levels), 1 (paths, thread per path), 2 (paths, warp per long path), 3 (dataflow)");
         c->opt_sweep = value;
+    } else if (s == "park_after") {
+        if (value != 0 && value < 8) return fail(c, FASTLEM_E_INVALID, "option park_after: 0 (never) or >= 8");
+        c->opt_park_after = value;
     } else if (s == "rebuild_every") {
         if (value < 0) return fail(c, FASTLEM_E_INVALID, "option rebuild_every: 0 (adaptive) or a positive period");
         c->opt_rebuild_every = value;
@@ -780,6 +791,8 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     FL_CK(dalloc(c, c->d_hgt, n));
     FL_CK(dalloc(c, c->d_hpre, n));
     FL_CK(dalloc(c, c->d_iota, n));
+    FL_CK(dalloc(c, c->d_parked, (size_t)n / 8 + 64));
+    c->sm_count = fl_sm_count();
     LAUNCH_N(k_iota, n, n, c->d_iota);
     c->max_degree = 0;
     for (uint32_t i = 0; i < n; ++i) {

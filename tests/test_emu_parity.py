@@ -81,6 +81,14 @@ def test_dataflow_sweeps_on_stale_numbering(oracle, emu_lib, name, every):
         assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
 
 
+@pytest.mark.parametrize("park_after", [0, 8, 64])
+def test_dataflow_parking(oracle, emu_lib, park_after):
+    m, p, outlets, initial, max_iteration = scenario("uniform")
+    with _ctx(emu_lib, sweep=3, park_after=park_after) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
+
+
 @pytest.mark.parametrize("k", [0, 1, 3])
 def test_max_iteration(oracle, emu_lib, k):
     m, p, outlets, initial, _ = scenario("uniform")

@@ -55,6 +55,16 @@ def test_dataflow_sweeps_on_stale_numbering(oracle, gpu_ctx_factory, name, every
         assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
 
 
+@pytest.mark.parametrize("park_after", [0, 8, 16, 64])
+@pytest.mark.parametrize("name", ["uniform", "max_slope", "uplift"])
+def test_dataflow_long_chain_hand_over(oracle, gpu_ctx_factory, name, park_after):
+    """Long chains are parked by the thread-level pass and continued by warps (park_after = 0: never)."""
+    m, p, outlets, initial, max_iteration = scenario(name, 30000)
+    with gpu_ctx_factory(sweep=3, park_after=park_after) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
+
+
 @pytest.mark.parametrize("n", [30000, 200000])
 def test_dataflow_sweeps_repeatable_at_size(oracle, gpu_ctx_factory, n):
     """The dataflow kernel's hand-offs race differently from run to run; results must not."""
