@@ -624,714 +624,3 @@ __global__ void __launch_bounds__(128) k_elev_paths_warp(uint32_t begin, uint32_
 }
 #endif  // !FL_EMU
 
-// ================================================================================================
-// "sweep" = 3: dataflow sweeps on DYNAMIC segments.
-//
-// A segment is a maximal run of positions q, q+1, ... with recv[q+1] == q (a chain that is contiguous in the
-// current numbering).  Right after a layout rebuild the segments are exactly the heavy paths; when receivers
-// change in later iterations a chain simply breaks into shorter segments -- nothing else has to be updated,
-// so the numbering can be kept for many iterations and is rebuilt only when it has degraded.
-//
-// K4 (drainage area) runs as ONE launch without any level structure:
-//   * every leaf starts a scan that climbs its segment with the running area in a register;
-//   * a scan that finishes a segment head h (A[h] final) reports to the parent site p = recv[h];
-//     the LAST child of p to report ("last arriver") gathers p's non-chain children in reverse adjacency
-//     order into   pre  = a_p + (children before the chain child)   and   post1, post2 (children after it),
-//     then either resumes the scan that is waiting at p or leaves the values for the scan still to come;
-//   * nobody ever spins: a thread either continues with work that is ready or exits.
-// The additions are the reference's, in the reference's order (generator.rs:154-159).
-// It also yields, per segment head, the nesting height (longest chain of segment hand-offs below it), which
-// orders the top-down sweep exactly for the CURRENT forest.
-// ================================================================================================
-#define FL_ST_COUNT_MASK 0x00FFFFFFu
-#define FL_ST_NP_SHIFT 24
-#define FL_ST_NP_MASK 0x0F000000u
-#define FL_ST_PRE_READY 0x40000000u
-#define FL_ST_SCAN_ARRIVED 0x80000000u
-
-#ifdef FL_EMU
-template <class T> __device__ __forceinline__ T fl_ld_cg(const T* p) { return *p; }
-__device__ __forceinline__ uint32_t fl_ld_acquire(const uint32_t* p) { return *p; }
-#else
-template <class T> __device__ __forceinline__ T fl_ld_cg(const T* p) { return __ldcg(p); }
-// acquire load: later loads of this thread (pre / posts) are ordered after it
-__device__ __forceinline__ uint32_t fl_ld_acquire(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-#endif
-// relaxed (pipelinable) load of a flag word; order later loads with one __threadfence() per batch
-#ifdef FL_EMU
-__device__ __forceinline__ uint32_t fl_ld_relaxed(const uint32_t* p) { return *p; }
-#else
-__device__ __forceinline__ uint32_t fl_ld_relaxed(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-#endif
-#define FL_BATCH 8
-
-struct FlFlow {
-    uint32_t n;
-    const uint32_t* row_ptr;
-    const uint32_t* col;
-    const uint32_t* recv;
-    const uint32_t* cmask;
-    const double* areas;
-    double* A;
-    uint32_t* state;  // zeroed before the launch
-    double* pre;
-    double* post1;
-    double* post2;
-    double* xbuf;     // running area handed over at a waiting site
-    uint32_t* hbuf;   // running nesting height handed over with it
-    uint32_t* hgt;    // out: nesting height for segment heads, FL_NONE elsewhere
-    uint32_t* hpre;   // max height over the non-chain children of a site (+1), written with pre
-    uint32_t* flags;
-    uint32_t* parked;    // sites where a long scan was parked for the warp-level pass
-    uint32_t* counters;  // [0] = number of parked scans, [1] = next one to take
-    uint32_t park_after; // a thread parks its scan after climbing this many sites in a row (0 = never)
-};
-
-// non-chain children of p, reverse adjacency order -> pre / posts; returns np (15 = more than two posts)
-__device__ __forceinline__ uint32_t fl_gather_lights(const FlFlow& f, uint32_t p, bool has_chain, double& pre,
-                                                     double& p1, double& p2, uint32_t& hmax) {
-    pre = f.areas[p];
-    p1 = 0.0; p2 = 0.0;
-    uint32_t np = 0;
-    bool seen = false;
-    hmax = 0;
-    const uint32_t s0 = f.row_ptr[p];
-    uint32_t m = f.cmask[p];
-    while (m) {
-        const uint32_t b = 31u - (uint32_t)__clz((int)m);
-        m ^= 1u << b;
-        const uint32_t c = f.col[s0 + b];
-        if (has_chain && c == p + 1u) { seen = true; continue; }
-        const double v = fl_ld_cg(&f.A[c]);
-        const uint32_t hc = fl_ld_cg(&f.hgt[c]) + 1u;
-        if (hc > hmax) hmax = hc;
-        if (!seen) pre += v;
-        else { if (np == 0) p1 = v; else if (np == 1) p2 = v; ++np; }
-    }
-    return np > 2 ? 15u : np;
-}
-
-// slow path for np == 15: add every post child in order
-__device__ double fl_add_posts(const FlFlow& f, uint32_t p, double y) {
-    bool seen = false;
-    const uint32_t s0 = f.row_ptr[p];
-    uint32_t m = f.cmask[p];
-    while (m) {
-        const uint32_t b = 31u - (uint32_t)__clz((int)m);
-        m ^= 1u << b;
-        const uint32_t c = f.col[s0 + b];
-        if (c == p + 1u) { seen = true; continue; }
-        if (seen) y += fl_ld_cg(&f.A[c]);
-    }
-    return y;
-}
-
-// One thread follows one flow: climb, report to the parent, possibly take over as last arriver, ...
-__device__ void fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t hrun, bool has_chain, bool may_park) {
-    // x: finished area of the chain child (valid when has_chain); hrun: nesting height along this segment
-    uint32_t climbed = 0;  // sites climbed through the fast path without a break
-    // `resume`: pre/posts of `cur` already in registers (we are the last arriver continuing the scan)
-    bool resume = false;
-    double pre = 0.0, p1 = 0.0, p2 = 0.0;
-    uint32_t np = 0, hp = 0;
-    for (;;) {
-        double y = 0.0;
-        uint32_t p = FL_NONE;
-        bool at_head = false;
-        // ---- fast path: up to FL_BATCH consecutive sites of the chain, every load issued up front ----
-        if (!resume) {
-            const uint32_t nb = cur + 1u < (uint32_t)FL_BATCH ? cur + 1u : (uint32_t)FL_BATCH;
-            uint32_t cm[FL_BATCH], rc[FL_BATCH], st[FL_BATCH], hq[FL_BATCH];
-            double ar[FL_BATCH], pr[FL_BATCH], q1[FL_BATCH], q2[FL_BATCH];
-#pragma unroll
-            for (int k = 0; k < FL_BATCH; ++k) {
-                cm[k] = 0u; rc[k] = FL_NONE; ar[k] = 0.0;
-                if ((uint32_t)k < nb) { cm[k] = f.cmask[cur - k]; rc[k] = f.recv[cur - k]; ar[k] = f.areas[cur - k]; }
-            }
-#pragma unroll
-            for (int k = 0; k < FL_BATCH; ++k) {
-                st[k] = 0u;
-                const uint32_t nl = (uint32_t)__popc(cm[k]) - ((k > 0 || has_chain) ? 1u : 0u);
-                if ((uint32_t)k < nb && cm[k] != 0u && nl > 0u) st[k] = fl_ld_relaxed(&f.state[cur - k]);
-            }
-            {
-                uint32_t any = 0u;
-#pragma unroll
-                for (int k = 0; k < FL_BATCH; ++k) any |= st[k];
-                if (any & FL_ST_PRE_READY) __threadfence();  // acquire: pre/posts are read after the flags
-            }
-#pragma unroll
-            for (int k = 0; k < FL_BATCH; ++k) {
-                pr[k] = 0.0; q1[k] = 0.0; q2[k] = 0.0; hq[k] = 0u;
-                if (st[k] & FL_ST_PRE_READY) {
-                    const uint32_t npk = (st[k] & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT;
-                    pr[k] = fl_ld_cg(&f.pre[cur - k]);
-                    hq[k] = fl_ld_cg(&f.hpre[cur - k]);
-                    if (npk >= 1u && npk != 15u) q1[k] = fl_ld_cg(&f.post1[cur - k]);
-                    if (npk >= 2u && npk != 15u) q2[k] = fl_ld_cg(&f.post2[cur - k]);
-                }
-            }
-            uint32_t done = 0;  // sites of the batch finished and climbed past
-#pragma unroll
-            for (int k = 0; k < FL_BATCH; ++k) {
-                if (!at_head && done == (uint32_t)k && (uint32_t)k < nb) {
-                    const uint32_t idx = cur - k;
-                    const bool hc = (k > 0) || has_chain;
-                    const uint32_t nl = (uint32_t)__popc(cm[k]) - (hc ? 1u : 0u);
-                    bool ok = true;
-                    if (nl == 0u) {
-                        y = hc ? (ar[k] + x) : ar[k];
-                    } else if (st[k] & FL_ST_PRE_READY) {
-                        const uint32_t npk = (st[k] & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT;
-                        y = hc ? (pr[k] + x) : pr[k];
-                        if (npk == 15u) y = fl_add_posts(f, idx, y);
-                        else {
-                            if (npk >= 1u) y += q1[k];
-                            if (npk >= 2u) y += q2[k];
-                        }
-                        if (hq[k] > hrun) hrun = hq[k];
-                    } else {
-                        ok = false;  // children of idx still running: take the hand-off path below
-                    }
-                    if (ok) {
-                        f.A[idx] = y;
-                        if (idx > 0u && rc[k] == idx - 1u) {
-                            f.hgt[idx] = FL_NONE;
-                            x = y;
-                            done = (uint32_t)k + 1u;
-                        } else {
-                            at_head = true;
-                            p = rc[k];
-                        }
-                    }
-                }
-            }
-            if (done > 0u) has_chain = true;
-            cur -= done;
-            if (!at_head && done == nb) {  // whole batch climbed
-                climbed += done;
-                if (may_park && f.park_after != 0u && climbed >= f.park_after) {
-                    // a long chain: leave it to the warp-level pass (k_area_flow_long)
-                    f.xbuf[cur] = x;
-                    f.hbuf[cur] = hrun;
-                    f.parked[atomicAdd(&f.counters[0], 1u)] = cur;
-                    return;
-                }
-                continue;  // next batch
-            }
-            climbed = 0;
-        }
-        if (!at_head) {
-            // ---- general path for one site: wait for / take over from its children ----
-            const uint32_t m = f.cmask[cur];
-            const uint32_t nlight = (uint32_t)__popc(m) - (has_chain ? 1u : 0u);
-            if (nlight == 0u) {
-                y = has_chain ? (f.areas[cur] + x) : f.areas[cur];
-            } else {
-                if (!resume) {
-                    uint32_t s = fl_ld_acquire(&f.state[cur]);
-                    if (!(s & FL_ST_PRE_READY)) {
-                        f.xbuf[cur] = x;
-                        f.hbuf[cur] = hrun;
-                        __threadfence();
-                        s = atomicOr(&f.state[cur], FL_ST_SCAN_ARRIVED);
-                        if (!(s & FL_ST_PRE_READY)) return;  // the last arriver of `cur` takes over
-                    }
-                    __threadfence();
-                    np = (s & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT;
-                    pre = fl_ld_cg(&f.pre[cur]);
-                    hp = fl_ld_cg(&f.hpre[cur]);
-                    if (np >= 1u && np != 15u) p1 = fl_ld_cg(&f.post1[cur]);
-                    if (np >= 2u && np != 15u) p2 = fl_ld_cg(&f.post2[cur]);
-                }
-                resume = false;
-                y = has_chain ? (pre + x) : pre;
-                if (np == 15u) y = fl_add_posts(f, cur, y);
-                else {
-                    if (np >= 1u) y += p1;
-                    if (np >= 2u) y += p2;
-                }
-                if (hp > hrun) hrun = hp;
-            }
-            f.A[cur] = y;
-            p = f.recv[cur];
-            if (cur > 0u && p == cur - 1u) {  // chained: climb
-                f.hgt[cur] = FL_NONE;
-                x = y;
-                has_chain = true;
-                cur = cur - 1u;
-                continue;
-            }
-        }
-        // ---- `cur` is a segment head with final area y; p = recv[cur] ----
-        f.hgt[cur] = hrun;
-        if (p == cur) {  // tree root: its segment has the largest nesting height of the tree
-            if (hrun > 0u) atomicMax(&f.flags[FL_FLAG_MAXDEPTH], hrun);
-            return;
-        }
-        __threadfence();  // publish A[cur], hgt[cur]
-        const uint32_t arrived = (atomicAdd(&f.state[p], 1u) & FL_ST_COUNT_MASK) + 1u;
-        const bool p_has_chain = (p + 1u < f.n) && (f.recv[p + 1u] == p);
-        const uint32_t p_lights = (uint32_t)__popc(f.cmask[p]) - (p_has_chain ? 1u : 0u);
-        if (arrived < p_lights) return;
-        // last arriver at p: gather p's non-chain children
-        __threadfence();
-        np = fl_gather_lights(f, p, p_has_chain, pre, p1, p2, hp);
-        if (!p_has_chain) {  // p ends its segment: nobody scans into it, start the scan here
-            cur = p; has_chain = false; x = 0.0; hrun = 0; resume = true;
-            continue;
-        }
-        f.pre[p] = pre;
-        f.hpre[p] = hp;
-        if (np >= 1u && np != 15u) f.post1[p] = p1;
-        if (np >= 2u && np != 15u) f.post2[p] = p2;
-        __threadfence();
-        const uint32_t old = atomicOr(&f.state[p], FL_ST_PRE_READY | (np << FL_ST_NP_SHIFT));
-        if (!(old & FL_ST_SCAN_ARRIVED)) return;  // the scan below p has not arrived yet; it will pick these up
-        __threadfence();
-        x = fl_ld_cg(&f.xbuf[p]);
-        hrun = fl_ld_cg(&f.hbuf[p]);
-        cur = p; has_chain = true; resume = true;
-    }
-}
-
-// pass 1: every leaf starts a thread-level flow
-__global__ void __launch_bounds__(256) k_area_flow(FlFlow f) {
-    const uint32_t q0 = FL_TID;
-    if (q0 >= f.n) return;
-    if (f.cmask[q0] != 0u) return;  // only leaves (no children at all) start a scan
-    fl_flow_thread(f, q0, 0.0, 0u, false, true);
-}
-
-#ifndef FL_EMU
-__device__ __forceinline__ uint32_t fl_warp_max(uint32_t v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const uint32_t w = __shfl_xor_sync(FL_FULL, v, o);
-        v = w > v ? w : v;
-    }
-    return v;
-}
-
-// One WARP follows one flow.  All lanes hold identical copies of the flow state; a 32-site window of the
-// chain is fetched by the lanes together, the additions run as a chain over shuffles.
-__device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t hrun, bool has_chain) {
-    const int lane = threadIdx.x & 31;
-    bool resume = false;
-    double pre = 0.0, p1 = 0.0, p2 = 0.0;
-    uint32_t np = 0, hp = 0;
-    for (;;) {
-        double y = 0.0;
-        uint32_t p = FL_NONE;
-        bool at_head = false;
-        if (!resume) {
-            const long long li = (long long)cur - lane;
-            const bool valid = li >= 0;
-            const uint32_t idx = (uint32_t)li;
-            uint32_t cm = 0u, rc = FL_NONE;
-            double ar = 0.0;
-            if (valid) { cm = f.cmask[idx]; rc = f.recv[idx]; ar = f.areas[idx]; }
-            const uint32_t rc_up = __shfl_up_sync(FL_FULL, rc, 1);
-            const bool link = valid && (lane == 0 || rc_up == idx);
-            const uint32_t linkmask = __ballot_sync(FL_FULL, link);
-            const uint32_t nchain = linkmask == FL_FULL ? 32u : (uint32_t)__ffs((int)~linkmask) - 1u;
-            const bool hc = (lane > 0) || has_chain;
-            const bool inwin = (uint32_t)lane < nchain;
-            const uint32_t nl = inwin ? (uint32_t)__popc(cm) - (hc ? 1u : 0u) : 0u;
-            uint32_t st = 0u;
-            if (inwin && nl > 0u) st = fl_ld_relaxed(&f.state[idx]);
-            const bool ready = inwin && (nl == 0u || (st & FL_ST_PRE_READY));
-            const uint32_t readymask = __ballot_sync(FL_FULL, ready);
-            const uint32_t nproc = readymask == FL_FULL ? 32u : (uint32_t)__ffs((int)~readymask) - 1u;
-            const bool mine_lit = (uint32_t)lane < nproc && nl > 0u;
-            if (__ballot_sync(FL_FULL, mine_lit)) __threadfence();  // acquire before reading pre/posts
-            double b = ar, q1 = 0.0, q2 = 0.0;
-            uint32_t npk = 0u, hq = 0u;
-            if (mine_lit) {
-                npk = (st & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT;
-                b = fl_ld_cg(&f.pre[idx]);
-                hq = fl_ld_cg(&f.hpre[idx]);
-                if (npk >= 1u && npk != 15u) q1 = fl_ld_cg(&f.post1[idx]);
-                if (npk >= 2u && npk != 15u) q2 = fl_ld_cg(&f.post2[idx]);
-            }
-            double mine = 0.0;
-            for (uint32_t k = 0; k < nproc; ++k) {
-                const double bk = fl_shfl(b, (int)k);
-                const double q1k = fl_shfl(q1, (int)k);
-                const double q2k = fl_shfl(q2, (int)k);
-                const uint32_t npk_k = __shfl_sync(FL_FULL, npk, (int)k);
-                double yy = ((k > 0u) || has_chain) ? (bk + x) : bk;
-                if (npk_k == 15u) {
-                    double v = 0.0;
-                    if ((uint32_t)lane == k) v = fl_add_posts(f, idx, yy);
-                    __syncwarp();
-                    yy = fl_shfl(v, (int)k);
-                } else {
-                    if (npk_k >= 1u) yy += q1k;
-                    if (npk_k >= 2u) yy += q2k;
-                }
-                x = yy;
-                if ((uint32_t)lane == k) mine = yy;
-            }
-            const uint32_t hw = fl_warp_max((uint32_t)lane < nproc ? hq : 0u);
-            if (hw > hrun) hrun = hw;
-            const bool climbs = valid && idx > 0u && rc == idx - 1u;
-            if ((uint32_t)lane < nproc) {
-                f.A[idx] = mine;
-                if (climbs) f.hgt[idx] = FL_NONE;
-            }
-            if (nproc > 0u) {
-                const int lastl = (int)nproc - 1;
-                const int last_climbs = __shfl_sync(FL_FULL, (int)climbs, lastl);
-                if (!last_climbs) {
-                    at_head = true;
-                    y = fl_shfl(mine, lastl);
-                    p = __shfl_sync(FL_FULL, rc, lastl);
-                    cur -= (uint32_t)lastl;
-                } else {
-                    has_chain = true;
-                    cur -= nproc;
-                    if (nproc == 32u) continue;  // whole window climbed
-                }
-            }
-        }
-        if (!at_head) {
-            // general path for the single site `cur` (uniform across the warp; lane 0 does the side effects)
-            const uint32_t nlight = (uint32_t)__popc(f.cmask[cur]) - (has_chain ? 1u : 0u);
-            if (nlight == 0u) {
-                y = has_chain ? (f.areas[cur] + x) : f.areas[cur];
-            } else {
-                if (!resume) {
-                    uint32_t sv = 0u;
-                    if (lane == 0) {
-                        sv = fl_ld_acquire(&f.state[cur]);
-                        if (!(sv & FL_ST_PRE_READY)) {
-                            f.xbuf[cur] = x;
-                            f.hbuf[cur] = hrun;
-                            __threadfence();
-                            sv = atomicOr(&f.state[cur], FL_ST_SCAN_ARRIVED);
-                        }
-                    }
-                    sv = __shfl_sync(FL_FULL, sv, 0);
-                    if (!(sv & FL_ST_PRE_READY)) return;  // the last arriver of `cur` takes over
-                    __threadfence();
-                    np = (sv & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT;
-                    pre = fl_ld_cg(&f.pre[cur]);
-                    hp = fl_ld_cg(&f.hpre[cur]);
-                    if (np >= 1u && np != 15u) p1 = fl_ld_cg(&f.post1[cur]);
-                    if (np >= 2u && np != 15u) p2 = fl_ld_cg(&f.post2[cur]);
-                }
-                resume = false;
-                y = has_chain ? (pre + x) : pre;
-                if (np == 15u) y = fl_add_posts(f, cur, y);
-                else {
-                    if (np >= 1u) y += p1;
-                    if (np >= 2u) y += p2;
-                }
-                if (hp > hrun) hrun = hp;
-            }
-            if (lane == 0) f.A[cur] = y;
-            p = f.recv[cur];
-            if (cur > 0u && p == cur - 1u) {
-                if (lane == 0) f.hgt[cur] = FL_NONE;
-                x = y;
-                has_chain = true;
-                cur = cur - 1u;
-                continue;
-            }
-        }
-        // `cur` is a segment head with final area y
-        if (lane == 0) f.hgt[cur] = hrun;
-        if (p == cur) {
-            if (lane == 0 && hrun > 0u) atomicMax(&f.flags[FL_FLAG_MAXDEPTH], hrun);
-            return;
-        }
-        uint32_t arrived = 0u;
-        if (lane == 0) {
-            __threadfence();
-            arrived = (atomicAdd(&f.state[p], 1u) & FL_ST_COUNT_MASK) + 1u;
-        }
-        arrived = __shfl_sync(FL_FULL, arrived, 0);
-        const bool p_has_chain = (p + 1u < f.n) && (f.recv[p + 1u] == p);
-        const uint32_t p_lights = (uint32_t)__popc(f.cmask[p]) - (p_has_chain ? 1u : 0u);
-        if (arrived < p_lights) return;
-        __threadfence();
-        np = fl_gather_lights(f, p, p_has_chain, pre, p1, p2, hp);  // uniform addresses: every lane, same values
-        if (!p_has_chain) {
-            cur = p; has_chain = false; x = 0.0; hrun = 0; resume = true;
-            continue;
-        }
-        uint32_t old = 0u;
-        if (lane == 0) {
-            f.pre[p] = pre;
-            f.hpre[p] = hp;
-            if (np >= 1u && np != 15u) f.post1[p] = p1;
-            if (np >= 2u && np != 15u) f.post2[p] = p2;
-            __threadfence();
-            old = atomicOr(&f.state[p], FL_ST_PRE_READY | (np << FL_ST_NP_SHIFT));
-        }
-        old = __shfl_sync(FL_FULL, old, 0);
-        if (!(old & FL_ST_SCAN_ARRIVED)) return;
-        __threadfence();
-        x = fl_ld_cg(&f.xbuf[p]);
-        hrun = fl_ld_cg(&f.hbuf[p]);
-        cur = p; has_chain = true; resume = true;
-    }
-}
-#endif
-
-// pass 2: the parked (long) scans.  Persistent: every warp (emulation: thread) takes parked scans until none is left.
-__global__ void __launch_bounds__(256) k_area_flow_long(FlFlow f) {
-#ifdef FL_EMU
-    for (;;) {
-        const uint32_t i = atomicAdd(&f.counters[1], 1u);
-        if (i >= f.counters[0]) return;
-        const uint32_t cur = f.parked[i];
-        fl_flow_thread(f, cur, f.xbuf[cur], f.hbuf[cur], true, false);
-    }
-#else
-    const int lane = threadIdx.x & 31;
-    for (;;) {
-        uint32_t i = 0u;
-        if (lane == 0) i = atomicAdd(&f.counters[1], 1u);
-        i = __shfl_sync(FL_FULL, i, 0);
-        if (i >= fl_ld_cg(&f.counters[0])) return;
-        const uint32_t cur = f.parked[i];
-        fl_flow_warp(f, cur, fl_ld_cg(&f.xbuf[cur]), fl_ld_cg(&f.hbuf[cur]), true);
-    }
-#endif
-}
-
-// K5 on dynamic segments: one thread per segment head, walks while recv[q+1] == q.  Sites are taken in
-// batches (4, then 8): all loads of a batch are issued together and the per-site celerity terms
-// t = 1/(k*sqrt(A))*d are computed side by side, so that only the running additions are serial.
-struct FlElev {
-    uint32_t n;
-    const uint32_t* recv;
-    const double* drecv;
-    const double* tcel;  // 1/(k*sqrt(A))*d per site (k_celerity_term)
-    const double* A;
-    const double* erod;
-    const double* uplift;
-    const double* tan_slope;  // may be null
-    const uint8_t* is_outlet;
-    double* elev;
-    double* rt;
-    uint32_t* root_of;
-    uint32_t* flags;
-};
-
-// generator.rs:172-173: celerity = k_i * A_i^0.5;  term = 1.0 / celerity * d_i  (fully parallel; the
-// division and square root stay out of the serial scans)
-__global__ void __launch_bounds__(256) k_celerity_term(uint32_t n, const double* __restrict__ erod,
-                                                        const double* __restrict__ A,
-                                                        const double* __restrict__ drecv, double* __restrict__ tcel) {
-    uint32_t q = FL_TID;
-    if (q >= n) return;
-    const double celerity = erod[q] * sqrt(A[q]);
-    tcel[q] = 1.0 / celerity * drecv[q];
-}
-
-template <int B>
-__device__ __forceinline__ bool fl_elev_batch(const FlElev& e, uint32_t& q, uint32_t h, bool is_root, uint32_t root,
-                                              double& rt_prev, double& z_prev, double& e_out, double& rt_out,
-                                              bool& changed) {
-    // returns true when the segment ended inside this batch
-    const uint32_t nb = e.n - q < (uint32_t)B ? e.n - q : (uint32_t)B;
-    double d[B], t[B], up[B], eo[B], ms[B];
-    uint32_t nx[B];
-#pragma unroll
-    for (int k = 0; k < B; ++k) {
-        d[k] = 1.0; t[k] = 1.0; up[k] = 0.0; eo[k] = 0.0; ms[k] = 0.0; nx[k] = FL_NONE;
-        if ((uint32_t)k < nb) {
-            const uint32_t i = q + k;
-            if (e.tan_slope) d[k] = e.drecv[i];
-            t[k] = e.tcel[i];
-            up[k] = e.uplift[i];
-            eo[k] = e.elev[i];
-            if (e.tan_slope) ms[k] = e.tan_slope[i];
-            nx[k] = (i + 1u < e.n) ? e.recv[i + 1u] : FL_NONE;
-        }
-    }
-    bool ended = false;
-#pragma unroll
-    for (int k = 0; k < B; ++k) {
-        if (!ended && (uint32_t)k < nb) {
-            const uint32_t i = q + k;
-            const double rti = 0.0 + (rt_prev + t[k]);
-            if (is_root && i == h) rt_out = rti;
-            double z = e_out + up[k] * fmax(rti - rt_out, 0.0);
-            if (e.tan_slope) {
-                if (ms[k] == ms[k]) {
-                    const double slope = (z - z_prev) / d[k];
-                    if (slope > ms[k]) z = z_prev + ms[k] * d[k];
-                }
-            }
-            changed |= (z != eo[k]);
-            if (is_root && i == h) e_out = z;
-            e.elev[i] = z;
-            e.rt[i] = rti;
-            e.root_of[i] = root;
-            rt_prev = rti;
-            z_prev = z;
-            if (nx[k] != i) ended = true;
-        }
-    }
-    q += nb;
-    return ended || q >= e.n;
-}
-
-#ifndef FL_EMU
-// rest of a long segment, walked by the whole warp: 32-site windows, shuffle chains.  Returns "changed".
-__device__ bool fl_elev_warp(const FlElev& e, uint32_t q, uint32_t root, double rt_prev, double z_prev, double e_out,
-                             double rt_out) {
-    const int lane = threadIdx.x & 31;
-    bool changed = false;
-    for (;;) {
-        const uint32_t i = q + (uint32_t)lane;
-        const bool valid = i < e.n;
-        double t = 0.0, up = 0.0, eold = 0.0, ms = 0.0, d = 1.0;
-        uint32_t nx = FL_NONE;
-        if (valid) {
-            t = e.tcel[i];
-            up = e.uplift[i];
-            eold = e.elev[i];
-            nx = (i + 1u < e.n) ? e.recv[i + 1u] : FL_NONE;
-            if (e.tan_slope) { ms = e.tan_slope[i]; d = e.drecv[i]; }
-        }
-        const uint32_t endmask = __ballot_sync(FL_FULL, !valid || nx != i);
-        uint32_t nproc = 32u;
-        if (endmask) {
-            const int el = __ffs((int)endmask) - 1;
-            const int el_valid = __shfl_sync(FL_FULL, (int)valid, el);
-            nproc = (uint32_t)el + (el_valid ? 1u : 0u);
-        }
-        double my_rt = 0.0;
-        for (uint32_t k = 0; k < nproc; ++k) {
-            const double tk = fl_shfl(t, (int)k);
-            rt_prev = 0.0 + (rt_prev + tk);
-            if ((uint32_t)lane == k) my_rt = rt_prev;
-        }
-        double z = e_out + up * fmax(my_rt - rt_out, 0.0);
-        if (e.tan_slope) {
-            double my_z = z;
-            for (uint32_t k = 0; k < nproc; ++k) {
-                double zk = fl_shfl(z, (int)k);
-                const double msk = fl_shfl(ms, (int)k);
-                const double dk = fl_shfl(d, (int)k);
-                if (msk == msk) {
-                    const double slope = (zk - z_prev) / dk;
-                    if (slope > msk) zk = z_prev + msk * dk;
-                }
-                z_prev = zk;
-                if ((uint32_t)lane == k) my_z = zk;
-            }
-            z = my_z;
-        }
-        if ((uint32_t)lane < nproc) {
-            changed |= (z != eold);
-            e.elev[i] = z;
-            e.rt[i] = my_rt;
-            e.root_of[i] = root;
-        }
-        q += nproc;
-        if (endmask) break;
-    }
-    return __ballot_sync(FL_FULL, changed) != 0u;
-}
-#endif
-
-// One thread per segment head for the first 12 sites; segments that go on are finished by the whole warp,
-// one after the other (GPU) -- or by the same thread (emulation).
-__global__ void __launch_bounds__(128) k_elev_flow(uint32_t begin, uint32_t count,
-                                                    const uint32_t* __restrict__ heads, FlElev e) {
-    const uint32_t t = FL_TID;
-    const bool active = t < count;
-    bool changed = false, longseg = false;
-    uint32_t q = 0, root = FL_NONE;
-    double rt_prev = 0.0, z_prev = 0.0, e_out = 0.0, rt_out = 0.0;
-    if (active) {
-        const uint32_t h = heads[begin + t];
-        const uint32_t p = e.recv[h];
-        const bool is_root = (p == h);
-        if (is_root) {
-            root = e.is_outlet[h] ? h : FL_NONE;
-            rt_prev = 0.0;
-            z_prev = e.elev[h];  // has_edge(i,i) is false: the clamp compares with the site's own old elevation
-            e_out = e.elev[h];
-            rt_out = 0.0;
-        } else {
-            root = e.root_of[p];
-            rt_prev = e.rt[p];
-            z_prev = e.elev[p];  // the receiver already holds its NEW elevation
-            e_out = root != FL_NONE ? e.elev[root] : 0.0;
-            rt_out = root != FL_NONE ? e.rt[root] : 0.0;
-        }
-        if (root == FL_NONE) {  // tree without outlet: never visited (generator.rs:149)
-            for (uint32_t r = h;; ++r) {
-                e.root_of[r] = FL_NONE;
-                if (r + 1u >= e.n || e.recv[r + 1u] != r) break;
-            }
-        } else {
-            q = h;
-            bool ended = fl_elev_batch<4>(e, q, h, is_root, root, rt_prev, z_prev, e_out, rt_out, changed);
-            if (!ended) ended = fl_elev_batch<8>(e, q, h, is_root, root, rt_prev, z_prev, e_out, rt_out, changed);
-            longseg = !ended;
-#ifdef FL_EMU
-            if (longseg) while (!fl_elev_batch<8>(e, q, h, false, root, rt_prev, z_prev, e_out, rt_out, changed)) {}
-#endif
-        }
-    }
-#ifndef FL_EMU
-    uint32_t todo = __ballot_sync(FL_FULL, longseg);
-    const int lane = threadIdx.x & 31;
-    while (todo) {
-        const int src = __ffs((int)todo) - 1;
-        todo &= todo - 1u;
-        const uint32_t q_s = __shfl_sync(FL_FULL, q, src);
-        const uint32_t root_s = __shfl_sync(FL_FULL, root, src);
-        const double rtp_s = fl_shfl(rt_prev, src);
-        const double zp_s = fl_shfl(z_prev, src);
-        const double eo_s = fl_shfl(e_out, src);
-        const double ro_s = fl_shfl(rt_out, src);
-        const bool ch = fl_elev_warp(e, q_s, root_s, rtp_s, zp_s, eo_s, ro_s);
-        if (lane == src) changed |= ch;
-    }
-#endif
-    if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
-}
-
-// keys for sorting segment heads by descending nesting height: key = maxh - hgt (heads), FL_NONE otherwise
-__global__ void __launch_bounds__(256) k_flow_sort_keys(uint32_t n, const uint32_t* __restrict__ hgt, uint32_t maxh,
-                                                         uint32_t* __restrict__ keys) {
-    uint32_t q = FL_TID;
-    if (q >= n) return;
-    const uint32_t h = hgt[q];
-    keys[q] = (h == FL_NONE) ? FL_NONE : (maxh - h);
-}
-
-// layout rebuild on dynamic segments: exclusive scan input = path length at heads (in index order), 0 elsewhere
-__global__ void __launch_bounds__(256) k_head_lengths(uint32_t n, const unsigned long long* __restrict__ pd,
-                                                       const uint32_t* __restrict__ plen,
-                                                       uint32_t* __restrict__ out) {
-    uint32_t q = FL_TID;
-    if (q >= n) return;
-    out[q] = ((uint32_t)pd[q] == q) ? plen[q] : 0u;
-}
-
-__global__ void __launch_bounds__(256) k_newpos_direct(uint32_t n, const unsigned long long* __restrict__ pd,
-                                                        const uint32_t* __restrict__ starts,
-                                                        uint32_t* __restrict__ newpos) {
-    uint32_t q = FL_TID;
-    if (q >= n) return;
-    const unsigned long long a = pd[q];
-    newpos[q] = starts[(uint32_t)a] + (uint32_t)(a >> 32);
-}

@@ -20,6 +20,7 @@
 
 #include "fl_flood.h"
 #include "fl_kernels.cuh"
+#include "fl_flow.cuh"
 #include "fl_paths.cuh"
 
 #ifdef FL_EMU
@@ -113,7 +114,7 @@ struct fastlem_ctx {
     uint32_t* d_iota = nullptr;
     uint32_t* d_parked = nullptr;
     int sm_count = 148;
-    int64_t opt_park_after = 16;
+    int64_t opt_park_after = 8;
     uint32_t max_degree = 0;
     uint32_t segs_at_rebuild = 0, maxh_at_rebuild = 0;
     bool need_rebuild = true;
@@ -583,7 +584,7 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     // K5: one launch per nesting height, outermost segments first
     FlElev e;
     LAUNCH_N(k_celerity_term, n, n, L.erod, c->d_A, L.drecv, c->d_pre);  // d_pre is free again after K4
-    e.n = n; e.recv = L.recv; e.drecv = L.drecv; e.tcel = c->d_pre; e.A = c->d_A; e.erod = L.erod; e.uplift = L.uplift;
+    e.n = n; e.recv = L.recv; e.drecv = L.drecv; e.tcel = c->d_pre; e.uplift = L.uplift;
     e.tan_slope = c->has_tan ? L.tan : nullptr; e.is_outlet = L.is_outlet; e.elev = L.elev; e.rt = c->d_rt;
     e.root_of = c->d_root_of; e.flags = c->d_flags;
     uint32_t launched = 0;
@@ -706,7 +707,7 @@ int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
                         "option sweep: 0 (levels), 1 (paths, thread per path), 2 (paths, warp per long path), 3 (dataflow)");
         c->opt_sweep = value;
     } else if (s == "park_after") {
-        if (value != 0 && value < 8) return fail(c, FASTLEM_E_INVALID, "option park_after: 0 (never) or >= 8");
+        if (value != 0 && value < 4) return fail(c, FASTLEM_E_INVALID, "option park_after: 0 (never) or >= 4");
         c->opt_park_after = value;
     } else if (s == "rebuild_every") {
         if (value < 0) return fail(c, FASTLEM_E_INVALID, "option rebuild_every: 0 (adaptive) or a positive period");
