@@ -136,7 +136,7 @@ struct fastlem_ctx {
     int64_t opt_sweep = 3;
 
     fastlem_stats stats{};
-    cudaEvent_t ev[ST_COUNT + 1] = {};
+    cudaEvent_t ev[ST_COUNT + 3] = {};
     cudaEvent_t ev_run[2] = {};
 };
 
@@ -537,6 +537,7 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     const bool rebuilt = c->need_rebuild || periodic || c->opt_rebuild_every == 1;
     if (rebuilt) FL_RC(rebuild_layout_flow(c, c->d_A));
     c->need_rebuild = false;
+    FL_RC(stage_mark(c, 7));  // end of the layout rebuild
     Layout& L = L_(c);
 
     // K4: one dataflow launch
@@ -552,7 +553,7 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
         c->stats.kernel_launches++;
     }
     c->stats.n_area += 2;
-    FL_RC(stage_mark(c, 4));
+    FL_RC(stage_mark(c, 8));  // end of K4
 
     // order the segment heads by descending nesting height (exact for the current forest)
     FL_RC(read_flags(c));
@@ -579,7 +580,7 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
              ((unsigned long long)n_heads * 100ull > (unsigned long long)c->segs_at_rebuild * 104ull ||
               maxh > c->maxh_at_rebuild + c->maxh_at_rebuild / 2 + 2))
         c->need_rebuild = true;  // the numbering has degraded: renumber in the next iteration
-    FL_RC(stage_mark(c, 5));
+    FL_RC(stage_mark(c, 5));  // end of the head ordering
 
     // K5: one launch per nesting height, outermost segments first
     FlElev e;
@@ -599,7 +600,17 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     FL_RC(read_flags(c));
     FL_CK(fl_last_error());
     *changed_out = c->h_flags[FL_FLAG_CHANGED] != 0;
-    return profile_accumulate(c);
+    if (c->opt_profile) {  // receivers | flags | lakes | rebuild + ordering | K4 | K5
+        const int from[7] = {0, 1, 2, 3, 8, 7, 5}, to[7] = {1, 2, 3, 7, 5, 8, 6};
+        double* acc[7] = {&c->stats.ms_receivers, &c->stats.ms_labels, &c->stats.ms_lakes, &c->stats.ms_order,
+                          &c->stats.ms_order,     &c->stats.ms_area,   &c->stats.ms_elevation};
+        for (int k = 0; k < 7; ++k) {
+            float ms = 0.f;
+            FL_CK(fl_event_elapsed(&ms, c->ev[from[k]], c->ev[to[k]]));
+            *acc[k] += ms;
+        }
+    }
+    return FASTLEM_OK;
 }
 
 // start of a run: working numbering = the caller's
@@ -666,7 +677,7 @@ int fastlem_create(fastlem_ctx** out, int device_ordinal) {
     }
     c->h_flags = (uint32_t*)hf;
     bool ok = true;
-    for (int k = 0; k <= ST_COUNT; ++k) ok = ok && fl_event_create(&c->ev[k]) == cudaSuccess;
+    for (int k = 0; k < ST_COUNT + 3; ++k) ok = ok && fl_event_create(&c->ev[k]) == cudaSuccess;
     for (int k = 0; k < 2; ++k) ok = ok && fl_event_create(&c->ev_run[k]) == cudaSuccess;
     void* fl = nullptr;
     ok = ok && fl_malloc(&fl, sizeof(uint32_t) * FL_N_FLAGS) == cudaSuccess;
@@ -686,7 +697,7 @@ void fastlem_destroy(fastlem_ctx* c) {
     if (c->d_tmp) fl_free(c->d_tmp);
     if (c->d_flags) fl_free(c->d_flags);
     if (c->h_flags) fl_free_host(c->h_flags);
-    for (int k = 0; k <= ST_COUNT; ++k)
+    for (int k = 0; k < ST_COUNT + 3; ++k)
         if (c->ev[k]) fl_event_destroy(c->ev[k]);
     for (int k = 0; k < 2; ++k)
         if (c->ev_run[k]) fl_event_destroy(c->ev_run[k]);
