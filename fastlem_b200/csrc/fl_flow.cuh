@@ -62,6 +62,7 @@ struct FlFlow {
     const uint32_t* cmask;
     const double* areas;
     double* A;
+    const uint32_t* nwait;  // non-leaf non-chain children per site (k_count_waits); leaves never report
     uint32_t* state;  // zeroed before the launch: [0,24) children reported, [24,28) np, bit 30 pre ready, bit 31 flow waiting
     double* pre;
     double* post1;
@@ -77,7 +78,8 @@ struct FlFlow {
 };
 
 // non-chain children of p, reverse adjacency order -> pre / posts; returns np (15 = more than two posts).
-// `dep` is an opaque zero that orders the loads after the atomic that made us last arriver.
+// Leaf children never run a flow: their area is their own cell area and their height 0.  `dep` is an opaque
+// zero that orders the loads of the other children's results after the atomic that made us last arriver.
 __device__ __forceinline__ uint32_t fl_gather_lights(const FlFlow& f, uint32_t p, bool has_chain, uint32_t dep,
                                                      double& pre, double& p1, double& p2, uint32_t& hmax) {
     pre = f.areas[p];
@@ -92,8 +94,14 @@ __device__ __forceinline__ uint32_t fl_gather_lights(const FlFlow& f, uint32_t p
         m ^= 1u << b;
         const uint32_t c = f.col[s0 + b];
         if (has_chain && c == p + 1u) { seen = true; continue; }
-        const double v = fl_ld_cg(&f.A[c + dep]);
-        const uint32_t hc = fl_ld_cg(&f.hgt[c + dep]) + 1u;
+        double v;
+        uint32_t hc = 1u;
+        if (f.cmask[c] == 0u) {
+            v = f.areas[c];
+        } else {
+            v = fl_ld_cg(&f.A[c + dep]);
+            hc = fl_ld_cg(&f.hgt[c + dep]) + 1u;
+        }
         if (hc > hmax) hmax = hc;
         if (!seen) pre += v;
         else { if (np == 0) p1 = v; else if (np == 1) p2 = v; ++np; }
@@ -111,7 +119,7 @@ __device__ double fl_add_posts(const FlFlow& f, uint32_t p, double y) {
         m ^= 1u << b;
         const uint32_t c = f.col[s0 + b];
         if (c == p + 1u) { seen = true; continue; }
-        if (seen) y += fl_ld_cg(&f.A[c]);
+        if (seen) y += (f.cmask[c] == 0u) ? f.areas[c] : fl_ld_cg(&f.A[c]);
     }
     return y;
 }
@@ -256,10 +264,9 @@ __device__ void fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t
         __threadfence();  // publish A[cur], hgt[cur]
         const uint32_t prev = atomicAdd(&f.state[p], 1u);
         const uint32_t arrived = (prev & FL_ST_COUNT_MASK) + 1u;
-        const bool p_has_chain = (p + 1u < f.n) && (f.recv[p + 1u] == p);
-        const uint32_t p_lights = (uint32_t)__popc(f.cmask[p]) - (p_has_chain ? 1u : 0u);
-        if (arrived < p_lights) return;
+        if (arrived < f.nwait[p]) return;
         // last arriver at p: gather p's non-chain children
+        const bool p_has_chain = (p + 1u < f.n) && (f.recv[p + 1u] == p);
         np = fl_gather_lights(f, p, p_has_chain, fl_dep0(prev), pre, p1, p2, hp);
         if (!p_has_chain) {  // p ends its segment: nobody climbs into it, the flow continues here
             cur = p; has_chain = false; x = 0.0; hrun = 0; resume = true; climbed = 0;
@@ -279,20 +286,58 @@ __device__ void fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t
     }
 }
 
-// pass 1: every leaf starts a thread-level flow
+// pre-pass A: how many children will REPORT to each site = its non-leaf segment heads.
+// (Leaves are resolved by their parent directly; chain children hand over inside the segment.)
+__global__ void __launch_bounds__(256) k_count_waits(uint32_t n, const uint32_t* __restrict__ recv,
+                                                      const uint32_t* __restrict__ cmask, uint32_t* nwait) {
+    const uint32_t q = FL_TID;
+    if (q >= n) return;
+    if (cmask[q] == 0u) return;
+    const uint32_t p = recv[q];
+    if (p == q || (q > 0u && p == q - 1u)) return;  // root, or chained to its receiver
+    atomicAdd(&nwait[p], 1u);
+}
+
+// pre-pass B: sites whose non-chain children are all leaves need nobody: their pre / posts are gathered
+// here, in parallel, and published as ready (plain stores: the kernel boundary orders them).
+__global__ void __launch_bounds__(256) k_simple_pre(FlFlow f) {
+    const uint32_t q = FL_TID;
+    if (q >= f.n) return;
+    const uint32_t cm = f.cmask[q];
+    if (cm == 0u || f.nwait[q] != 0u) return;
+    const bool has_chain = (q + 1u < f.n) && (f.recv[q + 1u] == q);
+    if ((uint32_t)__popc(cm) - (has_chain ? 1u : 0u) == 0u) return;  // only the chain child
+    double pre, p1, p2;
+    uint32_t hp;
+    const uint32_t np = fl_gather_lights(f, q, has_chain, 0u, pre, p1, p2, hp);
+    f.pre[q] = pre;
+    f.hpre[q] = hp;
+    if (np >= 1u && np != 15u) f.post1[q] = p1;
+    if (np >= 2u && np != 15u) f.post2[q] = p2;
+    f.state[q] = FL_ST_PRE_READY | (np << FL_ST_NP_SHIFT);
+}
+
+// pass 1: thread-level flows start at (a) leaves that are the tail of a chain and (b) ready sites that end
+// their segment.  All other leaves only publish their own area and height.
 __global__ void __launch_bounds__(256) k_area_flow(FlFlow f) {
     const uint32_t q = FL_TID;
     if (q >= f.n) return;
-    if (f.cmask[q] != 0u) return;  // only leaves (no children at all) start a flow
-    const double y = f.areas[q];
-    const uint32_t p = f.recv[q];
-    f.A[q] = y;
-    if (q > 0u && p == q - 1u) {  // the leaf is the tail of a chain
-        f.hgt[q] = FL_NONE;
-        fl_flow_thread(f, q - 1u, y, 0u, true, false, 0.0, FL_NONE, true);
-    } else {                      // single-site segment
-        fl_flow_thread(f, q, 0.0, 0u, false, true, y, p, true);
+    const uint32_t cm = f.cmask[q];
+    if (cm == 0u) {
+        const double y = f.areas[q];
+        const uint32_t p = f.recv[q];
+        f.A[q] = y;
+        if (q > 0u && p == q - 1u) {  // the leaf is the tail of a chain: climb
+            f.hgt[q] = FL_NONE;
+            fl_flow_thread(f, q - 1u, y, 0u, true, false, 0.0, FL_NONE, true);
+        } else {
+            f.hgt[q] = 0u;  // a one-site segment; its parent reads areas[q] itself
+        }
+        return;
     }
+    if (f.nwait[q] != 0u) return;                             // children will report: the last one continues here
+    if ((q + 1u < f.n) && (f.recv[q + 1u] == q)) return;      // a chain child will climb into q
+    fl_flow_thread(f, q, 0.0, 0u, false, false, 0.0, FL_NONE, true);  // tail whose children are all leaves
 }
 
 #ifndef FL_EMU
@@ -479,9 +524,8 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
         }
         prev = __shfl_sync(FL_FULL, prev, 0);
         const uint32_t arrived = (prev & FL_ST_COUNT_MASK) + 1u;
+        if (arrived < f.nwait[p]) return;
         const bool p_has_chain = (p + 1u < f.n) && (f.recv[p + 1u] == p);
-        const uint32_t p_lights = (uint32_t)__popc(f.cmask[p]) - (p_has_chain ? 1u : 0u);
-        if (arrived < p_lights) return;
         np = fl_gather_lights(f, p, p_has_chain, fl_dep0(prev), pre, p1, p2, hp);  // uniform: every lane, same values
         if (!p_has_chain) {
             cur = p; has_chain = false; x = 0.0; hrun = 0; resume = true;

@@ -113,6 +113,8 @@ struct fastlem_ctx {
     uint32_t* d_hpre = nullptr;
     uint32_t* d_iota = nullptr;
     uint32_t* d_parked = nullptr;
+    uint32_t* d_nwait = nullptr;
+    double* d_tcel = nullptr;
     int sm_count = 148;
     int64_t opt_park_after = 8;
     uint32_t max_degree = 0;
@@ -547,12 +549,16 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     f.A = c->d_A; f.state = c->d_state; f.pre = c->d_pre; f.post1 = c->d_post1; f.post2 = c->d_post2;
     f.xbuf = c->d_xbuf; f.hbuf = c->d_hbuf; f.hgt = c->d_hgt; f.hpre = c->d_hpre; f.flags = c->d_flags;
     f.parked = c->d_parked; f.counters = c->d_flags + FL_FLAG_PARKED; f.park_after = (uint32_t)c->opt_park_after;
+    FL_CK(fl_memset(c->d_nwait, 0, sizeof(uint32_t) * n, c->stream));
+    f.nwait = c->d_nwait;
+    LAUNCH_N(k_count_waits, n, n, L.recv, L.cmask, c->d_nwait);
+    LAUNCH_N(k_simple_pre, n, f);
     LAUNCH_N(k_area_flow, n, f);
     if (f.park_after) {  // pass 2: long chains, one warp each (persistent grid)
         FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 4u, 256, c->stream, f);
         c->stats.kernel_launches++;
     }
-    c->stats.n_area += 2;
+    c->stats.n_area += 4;
     FL_RC(stage_mark(c, 8));  // end of K4
 
     // order the segment heads by descending nesting height (exact for the current forest)
@@ -584,8 +590,8 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
 
     // K5: one launch per nesting height, outermost segments first
     FlElev e;
-    LAUNCH_N(k_celerity_term, n, n, L.erod, c->d_A, L.drecv, c->d_pre);  // d_pre is free again after K4
-    e.n = n; e.recv = L.recv; e.drecv = L.drecv; e.tcel = c->d_pre; e.uplift = L.uplift;
+    LAUNCH_N(k_celerity_term, n, n, L.erod, c->d_A, L.drecv, c->d_tcel);
+    e.n = n; e.recv = L.recv; e.drecv = L.drecv; e.tcel = c->d_tcel; e.uplift = L.uplift;
     e.tan_slope = c->has_tan ? L.tan : nullptr; e.is_outlet = L.is_outlet; e.elev = L.elev; e.rt = c->d_rt;
     e.root_of = c->d_root_of; e.flags = c->d_flags;
     uint32_t launched = 0;
@@ -803,7 +809,9 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     FL_CK(dalloc(c, c->d_hgt, n));
     FL_CK(dalloc(c, c->d_hpre, n));
     FL_CK(dalloc(c, c->d_iota, n));
-    FL_CK(dalloc(c, c->d_parked, (size_t)n / 8 + 64));
+    FL_CK(dalloc(c, c->d_parked, (size_t)n / 4 + 64));
+    FL_CK(dalloc(c, c->d_nwait, n));
+    FL_CK(dalloc(c, c->d_tcel, n));
     c->sm_count = fl_sm_count();
     LAUNCH_N(k_iota, n, n, c->d_iota);
     c->max_degree = 0;
