@@ -129,12 +129,17 @@ __device__ double fl_add_posts(const FlFlow& f, uint32_t p, double y) {
 // ------------------------------------------------------------------------------------------------
 // Entry states: at_head = false: about to process site `cur` (x = area of its chain child if has_chain);
 //               at_head = true : site `cur` is a finished segment head with area y and receiver p.
-__device__ void fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t hrun, bool has_chain, bool at_head,
-                               double y, uint32_t p, bool may_park) {
+//               resume  = true : pre/posts of `cur` are passed in registers (the caller is its last arriver).
+// defer = false: a flow that becomes last arriver at a site continues there at once (pure dataflow).
+// defer = true : it returns that site instead (round-synchronous mode: the caller queues it for the next launch,
+//                and the kernel boundary publishes the children's results, so no fence is needed to report).
+struct FlPre { double pre, p1, p2; uint32_t np, hp; };
+
+__device__ uint32_t fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t hrun, bool has_chain, bool at_head,
+                                   double y, uint32_t p, bool may_park, bool defer, bool resume, FlPre in) {
     uint32_t climbed = 0;  // sites climbed through the fast path without a break
-    bool resume = false;   // pre/posts of `cur` are in registers (we are its last arriver)
-    double pre = 0.0, p1 = 0.0, p2 = 0.0;
-    uint32_t np = 0, hp = 0;
+    double pre = in.pre, p1 = in.p1, p2 = in.p2;
+    uint32_t np = in.np, hp = in.hp;
     for (;;) {
         if (!at_head && !resume) {
             // ---- fast path: up to FL_TB consecutive sites, loads issued up front ----
@@ -207,7 +212,7 @@ __device__ void fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t
                     f.xbuf[cur] = x;  // a long chain: leave it to the warp-level pass
                     f.hbuf[cur] = hrun;
                     f.parked[atomicAdd(&f.counters[0], 1u)] = cur;
-                    return;
+                    return FL_NONE;
                 }
                 continue;
             }
@@ -226,7 +231,7 @@ __device__ void fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t
                         f.hbuf[cur] = hrun;
                         __threadfence();
                         s = atomicOr(&f.state[cur], FL_ST_SCAN_ARRIVED);
-                        if (!(s & FL_ST_PRE_READY)) return;  // the last arriver of `cur` takes over
+                        if (!(s & FL_ST_PRE_READY)) return FL_NONE;  // the last arriver of `cur` takes over
                     }
                     const uint32_t i = cur + fl_dep0(s);
                     np = (s & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT;
@@ -259,12 +264,13 @@ __device__ void fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t
         f.hgt[cur] = hrun;
         if (p == cur) {  // tree root: its segment has the largest nesting height of the tree
             if (hrun > 0u) atomicMax(&f.flags[FL_FLAG_MAXDEPTH], hrun);
-            return;
+            return FL_NONE;
         }
-        __threadfence();  // publish A[cur], hgt[cur]
+        if (!defer) __threadfence();  // publish A[cur], hgt[cur] (deferred mode: the kernel boundary does)
         const uint32_t prev = atomicAdd(&f.state[p], 1u);
         const uint32_t arrived = (prev & FL_ST_COUNT_MASK) + 1u;
-        if (arrived < f.nwait[p]) return;
+        if (arrived < f.nwait[p]) return FL_NONE;
+        if (defer) return p;  // queue p: its last arriver runs in the next launch
         // last arriver at p: gather p's non-chain children
         const bool p_has_chain = (p + 1u < f.n) && (f.recv[p + 1u] == p);
         np = fl_gather_lights(f, p, p_has_chain, fl_dep0(prev), pre, p1, p2, hp);
@@ -278,7 +284,7 @@ __device__ void fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t
         if (np >= 2u && np != 15u) f.post2[p] = p2;
         __threadfence();
         const uint32_t old = atomicOr(&f.state[p], FL_ST_PRE_READY | (np << FL_ST_NP_SHIFT));
-        if (!(old & FL_ST_SCAN_ARRIVED)) return;  // the flow below p has not arrived yet; it will pick these up
+        if (!(old & FL_ST_SCAN_ARRIVED)) return FL_NONE;  // the flow below p has not arrived yet; it will pick these up
         const uint32_t pi = p + fl_dep0(old);
         x = fl_ld_cg(&f.xbuf[pi]);
         hrun = fl_ld_cg(&f.hbuf[pi]);
@@ -329,7 +335,7 @@ __global__ void __launch_bounds__(256) k_area_flow(FlFlow f) {
         f.A[q] = y;
         if (q > 0u && p == q - 1u) {  // the leaf is the tail of a chain: climb
             f.hgt[q] = FL_NONE;
-            fl_flow_thread(f, q - 1u, y, 0u, true, false, 0.0, FL_NONE, true);
+            fl_flow_thread(f, q - 1u, y, 0u, true, false, 0.0, FL_NONE, true, false, false, FlPre{0.0, 0.0, 0.0, 0u, 0u});
         } else {
             f.hgt[q] = 0u;  // a one-site segment; its parent reads areas[q] itself
         }
@@ -337,7 +343,99 @@ __global__ void __launch_bounds__(256) k_area_flow(FlFlow f) {
     }
     if (f.nwait[q] != 0u) return;                             // children will report: the last one continues here
     if ((q + 1u < f.n) && (f.recv[q + 1u] == q)) return;      // a chain child will climb into q
-    fl_flow_thread(f, q, 0.0, 0u, false, false, 0.0, FL_NONE, true);  // tail whose children are all leaves
+    fl_flow_thread(f, q, 0.0, 0u, false, false, 0.0, FL_NONE, true, false, false, FlPre{0.0, 0.0, 0.0, 0u, 0u});  // tail whose children are all leaves
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4, round-synchronous variant (option "k4_rounds", default): the same protocol, but a flow that becomes the
+// last arriver at a site does not continue there -- the site is queued and processed by the next launch.
+// Every launch is then a regular kernel over a compact list (no long-lived divergent threads); the number of
+// launches is the nesting height of the segment forest.  Flows on long chains still park; the parked flows are
+// finished by k_area_flow_long (warp-level dataflow) after the last round.
+// ------------------------------------------------------------------------------------------------
+// append `value` (if pred) to list[*count ...]: one atomic per warp
+__device__ __forceinline__ void fl_append(uint32_t* list, uint32_t* count, uint32_t value, bool pred) {
+#ifdef FL_EMU
+    if (pred) list[atomicAdd(count, 1u)] = value;
+#else
+    const uint32_t mask = __ballot_sync(FL_FULL, pred);
+    if (!mask) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs((int)mask) - 1;
+    uint32_t base = 0u;
+    if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(mask));
+    base = __shfl_sync(FL_FULL, base, leader);
+    if (pred) list[base + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = value;
+#endif
+}
+
+// round 0 list + everything that needs no flow: leaves publish their own area / height, sites whose
+// non-chain children are all leaves get their pre / posts (as k_simple_pre), segment tails that wait for
+// nobody are queued as starters.
+__global__ void __launch_bounds__(256) k_flow_prepare(FlFlow f, uint32_t* list, uint32_t* count) {
+    const uint32_t q = FL_TID;
+    bool start = false;
+    if (q < f.n) {
+        const uint32_t cm = f.cmask[q];
+        const bool has_chain = (q + 1u < f.n) && (f.recv[q + 1u] == q);
+        if (cm == 0u) {
+            const uint32_t p = f.recv[q];
+            if (q > 0u && p == q - 1u) {
+                start = true;  // leaf at the tail of a chain: climbs in round 0
+            } else {
+                f.A[q] = f.areas[q];  // one-site segment; its parent reads areas[q] itself
+                f.hgt[q] = 0u;
+            }
+        } else if (f.nwait[q] == 0u) {
+            if ((uint32_t)__popc(cm) - (has_chain ? 1u : 0u) != 0u) {
+                double pre, p1, p2;
+                uint32_t hp;
+                const uint32_t np = fl_gather_lights(f, q, has_chain, 0u, pre, p1, p2, hp);
+                f.pre[q] = pre;
+                f.hpre[q] = hp;
+                if (np >= 1u && np != 15u) f.post1[q] = p1;
+                if (np >= 2u && np != 15u) f.post2[q] = p2;
+                f.state[q] = FL_ST_PRE_READY | (np << FL_ST_NP_SHIFT);
+            }
+            start = !has_chain;  // a tail that waits for nobody
+        }
+    }
+    fl_append(list, count, q, start);
+}
+
+// one queued site: either a starter (tail that waits for nobody) or a site whose last child has reported
+__device__ uint32_t fl_round_entry(const FlFlow& f, uint32_t p) {
+    const bool has_chain = (p + 1u < f.n) && (f.recv[p + 1u] == p);
+    const uint32_t nl = (uint32_t)__popc(f.cmask[p]) - (has_chain ? 1u : 0u);
+    FlPre in{0.0, 0.0, 0.0, 0u, 0u};
+    if (nl == 0u || (f.state[p] & FL_ST_PRE_READY))  // leaf tail, or prepared by k_flow_prepare
+        return fl_flow_thread(f, p, 0.0, 0u, false, false, 0.0, FL_NONE, true, true, false, in);
+    // we are p's last arriver (its children reported in earlier launches)
+    in.np = fl_gather_lights(f, p, has_chain, 0u, in.pre, in.p1, in.p2, in.hp);
+    if (!has_chain) return fl_flow_thread(f, p, 0.0, 0u, false, false, 0.0, FL_NONE, true, true, true, in);
+    f.pre[p] = in.pre;
+    f.hpre[p] = in.hp;
+    if (in.np >= 1u && in.np != 15u) f.post1[p] = in.p1;
+    if (in.np >= 2u && in.np != 15u) f.post2[p] = in.p2;
+    __threadfence();
+    const uint32_t old = atomicOr(&f.state[p], FL_ST_PRE_READY | (in.np << FL_ST_NP_SHIFT));
+    if (!(old & FL_ST_SCAN_ARRIVED)) return FL_NONE;  // the flow below p has not arrived yet; it will pick these up
+    const uint32_t pi = p + fl_dep0(old);
+    const double x = fl_ld_cg(&f.xbuf[pi]);
+    const uint32_t hrun = fl_ld_cg(&f.hbuf[pi]);
+    return fl_flow_thread(f, p, x, hrun, true, false, 0.0, FL_NONE, true, true, true, in);
+}
+
+__global__ void __launch_bounds__(256) k_area_round(FlFlow f, const uint32_t* __restrict__ list,
+                                                     const uint32_t* count_in, uint32_t* next, uint32_t* count_out) {
+    const uint32_t cnt = fl_ld_cg(count_in);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < cnt; base += stride) {  // block-uniform trip count
+        const uint32_t i = base + threadIdx.x;
+        uint32_t out = FL_NONE;
+        if (i < cnt) out = fl_round_entry(f, list[i]);
+        fl_append(next, count_out, out, out != FL_NONE);
+    }
 }
 
 #ifndef FL_EMU
@@ -557,7 +655,7 @@ __global__ void __launch_bounds__(256) k_area_flow_long(FlFlow f) {
         const uint32_t i = atomicAdd(&f.counters[1], 1u);
         if (i >= f.counters[0]) return;
         const uint32_t cur = f.parked[i];
-        fl_flow_thread(f, cur, f.xbuf[cur], f.hbuf[cur], true, false, 0.0, FL_NONE, false);
+        fl_flow_thread(f, cur, f.xbuf[cur], f.hbuf[cur], true, false, 0.0, FL_NONE, false, false, false, FlPre{0.0, 0.0, 0.0, 0u, 0u});
     }
 #else
     const int lane = threadIdx.x & 31;
@@ -671,60 +769,84 @@ __device__ __forceinline__ FlEWin fl_ewin_load(const FlElev& e, uint32_t base, i
     return w;
 }
 
-// rest of a long segment, walked by the whole warp.  Returns "changed".
+// one window of a long segment: the two serial chains (response time; clamp if max_slope) over the lanes
+__device__ __forceinline__ void fl_elev_window(const FlElev& e, const FlEWin& w, uint32_t q, uint32_t nproc, int lane,
+                                               uint32_t root, double& rt_prev, double& z_prev, double e_out,
+                                               double rt_out, bool& changed) {
+    double my_rt = 0.0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const double tk = fl_shfl(w.t, k);
+        if ((uint32_t)k < nproc) {
+            rt_prev = 0.0 + (rt_prev + tk);
+            if (lane == k) my_rt = rt_prev;
+        }
+    }
+    double z = e_out + w.up * fmax(my_rt - rt_out, 0.0);
+    if (e.tan_slope) {
+        double my_z = z;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            double zk = fl_shfl(z, k);
+            const double msk = fl_shfl(w.ms, k);
+            const double dk = fl_shfl(w.d, k);
+            if ((uint32_t)k < nproc) {
+                if (msk == msk) {
+                    const double slope = (zk - z_prev) / dk;
+                    if (slope > msk) zk = z_prev + msk * dk;
+                }
+                z_prev = zk;
+                if (lane == k) my_z = zk;
+            }
+        }
+        z = my_z;
+    }
+    if ((uint32_t)lane < nproc) {
+        const uint32_t i = q + (uint32_t)lane;
+        changed |= (z != w.eold);
+        e.elev[i] = z;
+        e.rt[i] = my_rt;
+        e.root_of[i] = root;
+    }
+}
+
+__device__ __forceinline__ uint32_t fl_elev_nproc(const FlEWin& w, uint32_t q, int lane, uint32_t& endmask) {
+    const uint32_t i = q + (uint32_t)lane;
+    endmask = __ballot_sync(FL_FULL, !w.valid || w.nx != i);
+    if (!endmask) return 32u;
+    const int el = __ffs((int)endmask) - 1;
+    const int el_valid = __shfl_sync(FL_FULL, (int)w.valid, el);
+    return (uint32_t)el + (el_valid ? 1u : 0u);
+}
+
+// rest of a long segment, walked by the whole warp.  Returns "changed".  The serial chains of a window are
+// much shorter than a DRAM round trip, so windows are fetched FL_EDEPTH ahead (registers) once the segment
+// has proved to be longer than one window.
+#define FL_EDEPTH 4
 __device__ bool fl_elev_warp(const FlElev& e, uint32_t q, uint32_t root, double rt_prev, double z_prev, double e_out,
                              double rt_out) {
     const int lane = threadIdx.x & 31;
     bool changed = false;
-    FlEWin w = fl_ewin_load(e, q, lane);
+    uint32_t endmask;
+    {
+        const FlEWin w0 = fl_ewin_load(e, q, lane);
+        const uint32_t nproc = fl_elev_nproc(w0, q, lane, endmask);
+        fl_elev_window(e, w0, q, nproc, lane, root, rt_prev, z_prev, e_out, rt_out, changed);
+        if (endmask) return __ballot_sync(FL_FULL, changed) != 0u;
+        q += 32u;
+    }
+    FlEWin ring[FL_EDEPTH];
+#pragma unroll
+    for (int j = 0; j < FL_EDEPTH; ++j) ring[j] = fl_ewin_load(e, q + 32u * (uint32_t)j, lane);
     for (;;) {
-        const uint32_t i = q + (uint32_t)lane;
-        const uint32_t endmask = __ballot_sync(FL_FULL, !w.valid || w.nx != i);
-        uint32_t nproc = 32u;
-        if (endmask) {
-            const int el = __ffs((int)endmask) - 1;
-            const int el_valid = __shfl_sync(FL_FULL, (int)w.valid, el);
-            nproc = (uint32_t)el + (el_valid ? 1u : 0u);
-        }
-        FlEWin nxt = w;
-        if (!endmask) nxt = fl_ewin_load(e, q + 32u, lane);  // prefetch while the chains run
-        double my_rt = 0.0;
+        const uint32_t nproc = fl_elev_nproc(ring[0], q, lane, endmask);
+        const FlEWin cur = ring[0];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            const double tk = fl_shfl(w.t, k);
-            if ((uint32_t)k < nproc) {
-                rt_prev = 0.0 + (rt_prev + tk);
-                if (lane == k) my_rt = rt_prev;
-            }
-        }
-        double z = e_out + w.up * fmax(my_rt - rt_out, 0.0);
-        if (e.tan_slope) {
-            double my_z = z;
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                double zk = fl_shfl(z, k);
-                const double msk = fl_shfl(w.ms, k);
-                const double dk = fl_shfl(w.d, k);
-                if ((uint32_t)k < nproc) {
-                    if (msk == msk) {
-                        const double slope = (zk - z_prev) / dk;
-                        if (slope > msk) zk = z_prev + msk * dk;
-                    }
-                    z_prev = zk;
-                    if (lane == k) my_z = zk;
-                }
-            }
-            z = my_z;
-        }
-        if ((uint32_t)lane < nproc) {
-            changed |= (z != w.eold);
-            e.elev[i] = z;
-            e.rt[i] = my_rt;
-            e.root_of[i] = root;
-        }
+        for (int j = 0; j + 1 < FL_EDEPTH; ++j) ring[j] = ring[j + 1];
+        if (!endmask) ring[FL_EDEPTH - 1] = fl_ewin_load(e, q + 32u * (uint32_t)FL_EDEPTH, lane);
+        fl_elev_window(e, cur, q, nproc, lane, root, rt_prev, z_prev, e_out, rt_out, changed);
         if (endmask) break;
         q += 32u;
-        w = nxt;
     }
     return __ballot_sync(FL_FULL, changed) != 0u;
 }

@@ -33,6 +33,7 @@ double wall_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+#define FL_MAX_ROUNDS 4096u
 enum Stage { ST_RECV = 0, ST_LABEL, ST_LAKE, ST_ORDER, ST_AREA, ST_ELEV, ST_COUNT };
 
 // One numbering of the sites and everything stored in it.
@@ -114,6 +115,10 @@ struct fastlem_ctx {
     uint32_t* d_iota = nullptr;
     uint32_t* d_parked = nullptr;
     uint32_t* d_nwait = nullptr;
+    uint32_t* d_round_list[2] = {nullptr, nullptr};
+    uint32_t* d_round_count = nullptr;
+    uint32_t rounds_hint = 16, last_rounds = 0;
+    int64_t opt_k4_rounds = 1;
     double* d_tcel = nullptr;
     int sm_count = 148;
     int64_t opt_park_after = 8;
@@ -552,9 +557,34 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     FL_CK(fl_memset(c->d_nwait, 0, sizeof(uint32_t) * n, c->stream));
     f.nwait = c->d_nwait;
     LAUNCH_N(k_count_waits, n, n, L.recv, L.cmask, c->d_nwait);
-    LAUNCH_N(k_simple_pre, n, f);
-    LAUNCH_N(k_area_flow, n, f);
-    if (f.park_after) {  // pass 2: long chains, one warp each (persistent grid)
+    if (c->opt_k4_rounds) {
+        // round-synchronous: list r -> list r+1, one launch per nesting height (estimated from the last
+        // iteration; checked below with the flag read-back, more rounds are added if the estimate was short)
+        const uint32_t max_rounds = FL_MAX_ROUNDS;
+        FL_CK(fl_memset(c->d_round_count, 0, sizeof(uint32_t) * (max_rounds + 2), c->stream));
+        LAUNCH_N(k_flow_prepare, n, f, c->d_round_list[0], c->d_round_count);
+        uint32_t r = 0;
+        uint32_t planned = c->rounds_hint + 2u;
+        for (;;) {
+            for (; r < planned && r < max_rounds; ++r) {
+                FL_LAUNCH(k_area_round, (unsigned)c->sm_count * 8u, 256, c->stream, f, c->d_round_list[r & 1],
+                          c->d_round_count + r, c->d_round_list[(r + 1) & 1], c->d_round_count + r + 1);
+                c->stats.kernel_launches++;
+            }
+            FL_CK(fl_d2h(c->h_offs, c->d_round_count, sizeof(uint32_t) * (r + 1), c->stream));
+            FL_CK(fl_stream_sync(c->stream));
+            if (c->h_offs[r] == 0u) break;
+            if (r >= max_rounds) return fail(c, FASTLEM_E_STATE, "K4: more hand-off rounds than FL_MAX_ROUNDS");
+            planned = r + 8u;
+        }
+        uint32_t used = 0;  // launches that had work
+        while (used < r && c->h_offs[used] != 0u) ++used;
+        c->last_rounds = used;
+    } else {
+        LAUNCH_N(k_simple_pre, n, f);
+        LAUNCH_N(k_area_flow, n, f);
+    }
+    if (f.park_after) {  // the parked (long) flows, one warp each, pure dataflow (persistent grid)
         FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 4u, 256, c->stream, f);
         c->stats.kernel_launches++;
     }
@@ -581,6 +611,7 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     c->stats.n_order += 3;
     c->stats.path_levels = maxh + 1;
     c->stats.paths = n_heads;
+    c->rounds_hint = c->last_rounds ? c->last_rounds : maxh + 1;
     if (rebuilt) { c->segs_at_rebuild = n_heads; c->maxh_at_rebuild = maxh; }
     else if (c->opt_rebuild_every == 0 &&
              ((unsigned long long)n_heads * 100ull > (unsigned long long)c->segs_at_rebuild * 104ull ||
@@ -726,6 +757,8 @@ int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
     } else if (s == "park_after") {
         if (value != 0 && value < 4) return fail(c, FASTLEM_E_INVALID, "option park_after: 0 (never) or >= 4");
         c->opt_park_after = value;
+    } else if (s == "k4_rounds") {
+        c->opt_k4_rounds = value != 0;
     } else if (s == "rebuild_every") {
         if (value < 0) return fail(c, FASTLEM_E_INVALID, "option rebuild_every: 0 (adaptive) or a positive period");
         c->opt_rebuild_every = value;
@@ -811,6 +844,9 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     FL_CK(dalloc(c, c->d_iota, n));
     FL_CK(dalloc(c, c->d_parked, (size_t)n / 4 + 64));
     FL_CK(dalloc(c, c->d_nwait, n));
+    FL_CK(dalloc(c, c->d_round_list[0], n));
+    FL_CK(dalloc(c, c->d_round_list[1], n));
+    FL_CK(dalloc(c, c->d_round_count, FL_MAX_ROUNDS + 2));
     FL_CK(dalloc(c, c->d_tcel, n));
     c->sm_count = fl_sm_count();
     LAUNCH_N(k_iota, n, n, c->d_iota);

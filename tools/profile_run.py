@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--lattice", action="store_true")
     ap.add_argument("--repeat", type=int, default=1)
     ap.add_argument("--max-slope", type=float, default=None)
+    ap.add_argument("--park-after", type=int, default=None)
+    ap.add_argument("--brief", action="store_true")
     args = ap.parse_args()
     cache = f"/tmp/fl_workload_{args.sites}_{int(args.lattice)}.npz"
     if os.path.exists(cache):
@@ -47,6 +49,8 @@ def main():
             ctx.set_option("sweep", args.sweep)
         if args.rebuild_every is not None:
             ctx.set_option("rebuild_every", args.rebuild_every)
+        if args.park_after is not None:
+            ctx.set_option("park_after", args.park_after)
         ctx.set_graph(m["row_ptr"], m["col"], m["dist"], m["areas"])
         ctx.set_parameters(initial, p["erodibility"], p["uplift"], tan, m["default_outlets"])
         for _ in range(args.repeat):
@@ -58,7 +62,13 @@ def main():
             st["sites"] = n
             st["msites_per_s_per_iter"] = n * it / dt / 1e6
             st["ms_per_iter"] = 1e3 * dt / max(it, 1)
-            print(json.dumps(st))
+            if args.brief:
+                it_ = max(it, 1)
+                print(f"sites={n} park_after={args.park_after} iters={it} ms/iter={st['ms_per_iter']:.3f} K1={st['ms_receivers']/it_:.3f} "
+                      f"order={st['ms_order']/it_:.3f} K4={st['ms_area']/it_:.3f} K5={st['ms_elevation']/it_:.3f} rebuilds={st['rebuilds']} "
+                      f"levels={st['path_levels']} segs={st['paths']}")
+            else:
+                print(json.dumps(st))
 
 
 if __name__ == "__main__":
