@@ -77,6 +77,9 @@ struct FlFlow {
     uint32_t park_after; // a thread parks its flow after climbing this many sites in a row (0 = never)
 };
 
+// per-warp staging area of the serial chains (warp-level scans)
+struct FlChainSmem { double in[32]; double out[32]; double aux1[32]; double aux2[32]; };
+
 // non-chain children of p, reverse adjacency order -> pre / posts; returns np (15 = more than two posts).
 // Leaf children never run a flow: their area is their own cell area and their height 0.  `dep` is an opaque
 // zero that orders the loads of the other children's results after the atomic that made us last arriver.
@@ -470,7 +473,7 @@ __device__ __forceinline__ FlWin fl_win_load(const FlFlow& f, uint32_t base, int
     return w;
 }
 
-__device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t hrun, bool has_chain) {
+__device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t hrun, bool has_chain, FlChainSmem& sm) {
     const int lane = threadIdx.x & 31;
     bool resume = false;
     double pre = 0.0, p1 = 0.0, p2 = 0.0;
@@ -515,28 +518,47 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
             const bool want_next = nproc == 32u && cur >= 32u;
             if (want_next) nxt = fl_win_load(f, cur - 32u, lane);
             const uint32_t postmask = __ballot_sync(FL_FULL, lit && npk != 0u);
-            double mine = 0.0;
+            double mine;
+            if (postmask == 0u) {
+                // common case, no children after the chain child anywhere in the window: y_k = b_k + y_{k-1}.
+                // Terms staged in shared memory, identical chain in every lane over broadcast reads.
+                __syncwarp();
+                sm.in[lane] = b;
+                __syncwarp();
+                double r = x;
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                const double bk = fl_shfl(b, k);
-                if ((uint32_t)k < nproc) {
-                    double yy = ((k > 0) || has_chain) ? (bk + x) : bk;
-                    if ((postmask >> k) & 1u) {  // children after the chain child: rare
-                        const uint32_t npk_k = __shfl_sync(FL_FULL, npk, k);
-                        if (npk_k == 15u) {
-                            double v = 0.0;
-                            if (lane == k) v = fl_add_posts(f, idx, yy);
-                            __syncwarp();
-                            yy = fl_shfl(v, k);
-                        } else {
-                            const double q1k = fl_shfl(q1, k);
-                            const double q2k = fl_shfl(q2, k);
-                            yy += q1k;
-                            if (npk_k >= 2u) yy += q2k;
+                for (int k = 0; k < 32; ++k) {
+                    const double bk = sm.in[k];
+                    if ((uint32_t)k < nproc) r = ((k > 0) || has_chain) ? (bk + r) : bk;
+                    sm.out[k] = r;
+                }
+                x = r;
+                __syncwarp();
+                mine = sm.out[lane];
+            } else {
+                mine = 0.0;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const double bk = fl_shfl(b, k);
+                    if ((uint32_t)k < nproc) {
+                        double yy = ((k > 0) || has_chain) ? (bk + x) : bk;
+                        if ((postmask >> k) & 1u) {  // children after the chain child
+                            const uint32_t npk_k = __shfl_sync(FL_FULL, npk, k);
+                            if (npk_k == 15u) {
+                                double v = 0.0;
+                                if (lane == k) v = fl_add_posts(f, idx, yy);
+                                __syncwarp();
+                                yy = fl_shfl(v, k);
+                            } else {
+                                const double q1k = fl_shfl(q1, k);
+                                const double q2k = fl_shfl(q2, k);
+                                yy += q1k;
+                                if (npk_k >= 2u) yy += q2k;
+                            }
                         }
+                        x = yy;
+                        if (lane == k) mine = yy;
                     }
-                    x = yy;
-                    if (lane == k) mine = yy;
                 }
             }
             const uint32_t hw = fl_warp_max((uint32_t)lane < nproc ? hq : 0u);
@@ -649,7 +671,7 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
 #endif
 
 // pass 2: the parked (long) flows.  Persistent: every warp (emulation: thread) takes parked flows until none is left.
-__global__ void __launch_bounds__(256) k_area_flow_long(FlFlow f) {
+__global__ void __launch_bounds__(256, 2) k_area_flow_long(FlFlow f) {
 #ifdef FL_EMU
     for (;;) {
         const uint32_t i = atomicAdd(&f.counters[1], 1u);
@@ -659,13 +681,15 @@ __global__ void __launch_bounds__(256) k_area_flow_long(FlFlow f) {
     }
 #else
     const int lane = threadIdx.x & 31;
+    __shared__ FlChainSmem chain_smem[8];  // one per warp (256 threads)
+    FlChainSmem& sm = chain_smem[threadIdx.x >> 5];
     for (;;) {
         uint32_t i = 0u;
         if (lane == 0) i = atomicAdd(&f.counters[1], 1u);
         i = __shfl_sync(FL_FULL, i, 0);
         if (i >= fl_ld_cg(&f.counters[0])) return;
         const uint32_t cur = f.parked[i];
-        fl_flow_warp(f, cur, fl_ld_cg(&f.xbuf[cur]), fl_ld_cg(&f.hbuf[cur]), true);
+        fl_flow_warp(f, cur, fl_ld_cg(&f.xbuf[cur]), fl_ld_cg(&f.hbuf[cur]), true, sm);
     }
 #endif
 }
@@ -769,37 +793,53 @@ __device__ __forceinline__ FlEWin fl_ewin_load(const FlElev& e, uint32_t base, i
     return w;
 }
 
-// one window of a long segment: the two serial chains (response time; clamp if max_slope) over the lanes
+// one window of a long segment: the two serial chains (response time; clamp if max_slope).  The per-lane
+// terms are staged in shared memory and every lane runs the identical chain over broadcast reads, so that
+// the dependent double additions are the only thing on the critical path (no shuffles, no selects).
+
 __device__ __forceinline__ void fl_elev_window(const FlElev& e, const FlEWin& w, uint32_t q, uint32_t nproc, int lane,
                                                uint32_t root, double& rt_prev, double& z_prev, double e_out,
-                                               double rt_out, bool& changed) {
-    double my_rt = 0.0;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-        const double tk = fl_shfl(w.t, k);
-        if ((uint32_t)k < nproc) {
-            rt_prev = 0.0 + (rt_prev + tk);
-            if (lane == k) my_rt = rt_prev;
-        }
-    }
-    double z = e_out + w.up * fmax(my_rt - rt_out, 0.0);
-    if (e.tan_slope) {
-        double my_z = z;
+                                               double rt_out, bool& changed, FlChainSmem& sm) {
+    __syncwarp();
+    sm.in[lane] = w.t;
+    __syncwarp();
+    {
+        double r = rt_prev;
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-            double zk = fl_shfl(z, k);
-            const double msk = fl_shfl(w.ms, k);
-            const double dk = fl_shfl(w.d, k);
+            const double tk = sm.in[k];
+            if ((uint32_t)k < nproc) r = 0.0 + (r + tk);
+            sm.out[k] = r;
+        }
+        rt_prev = r;
+    }
+    __syncwarp();
+    const double my_rt = sm.out[lane];
+    double z = e_out + w.up * fmax(my_rt - rt_out, 0.0);
+    if (e.tan_slope) {
+        __syncwarp();
+        sm.in[lane] = z;
+        sm.aux1[lane] = w.ms;
+        sm.aux2[lane] = w.d;
+        __syncwarp();
+        double zp = z_prev;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            double zk = sm.in[k];
+            const double msk = sm.aux1[k];
+            const double dk = sm.aux2[k];
             if ((uint32_t)k < nproc) {
                 if (msk == msk) {
-                    const double slope = (zk - z_prev) / dk;
-                    if (slope > msk) zk = z_prev + msk * dk;
+                    const double slope = (zk - zp) / dk;
+                    if (slope > msk) zk = zp + msk * dk;
                 }
-                z_prev = zk;
-                if (lane == k) my_z = zk;
+                zp = zk;
             }
+            sm.out[k] = zk;
         }
-        z = my_z;
+        z_prev = zp;
+        __syncwarp();
+        z = sm.out[lane];
     }
     if ((uint32_t)lane < nproc) {
         const uint32_t i = q + (uint32_t)lane;
@@ -824,14 +864,14 @@ __device__ __forceinline__ uint32_t fl_elev_nproc(const FlEWin& w, uint32_t q, i
 // has proved to be longer than one window.
 #define FL_EDEPTH 4
 __device__ bool fl_elev_warp(const FlElev& e, uint32_t q, uint32_t root, double rt_prev, double z_prev, double e_out,
-                             double rt_out) {
+                             double rt_out, FlChainSmem& sm) {
     const int lane = threadIdx.x & 31;
     bool changed = false;
     uint32_t endmask;
     {
         const FlEWin w0 = fl_ewin_load(e, q, lane);
         const uint32_t nproc = fl_elev_nproc(w0, q, lane, endmask);
-        fl_elev_window(e, w0, q, nproc, lane, root, rt_prev, z_prev, e_out, rt_out, changed);
+        fl_elev_window(e, w0, q, nproc, lane, root, rt_prev, z_prev, e_out, rt_out, changed, sm);
         if (endmask) return __ballot_sync(FL_FULL, changed) != 0u;
         q += 32u;
     }
@@ -844,7 +884,7 @@ __device__ bool fl_elev_warp(const FlElev& e, uint32_t q, uint32_t root, double 
 #pragma unroll
         for (int j = 0; j + 1 < FL_EDEPTH; ++j) ring[j] = ring[j + 1];
         if (!endmask) ring[FL_EDEPTH - 1] = fl_ewin_load(e, q + 32u * (uint32_t)FL_EDEPTH, lane);
-        fl_elev_window(e, cur, q, nproc, lane, root, rt_prev, z_prev, e_out, rt_out, changed);
+        fl_elev_window(e, cur, q, nproc, lane, root, rt_prev, z_prev, e_out, rt_out, changed, sm);
         if (endmask) break;
         q += 32u;
     }
@@ -894,6 +934,8 @@ __global__ void __launch_bounds__(128) k_elev_flow(uint32_t begin, uint32_t coun
         }
     }
 #ifndef FL_EMU
+    __shared__ FlChainSmem chain_smem[4];  // one per warp (128 threads)
+    FlChainSmem& sm = chain_smem[threadIdx.x >> 5];
     uint32_t todo = __ballot_sync(FL_FULL, longseg);
     const int lane = threadIdx.x & 31;
     while (todo) {
@@ -905,7 +947,7 @@ __global__ void __launch_bounds__(128) k_elev_flow(uint32_t begin, uint32_t coun
         const double zp_s = fl_shfl(z_prev, src);
         const double eo_s = fl_shfl(e_out, src);
         const double ro_s = fl_shfl(rt_out, src);
-        const bool ch = fl_elev_warp(e, q_s, root_s, rtp_s, zp_s, eo_s, ro_s);
+        const bool ch = fl_elev_warp(e, q_s, root_s, rtp_s, zp_s, eo_s, ro_s, sm);
         if (lane == src) changed |= ch;
     }
 #endif

@@ -136,6 +136,7 @@ struct fastlem_ctx {
     uint32_t* d_flags = nullptr;
     uint32_t* h_flags = nullptr;  // pinned
     uint32_t* h_offs = nullptr;   // pinned, n+2
+    uint32_t* h_rounds = nullptr; // pinned, FL_MAX_ROUNDS+2
     void* d_tmp = nullptr;        // CUB temp storage (sort / scan)
     size_t tmp_bytes = 0;
 
@@ -571,14 +572,14 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
                           c->d_round_count + r, c->d_round_list[(r + 1) & 1], c->d_round_count + r + 1);
                 c->stats.kernel_launches++;
             }
-            FL_CK(fl_d2h(c->h_offs, c->d_round_count, sizeof(uint32_t) * (r + 1), c->stream));
+            FL_CK(fl_d2h(c->h_rounds, c->d_round_count, sizeof(uint32_t) * (r + 1), c->stream));
             FL_CK(fl_stream_sync(c->stream));
-            if (c->h_offs[r] == 0u) break;
+            if (c->h_rounds[r] == 0u) break;
             if (r >= max_rounds) return fail(c, FASTLEM_E_STATE, "K4: more hand-off rounds than FL_MAX_ROUNDS");
             planned = r + 8u;
         }
         uint32_t used = 0;  // launches that had work
-        while (used < r && c->h_offs[used] != 0u) ++used;
+        while (used < r && c->h_rounds[used] != 0u) ++used;
         c->last_rounds = used;
     } else {
         LAUNCH_N(k_simple_pre, n, f);
@@ -713,6 +714,14 @@ int fastlem_create(fastlem_ctx** out, int device_ordinal) {
         return FASTLEM_E_NOMEM;
     }
     c->h_flags = (uint32_t*)hf;
+    void* hr = nullptr;
+    if (fl_malloc_host(&hr, sizeof(uint32_t) * (FL_MAX_ROUNDS + 2)) != cudaSuccess) {
+        fl_free_host(hf);
+        fl_stream_destroy(c->stream);
+        delete c;
+        return FASTLEM_E_NOMEM;
+    }
+    c->h_rounds = (uint32_t*)hr;
     bool ok = true;
     for (int k = 0; k < ST_COUNT + 3; ++k) ok = ok && fl_event_create(&c->ev[k]) == cudaSuccess;
     for (int k = 0; k < 2; ++k) ok = ok && fl_event_create(&c->ev_run[k]) == cudaSuccess;
@@ -734,6 +743,7 @@ void fastlem_destroy(fastlem_ctx* c) {
     if (c->d_tmp) fl_free(c->d_tmp);
     if (c->d_flags) fl_free(c->d_flags);
     if (c->h_flags) fl_free_host(c->h_flags);
+    if (c->h_rounds) fl_free_host(c->h_rounds);
     for (int k = 0; k < ST_COUNT + 3; ++k)
         if (c->ev[k]) fl_event_destroy(c->ev[k]);
     for (int k = 0; k < 2; ++k)
