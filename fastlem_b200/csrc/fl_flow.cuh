@@ -75,6 +75,8 @@ struct FlFlow {
     uint32_t* parked;    // sites where a long flow was parked for the warp-level pass
     uint32_t* counters;  // [0] = number of parked flows, [1] = next one to take
     uint32_t park_after; // a thread parks its flow after climbing this many sites in a row (0 = never)
+    uint32_t* next_list;   // round-synchronous mode: sites whose last child has just reported
+    uint32_t* next_count;
 };
 
 // per-warp staging area of the serial chains (warp-level scans)
@@ -473,7 +475,8 @@ __device__ __forceinline__ FlWin fl_win_load(const FlFlow& f, uint32_t base, int
     return w;
 }
 
-__device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t hrun, bool has_chain, FlChainSmem& sm) {
+__device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t hrun, bool has_chain, FlChainSmem& sm,
+                             bool defer) {
     const int lane = threadIdx.x & 31;
     bool resume = false;
     double pre = 0.0, p1 = 0.0, p2 = 0.0;
@@ -639,12 +642,16 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
         }
         uint32_t prev = 0u;
         if (lane == 0) {
-            __threadfence();
+            if (!defer) __threadfence();
             prev = atomicAdd(&f.state[p], 1u);
         }
         prev = __shfl_sync(FL_FULL, prev, 0);
         const uint32_t arrived = (prev & FL_ST_COUNT_MASK) + 1u;
         if (arrived < f.nwait[p]) return;
+        if (defer) {  // queue p for the next launch
+            if (lane == 0) f.next_list[atomicAdd(f.next_count, 1u)] = p;
+            return;
+        }
         const bool p_has_chain = (p + 1u < f.n) && (f.recv[p + 1u] == p);
         np = fl_gather_lights(f, p, p_has_chain, fl_dep0(prev), pre, p1, p2, hp);  // uniform: every lane, same values
         if (!p_has_chain) {
@@ -677,7 +684,10 @@ __global__ void __launch_bounds__(256, 2) k_area_flow_long(FlFlow f) {
         const uint32_t i = atomicAdd(&f.counters[1], 1u);
         if (i >= f.counters[0]) return;
         const uint32_t cur = f.parked[i];
-        fl_flow_thread(f, cur, f.xbuf[cur], f.hbuf[cur], true, false, 0.0, FL_NONE, false, false, false, FlPre{0.0, 0.0, 0.0, 0u, 0u});
+        const bool defer = f.next_list != nullptr;
+        const uint32_t out = fl_flow_thread(f, cur, f.xbuf[cur], f.hbuf[cur], true, false, 0.0, FL_NONE, false, defer, false,
+                                            FlPre{0.0, 0.0, 0.0, 0u, 0u});
+        if (out != FL_NONE) f.next_list[atomicAdd(f.next_count, 1u)] = out;
     }
 #else
     const int lane = threadIdx.x & 31;
@@ -689,7 +699,7 @@ __global__ void __launch_bounds__(256, 2) k_area_flow_long(FlFlow f) {
         i = __shfl_sync(FL_FULL, i, 0);
         if (i >= fl_ld_cg(&f.counters[0])) return;
         const uint32_t cur = f.parked[i];
-        fl_flow_warp(f, cur, fl_ld_cg(&f.xbuf[cur]), fl_ld_cg(&f.hbuf[cur]), true, sm);
+        fl_flow_warp(f, cur, fl_ld_cg(&f.xbuf[cur]), fl_ld_cg(&f.hbuf[cur]), true, sm, f.next_list != nullptr);
     }
 #endif
 }
@@ -952,6 +962,83 @@ __global__ void __launch_bounds__(128) k_elev_flow(uint32_t begin, uint32_t coun
     }
 #endif
     if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
+}
+
+// Levels with few segments (the top of the forest: few, long segments): one WARP per segment, so that long
+// segments of one level run side by side instead of one after the other inside a warp.
+__global__ void __launch_bounds__(128) k_elev_flow_warps(uint32_t begin, uint32_t count,
+                                                          const uint32_t* __restrict__ heads, FlElev e) {
+#ifdef FL_EMU
+    // emulation: one thread per segment, plain batches
+    const uint32_t t = FL_TID;
+    if (t >= count) return;
+    const uint32_t h = heads[begin + t];
+    const uint32_t p = e.recv[h];
+    const bool is_root = (p == h);
+    uint32_t root;
+    double rt_prev, z_prev, e_out, rt_out;
+    if (is_root) { root = e.is_outlet[h] ? h : FL_NONE; rt_prev = 0.0; z_prev = e.elev[h]; e_out = e.elev[h]; rt_out = 0.0; }
+    else {
+        root = e.root_of[p]; rt_prev = e.rt[p]; z_prev = e.elev[p];
+        e_out = root != FL_NONE ? e.elev[root] : 0.0; rt_out = root != FL_NONE ? e.rt[root] : 0.0;
+    }
+    if (root == FL_NONE) {
+        for (uint32_t r = h;; ++r) { e.root_of[r] = FL_NONE; if (r + 1u >= e.n || e.recv[r + 1u] != r) break; }
+        return;
+    }
+    bool changed = false;
+    uint32_t q = h;
+    bool ended = fl_elev_batch<4>(e, q, h, is_root, root, rt_prev, z_prev, e_out, rt_out, changed);
+    while (!ended) ended = fl_elev_batch<4>(e, q, h, false, root, rt_prev, z_prev, e_out, rt_out, changed);
+    if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
+#else
+    __shared__ FlChainSmem chain_smem[4];
+    FlChainSmem& sm = chain_smem[threadIdx.x >> 5];
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= count) return;
+    const uint32_t h = heads[begin + w];
+    const uint32_t p = e.recv[h];
+    const bool is_root = (p == h);
+    uint32_t root;
+    double rt_prev, z_prev, e_out, rt_out;
+    if (is_root) { root = e.is_outlet[h] ? h : FL_NONE; rt_prev = 0.0; z_prev = e.elev[h]; e_out = e.elev[h]; rt_out = 0.0; }
+    else {
+        root = e.root_of[p]; rt_prev = e.rt[p]; z_prev = e.elev[p];
+        e_out = root != FL_NONE ? e.elev[root] : 0.0; rt_out = root != FL_NONE ? e.rt[root] : 0.0;
+    }
+    if (root == FL_NONE) {
+        if (lane == 0)
+            for (uint32_t r = h;; ++r) { e.root_of[r] = FL_NONE; if (r + 1u >= e.n || e.recv[r + 1u] != r) break; }
+        return;
+    }
+    // the head site, identically in every lane (the root's special cases live here); lane 0 stores
+    bool changed = false;
+    {
+        const double t = e.tcel[h];
+        const double eold = e.elev[h];
+        const double rti = 0.0 + (rt_prev + t);
+        if (is_root) rt_out = rti;
+        double z = e_out + e.uplift[h] * fmax(rti - rt_out, 0.0);
+        if (e.tan_slope) {
+            const double ms = e.tan_slope[h];
+            if (ms == ms) {
+                const double d = e.drecv[h];
+                const double slope = (z - z_prev) / d;
+                if (slope > ms) z = z_prev + ms * d;
+            }
+        }
+        changed = (z != eold);
+        if (is_root) e_out = z;
+        __syncwarp();  // every lane has read elev[h] before lane 0 overwrites it
+        if (lane == 0) { e.elev[h] = z; e.rt[h] = rti; e.root_of[h] = root; }
+        rt_prev = rti;
+        z_prev = z;
+    }
+    if (h + 1u < e.n && e.recv[h + 1u] == h)
+        changed |= fl_elev_warp(e, h + 1u, root, rt_prev, z_prev, e_out, rt_out, sm);
+    if (changed && lane == 0) e.flags[FL_FLAG_CHANGED] = 1u;
+#endif
 }
 
 // keys for sorting segment heads by descending nesting height: key = maxh - hgt (heads), FL_NONE otherwise

@@ -34,6 +34,7 @@ double wall_ms() {
 }
 
 #define FL_MAX_ROUNDS 4096u
+#define FL_WARP_LEVEL_MAX 8192u  // K5: levels with at most this many segments run one warp per segment
 enum Stage { ST_RECV = 0, ST_LABEL, ST_LAKE, ST_ORDER, ST_AREA, ST_ELEV, ST_COUNT };
 
 // One numbering of the sites and everything stored in it.
@@ -555,6 +556,7 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     f.A = c->d_A; f.state = c->d_state; f.pre = c->d_pre; f.post1 = c->d_post1; f.post2 = c->d_post2;
     f.xbuf = c->d_xbuf; f.hbuf = c->d_hbuf; f.hgt = c->d_hgt; f.hpre = c->d_hpre; f.flags = c->d_flags;
     f.parked = c->d_parked; f.counters = c->d_flags + FL_FLAG_PARKED; f.park_after = (uint32_t)c->opt_park_after;
+    f.next_list = nullptr; f.next_count = nullptr;
     FL_CK(fl_memset(c->d_nwait, 0, sizeof(uint32_t) * n, c->stream));
     f.nwait = c->d_nwait;
     LAUNCH_N(k_count_waits, n, n, L.recv, L.cmask, c->d_nwait);
@@ -562,15 +564,27 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
         // round-synchronous: list r -> list r+1, one launch per nesting height (estimated from the last
         // iteration; checked below with the flag read-back, more rounds are added if the estimate was short)
         const uint32_t max_rounds = FL_MAX_ROUNDS;
-        FL_CK(fl_memset(c->d_round_count, 0, sizeof(uint32_t) * (max_rounds + 2), c->stream));
+        FL_CK(fl_memset(c->d_round_count, 0, sizeof(uint32_t) * (3 * (size_t)max_rounds + 8), c->stream));
+        uint32_t* park_counters = c->d_round_count + max_rounds + 2;  // [2r] = parked in round r, [2r+1] = taken
+        f.next_list = nullptr; f.next_count = nullptr;
+        f.counters = park_counters;
         LAUNCH_N(k_flow_prepare, n, f, c->d_round_list[0], c->d_round_count);
         uint32_t r = 0;
         uint32_t planned = c->rounds_hint + 2u;
         for (;;) {
             for (; r < planned && r < max_rounds; ++r) {
+                // threads work through list r; long chains are parked and finished by warps in the same round;
+                // both queue the sites whose last child reported into list r+1
+                f.counters = park_counters + 2 * r;
+                f.next_list = c->d_round_list[(r + 1) & 1];
+                f.next_count = c->d_round_count + r + 1;
                 FL_LAUNCH(k_area_round, (unsigned)c->sm_count * 8u, 256, c->stream, f, c->d_round_list[r & 1],
-                          c->d_round_count + r, c->d_round_list[(r + 1) & 1], c->d_round_count + r + 1);
+                          c->d_round_count + r, f.next_list, f.next_count);
                 c->stats.kernel_launches++;
+                if (f.park_after) {
+                    FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 2u, 256, c->stream, f);
+                    c->stats.kernel_launches++;
+                }
             }
             FL_CK(fl_d2h(c->h_rounds, c->d_round_count, sizeof(uint32_t) * (r + 1), c->stream));
             FL_CK(fl_stream_sync(c->stream));
@@ -585,7 +599,7 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
         LAUNCH_N(k_simple_pre, n, f);
         LAUNCH_N(k_area_flow, n, f);
     }
-    if (f.park_after) {  // the parked (long) flows, one warp each, pure dataflow (persistent grid)
+    if (!c->opt_k4_rounds && f.park_after) {  // the parked (long) flows, one warp each, pure dataflow
         FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 4u, 256, c->stream, f);
         c->stats.kernel_launches++;
     }
@@ -631,7 +645,10 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
         const uint32_t b = c->h_offs[g], cnt = c->h_offs[g + 1] - b;
         if (!cnt) continue;
         ++launched;
-        FL_LAUNCH(k_elev_flow, blocks_for(cnt, 128), 128, c->stream, b, cnt, c->d_order, e);
+        if (cnt <= FL_WARP_LEVEL_MAX)  // few segments: a warp each
+            FL_LAUNCH(k_elev_flow_warps, blocks_for(cnt * 32u, 128), 128, c->stream, b, cnt, c->d_order, e);
+        else
+            FL_LAUNCH(k_elev_flow, blocks_for(cnt, 128), 128, c->stream, b, cnt, c->d_order, e);
     }
     c->stats.kernel_launches += launched; c->stats.n_elevation += launched;
     FL_RC(stage_mark(c, 6));
@@ -856,7 +873,7 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     FL_CK(dalloc(c, c->d_nwait, n));
     FL_CK(dalloc(c, c->d_round_list[0], n));
     FL_CK(dalloc(c, c->d_round_list[1], n));
-    FL_CK(dalloc(c, c->d_round_count, FL_MAX_ROUNDS + 2));
+    FL_CK(dalloc(c, c->d_round_count, 3 * (size_t)FL_MAX_ROUNDS + 8));
     FL_CK(dalloc(c, c->d_tcel, n));
     c->sm_count = fl_sm_count();
     LAUNCH_N(k_iota, n, n, c->d_iota);
