@@ -77,6 +77,8 @@ struct FlFlow {
     uint32_t park_after; // a thread parks its flow after climbing this many sites in a row (0 = never)
     uint32_t* next_list;   // round-synchronous mode: sites whose last child has just reported
     uint32_t* next_count;
+    const uint32_t* lvl;   // nesting height of each site's segment in the PREVIOUS iteration (schedule hint)
+    uint32_t level, top_level;  // k_area_flow_long: take parked flows with min(lvl, top_level) == level
 };
 
 // per-warp staging area of the serial chains (warp-level scans)
@@ -677,28 +679,35 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
 }
 #endif
 
-// pass 2: the parked (long) flows.  Persistent: every warp (emulation: thread) takes parked flows until none is left.
+// pass 2: the parked (long) flows, continued by whole warps.  With a schedule hint (f.lvl != null) the
+// kernel is launched once per level of the PREVIOUS iteration's nesting height, bottom-up, and takes only the
+// parked flows of that level: when the forest has not changed, every flow then finds all its tributaries
+// finished and scans its chain without a single wait.  A wrong hint costs hand-offs, never correctness.
 __global__ void __launch_bounds__(256, 2) k_area_flow_long(FlFlow f) {
+    const uint32_t count = fl_ld_cg(&f.counters[0]);
 #ifdef FL_EMU
-    for (;;) {
-        const uint32_t i = atomicAdd(&f.counters[1], 1u);
-        if (i >= f.counters[0]) return;
+    for (uint32_t i = FL_TID; i < count; i += gridDim.x * blockDim.x) {
         const uint32_t cur = f.parked[i];
+        if (f.lvl) {
+            const uint32_t l = f.lvl[cur] < f.top_level ? f.lvl[cur] : f.top_level;
+            if (l != f.level) continue;
+        }
         const bool defer = f.next_list != nullptr;
         const uint32_t out = fl_flow_thread(f, cur, f.xbuf[cur], f.hbuf[cur], true, false, 0.0, FL_NONE, false, defer, false,
                                             FlPre{0.0, 0.0, 0.0, 0u, 0u});
         if (out != FL_NONE) f.next_list[atomicAdd(f.next_count, 1u)] = out;
     }
 #else
-    const int lane = threadIdx.x & 31;
     __shared__ FlChainSmem chain_smem[8];  // one per warp (256 threads)
     FlChainSmem& sm = chain_smem[threadIdx.x >> 5];
-    for (;;) {
-        uint32_t i = 0u;
-        if (lane == 0) i = atomicAdd(&f.counters[1], 1u);
-        i = __shfl_sync(FL_FULL, i, 0);
-        if (i >= fl_ld_cg(&f.counters[0])) return;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = warp; i < count; i += nwarps) {
         const uint32_t cur = f.parked[i];
+        if (f.lvl) {
+            const uint32_t lv = f.lvl[cur];
+            if ((lv < f.top_level ? lv : f.top_level) != f.level) continue;
+        }
         fl_flow_warp(f, cur, fl_ld_cg(&f.xbuf[cur]), fl_ld_cg(&f.hbuf[cur]), true, sm, f.next_list != nullptr);
     }
 #endif
@@ -719,6 +728,8 @@ struct FlElev {
     double* rt;
     uint32_t* root_of;
     uint32_t* flags;
+    uint32_t* lvl;       // out: nesting height of the segment each site belongs to (schedules the next K4)
+    uint32_t lvl_value;  // the height this launch works on
 };
 
 // generator.rs:172-173: celerity = k_i * A_i^0.5;  term = 1.0 / celerity * d_i  (fully parallel; the
@@ -771,6 +782,7 @@ __device__ __forceinline__ bool fl_elev_batch(const FlElev& e, uint32_t& q, uint
             e.elev[i] = z;
             e.rt[i] = rti;
             e.root_of[i] = root;
+            e.lvl[i] = e.lvl_value;
             rt_prev = rti;
             z_prev = z;
             if (nx[k] != i) ended = true;
@@ -857,6 +869,7 @@ __device__ __forceinline__ void fl_elev_window(const FlElev& e, const FlEWin& w,
         e.elev[i] = z;
         e.rt[i] = my_rt;
         e.root_of[i] = root;
+        e.lvl[i] = e.lvl_value;
     }
 }
 
@@ -1031,7 +1044,7 @@ __global__ void __launch_bounds__(128) k_elev_flow_warps(uint32_t begin, uint32_
         changed = (z != eold);
         if (is_root) e_out = z;
         __syncwarp();  // every lane has read elev[h] before lane 0 overwrites it
-        if (lane == 0) { e.elev[h] = z; e.rt[h] = rti; e.root_of[h] = root; }
+        if (lane == 0) { e.elev[h] = z; e.rt[h] = rti; e.root_of[h] = root; e.lvl[h] = e.lvl_value; }
         rt_prev = rti;
         z_prev = z;
     }

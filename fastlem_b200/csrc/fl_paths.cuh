@@ -255,8 +255,8 @@ struct FlNodeArrays {
     const double *areas, *erod, *uplift, *tan, *elev, *drecv;
     double *areas_n, *erod_n, *uplift_n, *tan_n, *elev_n, *drecv_n;
     // u32
-    const uint32_t *recv, *cmask, *rank, *orig_of;
-    uint32_t *recv_n, *cmask_n, *rank_n, *orig_of_n;
+    const uint32_t *recv, *cmask, *rank, *orig_of, *lvl;
+    uint32_t *recv_n, *cmask_n, *rank_n, *orig_of_n, *lvl_n;
     const uint8_t* is_outlet;
     uint8_t* is_outlet_n;
 };
@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(256) k_permute_nodes(uint32_t n, const uint32_
     a.cmask_n[p] = a.cmask[q];
     if (a.rank) a.rank_n[p] = a.rank[q];
     a.orig_of_n[p] = a.orig_of[q];
+    if (a.lvl) a.lvl_n[p] = a.lvl[q];
     a.is_outlet_n[p] = a.is_outlet[q];
 }
 

@@ -54,6 +54,7 @@ struct Layout {
     double* drecv = nullptr;
     uint32_t* recv = nullptr;
     uint32_t* cmask = nullptr;
+    uint32_t* lvl = nullptr;  // nesting height of the site's segment in the last K5 (sweep 3)
 };
 
 }  // namespace
@@ -118,8 +119,8 @@ struct fastlem_ctx {
     uint32_t* d_nwait = nullptr;
     uint32_t* d_round_list[2] = {nullptr, nullptr};
     uint32_t* d_round_count = nullptr;
-    uint32_t rounds_hint = 16, last_rounds = 0;
-    int64_t opt_k4_rounds = 1;
+    uint32_t rounds_hint = 16, last_rounds = 0, prev_maxh = 0;
+    int64_t opt_k4_rounds = 0;
     double* d_tcel = nullptr;
     int sm_count = 148;
     int64_t opt_park_after = 8;
@@ -396,6 +397,7 @@ int rebuild_layout(fastlem_ctx* c, const double* weight) {
     a.recv = L.recv; a.cmask = L.cmask; a.rank = c->rank_ready ? L.rank : nullptr; a.orig_of = L.orig_of;
     a.recv_n = M.recv; a.cmask_n = M.cmask; a.rank_n = M.rank; a.orig_of_n = M.orig_of;
     a.is_outlet = L.is_outlet; a.is_outlet_n = M.is_outlet;
+    a.lvl = nullptr; a.lvl_n = nullptr;
     LAUNCH_N(k_permute_nodes, n, n, c->d_newpos, a);
     c->cur ^= 1;
     if (c->rank_ready) LAUNCH_N(k_rank_inverse, n, n, M.rank, c->d_rank_to_node);
@@ -509,6 +511,7 @@ int rebuild_layout_flow(fastlem_ctx* c, const double* weight) {
     a.recv = L.recv; a.cmask = L.cmask; a.rank = c->rank_ready ? L.rank : nullptr; a.orig_of = L.orig_of;
     a.recv_n = M.recv; a.cmask_n = M.cmask; a.rank_n = M.rank; a.orig_of_n = M.orig_of;
     a.is_outlet = L.is_outlet; a.is_outlet_n = M.is_outlet;
+    a.lvl = L.lvl; a.lvl_n = M.lvl;
     LAUNCH_N(k_permute_nodes, n, n, c->d_newpos, a);
     c->cur ^= 1;
     if (c->rank_ready) LAUNCH_N(k_rank_inverse, n, n, M.rank, c->d_rank_to_node);
@@ -557,6 +560,7 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     f.xbuf = c->d_xbuf; f.hbuf = c->d_hbuf; f.hgt = c->d_hgt; f.hpre = c->d_hpre; f.flags = c->d_flags;
     f.parked = c->d_parked; f.counters = c->d_flags + FL_FLAG_PARKED; f.park_after = (uint32_t)c->opt_park_after;
     f.next_list = nullptr; f.next_count = nullptr;
+    f.lvl = nullptr; f.level = 0; f.top_level = 0;
     FL_CK(fl_memset(c->d_nwait, 0, sizeof(uint32_t) * n, c->stream));
     f.nwait = c->d_nwait;
     LAUNCH_N(k_count_waits, n, n, L.recv, L.cmask, c->d_nwait);
@@ -599,9 +603,16 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
         LAUNCH_N(k_simple_pre, n, f);
         LAUNCH_N(k_area_flow, n, f);
     }
-    if (!c->opt_k4_rounds && f.park_after) {  // the parked (long) flows, one warp each, pure dataflow
-        FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 4u, 256, c->stream, f);
-        c->stats.kernel_launches++;
+    if (!c->opt_k4_rounds && f.park_after) {
+        // the parked (long) flows, one warp each: one launch per nesting height of the previous iteration
+        f.lvl = L.lvl;
+        f.top_level = c->prev_maxh;
+        for (uint32_t lv = 0; lv <= c->prev_maxh; ++lv) {
+            f.level = lv;
+            FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 2u, 256, c->stream, f);
+            c->stats.kernel_launches++;
+        }
+        f.lvl = nullptr;
     }
     c->stats.n_area += 4;
     FL_RC(stage_mark(c, 8));  // end of K4
@@ -627,6 +638,7 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     c->stats.path_levels = maxh + 1;
     c->stats.paths = n_heads;
     c->rounds_hint = c->last_rounds ? c->last_rounds : maxh + 1;
+    c->prev_maxh = maxh;
     if (rebuilt) { c->segs_at_rebuild = n_heads; c->maxh_at_rebuild = maxh; }
     else if (c->opt_rebuild_every == 0 &&
              ((unsigned long long)n_heads * 100ull > (unsigned long long)c->segs_at_rebuild * 104ull ||
@@ -639,12 +651,13 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     LAUNCH_N(k_celerity_term, n, n, L.erod, c->d_A, L.drecv, c->d_tcel);
     e.n = n; e.recv = L.recv; e.drecv = L.drecv; e.tcel = c->d_tcel; e.uplift = L.uplift;
     e.tan_slope = c->has_tan ? L.tan : nullptr; e.is_outlet = L.is_outlet; e.elev = L.elev; e.rt = c->d_rt;
-    e.root_of = c->d_root_of; e.flags = c->d_flags;
+    e.root_of = c->d_root_of; e.flags = c->d_flags; e.lvl = L.lvl; e.lvl_value = 0;
     uint32_t launched = 0;
     for (uint32_t g = 0; g <= maxh; ++g) {
         const uint32_t b = c->h_offs[g], cnt = c->h_offs[g + 1] - b;
         if (!cnt) continue;
         ++launched;
+        e.lvl_value = maxh - g;
         if (cnt <= FL_WARP_LEVEL_MAX)  // few segments: a warp each
             FL_LAUNCH(k_elev_flow_warps, blocks_for(cnt * 32u, 128), 128, c->stream, b, cnt, c->d_order, e);
         else
@@ -687,6 +700,8 @@ int reset_layout(fastlem_ctx* c) {
     FL_CK(fl_d2d(L.is_outlet, O.is_outlet, n, c->stream));
     FL_CK(fl_d2d(L.elev, c->d_init, sizeof(double) * n, c->stream));
     LAUNCH_N(k_iota, n, n, L.orig_of);
+    FL_CK(fl_memset(L.lvl, 0, sizeof(uint32_t) * n, c->stream));
+    c->prev_maxh = 0;
     if (c->rank_ready) {
         FL_CK(fl_d2d(L.rank, O.rank, sizeof(uint32_t) * n, c->stream));
         FL_CK(fl_memset(c->d_rank_to_node, 0xFF, sizeof(uint32_t) * n, c->stream));
@@ -831,6 +846,7 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
         FL_CK(dalloc(c, S.drecv, n));
         FL_CK(dalloc(c, S.recv, n));
         FL_CK(dalloc(c, S.cmask, n));
+        FL_CK(dalloc(c, S.lvl, n));
     }
     FL_CK(fl_h2d(c->orig.row_ptr, row_ptr, sizeof(uint32_t) * n1, c->stream));
     if (nnz) {
