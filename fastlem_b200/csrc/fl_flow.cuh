@@ -702,13 +702,25 @@ __global__ void __launch_bounds__(256, 2) k_area_flow_long(FlFlow f) {
     FlChainSmem& sm = chain_smem[threadIdx.x >> 5];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t i = warp; i < count; i += nwarps) {
-        const uint32_t cur = f.parked[i];
-        if (f.lvl) {
-            const uint32_t lv = f.lvl[cur];
-            if ((lv < f.top_level ? lv : f.top_level) != f.level) continue;
+    const int lane = threadIdx.x & 31;
+    // every warp looks at 32 parked flows at a time (one per lane) and walks the ones of this level
+    for (uint32_t base = warp * 32u; base < count; base += nwarps * 32u) {
+        const uint32_t i = base + (uint32_t)lane;
+        uint32_t mine = FL_NONE;
+        if (i < count) {
+            mine = f.parked[i];
+            if (f.lvl) {
+                const uint32_t lv = f.lvl[mine];
+                if ((lv < f.top_level ? lv : f.top_level) != f.level) mine = FL_NONE;
+            }
         }
-        fl_flow_warp(f, cur, fl_ld_cg(&f.xbuf[cur]), fl_ld_cg(&f.hbuf[cur]), true, sm, f.next_list != nullptr);
+        uint32_t todo = __ballot_sync(FL_FULL, mine != FL_NONE);
+        while (todo) {
+            const int src = __ffs((int)todo) - 1;
+            todo &= todo - 1u;
+            const uint32_t cur = __shfl_sync(FL_FULL, mine, src);
+            fl_flow_warp(f, cur, fl_ld_cg(&f.xbuf[cur]), fl_ld_cg(&f.hbuf[cur]), true, sm, f.next_list != nullptr);
+        }
     }
 #endif
 }
