@@ -121,6 +121,7 @@ struct fastlem_ctx {
     uint32_t* d_round_count = nullptr;
     uint32_t rounds_hint = 16, last_rounds = 0, prev_maxh = 0;
     int64_t opt_k4_rounds = 0;
+    int64_t opt_k4_long_levels = 0;
     double* d_tcel = nullptr;
     int sm_count = 148;
     int64_t opt_park_after = 8;
@@ -605,14 +606,19 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     }
     if (!c->opt_k4_rounds && f.park_after) {
         // the parked (long) flows, one warp each: one launch per nesting height of the previous iteration
-        f.lvl = L.lvl;
-        f.top_level = c->prev_maxh;
-        for (uint32_t lv = 0; lv <= c->prev_maxh; ++lv) {
-            f.level = lv;
-            FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 2u, 256, c->stream, f);
+        if (c->opt_k4_long_levels) {
+            f.lvl = L.lvl;
+            f.top_level = c->prev_maxh;
+            for (uint32_t lv = 0; lv <= c->prev_maxh; ++lv) {
+                f.level = lv;
+                FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 2u, 256, c->stream, f);
+                c->stats.kernel_launches++;
+            }
+            f.lvl = nullptr;
+        } else {
+            FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 4u, 256, c->stream, f);
             c->stats.kernel_launches++;
         }
-        f.lvl = nullptr;
     }
     c->stats.n_area += 4;
     FL_RC(stage_mark(c, 8));  // end of K4
@@ -799,6 +805,8 @@ int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
     } else if (s == "park_after") {
         if (value != 0 && value < 4) return fail(c, FASTLEM_E_INVALID, "option park_after: 0 (never) or >= 4");
         c->opt_park_after = value;
+    } else if (s == "k4_long_levels") {
+        c->opt_k4_long_levels = value != 0;
     } else if (s == "k4_rounds") {
         c->opt_k4_rounds = value != 0;
     } else if (s == "rebuild_every") {
