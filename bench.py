@@ -219,17 +219,23 @@ def main():
     work, launches_all = float(w[0]), int(w[1])
     value = work / wall_max
 
-    # e2e through the C ABI with host buffers (same steps, fresh context each time)
+    # e2e through the C ABI with host buffers (same steps, fresh context each time); the host buffers are
+    # pinned copies of the model (torch.pin_memory), handed to the C ABI as plain pointers
+    def pinned(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    hm = {k: pinned(m[k]) for k in ("row_ptr", "col", "dist", "areas")}
+    hp = {"initial": pinned(initial), "erodibility": pinned(p["erodibility"]), "uplift": pinned(p["uplift"]),
+          "outlets": pinned(outlets)}
     e2e_iters, e2e_t = 0, 0.0
-    out = np.empty(n, dtype=np.float64)
+    out = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
     barrier()
     t1 = time.perf_counter()
     for _ in range(args.steps):
         with _native.Context(local_rank) as c2:
             if args.sweep is not None:
                 c2.set_option("sweep", args.sweep)
-            c2.set_graph(m["row_ptr"], m["col"], m["dist"], m["areas"])
-            c2.set_parameters(initial, p["erodibility"], p["uplift"], None, outlets)
+            c2.set_graph(hm["row_ptr"], hm["col"], hm["dist"], hm["areas"])
+            c2.set_parameters(hp["initial"], hp["erodibility"], hp["uplift"], None, hp["outlets"])
             _, it = c2.generate(out=out)
             e2e_iters += it
             e2e_stats = c2.stats()
@@ -244,7 +250,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
-        dom = max(("receivers", "labels", "area", "elevation"), key=lambda k: stage_ms[k])
+        dom = max(("receivers", "area", "elevation"), key=lambda k: stage_ms[k])
         # one "launch" of a stage = one pass of that stage over all n sites (= one iteration's worth)
         passes = iters_total
         alg_bytes = STAGE_BYTES[dom] * n
@@ -256,6 +262,8 @@ def main():
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                     "bytes_per_pass": alg_bytes, "ms_per_pass": stage_ms[dom] / max(passes, 1),
                     "kernel_launches_per_pass": stage_n[dom] / max(passes, 1),
+                    "kernel_names": {"receivers": "k_receivers_mask", "area": "k_count_waits+k_simple_pre+k_area_flow+k_area_flow_long",
+                                     "elevation": "k_celerity_term+k_elev_flow[_warps]"}[dom],
                     "receivers_kernel": {"achieved": k1, "frac": k1 / peak,
                                          "ms_per_launch": stage_ms["receivers"] / max(stage_n["receivers"], 1)},
                     "whole_iteration": {"achieved": whole, "frac": whole / peak, "bytes": iter_bytes},
@@ -281,11 +289,13 @@ def main():
                            "parallelism": "1 terrain per GPU" if world > 1 else "single GPU",
                            "sweep": args.sweep},
                 "generate_seconds": wall_max / args.steps, "device_ms_per_step": 1e3 * dev_max / args.steps,
-                "depth_first_last": [last["depth_first"], last["depth_last"]],
+                "first_iteration_tree_depth": last["depth_first"],
+                "layout": {"rebuilds_per_step": last["rebuilds"], "nesting_levels": last["path_levels"],
+                           "segments": last["paths"]},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(graph_bytes + param_bytes),
                         "d2h_bytes_per_step": int(8 * n), "seconds_per_step": float(te[0]) / args.steps,
                         "flood_rank_host_ms": e2e_stats["ms_flood_rank"], "upload_ms": e2e_stats["ms_upload"],
-                        "host_buffers": "pageable numpy arrays handed to the C ABI"},
+                        "host_buffers": "pinned host arrays handed to the C ABI as plain pointers"},
                 "gpu_launches": launches_all, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "workload_build_s": t_build}
         print(json.dumps(line), flush=True)

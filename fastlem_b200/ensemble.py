@@ -1,0 +1,56 @@
+"""Ensembles of independent terrains over several GPUs.
+
+A single terrain's receiver forest is global, so one terrain = one GPU ("replicas only").  An ensemble
+(different seeds / erodibility fields / outlet masks) shards trivially: member t runs on rank t mod world,
+every rank owns one fastlem context per member it runs, there is no collective on the data path, and the
+elevations are gathered once at the end (NCCL all_gather over NVLink on GPUs, gloo in the CPU tests).
+"""
+import numpy as np
+
+
+def members_of_rank(n_members, rank, world):
+    """Round-robin assignment: member t -> rank t % world."""
+    return list(range(rank, n_members, world))
+
+
+def run_members(member_inputs, make_context, max_iteration=None):
+    """Run generate() for this rank's members.
+
+    member_inputs: list of dicts with keys row_ptr, col, dist, areas, initial, erodibility, uplift, tan_max_slope,
+                   outlets (the boundary format of include/fastlem_b200.h)
+    make_context : callable returning a fastlem_b200._native.Context
+    returns      : list of (elevations, iterations)
+    """
+    out = []
+    for m in member_inputs:
+        with make_context() as ctx:
+            ctx.set_graph(m["row_ptr"], m["col"], m["dist"], m["areas"])
+            ctx.set_parameters(m["initial"], m["erodibility"], m["uplift"], m.get("tan_max_slope"), m["outlets"])
+            out.append(ctx.generate(max_iteration))
+    return out
+
+
+def gather_elevations(local, n_members, n_sites, rank, world, device="cpu"):
+    """All-gather the members' elevations: returns an (n_members, n_sites) float64 array on every rank.
+
+    local: dict member index -> elevations (numpy) for the members this rank ran.
+    Uses torch.distributed when world > 1 (the caller has initialised the process group: nccl on GPUs, gloo on CPU).
+    """
+    import torch
+    per_rank = (n_members + world - 1) // world
+    buf = torch.zeros((per_rank, n_sites), dtype=torch.float64, device=device)
+    mine = members_of_rank(n_members, rank, world)
+    for k, t in enumerate(mine):
+        buf[k].copy_(torch.from_numpy(np.ascontiguousarray(local[t])))
+    if world == 1:
+        gathered = [buf]
+    else:
+        import torch.distributed as dist
+        gathered = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(gathered, buf)
+    out = np.empty((n_members, n_sites), dtype=np.float64)
+    for r in range(world):
+        g = gathered[r].cpu().numpy()
+        for k, t in enumerate(members_of_rank(n_members, r, world)):
+            out[t] = g[k]
+    return out

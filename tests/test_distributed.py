@@ -1,0 +1,57 @@
+"""CPU tier: the multi-GPU path (ensemble sharding + final gather) with gloo, world size 2.
+Compute runs on the host emulation build here; on GPUs the same code runs with the product library and nccl."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from scenarios import ROOT, scenario
+
+
+def _member(name, n, k_scale):
+    m, p, outlets, initial, _ = scenario(name, n)
+    return dict(row_ptr=m["row_ptr"], col=m["col"], dist=m["dist"], areas=m["areas"], initial=initial,
+                erodibility=p["erodibility"] * k_scale, uplift=p["uplift"], tan_max_slope=None, outlets=outlets), m, p
+
+
+def _worker(rank, world, port, emu_lib, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from fastlem_b200 import _native, ensemble
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_members = 5
+    scales = [1.0, 0.5, 2.0, 1.5, 0.75]
+    mine = ensemble.members_of_rank(n_members, rank, world)
+    inputs = [_member("uniform", 600, scales[t])[0] for t in mine]
+    res = ensemble.run_members(inputs, lambda: _native.Context(0, emu_lib), max_iteration=None)
+    local = {t: res[k][0] for k, t in enumerate(mine)}
+    allv = ensemble.gather_elevations(local, n_members, inputs[0]["areas"].size, rank, world)
+    np.save(os.path.join(out_dir, f"gathered_{rank}.npy"), allv)
+    dist.destroy_process_group()
+
+
+def test_members_of_rank_partition():
+    from fastlem_b200 import ensemble
+    for world in (1, 2, 4, 8):
+        seen = sorted(t for r in range(world) for t in ensemble.members_of_rank(64, r, world))
+        assert seen == list(range(64))
+        sizes = [len(ensemble.members_of_rank(64, r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_ensemble_two_ranks_gloo(tmp_path, emu_lib, oracle):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 1000)
+    mp.spawn(_worker, args=(2, port, emu_lib, str(tmp_path)), nprocs=2, join=True)
+    a = np.load(tmp_path / "gathered_0.npy")
+    b = np.load(tmp_path / "gathered_1.npy")
+    assert np.array_equal(a, b), "every rank holds the same gathered ensemble"
+    scales = [1.0, 0.5, 2.0, 1.5, 0.75]
+    for t, sc in enumerate(scales):
+        inp, m, p = _member("uniform", 600, sc)
+        ref, _ = oracle.generate(m, inp["erodibility"], inp["uplift"], None, inp["outlets"], inp["initial"])
+        assert np.array_equal(a[t], ref), f"member {t}"
