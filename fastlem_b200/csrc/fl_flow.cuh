@@ -25,9 +25,14 @@
 #pragma once
 #include "fl_paths.cuh"
 
-#define FL_ST_COUNT_MASK 0x00FFFFFFu
-#define FL_ST_NP_SHIFT 24
-#define FL_ST_NP_MASK 0x0F000000u
+// state word of a site: [0,8) children reported, [8,12) np (posts; 15 = more than two), [12,30) hpre (max child
+// height + 1; 0x3FFFF = too large, read hpre[]), bit 30 pre/posts published, bit 31 a flow is waiting below
+#define FL_ST_COUNT_MASK 0x000000FFu
+#define FL_ST_NP_SHIFT 8
+#define FL_ST_NP_MASK 0x00000F00u
+#define FL_ST_HP_SHIFT 12
+#define FL_ST_HP_MASK 0x3FFFF000u
+#define FL_ST_HP_OVER 0x3FFFFu
 #define FL_ST_PRE_READY 0x40000000u
 #define FL_ST_SCAN_ARRIVED 0x80000000u
 #define FL_TB 4  // sites per batch of a thread-level flow
@@ -53,6 +58,26 @@ __device__ __forceinline__ uint32_t fl_dep0(uint32_t v) {
     return z;
 }
 #endif
+
+__device__ __forceinline__ uint32_t fl_st_publish(uint32_t np, uint32_t hp) {
+    const uint32_t h18 = hp < FL_ST_HP_OVER ? hp : FL_ST_HP_OVER;
+    return FL_ST_PRE_READY | (np << FL_ST_NP_SHIFT) | (h18 << FL_ST_HP_SHIFT);
+}
+__device__ __forceinline__ uint32_t fl_st_np(uint32_t s) { return (s & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT; }
+// max child height + 1 of site i, from its state word s (i must already carry the address dependency on s)
+__device__ __forceinline__ uint32_t fl_st_hp(uint32_t s, const uint32_t* hpre, uint32_t i) {
+    const uint32_t h = (s & FL_ST_HP_MASK) >> FL_ST_HP_SHIFT;
+    return h != FL_ST_HP_OVER ? h : fl_ld_cg(&hpre[i]);
+}
+// pre[] and post1[] are filled with this bit pattern (a NaN no addition produces) before every K4, so a
+// speculative load of them validates itself: anything else is a value published in this iteration.
+__device__ __forceinline__ bool fl_is_unset(double v) {
+#ifdef FL_EMU
+    unsigned long long b; std::memcpy(&b, &v, 8); return b == 0xFFFFFFFFFFFFFFFFull;
+#else
+    return __double_as_longlong(v) == -1ll;
+#endif
+}
 
 struct FlFlow {
     uint32_t n;
@@ -168,10 +193,10 @@ __device__ uint32_t fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint
             for (int k = 0; k < FL_TB; ++k) {
                 pr[k] = 0.0; q1[k] = 0.0; q2[k] = 0.0; hq[k] = 0u;
                 if (st[k] & FL_ST_PRE_READY) {
-                    const uint32_t npk = (st[k] & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT;
+                    const uint32_t npk = fl_st_np(st[k]);
                     const uint32_t i = cur - k + fl_dep0(st[k]);
                     pr[k] = fl_ld_cg(&f.pre[i]);
-                    hq[k] = fl_ld_cg(&f.hpre[i]);
+                    hq[k] = fl_st_hp(st[k], f.hpre, i);
                     if (npk >= 1u && npk != 15u) q1[k] = fl_ld_cg(&f.post1[i]);
                     if (npk >= 2u && npk != 15u) q2[k] = fl_ld_cg(&f.post2[i]);
                 }
@@ -187,7 +212,7 @@ __device__ uint32_t fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint
                     if (nl == 0u) {
                         y = hc ? (ar[k] + x) : ar[k];
                     } else if (st[k] & FL_ST_PRE_READY) {
-                        const uint32_t npk = (st[k] & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT;
+                        const uint32_t npk = fl_st_np(st[k]);
                         y = hc ? (pr[k] + x) : pr[k];
                         if (npk == 15u) y = fl_add_posts(f, idx, y);
                         else {
@@ -241,9 +266,9 @@ __device__ uint32_t fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint
                         if (!(s & FL_ST_PRE_READY)) return FL_NONE;  // the last arriver of `cur` takes over
                     }
                     const uint32_t i = cur + fl_dep0(s);
-                    np = (s & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT;
+                    np = fl_st_np(s);
                     pre = fl_ld_cg(&f.pre[i]);
-                    hp = fl_ld_cg(&f.hpre[i]);
+                    hp = fl_st_hp(s, f.hpre, i);
                     if (np >= 1u && np != 15u) p1 = fl_ld_cg(&f.post1[i]);
                     if (np >= 2u && np != 15u) p2 = fl_ld_cg(&f.post2[i]);
                 }
@@ -290,7 +315,7 @@ __device__ uint32_t fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint
         if (np >= 1u && np != 15u) f.post1[p] = p1;
         if (np >= 2u && np != 15u) f.post2[p] = p2;
         __threadfence();
-        const uint32_t old = atomicOr(&f.state[p], FL_ST_PRE_READY | (np << FL_ST_NP_SHIFT));
+        const uint32_t old = atomicOr(&f.state[p], fl_st_publish(np, hp));
         if (!(old & FL_ST_SCAN_ARRIVED)) return FL_NONE;  // the flow below p has not arrived yet; it will pick these up
         const uint32_t pi = p + fl_dep0(old);
         x = fl_ld_cg(&f.xbuf[pi]);
@@ -327,7 +352,7 @@ __global__ void __launch_bounds__(256) k_simple_pre(FlFlow f) {
     f.hpre[q] = hp;
     if (np >= 1u && np != 15u) f.post1[q] = p1;
     if (np >= 2u && np != 15u) f.post2[q] = p2;
-    f.state[q] = FL_ST_PRE_READY | (np << FL_ST_NP_SHIFT);
+    f.state[q] = fl_st_publish(np, hp);
 }
 
 // pass 1: thread-level flows start at (a) leaves that are the tail of a chain and (b) ready sites that end
@@ -402,7 +427,7 @@ __global__ void __launch_bounds__(256) k_flow_prepare(FlFlow f, uint32_t* list, 
                 f.hpre[q] = hp;
                 if (np >= 1u && np != 15u) f.post1[q] = p1;
                 if (np >= 2u && np != 15u) f.post2[q] = p2;
-                f.state[q] = FL_ST_PRE_READY | (np << FL_ST_NP_SHIFT);
+                f.state[q] = fl_st_publish(np, hp);
             }
             start = !has_chain;  // a tail that waits for nobody
         }
@@ -425,7 +450,7 @@ __device__ uint32_t fl_round_entry(const FlFlow& f, uint32_t p) {
     if (in.np >= 1u && in.np != 15u) f.post1[p] = in.p1;
     if (in.np >= 2u && in.np != 15u) f.post2[p] = in.p2;
     __threadfence();
-    const uint32_t old = atomicOr(&f.state[p], FL_ST_PRE_READY | (in.np << FL_ST_NP_SHIFT));
+    const uint32_t old = atomicOr(&f.state[p], fl_st_publish(in.np, in.hp));
     if (!(old & FL_ST_SCAN_ARRIVED)) return FL_NONE;  // the flow below p has not arrived yet; it will pick these up
     const uint32_t pi = p + fl_dep0(old);
     const double x = fl_ld_cg(&f.xbuf[pi]);
@@ -460,12 +485,12 @@ __device__ __forceinline__ uint32_t fl_warp_max(uint32_t v) {
 // ------------------------------------------------------------------------------------------------
 struct FlWin {  // one 32-site window of a chain: lane l holds site base - l
     uint32_t cm, rc, st;
-    double ar;
+    double ar, pre, p1;  // pre / p1: speculative copies of pre[] / post1[] (self-validating, see fl_is_unset)
 };
 
 __device__ __forceinline__ FlWin fl_win_load(const FlFlow& f, uint32_t base, int lane) {
     FlWin w;
-    w.cm = 0u; w.rc = FL_NONE; w.st = 0u; w.ar = 0.0;
+    w.cm = 0u; w.rc = FL_NONE; w.st = 0u; w.ar = 0.0; w.pre = 0.0; w.p1 = 0.0;
     const long long li = (long long)base - lane;
     if (li >= 0) {
         const uint32_t idx = (uint32_t)li;
@@ -473,9 +498,13 @@ __device__ __forceinline__ FlWin fl_win_load(const FlFlow& f, uint32_t base, int
         w.rc = f.recv[idx];
         w.ar = f.areas[idx];
         w.st = fl_ld_relaxed(&f.state[idx]);
+        w.pre = fl_ld_cg(&f.pre[idx]);
+        w.p1 = fl_ld_cg(&f.post1[idx]);
     }
     return w;
 }
+
+#define FL_WDEPTH 3  // windows kept in flight on a long chain
 
 __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t hrun, bool has_chain, FlChainSmem& sm,
                              bool defer) {
@@ -483,16 +512,18 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
     bool resume = false;
     double pre = 0.0, p1 = 0.0, p2 = 0.0;
     uint32_t np = 0, hp = 0;
-    bool have_win = false;  // `win` holds the window whose lane 0 is `cur`
-    FlWin win;
-    win.cm = 0u; win.rc = FL_NONE; win.st = 0u; win.ar = 0.0;
+    // ring[j] holds the window whose lane 0 is site cur - 32*j, for j < nring
+    FlWin ring[FL_WDEPTH];
+    uint32_t nring = 0;
+#pragma unroll
+    for (int j = 0; j < FL_WDEPTH; ++j) { ring[j].cm = 0u; ring[j].rc = FL_NONE; ring[j].st = 0u; ring[j].ar = 0.0; ring[j].pre = 0.0; ring[j].p1 = 0.0; }
     for (;;) {
         double y = 0.0;
         uint32_t p = FL_NONE;
         bool at_head = false;
         if (!resume) {
-            if (!have_win) win = fl_win_load(f, cur, lane);
-            have_win = false;
+            if (nring == 0u) { ring[0] = fl_win_load(f, cur, lane); nring = 1u; }
+            const FlWin win = ring[0];
             const long long li = (long long)cur - lane;
             const bool valid = li >= 0;
             const uint32_t idx = (uint32_t)li;
@@ -507,21 +538,34 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
             const uint32_t readymask = __ballot_sync(FL_FULL, ready);
             const uint32_t nproc = readymask == FL_FULL ? 32u : (uint32_t)__ffs((int)~readymask) - 1u;
             const bool lit = (uint32_t)lane < nproc && nl > 0u;
+            const bool climbs = valid && idx > 0u && win.rc == idx - 1u;
+            // keep FL_WDEPTH windows in flight while the chain goes on
+            const bool goes_on = nproc == 32u && __shfl_sync(FL_FULL, (int)climbs, 31) && cur >= 32u;
+            if (goes_on) {
+#pragma unroll
+                for (int j = 1; j < FL_WDEPTH; ++j)
+                    if (nring == (uint32_t)j && cur >= 32u * (uint32_t)j) { ring[j] = fl_win_load(f, cur - 32u * (uint32_t)j, lane); nring = (uint32_t)j + 1u; }
+            }
             double b = win.ar, q1 = 0.0, q2 = 0.0;
             uint32_t npk = 0u, hq = 0u;
-            if (lit) {  // loads address-dependent on the flag: no fence on the reader side
-                npk = (win.st & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT;
-                const uint32_t i = idx + fl_dep0(win.st);
-                b = fl_ld_cg(&f.pre[i]);
-                hq = fl_ld_cg(&f.hpre[i]);
-                if (npk >= 1u && npk != 15u) q1 = fl_ld_cg(&f.post1[i]);
-                if (npk >= 2u && npk != 15u) q2 = fl_ld_cg(&f.post2[i]);
+            if (lit) {
+                npk = fl_st_np(win.st);
+                b = win.pre;
+                q1 = win.p1;
+                hq = (win.st & FL_ST_HP_MASK) >> FL_ST_HP_SHIFT;
             }
-            // prefetch the next window while this one is being added up
-            FlWin nxt;
-            nxt.cm = 0u; nxt.rc = FL_NONE; nxt.st = 0u; nxt.ar = 0.0;
-            const bool want_next = nproc == 32u && cur >= 32u;
-            if (want_next) nxt = fl_win_load(f, cur - 32u, lane);
+            // speculative copies that cannot be trusted (or are not enough) are re-read, address-dependent on the flag
+            const bool redo = lit && (fl_is_unset(b) || (npk >= 1u && npk != 15u && fl_is_unset(q1)) ||
+                                      (npk >= 2u && npk != 15u) || hq == FL_ST_HP_OVER);
+            if (__ballot_sync(FL_FULL, redo)) {
+                if (redo) {
+                    const uint32_t i = idx + fl_dep0(win.st);
+                    b = fl_ld_cg(&f.pre[i]);
+                    hq = fl_st_hp(win.st, f.hpre, i);
+                    if (npk >= 1u && npk != 15u) q1 = fl_ld_cg(&f.post1[i]);
+                    if (npk >= 2u && npk != 15u) q2 = fl_ld_cg(&f.post2[i]);
+                }
+            }
             const uint32_t postmask = __ballot_sync(FL_FULL, lit && npk != 0u);
             double mine;
             if (postmask == 0u) {
@@ -568,7 +612,6 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
             }
             const uint32_t hw = fl_warp_max((uint32_t)lane < nproc ? hq : 0u);
             if (hw > hrun) hrun = hw;
-            const bool climbs = valid && idx > 0u && win.rc == idx - 1u;
             if ((uint32_t)lane < nproc) {
                 f.A[idx] = mine;
                 if (climbs) f.hgt[idx] = FL_NONE;
@@ -581,14 +624,20 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
                     y = fl_shfl(mine, lastl);
                     p = __shfl_sync(FL_FULL, win.rc, lastl);
                     cur -= (uint32_t)lastl;
+                    nring = 0u;
                 } else {
                     has_chain = true;
                     cur -= nproc;
-                    if (nproc == 32u) {  // whole window climbed
-                        if (want_next) { win = nxt; have_win = true; }
+                    if (nproc == 32u) {  // whole window climbed: shift the ring
+#pragma unroll
+                        for (int j = 0; j + 1 < FL_WDEPTH; ++j) ring[j] = ring[j + 1];
+                        nring = nring > 0u ? nring - 1u : 0u;
                         continue;
                     }
+                    nring = 0u;
                 }
+            } else {
+                nring = 0u;
             }
         }
         if (!at_head) {
@@ -611,9 +660,9 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
                     sv = __shfl_sync(FL_FULL, sv, 0);
                     if (!(sv & FL_ST_PRE_READY)) return;  // the last arriver of `cur` takes over
                     const uint32_t i = cur + fl_dep0(sv);
-                    np = (sv & FL_ST_NP_MASK) >> FL_ST_NP_SHIFT;
+                    np = fl_st_np(sv);
                     pre = fl_ld_cg(&f.pre[i]);
-                    hp = fl_ld_cg(&f.hpre[i]);
+                    hp = fl_st_hp(sv, f.hpre, i);
                     if (np >= 1u && np != 15u) p1 = fl_ld_cg(&f.post1[i]);
                     if (np >= 2u && np != 15u) p2 = fl_ld_cg(&f.post2[i]);
                 }
@@ -628,6 +677,7 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
             }
             if (lane == 0) f.A[cur] = y;
             p = f.recv[cur];
+            nring = 0u;
             if (cur > 0u && p == cur - 1u) {
                 if (lane == 0) f.hgt[cur] = FL_NONE;
                 x = y;
@@ -667,7 +717,7 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
             if (np >= 1u && np != 15u) f.post1[p] = p1;
             if (np >= 2u && np != 15u) f.post2[p] = p2;
             __threadfence();
-            old = atomicOr(&f.state[p], FL_ST_PRE_READY | (np << FL_ST_NP_SHIFT));
+            old = atomicOr(&f.state[p], fl_st_publish(np, hp));
         }
         old = __shfl_sync(FL_FULL, old, 0);
         if (!(old & FL_ST_SCAN_ARRIVED)) return;
@@ -700,19 +750,28 @@ __global__ void __launch_bounds__(256, 2) k_area_flow_long(FlFlow f) {
 #else
     __shared__ FlChainSmem chain_smem[8];  // one per warp (256 threads)
     FlChainSmem& sm = chain_smem[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    if (!f.lvl) {
+        // no schedule: every warp takes the next parked flow (dynamic balancing through one atomic counter)
+        for (;;) {
+            uint32_t i = 0u;
+            if (lane == 0) i = atomicAdd(&f.counters[1], 1u);
+            i = __shfl_sync(FL_FULL, i, 0);
+            if (i >= count) return;
+            const uint32_t cur = f.parked[i];
+            fl_flow_warp(f, cur, fl_ld_cg(&f.xbuf[cur]), fl_ld_cg(&f.hbuf[cur]), true, sm, f.next_list != nullptr);
+        }
+    }
+    // scheduled by level: every warp looks at 32 parked flows at a time (one per lane), walks those of this level
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    // every warp looks at 32 parked flows at a time (one per lane) and walks the ones of this level
     for (uint32_t base = warp * 32u; base < count; base += nwarps * 32u) {
         const uint32_t i = base + (uint32_t)lane;
         uint32_t mine = FL_NONE;
         if (i < count) {
             mine = f.parked[i];
-            if (f.lvl) {
-                const uint32_t lv = f.lvl[mine];
-                if ((lv < f.top_level ? lv : f.top_level) != f.level) mine = FL_NONE;
-            }
+            const uint32_t lv = f.lvl[mine];
+            if ((lv < f.top_level ? lv : f.top_level) != f.level) mine = FL_NONE;
         }
         uint32_t todo = __ballot_sync(FL_FULL, mine != FL_NONE);
         while (todo) {

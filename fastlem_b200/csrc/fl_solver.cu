@@ -563,6 +563,8 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     f.next_list = nullptr; f.next_count = nullptr;
     f.lvl = nullptr; f.level = 0; f.top_level = 0;
     FL_CK(fl_memset(c->d_nwait, 0, sizeof(uint32_t) * n, c->stream));
+    FL_CK(fl_memset(c->d_pre, 0xFF, sizeof(double) * n, c->stream));    // "unset" pattern, see fl_is_unset
+    FL_CK(fl_memset(c->d_post1, 0xFF, sizeof(double) * n, c->stream));
     f.nwait = c->d_nwait;
     LAUNCH_N(k_count_waits, n, n, L.recv, L.cmask, c->d_nwait);
     if (c->opt_k4_rounds) {
