@@ -113,6 +113,14 @@ inline cudaError_t fl_exclusive_sum(void*, size_t& temp_bytes, const uint32_t* i
     return 0;
 }
 
+inline cudaError_t fl_inclusive_max(void*, size_t& temp_bytes, const uint32_t* in, uint32_t* out, uint32_t n,
+                                    cudaStream_t, bool query) {
+    if (query) { temp_bytes = 1; return 0; }
+    uint32_t acc = 0;
+    for (uint32_t i = 0; i < n; ++i) { acc = in[i] > acc ? in[i] : acc; out[i] = acc; }
+    return 0;
+}
+
 #else
 // ------------------------------------------------------------------------------------------------
 #include <cuda_runtime.h>
@@ -163,5 +171,12 @@ inline cudaError_t fl_sort_pairs(void* temp, size_t& temp_bytes, const uint32_t*
 inline cudaError_t fl_exclusive_sum(void* temp, size_t& temp_bytes, const uint32_t* in, uint32_t* out, uint32_t n,
                                     cudaStream_t s, bool query) {
     return cub::DeviceScan::ExclusiveSum(query ? nullptr : temp, temp_bytes, in, out, (int)n, s);
+}
+struct FlMaxOp {
+    __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+inline cudaError_t fl_inclusive_max(void* temp, size_t& temp_bytes, const uint32_t* in, uint32_t* out, uint32_t n,
+                                    cudaStream_t s, bool query) {
+    return cub::DeviceScan::InclusiveScan(query ? nullptr : temp, temp_bytes, in, out, FlMaxOp(), (int)n, s);
 }
 #endif

@@ -117,11 +117,12 @@ struct fastlem_ctx {
     uint32_t* d_iota = nullptr;
     uint32_t* d_parked = nullptr;
     uint32_t* d_nwait = nullptr;
-    uint32_t* d_round_list[2] = {nullptr, nullptr};
-    uint32_t* d_round_count = nullptr;
-    uint32_t rounds_hint = 16, last_rounds = 0, prev_maxh = 0;
-    int64_t opt_k4_rounds = 0;
-    int64_t opt_k4_long_levels = 0;
+    uint32_t* d_sg_head = nullptr;  // dynamic segments of the dataflow K4: head of each site's segment,
+    uint32_t* d_sg_tail = nullptr;  // and per head: tail, waiting sites, published sites
+    uint32_t* d_sg_wait = nullptr;
+    uint32_t* d_sg_done = nullptr;
+    unsigned long long* d_flow_stats = nullptr;
+    uint32_t prev_maxh = 0;
     double* d_tcel = nullptr;
     int sm_count = 148;
     int64_t opt_park_after = 8;
@@ -553,81 +554,34 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     FL_RC(stage_mark(c, 7));  // end of the layout rebuild
     Layout& L = L_(c);
 
-    // K4: one dataflow launch
+    // K4 (fl_flow.cuh): segment bookkeeping, then the two dataflow passes
     FL_CK(fl_memset(c->d_state, 0, sizeof(uint32_t) * n, c->stream));
+    FL_CK(fl_memset(c->d_nwait, 0, sizeof(uint32_t) * n, c->stream));
+    FL_CK(fl_memset(c->d_sg_wait, 0, sizeof(uint32_t) * n, c->stream));
+    FL_CK(fl_memset(c->d_sg_done, 0, sizeof(uint32_t) * n, c->stream));
+    LAUNCH_N(k_count_waits, n, n, L.recv, L.cmask, c->d_nwait);
+    LAUNCH_N(k_seg_keys, n, n, L.recv, c->d_depth);
+    FL_CK(fl_inclusive_max(c->d_tmp, c->tmp_bytes, c->d_depth, c->d_sg_head, n, c->stream, false));
     FlFlow f;
     f.n = n; f.row_ptr = L.row_ptr; f.col = L.col; f.recv = L.recv; f.cmask = L.cmask; f.areas = L.areas;
-    f.A = c->d_A; f.state = c->d_state; f.pre = c->d_pre; f.post1 = c->d_post1; f.post2 = c->d_post2;
-    f.xbuf = c->d_xbuf; f.hbuf = c->d_hbuf; f.hgt = c->d_hgt; f.hpre = c->d_hpre; f.flags = c->d_flags;
-    f.parked = c->d_parked; f.counters = c->d_flags + FL_FLAG_PARKED; f.park_after = (uint32_t)c->opt_park_after;
-    f.next_list = nullptr; f.next_count = nullptr;
-    f.lvl = nullptr; f.level = 0; f.top_level = 0;
-    FL_CK(fl_memset(c->d_nwait, 0, sizeof(uint32_t) * n, c->stream));
-    FL_CK(fl_memset(c->d_pre, 0xFF, sizeof(double) * n, c->stream));    // "unset" pattern, see fl_is_unset
-    FL_CK(fl_memset(c->d_post1, 0xFF, sizeof(double) * n, c->stream));
-    f.nwait = c->d_nwait;
-    LAUNCH_N(k_count_waits, n, n, L.recv, L.cmask, c->d_nwait);
-    if (c->opt_k4_rounds) {
-        // round-synchronous: list r -> list r+1, one launch per nesting height (estimated from the last
-        // iteration; checked below with the flag read-back, more rounds are added if the estimate was short)
-        const uint32_t max_rounds = FL_MAX_ROUNDS;
-        FL_CK(fl_memset(c->d_round_count, 0, sizeof(uint32_t) * (3 * (size_t)max_rounds + 8), c->stream));
-        uint32_t* park_counters = c->d_round_count + max_rounds + 2;  // [2r] = parked in round r, [2r+1] = taken
-        f.next_list = nullptr; f.next_count = nullptr;
-        f.counters = park_counters;
-        LAUNCH_N(k_flow_prepare, n, f, c->d_round_list[0], c->d_round_count);
-        uint32_t r = 0;
-        uint32_t planned = c->rounds_hint + 2u;
-        for (;;) {
-            for (; r < planned && r < max_rounds; ++r) {
-                // threads work through list r; long chains are parked and finished by warps in the same round;
-                // both queue the sites whose last child reported into list r+1
-                f.counters = park_counters + 2 * r;
-                f.next_list = c->d_round_list[(r + 1) & 1];
-                f.next_count = c->d_round_count + r + 1;
-                FL_LAUNCH(k_area_round, (unsigned)c->sm_count * 8u, 256, c->stream, f, c->d_round_list[r & 1],
-                          c->d_round_count + r, f.next_list, f.next_count);
-                c->stats.kernel_launches++;
-                if (f.park_after) {
-                    FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 2u, 256, c->stream, f);
-                    c->stats.kernel_launches++;
-                }
-            }
-            FL_CK(fl_d2h(c->h_rounds, c->d_round_count, sizeof(uint32_t) * (r + 1), c->stream));
-            FL_CK(fl_stream_sync(c->stream));
-            if (c->h_rounds[r] == 0u) break;
-            if (r >= max_rounds) return fail(c, FASTLEM_E_STATE, "K4: more hand-off rounds than FL_MAX_ROUNDS");
-            planned = r + 8u;
-        }
-        uint32_t used = 0;  // launches that had work
-        while (used < r && c->h_rounds[used] != 0u) ++used;
-        c->last_rounds = used;
-    } else {
-        LAUNCH_N(k_simple_pre, n, f);
-        LAUNCH_N(k_area_flow, n, f);
+    f.A = c->d_A; f.nwait = c->d_nwait; f.seg_head = c->d_sg_head; f.seg_tail = c->d_sg_tail;
+    f.seg_wait = c->d_sg_wait; f.seg_done = c->d_sg_done; f.state = c->d_state; f.pre = c->d_pre;
+    f.post1 = c->d_post1; f.post2 = c->d_post2; f.hpre = c->d_hpre; f.xbuf = c->d_xbuf; f.hbuf = c->d_hbuf;
+    f.hgt = c->d_hgt; f.flags = c->d_flags; f.parked = c->d_parked; f.counters = c->d_flags + FL_FLAG_PARKED;
+    f.park_after = (uint32_t)c->opt_park_after; f.stats = c->d_flow_stats;
+    LAUNCH_N(k_seg_prepare, n, f, c->d_sg_tail, c->d_sg_wait);
+    LAUNCH_N(k_area_flow, n, f);
+    if (f.park_after) {  // the parked (long) climbs, one warp each (persistent grid)
+        FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 4u, 256, c->stream, f);
+        c->stats.kernel_launches++;
     }
-    if (!c->opt_k4_rounds && f.park_after) {
-        // the parked (long) flows, one warp each: one launch per nesting height of the previous iteration
-        if (c->opt_k4_long_levels) {
-            f.lvl = L.lvl;
-            f.top_level = c->prev_maxh;
-            for (uint32_t lv = 0; lv <= c->prev_maxh; ++lv) {
-                f.level = lv;
-                FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 2u, 256, c->stream, f);
-                c->stats.kernel_launches++;
-            }
-            f.lvl = nullptr;
-        } else {
-            FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 4u, 256, c->stream, f);
-            c->stats.kernel_launches++;
-        }
-    }
-    c->stats.n_area += 4;
+    c->stats.n_area += 6;
     FL_RC(stage_mark(c, 8));  // end of K4
 
     // order the segment heads by descending nesting height (exact for the current forest)
     FL_RC(read_flags(c));
     const uint32_t maxh = c->h_flags[FL_FLAG_MAXDEPTH];
+    if (c->h_flags[FL_FLAG_BROKEN]) return fail(c, FASTLEM_E_STATE, "K4: a climb met an unpublished site (internal error)");
     int bits = 1;
     while (bits < 32 && (1ull << bits) <= (unsigned long long)maxh + 1ull) ++bits;
     LAUNCH_N(k_flow_sort_keys, n, n, c->d_hgt, maxh, c->d_depth);
@@ -645,7 +599,6 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     c->stats.n_order += 3;
     c->stats.path_levels = maxh + 1;
     c->stats.paths = n_heads;
-    c->rounds_hint = c->last_rounds ? c->last_rounds : maxh + 1;
     c->prev_maxh = maxh;
     if (rebuilt) { c->segs_at_rebuild = n_heads; c->maxh_at_rebuild = maxh; }
     else if (c->opt_rebuild_every == 0 &&
@@ -807,10 +760,6 @@ int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
     } else if (s == "park_after") {
         if (value != 0 && value < 4) return fail(c, FASTLEM_E_INVALID, "option park_after: 0 (never) or >= 4");
         c->opt_park_after = value;
-    } else if (s == "k4_long_levels") {
-        c->opt_k4_long_levels = value != 0;
-    } else if (s == "k4_rounds") {
-        c->opt_k4_rounds = value != 0;
     } else if (s == "rebuild_every") {
         if (value < 0) return fail(c, FASTLEM_E_INVALID, "option rebuild_every: 0 (adaptive) or a positive period");
         c->opt_rebuild_every = value;
@@ -897,9 +846,12 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     FL_CK(dalloc(c, c->d_iota, n));
     FL_CK(dalloc(c, c->d_parked, (size_t)n / 4 + 64));
     FL_CK(dalloc(c, c->d_nwait, n));
-    FL_CK(dalloc(c, c->d_round_list[0], n));
-    FL_CK(dalloc(c, c->d_round_list[1], n));
-    FL_CK(dalloc(c, c->d_round_count, 3 * (size_t)FL_MAX_ROUNDS + 8));
+    FL_CK(dalloc(c, c->d_sg_head, n));
+    FL_CK(dalloc(c, c->d_sg_tail, n));
+    FL_CK(dalloc(c, c->d_sg_wait, n));
+    FL_CK(dalloc(c, c->d_sg_done, n));
+    FL_CK(dalloc(c, c->d_flow_stats, 32));
+    FL_CK(fl_memset(c->d_flow_stats, 0, 32 * sizeof(unsigned long long), c->stream));
     FL_CK(dalloc(c, c->d_tcel, n));
     c->sm_count = fl_sm_count();
     LAUNCH_N(k_iota, n, n, c->d_iota);
@@ -919,6 +871,9 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     size_t sort_bytes = 0, scan_bytes = 0;
     FL_CK(fl_sort_pairs(nullptr, sort_bytes, c->d_depth, c->d_sorted, c->d_ids, c->d_order, n, 32, c->stream, true));
     FL_CK(fl_exclusive_sum(nullptr, scan_bytes, c->d_deg_new, c->d_seg_head, n + 1, c->stream, true));
+    size_t max_bytes = 0;
+    FL_CK(fl_inclusive_max(nullptr, max_bytes, c->d_deg_new, c->d_sg_head, n, c->stream, true));
+    if (max_bytes > scan_bytes) scan_bytes = max_bytes;
     if (c->d_tmp) { fl_free(c->d_tmp); c->d_tmp = nullptr; }
     c->tmp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
     FL_CK(fl_malloc(&c->d_tmp, c->tmp_bytes));
@@ -1039,6 +994,13 @@ int fastlem_debug_fetch(fastlem_ctx* c, int stage, void* out, size_t bytes) {
     if (!c->has_graph || !c->has_params) return fail(c, FASTLEM_E_STATE, "debug_fetch: no run yet");
     FL_CK(fl_set_device(c->device));
     const uint32_t n = c->n;
+    if (stage == 9) {  // FL_FLOW_STATS counters (debug builds): 32 x u64, also resets them
+        if (bytes != 256) return fail(c, FASTLEM_E_INVALID, "debug_fetch: flow stats are 256 bytes");
+        FL_CK(fl_d2h(out, c->d_flow_stats, 256, c->stream));
+        FL_CK(fl_memset(c->d_flow_stats, 0, 256, c->stream));
+        FL_CK(fl_stream_sync(c->stream));
+        return FASTLEM_OK;
+    }
     if (!c->layout_valid && stage != FASTLEM_STAGE_FLOOD_RANK)
         return fail(c, FASTLEM_E_STATE, "debug_fetch: no run yet");
     Layout& L = L_(c);
