@@ -48,7 +48,12 @@
 #endif
 enum { FLS_T_CLIMBS = 0, FLS_T_BATCH, FLS_T_SITES, FLS_T_HEADS, FLS_T_LAST, FLS_T_SEGSTART, FLS_T_PARKED, FLS_T_NOTREADY,
        FLS_W_FLOWS, FLS_W_WINDOWS, FLS_W_SITES, FLS_W_HEADS, FLS_W_LAST, FLS_W_SEGSTART, FLS_W_REDO, FLS_W_NOTREADY,
-       FLS_COUNT_N = 24 };
+       FLS_W_CYC_FLOW, FLS_W_CYC_REPORT, FLS_W_CYC_FIRSTWIN, FLS_W_CYC_WIN, FLS_COUNT_N = 24 };
+#if defined(FL_FLOW_STATS) && !defined(FL_EMU)
+#define FL_CLOCK() clock64()
+#else
+#define FL_CLOCK() 0ll
+#endif
 
 #ifdef FL_EMU
 template <class T> __device__ __forceinline__ T fl_ld_cg(const T* p) { return *p; }
@@ -178,7 +183,7 @@ __device__ __forceinline__ uint32_t fl_gather_lights(const FlFlow& f, uint32_t p
 }
 
 // slow path for np == 15: add every child after the chain child, in order
-__device__ double fl_add_posts(const FlFlow& f, uint32_t p, double y) {
+__device__ __noinline__ double fl_add_posts(const FlFlow& f, uint32_t p, double y) {
     bool seen = false;
     const uint32_t s0 = f.row_ptr[p];
     uint32_t m = f.cmask[p];
@@ -410,6 +415,8 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
 #pragma unroll
     for (int j = 0; j < FL_WDEPTH; ++j) { ring[j].cm = 0u; ring[j].rc = FL_NONE; ring[j].st = 0u; ring[j].ar = 0.0; ring[j].pre = 0.0; ring[j].p1 = 0.0; }
     for (;;) {
+        const long long t_win = FL_CLOCK();
+        const bool first_win = nring == 0u;
         if (nring == 0u) { ring[0] = fl_win_load(f, cur, lane); nring = 1u; }
         const FlWin win = ring[0];
         const long long li = (long long)cur - lane;
@@ -455,40 +462,46 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
             sm.in[lane] = b;
             __syncwarp();
             double r = x;
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                const double bk = sm.in[k];
-                if ((uint32_t)k < nproc) r = ((k > 0) || has_chain) ? (bk + r) : bk;
+            {   // site 0 of the window may be a tail (no chain child)
+                const double b0 = sm.in[0];
+                r = has_chain ? (b0 + r) : b0;
+                sm.out[0] = r;
+            }
+#pragma unroll 4
+            for (uint32_t k = 1; k < nproc; ++k) {  // code kept small on purpose: the kernel must stay in the i-cache
+                r = sm.in[k] + r;
                 sm.out[k] = r;
             }
             x = r;
             __syncwarp();
             mine = sm.out[lane];
         } else {
-            mine = 0.0;
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                const double bk = fl_shfl(b, k);
-                if ((uint32_t)k < nproc) {
-                    double yy = ((k > 0) || has_chain) ? (bk + x) : bk;
-                    if ((postmask >> k) & 1u) {  // children after the chain child
-                        const uint32_t npk_k = __shfl_sync(FL_FULL, npk, k);
-                        if (npk_k == 15u) {
-                            double v = 0.0;
-                            if (lane == k) v = fl_add_posts(f, idx, yy);
-                            __syncwarp();
-                            yy = fl_shfl(v, k);
-                        } else {
-                            const double q1k = fl_shfl(q1, k);
-                            const double q2k = fl_shfl(q2, k);
-                            yy += q1k;
-                            if (npk_k >= 2u) yy += q2k;
-                        }
+            // some site of the window has children after its chain child: stage those too
+            __syncwarp();
+            sm.in[lane] = b;
+            sm.aux1[lane] = q1;
+            sm.aux2[lane] = q2;
+            __syncwarp();
+            double r = x;
+            for (uint32_t k = 0; k < nproc; ++k) {
+                r = ((k > 0u) || has_chain) ? (sm.in[k] + r) : sm.in[k];
+                if ((postmask >> k) & 1u) {
+                    const uint32_t npk_k = __shfl_sync(FL_FULL, npk, (int)k);
+                    if (npk_k == 15u) {
+                        double v = 0.0;
+                        if ((uint32_t)lane == k) v = fl_add_posts(f, idx, r);
+                        __syncwarp();
+                        r = fl_shfl(v, (int)k);
+                    } else {
+                        r += sm.aux1[k];
+                        if (npk_k >= 2u) r += sm.aux2[k];
                     }
-                    x = yy;
-                    if (lane == k) mine = yy;
                 }
+                sm.out[k] = r;
             }
+            x = r;
+            __syncwarp();
+            mine = sm.out[lane];
         }
         const uint32_t hw = fl_warp_max(inwin ? hq : 0u);
         if (hw > hrun) hrun = hw;
@@ -496,6 +509,7 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
             f.A[idx] = mine;
             if (climbs) f.hgt[idx] = FL_NONE;
         }
+        if (lane == 0) FL_COUNT(f, first_win ? FLS_W_CYC_FIRSTWIN : FLS_W_CYC_WIN, FL_CLOCK() - t_win);
         const int lastl = (int)nproc - 1;  // nproc >= 1: lane 0 is always on the chain
         const int last_climbs = __shfl_sync(FL_FULL, (int)climbs, lastl);
         if (last_climbs) {  // nproc == 32: whole window climbed, shift the ring
@@ -516,8 +530,10 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
             return;
         }
         uint32_t next_tail = FL_NONE, dep = 0u;
+        const long long t_rep = FL_CLOCK();
         if (lane == 0) next_tail = fl_report(f, h, p, hrun, true, &dep);
         next_tail = __shfl_sync(FL_FULL, next_tail, 0);
+        if (lane == 0) FL_COUNT(f, FLS_W_CYC_REPORT, FL_CLOCK() - t_rep);
         if (next_tail == FL_NONE) return;
         if (lane == 0) FL_COUNT(f, FLS_W_SEGSTART, 1);
         cur = next_tail + fl_dep0(next_tail);  // the broadcast value came after lane 0's atomics
@@ -546,7 +562,9 @@ __global__ void __launch_bounds__(256, 2) k_area_flow_long(FlFlow f) {
         if (i >= count) return;
         const uint32_t cur = f.parked[i];
         if (lane == 0) FL_COUNT(f, FLS_W_FLOWS, 1);
+        const long long t_flow = FL_CLOCK();
         fl_flow_warp(f, cur, fl_ld_cg(&f.xbuf[cur]), fl_ld_cg(&f.hbuf[cur]), true, sm);
+        if (lane == 0) FL_COUNT(f, FLS_W_CYC_FLOW, FL_CLOCK() - t_flow);
     }
 #endif
 }
@@ -665,10 +683,9 @@ __device__ __forceinline__ void fl_elev_window(const FlElev& e, const FlEWin& w,
     __syncwarp();
     {
         double r = rt_prev;
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            const double tk = sm.in[k];
-            if ((uint32_t)k < nproc) r = 0.0 + (r + tk);
+#pragma unroll 4
+        for (uint32_t k = 0; k < nproc; ++k) {  // code kept small on purpose (i-cache)
+            r = 0.0 + (r + sm.in[k]);
             sm.out[k] = r;
         }
         rt_prev = r;
@@ -683,18 +700,15 @@ __device__ __forceinline__ void fl_elev_window(const FlElev& e, const FlEWin& w,
         sm.aux2[lane] = w.d;
         __syncwarp();
         double zp = z_prev;
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
+        for (uint32_t k = 0; k < nproc; ++k) {
             double zk = sm.in[k];
             const double msk = sm.aux1[k];
             const double dk = sm.aux2[k];
-            if ((uint32_t)k < nproc) {
-                if (msk == msk) {
-                    const double slope = (zk - zp) / dk;
-                    if (slope > msk) zk = zp + msk * dk;
-                }
-                zp = zk;
+            if (msk == msk) {
+                const double slope = (zk - zp) / dk;
+                if (slope > msk) zk = zp + msk * dk;
             }
+            zp = zk;
             sm.out[k] = zk;
         }
         z_prev = zp;

@@ -7,7 +7,8 @@ from fastlem_b200 import _native
 from tools import workloads as W
 LIB = os.path.join(ROOT, "tools", "_dbg", "libfastlem_stats.so")
 NAMES = ["T_CLIMBS", "T_BATCH", "T_SITES", "T_HEADS", "T_LAST", "T_SEGSTART", "T_PARKED", "T_NOTREADY",
-         "W_FLOWS", "W_WINDOWS", "W_SITES", "W_HEADS", "W_LAST", "W_SEGSTART", "W_REDO", "W_NOTREADY"]
+         "W_FLOWS", "W_WINDOWS", "W_SITES", "W_HEADS", "W_LAST", "W_SEGSTART", "W_REDO", "W_NOTREADY",
+         "W_CYC_FLOW", "W_CYC_REPORT", "W_CYC_FIRSTWIN", "W_CYC_WIN"]
 
 def fetch(ctx):
     out = np.zeros(32, dtype=np.uint64)
