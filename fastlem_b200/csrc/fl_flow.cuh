@@ -531,6 +531,8 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
         }
         uint32_t next_tail = FL_NONE, dep = 0u;
         const long long t_rep = FL_CLOCK();
+        __threadfence();  // every lane publishes its own stores (A, hgt) before lane 0 reports
+        __syncwarp();
         if (lane == 0) next_tail = fl_report(f, h, p, hrun, true, &dep);
         next_tail = __shfl_sync(FL_FULL, next_tail, 0);
         if (lane == 0) FL_COUNT(f, FLS_W_CYC_REPORT, FL_CLOCK() - t_rep);
