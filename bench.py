@@ -230,15 +230,25 @@ def main():
     out = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
     barrier()
     t1 = time.perf_counter()
+    e2e_parts = {"create": 0.0, "set_graph": 0.0, "set_parameters": 0.0, "generate": 0.0, "destroy": 0.0}
     for _ in range(args.steps):
-        with _native.Context(local_rank) as c2:
-            if args.sweep is not None:
-                c2.set_option("sweep", args.sweep)
-            c2.set_graph(hm["row_ptr"], hm["col"], hm["dist"], hm["areas"])
-            c2.set_parameters(hp["initial"], hp["erodibility"], hp["uplift"], None, hp["outlets"])
-            _, it = c2.generate(out=out)
-            e2e_iters += it
-            e2e_stats = c2.stats()
+        ta = time.perf_counter()
+        c2 = _native.Context(local_rank)
+        if args.sweep is not None:
+            c2.set_option("sweep", args.sweep)
+        tb = time.perf_counter()
+        c2.set_graph(hm["row_ptr"], hm["col"], hm["dist"], hm["areas"])
+        tc = time.perf_counter()
+        c2.set_parameters(hp["initial"], hp["erodibility"], hp["uplift"], None, hp["outlets"])
+        td = time.perf_counter()
+        _, it = c2.generate(out=out)
+        te_ = time.perf_counter()
+        e2e_iters += it
+        e2e_stats = c2.stats()
+        c2.close()
+        tf = time.perf_counter()
+        for k, v in zip(e2e_parts, (tb - ta, tc - tb, td - tc, te_ - td, tf - te_)):
+            e2e_parts[k] += v / args.steps
     barrier()
     e2e_t = time.perf_counter() - t1
     te = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
@@ -295,6 +305,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(graph_bytes + param_bytes),
                         "d2h_bytes_per_step": int(8 * n), "seconds_per_step": float(te[0]) / args.steps,
                         "flood_rank_host_ms": e2e_stats["ms_flood_rank"], "upload_ms": e2e_stats["ms_upload"],
+                        "seconds_by_call": e2e_parts, "device_ms_in_generate": e2e_stats["ms_run"],
                         "host_buffers": "pinned host arrays handed to the C ABI as plain pointers"},
                 "gpu_launches": launches_all, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "workload_build_s": t_build}
