@@ -272,7 +272,7 @@ def main():
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                     "bytes_per_pass": alg_bytes, "ms_per_pass": stage_ms[dom] / max(passes, 1),
                     "kernel_launches_per_pass": stage_n[dom] / max(passes, 1),
-                    "kernel_names": {"receivers": "k_receivers_mask", "area": "k_count_waits+k_simple_pre+k_area_flow+k_area_flow_long",
+                    "kernel_names": {"receivers": "k_receivers_mask", "area": "k_count_waits+k_seg_keys+scan+k_seg_prepare+k_area_flow+k_area_flow_long",
                                      "elevation": "k_celerity_term+k_elev_flow[_warps]"}[dom],
                     "receivers_kernel": {"achieved": k1, "frac": k1 / peak,
                                          "ms_per_launch": stage_ms["receivers"] / max(stage_n["receivers"], 1)},
