@@ -95,10 +95,11 @@ struct FlFlow {
     const uint32_t* cmask;
     const double* areas;
     double* A;
-    const uint32_t* nwait;     // children that REPORT to a site = its non-leaf segment heads (k_count_waits)
+    uint32_t* nwait;           // children that REPORT to a site = its non-leaf segment heads (k_count_waits);
+                               // incremental mode: its DIRTY segment heads, bit 31 = site is on the regather list
     const uint32_t* seg_head;  // head (lowest position) of the segment each site is on (max-scan)
-    const uint32_t* seg_tail;  // at a head: the tail (highest position) of its segment
-    const uint32_t* seg_wait;  // at a head: number of waiting sites (nwait > 0) on the segment
+    const uint32_t* seg_tail;  // at a head: the tail (highest position) of its segment (full mode)
+    uint32_t* seg_wait;        // at a head: number of waiting sites (nwait > 0) on the segment
     uint32_t* seg_done;        // at a head: how many of them have been published (zeroed before the launch)
     uint32_t* state;           // per site, zeroed before the launch (layout above)
     double* pre;
@@ -108,6 +109,11 @@ struct FlFlow {
     double* xbuf;        // running area of a parked climb
     uint32_t* hbuf;      // running nesting height of a parked climb
     uint32_t* hgt;       // out: nesting height for segment heads, FL_NONE elsewhere
+    uint32_t* hsuf;      // out: running nesting height of the climb after each site (max over the chain above it)
+    // incremental mode (dirty_from != nullptr): only the sites whose drainage area can have changed are redone
+    uint32_t* dirty_from;  // at a head: 1 + highest dirty position of the segment (0 = clean)
+    uint32_t* rlist;       // sites that regather their partial sums; count in flags[FL_FLAG_NREGATHER]
+    uint32_t* slist;       // heads of the dirty segments; count in flags[FL_FLAG_NDIRTY]
     uint32_t* flags;
     uint32_t* parked;    // sites where a long climb was parked for the warp-level pass
     uint32_t* counters;  // [0] = number of parked climbs, [1] = next one to take
@@ -115,13 +121,31 @@ struct FlFlow {
     unsigned long long* stats;
 };
 
+#define FL_NW_RFLAG 0x80000000u
+#define FL_NW_COUNT 0x7FFFFFFFu
+
+// Where the climb of a segment starts and what it starts with.  Full mode: at the tail, with nothing.
+// Incremental mode: at the highest dirty site; the chain above it is clean, so its area and running
+// nesting height are the ones stored by an earlier iteration.
+__device__ __forceinline__ uint32_t fl_seg_start(const FlFlow& f, uint32_t sh) {
+    return f.dirty_from ? (f.dirty_from[sh] - 1u) : f.seg_tail[sh];
+}
+__device__ __forceinline__ void fl_seg_entry(const FlFlow& f, uint32_t cur, double& x, uint32_t& hrun, bool& has_chain) {
+    x = 0.0; hrun = 0u; has_chain = false;
+    if (f.dirty_from && cur + 1u < f.n && f.recv[cur + 1u] == cur) {
+        has_chain = true;
+        x = f.A[cur + 1u];
+        hrun = f.hsuf[cur + 1u];
+    }
+}
+
 // per-warp staging area of the serial chains (warp-level scans)
 struct FlChainSmem { double in[32]; double out[32]; double aux1[32]; double aux2[32]; };
 
 // Partial sums of site p over its non-chain children, reverse adjacency order; returns np (15 = more than two
-// children after the chain child).  Leaf children never run a flow: their area is their own cell area, their
-// height 0.  `dep` is an opaque zero that orders the loads of the other children's results after the atomic
-// that made the caller the last reporter.
+// children after the chain child).  A light child is always a segment head; leaf heads hold A = their cell area
+// and height 0 from the pre-pass (k_count_waits) or from their own climb.  `dep` is an opaque zero that orders
+// the loads of the children's results after the atomic that made the caller the last reporter.
 __device__ __forceinline__ uint32_t fl_gather_lights(const FlFlow& f, uint32_t p, bool has_chain, uint32_t dep,
                                                      double& pre, double& p1, double& p2, uint32_t& hmax) {
     pre = f.areas[p];
@@ -147,12 +171,8 @@ __device__ __forceinline__ uint32_t fl_gather_lights(const FlFlow& f, uint32_t p
         val[k] = 0.0; hk[k] = 1u;
         if (k < nk && !(has_chain && kid[k] == p + 1u)) {
             const uint32_t c = kid[k];
-            if (f.cmask[c] == 0u) {
-                val[k] = f.areas[c];
-            } else {
-                val[k] = fl_ld_cg(&f.A[c + dep]);
-                hk[k] = fl_ld_cg(&f.hgt[c + dep]) + 1u;
-            }
+            val[k] = fl_ld_cg(&f.A[c + dep]);
+            hk[k] = fl_ld_cg(&f.hgt[c + dep]) + 1u;
         }
     }
 #pragma unroll
@@ -171,10 +191,8 @@ __device__ __forceinline__ uint32_t fl_gather_lights(const FlFlow& f, uint32_t p
         rest ^= 1u << b;
         const uint32_t c = f.col[s0 + b];
         if (has_chain && c == p + 1u) { seen = true; continue; }
-        double v;
-        uint32_t hc = 1u;
-        if (f.cmask[c] == 0u) v = f.areas[c];
-        else { v = fl_ld_cg(&f.A[c + dep]); hc = fl_ld_cg(&f.hgt[c + dep]) + 1u; }
+        const double v = fl_ld_cg(&f.A[c + dep]);
+        const uint32_t hc = fl_ld_cg(&f.hgt[c + dep]) + 1u;
         if (hc > hmax) hmax = hc;
         if (!seen) pre += v;
         else { if (np == 0) p1 = v; else if (np == 1) p2 = v; ++np; }
@@ -192,22 +210,33 @@ __device__ __noinline__ double fl_add_posts(const FlFlow& f, uint32_t p, double 
         m ^= 1u << b;
         const uint32_t c = f.col[s0 + b];
         if (c == p + 1u) { seen = true; continue; }
-        if (seen) y += (f.cmask[c] == 0u) ? f.areas[c] : fl_ld_cg(&f.A[c]);
+        if (seen) y += fl_ld_cg(&f.A[c]);
     }
     return y;
 }
 
-// A finished segment head `h` (area y already stored) reports to its receiver p.  Returns the tail of the
-// segment to climb next (the caller continues there), or FL_NONE when this flow ends.  *dep_out carries the
-// opaque zero that orders the next climb's loads after the deciding atomic.
-__device__ __forceinline__ uint32_t fl_report(const FlFlow& f, uint32_t h, uint32_t p, uint32_t hrun, bool warp_lane0,
-                                              uint32_t* dep_out) {
-    (void)warp_lane0;
-    __threadfence();  // publish A[h], hgt[h]
+// release fence at gpu scope (lighter than __threadfence(), which is fence.sc)
+__device__ __forceinline__ void fl_fence_release() {
+#ifndef FL_EMU
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
+}
+
+// A finished segment head `h` (area y already stored) reports to its receiver p.  Returns the site where the
+// next climb starts (the caller continues there), or FL_NONE when this flow ends.  *dep_out carries the
+// opaque zero that orders the next climb's loads after the deciding atomic.  `fenced`: the caller has already
+// fenced its stores.  The static data of p (counts, row, child mask) is requested right behind the atomic so
+// that the round trips overlap.
+__device__ __forceinline__ uint32_t fl_report(const FlFlow& f, uint32_t h, uint32_t p, bool fenced, uint32_t* dep_out) {
+    (void)h;
+    if (!fenced) fl_fence_release();  // publish A[h], hgt[h]
     const uint32_t prev = atomicAdd(&f.state[p], 1u);
-    if ((prev & FL_ST_COUNT_MASK) + 1u < f.nwait[p]) return FL_NONE;
-    // last reporter at p: gather and publish p's partial sums
+    const uint32_t nw = f.nwait[p] & FL_NW_COUNT;
+    const uint32_t sh = f.seg_head[p];
     const bool p_has_chain = (p + 1u < f.n) && (f.recv[p + 1u] == p);
+    if ((prev & FL_ST_COUNT_MASK) + 1u < nw) return FL_NONE;
+    // last reporter at p: gather and publish p's partial sums
+    const uint32_t swait = f.seg_wait[sh];
     double pre, p1, p2;
     uint32_t hp;
     const uint32_t np = fl_gather_lights(f, p, p_has_chain, fl_dep0(prev), pre, p1, p2, hp);
@@ -215,13 +244,12 @@ __device__ __forceinline__ uint32_t fl_report(const FlFlow& f, uint32_t h, uint3
     f.hpre[p] = hp;
     if (np >= 1u && np != 15u) f.post1[p] = p1;
     if (np >= 2u && np != 15u) f.post2[p] = p2;
-    atomicOr(&f.state[p], fl_st_publish(np, hp));
-    __threadfence();  // publish the partial sums before the segment counter moves
-    const uint32_t sh = f.seg_head[p];
+    f.state[p] = fl_st_publish(np, hp);  // no report can follow the last one: a plain store
+    fl_fence_release();  // publish the partial sums before the segment counter moves
     const uint32_t done = atomicAdd(&f.seg_done[sh], 1u) + 1u;
-    if (done < f.seg_wait[sh]) return FL_NONE;
+    if (done < swait) return FL_NONE;
     *dep_out = fl_dep0(done);
-    return f.seg_tail[sh];  // every waiting site of the segment is published: climb it
+    return fl_seg_start(f, sh);  // every waiting site of the segment is published: climb it
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -273,6 +301,7 @@ __device__ void fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t
                     if (hq > hrun) hrun = hq;
                 }
                 f.A[idx] = y;
+                f.hsuf[idx] = hrun;
                 if (idx > 0u && rc[k] == idx - 1u) {
                     f.hgt[idx] = FL_NONE;
                     x = y;
@@ -305,22 +334,30 @@ __device__ void fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t
             return;
         }
         uint32_t dep = 0u;
-        const uint32_t next_tail = fl_report(f, cur, p, hrun, true, &dep);
+        const uint32_t next_tail = fl_report(f, cur, p, false, &dep);
         if (next_tail == FL_NONE) return;
         FL_COUNT(f, FLS_T_SEGSTART, 1);
-        cur = next_tail + dep; x = 0.0; hrun = 0u; has_chain = false; climbed = 0u;
+        cur = next_tail + dep; climbed = 0u;
+        fl_seg_entry(f, cur, x, hrun, has_chain);
     }
 }
 
 // pre-pass A: how many children will REPORT to each site = its non-leaf segment heads.
 // (Leaves are read by their parent directly; chain children hand over inside the segment.)
 __global__ void __launch_bounds__(256) k_count_waits(uint32_t n, const uint32_t* __restrict__ recv,
-                                                      const uint32_t* __restrict__ cmask, uint32_t* nwait) {
+                                                      const uint32_t* __restrict__ cmask,
+                                                      const double* __restrict__ areas, uint32_t* nwait,
+                                                      double* __restrict__ A, uint32_t* __restrict__ hgt,
+                                                      uint32_t* __restrict__ hsuf) {
     const uint32_t q = FL_TID;
     if (q >= n) return;
-    if (cmask[q] == 0u) return;
     const uint32_t p = recv[q];
-    if (p == q || (q > 0u && p == q - 1u)) return;  // root, or chained to its receiver
+    const bool chained = q > 0u && p == q - 1u;
+    if (cmask[q] == 0u) {
+        if (!chained) { A[q] = areas[q]; hgt[q] = 0u; hsuf[q] = 0u; }  // a leaf that is a segment of its own
+        return;
+    }
+    if (p == q || chained) return;  // root, or chained to its receiver
     atomicAdd(&nwait[p], 1u);
 }
 
@@ -361,11 +398,7 @@ __global__ void __launch_bounds__(256) k_area_flow(FlFlow f) {
     if (q >= f.n) return;
     if ((q + 1u < f.n) && (f.recv[q + 1u] == q)) return;  // not a tail
     const uint32_t sh = f.seg_head[q];
-    if (sh == q && f.cmask[q] == 0u) {  // a leaf that is a segment of its own; its parent reads areas[q] itself
-        f.A[q] = f.areas[q];
-        f.hgt[q] = 0u;
-        return;
-    }
+    if (sh == q && f.cmask[q] == 0u) return;  // a leaf that is a segment of its own: done in k_count_waits
     if (f.seg_wait[sh] != 0u) return;
     FL_COUNT(f, FLS_T_CLIMBS, 1);
     fl_flow_thread(f, q, 0.0, 0u, false, true);
@@ -386,12 +419,12 @@ __device__ __forceinline__ uint32_t fl_warp_max(uint32_t v) {
 // ------------------------------------------------------------------------------------------------
 struct FlWin {  // one 32-site window of a chain: lane l holds site base - l
     uint32_t cm, rc, st;
-    double ar, pre, p1;
+    double ar, pre, p1, p2;
 };
 
 __device__ __forceinline__ FlWin fl_win_load(const FlFlow& f, uint32_t base, int lane) {
     FlWin w;
-    w.cm = 0u; w.rc = FL_NONE; w.st = 0u; w.ar = 0.0; w.pre = 0.0; w.p1 = 0.0;
+    w.cm = 0u; w.rc = FL_NONE; w.st = 0u; w.ar = 0.0; w.pre = 0.0; w.p1 = 0.0; w.p2 = 0.0;
     const long long li = (long long)base - lane;
     if (li >= 0) {
         const uint32_t idx = (uint32_t)li;
@@ -401,6 +434,7 @@ __device__ __forceinline__ FlWin fl_win_load(const FlFlow& f, uint32_t base, int
         w.st = fl_ld_cg(&f.state[idx]);
         w.pre = fl_ld_cg(&f.pre[idx]);
         w.p1 = fl_ld_cg(&f.post1[idx]);
+        w.p2 = fl_ld_cg(&f.post2[idx]);
     }
     return w;
 }
@@ -413,7 +447,7 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
     FlWin ring[FL_WDEPTH];
     uint32_t nring = 0;
 #pragma unroll
-    for (int j = 0; j < FL_WDEPTH; ++j) { ring[j].cm = 0u; ring[j].rc = FL_NONE; ring[j].st = 0u; ring[j].ar = 0.0; ring[j].pre = 0.0; ring[j].p1 = 0.0; }
+    for (int j = 0; j < FL_WDEPTH; ++j) { ring[j].cm = 0u; ring[j].rc = FL_NONE; ring[j].st = 0u; ring[j].ar = 0.0; ring[j].pre = 0.0; ring[j].p1 = 0.0; ring[j].p2 = 0.0; }
     for (;;) {
         const long long t_win = FL_CLOCK();
         const bool first_win = nring == 0u;
@@ -447,36 +481,52 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
         if (lit) {
             npk = fl_st_np(win.st);
             b = win.pre;
-            q1 = win.p1;
+            if (npk >= 1u && npk != 15u) q1 = win.p1;
+            if (npk >= 2u && npk != 15u) q2 = win.p2;
             hq = (win.st & FL_ST_HP_MASK) >> FL_ST_HP_SHIFT;
-            if (npk >= 2u && npk != 15u) q2 = fl_ld_cg(&f.post2[idx]);
             if (hq == FL_ST_HP_OVER) hq = fl_ld_cg(&f.hpre[idx]);
         }
         if (lane == 0) { FL_COUNT(f, FLS_W_WINDOWS, 1); FL_COUNT(f, FLS_W_SITES, nproc); }
         const uint32_t postmask = __ballot_sync(FL_FULL, lit && npk != 0u);
+        const uint32_t manymask = __ballot_sync(FL_FULL, lit && npk == 15u);
+        // The first site of a segment without a chain child starts from x = 0.0: b + 0.0 == b exactly (areas are
+        // positive), so the chains below need no special case for it.
+        if (!has_chain) x = 0.0;
         double mine;
         if (postmask == 0u) {
-            // common case, no children after the chain child anywhere in the window: y_k = b_k + y_{k-1}.
+            // no children after the chain child anywhere in the window: y_k = b_k + y_{k-1}.
             // Terms staged in shared memory, identical chain in every lane over broadcast reads.
             __syncwarp();
             sm.in[lane] = b;
             __syncwarp();
             double r = x;
-            {   // site 0 of the window may be a tail (no chain child)
-                const double b0 = sm.in[0];
-                r = has_chain ? (b0 + r) : b0;
-                sm.out[0] = r;
-            }
 #pragma unroll 4
-            for (uint32_t k = 1; k < nproc; ++k) {  // code kept small on purpose: the kernel must stay in the i-cache
+            for (uint32_t k = 0; k < nproc; ++k) {  // code kept small on purpose: the kernel must stay in the i-cache
                 r = sm.in[k] + r;
                 sm.out[k] = r;
             }
             x = r;
             __syncwarp();
             mine = sm.out[lane];
+        } else if (manymask == 0u) {
+            // at most two children after the chain child: y_k = ((b_k + y_{k-1}) + q1_k) + q2_k with absent terms
+            // = 0.0 (y + 0.0 == y exactly), so the chain is branch-free
+            __syncwarp();
+            sm.in[lane] = b;
+            sm.aux1[lane] = q1;
+            sm.aux2[lane] = q2;
+            __syncwarp();
+            double r = x;
+#pragma unroll 4
+            for (uint32_t k = 0; k < nproc; ++k) {
+                r = ((sm.in[k] + r) + sm.aux1[k]) + sm.aux2[k];
+                sm.out[k] = r;
+            }
+            x = r;
+            __syncwarp();
+            mine = sm.out[lane];
         } else {
-            // some site of the window has children after its chain child: stage those too
+            // some site of the window has more than two children after its chain child (rare)
             __syncwarp();
             sm.in[lane] = b;
             sm.aux1[lane] = q1;
@@ -484,18 +534,14 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
             __syncwarp();
             double r = x;
             for (uint32_t k = 0; k < nproc; ++k) {
-                r = ((k > 0u) || has_chain) ? (sm.in[k] + r) : sm.in[k];
-                if ((postmask >> k) & 1u) {
-                    const uint32_t npk_k = __shfl_sync(FL_FULL, npk, (int)k);
-                    if (npk_k == 15u) {
-                        double v = 0.0;
-                        if ((uint32_t)lane == k) v = fl_add_posts(f, idx, r);
-                        __syncwarp();
-                        r = fl_shfl(v, (int)k);
-                    } else {
-                        r += sm.aux1[k];
-                        if (npk_k >= 2u) r += sm.aux2[k];
-                    }
+                r = sm.in[k] + r;
+                if ((manymask >> k) & 1u) {
+                    double v = 0.0;
+                    if ((uint32_t)lane == k) v = fl_add_posts(f, idx, r);
+                    __syncwarp();
+                    r = fl_shfl(v, (int)k);
+                } else {
+                    r = (r + sm.aux1[k]) + sm.aux2[k];
                 }
                 sm.out[k] = r;
             }
@@ -503,10 +549,18 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
             __syncwarp();
             mine = sm.out[lane];
         }
-        const uint32_t hw = fl_warp_max(inwin ? hq : 0u);
-        if (hw > hrun) hrun = hw;
+        // running nesting height after every site of the window (lane 0 is climbed first)
+        uint32_t hs = inwin ? hq : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t w = __shfl_up_sync(FL_FULL, hs, o);
+            if (lane >= o && w > hs) hs = w;
+        }
+        if (hrun > hs) hs = hrun;
+        hrun = __shfl_sync(FL_FULL, hs, 31);
         if (inwin) {
             f.A[idx] = mine;
+            f.hsuf[idx] = hs;
             if (climbs) f.hgt[idx] = FL_NONE;
         }
         if (lane == 0) FL_COUNT(f, first_win ? FLS_W_CYC_FIRSTWIN : FLS_W_CYC_WIN, FL_CLOCK() - t_win);
@@ -531,15 +585,15 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
         }
         uint32_t next_tail = FL_NONE, dep = 0u;
         const long long t_rep = FL_CLOCK();
-        __threadfence();  // every lane publishes its own stores (A, hgt) before lane 0 reports
+        fl_fence_release();  // every lane publishes its own stores (A, hgt) before lane 0 reports
         __syncwarp();
-        if (lane == 0) next_tail = fl_report(f, h, p, hrun, true, &dep);
+        if (lane == 0) next_tail = fl_report(f, h, p, true, &dep);
         next_tail = __shfl_sync(FL_FULL, next_tail, 0);
         if (lane == 0) FL_COUNT(f, FLS_W_CYC_REPORT, FL_CLOCK() - t_rep);
         if (next_tail == FL_NONE) return;
         if (lane == 0) FL_COUNT(f, FLS_W_SEGSTART, 1);
         cur = next_tail + fl_dep0(next_tail);  // the broadcast value came after lane 0's atomics
-        x = 0.0; hrun = 0u; has_chain = false;
+        fl_seg_entry(f, cur, x, hrun, has_chain);
     }
 }
 #endif
@@ -569,6 +623,96 @@ __global__ void __launch_bounds__(256, 2) k_area_flow_long(FlFlow f) {
         if (lane == 0) FL_COUNT(f, FLS_W_CYC_FLOW, FL_CLOCK() - t_flow);
     }
 #endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// Incremental K4.  The drainage area of a site is a function of its subtree only, so between two
+// iterations it changes only at the ancestors of sites whose receiver changed (a few percent of the sites
+// after the first iterations).  Everything the full pass leaves behind -- A, the published partial sums,
+// hgt at the heads, hsuf along the chains -- stays valid elsewhere, in the same numbering.  What is redone:
+//   * regather list: the old and the new receiver of every re-routed site (their child sets changed) and the
+//     receiver of every dirty segment head (a child's area / height changed);
+//   * per segment, the sites from the highest regathered one down to the head are climbed again, starting
+//     from the stored area / running height of the clean chain above (fl_seg_entry);
+//   * the dataflow between dirty segments is the one of the full pass: a dirty head reports to its receiver,
+//     the last reporter regathers, a segment is climbed once when its waiting sites are all published.
+// Every addition is still the reference's, in the reference's order; clean sites simply keep a result that a
+// recomputation would reproduce bit for bit.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fl_mark_up(const FlFlow& f, uint32_t p) {
+    for (;;) {
+        const uint32_t old = atomicOr(&f.nwait[p], FL_NW_RFLAG);
+        if (!(old & FL_NW_RFLAG)) f.rlist[atomicAdd(&f.flags[FL_FLAG_NREGATHER], 1u)] = p;
+        const uint32_t sh = f.seg_head[p];
+        const uint32_t prev = atomicMax(&f.dirty_from[sh], p + 1u);
+        if (prev != 0u) return;  // the segment is already dirty: whoever marked it first walks on from its head
+        f.slist[atomicAdd(&f.flags[FL_FLAG_NDIRTY], 1u)] = sh;
+        const uint32_t pp = f.recv[sh];
+        if (pp == sh) return;  // tree root
+        atomicAdd(&f.nwait[pp], 1u);  // the dirty head sh will report to pp
+        p = pp;
+    }
+}
+
+// one thread per re-routed site (list written by K1)
+__global__ void __launch_bounds__(128) k_incr_mark(FlFlow f, uint32_t nchg, const uint32_t* __restrict__ chg_node,
+                                                    const uint32_t* __restrict__ chg_old) {
+    const uint32_t k = FL_TID;
+    if (k >= nchg) return;
+    const uint32_t q = chg_node[k], po = chg_old[k], pn = f.recv[q];
+    if (q > 0u && pn == q - 1u) f.hgt[q] = FL_NONE;         // now chained to its receiver: no longer a head
+    else if (q > 0u && po == q - 1u) f.hgt[q] = f.hsuf[q];  // the chain broke below q: q heads what is left of it
+    if (pn != q) fl_mark_up(f, pn);
+    if (po != q) fl_mark_up(f, po);
+}
+
+// regather list: sites that wait for dirty heads are counted on their segment, the others are published here
+__global__ void __launch_bounds__(128) k_incr_prepare(FlFlow f) {
+    const uint32_t cnt = f.flags[FL_FLAG_NREGATHER];
+    for (uint32_t k = FL_TID; k < cnt; k += gridDim.x * blockDim.x) {
+        const uint32_t p = f.rlist[k];
+        f.state[p] = 0u;
+        if (f.nwait[p] & FL_NW_COUNT) { atomicAdd(&f.seg_wait[f.seg_head[p]], 1u); continue; }
+        const uint32_t cm = f.cmask[p];
+        const bool has_chain = (p + 1u < f.n) && (f.recv[p + 1u] == p);
+        if (cm == 0u || (uint32_t)__popc(cm) - (has_chain ? 1u : 0u) == 0u) continue;  // nothing to gather
+        double pre, p1, p2;
+        uint32_t hp;
+        const uint32_t np = fl_gather_lights(f, p, has_chain, 0u, pre, p1, p2, hp);
+        f.pre[p] = pre;
+        f.hpre[p] = hp;
+        if (np >= 1u && np != 15u) f.post1[p] = p1;
+        if (np >= 2u && np != 15u) f.post2[p] = p2;
+        f.state[p] = fl_st_publish(np, hp);
+    }
+}
+
+// dirty segments that wait for nobody start right away; the others are started by their last publisher
+__global__ void __launch_bounds__(64) k_incr_start(FlFlow f) {
+    const uint32_t cnt = f.flags[FL_FLAG_NDIRTY];
+    for (uint32_t k = FL_TID; k < cnt; k += gridDim.x * blockDim.x) {
+        const uint32_t sh = f.slist[k];
+        if (f.seg_wait[sh] != 0u) continue;
+        const uint32_t cur = fl_seg_start(f, sh);
+        double x;
+        uint32_t hrun;
+        bool has_chain;
+        fl_seg_entry(f, cur, x, hrun, has_chain);
+        FL_COUNT(f, FLS_T_CLIMBS, 1);
+        fl_flow_thread(f, cur, x, hrun, has_chain, true);
+    }
+}
+
+// leave the bookkeeping zeroed for the next incremental pass
+__global__ void __launch_bounds__(256) k_incr_cleanup(FlFlow f) {
+    const uint32_t nr = f.flags[FL_FLAG_NREGATHER], ns = f.flags[FL_FLAG_NDIRTY];
+    for (uint32_t k = FL_TID; k < nr; k += gridDim.x * blockDim.x) f.nwait[f.rlist[k]] = 0u;
+    for (uint32_t k = FL_TID; k < ns; k += gridDim.x * blockDim.x) {
+        const uint32_t sh = f.slist[k];
+        f.dirty_from[sh] = 0u;
+        f.seg_wait[sh] = 0u;
+        f.seg_done[sh] = 0u;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -51,7 +51,9 @@ __global__ void __launch_bounds__(256) k_receivers_mask(uint32_t n, const uint32
                                                          const double* __restrict__ elev,
                                                          const uint8_t* __restrict__ is_outlet,
                                                          uint32_t* __restrict__ recv, double* __restrict__ drecv,
-                                                         uint32_t* cmask, uint32_t* __restrict__ flags) {
+                                                         uint32_t* cmask, uint32_t* __restrict__ flags,
+                                                         uint32_t* __restrict__ chg_node,
+                                                         uint32_t* __restrict__ chg_old) {
     uint32_t i = FL_TID;
     if (i >= n) return;
     uint32_t best = i, best_s = FL_NONE;
@@ -75,6 +77,14 @@ __global__ void __launch_bounds__(256) k_receivers_mask(uint32_t n, const uint32
             }
         }
         if (best == i) atomicOr(&flags[FL_FLAG_LAKE], 1u);
+    }
+    if (chg_node) {  // incremental K4: sites whose receiver differs from the previous iteration's (final) one
+        const uint32_t old = recv[i];
+        if (old != best) {
+            const uint32_t k = atomicAdd(&flags[FL_FLAG_NCHG], 1u);
+            chg_node[k] = i;
+            chg_old[k] = old;
+        }
     }
     recv[i] = best;
     drecv[i] = best_d;

@@ -121,6 +121,17 @@ struct fastlem_ctx {
     uint32_t* d_sg_tail = nullptr;  // and per head: tail, waiting sites, published sites
     uint32_t* d_sg_wait = nullptr;
     uint32_t* d_sg_done = nullptr;
+    // incremental K4 (fl_flow.cuh): state kept between iterations + per-iteration work lists
+    uint32_t* d_hsuf = nullptr;
+    uint32_t* d_dirty_from = nullptr;
+    uint32_t* d_rlist = nullptr;
+    uint32_t* d_slist = nullptr;
+    uint32_t* d_chg_node = nullptr;
+    uint32_t* d_chg_old = nullptr;
+    bool k4_valid = false;      // the arrays above and A/pre/post/state/hgt describe the forest of L.recv
+    bool k4_last_full = true;   // the previous K4 was a full pass (its counters are not zeroed)
+    int64_t opt_incremental = 1;
+    int64_t opt_incr_div = 16;  // incremental pass when re-routed sites * incr_div <= n
     unsigned long long* d_flow_stats = nullptr;
     uint32_t prev_maxh = 0;
     double* d_tcel = nullptr;
@@ -294,6 +305,7 @@ int profile_accumulate(fastlem_ctx* c) {
 int iterate_levels(fastlem_ctx* c, bool first, bool* changed_out) {
     const uint32_t n = c->n;
     Layout& L = L_(c);
+    c->k4_valid = false;
     FL_CK(fl_memset(c->d_flags, 0, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
     FL_RC(stage_mark(c, 0));
 
@@ -415,13 +427,14 @@ int rebuild_layout(fastlem_ctx* c, const double* weight) {
 
 int iterate_paths(fastlem_ctx* c, bool* changed_out) {
     const uint32_t n = c->n;
+    c->k4_valid = false;
     FL_CK(fl_memset(c->d_flags, 0, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
     FL_CK(fl_memset(L_(c).cmask, 0, sizeof(uint32_t) * n, c->stream));
     FL_RC(stage_mark(c, 0));
     {
         Layout& L = L_(c);
         LAUNCH_N(k_receivers_mask, n, n, L.row_ptr, L.col, L.dist, L.rev, L.elev, L.is_outlet, L.recv, L.drecv, L.cmask,
-                 c->d_flags);
+                 c->d_flags, (uint32_t*)nullptr, (uint32_t*)nullptr);
         c->stats.n_receivers++;
     }
     FL_RC(stage_mark(c, 1));
@@ -527,15 +540,18 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     FL_CK(fl_memset(c->d_flags, 0, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
     FL_CK(fl_memset(L_(c).cmask, 0, sizeof(uint32_t) * n, c->stream));
     FL_RC(stage_mark(c, 0));
+    // K1 lists the re-routed sites when the K4 state of the previous iteration can be reused
+    const bool track = c->opt_incremental != 0 && c->k4_valid && !c->need_rebuild && c->opt_rebuild_every != 1;
     {
         Layout& L = L_(c);
         LAUNCH_N(k_receivers_mask, n, n, L.row_ptr, L.col, L.dist, L.rev, L.elev, L.is_outlet, L.recv, L.drecv, L.cmask,
-                 c->d_flags);
+                 c->d_flags, track ? c->d_chg_node : (uint32_t*)nullptr, track ? c->d_chg_old : (uint32_t*)nullptr);
         c->stats.n_receivers++;
     }
     FL_RC(stage_mark(c, 1));
     FL_RC(read_flags(c));
     const bool has_lake = c->h_flags[FL_FLAG_LAKE] != 0;
+    const uint32_t n_chg = c->h_flags[FL_FLAG_NCHG];
     FL_RC(stage_mark(c, 2));
     c->stages_valid = false;
     if (has_lake) {
@@ -553,15 +569,10 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     c->need_rebuild = false;
     FL_RC(stage_mark(c, 7));  // end of the layout rebuild
     Layout& L = L_(c);
+    const bool incr = track && !has_lake && !rebuilt &&
+                      (unsigned long long)n_chg * (unsigned long long)c->opt_incr_div <= (unsigned long long)n;
 
     // K4 (fl_flow.cuh): segment bookkeeping, then the two dataflow passes
-    FL_CK(fl_memset(c->d_state, 0, sizeof(uint32_t) * n, c->stream));
-    FL_CK(fl_memset(c->d_nwait, 0, sizeof(uint32_t) * n, c->stream));
-    FL_CK(fl_memset(c->d_sg_wait, 0, sizeof(uint32_t) * n, c->stream));
-    FL_CK(fl_memset(c->d_sg_done, 0, sizeof(uint32_t) * n, c->stream));
-    LAUNCH_N(k_count_waits, n, n, L.recv, L.cmask, c->d_nwait);
-    LAUNCH_N(k_seg_keys, n, n, L.recv, c->d_depth);
-    FL_CK(fl_inclusive_max(c->d_tmp, c->tmp_bytes, c->d_depth, c->d_sg_head, n, c->stream, false));
     FlFlow f;
     f.n = n; f.row_ptr = L.row_ptr; f.col = L.col; f.recv = L.recv; f.cmask = L.cmask; f.areas = L.areas;
     f.A = c->d_A; f.nwait = c->d_nwait; f.seg_head = c->d_sg_head; f.seg_tail = c->d_sg_tail;
@@ -569,18 +580,54 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     f.post1 = c->d_post1; f.post2 = c->d_post2; f.hpre = c->d_hpre; f.xbuf = c->d_xbuf; f.hbuf = c->d_hbuf;
     f.hgt = c->d_hgt; f.flags = c->d_flags; f.parked = c->d_parked; f.counters = c->d_flags + FL_FLAG_PARKED;
     f.park_after = (uint32_t)c->opt_park_after; f.stats = c->d_flow_stats;
-    LAUNCH_N(k_seg_prepare, n, f, c->d_sg_tail, c->d_sg_wait);
-    LAUNCH_N(k_area_flow, n, f);
-    if (f.park_after) {  // the parked (long) climbs, one warp each (persistent grid)
-        FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 4u, 256, c->stream, f);
-        c->stats.kernel_launches++;
+    f.hsuf = c->d_hsuf; f.dirty_from = nullptr; f.rlist = c->d_rlist; f.slist = c->d_slist;
+    if (!incr) {
+        FL_CK(fl_memset(c->d_state, 0, sizeof(uint32_t) * n, c->stream));
+        FL_CK(fl_memset(c->d_nwait, 0, sizeof(uint32_t) * n, c->stream));
+        FL_CK(fl_memset(c->d_sg_wait, 0, sizeof(uint32_t) * n, c->stream));
+        FL_CK(fl_memset(c->d_sg_done, 0, sizeof(uint32_t) * n, c->stream));
+        LAUNCH_N(k_count_waits, n, n, L.recv, L.cmask, L.areas, c->d_nwait, c->d_A, c->d_hgt, c->d_hsuf);
+        LAUNCH_N(k_seg_keys, n, n, L.recv, c->d_depth);
+        FL_CK(fl_inclusive_max(c->d_tmp, c->tmp_bytes, c->d_depth, c->d_sg_head, n, c->stream, false));
+        LAUNCH_N(k_seg_prepare, n, f, c->d_sg_tail, c->d_sg_wait);
+        LAUNCH_N(k_area_flow, n, f);
+        if (f.park_after) {  // the parked (long) climbs, one warp each (persistent grid)
+            FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 4u, 256, c->stream, f);
+            c->stats.kernel_launches++;
+        }
+        c->stats.n_area += 6;
+        c->k4_valid = true;
+        c->k4_last_full = true;
+    } else {
+        if (c->k4_last_full) {  // the full pass leaves its counters behind
+            FL_CK(fl_memset(c->d_nwait, 0, sizeof(uint32_t) * n, c->stream));
+            FL_CK(fl_memset(c->d_sg_wait, 0, sizeof(uint32_t) * n, c->stream));
+            FL_CK(fl_memset(c->d_sg_done, 0, sizeof(uint32_t) * n, c->stream));
+            FL_CK(fl_memset(c->d_dirty_from, 0, sizeof(uint32_t) * n, c->stream));
+            c->k4_last_full = false;
+        }
+        if (n_chg) {
+            f.dirty_from = c->d_dirty_from;
+            LAUNCH_N(k_seg_keys, n, n, L.recv, c->d_depth);
+            FL_CK(fl_inclusive_max(c->d_tmp, c->tmp_bytes, c->d_depth, c->d_sg_head, n, c->stream, false));
+            FL_LAUNCH(k_incr_mark, blocks_for(n_chg, 128), 128, c->stream, f, n_chg, c->d_chg_node, c->d_chg_old);
+            const unsigned wide = (unsigned)c->sm_count * 8u;
+            FL_LAUNCH(k_incr_prepare, wide, 128, c->stream, f);
+            FL_LAUNCH(k_incr_start, wide * 2u, 64, c->stream, f);
+            if (f.park_after) FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 4u, 256, c->stream, f);
+            FL_LAUNCH(k_incr_cleanup, wide, 256, c->stream, f);
+            c->stats.kernel_launches += f.park_after ? 7 : 6;
+            c->stats.n_area += f.park_after ? 7 : 6;
+        }
+        c->stats.incremental_iterations++;
     }
-    c->stats.n_area += 6;
     FL_RC(stage_mark(c, 8));  // end of K4
 
-    // order the segment heads by descending nesting height (exact for the current forest)
+    // order the segment heads by descending nesting height (exact for the current forest; an upper bound of the
+    // largest height after incremental passes -- heights that no longer occur are empty levels)
     FL_RC(read_flags(c));
-    const uint32_t maxh = c->h_flags[FL_FLAG_MAXDEPTH];
+    uint32_t maxh = c->h_flags[FL_FLAG_MAXDEPTH];
+    if (incr && c->prev_maxh > maxh) maxh = c->prev_maxh;
     if (c->h_flags[FL_FLAG_BROKEN]) return fail(c, FASTLEM_E_STATE, "K4: a climb met an unpublished site (internal error)");
     int bits = 1;
     while (bits < 32 && (1ull << bits) <= (unsigned long long)maxh + 1ull) ++bits;
@@ -592,8 +639,10 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     LAUNCH_N(k_level_offsets, n, n, c->d_sorted, c->d_offs, c->d_flags);
     FL_CK(fl_d2h(c->h_offs, c->d_offs, sizeof(uint32_t) * ((size_t)maxh + 2), c->stream));
     FL_RC(read_flags(c));
-    if (c->h_flags[FL_FLAG_MAXDEPTH] != maxh) return fail(c, FASTLEM_E_STATE, "flow: height bookkeeping broke");
+    const uint32_t last_key = c->h_flags[FL_FLAG_MAXDEPTH];  // = maxh - (smallest height that occurs)
+    if (last_key > maxh || (!incr && last_key != maxh)) return fail(c, FASTLEM_E_STATE, "flow: height bookkeeping broke");
     const uint32_t n_heads = c->h_flags[FL_FLAG_REACHED];
+    for (uint32_t g = last_key + 2; g <= maxh + 1; ++g) c->h_offs[g] = n_heads;
     for (uint32_t g = maxh + 1; g-- > 0;)
         if (c->h_offs[g] == FL_NONE) c->h_offs[g] = c->h_offs[g + 1];
     c->stats.n_order += 3;
@@ -663,6 +712,8 @@ int reset_layout(fastlem_ctx* c) {
     LAUNCH_N(k_iota, n, n, L.orig_of);
     FL_CK(fl_memset(L.lvl, 0, sizeof(uint32_t) * n, c->stream));
     c->prev_maxh = 0;
+    c->k4_valid = false;
+    c->k4_last_full = true;
     if (c->rank_ready) {
         FL_CK(fl_d2d(L.rank, O.rank, sizeof(uint32_t) * n, c->stream));
         FL_CK(fl_memset(c->d_rank_to_node, 0xFF, sizeof(uint32_t) * n, c->stream));
@@ -760,6 +811,11 @@ int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
     } else if (s == "park_after") {
         if (value != 0 && value < 4) return fail(c, FASTLEM_E_INVALID, "option park_after: 0 (never) or >= 4");
         c->opt_park_after = value;
+    } else if (s == "incremental") {
+        c->opt_incremental = value != 0;
+    } else if (s == "incr_div") {
+        if (value < 1) return fail(c, FASTLEM_E_INVALID, "option incr_div: >= 1");
+        c->opt_incr_div = value;
     } else if (s == "rebuild_every") {
         if (value < 0) return fail(c, FASTLEM_E_INVALID, "option rebuild_every: 0 (adaptive) or a positive period");
         c->opt_rebuild_every = value;
@@ -850,6 +906,12 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     FL_CK(dalloc(c, c->d_sg_tail, n));
     FL_CK(dalloc(c, c->d_sg_wait, n));
     FL_CK(dalloc(c, c->d_sg_done, n));
+    FL_CK(dalloc(c, c->d_hsuf, n));
+    FL_CK(dalloc(c, c->d_dirty_from, n));
+    FL_CK(dalloc(c, c->d_rlist, n));
+    FL_CK(dalloc(c, c->d_slist, n));
+    FL_CK(dalloc(c, c->d_chg_node, n));
+    FL_CK(dalloc(c, c->d_chg_old, n));
     FL_CK(dalloc(c, c->d_flow_stats, 32));
     FL_CK(fl_memset(c->d_flow_stats, 0, 32 * sizeof(unsigned long long), c->stream));
     FL_CK(dalloc(c, c->d_tcel, n));

@@ -112,7 +112,7 @@ typedef struct fastlem_stats {
     uint32_t rebuilds;    /* layout rebuilds (site renumberings) during the last run */
     uint32_t path_levels; /* nesting depth of the path decomposition = rounds per sweep */
     uint32_t paths;       /* number of paths */
-    uint32_t reserved;
+    uint32_t incremental_iterations; /* iterations whose drainage areas were updated incrementally */
 } fastlem_stats;
 int fastlem_get_stats(const fastlem_ctx* ctx, fastlem_stats* out);
 

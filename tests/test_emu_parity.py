@@ -117,3 +117,41 @@ def test_rerun_restarts_from_initial(emu_lib):
         a, ita = ctx.generate()
         b, itb = ctx.generate()
         assert ita == itb and np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("incr_div", [1, 4, 16])
+@pytest.mark.parametrize("every", [0, 3, 1000])
+@pytest.mark.parametrize("name", ["uniform", "max_slope", "uplift", "advanced", "disconnected", "lattice_regular",
+                                  "interior_outlets", "single_outlet", "base_field"])
+def test_incremental_area_update(oracle, emu_lib, name, every, incr_div):
+    """K4 redone only above re-routed sites (fl_flow.cuh, 'Incremental K4'): same bits, same iteration count.
+    incr_div = 1 takes the incremental pass whenever the previous state is reusable."""
+    m, p, outlets, initial, max_iteration = scenario(name)
+    with _ctx(emu_lib, sweep=3, rebuild_every=every, incr_div=incr_div) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
+        st = ctx.stats()
+        if name in ("uniform", "advanced", "max_slope") and every != 1:
+            assert st["incremental_iterations"] > 0
+    with _ctx(emu_lib, sweep=3, rebuild_every=every, incremental=0) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
+        assert ctx.stats()["incremental_iterations"] == 0
+
+
+def test_incremental_stages_midway(oracle, emu_lib):
+    """Stage dumps (areas, response times, receivers) after an incremental iteration."""
+    m, p, outlets, initial, _ = scenario("uniform", 6000)
+    for k in (6, 9, 15):
+        e = initial.copy()
+        for _ in range(k - 1):
+            e = oracle.iterate_once(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, e)["elevations"]
+        ref = oracle.iterate_once(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, e)
+        with _ctx(emu_lib, sweep=3, incr_div=1, rebuild_every=1000) as ctx:
+            helpers.load_ctx(ctx, m, p, outlets, initial)
+            out, it = ctx.generate(k)
+            assert it == k and ctx.stats()["incremental_iterations"] >= k - 3
+            assert np.array_equal(out, ref["elevations"])
+            assert np.array_equal(ctx.fetch("receivers"), ref["next"])
+            assert np.array_equal(ctx.fetch("drainage_area"), ref["drainage"])
+            assert np.array_equal(ctx.fetch("response_time"), ref["response"])

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--max-slope", type=float, default=None)
     ap.add_argument("--park-after", type=int, default=None)
     ap.add_argument("--brief", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="solver option name=value (repeatable)")
     args = ap.parse_args()
     cache = f"/tmp/fl_workload_{args.sites}_{int(args.lattice)}.npz"
     if os.path.exists(cache):
@@ -51,6 +52,9 @@ def main():
             ctx.set_option("rebuild_every", args.rebuild_every)
         if args.park_after is not None:
             ctx.set_option("park_after", args.park_after)
+        for kv in args.opt:
+            k, v = kv.split("=")
+            ctx.set_option(k, int(v))
         ctx.set_graph(m["row_ptr"], m["col"], m["dist"], m["areas"])
         ctx.set_parameters(initial, p["erodibility"], p["uplift"], tan, m["default_outlets"])
         for _ in range(args.repeat):
@@ -64,7 +68,7 @@ def main():
             st["ms_per_iter"] = 1e3 * dt / max(it, 1)
             if args.brief:
                 it_ = max(it, 1)
-                print(f"sites={n} park_after={args.park_after} iters={it} ms/iter={st['ms_per_iter']:.3f} K1={st['ms_receivers']/it_:.3f} "
+                print(f"sites={n} opts={args.opt} incr={st['incremental_iterations']} iters={it} ms/iter={st['ms_per_iter']:.3f} K1={st['ms_receivers']/it_:.3f} "
                       f"order={st['ms_order']/it_:.3f} K4={st['ms_area']/it_:.3f} K5={st['ms_elevation']/it_:.3f} rebuilds={st['rebuilds']} "
                       f"levels={st['path_levels']} segs={st['paths']}")
             else:
