@@ -51,8 +51,16 @@ enum { FLS_T_CLIMBS = 0, FLS_T_BATCH, FLS_T_SITES, FLS_T_HEADS, FLS_T_LAST, FLS_
        FLS_W_CYC_FLOW, FLS_W_CYC_REPORT, FLS_W_CYC_FIRSTWIN, FLS_W_CYC_WIN, FLS_COUNT_N = 24 };
 #if defined(FL_FLOW_STATS) && !defined(FL_EMU)
 #define FL_CLOCK() clock64()
+__device__ __forceinline__ unsigned long long fl_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// timeline of a segment (debug): slot 0 climb started, 1 parked, 2 resumed by a warp, 3 head finished
+#define FL_TLOG(f, site, slot) do { if ((f).tlog) (f).tlog[4ull * (f).seg_head[(site)] + (slot)] = fl_gtime(); } while (0)
 #else
 #define FL_CLOCK() 0ll
+#define FL_TLOG(f, site, slot) ((void)0)
 #endif
 
 #ifdef FL_EMU
@@ -105,6 +113,7 @@ struct FlFlow {
     double* pre;
     double* post1;
     double* post2;
+    double* xpost;  // FL_XPOST per site: the 3rd .. 8th child after the chain child (np in 3..8)
     uint32_t* hpre;
     double* xbuf;        // running area of a parked climb
     uint32_t* hbuf;      // running nesting height of a parked climb
@@ -119,6 +128,7 @@ struct FlFlow {
     uint32_t* counters;  // [0] = number of parked climbs, [1] = next one to take
     uint32_t park_after; // a thread parks its climb after this many sites (0 = never)
     unsigned long long* stats;
+    unsigned long long* tlog;  // FL_FLOW_STATS builds: 4 time stamps per segment head
 };
 
 #define FL_NW_RFLAG 0x80000000u
@@ -140,7 +150,15 @@ __device__ __forceinline__ void fl_seg_entry(const FlFlow& f, uint32_t cur, doub
 }
 
 // per-warp staging area of the serial chains (warp-level scans)
-struct FlChainSmem { double in[32]; double out[32]; double aux1[32]; double aux2[32]; };
+#define FL_MAXPOST 8  // children after the chain child kept with a site's partial sums (more: slow path, np = 15)
+#define FL_XPOST (FL_MAXPOST - 2)
+struct FlChainSmem { double in[32]; double out[32]; double aux1[32]; double aux2[32]; };  // K5 windows
+// K4 windows: the additions of a 32-site window, flattened into ONE sequence of terms (per site: its partial sum,
+// then each child after the chain child); the prefix sums overwrite the terms in place.
+struct FlAreaSmem {
+    double t[32 * (1 + FL_MAXPOST) + 8];  // terms
+    double p[32 * (1 + FL_MAXPOST) + 8];  // prefix sums
+};
 
 // Partial sums of site p over its non-chain children, reverse adjacency order; returns np (15 = more than two
 // children after the chain child).  A light child is always a segment head; leaf heads hold A = their cell area
@@ -148,6 +166,7 @@ struct FlChainSmem { double in[32]; double out[32]; double aux1[32]; double aux2
 // the loads of the children's results after the atomic that made the caller the last reporter.
 __device__ __forceinline__ uint32_t fl_gather_lights(const FlFlow& f, uint32_t p, bool has_chain, uint32_t dep,
                                                      double& pre, double& p1, double& p2, uint32_t& hmax) {
+    double* const xp = f.xpost + (size_t)p * FL_XPOST;
     pre = f.areas[p];
     p1 = 0.0; p2 = 0.0;
     uint32_t np = 0;
@@ -182,10 +201,14 @@ __device__ __forceinline__ uint32_t fl_gather_lights(const FlFlow& f, uint32_t p
             else {
                 if (hk[k] > hmax) hmax = hk[k];
                 if (!seen) pre += val[k];
-                else { if (np == 0) p1 = val[k]; else if (np == 1) p2 = val[k]; ++np; }
+                else {
+                    if (np == 0) p1 = val[k]; else if (np == 1) p2 = val[k]; else if (np < FL_MAXPOST) xp[np - 2] = val[k];
+                    ++np;
+                }
             }
         }
     }
+    if (rest) np = 255u;  // more than 8 children: slow path
     while (rest) {  // more than 8 children: one at a time
         const uint32_t b = 31u - (uint32_t)__clz((int)rest);
         rest ^= 1u << b;
@@ -195,13 +218,12 @@ __device__ __forceinline__ uint32_t fl_gather_lights(const FlFlow& f, uint32_t p
         const uint32_t hc = fl_ld_cg(&f.hgt[c + dep]) + 1u;
         if (hc > hmax) hmax = hc;
         if (!seen) pre += v;
-        else { if (np == 0) p1 = v; else if (np == 1) p2 = v; ++np; }
     }
-    return np > 2 ? 15u : np;
+    return np > FL_MAXPOST ? 15u : np;
 }
 
-// slow path for np == 15: add every child after the chain child, in order
-__device__ __noinline__ double fl_add_posts(const FlFlow& f, uint32_t p, double y) {
+// np == 15: add every child after the chain child, in order, straight from the children
+__device__ __noinline__ double fl_add_posts_slow(const FlFlow& f, uint32_t p, double y) {
     bool seen = false;
     const uint32_t s0 = f.row_ptr[p];
     uint32_t m = f.cmask[p];
@@ -222,6 +244,18 @@ __device__ __forceinline__ void fl_fence_release() {
 #endif
 }
 
+// gather the partial sums of p and store them; returns the state word that publishes them
+__device__ __forceinline__ uint32_t fl_gather_store(const FlFlow& f, uint32_t p, bool has_chain, uint32_t dep) {
+    double pre, p1, p2;
+    uint32_t hp;
+    const uint32_t np = fl_gather_lights(f, p, has_chain, dep, pre, p1, p2, hp);
+    f.pre[p] = pre;
+    f.hpre[p] = hp;
+    if (np >= 1u && np != 15u) f.post1[p] = p1;
+    if (np >= 2u && np != 15u) f.post2[p] = p2;
+    return fl_st_publish(np, hp);
+}
+
 // A finished segment head `h` (area y already stored) reports to its receiver p.  Returns the site where the
 // next climb starts (the caller continues there), or FL_NONE when this flow ends.  *dep_out carries the
 // opaque zero that orders the next climb's loads after the deciding atomic.  `fenced`: the caller has already
@@ -237,14 +271,7 @@ __device__ __forceinline__ uint32_t fl_report(const FlFlow& f, uint32_t h, uint3
     if ((prev & FL_ST_COUNT_MASK) + 1u < nw) return FL_NONE;
     // last reporter at p: gather and publish p's partial sums
     const uint32_t swait = f.seg_wait[sh];
-    double pre, p1, p2;
-    uint32_t hp;
-    const uint32_t np = fl_gather_lights(f, p, p_has_chain, fl_dep0(prev), pre, p1, p2, hp);
-    f.pre[p] = pre;
-    f.hpre[p] = hp;
-    if (np >= 1u && np != 15u) f.post1[p] = p1;
-    if (np >= 2u && np != 15u) f.post2[p] = p2;
-    f.state[p] = fl_st_publish(np, hp);  // no report can follow the last one: a plain store
+    f.state[p] = fl_gather_store(f, p, p_has_chain, fl_dep0(prev));  // no report can follow the last one: a plain store
     fl_fence_release();  // publish the partial sums before the segment counter moves
     const uint32_t done = atomicAdd(&f.seg_done[sh], 1u) + 1u;
     if (done < swait) return FL_NONE;
@@ -257,6 +284,7 @@ __device__ __forceinline__ uint32_t fl_report(const FlFlow& f, uint32_t h, uint3
 // ------------------------------------------------------------------------------------------------
 __device__ void fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t hrun, bool has_chain, bool may_park) {
     uint32_t climbed = 0;
+    if (may_park) FL_TLOG(f, cur, 0);
     for (;;) {
         double y = 0.0;
         uint32_t p = FL_NONE;
@@ -292,10 +320,20 @@ __device__ void fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t
                     }
                     const uint32_t npk = fl_st_np(st[k]);
                     y = hc ? (pr[k] + x) : pr[k];
-                    if (npk == 15u) y = fl_add_posts(f, idx, y);
-                    else {
-                        if (npk >= 1u) y += q1[k];
-                        if (npk >= 2u) y += fl_ld_cg(&f.post2[idx]);
+                    if (npk == 15u) y = fl_add_posts_slow(f, idx, y);
+                    else if (npk >= 1u) {
+                        y += q1[k];
+                        if (npk >= 2u) {
+                            const double p2v = fl_ld_cg(&f.post2[idx]);
+                            double xv[FL_XPOST];
+#pragma unroll
+                            for (int j = 0; j < FL_XPOST; ++j)
+                                xv[j] = ((uint32_t)j + 2u < npk) ? fl_ld_cg(&f.xpost[(size_t)idx * FL_XPOST + j]) : 0.0;
+                            y += p2v;
+#pragma unroll
+                            for (int j = 0; j < FL_XPOST; ++j)
+                                if ((uint32_t)j + 2u < npk) y += xv[j];
+                        }
                     }
                     const uint32_t hq = fl_st_hp(st[k], f.hpre, idx);
                     if (hq > hrun) hrun = hq;
@@ -319,6 +357,7 @@ __device__ void fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t
             climbed += done;
             if (may_park && f.park_after != 0u && climbed >= f.park_after) {
                 FL_COUNT(f, FLS_T_PARKED, 1);
+                FL_TLOG(f, cur, 1);
                 f.xbuf[cur] = x;  // a long chain: leave the rest to the warp-level pass
                 f.hbuf[cur] = hrun;
                 f.parked[atomicAdd(&f.counters[0], 1u)] = cur;
@@ -328,6 +367,7 @@ __device__ void fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t
         }
         // ---- `cur` is the segment head with final area y; p = recv[cur] ----
         FL_COUNT(f, FLS_T_HEADS, 1);
+        FL_TLOG(f, cur, 3);
         f.hgt[cur] = hrun;
         if (p == cur) {  // tree root: its segment has the largest nesting height of the tree
             if (hrun > 0u) atomicMax(&f.flags[FL_FLAG_MAXDEPTH], hrun);
@@ -338,6 +378,7 @@ __device__ void fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t
         if (next_tail == FL_NONE) return;
         FL_COUNT(f, FLS_T_SEGSTART, 1);
         cur = next_tail + dep; climbed = 0u;
+        FL_TLOG(f, cur, 0);
         fl_seg_entry(f, cur, x, hrun, has_chain);
     }
 }
@@ -381,14 +422,7 @@ __global__ void __launch_bounds__(256) k_seg_prepare(FlFlow f, uint32_t* seg_tai
     if (cm == 0u) return;
     if (f.nwait[q] != 0u) { atomicAdd(&seg_wait[sh], 1u); return; }
     if ((uint32_t)__popc(cm) - (has_chain ? 1u : 0u) == 0u) return;  // only the chain child
-    double pre, p1, p2;
-    uint32_t hp;
-    const uint32_t np = fl_gather_lights(f, q, has_chain, 0u, pre, p1, p2, hp);
-    f.pre[q] = pre;
-    f.hpre[q] = hp;
-    if (np >= 1u && np != 15u) f.post1[q] = p1;
-    if (np >= 2u && np != 15u) f.post2[q] = p2;
-    f.state[q] = fl_st_publish(np, hp);
+    f.state[q] = fl_gather_store(f, q, has_chain, 0u);
 }
 
 // pass 1: one thread per segment TAIL whose segment waits for nobody; all other segments are started by the
@@ -441,7 +475,7 @@ __device__ __forceinline__ FlWin fl_win_load(const FlFlow& f, uint32_t base, int
 
 #define FL_WDEPTH 3  // windows kept in flight on a long chain
 
-__device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t hrun, bool has_chain, FlChainSmem& sm) {
+__device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t hrun, bool has_chain, FlAreaSmem& sm) {
     const int lane = threadIdx.x & 31;
     // ring[j] holds the window whose lane 0 is site cur - 32*j, for j < nring
     FlWin ring[FL_WDEPTH];
@@ -487,67 +521,88 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
             if (hq == FL_ST_HP_OVER) hq = fl_ld_cg(&f.hpre[idx]);
         }
         if (lane == 0) { FL_COUNT(f, FLS_W_WINDOWS, 1); FL_COUNT(f, FLS_W_SITES, nproc); }
-        const uint32_t postmask = __ballot_sync(FL_FULL, lit && npk != 0u);
-        const uint32_t manymask = __ballot_sync(FL_FULL, lit && npk == 15u);
-        // The first site of a segment without a chain child starts from x = 0.0: b + 0.0 == b exactly (areas are
-        // positive), so the chains below need no special case for it.
+        // The first site of a segment without a chain child starts from x = 0.0: 0.0 + b == b exactly (areas are
+        // positive), so the chain below needs no special case for it.
         if (!has_chain) x = 0.0;
-        double mine;
-        if (postmask == 0u) {
-            // no children after the chain child anywhere in the window: y_k = b_k + y_{k-1}.
-            // Terms staged in shared memory, identical chain in every lane over broadcast reads.
+        // my site's terms: b, then the children after the chain child
+        uint32_t nterm = 0u;
+        bool slow = false;
+        double xv[FL_XPOST];
+#pragma unroll
+        for (int j = 0; j < FL_XPOST; ++j) xv[j] = 0.0;
+        if (inwin) {
+            nterm = 1u;
+            if (lit) {
+                if (npk == 15u) slow = true;
+                else {
+                    nterm += npk;
+                    if (npk > 2u) {
+#pragma unroll
+                        for (int j = 0; j < FL_XPOST; ++j)
+                            if ((uint32_t)j + 2u < npk) xv[j] = fl_ld_cg(&f.xpost[(size_t)idx * FL_XPOST + j]);
+                    }
+                }
+            }
+        }
+        const uint32_t slowmask = __ballot_sync(FL_FULL, slow);
+        uint32_t off = nterm;  // inclusive scan over the lanes -> where my terms go
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t w = __shfl_up_sync(FL_FULL, off, o);
+            if (lane >= o) off += w;
+        }
+        const uint32_t nall = __shfl_sync(FL_FULL, off, 31);
+        off -= nterm;
+        double mine = 0.0;
+        if (slowmask == 0u) {
             __syncwarp();
-            sm.in[lane] = b;
+            if (inwin) {
+                sm.t[off] = b;
+                if (lit) {
+                    if (npk >= 1u) sm.t[off + 1u] = q1;
+                    if (npk >= 2u) sm.t[off + 2u] = q2;
+#pragma unroll
+                    for (int j = 0; j < FL_XPOST; ++j)
+                        if ((uint32_t)j + 2u < npk) sm.t[off + 3u + (uint32_t)j] = xv[j];
+                }
+            }
+            if (lane < 8) sm.t[nall + (uint32_t)lane] = 0.0;  // padding: r + 0.0 == r
             __syncwarp();
+            // the serial chain, identically in every lane: 8 terms fetched together, then 8 dependent additions
             double r = x;
-#pragma unroll 4
-            for (uint32_t k = 0; k < nproc; ++k) {  // code kept small on purpose: the kernel must stay in the i-cache
-                r = sm.in[k] + r;
-                sm.out[k] = r;
+            for (uint32_t t0 = 0; t0 < nall; t0 += 8u) {
+                double v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = sm.t[t0 + (uint32_t)j];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { r = r + v[j]; v[j] = r; }
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) sm.p[t0 + (uint32_t)j] = v[j];
+                }
             }
             x = r;
             __syncwarp();
-            mine = sm.out[lane];
-        } else if (manymask == 0u) {
-            // at most two children after the chain child: y_k = ((b_k + y_{k-1}) + q1_k) + q2_k with absent terms
-            // = 0.0 (y + 0.0 == y exactly), so the chain is branch-free
-            __syncwarp();
-            sm.in[lane] = b;
-            sm.aux1[lane] = q1;
-            sm.aux2[lane] = q2;
-            __syncwarp();
-            double r = x;
-#pragma unroll 4
-            for (uint32_t k = 0; k < nproc; ++k) {
-                r = ((sm.in[k] + r) + sm.aux1[k]) + sm.aux2[k];
-                sm.out[k] = r;
-            }
-            x = r;
-            __syncwarp();
-            mine = sm.out[lane];
+            if (inwin) mine = sm.p[off + nterm - 1u];
         } else {
-            // some site of the window has more than two children after its chain child (rare)
-            __syncwarp();
-            sm.in[lane] = b;
-            sm.aux1[lane] = q1;
-            sm.aux2[lane] = q2;
-            __syncwarp();
+            // a site with more than FL_MAXPOST children after its chain child (or more than 8 children): rare
             double r = x;
             for (uint32_t k = 0; k < nproc; ++k) {
-                r = sm.in[k] + r;
-                if ((manymask >> k) & 1u) {
+                r = fl_shfl(b, (int)k) + r;
+                const uint32_t npk_k = __shfl_sync(FL_FULL, lit ? npk : 0u, (int)k);
+                if (npk_k >= 3u) {  // all children after the chain child, straight from the children
                     double v = 0.0;
-                    if ((uint32_t)lane == k) v = fl_add_posts(f, idx, r);
+                    if ((uint32_t)lane == k) v = fl_add_posts_slow(f, idx, r);
                     __syncwarp();
                     r = fl_shfl(v, (int)k);
                 } else {
-                    r = (r + sm.aux1[k]) + sm.aux2[k];
+                    const double a1 = fl_shfl(q1, (int)k), a2 = fl_shfl(q2, (int)k);
+                    if (npk_k >= 1u) r += a1;
+                    if (npk_k >= 2u) r += a2;
                 }
-                sm.out[k] = r;
+                if ((uint32_t)lane == k) mine = r;
             }
             x = r;
-            __syncwarp();
-            mine = sm.out[lane];
         }
         // running nesting height after every site of the window (lane 0 is climbed first)
         uint32_t hs = inwin ? hq : 0u;
@@ -578,7 +633,7 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
         const uint32_t h = cur - (uint32_t)lastl;
         const uint32_t p = __shfl_sync(FL_FULL, win.rc, lastl);
         nring = 0u;
-        if (lane == 0) { f.hgt[h] = hrun; FL_COUNT(f, FLS_W_HEADS, 1); }
+        if (lane == 0) { f.hgt[h] = hrun; FL_COUNT(f, FLS_W_HEADS, 1); FL_TLOG(f, h, 3); }
         if (p == h) {
             if (lane == 0 && hrun > 0u) atomicMax(&f.flags[FL_FLAG_MAXDEPTH], hrun);
             return;
@@ -593,6 +648,7 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
         if (next_tail == FL_NONE) return;
         if (lane == 0) FL_COUNT(f, FLS_W_SEGSTART, 1);
         cur = next_tail + fl_dep0(next_tail);  // the broadcast value came after lane 0's atomics
+        if (lane == 0) FL_TLOG(f, cur, 0);
         fl_seg_entry(f, cur, x, hrun, has_chain);
     }
 }
@@ -608,8 +664,8 @@ __global__ void __launch_bounds__(256, 2) k_area_flow_long(FlFlow f) {
         fl_flow_thread(f, cur, f.xbuf[cur], f.hbuf[cur], true, false);
     }
 #else
-    __shared__ FlChainSmem chain_smem[8];  // one per warp (256 threads)
-    FlChainSmem& sm = chain_smem[threadIdx.x >> 5];
+    __shared__ FlAreaSmem chain_smem[8];  // one per warp (256 threads)
+    FlAreaSmem& sm = chain_smem[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     for (;;) {
         uint32_t i = 0u;
@@ -617,7 +673,7 @@ __global__ void __launch_bounds__(256, 2) k_area_flow_long(FlFlow f) {
         i = __shfl_sync(FL_FULL, i, 0);
         if (i >= count) return;
         const uint32_t cur = f.parked[i];
-        if (lane == 0) FL_COUNT(f, FLS_W_FLOWS, 1);
+        if (lane == 0) { FL_COUNT(f, FLS_W_FLOWS, 1); FL_TLOG(f, cur, 2); }
         const long long t_flow = FL_CLOCK();
         fl_flow_warp(f, cur, fl_ld_cg(&f.xbuf[cur]), fl_ld_cg(&f.hbuf[cur]), true, sm);
         if (lane == 0) FL_COUNT(f, FLS_W_CYC_FLOW, FL_CLOCK() - t_flow);
@@ -676,14 +732,7 @@ __global__ void __launch_bounds__(128) k_incr_prepare(FlFlow f) {
         const uint32_t cm = f.cmask[p];
         const bool has_chain = (p + 1u < f.n) && (f.recv[p + 1u] == p);
         if (cm == 0u || (uint32_t)__popc(cm) - (has_chain ? 1u : 0u) == 0u) continue;  // nothing to gather
-        double pre, p1, p2;
-        uint32_t hp;
-        const uint32_t np = fl_gather_lights(f, p, has_chain, 0u, pre, p1, p2, hp);
-        f.pre[p] = pre;
-        f.hpre[p] = hp;
-        if (np >= 1u && np != 15u) f.post1[p] = p1;
-        if (np >= 2u && np != 15u) f.post2[p] = p2;
-        f.state[p] = fl_st_publish(np, hp);
+        f.state[p] = fl_gather_store(f, p, has_chain, 0u);
     }
 }
 

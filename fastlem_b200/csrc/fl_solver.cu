@@ -111,6 +111,7 @@ struct fastlem_ctx {
     double* d_post1 = nullptr;
     double* d_post2 = nullptr;
     double* d_xbuf = nullptr;
+    double* d_xpost = nullptr;
     uint32_t* d_hbuf = nullptr;
     uint32_t* d_hgt = nullptr;
     uint32_t* d_hpre = nullptr;
@@ -133,6 +134,7 @@ struct fastlem_ctx {
     int64_t opt_incremental = 1;
     int64_t opt_incr_div = 16;  // incremental pass when re-routed sites * incr_div <= n
     unsigned long long* d_flow_stats = nullptr;
+    unsigned long long* d_tlog = nullptr;  // FL_FLOW_STATS builds only
     uint32_t prev_maxh = 0;
     double* d_tcel = nullptr;
     int sm_count = 148;
@@ -577,9 +579,9 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     f.n = n; f.row_ptr = L.row_ptr; f.col = L.col; f.recv = L.recv; f.cmask = L.cmask; f.areas = L.areas;
     f.A = c->d_A; f.nwait = c->d_nwait; f.seg_head = c->d_sg_head; f.seg_tail = c->d_sg_tail;
     f.seg_wait = c->d_sg_wait; f.seg_done = c->d_sg_done; f.state = c->d_state; f.pre = c->d_pre;
-    f.post1 = c->d_post1; f.post2 = c->d_post2; f.hpre = c->d_hpre; f.xbuf = c->d_xbuf; f.hbuf = c->d_hbuf;
+    f.post1 = c->d_post1; f.post2 = c->d_post2; f.xpost = c->d_xpost; f.hpre = c->d_hpre; f.xbuf = c->d_xbuf; f.hbuf = c->d_hbuf;
     f.hgt = c->d_hgt; f.flags = c->d_flags; f.parked = c->d_parked; f.counters = c->d_flags + FL_FLAG_PARKED;
-    f.park_after = (uint32_t)c->opt_park_after; f.stats = c->d_flow_stats;
+    f.park_after = (uint32_t)c->opt_park_after; f.stats = c->d_flow_stats; f.tlog = c->d_tlog;
     f.hsuf = c->d_hsuf; f.dirty_from = nullptr; f.rlist = c->d_rlist; f.slist = c->d_slist;
     if (!incr) {
         FL_CK(fl_memset(c->d_state, 0, sizeof(uint32_t) * n, c->stream));
@@ -896,6 +898,7 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     FL_CK(dalloc(c, c->d_post1, n));
     FL_CK(dalloc(c, c->d_post2, n));
     FL_CK(dalloc(c, c->d_xbuf, n));
+    FL_CK(dalloc(c, c->d_xpost, (size_t)n * FL_XPOST));
     FL_CK(dalloc(c, c->d_hbuf, n));
     FL_CK(dalloc(c, c->d_hgt, n));
     FL_CK(dalloc(c, c->d_hpre, n));
@@ -912,6 +915,10 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     FL_CK(dalloc(c, c->d_slist, n));
     FL_CK(dalloc(c, c->d_chg_node, n));
     FL_CK(dalloc(c, c->d_chg_old, n));
+#ifdef FL_FLOW_STATS
+    FL_CK(dalloc(c, c->d_tlog, (size_t)n * 4));
+    FL_CK(fl_memset(c->d_tlog, 0, sizeof(unsigned long long) * 4 * n, c->stream));
+#endif
     FL_CK(dalloc(c, c->d_flow_stats, 32));
     FL_CK(fl_memset(c->d_flow_stats, 0, 32 * sizeof(unsigned long long), c->stream));
     FL_CK(dalloc(c, c->d_tcel, n));
@@ -1063,6 +1070,25 @@ int fastlem_debug_fetch(fastlem_ctx* c, int stage, void* out, size_t bytes) {
         FL_CK(fl_stream_sync(c->stream));
         return FASTLEM_OK;
     }
+#ifdef FL_FLOW_STATS
+    if (stage >= 100) {  // raw internal arrays in the CURRENT numbering (debug builds)
+        const void* src = nullptr;
+        size_t want = (size_t)n * 4;
+        switch (stage) {
+            case 100: src = c->d_tlog; want = (size_t)n * 32; break;
+            case 101: src = L_(c).recv; break;
+            case 102: src = c->d_sg_head; break;
+            case 103: src = c->d_hgt; break;
+            case 104: src = c->d_dirty_from; break;
+            default: return fail(c, FASTLEM_E_INVALID, "debug_fetch: unknown raw stage");
+        }
+        if (bytes != want) return fail(c, FASTLEM_E_INVALID, "debug_fetch: wrong buffer size");
+        FL_CK(fl_d2h(out, src, bytes, c->stream));
+        if (stage == 100) FL_CK(fl_memset(c->d_tlog, 0, want, c->stream));
+        FL_CK(fl_stream_sync(c->stream));
+        return FASTLEM_OK;
+    }
+#endif
     if (!c->layout_valid && stage != FASTLEM_STAGE_FLOOD_RANK)
         return fail(c, FASTLEM_E_STATE, "debug_fetch: no run yet");
     Layout& L = L_(c);
