@@ -300,11 +300,12 @@ def main():
                            "sweep": args.sweep},
                 "generate_seconds": wall_max / args.steps, "device_ms_per_step": 1e3 * dev_max / args.steps,
                 "first_iteration_tree_depth": last["depth_first"],
+                "incremental_area_iterations": last["incremental_iterations"],
                 "layout": {"rebuilds_per_step": last["rebuilds"], "nesting_levels": last["path_levels"],
                            "segments": last["paths"]},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(graph_bytes + param_bytes),
                         "d2h_bytes_per_step": int(8 * n), "seconds_per_step": float(te[0]) / args.steps,
-                        "flood_rank_host_ms": e2e_stats["ms_flood_rank"], "upload_ms": e2e_stats["ms_upload"],
+                        "flood_rank_ms": e2e_stats["ms_flood_rank"], "flood_rank_on_device": bool(e2e_stats["flood_on_device"]), "upload_ms": e2e_stats["ms_upload"],
                         "seconds_by_call": e2e_parts, "device_ms_in_generate": e2e_stats["ms_run"],
                         "host_buffers": "pinned host arrays handed to the C ABI as plain pointers"},
                 "gpu_launches": launches_all, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,

@@ -37,7 +37,8 @@ class Stats(ctypes.Structure):
                 ("n_receivers", ctypes.c_uint64), ("n_labels", ctypes.c_uint64), ("n_lakes", ctypes.c_uint64),
                 ("n_order", ctypes.c_uint64), ("n_area", ctypes.c_uint64), ("n_elevation", ctypes.c_uint64),
                 ("rebuilds", ctypes.c_uint32), ("path_levels", ctypes.c_uint32), ("paths", ctypes.c_uint32),
-                ("incremental_iterations", ctypes.c_uint32)]
+                ("incremental_iterations", ctypes.c_uint32),
+                ("flood_on_device", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -74,12 +74,17 @@ struct ReplayHeap {
 
 void fl_flood_rank(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const double* dist,
                    const uint32_t* outlets, uint32_t n_outlets, uint32_t* rank) {
+    fl_flood_rank_prefix(n, row_ptr, col, dist, outlets, n_outlets, rank, 0xFFFFFFFFu);
+}
+
+uint32_t fl_flood_rank_prefix(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, const double* dist,
+                              const uint32_t* outlets, uint32_t n_outlets, uint32_t* rank, uint32_t stop_after) {
     for (uint32_t i = 0; i < n; ++i) rank[i] = FL_RANK_NONE;
     ReplayHeap heap;
     heap.h.reserve((size_t)n + 16);
     for (uint32_t k = 0; k < n_outlets; ++k) heap.push(0.0, outlets[k]);
     uint32_t seq = 0;
-    while (!heap.h.empty()) {
+    while (!heap.h.empty() && seq < stop_after) {
         Entry e = heap.pop();
         uint32_t i = e.node;
         if (rank[i] != FL_RANK_NONE) continue;  // visited
@@ -91,4 +96,5 @@ void fl_flood_rank(uint32_t n, const uint32_t* row_ptr, const uint32_t* col, con
         }
         rank[i] = seq++;
     }
+    return seq;
 }

@@ -1,0 +1,269 @@
+// fl_floodgpu.cuh -- the flood order of lake removal, computed on the device.
+//
+// remove_lakes_from_stream_tree (reference src/lem/stream_tree.rs:175-243) pops sites from a binary heap keyed on
+// edge length, starting from all outlets with key 0.0.  With lazy deletion that is Prim's algorithm on the site
+// graph with the outlets contracted into one source S, so -- when all edge lengths are distinct and positive -- the
+// pop order T of the other sites is a function of the MINIMUM SPANNING TREE only:
+//
+//   Root the MST at S; let w(v) be the length of v's parent edge.  Prim leaves the component "everything reachable
+//   over edges lighter than w(v)" only through its lightest outgoing edge, hence (Kruskal reconstruction tree) for an
+//   MST edge e = (a -> b): all of A_e (the sites reachable from a over lighter edges) is popped before any of B_e
+//   (the same from b), and B_e lies inside b's subtree.  Let nga(v) be the nearest ancestor of v whose parent edge is
+//   heavier than w(v) (S if none).  Then
+//       B_e(v)   = the subtree of v in the forest of nga pointers,
+//       |A_e(v)| = |{nga(v)}| + sum of |B| over the nga-siblings of v with a lighter parent edge
+//                  (|{S}| = number of outlets),
+//       T(v)     = |A_e(v)| + T(nga(v)),   T(S) = 0.
+//   Everything is integer work: Boruvka rounds (64-bit atomicMin on the length bits), a frontier walk that roots the
+//   tree, pointer walks for nga, a counting sweep for |B|, two radix sorts + scans for the sibling prefix, and
+//   pointer jumping for the final sums.
+//
+// The outlets' own ranks depend on the heap's behaviour at equal keys (all 0.0); the host replays just that prefix
+// (fl_flood_rank_prefix).  Graphs with equal or non-positive edge lengths fall back to the full host replay
+// (fl_flood.cpp), which reproduces Rust's BinaryHeap at ties.
+#pragma once
+#include "fl_kernels.cuh"
+
+#define FLG_KEY_NONE 0xFFFFFFFFFFFFFFFFull
+
+struct FlFloodG {
+    uint32_t n;    // sites; index n = the contracted source S
+    uint32_t src;  // label of the source component (an outlet)
+    const uint32_t* row_ptr;
+    const uint32_t* col;
+    const double* dist;
+    const uint8_t* rev;
+    const uint8_t* is_outlet;
+    uint32_t* comp;               // n
+    uint32_t* link;               // n
+    unsigned long long* best;     // n
+    uint32_t* pick;               // n: slot of the lightest outgoing edge of a component
+    uint8_t* mst;                 // nnz: slot belongs to the spanning tree
+    uint32_t* par;                // n+1: parent in the rooted tree (n = S), FL_NONE = not reached
+    unsigned long long* wbits;    // n+1: bits of the parent edge length
+    uint32_t* nga;                // n+1
+    uint32_t* cnt;                // n+1: nga children still to report
+    uint32_t* size;               // n+1: |B|
+    uint32_t* flags;              // [0] any component hooked, [1] next frontier size, [2] work left, [3] bad edge length
+};
+
+__device__ __forceinline__ unsigned long long flg_bits(double d) { return (unsigned long long)__double_as_longlong(d); }
+
+// undirected edge lengths (each edge once, from its lower endpoint) as sortable keys; flags[3] on a non-positive or
+// non-finite length.  Slots that are not the lower endpoint get FLG_KEY_NONE (sorted last).
+__global__ void __launch_bounds__(256) k_flg_edge_keys(FlFloodG g, unsigned long long* keys) {
+    const uint32_t i = FL_TID;
+    if (i >= g.n) return;
+    for (uint32_t s = g.row_ptr[i]; s < g.row_ptr[i + 1]; ++s) {
+        const double d = g.dist[s];
+        if (!(d > 0.0) || !(d < 1.7976931348623157e308)) g.flags[3] = 1u;
+        keys[s] = (g.col[s] > i) ? flg_bits(d) : FLG_KEY_NONE;
+    }
+}
+__global__ void __launch_bounds__(256) k_flg_dup_check(uint32_t m, const unsigned long long* __restrict__ sorted,
+                                                        uint32_t* flags) {
+    const uint32_t i = FL_TID;
+    if (i + 1u >= m) return;
+    const unsigned long long a = sorted[i];
+    if (a != FLG_KEY_NONE && a == sorted[i + 1u]) flags[3] = 1u;
+}
+
+__global__ void __launch_bounds__(256) k_flg_init(FlFloodG g) {
+    const uint32_t v = FL_TID;
+    if (v > g.n) return;
+    g.par[v] = FL_NONE;
+    g.nga[v] = FL_NONE;
+    g.cnt[v] = 0u;
+    g.size[v] = 1u;
+    g.wbits[v] = 0ull;
+    if (v == g.n) return;
+    const uint32_t c = g.is_outlet[v] ? g.src : v;
+    g.comp[v] = c;
+    g.link[v] = c;
+    g.best[v] = FLG_KEY_NONE;
+}
+
+// Boruvka round, step 1: lightest edge leaving each component
+__global__ void __launch_bounds__(256) k_flg_min(FlFloodG g) {
+    const uint32_t v = FL_TID;
+    if (v >= g.n) return;
+    const uint32_t cv = g.comp[v];
+    unsigned long long m = FLG_KEY_NONE;
+    for (uint32_t s = g.row_ptr[v]; s < g.row_ptr[v + 1]; ++s) {
+        if (g.comp[g.col[s]] == cv) continue;
+        const unsigned long long k = flg_bits(g.dist[s]);
+        if (k < m) m = k;
+    }
+    if (m != FLG_KEY_NONE) atomicMin(&g.best[cv], m);
+}
+// step 2: the slot that carries it (lengths are distinct: exactly one slot inside the component)
+__global__ void __launch_bounds__(256) k_flg_pick(FlFloodG g) {
+    const uint32_t v = FL_TID;
+    if (v >= g.n) return;
+    const uint32_t cv = g.comp[v];
+    const unsigned long long b = g.best[cv];
+    if (b == FLG_KEY_NONE) return;
+    for (uint32_t s = g.row_ptr[v]; s < g.row_ptr[v + 1]; ++s)
+        if (flg_bits(g.dist[s]) == b && g.comp[g.col[s]] != cv) { g.pick[cv] = s; return; }
+}
+// step 3: hook each component onto the one its edge leads to; of two components that chose the same edge the
+// smaller label stays a root.  The chosen edges join the spanning tree (both directions).
+__global__ void __launch_bounds__(256) k_flg_hook(FlFloodG g) {
+    const uint32_t r = FL_TID;
+    if (r >= g.n) return;
+    if (g.comp[r] != r) return;  // not a component label
+    const unsigned long long b = g.best[r];
+    if (b == FLG_KEY_NONE) return;
+    const uint32_t s = g.pick[r];
+    const uint32_t u = g.col[s];
+    const uint32_t cu = g.comp[u];
+    // owner of slot s: the site v with row_ptr[v] <= s < row_ptr[v+1]; reverse slot through rev
+    g.mst[s] = 1u;
+    g.mst[g.row_ptr[u] + g.rev[s]] = 1u;
+    const bool mutual = g.best[cu] == b;
+    if (!mutual || r > cu) g.link[r] = cu;
+    g.flags[0] = 1u;
+}
+// step 4: new labels = roots of the hook forest; reset for the next round
+__global__ void __launch_bounds__(256) k_flg_relabel(FlFloodG g) {
+    const uint32_t v = FL_TID;
+    if (v >= g.n) return;
+    uint32_t r = g.comp[v];
+    for (;;) {
+        const uint32_t up = g.link[r];
+        if (up == r) break;
+        r = up;
+    }
+    g.comp[v] = r;
+}
+__global__ void __launch_bounds__(256) k_flg_reset(FlFloodG g) {
+    const uint32_t v = FL_TID;
+    if (v >= g.n) return;
+    g.best[v] = FLG_KEY_NONE;
+    g.link[v] = g.comp[v];  // every site now points at its (root) label; labels point at themselves
+}
+
+// rooting: outlets form level 0 (they ARE the source); one launch per tree level, no host round trip in between:
+// level L reads its frontier size from cnt3[L % 3], appends to cnt3[(L + 1) % 3] and clears cnt3[(L + 2) % 3].
+__global__ void __launch_bounds__(256) k_flg_root_init(FlFloodG g, uint32_t* frontier, uint32_t* cnt3) {
+    const uint32_t v = FL_TID;
+    if (v >= g.n) return;
+    if (!g.is_outlet[v]) return;
+    g.par[v] = g.n;
+    frontier[atomicAdd(&cnt3[0], 1u)] = v;
+}
+__global__ void __launch_bounds__(256) k_flg_root_level(FlFloodG g, const uint32_t* __restrict__ frontier,
+                                                         uint32_t* next, uint32_t* cnt3, uint32_t level) {
+    const uint32_t count = cnt3[level % 3u];
+    uint32_t* const next_count = &cnt3[(level + 1u) % 3u];
+    if (FL_TID == 0u) cnt3[(level + 2u) % 3u] = 0u;
+    for (uint32_t t = FL_TID; t < count; t += gridDim.x * blockDim.x) {
+        const uint32_t v = frontier[t];
+        const uint32_t pv = g.is_outlet[v] ? g.n : v;  // children of an outlet hang under S
+        for (uint32_t s = g.row_ptr[v]; s < g.row_ptr[v + 1]; ++s) {
+            if (!g.mst[s]) continue;
+            const uint32_t u = g.col[s];
+            if (g.par[u] != FL_NONE) continue;  // its own parent (or an outlet)
+            g.par[u] = pv;
+            g.wbits[u] = flg_bits(g.dist[s]);
+            g.nga[u] = pv;  // first candidate
+            next[atomicAdd(next_count, 1u)] = u;
+        }
+    }
+}
+
+// nearest ancestor with a heavier parent edge.  Invariant: every ancestor strictly between v and nga[v] has a parent
+// edge lighter than w(v); any value another thread has stored for an ancestor satisfies the same for that
+// ancestor, so reading it mid-way is safe.
+__global__ void __launch_bounds__(256) k_flg_nga(FlFloodG g, uint32_t max_hops) {
+    const uint32_t v = FL_TID;
+    if (v >= g.n) return;
+    if (g.is_outlet[v] || g.par[v] == FL_NONE) return;
+    const unsigned long long wv = g.wbits[v];
+    volatile uint32_t* nga = g.nga;
+    uint32_t c = nga[v];
+    uint32_t hops = 0;
+    while (c != g.n && g.wbits[c] < wv) {
+        if (hops++ == max_hops) { g.flags[2] = 1u; break; }
+        c = nga[c];
+    }
+    nga[v] = c;
+}
+
+// |B|: children counts, then a counting sweep from the leaves of the nga forest (integer sums: order-free)
+__global__ void __launch_bounds__(256) k_flg_count_children(FlFloodG g) {
+    const uint32_t v = FL_TID;
+    if (v >= g.n) return;
+    if (g.is_outlet[v] || g.par[v] == FL_NONE) return;
+    atomicAdd(&g.cnt[g.nga[v]], 1u);
+}
+// sites with children get a count biased by one, so that "no children" (0) stays distinguishable from "all children
+// have reported" (1) while the sweep runs
+__global__ void __launch_bounds__(256) k_flg_bias_counts(FlFloodG g) {
+    const uint32_t v = FL_TID;
+    if (v > g.n) return;
+    if (g.cnt[v] != 0u) g.cnt[v] += 1u;
+}
+__global__ void __launch_bounds__(256) k_flg_sizes(FlFloodG g) {
+    uint32_t v = FL_TID;
+    if (v >= g.n) return;
+    if (g.is_outlet[v] || g.par[v] == FL_NONE) return;
+    if (g.cnt[v] != 0u) return;  // not a leaf of the nga forest
+    uint32_t sz = 1u;
+    for (;;) {
+        const uint32_t p = g.nga[v];
+        if (p == g.n) return;
+        atomicAdd(&g.size[p], sz);
+        __threadfence();
+        if (atomicSub(&g.cnt[p], 1u) != 2u) return;  // somebody else arrives last (counts are biased by one)
+        sz = atomicAdd(&g.size[p], 0u);
+        v = p;
+    }
+}
+
+// sibling prefix: sort by (nga parent, parent edge length); sizes in that order; group starts
+__global__ void __launch_bounds__(256) k_flg_sort_keys(FlFloodG g, unsigned long long* wkey, uint32_t* ids) {
+    const uint32_t v = FL_TID;
+    if (v >= g.n) return;
+    ids[v] = v;
+    wkey[v] = (g.is_outlet[v] || g.par[v] == FL_NONE) ? FLG_KEY_NONE : g.wbits[v];
+}
+__global__ void __launch_bounds__(256) k_flg_parent_keys(FlFloodG g, const uint32_t* __restrict__ ids,
+                                                          unsigned long long* pkey) {
+    const uint32_t i = FL_TID;
+    if (i >= g.n) return;
+    const uint32_t v = ids[i];
+    pkey[i] = (g.is_outlet[v] || g.par[v] == FL_NONE) ? 0xFFFFFFFFull : (unsigned long long)g.nga[v];
+}
+__global__ void __launch_bounds__(256) k_flg_group(FlFloodG g, const unsigned long long* __restrict__ pkey_sorted,
+                                                    const uint32_t* __restrict__ ids_sorted,
+                                                    unsigned long long* sz_sorted, uint32_t* gstart) {
+    const uint32_t i = FL_TID;
+    if (i >= g.n) return;
+    sz_sorted[i] = (pkey_sorted[i] == 0xFFFFFFFFull) ? 0ull : (unsigned long long)g.size[ids_sorted[i]];
+    gstart[i] = (i == 0u || pkey_sorted[i] != pkey_sorted[i - 1u]) ? i : 0u;
+}
+// pd[v] = (nga[v], |A_e(v)|) for the final pointer jumping; sites outside the flood point at themselves
+__global__ void __launch_bounds__(256) k_flg_terms(FlFloodG g, uint32_t n_outlets,
+                                                    const unsigned long long* __restrict__ pkey_sorted,
+                                                    const uint32_t* __restrict__ ids_sorted,
+                                                    const unsigned long long* __restrict__ scan,
+                                                    const uint32_t* __restrict__ gstart_scan,
+                                                    unsigned long long* pd) {
+    const uint32_t i = FL_TID;
+    if (i > g.n) return;
+    if (i == g.n) { pd[g.n] = (unsigned long long)g.n; return; }
+    const uint32_t v = ids_sorted[i];
+    if (pkey_sorted[i] == 0xFFFFFFFFull) { pd[v] = (unsigned long long)v; return; }
+    const uint32_t p = (uint32_t)pkey_sorted[i];
+    const unsigned long long lighter = scan[i] - scan[gstart_scan[i]];
+    const unsigned long long a = (p == g.n ? (unsigned long long)n_outlets : 1ull) + lighter;
+    pd[v] = (unsigned long long)p | (a << 32);
+}
+__global__ void __launch_bounds__(256) k_flg_finish(FlFloodG g, const unsigned long long* __restrict__ pd,
+                                                     const uint32_t* __restrict__ outlet_rank, uint32_t* rank) {
+    const uint32_t v = FL_TID;
+    if (v >= g.n) return;
+    if (g.is_outlet[v]) { rank[v] = outlet_rank[v]; return; }
+    rank[v] = (g.par[v] == FL_NONE) ? FL_NONE : (uint32_t)(pd[v] >> 32);
+}

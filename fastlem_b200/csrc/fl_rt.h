@@ -46,6 +46,8 @@ typedef fl_event* cudaEvent_t;
 
 template <class T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
 template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> inline T atomicSub(T* p, T v) { T o = *p; *p = o - v; return o; }
+inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
 template <class T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
 template <class T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
@@ -122,6 +124,34 @@ inline cudaError_t fl_inclusive_max(void*, size_t& temp_bytes, const uint32_t* i
     return 0;
 }
 
+// 64-bit keys (flood order on the device, fl_floodgpu.cuh)
+inline cudaError_t fl_sort_pairs64(void*, size_t& temp_bytes, const unsigned long long* kin, unsigned long long* kout,
+                                   const uint32_t* vin, uint32_t* vout, uint32_t n, int end_bit, cudaStream_t,
+                                   bool query) {
+    if (query) { temp_bytes = 1; return 0; }
+    std::vector<uint32_t> idx(n);
+    for (uint32_t i = 0; i < n; ++i) idx[i] = i;
+    unsigned long long mask = end_bit >= 64 ? ~0ull : ((1ull << end_bit) - 1ull);
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return (kin[a] & mask) < (kin[b] & mask); });
+    for (uint32_t i = 0; i < n; ++i) { kout[i] = kin[idx[i]]; vout[i] = vin[idx[i]]; }
+    return 0;
+}
+inline cudaError_t fl_sort_keys64(void*, size_t& temp_bytes, const unsigned long long* kin, unsigned long long* kout,
+                                  uint32_t n, cudaStream_t, bool query) {
+    if (query) { temp_bytes = 1; return 0; }
+    std::vector<unsigned long long> v(kin, kin + n);
+    std::sort(v.begin(), v.end());
+    for (uint32_t i = 0; i < n; ++i) kout[i] = v[i];
+    return 0;
+}
+inline cudaError_t fl_exclusive_sum64(void*, size_t& temp_bytes, const unsigned long long* in, unsigned long long* out,
+                                      uint32_t n, cudaStream_t, bool query) {
+    if (query) { temp_bytes = 1; return 0; }
+    unsigned long long acc = 0;
+    for (uint32_t i = 0; i < n; ++i) { unsigned long long v = in[i]; out[i] = acc; acc += v; }
+    return 0;
+}
+
 #else
 // ------------------------------------------------------------------------------------------------
 #include <cuda_runtime.h>
@@ -179,5 +209,19 @@ struct FlMaxOp {
 inline cudaError_t fl_inclusive_max(void* temp, size_t& temp_bytes, const uint32_t* in, uint32_t* out, uint32_t n,
                                     cudaStream_t s, bool query) {
     return cub::DeviceScan::InclusiveScan(query ? nullptr : temp, temp_bytes, in, out, FlMaxOp(), (int)n, s);
+}
+inline cudaError_t fl_sort_pairs64(void* temp, size_t& temp_bytes, const unsigned long long* kin,
+                                   unsigned long long* kout, const uint32_t* vin, uint32_t* vout, uint32_t n,
+                                   int end_bit, cudaStream_t s, bool query) {
+    return cub::DeviceRadixSort::SortPairs(query ? nullptr : temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, end_bit,
+                                           s);
+}
+inline cudaError_t fl_sort_keys64(void* temp, size_t& temp_bytes, const unsigned long long* kin, unsigned long long* kout,
+                                  uint32_t n, cudaStream_t s, bool query) {
+    return cub::DeviceRadixSort::SortKeys(query ? nullptr : temp, temp_bytes, kin, kout, (int)n, 0, 64, s);
+}
+inline cudaError_t fl_exclusive_sum64(void* temp, size_t& temp_bytes, const unsigned long long* in,
+                                      unsigned long long* out, uint32_t n, cudaStream_t s, bool query) {
+    return cub::DeviceScan::ExclusiveSum(query ? nullptr : temp, temp_bytes, in, out, (int)n, s);
 }
 #endif

@@ -21,6 +21,7 @@
 #include "fl_flood.h"
 #include "fl_kernels.cuh"
 #include "fl_flow.cuh"
+#include "fl_floodgpu.cuh"
 #include "fl_paths.cuh"
 
 #ifdef FL_EMU
@@ -131,6 +132,7 @@ struct fastlem_ctx {
     uint32_t* d_chg_old = nullptr;
     bool k4_valid = false;      // the arrays above and A/pre/post/state/hgt describe the forest of L.recv
     bool k4_last_full = true;   // the previous K4 was a full pass (its counters are not zeroed)
+    int64_t opt_flood_device = 1;  // flood order on the device (fl_floodgpu.cuh) when the edge lengths allow it
     int64_t opt_incremental = 1;
     int64_t opt_incr_div = 16;  // incremental pass when re-routed sites * incr_div <= n
     unsigned long long* d_flow_stats = nullptr;
@@ -249,15 +251,179 @@ int run_labels(fastlem_ctx* c) {
     return jump_loop(c, c->d_pd);
 }
 
-// flood order (fl_flood.cpp): computed once per (graph, outlets) in the caller's numbering
+// device allocations that live for one call
+struct FlTmpAlloc {
+    std::vector<void*> p;
+    ~FlTmpAlloc() { for (void* q : p) fl_free(q); }
+    template <class T> cudaError_t get(T*& out, size_t count) {
+        void* v = nullptr;
+        cudaError_t e = fl_malloc(&v, (count ? count : 1) * sizeof(T));
+        if (e == cudaSuccess) p.push_back(v);
+        out = (T*)v;
+        return e;
+    }
+};
+
+// flood order on the device (fl_floodgpu.cuh).  *done = false: the graph has equal / non-positive edge lengths (or
+// rows too long for the reverse-slot table) and the exact host replay must be used instead.
+int device_flood_rank(fastlem_ctx* c, bool* done) {
+    *done = false;
+    const uint32_t n = c->n, nnz = c->nnz;
+    if (c->max_degree >= 255u || c->outlets.empty() || nnz == 0u) return FASTLEM_OK;
+    FlTmpAlloc tmp;
+    const size_t n1 = (size_t)n + 1;
+    FlFloodG g;
+    g.n = n; g.src = c->outlets[0];
+    g.row_ptr = c->orig.row_ptr; g.col = c->orig.col; g.dist = c->orig.dist; g.rev = c->orig.rev;
+    g.is_outlet = c->orig.is_outlet;
+    uint32_t *frontier_a = nullptr, *frontier_b = nullptr, *ids_a = nullptr, *ids_b = nullptr, *gstart = nullptr,
+             *gscan = nullptr, *outlet_rank = nullptr;
+    unsigned long long *keys_a = nullptr, *keys_b = nullptr, *k64a = nullptr, *k64b = nullptr, *szs = nullptr,
+                       *scan = nullptr, *pd = nullptr;
+    FL_CK(tmp.get(g.comp, n)); FL_CK(tmp.get(g.link, n)); FL_CK(tmp.get(g.best, n)); FL_CK(tmp.get(g.pick, n));
+    FL_CK(tmp.get(g.mst, nnz)); FL_CK(tmp.get(g.par, n1)); FL_CK(tmp.get(g.wbits, n1)); FL_CK(tmp.get(g.nga, n1));
+    FL_CK(tmp.get(g.cnt, n1)); FL_CK(tmp.get(g.size, n1)); FL_CK(tmp.get(g.flags, 8));
+    FL_CK(tmp.get(keys_a, nnz)); FL_CK(tmp.get(keys_b, nnz));
+    FL_CK(fl_memset(g.flags, 0, sizeof(uint32_t) * 8, c->stream));
+    size_t need = 0, t1 = 0;
+    FL_CK(fl_sort_keys64(nullptr, need, keys_a, keys_b, nnz, c->stream, true));
+    FL_CK(fl_sort_pairs64(nullptr, t1, k64a, k64b, ids_a, ids_b, n, 64, c->stream, true));
+    if (t1 > need) need = t1;
+    FL_CK(fl_exclusive_sum64(nullptr, t1, szs, scan, n, c->stream, true));
+    if (t1 > need) need = t1;
+    if (c->tmp_bytes > need) need = c->tmp_bytes;
+    unsigned char* cub_raw = nullptr;
+    FL_CK(tmp.get(cub_raw, need));
+    void* const cub_tmp = cub_raw;
+
+    // 1. all edge lengths positive, finite and pairwise distinct?
+    LAUNCH_N(k_flg_edge_keys, n, g, keys_a);
+    FL_CK(fl_sort_keys64(cub_tmp, need, keys_a, keys_b, nnz, c->stream, false));
+    LAUNCH_N(k_flg_dup_check, nnz, nnz, keys_b, g.flags);
+    uint32_t hf[8];
+    FL_CK(fl_d2h(hf, g.flags, sizeof(hf), c->stream));
+    FL_CK(fl_stream_sync(c->stream));
+    if (hf[3]) return FASTLEM_OK;  // ties: the host replay reproduces the heap's behaviour
+
+    // 2. the outlets' own ranks (equal keys 0.0: heap behaviour) -- exact replay of that prefix on the host
+    std::vector<uint32_t> orank(n);
+    uint32_t n_out = 0;  // distinct outlets = |S|
+    {
+        std::vector<uint8_t> seen(n, 0);
+        for (uint32_t o : c->outlets)
+            if (!seen[o]) { seen[o] = 1; ++n_out; }
+        fl_flood_rank_prefix(n, c->h_row_ptr, c->h_col, c->h_dist, c->outlets.data(), (uint32_t)c->outlets.size(),
+                             orank.data(), n_out);
+        FL_CK(tmp.get(outlet_rank, n));
+        FL_CK(fl_h2d(outlet_rank, orank.data(), sizeof(uint32_t) * n, c->stream));
+    }
+
+    // 3. Boruvka: minimum spanning forest of the graph with the outlets contracted
+    LAUNCH_N(k_flg_init, n + 1, g);
+    FL_CK(fl_memset(g.mst, 0, nnz, c->stream));
+    for (int round = 0; round < 64; ++round) {
+        FL_CK(fl_memset(g.flags, 0, sizeof(uint32_t), c->stream));
+        LAUNCH_N(k_flg_min, n, g);
+        LAUNCH_N(k_flg_pick, n, g);
+        LAUNCH_N(k_flg_hook, n, g);
+        LAUNCH_N(k_flg_relabel, n, g);
+        LAUNCH_N(k_flg_reset, n, g);
+        FL_CK(fl_d2h(hf, g.flags, sizeof(uint32_t), c->stream));
+        FL_CK(fl_stream_sync(c->stream));
+        if (!hf[0]) break;
+        if (round == 63) return fail(c, FASTLEM_E_STATE, "flood order: spanning forest did not converge");
+    }
+
+    // 4. root the tree at the source: one launch per level, frontier sizes stay on the device
+    FL_CK(tmp.get(frontier_a, n)); FL_CK(tmp.get(frontier_b, n));
+    uint32_t* cnt3 = g.flags + 4;
+    FL_CK(fl_memset(cnt3, 0, sizeof(uint32_t) * 3, c->stream));
+    LAUNCH_N(k_flg_root_init, n, g, frontier_a, cnt3);
+    {
+        const unsigned grid = (unsigned)c->sm_count * 2u;
+        uint32_t level = 0;
+        for (;;) {
+            for (int k = 0; k < 512; ++k, ++level) {
+                FL_LAUNCH(k_flg_root_level, grid, 256, c->stream, g, (level & 1u) ? frontier_b : frontier_a,
+                          (level & 1u) ? frontier_a : frontier_b, cnt3, level);
+            }
+            c->stats.kernel_launches += 512;
+            FL_CK(fl_d2h(hf, cnt3, sizeof(uint32_t) * 3, c->stream));
+            FL_CK(fl_stream_sync(c->stream));
+            if (hf[level % 3u] == 0u) break;  // the frontier the next launch would read is empty
+            if (level > n + 1024u) return fail(c, FASTLEM_E_STATE, "flood order: rooting did not terminate");
+        }
+    }
+
+    // 5. nearest heavier ancestor, sizes of the nga subtrees
+    for (int pass = 0; pass < 64; ++pass) {
+        FL_CK(fl_memset(g.flags + 2, 0, sizeof(uint32_t), c->stream));
+        LAUNCH_N(k_flg_nga, n, g, 1u << 16);
+        FL_CK(fl_d2h(hf, g.flags, sizeof(uint32_t) * 4, c->stream));
+        FL_CK(fl_stream_sync(c->stream));
+        if (!hf[2]) break;
+        if (pass == 63) return fail(c, FASTLEM_E_STATE, "flood order: ancestor search did not converge");
+    }
+    LAUNCH_N(k_flg_count_children, n, g);
+    LAUNCH_N(k_flg_bias_counts, n + 1, g);
+    LAUNCH_N(k_flg_sizes, n, g);
+
+    // 6. siblings by (nga parent, parent edge length); lighter siblings' sizes by a scan
+    FL_CK(tmp.get(k64a, n)); FL_CK(tmp.get(k64b, n)); FL_CK(tmp.get(ids_a, n)); FL_CK(tmp.get(ids_b, n));
+    FL_CK(tmp.get(szs, n)); FL_CK(tmp.get(scan, n)); FL_CK(tmp.get(gstart, n)); FL_CK(tmp.get(gscan, n));
+    FL_CK(tmp.get(pd, n1));
+    LAUNCH_N(k_flg_sort_keys, n, g, k64a, ids_a);
+    FL_CK(fl_sort_pairs64(cub_tmp, need, k64a, k64b, ids_a, ids_b, n, 64, c->stream, false));
+    LAUNCH_N(k_flg_parent_keys, n, g, ids_b, k64a);
+    FL_CK(fl_sort_pairs64(cub_tmp, need, k64a, k64b, ids_b, ids_a, n, 33, c->stream, false));  // stable
+    LAUNCH_N(k_flg_group, n, g, k64b, ids_a, szs, gstart);
+    FL_CK(fl_exclusive_sum64(cub_tmp, need, szs, scan, n, c->stream, false));
+    FL_CK(fl_inclusive_max(cub_tmp, need, gstart, gscan, n, c->stream, false));
+    LAUNCH_N(k_flg_terms, n + 1, g, n_out, k64b, ids_a, scan, gscan, pd);
+
+    // 7. T(v) = sum of the terms along the nga pointers
+    for (int batch = 0; batch < 24; ++batch) {
+        LAUNCH_N(k_jump, n + 1, n + 1, pd, c->d_flags);
+        LAUNCH_N(k_jump, n + 1, n + 1, pd, c->d_flags);
+        FL_CK(fl_memset(c->d_flags + FL_FLAG_JUMP, 0, sizeof(uint32_t), c->stream));
+        LAUNCH_N(k_jump, n + 1, n + 1, pd, c->d_flags);
+        FL_RC(read_flags(c));
+        if (!c->h_flags[FL_FLAG_JUMP]) break;
+        if (batch == 23) return fail(c, FASTLEM_E_STATE, "flood order: final sums did not converge");
+    }
+    LAUNCH_N(k_flg_finish, n, g, pd, outlet_rank, c->orig.rank);
+#ifdef FL_EMU
+    if (const char* path = std::getenv("FL_FLOOD_DUMP")) {  // host emulation only: intermediate arrays for debugging
+        if (FILE* fp = std::fopen(path, "wb")) {
+            std::fwrite(g.par, 4, n1, fp); std::fwrite(g.wbits, 8, n1, fp); std::fwrite(g.nga, 4, n1, fp);
+            std::fwrite(g.size, 4, n1, fp); std::fwrite(pd, 8, n1, fp);
+            std::fclose(fp);
+        }
+    }
+#endif
+    FL_CK(fl_stream_sync(c->stream));
+    FL_CK(fl_last_error());
+    *done = true;
+    return FASTLEM_OK;
+}
+
+// flood order: computed once per (graph, outlets) in the caller's numbering -- on the device when the edge lengths
+// are distinct (fl_floodgpu.cuh), else by the exact host replay (fl_flood.cpp)
 int ensure_rank(fastlem_ctx* c) {
     if (c->rank_ready) return FASTLEM_OK;
     double t0 = wall_ms();
     const uint32_t n = c->n;
-    std::vector<uint32_t> rank(n);
-    fl_flood_rank(n, c->h_row_ptr, c->h_col, c->h_dist, c->outlets.data(), (uint32_t)c->outlets.size(), rank.data());
-    FL_CK(fl_h2d(c->orig.rank, rank.data(), sizeof(uint32_t) * n, c->stream));
-    FL_CK(fl_stream_sync(c->stream));
+    bool done = false;
+    const uint64_t launches_before = c->stats.kernel_launches;
+    if (c->opt_flood_device) FL_RC(device_flood_rank(c, &done));
+    c->stats.flood_on_device = done ? 1u : 0u;
+    if (!done) {
+        c->stats.kernel_launches = launches_before;
+        std::vector<uint32_t> rank(n);
+        fl_flood_rank(n, c->h_row_ptr, c->h_col, c->h_dist, c->outlets.data(), (uint32_t)c->outlets.size(), rank.data());
+        FL_CK(fl_h2d(c->orig.rank, rank.data(), sizeof(uint32_t) * n, c->stream));
+        FL_CK(fl_stream_sync(c->stream));
+    }
     if (c->layout_valid) {  // into the current numbering (otherwise reset_layout does it at the next run)
         Layout& L = L_(c);
         LAUNCH_N(k_gather_u32, n, n, L.orig_of, c->orig.rank, L.rank);
@@ -813,6 +979,9 @@ int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
     } else if (s == "park_after") {
         if (value != 0 && value < 4) return fail(c, FASTLEM_E_INVALID, "option park_after: 0 (never) or >= 4");
         c->opt_park_after = value;
+    } else if (s == "flood_device") {
+        c->opt_flood_device = value != 0;
+        c->rank_ready = false;
     } else if (s == "incremental") {
         c->opt_incremental = value != 0;
     } else if (s == "incr_div") {
@@ -997,9 +1166,11 @@ int fastlem_run(fastlem_ctx* c, uint32_t max_iteration, uint32_t* iterations_don
     FL_CK(fl_set_device(c->device));
     // reset per-run stats, keep the one-off ones
     double up = c->stats.ms_upload, fr = c->stats.ms_flood_rank;
+    const uint32_t fd = c->stats.flood_on_device;
     c->stats = fastlem_stats{};
     c->stats.ms_upload = up;
     c->stats.ms_flood_rank = fr;
+    c->stats.flood_on_device = fd;
     FL_CK(fl_event_record(c->ev_run[0], c->stream));
     FL_RC(reset_layout(c));
     c->need_rebuild = true;

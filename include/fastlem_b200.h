@@ -113,6 +113,8 @@ typedef struct fastlem_stats {
     uint32_t path_levels; /* nesting depth of the path decomposition = rounds per sweep */
     uint32_t paths;       /* number of paths */
     uint32_t incremental_iterations; /* iterations whose drainage areas were updated incrementally */
+    uint32_t flood_on_device; /* 1: the flood order was computed on the device, 0: exact host replay (ties) */
+    uint32_t reserved;
 } fastlem_stats;
 int fastlem_get_stats(const fastlem_ctx* ctx, fastlem_stats* out);
 

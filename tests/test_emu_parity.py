@@ -102,12 +102,27 @@ def test_max_iteration(oracle, emu_lib, k):
             assert np.array_equal(e, initial)  # generator.rs:140: zero bodies -> the noise comes back
 
 
-def test_flood_rank_matches_oracle(oracle, emu_lib):
-    for name in ("uniform", "lattice", "lattice_regular", "advanced", "disconnected"):
-        m, p, outlets, initial, _ = scenario(name)
-        with _ctx(emu_lib) as ctx:
-            helpers.load_ctx(ctx, m, p, outlets, initial)
-            assert np.array_equal(ctx.fetch("flood_rank"), oracle.flood_order(m, outlets)), name
+@pytest.mark.parametrize("device", [0, 1])
+@pytest.mark.parametrize("name", SMALL)
+def test_flood_rank_matches_oracle(oracle, emu_lib, name, device):
+    """Pop order of the lake flood (stream_tree.rs:175-243): exact host replay (flood_device=0) and the spanning-tree
+    formulation on the device (fl_floodgpu.cuh), which must fall back to the replay when edge lengths tie."""
+    m, p, outlets, initial, _ = scenario(name)
+    with _ctx(emu_lib, flood_device=device) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert np.array_equal(ctx.fetch("flood_rank"), oracle.flood_order(m, outlets)), name
+        on_device = ctx.stats()["flood_on_device"]
+        assert on_device == (1 if device and name not in ("lattice_regular",) else 0)
+
+
+@pytest.mark.parametrize("name,n", [("uniform", 20000), ("advanced", 30000), ("interior_outlets", 8000),
+                                    ("single_outlet", 6000)])
+def test_flood_rank_device_larger(oracle, emu_lib, name, n):
+    m, p, outlets, initial, _ = scenario(name, n)
+    with _ctx(emu_lib) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert np.array_equal(ctx.fetch("flood_rank"), oracle.flood_order(m, outlets))
+        assert ctx.stats()["flood_on_device"] == 1
 
 
 def test_rerun_restarts_from_initial(emu_lib):

@@ -144,6 +144,23 @@ def test_c7_nonuniform_uplift_lakes_every_iteration(oracle, gpu_ctx_factory):
         assert ctx.stats()["lake_iterations"] > 1
 
 
+@pytest.mark.parametrize("name,n", [("uniform", 3000), ("advanced", 5000), ("lattice", None), ("lattice_regular", None),
+                                    ("disconnected", None), ("interior_outlets", 8000), ("single_outlet", 6000),
+                                    ("uniform", 200000), ("advanced", 200000), ("uniform", 1000000)])
+def test_flood_order_on_device(oracle, gpu_ctx_factory, name, n):
+    """fl_floodgpu.cuh: pop order of the lake flood from the minimum spanning tree, against the oracle's heap replay."""
+    m, p, outlets, initial, _ = scenario(name, n) if n else scenario(name)
+    ref = oracle.flood_order(m, outlets)
+    with gpu_ctx_factory() as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert np.array_equal(ctx.fetch("flood_rank"), ref)
+        assert ctx.stats()["flood_on_device"] == (0 if name == "lattice_regular" else 1)
+    with gpu_ctx_factory(flood_device=0) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert np.array_equal(ctx.fetch("flood_rank"), ref)
+        assert ctx.stats()["flood_on_device"] == 0
+
+
 def test_c2_one_million_sites(oracle, gpu_ctx_factory):
     """BASELINE config C2 (1M random sites, uniform erodibility, hull outlets): the oracle is too slow to
     converge here (~10 min), so compare the first iterations against it, then check size-independent
