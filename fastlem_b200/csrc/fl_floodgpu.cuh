@@ -39,6 +39,9 @@ struct FlFloodG {
     unsigned long long* best;     // n
     uint32_t* pick;               // n: slot of the lightest outgoing edge of a component
     uint8_t* mst;                 // nnz: slot belongs to the spanning tree
+    uint32_t* tptr;               // n+1: compact adjacency of the spanning tree (built after the Boruvka rounds)
+    uint32_t* tcol;               // 2(n-1)
+    unsigned long long* twb;      // 2(n-1): edge length bits
     uint32_t* par;                // n+1: parent in the rooted tree (n = S), FL_NONE = not reached
     unsigned long long* wbits;    // n+1: bits of the parent edge length
     uint32_t* nga;                // n+1
@@ -143,8 +146,7 @@ __global__ void __launch_bounds__(256) k_flg_reset(FlFloodG g) {
     g.link[v] = g.comp[v];  // every site now points at its (root) label; labels point at themselves
 }
 
-// rooting: outlets form level 0 (they ARE the source); one launch per tree level, no host round trip in between:
-// level L reads its frontier size from cnt3[L % 3], appends to cnt3[(L + 1) % 3] and clears cnt3[(L + 2) % 3].
+// rooting: outlets form level 0 (they ARE the source)
 __global__ void __launch_bounds__(256) k_flg_root_init(FlFloodG g, uint32_t* frontier, uint32_t* cnt3) {
     const uint32_t v = FL_TID;
     if (v >= g.n) return;
@@ -152,24 +154,78 @@ __global__ void __launch_bounds__(256) k_flg_root_init(FlFloodG g, uint32_t* fro
     g.par[v] = g.n;
     frontier[atomicAdd(&cnt3[0], 1u)] = v;
 }
-__global__ void __launch_bounds__(256) k_flg_root_level(FlFloodG g, const uint32_t* __restrict__ frontier,
-                                                         uint32_t* next, uint32_t* cnt3, uint32_t level) {
-    const uint32_t count = cnt3[level % 3u];
-    uint32_t* const next_count = &cnt3[(level + 1u) % 3u];
-    if (FL_TID == 0u) cnt3[(level + 2u) % 3u] = 0u;
-    for (uint32_t t = FL_TID; t < count; t += gridDim.x * blockDim.x) {
-        const uint32_t v = frontier[t];
-        const uint32_t pv = g.is_outlet[v] ? g.n : v;  // children of an outlet hang under S
-        for (uint32_t s = g.row_ptr[v]; s < g.row_ptr[v + 1]; ++s) {
-            if (!g.mst[s]) continue;
-            const uint32_t u = g.col[s];
-            if (g.par[u] != FL_NONE) continue;  // its own parent (or an outlet)
-            g.par[u] = pv;
-            g.wbits[u] = flg_bits(g.dist[s]);
-            g.nga[u] = pv;  // first candidate
-            next[atomicAdd(next_count, 1u)] = u;
+// compact adjacency of the spanning tree, so that the level walk below touches tree edges only
+__global__ void __launch_bounds__(256) k_flg_tree_degree(FlFloodG g, uint32_t* deg) {
+    const uint32_t v = FL_TID;
+    if (v > g.n) return;
+    uint32_t d = 0;
+    if (v < g.n)
+        for (uint32_t s = g.row_ptr[v]; s < g.row_ptr[v + 1]; ++s) d += g.mst[s] ? 1u : 0u;
+    deg[v] = d;
+}
+__global__ void __launch_bounds__(256) k_flg_tree_fill(FlFloodG g) {
+    const uint32_t v = FL_TID;
+    if (v >= g.n) return;
+    uint32_t k = g.tptr[v];
+    for (uint32_t s = g.row_ptr[v]; s < g.row_ptr[v + 1]; ++s)
+        if (g.mst[s]) { g.tcol[k] = g.col[s]; g.twb[k] = flg_bits(g.dist[s]); ++k; }
+}
+
+// one frontier vertex: adopt the tree neighbours that have no parent yet
+__device__ __forceinline__ void flg_expand(const FlFloodG& g, uint32_t v, uint32_t* next, uint32_t* next_count) {
+    const uint32_t pv = g.is_outlet[v] ? g.n : v;  // children of an outlet hang under S
+    const uint32_t k0 = g.tptr[v], k1 = g.tptr[v + 1];
+    for (uint32_t kb = k0; kb < k1; kb += 4u) {  // four neighbours' loads in flight together
+        uint32_t u[4], pu[4];
+        unsigned long long w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            u[j] = FL_NONE; w[j] = 0ull;
+            if (kb + (uint32_t)j < k1) { u[j] = g.tcol[kb + j]; w[j] = g.twb[kb + j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pu[j] = (u[j] != FL_NONE) ? g.par[u[j]] : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (u[j] == FL_NONE || pu[j] != FL_NONE) continue;  // its own parent (or an outlet)
+            g.par[u[j]] = pv;
+            g.wbits[u[j]] = w[j];
+            g.nga[u[j]] = pv;  // first candidate
+            next[atomicAdd(next_count, 1u)] = u[j];
         }
     }
+}
+
+// The spanning tree is thousands of levels deep with ~100 sites per level: one CTA walks ALL levels, a block barrier
+// between them, instead of one launch per level.
+__global__ void __launch_bounds__(1024) k_flg_root_walk(FlFloodG g, uint32_t* fa, uint32_t* fb, uint32_t* cnt3) {
+#ifdef FL_EMU
+    if (FL_TID != 0u) return;
+    uint32_t count = cnt3[0];
+    uint32_t* cur = fa;
+    uint32_t* nxt = fb;
+    while (count) {
+        uint32_t produced = 0;
+        for (uint32_t t = 0; t < count; ++t) flg_expand(g, cur[t], nxt, &produced);
+        uint32_t* tmp = cur; cur = nxt; nxt = tmp;
+        count = produced;
+    }
+#else
+    __shared__ uint32_t s_count, s_next;
+    uint32_t* cur = fa;
+    uint32_t* nxt = fb;
+    if (threadIdx.x == 0) { s_count = cnt3[0]; s_next = 0u; }
+    __syncthreads();
+    for (;;) {
+        const uint32_t count = s_count;
+        if (count == 0u) break;
+        for (uint32_t t = threadIdx.x; t < count; t += blockDim.x) flg_expand(g, cur[t], nxt, &s_next);
+        __syncthreads();
+        if (threadIdx.x == 0) { s_count = s_next; s_next = 0u; }
+        uint32_t* tmp = cur; cur = nxt; nxt = tmp;
+        __syncthreads();
+    }
+#endif
 }
 
 // nearest ancestor with a heavier parent edge.  Invariant: every ancestor strictly between v and nga[v] has a parent

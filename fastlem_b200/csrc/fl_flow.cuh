@@ -874,14 +874,21 @@ __device__ __forceinline__ void fl_elev_window(const FlElev& e, const FlEWin& w,
                                                uint32_t root, double& rt_prev, double& z_prev, double e_out,
                                                double rt_out, bool& changed, FlChainSmem& sm) {
     __syncwarp();
-    sm.in[lane] = w.t;
+    sm.in[lane] = ((uint32_t)lane < nproc) ? w.t : 0.0;  // padding: 0.0 + (r + 0.0) == r (r >= +0.0)
     __syncwarp();
     {
+        // 8 terms fetched together, then the dependent additions (identically in every lane)
         double r = rt_prev;
-#pragma unroll 4
-        for (uint32_t k = 0; k < nproc; ++k) {  // code kept small on purpose (i-cache)
-            r = 0.0 + (r + sm.in[k]);
-            sm.out[k] = r;
+        for (uint32_t k0 = 0; k0 < nproc; k0 += 8u) {
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = sm.in[k0 + (uint32_t)j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { r = 0.0 + (r + v[j]); v[j] = r; }
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sm.out[k0 + (uint32_t)j] = v[j];
+            }
         }
         rt_prev = r;
     }
@@ -1098,6 +1105,123 @@ __global__ void __launch_bounds__(128) k_elev_flow_warps(uint32_t begin, uint32_
     if (h + 1u < e.n && e.recv[h + 1u] == h)
         changed |= fl_elev_warp(e, h + 1u, root, rt_prev, z_prev, e_out, rt_out, sm);
     if (changed && lane == 0) e.flags[FL_FLAG_CHANGED] = 1u;
+#endif
+}
+
+// The sparse levels at the top of the forest (few, long segments) in ONE launch: warps take the segments in level
+// order through a ticket counter; a segment whose receiver lies on another segment waits until that segment's ticket is
+// marked done.  The receiver's segment is on an earlier level, so its ticket was handed out earlier to a warp that is
+// running: the wait always ends.  Saves a launch per level and the idle tail of every level.
+struct FlFused {
+    uint32_t count;            // segments in the fused prefix of the level order
+    const uint32_t* heads;     // level order
+    const uint32_t* seg_head;  // site -> head of its segment
+    const uint32_t* ticket_of; // head -> position in the level order (valid for the fused prefix)
+    uint32_t* done;            // per ticket
+    uint32_t* next_ticket;
+    const uint32_t* lvl_of;    // per ticket: the nesting height (value written to e.lvl)
+};
+
+__global__ void __launch_bounds__(256) k_fused_index(uint32_t count, const uint32_t* __restrict__ heads,
+                                                      const uint32_t* __restrict__ hgt, uint32_t* __restrict__ ticket_of,
+                                                      uint32_t* __restrict__ lvl_of, uint32_t* __restrict__ done) {
+    const uint32_t i = FL_TID;
+    if (i >= count) return;
+    const uint32_t h = heads[i];
+    ticket_of[h] = i;
+    lvl_of[i] = hgt[h];
+    done[i] = 0u;
+}
+
+__global__ void __launch_bounds__(128) k_elev_flow_fused(FlFused u, FlElev e) {
+#ifdef FL_EMU
+    // emulation: threads run one after the other in ticket order, so receivers are always finished
+    const uint32_t t = FL_TID;
+    if (t >= u.count) return;
+    const uint32_t h = u.heads[t];
+    const uint32_t p = e.recv[h];
+    const bool is_root = (p == h);
+    e.lvl_value = u.lvl_of[t];
+    uint32_t root;
+    double rt_prev, z_prev, e_out, rt_out;
+    if (is_root) { root = e.is_outlet[h] ? h : FL_NONE; rt_prev = 0.0; z_prev = e.elev[h]; e_out = e.elev[h]; rt_out = 0.0; }
+    else {
+        root = e.root_of[p]; rt_prev = e.rt[p]; z_prev = e.elev[p];
+        e_out = root != FL_NONE ? e.elev[root] : 0.0; rt_out = root != FL_NONE ? e.rt[root] : 0.0;
+    }
+    if (root == FL_NONE) {
+        for (uint32_t r = h;; ++r) { e.root_of[r] = FL_NONE; if (r + 1u >= e.n || e.recv[r + 1u] != r) break; }
+        return;
+    }
+    bool changed = false;
+    uint32_t q = h;
+    bool ended = fl_elev_batch<4>(e, q, h, is_root, root, rt_prev, z_prev, e_out, rt_out, changed);
+    while (!ended) ended = fl_elev_batch<4>(e, q, h, false, root, rt_prev, z_prev, e_out, rt_out, changed);
+    if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
+#else
+    __shared__ FlChainSmem chain_smem[4];
+    FlChainSmem& sm = chain_smem[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t i = 0u;
+        if (lane == 0) i = atomicAdd(u.next_ticket, 1u);
+        i = __shfl_sync(FL_FULL, i, 0);
+        if (i >= u.count) return;
+        const uint32_t h = u.heads[i];
+        const uint32_t p = e.recv[h];
+        const bool is_root = (p == h);
+        e.lvl_value = u.lvl_of[i];
+        if (!is_root) {  // wait for the receiver's segment
+            const uint32_t j = u.ticket_of[u.seg_head[p]];
+            if (lane == 0) {
+                uint32_t spins = 0u;
+                while (fl_ld_relaxed(&u.done[j]) == 0u) {
+                    __nanosleep(40);
+                    if (++spins > (1u << 24)) { atomicOr(&e.flags[FL_FLAG_BROKEN], 2u); break; }
+                }
+            }
+            __syncwarp();
+        }
+        uint32_t root;
+        double rt_prev, z_prev, e_out, rt_out;
+        if (is_root) { root = e.is_outlet[h] ? h : FL_NONE; rt_prev = 0.0; z_prev = e.elev[h]; e_out = e.elev[h]; rt_out = 0.0; }
+        else {  // written by another warp of this launch: read through L2
+            root = fl_ld_cg(&e.root_of[p]); rt_prev = fl_ld_cg(&e.rt[p]); z_prev = fl_ld_cg(&e.elev[p]);
+            e_out = root != FL_NONE ? fl_ld_cg(&e.elev[root]) : 0.0; rt_out = root != FL_NONE ? fl_ld_cg(&e.rt[root]) : 0.0;
+        }
+        bool changed = false;
+        if (root == FL_NONE) {
+            if (lane == 0)
+                for (uint32_t r = h;; ++r) { e.root_of[r] = FL_NONE; if (r + 1u >= e.n || e.recv[r + 1u] != r) break; }
+        } else {
+            // the head site, identically in every lane (the root's special cases live here); lane 0 stores
+            const double t = e.tcel[h];
+            const double eold = e.elev[h];
+            const double rti = 0.0 + (rt_prev + t);
+            if (is_root) rt_out = rti;
+            double z = e_out + e.uplift[h] * fmax(rti - rt_out, 0.0);
+            if (e.tan_slope) {
+                const double ms = e.tan_slope[h];
+                if (ms == ms) {
+                    const double d = e.drecv[h];
+                    const double slope = (z - z_prev) / d;
+                    if (slope > ms) z = z_prev + ms * d;
+                }
+            }
+            changed = (z != eold);
+            if (is_root) e_out = z;
+            __syncwarp();  // every lane has read elev[h] before lane 0 overwrites it
+            if (lane == 0) { e.elev[h] = z; e.rt[h] = rti; e.root_of[h] = root; e.lvl[h] = e.lvl_value; }
+            rt_prev = rti;
+            z_prev = z;
+            if (h + 1u < e.n && e.recv[h + 1u] == h)
+                changed |= fl_elev_warp(e, h + 1u, root, rt_prev, z_prev, e_out, rt_out, sm);
+            if (changed && lane == 0) e.flags[FL_FLAG_CHANGED] = 1u;
+        }
+        fl_fence_release();  // every lane publishes its own stores before the ticket is marked done
+        __syncwarp();
+        if (lane == 0) atomicExch(&u.done[i], 1u);
+    }
 #endif
 }
 

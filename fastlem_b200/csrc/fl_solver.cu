@@ -124,6 +124,10 @@ struct fastlem_ctx {
     uint32_t* d_sg_wait = nullptr;
     uint32_t* d_sg_done = nullptr;
     // incremental K4 (fl_flow.cuh): state kept between iterations + per-iteration work lists
+    uint32_t* d_ticket_of = nullptr;  // fused sparse levels of K5
+    uint32_t* d_fdone = nullptr;
+    uint32_t* d_flvl = nullptr;
+    int64_t opt_fuse_levels = 1;
     uint32_t* d_hsuf = nullptr;
     uint32_t* d_dirty_from = nullptr;
     uint32_t* d_rlist = nullptr;
@@ -145,6 +149,7 @@ struct fastlem_ctx {
     uint32_t segs_at_rebuild = 0, maxh_at_rebuild = 0;
     bool need_rebuild = true;
     int64_t opt_rebuild_every = 0;  // 0 = adaptive
+    int64_t opt_rebuild_growth = 4;  // adaptive: renumber when the segment count grew by this many percent
     // scratch in the caller's numbering (download, debug fetch, kept stages)
     double* d_out_f64 = nullptr;
     uint32_t* d_out_u32 = nullptr;
@@ -251,6 +256,20 @@ int run_labels(fastlem_ctx* c) {
     return jump_loop(c, c->d_pd);
 }
 
+// FASTLEM_TRACE=1: wall-clock phase times on stderr (debug aid)
+struct FlTrace {
+    bool on;
+    double t;
+    const char* what;
+    explicit FlTrace(const char* w) : on(std::getenv("FASTLEM_TRACE") != nullptr), t(wall_ms()), what(w) {}
+    void mark(const char* phase) {
+        if (!on) return;
+        const double now = wall_ms();
+        std::fprintf(stderr, "[fastlem trace] %s: %s %.3f ms\n", what, phase, now - t);
+        t = now;
+    }
+};
+
 // device allocations that live for one call
 struct FlTmpAlloc {
     std::vector<void*> p;
@@ -270,6 +289,7 @@ int device_flood_rank(fastlem_ctx* c, bool* done) {
     *done = false;
     const uint32_t n = c->n, nnz = c->nnz;
     if (c->max_degree >= 255u || c->outlets.empty() || nnz == 0u) return FASTLEM_OK;
+    FlTrace tr("flood");
     FlTmpAlloc tmp;
     const size_t n1 = (size_t)n + 1;
     FlFloodG g;
@@ -296,6 +316,7 @@ int device_flood_rank(fastlem_ctx* c, bool* done) {
     FL_CK(tmp.get(cub_raw, need));
     void* const cub_tmp = cub_raw;
 
+    tr.mark("alloc");
     // 1. all edge lengths positive, finite and pairwise distinct?
     LAUNCH_N(k_flg_edge_keys, n, g, keys_a);
     FL_CK(fl_sort_keys64(cub_tmp, need, keys_a, keys_b, nnz, c->stream, false));
@@ -305,6 +326,7 @@ int device_flood_rank(fastlem_ctx* c, bool* done) {
     FL_CK(fl_stream_sync(c->stream));
     if (hf[3]) return FASTLEM_OK;  // ties: the host replay reproduces the heap's behaviour
 
+    tr.mark("distinct check");
     // 2. the outlets' own ranks (equal keys 0.0: heap behaviour) -- exact replay of that prefix on the host
     std::vector<uint32_t> orank(n);
     uint32_t n_out = 0;  // distinct outlets = |S|
@@ -318,6 +340,7 @@ int device_flood_rank(fastlem_ctx* c, bool* done) {
         FL_CK(fl_h2d(outlet_rank, orank.data(), sizeof(uint32_t) * n, c->stream));
     }
 
+    tr.mark("outlet prefix (host)");
     // 3. Boruvka: minimum spanning forest of the graph with the outlets contracted
     LAUNCH_N(k_flg_init, n + 1, g);
     FL_CK(fl_memset(g.mst, 0, nnz, c->stream));
@@ -334,27 +357,20 @@ int device_flood_rank(fastlem_ctx* c, bool* done) {
         if (round == 63) return fail(c, FASTLEM_E_STATE, "flood order: spanning forest did not converge");
     }
 
-    // 4. root the tree at the source: one launch per level, frontier sizes stay on the device
-    FL_CK(tmp.get(frontier_a, n)); FL_CK(tmp.get(frontier_b, n));
+    tr.mark("boruvka");
+    // 4. root the tree at the source (one CTA walks all levels over a compact copy of the tree's adjacency)
+    FL_CK(tmp.get(frontier_a, n1)); FL_CK(tmp.get(frontier_b, n1));
+    FL_CK(tmp.get(g.tptr, n1)); FL_CK(tmp.get(g.tcol, 2 * (size_t)n)); FL_CK(tmp.get(g.twb, 2 * (size_t)n));
+    LAUNCH_N(k_flg_tree_degree, n + 1, g, frontier_b);
+    FL_CK(fl_exclusive_sum(cub_tmp, need, frontier_b, g.tptr, n + 1, c->stream, false));
+    LAUNCH_N(k_flg_tree_fill, n, g);
     uint32_t* cnt3 = g.flags + 4;
     FL_CK(fl_memset(cnt3, 0, sizeof(uint32_t) * 3, c->stream));
     LAUNCH_N(k_flg_root_init, n, g, frontier_a, cnt3);
-    {
-        const unsigned grid = (unsigned)c->sm_count * 2u;
-        uint32_t level = 0;
-        for (;;) {
-            for (int k = 0; k < 512; ++k, ++level) {
-                FL_LAUNCH(k_flg_root_level, grid, 256, c->stream, g, (level & 1u) ? frontier_b : frontier_a,
-                          (level & 1u) ? frontier_a : frontier_b, cnt3, level);
-            }
-            c->stats.kernel_launches += 512;
-            FL_CK(fl_d2h(hf, cnt3, sizeof(uint32_t) * 3, c->stream));
-            FL_CK(fl_stream_sync(c->stream));
-            if (hf[level % 3u] == 0u) break;  // the frontier the next launch would read is empty
-            if (level > n + 1024u) return fail(c, FASTLEM_E_STATE, "flood order: rooting did not terminate");
-        }
-    }
-
+    FL_LAUNCH(k_flg_root_walk, 1, 1024, c->stream, g, frontier_a, frontier_b, cnt3);
+    c->stats.kernel_launches++;
+    FL_CK(fl_stream_sync(c->stream));
+    tr.mark("rooting");
     // 5. nearest heavier ancestor, sizes of the nga subtrees
     for (int pass = 0; pass < 64; ++pass) {
         FL_CK(fl_memset(g.flags + 2, 0, sizeof(uint32_t), c->stream));
@@ -368,6 +384,8 @@ int device_flood_rank(fastlem_ctx* c, bool* done) {
     LAUNCH_N(k_flg_bias_counts, n + 1, g);
     LAUNCH_N(k_flg_sizes, n, g);
 
+    FL_CK(fl_stream_sync(c->stream));
+    tr.mark("nga + sizes");
     // 6. siblings by (nga parent, parent edge length); lighter siblings' sizes by a scan
     FL_CK(tmp.get(k64a, n)); FL_CK(tmp.get(k64b, n)); FL_CK(tmp.get(ids_a, n)); FL_CK(tmp.get(ids_b, n));
     FL_CK(tmp.get(szs, n)); FL_CK(tmp.get(scan, n)); FL_CK(tmp.get(gstart, n)); FL_CK(tmp.get(gscan, n));
@@ -403,6 +421,7 @@ int device_flood_rank(fastlem_ctx* c, bool* done) {
 #endif
     FL_CK(fl_stream_sync(c->stream));
     FL_CK(fl_last_error());
+    tr.mark("sort + scan + jump");
     *done = true;
     return FASTLEM_OK;
 }
@@ -797,6 +816,7 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     uint32_t maxh = c->h_flags[FL_FLAG_MAXDEPTH];
     if (incr && c->prev_maxh > maxh) maxh = c->prev_maxh;
     if (c->h_flags[FL_FLAG_BROKEN]) return fail(c, FASTLEM_E_STATE, "K4: a climb met an unpublished site (internal error)");
+    // (a wait of the fused K5 launch that ran out would show up here as well, one iteration late, and below)
     int bits = 1;
     while (bits < 32 && (1ull << bits) <= (unsigned long long)maxh + 1ull) ++bits;
     LAUNCH_N(k_flow_sort_keys, n, n, c->d_hgt, maxh, c->d_depth);
@@ -819,7 +839,8 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     c->prev_maxh = maxh;
     if (rebuilt) { c->segs_at_rebuild = n_heads; c->maxh_at_rebuild = maxh; }
     else if (c->opt_rebuild_every == 0 &&
-             ((unsigned long long)n_heads * 100ull > (unsigned long long)c->segs_at_rebuild * 104ull ||
+             ((unsigned long long)n_heads * 100ull >
+                  (unsigned long long)c->segs_at_rebuild * (100ull + (unsigned long long)c->opt_rebuild_growth) ||
               maxh > c->maxh_at_rebuild + c->maxh_at_rebuild / 2 + 2))
         c->need_rebuild = true;  // the numbering has degraded: renumber in the next iteration
     FL_RC(stage_mark(c, 5));  // end of the head ordering
@@ -831,7 +852,30 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     e.tan_slope = c->has_tan ? L.tan : nullptr; e.is_outlet = L.is_outlet; e.elev = L.elev; e.rt = c->d_rt;
     e.root_of = c->d_root_of; e.flags = c->d_flags; e.lvl = L.lvl; e.lvl_value = 0;
     uint32_t launched = 0;
-    for (uint32_t g = 0; g <= maxh; ++g) {
+    // the sparse levels at the top of the forest go out as ONE launch (ticket order = level order)
+    uint32_t g_first = 0;
+    if (c->opt_fuse_levels) {
+        uint32_t gf = 0;
+        while (gf <= maxh && c->h_offs[gf + 1] - c->h_offs[gf] <= FL_WARP_LEVEL_MAX) ++gf;
+        const uint32_t total = c->h_offs[gf];
+        if (gf >= 2 && total > 0) {
+            FlFused u;
+            u.count = total; u.heads = c->d_order; u.seg_head = c->d_sg_head; u.ticket_of = c->d_ticket_of;
+            u.done = c->d_fdone; u.next_ticket = c->d_flags + FL_FLAG_TICKET; u.lvl_of = c->d_flvl;
+            LAUNCH_N(k_fused_index, total, total, c->d_order, c->d_hgt, c->d_ticket_of, c->d_flvl, c->d_fdone);
+#ifdef FL_EMU
+            const unsigned blocks = blocks_for(total, 128);  // emulation: one thread per ticket, in ticket order
+#else
+            unsigned blocks = blocks_for(total * 32u, 128);
+            const unsigned cap = (unsigned)c->sm_count * 8u;
+            if (blocks > cap) blocks = cap;
+#endif
+            FL_LAUNCH(k_elev_flow_fused, blocks, 128, c->stream, u, e);
+            launched += 1;
+            g_first = gf;
+        }
+    }
+    for (uint32_t g = g_first; g <= maxh; ++g) {
         const uint32_t b = c->h_offs[g], cnt = c->h_offs[g + 1] - b;
         if (!cnt) continue;
         ++launched;
@@ -845,6 +889,7 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     FL_RC(stage_mark(c, 6));
     FL_RC(read_flags(c));
     FL_CK(fl_last_error());
+    if (c->h_flags[FL_FLAG_BROKEN]) return fail(c, FASTLEM_E_STATE, "K5: a segment waited for its receiver's segment too long (internal error)");
     *changed_out = c->h_flags[FL_FLAG_CHANGED] != 0;
     if (c->opt_profile) {  // receivers | flags | lakes | rebuild + ordering | K4 | K5
         const int from[7] = {0, 1, 2, 3, 8, 7, 5}, to[7] = {1, 2, 3, 7, 5, 8, 6};
@@ -951,7 +996,9 @@ int fastlem_create(fastlem_ctx** out, int device_ordinal) {
 void fastlem_destroy(fastlem_ctx* c) {
     if (!c) return;
     fl_set_device(c->device);
+    FlTrace tr("destroy");
     free_all(c);
+    tr.mark("free_all");
     if (c->d_tmp) fl_free(c->d_tmp);
     if (c->d_flags) fl_free(c->d_flags);
     if (c->h_flags) fl_free_host(c->h_flags);
@@ -987,6 +1034,11 @@ int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
     } else if (s == "incr_div") {
         if (value < 1) return fail(c, FASTLEM_E_INVALID, "option incr_div: >= 1");
         c->opt_incr_div = value;
+    } else if (s == "fuse_levels") {
+        c->opt_fuse_levels = value != 0;
+    } else if (s == "rebuild_growth") {
+        if (value < 1) return fail(c, FASTLEM_E_INVALID, "option rebuild_growth: percent >= 1");
+        c->opt_rebuild_growth = value;
     } else if (s == "rebuild_every") {
         if (value < 0) return fail(c, FASTLEM_E_INVALID, "option rebuild_every: 0 (adaptive) or a positive period");
         c->opt_rebuild_every = value;
@@ -1008,7 +1060,9 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
         if (col[s] >= n) return fail(c, FASTLEM_E_INVALID, "set_graph: neighbour index out of range");
     FL_CK(fl_set_device(c->device));
     double t0 = wall_ms();
+    FlTrace tr("set_graph");
     free_all(c);
+    tr.mark("free previous");
     c->n = n;
     c->nnz = nnz;
     c->h_row_ptr = row_ptr; c->h_col = col; c->h_dist = dist;
@@ -1034,6 +1088,7 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
         FL_CK(dalloc(c, S.cmask, n));
         FL_CK(dalloc(c, S.lvl, n));
     }
+    tr.mark("layout allocations");
     FL_CK(fl_h2d(c->orig.row_ptr, row_ptr, sizeof(uint32_t) * n1, c->stream));
     if (nnz) {
         FL_CK(fl_h2d(c->orig.col, col, sizeof(uint32_t) * nnz, c->stream));
@@ -1078,6 +1133,9 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     FL_CK(dalloc(c, c->d_sg_tail, n));
     FL_CK(dalloc(c, c->d_sg_wait, n));
     FL_CK(dalloc(c, c->d_sg_done, n));
+    FL_CK(dalloc(c, c->d_ticket_of, n));
+    FL_CK(dalloc(c, c->d_fdone, n));
+    FL_CK(dalloc(c, c->d_flvl, n));
     FL_CK(dalloc(c, c->d_hsuf, n));
     FL_CK(dalloc(c, c->d_dirty_from, n));
     FL_CK(dalloc(c, c->d_rlist, n));
@@ -1115,7 +1173,9 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     if (c->d_tmp) { fl_free(c->d_tmp); c->d_tmp = nullptr; }
     c->tmp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
     FL_CK(fl_malloc(&c->d_tmp, c->tmp_bytes));
+    tr.mark("work allocations");
     FL_CK(fl_stream_sync(c->stream));
+    tr.mark("copies + sync");
     FL_CK(fl_last_error());
     c->has_graph = true;
     c->stats = fastlem_stats{};
