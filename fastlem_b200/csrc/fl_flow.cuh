@@ -1225,13 +1225,19 @@ __global__ void __launch_bounds__(128) k_elev_flow_fused(FlFused u, FlElev e) {
 #endif
 }
 
-// keys for sorting segment heads by descending nesting height: key = maxh - hgt (heads), FL_NONE otherwise
-__global__ void __launch_bounds__(256) k_flow_sort_keys(uint32_t n, const uint32_t* __restrict__ hgt, uint32_t maxh,
-                                                         uint32_t* __restrict__ keys) {
+// keys for sorting segment heads by descending nesting height: key = base - hgt (heads), FL_NONE otherwise
+__global__ void __launch_bounds__(256) k_flow_sort_keys(uint32_t n, const uint32_t* __restrict__ hgt, uint32_t base,
+                                                         uint32_t* __restrict__ keys, uint32_t* flags) {
     uint32_t q = FL_TID;
     if (q >= n) return;
+    if (q == 0u) flags[FL_FLAG_K4MAXH] = flags[FL_FLAG_MAXDEPTH];  // K4's result, before the slot is reused below
     const uint32_t h = hgt[q];
-    keys[q] = (h == FL_NONE) ? FL_NONE : (maxh - h);
+    uint32_t key = FL_NONE;
+    if (h != FL_NONE) {
+        if (h > base) atomicOr(&flags[FL_FLAG_BROKEN], 4u);
+        else key = base - h;
+    }
+    keys[q] = key;
 }
 
 // layout rebuild on dynamic segments: exclusive scan input = path length at heads (in index order), 0 elsewhere

@@ -61,18 +61,30 @@ __global__ void __launch_bounds__(256) k_receivers_mask(uint32_t n, const uint32
     if (!is_outlet[i]) {
         const double ei = elev[i];
         double steepest = 0.0;
-        const uint32_t s1 = row_ptr[i + 1];
-        for (uint32_t s = row_ptr[i]; s < s1; ++s) {
-            const uint32_t j = col[s];
-            const double ej = elev[j];
-            if (ei > ej) {
-                const double d = dist[s];
-                const double slope = (ei - ej) / d;
-                if (slope > steepest) {
-                    steepest = slope;
-                    best = j;
-                    best_d = d;
-                    best_s = s;
+        const uint32_t s0 = row_ptr[i], s1 = row_ptr[i + 1];
+        // eight neighbours at a time: their ids and edge lengths first, then the elevation gathers -- all loads of a
+        // batch are in flight together; the comparisons then run in adjacency order (first slot wins ties)
+        for (uint32_t sb = s0; sb < s1; sb += 8u) {
+            uint32_t j[8];
+            double d[8], ej[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const bool ok = sb + (uint32_t)k < s1;
+                j[k] = ok ? col[sb + k] : i;  // padding: the site itself (never lower than itself)
+                d[k] = ok ? dist[sb + k] : 1.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ej[k] = elev[j[k]];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (ei > ej[k]) {
+                    const double slope = (ei - ej[k]) / d[k];
+                    if (slope > steepest) {
+                        steepest = slope;
+                        best = j[k];
+                        best_d = d[k];
+                        best_s = sb + (uint32_t)k;
+                    }
                 }
             }
         }

@@ -35,6 +35,7 @@ double wall_ms() {
 }
 
 #define FL_MAX_ROUNDS 4096u
+#define FL_KEY_BASE 254u  // sort key of a segment head = FL_KEY_BASE - nesting height (one 8-bit radix pass)
 #define FL_WARP_LEVEL_MAX 8192u  // K5: levels with at most this many segments run one warp per segment
 enum Stage { ST_RECV = 0, ST_LABEL, ST_LAKE, ST_ORDER, ST_AREA, ST_ELEV, ST_COUNT };
 
@@ -128,6 +129,8 @@ struct fastlem_ctx {
     uint32_t* d_fdone = nullptr;
     uint32_t* d_flvl = nullptr;
     int64_t opt_fuse_levels = 1;
+    bool trace_iters = std::getenv("FASTLEM_TRACE_ITERS") != nullptr;
+    int64_t opt_key_base = FL_KEY_BASE;  // tests lower it to exercise the deep-nesting path of the head ordering
     uint32_t* d_hsuf = nullptr;
     uint32_t* d_dirty_from = nullptr;
     uint32_t* d_rlist = nullptr;
@@ -149,6 +152,7 @@ struct fastlem_ctx {
     uint32_t segs_at_rebuild = 0, maxh_at_rebuild = 0;
     bool need_rebuild = true;
     int64_t opt_rebuild_every = 0;  // 0 = adaptive
+    int64_t opt_rebuild_height = 150;  // adaptive: ... or when the nesting height exceeds this many percent of its value + 2
     int64_t opt_rebuild_growth = 4;  // adaptive: renumber when the segment count grew by this many percent
     // scratch in the caller's numbering (download, debug fetch, kept stages)
     double* d_out_f64 = nullptr;
@@ -159,7 +163,8 @@ struct fastlem_ctx {
 
     uint32_t* d_flags = nullptr;
     uint32_t* h_flags = nullptr;  // pinned
-    uint32_t* h_offs = nullptr;   // pinned, n+2
+    uint32_t* h_offs = nullptr;   // pinned, n+2 (level offsets of sweeps 0-2)
+    uint32_t* h_offs_k = nullptr; // pinned, FL_KEY_BASE+2 (level offsets of sweep 3, indexed by sort key)
     uint32_t* h_rounds = nullptr; // pinned, FL_MAX_ROUNDS+2
     void* d_tmp = nullptr;        // CUB temp storage (sort / scan)
     size_t tmp_bytes = 0;
@@ -812,27 +817,49 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
 
     // order the segment heads by descending nesting height (exact for the current forest; an upper bound of the
     // largest height after incremental passes -- heights that no longer occur are empty levels)
-    FL_RC(read_flags(c));
-    uint32_t maxh = c->h_flags[FL_FLAG_MAXDEPTH];
-    if (incr && c->prev_maxh > maxh) maxh = c->prev_maxh;
-    if (c->h_flags[FL_FLAG_BROKEN]) return fail(c, FASTLEM_E_STATE, "K4: a climb met an unpublished site (internal error)");
-    // (a wait of the fused K5 launch that ran out would show up here as well, one iteration late, and below)
-    int bits = 1;
-    while (bits < 32 && (1ull << bits) <= (unsigned long long)maxh + 1ull) ++bits;
-    LAUNCH_N(k_flow_sort_keys, n, n, c->d_hgt, maxh, c->d_depth);
-    FL_CK(fl_sort_pairs(c->d_tmp, c->tmp_bytes, c->d_depth, c->d_sorted, c->d_iota, c->d_order, n, bits, c->stream,
-                        false));
-    FL_CK(fl_memset(c->d_flags + FL_FLAG_MAXDEPTH, 0xFF, sizeof(uint32_t), c->stream));
-    FL_CK(fl_memset(c->d_offs, 0xFF, sizeof(uint32_t) * ((size_t)maxh + 2), c->stream));
-    LAUNCH_N(k_level_offsets, n, n, c->d_sorted, c->d_offs, c->d_flags);
-    FL_CK(fl_d2h(c->h_offs, c->d_offs, sizeof(uint32_t) * ((size_t)maxh + 2), c->stream));
-    FL_RC(read_flags(c));
-    const uint32_t last_key = c->h_flags[FL_FLAG_MAXDEPTH];  // = maxh - (smallest height that occurs)
-    if (last_key > maxh || (!incr && last_key != maxh)) return fail(c, FASTLEM_E_STATE, "flow: height bookkeeping broke");
+    // Keys are base - height with a fixed base, so the sort does not have to wait for the host to learn the largest
+    // height: one read-back after the level offsets brings everything.  Only when segments nest deeper than the fixed
+    // base (stale numbering in the first iterations) the ordering is redone with the exact height as base.
+    uint32_t key_base = (uint32_t)c->opt_key_base;
+    uint32_t* hbuf = c->h_offs_k;
+    uint32_t maxh = 0;
+    for (int attempt = 0;; ++attempt) {
+        int bits = 8;
+        if (attempt || key_base != FL_KEY_BASE) {
+            bits = 1;
+            while (bits < 32 && (1ull << bits) <= (unsigned long long)key_base + 1ull) ++bits;
+        }
+        if (attempt) {
+            FL_CK(fl_memset(c->d_flags + FL_FLAG_BROKEN, 0, sizeof(uint32_t), c->stream));
+            FL_CK(fl_d2d(c->d_flags + FL_FLAG_MAXDEPTH, c->d_flags + FL_FLAG_K4MAXH, sizeof(uint32_t), c->stream));
+        }
+        LAUNCH_N(k_flow_sort_keys, n, n, c->d_hgt, key_base, c->d_depth, c->d_flags);
+        FL_CK(fl_sort_pairs(c->d_tmp, c->tmp_bytes, c->d_depth, c->d_sorted, c->d_iota, c->d_order, n, bits, c->stream,
+                            false));
+        FL_CK(fl_memset(c->d_flags + FL_FLAG_MAXDEPTH, 0xFF, sizeof(uint32_t), c->stream));
+        FL_CK(fl_memset(c->d_offs, 0xFF, sizeof(uint32_t) * ((size_t)key_base + 2), c->stream));
+        LAUNCH_N(k_level_offsets, n, n, c->d_sorted, c->d_offs, c->d_flags);
+        FL_CK(fl_d2h(hbuf, c->d_offs, sizeof(uint32_t) * ((size_t)key_base + 2), c->stream));
+        FL_RC(read_flags(c));
+        if (c->h_flags[FL_FLAG_BROKEN] & 1u)
+            return fail(c, FASTLEM_E_STATE, "K4: a climb met an unpublished site (internal error)");
+        maxh = c->h_flags[FL_FLAG_K4MAXH];
+        if (incr && c->prev_maxh > maxh) maxh = c->prev_maxh;
+        if (!(c->h_flags[FL_FLAG_BROKEN] & 4u)) break;
+        if (attempt) return fail(c, FASTLEM_E_STATE, "flow: height bookkeeping broke (keys)");
+        key_base = maxh;  // deeper than the fixed base: exact base, more key bits, the large host buffer
+        hbuf = c->h_offs;
+    }
+    uint32_t* const hoffs = hbuf + (key_base - maxh);  // hoffs[g]: first head of height maxh - g
+    const uint32_t last_abs = c->h_flags[FL_FLAG_MAXDEPTH];  // = key_base - (smallest height that occurs)
+    if (last_abs == FL_NONE || last_abs < key_base - maxh || last_abs > key_base || (!incr && last_abs != key_base))
+        return fail(c, FASTLEM_E_STATE, "flow: height bookkeeping broke");
+    const uint32_t last_key = last_abs - (key_base - maxh);
     const uint32_t n_heads = c->h_flags[FL_FLAG_REACHED];
-    for (uint32_t g = last_key + 2; g <= maxh + 1; ++g) c->h_offs[g] = n_heads;
+    for (uint32_t g = last_key + 2; g <= maxh + 1; ++g) hoffs[g] = n_heads;
     for (uint32_t g = maxh + 1; g-- > 0;)
-        if (c->h_offs[g] == FL_NONE) c->h_offs[g] = c->h_offs[g + 1];
+        if (hoffs[g] == FL_NONE) hoffs[g] = hoffs[g + 1];
+    if (hoffs[0] == FL_NONE) hoffs[0] = 0;
     c->stats.n_order += 3;
     c->stats.path_levels = maxh + 1;
     c->stats.paths = n_heads;
@@ -841,8 +868,12 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     else if (c->opt_rebuild_every == 0 &&
              ((unsigned long long)n_heads * 100ull >
                   (unsigned long long)c->segs_at_rebuild * (100ull + (unsigned long long)c->opt_rebuild_growth) ||
-              maxh > c->maxh_at_rebuild + c->maxh_at_rebuild / 2 + 2))
+              (unsigned long long)maxh * 100ull >
+                  (unsigned long long)c->maxh_at_rebuild * (unsigned long long)c->opt_rebuild_height + 200ull))
         c->need_rebuild = true;  // the numbering has degraded: renumber in the next iteration
+    if (c->trace_iters && it < 400u)
+        std::fprintf(stderr, "[fastlem trace] it %u: chg %u incr %d rebuilt %d heads %u maxh %u next_rebuild %d\n", it, n_chg,
+                     (int)incr, (int)rebuilt, n_heads, maxh, (int)c->need_rebuild);
     FL_RC(stage_mark(c, 5));  // end of the head ordering
 
     // K5: one launch per nesting height, outermost segments first
@@ -856,8 +887,8 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     uint32_t g_first = 0;
     if (c->opt_fuse_levels) {
         uint32_t gf = 0;
-        while (gf <= maxh && c->h_offs[gf + 1] - c->h_offs[gf] <= FL_WARP_LEVEL_MAX) ++gf;
-        const uint32_t total = c->h_offs[gf];
+        while (gf <= maxh && hoffs[gf + 1] - hoffs[gf] <= FL_WARP_LEVEL_MAX) ++gf;
+        const uint32_t total = hoffs[gf];
         if (gf >= 2 && total > 0) {
             FlFused u;
             u.count = total; u.heads = c->d_order; u.seg_head = c->d_sg_head; u.ticket_of = c->d_ticket_of;
@@ -876,7 +907,7 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
         }
     }
     for (uint32_t g = g_first; g <= maxh; ++g) {
-        const uint32_t b = c->h_offs[g], cnt = c->h_offs[g + 1] - b;
+        const uint32_t b = hoffs[g], cnt = hoffs[g + 1] - b;
         if (!cnt) continue;
         ++launched;
         e.lvl_value = maxh - g;
@@ -979,6 +1010,15 @@ int fastlem_create(fastlem_ctx** out, int device_ordinal) {
         return FASTLEM_E_NOMEM;
     }
     c->h_rounds = (uint32_t*)hr;
+    void* hk = nullptr;
+    if (fl_malloc_host(&hk, sizeof(uint32_t) * (FL_KEY_BASE + 2)) != cudaSuccess) {
+        fl_free_host(hf);
+        fl_free_host(hr);
+        fl_stream_destroy(c->stream);
+        delete c;
+        return FASTLEM_E_NOMEM;
+    }
+    c->h_offs_k = (uint32_t*)hk;
     bool ok = true;
     for (int k = 0; k < ST_COUNT + 3; ++k) ok = ok && fl_event_create(&c->ev[k]) == cudaSuccess;
     for (int k = 0; k < 2; ++k) ok = ok && fl_event_create(&c->ev_run[k]) == cudaSuccess;
@@ -1003,6 +1043,7 @@ void fastlem_destroy(fastlem_ctx* c) {
     if (c->d_flags) fl_free(c->d_flags);
     if (c->h_flags) fl_free_host(c->h_flags);
     if (c->h_rounds) fl_free_host(c->h_rounds);
+    if (c->h_offs_k) fl_free_host(c->h_offs_k);
     for (int k = 0; k < ST_COUNT + 3; ++k)
         if (c->ev[k]) fl_event_destroy(c->ev[k]);
     for (int k = 0; k < 2; ++k)
@@ -1034,8 +1075,14 @@ int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
     } else if (s == "incr_div") {
         if (value < 1) return fail(c, FASTLEM_E_INVALID, "option incr_div: >= 1");
         c->opt_incr_div = value;
+    } else if (s == "key_base") {
+        if (value < 1 || value > (int64_t)FL_KEY_BASE) return fail(c, FASTLEM_E_INVALID, "option key_base: 1..254");
+        c->opt_key_base = value;
     } else if (s == "fuse_levels") {
         c->opt_fuse_levels = value != 0;
+    } else if (s == "rebuild_height") {
+        if (value < 100) return fail(c, FASTLEM_E_INVALID, "option rebuild_height: percent >= 100");
+        c->opt_rebuild_height = value;
     } else if (s == "rebuild_growth") {
         if (value < 1) return fail(c, FASTLEM_E_INVALID, "option rebuild_growth: percent >= 1");
         c->opt_rebuild_growth = value;
@@ -1106,7 +1153,7 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     FL_CK(dalloc(c, c->d_ids, n));
     FL_CK(dalloc(c, c->d_sorted, n));
     FL_CK(dalloc(c, c->d_order, n));
-    FL_CK(dalloc(c, c->d_offs, (size_t)n + 2));
+    FL_CK(dalloc(c, c->d_offs, (size_t)n + 2 > FL_KEY_BASE + 2 ? (size_t)n + 2 : (size_t)FL_KEY_BASE + 2));
     FL_CK(dalloc(c, c->d_A, n));
     FL_CK(dalloc(c, c->d_rt, n));
     FL_CK(dalloc(c, c->d_root_of, n));

@@ -170,3 +170,13 @@ def test_incremental_stages_midway(oracle, emu_lib):
             assert np.array_equal(ctx.fetch("receivers"), ref["next"])
             assert np.array_equal(ctx.fetch("drainage_area"), ref["drainage"])
             assert np.array_equal(ctx.fetch("response_time"), ref["response"])
+
+
+@pytest.mark.parametrize("name", ["uniform", "advanced", "uplift", "max_slope"])
+def test_head_ordering_deep_nesting_path(oracle, emu_lib, name):
+    """The head ordering of sweep 3 sorts on a fixed key base; segments nesting deeper than the base take a second
+    pass with the exact base.  key_base=1 forces that path on small inputs."""
+    m, p, outlets, initial, max_iteration = scenario(name)
+    with _ctx(emu_lib, sweep=3, key_base=1) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)

@@ -144,6 +144,18 @@ def test_c7_nonuniform_uplift_lakes_every_iteration(oracle, gpu_ctx_factory):
         assert ctx.stats()["lake_iterations"] > 1
 
 
+@pytest.mark.parametrize("opts", [dict(key_base=1), dict(fuse_levels=0), dict(incremental=0), dict(incr_div=1),
+                                  dict(flood_device=0)])
+@pytest.mark.parametrize("name,n", [("uniform", 30000), ("advanced", 20000), ("max_slope", 20000)])
+def test_solver_options_do_not_change_results(oracle, gpu_ctx_factory, name, n, opts):
+    """Every scheduling option (deep-nesting ordering path, per-level K5 launches, full K4 every iteration, incremental
+    K4 whenever possible, host flood replay) must give the oracle's bits."""
+    m, p, outlets, initial, max_iteration = scenario(name, n)
+    with gpu_ctx_factory(**opts) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
+
+
 @pytest.mark.parametrize("name,n", [("uniform", 3000), ("advanced", 5000), ("lattice", None), ("lattice_regular", None),
                                     ("disconnected", None), ("interior_outlets", 8000), ("single_outlet", 6000),
                                     ("uniform", 200000), ("advanced", 200000), ("uniform", 1000000)])
