@@ -139,6 +139,9 @@ def main():
     ap.add_argument("--cpu-baseline-iters", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", type=int, default=None, help="solver option 'sweep' (DESIGN.md)")
+    ap.add_argument("--max-iter", type=int, default=None,
+                    help="profiling aid: stop every generate() after this many iterations (the metric is then NOT the "
+                         "benchmark's; used for ncu launch lists of the same command)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -179,7 +182,7 @@ def main():
         torch.cuda.synchronize()
 
     def resident_step():
-        it = ctx.run()
+        it = ctx.run(args.max_iter)
         if world > 1:
             ctx.download_to_device(mine.data_ptr())
             dist.all_gather(gathered, mine)
@@ -241,7 +244,7 @@ def main():
         tc = time.perf_counter()
         c2.set_parameters(hp["initial"], hp["erodibility"], hp["uplift"], None, hp["outlets"])
         td = time.perf_counter()
-        _, it = c2.generate(out=out)
+        _, it = c2.generate(args.max_iter, out=out)
         te_ = time.perf_counter()
         e2e_iters += it
         e2e_stats = c2.stats()
@@ -296,6 +299,7 @@ def main():
                            "sites": n, "directed_edges": int(m["col"].size),
                            "iterations_per_step": iters_total / args.steps,
                            "l2": "working set ~170 MB per iteration > 126 MB L2; hundreds of iterations per step, no flush",
+                           "max_iteration": args.max_iter,
                            "parallelism": "1 terrain per GPU" if world > 1 else "single GPU",
                            "sweep": args.sweep},
                 "generate_seconds": wall_max / args.steps, "device_ms_per_step": 1e3 * dev_max / args.steps,

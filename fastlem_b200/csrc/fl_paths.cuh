@@ -69,9 +69,10 @@ __global__ void __launch_bounds__(256) k_receivers_mask(uint32_t n, const uint32
             double d[8], ej[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const bool ok = sb + (uint32_t)k < s1;
-                j[k] = ok ? col[sb + k] : i;  // padding: the site itself (never lower than itself)
-                d[k] = ok ? dist[sb + k] : 1.0;
+                const uint32_t s = sb + (uint32_t)k;
+                const bool ok = s < s1;
+                j[k] = ok ? col[s] : i;  // padding: the site itself (never lower than itself)
+                d[k] = ok ? dist[s] : 1.0;
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k) ej[k] = elev[j[k]];
