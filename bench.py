@@ -303,7 +303,7 @@ def main():
                            "parallelism": "1 terrain per GPU" if world > 1 else "single GPU",
                            "sweep": args.sweep},
                 "generate_seconds": wall_max / args.steps, "device_ms_per_step": 1e3 * dev_max / args.steps,
-                "first_iteration_tree_depth": last["depth_first"],
+                "first_iteration_nesting_levels_or_tree_depth": last["depth_first"] or None,
                 "incremental_area_iterations": last["incremental_iterations"],
                 "layout": {"rebuilds_per_step": last["rebuilds"], "nesting_levels": last["path_levels"],
                            "segments": last["paths"]},

@@ -125,6 +125,10 @@ struct fastlem_ctx {
     uint32_t* d_sg_wait = nullptr;
     uint32_t* d_sg_done = nullptr;
     // incremental K4 (fl_flow.cuh): state kept between iterations + per-iteration work lists
+    uint32_t* d_ready = nullptr;      // fused incremental K4: per parked slot
+    int incr_flow_blocks = 0;         // resident blocks of k_incr_flow (0 = not available)
+    int64_t opt_fuse_k4 = 0;     // measured no faster than two launches: kept as an option
+    int64_t opt_first_flow = 1;  // the first iteration also uses the dataflow sweeps (layout by subtree sizes)
     uint32_t* d_ticket_of = nullptr;  // fused sparse levels of K5
     uint32_t* d_fdone = nullptr;
     uint32_t* d_flvl = nullptr;
@@ -757,7 +761,16 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
 
     const bool periodic = c->opt_rebuild_every > 0 && (it % (uint32_t)c->opt_rebuild_every) == 0;
     const bool rebuilt = c->need_rebuild || periodic || c->opt_rebuild_every == 1;
-    if (rebuilt) FL_RC(rebuild_layout_flow(c, c->d_A));
+    if (rebuilt) {
+        if (it == 0) {  // no previous areas yet: rank the children by subtree size (fl_flow.cuh)
+            Layout& L0 = L_(c);
+            LAUNCH_N(k_subtree_init, n, n, L0.cmask, c->d_state, c->d_nwait);
+            LAUNCH_N(k_subtree_sweep, n, n, L0.recv, L0.cmask, c->d_state, c->d_nwait);
+            LAUNCH_N(k_subtree_weight, n, n, c->d_state, c->d_A);
+            c->stats.n_order += 3;
+        }
+        FL_RC(rebuild_layout_flow(c, c->d_A));
+    }
     c->need_rebuild = false;
     FL_RC(stage_mark(c, 7));  // end of the layout rebuild
     Layout& L = L_(c);
@@ -773,6 +786,7 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     f.hgt = c->d_hgt; f.flags = c->d_flags; f.parked = c->d_parked; f.counters = c->d_flags + FL_FLAG_PARKED;
     f.park_after = (uint32_t)c->opt_park_after; f.stats = c->d_flow_stats; f.tlog = c->d_tlog;
     f.hsuf = c->d_hsuf; f.dirty_from = nullptr; f.rlist = c->d_rlist; f.slist = c->d_slist;
+    f.ready = c->d_ready; f.remaining = nullptr;
     if (!incr) {
         FL_CK(fl_memset(c->d_state, 0, sizeof(uint32_t) * n, c->stream));
         FL_CK(fl_memset(c->d_nwait, 0, sizeof(uint32_t) * n, c->stream));
@@ -805,11 +819,24 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
             FL_LAUNCH(k_incr_mark, blocks_for(n_chg, 128), 128, c->stream, f, n_chg, c->d_chg_node, c->d_chg_old);
             const unsigned wide = (unsigned)c->sm_count * 8u;
             FL_LAUNCH(k_incr_prepare, wide, 128, c->stream, f);
-            FL_LAUNCH(k_incr_start, wide * 2u, 64, c->stream, f);
-            if (f.park_after) FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 4u, 256, c->stream, f);
+            bool fused = false;
+#ifndef FL_EMU
+            if (c->opt_fuse_k4 && f.park_after && c->incr_flow_blocks > 0) {
+                // one launch for the thread-level starts and the warp-level continuation (all blocks resident)
+                f.remaining = c->d_flags + FL_FLAG_NROOTS;
+                FL_LAUNCH(k_incr_flow, (unsigned)c->incr_flow_blocks, 256, c->stream, f);
+                f.remaining = nullptr;
+                fused = true;
+            }
+#endif
+            if (!fused) {
+                FL_LAUNCH(k_incr_start, wide * 2u, 64, c->stream, f);
+                if (f.park_after) FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 4u, 256, c->stream, f);
+            }
             FL_LAUNCH(k_incr_cleanup, wide, 256, c->stream, f);
-            c->stats.kernel_launches += f.park_after ? 7 : 6;
-            c->stats.n_area += f.park_after ? 7 : 6;
+            const uint64_t nl = fused ? 6 : (f.park_after ? 7 : 6);
+            c->stats.kernel_launches += nl;
+            c->stats.n_area += nl;
         }
         c->stats.incremental_iterations++;
     }
@@ -843,6 +870,8 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
         FL_RC(read_flags(c));
         if (c->h_flags[FL_FLAG_BROKEN] & 1u)
             return fail(c, FASTLEM_E_STATE, "K4: a climb met an unpublished site (internal error)");
+        if (c->h_flags[FL_FLAG_BROKEN] & 8u)
+            return fail(c, FASTLEM_E_STATE, "K4: the fused pass waited for parked work too long (internal error)");
         maxh = c->h_flags[FL_FLAG_K4MAXH];
         if (incr && c->prev_maxh > maxh) maxh = c->prev_maxh;
         if (!(c->h_flags[FL_FLAG_BROKEN] & 4u)) break;
@@ -1075,6 +1104,10 @@ int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
     } else if (s == "incr_div") {
         if (value < 1) return fail(c, FASTLEM_E_INVALID, "option incr_div: >= 1");
         c->opt_incr_div = value;
+    } else if (s == "first_flow") {
+        c->opt_first_flow = value != 0;
+    } else if (s == "fuse_k4") {
+        c->opt_fuse_k4 = value != 0;
     } else if (s == "key_base") {
         if (value < 1 || value > (int64_t)FL_KEY_BASE) return fail(c, FASTLEM_E_INVALID, "option key_base: 1..254");
         c->opt_key_base = value;
@@ -1180,6 +1213,15 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     FL_CK(dalloc(c, c->d_sg_tail, n));
     FL_CK(dalloc(c, c->d_sg_wait, n));
     FL_CK(dalloc(c, c->d_sg_done, n));
+    FL_CK(dalloc(c, c->d_ready, (size_t)n + 65536));
+    FL_CK(fl_memset(c->d_ready, 0, sizeof(uint32_t) * ((size_t)n + 65536), c->stream));
+#ifndef FL_EMU
+    {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_incr_flow, 256, 0) == cudaSuccess && occ > 0)
+            c->incr_flow_blocks = occ * fl_sm_count();
+    }
+#endif
     FL_CK(dalloc(c, c->d_ticket_of, n));
     FL_CK(dalloc(c, c->d_fdone, n));
     FL_CK(dalloc(c, c->d_flvl, n));
@@ -1286,8 +1328,9 @@ int fastlem_run(fastlem_ctx* c, uint32_t max_iteration, uint32_t* iterations_don
         bool changed = false;
         // The first body runs level-synchronously: it yields the drainage areas that rank the heavy
         // children of the path layout from the second body on.
-        if (c->opt_sweep == 0 || it == 0) FL_RC(iterate_levels(c, it == 0, &changed));
-        else if (c->opt_sweep == 3 && c->max_degree <= 32) FL_RC(iterate_flow(c, it, &changed));
+        const bool flow_ok = c->opt_sweep == 3 && c->max_degree <= 32;
+        if (c->opt_sweep == 0 || (it == 0 && !(flow_ok && c->opt_first_flow))) FL_RC(iterate_levels(c, it == 0, &changed));
+        else if (flow_ok) FL_RC(iterate_flow(c, it, &changed));
         else FL_RC(iterate_paths(c, &changed));
         ++it;
         if (!changed) break;

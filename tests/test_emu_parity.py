@@ -180,3 +180,13 @@ def test_head_ordering_deep_nesting_path(oracle, emu_lib, name):
     with _ctx(emu_lib, sweep=3, key_base=1) as ctx:
         helpers.load_ctx(ctx, m, p, outlets, initial)
         assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
+
+
+@pytest.mark.parametrize("name", ["uniform", "advanced", "uplift", "plateau", "disconnected", "interior_outlets"])
+def test_first_iteration_levels_vs_flow(oracle, emu_lib, name):
+    """first_flow=0: iteration 1 one launch per tree level; default: dataflow sweeps on a layout by subtree sizes."""
+    m, p, outlets, initial, max_iteration = scenario(name)
+    for first_flow in (0, 1):
+        with _ctx(emu_lib, sweep=3, first_flow=first_flow) as ctx:
+            helpers.load_ctx(ctx, m, p, outlets, initial)
+            assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
