@@ -22,21 +22,35 @@ __device__ __forceinline__ double fl_shfl(double v, int src) { return __shfl_syn
 #endif
 
 // ------------------------------------------------------------------------------------------------
-// static per-graph table: rev[s] = slot of i inside adj(col[s]) (first match), 255 if >= 255 / absent
+// static per-graph table: rev[s] = slot of i inside adj(col[s]) (first match), 255 if >= 255 / absent;
+// also checks that the graph is what terrain-graph's add_edge produces from a triangulation: simple and symmetric
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_rev_slots(uint32_t n, const uint32_t* __restrict__ row_ptr,
-                                                    const uint32_t* __restrict__ col, uint8_t* __restrict__ rev) {
+                                                    const uint32_t* __restrict__ col, const double* __restrict__ dist,
+                                                    uint8_t* __restrict__ rev, uint32_t* __restrict__ bad) {
     uint32_t i = FL_TID;
     if (i >= n) return;
-    const uint32_t s1 = row_ptr[i + 1];
-    for (uint32_t s = row_ptr[i]; s < s1; ++s) {
+    const uint32_t s0 = row_ptr[i], s1 = row_ptr[i + 1];
+    uint32_t flaws = 0u;  // 1 self loop, 2 parallel edge, 4 no reverse edge, 8 lengths differ between the directions
+    for (uint32_t s = s0; s < s1; ++s) {
         const uint32_t j = col[s];
+        if (j == i) flaws |= 1u;
+        for (uint32_t t = s0; t < s; ++t)
+            if (col[t] == j) flaws |= 2u;
         const uint32_t t0 = row_ptr[j], t1 = row_ptr[j + 1];
         uint32_t r = 255;
+        bool found = false;
         for (uint32_t t = t0; t < t1; ++t)
-            if (col[t] == i) { r = (t - t0) < 255u ? (t - t0) : 255u; break; }
+            if (col[t] == i) {
+                r = (t - t0) < 255u ? (t - t0) : 255u;
+                found = true;
+                if (!(dist[t] == dist[s])) flaws |= 8u;
+                break;
+            }
+        if (!found) flaws |= 4u;
         rev[s] = (uint8_t)r;
     }
+    if (flaws) atomicOr(bad, flaws);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1175,7 +1175,9 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
         FL_CK(fl_h2d(c->orig.dist, dist, sizeof(double) * nnz, c->stream));
     }
     FL_CK(fl_h2d(c->orig.areas, areas, sizeof(double) * n, c->stream));
-    LAUNCH_N(k_rev_slots, n, n, c->orig.row_ptr, c->orig.col, c->orig.rev);
+    FL_CK(fl_memset(c->d_flags, 0, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
+    LAUNCH_N(k_rev_slots, n, n, c->orig.row_ptr, c->orig.col, c->orig.dist, c->orig.rev, c->d_flags);
+    FL_CK(fl_d2h(c->h_flags, c->d_flags, sizeof(uint32_t), c->stream));
     FL_CK(dalloc(c, c->d_init, n));
     FL_CK(dalloc(c, c->d_rank_to_node, n));
     FL_CK(dalloc(c, c->d_pd, n));
@@ -1266,6 +1268,15 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     FL_CK(fl_stream_sync(c->stream));
     tr.mark("copies + sync");
     FL_CK(fl_last_error());
+    if (c->h_flags[0]) {
+        const uint32_t fw = c->h_flags[0];
+        free_all(c);
+        return fail(c, FASTLEM_E_INVALID,
+                    std::string("set_graph: the graph must be simple and symmetric with equal lengths in both directions (") +
+                        ((fw & 1u) ? "self loop; " : "") + ((fw & 2u) ? "parallel edges; " : "") +
+                        ((fw & 4u) ? "edge without its reverse; " : "") + ((fw & 8u) ? "lengths differ between the two directions; " : "") +
+                        "terrain-graph's add_edge on a triangulation never produces these)");
+    }
     c->has_graph = true;
     c->stats = fastlem_stats{};
     c->stats.ms_upload = wall_ms() - t0;

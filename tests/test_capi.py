@@ -103,3 +103,28 @@ def test_no_outlets_runs_one_idle_iteration(emu_lib, oracle):
         e, it = ctx.generate()
     ref, ref_it = oracle.generate(m, p["erodibility"], p["uplift"], None, none, initial)
     assert it == ref_it == 1 and np.array_equal(e, ref) and np.array_equal(e, initial)
+
+
+def test_non_simple_graphs_are_rejected(emu_lib):
+    """The solver needs what terrain-graph's add_edge produces from a triangulation: a simple, symmetric graph with
+    equal lengths in both directions.  Anything else is refused by fastlem_set_graph instead of diverging later."""
+    from fastlem_b200 import _native
+    ok = dict(row_ptr=np.array([0, 1, 3, 4], dtype=np.uint32), col=np.array([1, 0, 2, 1], dtype=np.uint32),
+              dist=np.array([1.0, 1.0, 2.0, 2.0]), areas=np.ones(3))
+    cases = {
+        "self loop": dict(row_ptr=np.array([0, 2, 3, 3], dtype=np.uint32), col=np.array([0, 1, 0], dtype=np.uint32),
+                          dist=np.array([1.0, 1.0, 1.0])),
+        "parallel edges": dict(row_ptr=np.array([0, 2, 4, 4], dtype=np.uint32), col=np.array([1, 1, 0, 0], dtype=np.uint32),
+                               dist=np.array([1.0, 1.5, 1.0, 1.5])),
+        "edge without its reverse": dict(row_ptr=np.array([0, 1, 1, 1], dtype=np.uint32), col=np.array([1], dtype=np.uint32),
+                                         dist=np.array([1.0])),
+        "lengths differ": dict(row_ptr=np.array([0, 1, 2, 2], dtype=np.uint32), col=np.array([1, 0], dtype=np.uint32),
+                               dist=np.array([1.0, 2.0])),
+    }
+    with _native.Context(0, emu_lib) as ctx:
+        ctx.set_graph(ok["row_ptr"], ok["col"], ok["dist"], ok["areas"])
+        for what, g in cases.items():
+            with pytest.raises(_native.FastlemError) as ei:
+                ctx.set_graph(g["row_ptr"], g["col"], g["dist"], np.ones(3))
+            assert ei.value.code == _native.E_INVALID, what
+            assert what.split()[0] in str(ei.value), what

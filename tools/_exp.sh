@@ -1,3 +1,2 @@
-timeout 100 python tools/profile_run.py --sites 1000000 --brief --repeat 2 | tail -1
-timeout 100 python tools/profile_run.py --sites 1000000 --brief --repeat 2 --opt park_after=4 | tail -1
-timeout 100 python tools/profile_run.py --sites 1000000 --brief --repeat 2 --opt park_after=16 | tail -1
+set -x
+FASTLEM_TRACE=1 timeout 800 python tools/profile_run.py --sites 16000000 --lattice --brief --repeat 2 2>&1 | grep -v "set_graph: free\|copies"

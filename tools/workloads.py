@@ -30,7 +30,7 @@ def _orient_ccw(pts, tri):
     return tri, np.abs(cross) * 0.5
 
 
-def model_from_triangles(pts, tri, hull_cycle=None):
+def model_from_triangles(pts, tri, hull_cycle=None, dedupe=False):
     """Boundary-format model from CCW triangles, following builder.rs:249-270."""
     pts = np.ascontiguousarray(pts, dtype=np.float64)
     n = pts.shape[0]
@@ -40,6 +40,11 @@ def model_from_triangles(pts, tri, hull_cycle=None):
     to = tri[:, [1, 2, 0]].reshape(-1)
     keep = frm < to
     ea, eb = frm[keep], to[keep]
+    if dedupe:  # inputs that are not proper triangulations (jittered lattice with flipped cells): keep a simple graph
+        key = ea * np.int64(n) + eb
+        _, first = np.unique(key, return_index=True)
+        first.sort()
+        ea, eb = ea[first], eb[first]
     ne = ea.size
     d = np.sqrt((pts[ea, 0] - pts[eb, 0]) ** 2 + (pts[ea, 1] - pts[eb, 1]) ** 2)
     # add_edge(a,b,w): push (b,w) to a's list and (a,w) to b's list, in edge order
@@ -153,7 +158,7 @@ def lattice_model(nx, ny, bound_max=(100.0, 100.0), jitter=0.35, seed=0):
     tri = np.empty((2 * v00.size, 3), dtype=np.int64)
     tri[0::2], tri[1::2] = t1, t2
     rim = np.concatenate([idx[0, :-1], idx[:-1, -1], idx[-1, :0:-1], idx[:0:-1, 0]])
-    return model_from_triangles(pts, tri, hull_cycle=rim)
+    return model_from_triangles(pts, tri, hull_cycle=rim, dedupe=True)
 
 
 # ------------------------------------------------------------------------------------------------
