@@ -31,6 +31,12 @@ METRIC = "sites_per_sec_per_generate_iteration"
 UNIT = "sites/s"
 # algorithmic bytes per site per iteration (DESIGN.md "Roofline")
 STAGE_BYTES = {"receivers": 88.125, "labels": 8.0, "area": 20.0, "elevation": 64.0}
+# dram__bytes_read.sum + dram__bytes_write.sum per pass at 1M sites from one `ncu --set full` capture of a late iteration
+# (profiles/r1b_ncu_kernels.txt): K1 = k_receivers_mask; K4 = the two flow kernels of an incremental pass
+NCU_TRAFFIC = {"receivers": 107.6e6, "area": 11.0e6}
+NCU_TRAFFIC_NOTE = {"receivers": "ncu: 99.1 MB read + 8.5 MB written per launch (88.1 MB algorithmic)",
+                    "area": "ncu: k_incr_start 6.8 MB + k_area_flow_long 4.1 MB per incremental pass (20 MB algorithmic for a "
+                            "full pass; the incremental pass touches 3-10 % of the sites)"}
 
 
 def build_workload(n_sites, seed):
@@ -272,11 +278,16 @@ def main():
         iter_bytes = 180.0 * n
         whole = iter_bytes * passes / (dev_ms / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(dom) if n == 1000000 else None,
+                    "peak_source": peak_src,
                     "bytes_per_pass": alg_bytes, "ms_per_pass": stage_ms[dom] / max(passes, 1),
                     "kernel_launches_per_pass": stage_n[dom] / max(passes, 1),
-                    "kernel_names": {"receivers": "k_receivers_mask", "area": "k_count_waits+k_seg_keys+scan+k_seg_prepare+k_area_flow+k_area_flow_long",
-                                     "elevation": "k_celerity_term+k_elev_flow[_warps]"}[dom],
+                    "kernel_names": {"receivers": "k_receivers_mask",
+                                     "area": "incremental pass (9 of 10 iterations): k_seg_keys+scan+k_incr_mark+k_incr_prepare+"
+                                             "k_incr_start+k_area_flow_long+k_incr_cleanup; full pass: k_count_waits+k_seg_keys+scan+"
+                                             "k_seg_prepare+k_area_flow+k_area_flow_long",
+                                     "elevation": "k_celerity_term+k_fused_index+k_elev_flow_fused+k_elev_flow"}[dom],
+                    "traffic_note": NCU_TRAFFIC_NOTE.get(dom),
                     "receivers_kernel": {"achieved": k1, "frac": k1 / peak,
                                          "ms_per_launch": stage_ms["receivers"] / max(stage_n["receivers"], 1)},
                     "whole_iteration": {"achieved": whole, "frac": whole / peak, "bytes": iter_bytes},

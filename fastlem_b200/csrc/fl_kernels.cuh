@@ -76,15 +76,25 @@ __global__ void __launch_bounds__(256) k_jump_init(uint32_t n, const uint32_t* _
 __global__ void __launch_bounds__(256) k_jump(uint32_t n, volatile unsigned long long* pd, uint32_t* flags) {
     uint32_t i = FL_TID;
     if (i >= n) return;
+    // up to four jumps per launch: every intermediate (pointer, distance) pair another thread may read is consistent,
+    // so the rounds need no barrier between them -- fewer launches and read-backs per pointer-jumping loop
     unsigned long long a = pd[i];
-    uint32_t p = (uint32_t)a;
-    if (p == i) return;
-    unsigned long long b = pd[p];
-    uint32_t q = (uint32_t)b;
-    if (q == p) return;  // p is a root: done
-    uint32_t d = (uint32_t)(a >> 32) + (uint32_t)(b >> 32);
-    pd[i] = (unsigned long long)q | ((unsigned long long)d << 32);
-    flags[FL_FLAG_JUMP] = 1u;
+    bool moved = false;
+#pragma unroll 1
+    for (int hop = 0; hop < 4; ++hop) {
+        const uint32_t p = (uint32_t)a;
+        if (p == i) break;
+        const unsigned long long b = pd[p];
+        const uint32_t q = (uint32_t)b;
+        if (q == p) break;  // p is a root: done
+        const uint32_t d = (uint32_t)(a >> 32) + (uint32_t)(b >> 32);
+        a = (unsigned long long)q | ((unsigned long long)d << 32);
+        moved = true;
+    }
+    if (moved) {
+        pd[i] = a;
+        flags[FL_FLAG_JUMP] = 1u;
+    }
 }
 
 // label = root; depth key = depth if the root is an outlet, FL_NONE otherwise (such nodes are in no
