@@ -67,6 +67,12 @@ struct fastlem_ctx {
     bool stream_ok = false;
     std::string err;
     std::vector<void**> owned;  // every device allocation, for free_all
+    // set_graph's buffers come out of ONE device allocation (cudaMalloc / cudaFree cost milliseconds each on a busy
+    // box and there are ~120 buffers): a dry pass adds up the sizes, then the same calls carve the slab
+    unsigned char* slab = nullptr;
+    size_t slab_size = 0, slab_used = 0, slab_need = 0;
+    bool slab_dry = false;
+    std::vector<void**> slab_ptrs;
 
     uint32_t n = 0, nnz = 0;
     bool has_graph = false, has_params = false, has_tan = false;
@@ -201,6 +207,14 @@ int fail(fastlem_ctx* c, int code, const std::string& msg) {
     } while (0)
 
 template <class T> cudaError_t dalloc(fastlem_ctx* c, T*& p, size_t count) {
+    const size_t bytes = ((count ? count : 1) * sizeof(T) + 255) & ~(size_t)255;
+    if (c->slab_dry) { c->slab_need += bytes; return cudaSuccess; }
+    if (c->slab && c->slab_used + bytes <= c->slab_size) {
+        p = (T*)(c->slab + c->slab_used);
+        c->slab_used += bytes;
+        c->slab_ptrs.push_back((void**)&p);
+        return cudaSuccess;
+    }
     if (p) { fl_free(p); p = nullptr; }
     void* v = nullptr;
     cudaError_t e = fl_malloc(&v, count * sizeof(T));
@@ -215,9 +229,24 @@ void free_all(fastlem_ctx* c) {
     for (void** q : c->owned)
         if (*q) { fl_free(*q); *q = nullptr; }
     c->owned.clear();
+    for (void** q : c->slab_ptrs) *q = nullptr;
+    c->slab_ptrs.clear();
+    if (c->slab) fl_free(c->slab);
+    c->slab = nullptr;
+    c->slab_size = c->slab_used = c->slab_need = 0;
     if (c->h_offs) fl_free_host(c->h_offs);
     c->h_offs = nullptr;
     c->has_graph = c->has_params = c->rank_ready = c->stages_valid = c->has_tan = c->layout_valid = false;
+}
+
+// pinned host buffer for the per-level offsets of the level / path sweeps (allocated on first use: the default
+// dataflow sweeps read back FL_KEY_BASE+2 words only)
+int ensure_h_offs(fastlem_ctx* c) {
+    if (c->h_offs) return FASTLEM_OK;
+    void* ho = nullptr;
+    FL_CK(fl_malloc_host(&ho, sizeof(uint32_t) * ((size_t)c->n + 2)));
+    c->h_offs = (uint32_t*)ho;
+    return FASTLEM_OK;
 }
 
 inline unsigned blocks_for(uint32_t count, unsigned block = 256) { return (count + block - 1u) / block; }
@@ -282,10 +311,20 @@ struct FlTrace {
 // device allocations that live for one call
 struct FlTmpAlloc {
     std::vector<void*> p;
+    unsigned char* slab = nullptr;
+    size_t size = 0, used = 0;
     ~FlTmpAlloc() { for (void* q : p) fl_free(q); }
-    template <class T> cudaError_t get(T*& out, size_t count) {
+    cudaError_t reserve(size_t bytes) {  // one allocation for everything that fits
         void* v = nullptr;
-        cudaError_t e = fl_malloc(&v, (count ? count : 1) * sizeof(T));
+        cudaError_t e = fl_malloc(&v, bytes);
+        if (e == cudaSuccess) { p.push_back(v); slab = (unsigned char*)v; size = bytes; used = 0; }
+        return e;
+    }
+    template <class T> cudaError_t get(T*& out, size_t count) {
+        const size_t bytes = ((count ? count : 1) * sizeof(T) + 255) & ~(size_t)255;
+        if (slab && used + bytes <= size) { out = (T*)(slab + used); used += bytes; return cudaSuccess; }
+        void* v = nullptr;
+        cudaError_t e = fl_malloc(&v, bytes);
         if (e == cudaSuccess) p.push_back(v);
         out = (T*)v;
         return e;
@@ -301,6 +340,8 @@ int device_flood_rank(fastlem_ctx* c, bool* done) {
     FlTrace tr("flood");
     FlTmpAlloc tmp;
     const size_t n1 = (size_t)n + 1;
+    // everything below comes out of one allocation: 17 bytes per slot (tree flags, two key arrays) and ~150 per site
+    FL_CK(tmp.reserve((size_t)nnz * 17 + n1 * 160 + ((size_t)1 << 20) + 2 * c->tmp_bytes));
     FlFloodG g;
     g.n = n; g.src = c->outlets[0];
     g.row_ptr = c->orig.row_ptr; g.col = c->orig.col; g.dist = c->orig.dist; g.rev = c->orig.rev;
@@ -502,6 +543,7 @@ int iterate_levels(fastlem_ctx* c, bool first, bool* changed_out) {
     const uint32_t n = c->n;
     Layout& L = L_(c);
     c->k4_valid = false;
+    FL_RC(ensure_h_offs(c));
     FL_CK(fl_memset(c->d_flags, 0, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
     FL_RC(stage_mark(c, 0));
 
@@ -562,6 +604,7 @@ int iterate_levels(fastlem_ctx* c, bool first, bool* changed_out) {
 // ------------------------------------------------------------------------------------------------
 int rebuild_layout(fastlem_ctx* c, const double* weight) {
     const uint32_t n = c->n;
+    FL_RC(ensure_h_offs(c));
     Layout& L = c->lay[c->cur];
     Layout& M = c->lay[c->cur ^ 1];
 
@@ -877,6 +920,7 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
         if (!(c->h_flags[FL_FLAG_BROKEN] & 4u)) break;
         if (attempt) return fail(c, FASTLEM_E_STATE, "flow: height bookkeeping broke (keys)");
         key_base = maxh;  // deeper than the fixed base: exact base, more key bits, the large host buffer
+        FL_RC(ensure_h_offs(c));
         hbuf = c->h_offs;
     }
     uint32_t* const hoffs = hbuf + (key_base - maxh);  // hoffs[g]: first head of height maxh - g
@@ -993,6 +1037,89 @@ int reset_layout(fastlem_ctx* c) {
         LAUNCH_N(k_rank_inverse, n, n, L.rank, c->d_rank_to_node);
     }
     c->layout_valid = true;
+    return FASTLEM_OK;
+}
+
+// every device buffer of a graph (see fastlem_ctx::slab)
+int alloc_graph_buffers(fastlem_ctx* c, uint32_t n, uint32_t nnz) {
+    const size_t n1 = (size_t)n + 1;
+    Layout* sets[3] = {&c->orig, &c->lay[0], &c->lay[1]};
+    for (Layout* S : sets) {
+        FL_CK(dalloc(c, S->row_ptr, n1));
+        FL_CK(dalloc(c, S->col, nnz));
+        FL_CK(dalloc(c, S->dist, nnz));
+        FL_CK(dalloc(c, S->rev, nnz));
+        FL_CK(dalloc(c, S->areas, n));
+        FL_CK(dalloc(c, S->erod, n));
+        FL_CK(dalloc(c, S->uplift, n));
+        FL_CK(dalloc(c, S->is_outlet, n));
+        FL_CK(dalloc(c, S->rank, n));
+    }
+    for (int k = 0; k < 2; ++k) {
+        Layout& S = c->lay[k];
+        FL_CK(dalloc(c, S.orig_of, n));
+        FL_CK(dalloc(c, S.elev, n));
+        FL_CK(dalloc(c, S.drecv, n));
+        FL_CK(dalloc(c, S.recv, n));
+        FL_CK(dalloc(c, S.cmask, n));
+        FL_CK(dalloc(c, S.lvl, n));
+    }
+    FL_CK(dalloc(c, c->d_init, n));
+    FL_CK(dalloc(c, c->d_rank_to_node, n));
+    FL_CK(dalloc(c, c->d_pd, n));
+    FL_CK(dalloc(c, c->d_pd2, n));
+    FL_CK(dalloc(c, c->d_lake_key, n));
+    FL_CK(dalloc(c, c->d_label, n));
+    FL_CK(dalloc(c, c->d_depth, n));
+    FL_CK(dalloc(c, c->d_ids, n));
+    FL_CK(dalloc(c, c->d_sorted, n));
+    FL_CK(dalloc(c, c->d_order, n));
+    FL_CK(dalloc(c, c->d_offs, (size_t)n + 2 > FL_KEY_BASE + 2 ? (size_t)n + 2 : (size_t)FL_KEY_BASE + 2));
+    FL_CK(dalloc(c, c->d_A, n));
+    FL_CK(dalloc(c, c->d_rt, n));
+    FL_CK(dalloc(c, c->d_root_of, n));
+    FL_CK(dalloc(c, c->d_heavy, n));
+    FL_CK(dalloc(c, c->d_plen, n));
+    FL_CK(dalloc(c, c->d_len_sorted, n));
+    FL_CK(dalloc(c, c->d_hrank, n));
+    FL_CK(dalloc(c, c->d_seg_head, n1));
+    FL_CK(dalloc(c, c->d_newpos, n));
+    FL_CK(dalloc(c, c->d_deg_new, n1));
+    FL_CK(dalloc(c, c->d_state, n));
+    FL_CK(dalloc(c, c->d_pre, n));
+    FL_CK(dalloc(c, c->d_post1, n));
+    FL_CK(dalloc(c, c->d_post2, n));
+    FL_CK(dalloc(c, c->d_xbuf, n));
+    FL_CK(dalloc(c, c->d_xpost, (size_t)n * FL_XPOST));
+    FL_CK(dalloc(c, c->d_hbuf, n));
+    FL_CK(dalloc(c, c->d_hgt, n));
+    FL_CK(dalloc(c, c->d_hpre, n));
+    FL_CK(dalloc(c, c->d_iota, n));
+    FL_CK(dalloc(c, c->d_parked, (size_t)n / 4 + 64));
+    FL_CK(dalloc(c, c->d_nwait, n));
+    FL_CK(dalloc(c, c->d_sg_head, n));
+    FL_CK(dalloc(c, c->d_sg_tail, n));
+    FL_CK(dalloc(c, c->d_sg_wait, n));
+    FL_CK(dalloc(c, c->d_sg_done, n));
+    FL_CK(dalloc(c, c->d_ready, (size_t)n + 65536));
+    FL_CK(dalloc(c, c->d_ticket_of, n));
+    FL_CK(dalloc(c, c->d_fdone, n));
+    FL_CK(dalloc(c, c->d_flvl, n));
+    FL_CK(dalloc(c, c->d_hsuf, n));
+    FL_CK(dalloc(c, c->d_dirty_from, n));
+    FL_CK(dalloc(c, c->d_rlist, n));
+    FL_CK(dalloc(c, c->d_slist, n));
+    FL_CK(dalloc(c, c->d_chg_node, n));
+    FL_CK(dalloc(c, c->d_chg_old, n));
+#ifdef FL_FLOW_STATS
+    FL_CK(dalloc(c, c->d_tlog, (size_t)n * 4));
+#endif
+    FL_CK(dalloc(c, c->d_flow_stats, 32));
+    FL_CK(dalloc(c, c->d_tcel, n));
+    FL_CK(dalloc(c, c->d_out_f64, n));
+    FL_CK(dalloc(c, c->d_out_u32, n));
+    FL_CK(dalloc(c, c->d_recv0, n));
+    FL_CK(dalloc(c, c->d_label0, n));
     return FASTLEM_OK;
 }
 
@@ -1147,27 +1274,18 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     c->nnz = nnz;
     c->h_row_ptr = row_ptr; c->h_col = col; c->h_dist = dist;
     const size_t n1 = (size_t)n + 1;
-    Layout* sets[3] = {&c->orig, &c->lay[0], &c->lay[1]};
-    for (Layout* S : sets) {
-        FL_CK(dalloc(c, S->row_ptr, n1));
-        FL_CK(dalloc(c, S->col, nnz));
-        FL_CK(dalloc(c, S->dist, nnz));
-        FL_CK(dalloc(c, S->rev, nnz));
-        FL_CK(dalloc(c, S->areas, n));
-        FL_CK(dalloc(c, S->erod, n));
-        FL_CK(dalloc(c, S->uplift, n));
-        FL_CK(dalloc(c, S->is_outlet, n));
-        FL_CK(dalloc(c, S->rank, n));
+    c->slab_dry = true;  // sizes first, then one allocation, then the same calls carve it up
+    c->slab_need = 0;
+    FL_RC(alloc_graph_buffers(c, n, nnz));
+    c->slab_dry = false;
+    {
+        void* v = nullptr;
+        FL_CK(fl_malloc(&v, c->slab_need));
+        c->slab = (unsigned char*)v;
+        c->slab_size = c->slab_need;
+        c->slab_used = 0;
     }
-    for (int k = 0; k < 2; ++k) {
-        Layout& S = c->lay[k];
-        FL_CK(dalloc(c, S.orig_of, n));
-        FL_CK(dalloc(c, S.elev, n));
-        FL_CK(dalloc(c, S.drecv, n));
-        FL_CK(dalloc(c, S.recv, n));
-        FL_CK(dalloc(c, S.cmask, n));
-        FL_CK(dalloc(c, S.lvl, n));
-    }
+    FL_RC(alloc_graph_buffers(c, n, nnz));
     tr.mark("layout allocations");
     FL_CK(fl_h2d(c->orig.row_ptr, row_ptr, sizeof(uint32_t) * n1, c->stream));
     if (nnz) {
@@ -1178,44 +1296,6 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     FL_CK(fl_memset(c->d_flags, 0, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
     LAUNCH_N(k_rev_slots, n, n, c->orig.row_ptr, c->orig.col, c->orig.dist, c->orig.rev, c->d_flags);
     FL_CK(fl_d2h(c->h_flags, c->d_flags, sizeof(uint32_t), c->stream));
-    FL_CK(dalloc(c, c->d_init, n));
-    FL_CK(dalloc(c, c->d_rank_to_node, n));
-    FL_CK(dalloc(c, c->d_pd, n));
-    FL_CK(dalloc(c, c->d_pd2, n));
-    FL_CK(dalloc(c, c->d_lake_key, n));
-    FL_CK(dalloc(c, c->d_label, n));
-    FL_CK(dalloc(c, c->d_depth, n));
-    FL_CK(dalloc(c, c->d_ids, n));
-    FL_CK(dalloc(c, c->d_sorted, n));
-    FL_CK(dalloc(c, c->d_order, n));
-    FL_CK(dalloc(c, c->d_offs, (size_t)n + 2 > FL_KEY_BASE + 2 ? (size_t)n + 2 : (size_t)FL_KEY_BASE + 2));
-    FL_CK(dalloc(c, c->d_A, n));
-    FL_CK(dalloc(c, c->d_rt, n));
-    FL_CK(dalloc(c, c->d_root_of, n));
-    FL_CK(dalloc(c, c->d_heavy, n));
-    FL_CK(dalloc(c, c->d_plen, n));
-    FL_CK(dalloc(c, c->d_len_sorted, n));
-    FL_CK(dalloc(c, c->d_hrank, n));
-    FL_CK(dalloc(c, c->d_seg_head, n1));
-    FL_CK(dalloc(c, c->d_newpos, n));
-    FL_CK(dalloc(c, c->d_deg_new, n1));
-    FL_CK(dalloc(c, c->d_state, n));
-    FL_CK(dalloc(c, c->d_pre, n));
-    FL_CK(dalloc(c, c->d_post1, n));
-    FL_CK(dalloc(c, c->d_post2, n));
-    FL_CK(dalloc(c, c->d_xbuf, n));
-    FL_CK(dalloc(c, c->d_xpost, (size_t)n * FL_XPOST));
-    FL_CK(dalloc(c, c->d_hbuf, n));
-    FL_CK(dalloc(c, c->d_hgt, n));
-    FL_CK(dalloc(c, c->d_hpre, n));
-    FL_CK(dalloc(c, c->d_iota, n));
-    FL_CK(dalloc(c, c->d_parked, (size_t)n / 4 + 64));
-    FL_CK(dalloc(c, c->d_nwait, n));
-    FL_CK(dalloc(c, c->d_sg_head, n));
-    FL_CK(dalloc(c, c->d_sg_tail, n));
-    FL_CK(dalloc(c, c->d_sg_wait, n));
-    FL_CK(dalloc(c, c->d_sg_done, n));
-    FL_CK(dalloc(c, c->d_ready, (size_t)n + 65536));
     FL_CK(fl_memset(c->d_ready, 0, sizeof(uint32_t) * ((size_t)n + 65536), c->stream));
 #ifndef FL_EMU
     {
@@ -1224,22 +1304,10 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
             c->incr_flow_blocks = occ * fl_sm_count();
     }
 #endif
-    FL_CK(dalloc(c, c->d_ticket_of, n));
-    FL_CK(dalloc(c, c->d_fdone, n));
-    FL_CK(dalloc(c, c->d_flvl, n));
-    FL_CK(dalloc(c, c->d_hsuf, n));
-    FL_CK(dalloc(c, c->d_dirty_from, n));
-    FL_CK(dalloc(c, c->d_rlist, n));
-    FL_CK(dalloc(c, c->d_slist, n));
-    FL_CK(dalloc(c, c->d_chg_node, n));
-    FL_CK(dalloc(c, c->d_chg_old, n));
 #ifdef FL_FLOW_STATS
-    FL_CK(dalloc(c, c->d_tlog, (size_t)n * 4));
     FL_CK(fl_memset(c->d_tlog, 0, sizeof(unsigned long long) * 4 * n, c->stream));
 #endif
-    FL_CK(dalloc(c, c->d_flow_stats, 32));
     FL_CK(fl_memset(c->d_flow_stats, 0, 32 * sizeof(unsigned long long), c->stream));
-    FL_CK(dalloc(c, c->d_tcel, n));
     c->sm_count = fl_sm_count();
     LAUNCH_N(k_iota, n, n, c->d_iota);
     c->max_degree = 0;
@@ -1247,13 +1315,6 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
         const uint32_t d = row_ptr[i + 1] - row_ptr[i];
         if (d > c->max_degree) c->max_degree = d;
     }
-    FL_CK(dalloc(c, c->d_out_f64, n));
-    FL_CK(dalloc(c, c->d_out_u32, n));
-    FL_CK(dalloc(c, c->d_recv0, n));
-    FL_CK(dalloc(c, c->d_label0, n));
-    void* ho = nullptr;
-    FL_CK(fl_malloc_host(&ho, sizeof(uint32_t) * ((size_t)n + 2)));
-    c->h_offs = (uint32_t*)ho;
     // CUB temp storage: the larger of the sort and the scan
     size_t sort_bytes = 0, scan_bytes = 0;
     FL_CK(fl_sort_pairs(nullptr, sort_bytes, c->d_depth, c->d_sorted, c->d_ids, c->d_order, n, 32, c->stream, true));
