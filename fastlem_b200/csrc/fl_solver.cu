@@ -1151,30 +1151,16 @@ int fastlem_create(fastlem_ctx** out, int device_ordinal) {
         return FASTLEM_E_CUDA;
     }
     c->stream_ok = true;
+    // one pinned block: flag words | level offsets of sweep 3 | round counts
     void* hf = nullptr;
-    if (fl_malloc_host(&hf, sizeof(uint32_t) * FL_N_FLAGS) != cudaSuccess) {
+    if (fl_malloc_host(&hf, sizeof(uint32_t) * (FL_N_FLAGS + (FL_KEY_BASE + 2) + (FL_MAX_ROUNDS + 2))) != cudaSuccess) {
         fl_stream_destroy(c->stream);
         delete c;
         return FASTLEM_E_NOMEM;
     }
     c->h_flags = (uint32_t*)hf;
-    void* hr = nullptr;
-    if (fl_malloc_host(&hr, sizeof(uint32_t) * (FL_MAX_ROUNDS + 2)) != cudaSuccess) {
-        fl_free_host(hf);
-        fl_stream_destroy(c->stream);
-        delete c;
-        return FASTLEM_E_NOMEM;
-    }
-    c->h_rounds = (uint32_t*)hr;
-    void* hk = nullptr;
-    if (fl_malloc_host(&hk, sizeof(uint32_t) * (FL_KEY_BASE + 2)) != cudaSuccess) {
-        fl_free_host(hf);
-        fl_free_host(hr);
-        fl_stream_destroy(c->stream);
-        delete c;
-        return FASTLEM_E_NOMEM;
-    }
-    c->h_offs_k = (uint32_t*)hk;
+    c->h_offs_k = c->h_flags + FL_N_FLAGS;
+    c->h_rounds = c->h_offs_k + (FL_KEY_BASE + 2);
     bool ok = true;
     for (int k = 0; k < ST_COUNT + 3; ++k) ok = ok && fl_event_create(&c->ev[k]) == cudaSuccess;
     for (int k = 0; k < 2; ++k) ok = ok && fl_event_create(&c->ev_run[k]) == cudaSuccess;
@@ -1198,8 +1184,7 @@ void fastlem_destroy(fastlem_ctx* c) {
     if (c->d_tmp) fl_free(c->d_tmp);
     if (c->d_flags) fl_free(c->d_flags);
     if (c->h_flags) fl_free_host(c->h_flags);
-    if (c->h_rounds) fl_free_host(c->h_rounds);
-    if (c->h_offs_k) fl_free_host(c->h_offs_k);
+
     for (int k = 0; k < ST_COUNT + 3; ++k)
         if (c->ev[k]) fl_event_destroy(c->ev[k]);
     for (int k = 0; k < 2; ++k)
