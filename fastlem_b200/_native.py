@@ -24,7 +24,10 @@ _STAGE_DTYPE = {0: np.uint32, 1: np.uint32, 2: np.uint32, 3: np.uint32, 4: np.ui
 SYMBOLS = ["fastlem_create", "fastlem_destroy", "fastlem_last_error", "fastlem_set_graph",
            "fastlem_set_parameters", "fastlem_generate", "fastlem_run", "fastlem_download", "fastlem_download_to_device",
            "fastlem_set_option", "fastlem_get_stats", "fastlem_debug_fetch", "fastlem_version",
-           "fastlem_host_initial_elevations"]
+           "fastlem_host_initial_elevations",
+           "fastlem_interp_create", "fastlem_interp_destroy", "fastlem_interp_last_error", "fastlem_interp_set_values",
+           "fastlem_interp_set_values_device", "fastlem_interp_set_values_from", "fastlem_interp_points",
+           "fastlem_interp_raster", "fastlem_interp_raster_device", "fastlem_interp_get_stats"]
 
 
 class Stats(ctypes.Structure):
@@ -42,6 +45,22 @@ class Stats(ctypes.Structure):
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class InterpStats(ctypes.Structure):
+    _fields_ = [("ms_setup", ctypes.c_double), ("ms_query_kernel", ctypes.c_double), ("queries", ctypes.c_uint64),
+                ("kernel_launches", ctypes.c_uint64), ("grid_x", ctypes.c_uint32), ("grid_y", ctypes.c_uint32),
+                ("grid_passes", ctypes.c_uint32), ("clockwise", ctypes.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Raster(ctypes.Structure):
+    """fastlem_raster: pixel (col,row) -> x = span_x*((col+pixel_offset)/width)+x0, y likewise."""
+    _fields_ = [("x0", ctypes.c_double), ("y0", ctypes.c_double), ("span_x", ctypes.c_double),
+                ("span_y", ctypes.c_double), ("pixel_offset", ctypes.c_double), ("width", ctypes.c_uint32),
+                ("height", ctypes.c_uint32), ("row_begin", ctypes.c_uint32), ("row_end", ctypes.c_uint32)]
 
 
 class FastlemError(RuntimeError):
@@ -81,6 +100,18 @@ def load(path=None):
     lib.fastlem_version.restype = ctypes.c_char_p
     lib.fastlem_host_initial_elevations.argtypes = [u32, f64p, f64p]
     lib.fastlem_host_initial_elevations.restype = None
+    lib.fastlem_interp_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, u32, f64p, u32, u32p, u32p]
+    lib.fastlem_interp_destroy.argtypes = [vp]
+    lib.fastlem_interp_destroy.restype = None
+    lib.fastlem_interp_last_error.argtypes = [vp]
+    lib.fastlem_interp_last_error.restype = ctypes.c_char_p
+    lib.fastlem_interp_set_values.argtypes = [vp, f64p]
+    lib.fastlem_interp_set_values_device.argtypes = [vp, vp]
+    lib.fastlem_interp_set_values_from.argtypes = [vp, vp]
+    lib.fastlem_interp_points.argtypes = [vp, u32, f64p, f64p]
+    lib.fastlem_interp_raster.argtypes = [vp, ctypes.POINTER(Raster), f64p]
+    lib.fastlem_interp_raster_device.argtypes = [vp, ctypes.POINTER(Raster), vp]
+    lib.fastlem_interp_get_stats.argtypes = [vp, ctypes.POINTER(InterpStats)]
     _libs[path] = lib
     return lib
 
@@ -187,6 +218,84 @@ class Context:
         out = np.empty(self.n, dtype=_STAGE_DTYPE[code])
         self._ck(self._lib.fastlem_debug_fetch(self._h, code, out.ctypes.data_as(ctypes.c_void_p), out.nbytes))
         return out
+
+
+class Interpolator:
+    """One fastlem_interp: natural-neighbour interpolation over a Delaunay triangulation in delaunator's layout
+    (triangles[3T], halfedges[3T] with 0xFFFFFFFF on the hull)."""
+
+    def __init__(self, sites, triangles, halfedges, device=0, lib_path=None):
+        self._lib = load(lib_path)
+        self._h = ctypes.c_void_p()
+        xy = _f64(sites).reshape(-1)
+        tri, he = _u32(triangles).reshape(-1), _u32(halfedges).reshape(-1)
+        if xy.size % 2 or tri.size % 3 or tri.size != he.size:
+            raise ValueError("Interpolator: inconsistent array sizes")
+        self.n = xy.size // 2
+        rc = self._lib.fastlem_interp_create(ctypes.byref(self._h), int(device), self.n, _p(xy, ctypes.c_double),
+                                             tri.size // 3, _p(tri, ctypes.c_uint32), _p(he, ctypes.c_uint32))
+        if rc != OK:
+            self._h = None
+            raise FastlemError(rc, "cannot create interpolator on CUDA device %d (details on stderr; no CPU fallback)"
+                               % device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fastlem_interp_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise FastlemError(rc, self._lib.fastlem_interp_last_error(self._h).decode())
+
+    def set_values(self, values):
+        v = _f64(values)
+        if v.size != self.n:
+            raise ValueError("set_values: one value per site")
+        self._ck(self._lib.fastlem_interp_set_values(self._h, _p(v, ctypes.c_double)))
+
+    def set_values_device(self, device_ptr):
+        self._ck(self._lib.fastlem_interp_set_values_device(self._h, ctypes.c_void_p(int(device_ptr))))
+
+    def set_values_from(self, ctx):
+        """Take the elevations of a solver Context that has run, device to device."""
+        self._ck(self._lib.fastlem_interp_set_values_from(self._h, ctx._h))
+
+    def points(self, points_xy, out=None):
+        q = _f64(points_xy).reshape(-1)
+        if q.size % 2:
+            raise ValueError("points: x y pairs expected")
+        nq = q.size // 2
+        out = np.empty(nq, dtype=np.float64) if out is None else out
+        self._ck(self._lib.fastlem_interp_points(self._h, nq, _p(q, ctypes.c_double), _p(out, ctypes.c_double)))
+        return out
+
+    @staticmethod
+    def raster_desc(width, height, x0, y0, span_x, span_y, pixel_offset=0.0, row_begin=0, row_end=None):
+        return Raster(float(x0), float(y0), float(span_x), float(span_y), float(pixel_offset), int(width), int(height),
+                      int(row_begin), int(height if row_end is None else row_end))
+
+    def raster(self, desc, out=None):
+        rows = desc.row_end - desc.row_begin
+        out = np.empty((max(rows, 0), desc.width), dtype=np.float64) if out is None else out
+        self._ck(self._lib.fastlem_interp_raster(self._h, ctypes.byref(desc), _p(out, ctypes.c_double)))
+        return out
+
+    def raster_device(self, desc, device_ptr):
+        self._ck(self._lib.fastlem_interp_raster_device(self._h, ctypes.byref(desc), ctypes.c_void_p(int(device_ptr))))
+
+    def stats(self):
+        s = InterpStats()
+        self._ck(self._lib.fastlem_interp_get_stats(self._h, ctypes.byref(s)))
+        return s.as_dict()
 
 
 def host_initial_elevations(base_elevation, lib_path=None):

@@ -137,6 +137,68 @@ int fastlem_debug_fetch(fastlem_ctx* ctx, int stage, void* out, size_t bytes);
  * using the `rand` crate): generator.rs:134-138, out[i] = base[i] + StdRng::seed_from_u64(0).gen::<f64>() * EPSILON. */
 void fastlem_host_initial_elevations(uint32_t n, const double* base_elevation, double* out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Terrain2D::get_elevation  
+ *
+ * Replaces TerrainInterpolator2D (reference src/models/surface/interpolator.rs:6-28), i.e. the calls
+ * `naturalneighbor::Interpolator::new(sites)` (interpolator.rs:11-15, made by
+ * TerrainModel2D::create_terrain_from_result, model.rs:62-68) and
+ * `Interpolator::interpolate(&elevations, point)` (interpolator.rs:17-27, made once per pixel through
+ * Terrain2D::get_elevation, terrain.rs:36-38, by every consumer: examples/landscape_evolution.rs:48-59,
+ * examples/terrain_generation_advanced.rs:294-315).  The interpolant is Sibson's natural-neighbour
+ * interpolation on the Delaunay triangulation of the sites; a query outside the convex hull is `None`,
+ * returned here as NaN.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct fastlem_interp fastlem_interp;
+
+/* TerrainInterpolator2D::new (interpolator.rs:11-15).  The Delaunay triangulation is handed over in
+ * delaunator's layout -- the shim calls `delaunator::triangulate(&points)` exactly as the crate does:
+ *   sites_xy   = 2 * n_sites doubles, x0 y0 x1 y1 ...
+ *   triangles  = 3 * n_triangles site indices; half-edge e = 3 t + k runs triangles[e] -> triangles[3 t + (k+1)%3]
+ *   halfedges  = 3 * n_triangles: index of the opposite half-edge, 0xFFFFFFFF (usize::MAX truncated) on the hull
+ * Either orientation is accepted as long as all triangles agree.  Checked on the device: index ranges, half-edge
+ * pairing, orientation, the Delaunay property; a violation returns FASTLEM_E_INVALID (text on stderr).
+ * The arrays are copied to HBM; the pointers need not stay valid. */
+int fastlem_interp_create(fastlem_interp** out, int device_ordinal, uint32_t n_sites, const double* sites_xy,
+                          uint32_t n_triangles, const uint32_t* triangles, const uint32_t* halfedges);
+void fastlem_interp_destroy(fastlem_interp* it);
+const char* fastlem_interp_last_error(const fastlem_interp* it);
+
+/* The `elevations` slice of interpolate() (interpolator.rs:17): n_sites doubles from the host, from a device
+ * buffer on the interpolator's device, or straight from a solver context that has run (same device; no host
+ * round trip -- Terrain2D built lazily from the generate() result). */
+int fastlem_interp_set_values(fastlem_interp* it, const double* values);
+int fastlem_interp_set_values_device(fastlem_interp* it, const double* device_values);
+int fastlem_interp_set_values_from(fastlem_interp* it, fastlem_ctx* solver);
+
+/* Terrain2D::get_elevation for a batch of points: out[i] = interpolate(values, (x_i, y_i)), NaN = None. */
+int fastlem_interp_points(fastlem_interp* it, uint32_t n_points, const double* points_xy, double* out);
+
+/* The per-pixel loop of the examples as one call.  Pixel (col, row) is queried at
+ *     x = span_x * ((col + pixel_offset) / width)  + x0
+ *     y = span_y * ((row + pixel_offset) / height) + y0
+ * (examples/landscape_evolution.rs:49-50: x0 = 0, span = bound_max, offset 0;
+ *  examples/terrain_generation_advanced.rs:296-299: offset 0.5).  Rows [row_begin, row_end) are computed --
+ * the unit of partitioning across GPUs -- and written row-major, (row_end - row_begin) * width doubles. */
+typedef struct fastlem_raster {
+    double x0, y0, span_x, span_y, pixel_offset;
+    uint32_t width, height, row_begin, row_end;
+} fastlem_raster;
+int fastlem_interp_raster(fastlem_interp* it, const fastlem_raster* raster, double* out);
+/* Same, into a caller-owned DEVICE buffer on the interpolator's device (for an NCCL gather of row blocks). */
+int fastlem_interp_raster_device(fastlem_interp* it, const fastlem_raster* raster, double* device_out);
+
+typedef struct fastlem_interp_stats {
+    double ms_setup;          /* fastlem_interp_create: uploads, circumcircles, checks, hint grid (wall clock) */
+    double ms_query_kernel;   /* device time of the last points / raster kernel, CUDA events */
+    uint64_t queries;         /* points or pixels of the last query call */
+    uint64_t kernel_launches; /* kernels of this library launched on this interpolator so far */
+    uint32_t grid_x, grid_y;  /* hint grid */
+    uint32_t grid_passes;     /* dilation passes needed to fill empty hint cells */
+    uint32_t clockwise;       /* 1 if the triangles were clockwise */
+} fastlem_interp_stats;
+int fastlem_interp_get_stats(const fastlem_interp* it, fastlem_interp_stats* out);
+
 /* Library identification: "fastlem_b200 <version> sm_100a" (or "... emu" for the test-only host build). */
 const char* fastlem_version(void);
 

@@ -1,7 +1,8 @@
 """ctypes wrapper around the CPU oracle (TEST INFRASTRUCTURE ONLY).
 
 Loads oracle/libfastlem_oracle.so (built by oracle/Makefile from fastlem_oracle.cpp, the
-single-threaded restatement of /root/reference src/lem/{generator,stream_tree,drainage_basin}.rs).
+single-threaded restatement of /root/reference src/lem/{generator,stream_tree,drainage_basin}.rs, and from
+nn_oracle.cpp, the natural-neighbour interpolation behind Terrain2D::get_elevation).
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
 """
 import ctypes
@@ -20,8 +21,8 @@ _intp = ctypes.POINTER(ctypes.c_int)
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "fastlem_oracle.cpp")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("fastlem_oracle.cpp", "nn_oracle.cpp", "Makefile")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B"], stdout=subprocess.DEVNULL)
     return _SO
 
@@ -36,6 +37,7 @@ def lib():
         _lib = ctypes.CDLL(_SO)
         _lib.fo_generate.restype = ctypes.c_uint32
         _lib.fo_iterate_once.restype = ctypes.c_int
+        _lib.fo_nn_weights.restype = ctypes.c_uint32
     return _lib
 
 
@@ -150,3 +152,25 @@ def generate(m, erodibility, uplift_rate, max_slope, outlets, initial, max_itera
                            _p(k, _f64p), _p(u, _f64p), _p(ms, _f64p), _p(outlets, _u32p),
                            ctypes.c_uint32(outlets.size), ctypes.c_uint32(mi), _p(e, _f64p))
     return e, int(it)
+
+
+# ------------------------------------------------------------------------------------------------
+# Terrain2D::get_elevation (nn_oracle.cpp)
+# ------------------------------------------------------------------------------------------------
+def nn_interpolate(sites, triangles, values, queries):
+    """terrain.rs:36-38 / interpolator.rs:17-27 for a batch of points; NaN = None."""
+    xy, tri, v, q = _f64(sites).reshape(-1), _u32(triangles).reshape(-1), _f64(values), _f64(queries).reshape(-1)
+    out = np.empty(q.size // 2, dtype=np.float64)
+    lib().fo_nn_interpolate(ctypes.c_uint32(xy.size // 2), _p(xy, _f64p), ctypes.c_uint32(tri.size // 3), _p(tri, _u32p),
+                            _p(v, _f64p), ctypes.c_uint32(out.size), _p(q, _f64p), _p(out, _f64p))
+    return out
+
+
+def nn_weights(sites, triangles, x, y, cap=256):
+    """Natural neighbours and Sibson weights of one query: (ids, weights), empty for None."""
+    xy, tri = _f64(sites).reshape(-1), _u32(triangles).reshape(-1)
+    ids = np.empty(cap, dtype=np.uint32)
+    w = np.empty(cap, dtype=np.float64)
+    k = lib().fo_nn_weights(ctypes.c_uint32(xy.size // 2), _p(xy, _f64p), ctypes.c_uint32(tri.size // 3), _p(tri, _u32p),
+                            ctypes.c_double(x), ctypes.c_double(y), ctypes.c_uint32(cap), _p(ids, _u32p), _p(w, _f64p))
+    return ids[:k].copy(), w[:k].copy()

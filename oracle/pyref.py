@@ -277,3 +277,64 @@ def generate(adj, areas, erodibility, uplift, max_slope, outlets, initial, max_i
         if not r["changed"]:
             break
     return e, it
+
+
+# ---- Terrain2D::get_elevation: Sibson's interpolant straight from its definition ----------------------
+# terrain.rs:36-38 -> interpolator.rs:17-27 -> naturalneighbor::Interpolator::interpolate (crate not vendored;
+# PARITY UNPINNED).  No triangulation, no cavity: Voronoi cells are built by clipping a large box with
+# perpendicular-bisector half-planes, so this shares nothing with nn_oracle.cpp or the device code.
+#   V(i)  = { x : |x - s_i| <= |x - s_j| for all j }          (sites only)
+#   V'(p) = { x : |x - p|   <= |x - s_j| for all j }
+#   w_i   = area(V'(p) & V(i)) / area(V'(p)),   z(p) = sum_i w_i z_i
+# Valid for queries whose new cell is bounded by the bisectors (away from the convex hull); O(n^2) per query.
+def _clip_halfplane(poly, a, b, c):
+    """Keep the part of the convex polygon `poly` with a*x + b*y <= c (Sutherland-Hodgman, one plane)."""
+    out = []
+    k = len(poly)
+    for i in range(k):
+        p, q = poly[i], poly[(i + 1) % k]
+        fp, fq = a * p[0] + b * p[1] - c, a * q[0] + b * q[1] - c
+        if fp <= 0.0:
+            out.append(p)
+        if (fp < 0.0 < fq) or (fq < 0.0 < fp):
+            t = fp / (fp - fq)
+            out.append((p[0] + t * (q[0] - p[0]), p[1] + t * (q[1] - p[1])))
+    return out
+
+
+def _bisector(p, s):
+    """Half-plane of the points at least as close to p as to s:  2 (s - p) . x <= |s|^2 - |p|^2."""
+    return 2.0 * (s[0] - p[0]), 2.0 * (s[1] - p[1]), (s[0] * s[0] + s[1] * s[1]) - (p[0] * p[0] + p[1] * p[1])
+
+
+def _poly_area(poly):
+    if len(poly) < 3:
+        return 0.0
+    o = poly[0]
+    acc = 0.0
+    for i in range(1, len(poly) - 1):
+        acc += (poly[i][0] - o[0]) * (poly[i + 1][1] - o[1]) - (poly[i][1] - o[1]) * (poly[i + 1][0] - o[0])
+    return 0.5 * acc
+
+
+def nn_interpolate(sites, values, p, box=1.0e4):
+    """Sibson interpolation of `values` at p from the definition.  Returns (z, weights dict) ."""
+    sites = [(float(x), float(y)) for x, y in sites]
+    p = (float(p[0]), float(p[1]))
+    cell = [(-box, -box), (box, -box), (box, box), (-box, box)]
+    for s in sites:
+        cell = _clip_halfplane(cell, *_bisector(p, s))
+    total = _poly_area(cell)
+    weights = {}
+    for i, s in enumerate(sites):
+        part = cell
+        for j, t in enumerate(sites):
+            if j != i:
+                part = _clip_halfplane(part, *_bisector(s, t))
+                if len(part) < 3:
+                    break
+        a = _poly_area(part)
+        if a > 0.0:
+            weights[i] = a / total
+    z = math.fsum(w * float(values[i]) for i, w in weights.items())
+    return z, weights

@@ -66,7 +66,12 @@ def check_generate(ctx, O, m, p, outlets, initial, max_iteration):
 
 
 def golden_cases():
-    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """generate() cases (nn_*.npz are the get_elevation cases)."""
+    return [p for p in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))) if not os.path.basename(p).startswith("nn_")]
+
+
+def nn_golden_cases():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "nn_*.npz")))
 
 
 def load_golden(path):

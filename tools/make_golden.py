@@ -44,8 +44,33 @@ def case(name, m, p, max_iteration=None):
     print(f"{name}: n={m['n']} iterations={iters} lakes_in_it1={first['has_lake']}")
 
 
+def nn_case(name, n_sites, seed, n_queries, bound_max=(100.0, 100.0)):
+    """Terrain2D::get_elevation: expected values from the definition-based Sibson restatement (pyref.nn_interpolate)
+    at interior queries, plus queries outside the convex hull (expected None = NaN) and on sites (expected = the
+    site's value)."""
+    m = W.delaunay_model(W.random_sites(n_sites, (0.0, 0.0), bound_max, seed=seed))
+    sites, tri, he = W.triangulation_of(m)
+    rng = np.random.default_rng(seed + 1)
+    values = 50.0 + 40.0 * W.value_noise(sites, 0.05, seed=seed, octaves=3) + rng.random(n_sites)
+    bx, by = bound_max
+    inner = np.stack([bx * (0.3 + 0.4 * rng.random(n_queries)), by * (0.3 + 0.4 * rng.random(n_queries))], axis=1)
+    expected = np.array([pyref.nn_interpolate(sites, values, q)[0] for q in inner])
+    outside = np.array([[-1.0, 50.0], [bx + 1.0, 20.0], [30.0, -0.5], [40.0, by + 2.0], [-5.0, -5.0]])
+    on_sites = sites[rng.integers(0, n_sites, 5)]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), sites=sites, triangles=tri, halfedges=he, values=values,
+                        queries=inner, expected=expected, outside=outside, on_sites=on_sites)
+    print(f"{name}: n={n_sites} triangles={tri.size // 3} queries={n_queries}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--nn-only" not in sys.argv:
+        generate_cases()
+    nn_case("nn_delaunay150", 150, 201, 40)
+    nn_case("nn_delaunay400_wide", 400, 202, 40, bound_max=(200.0, 100.0))
+
+
+def generate_cases():
     chain = dict(n=4, row_ptr=np.array([0, 1, 3, 5, 6], dtype=np.uint32), col=np.array([1, 0, 2, 1, 3, 2], dtype=np.uint32),
                  dist=np.array([1.0, 1.0, 2.0, 2.0, 0.5, 0.5]), areas=np.array([1.0, 2.0, 3.0, 4.0]),
                  default_outlets=np.array([0], dtype=np.uint32), sites=np.zeros((4, 2)))
