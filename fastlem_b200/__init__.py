@@ -9,6 +9,7 @@ Python host-side mirror of the reference's public interface for the one path thi
     models::surface::sites::Site2D                       Site2D                    (sites.rs)
     models::surface::model::TerrainModel2D (trait Model) TerrainModel2D            (model.rs:41-69, traits.rs:13-20)
     models::surface::terrain::Terrain2D                  Terrain2D                 (terrain.rs:8-39)
+    models::surface::interpolator::TerrainInterpolator2D TerrainInterpolator2D     (interpolator.rs:6-28)
     lem::generator::TerrainGenerator                     TerrainGenerator          (generator.rs:36-213)
     lem::generator::GenerationError                      GenerationError + variants (generator.rs:18-26)
 
@@ -22,7 +23,7 @@ import numpy as np
 from . import _native
 
 __all__ = ["Site2D", "TopographicalParameters", "ParameterArrays", "TerrainModel2D", "Terrain2D",
-           "TerrainGenerator", "GenerationError", "InvalidNumberOfParameters", "ParametersNotSet", "ModelNotSet"]
+           "TerrainInterpolator2D", "TerrainGenerator", "GenerationError", "InvalidNumberOfParameters", "ParametersNotSet", "ModelNotSet"]
 
 
 class GenerationError(Exception):
@@ -123,7 +124,16 @@ class ParameterArrays:
 class TerrainModel2D:
     """model.rs:18-69.  The graph is held as the CSR the C ABI takes: row i = graph.neighbors_of(i) in order."""
 
-    def __init__(self, sites, areas, row_ptr, col, dist, default_outlets):
+    def __init__(self, sites, areas, row_ptr, col, dist, default_outlets, triangles=None, halfedges=None):
+        # triangles / halfedges: the builder's Delaunay triangulation in delaunator's layout, if it is at hand; the
+        # interpolator of the resulting Terrain2D reuses it instead of triangulating a second time (SURVEY f2)
+        self._triangulation = None
+        if triangles is not None:
+            from . import triangulation as _tr
+            tri = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1)
+            he = _tr.halfedges_from_triangles(tri, len(areas)) if halfedges is None else \
+                np.ascontiguousarray(halfedges, dtype=np.uint32).reshape(-1)
+            self._triangulation = (tri, he)
         self._sites = np.ascontiguousarray(sites, dtype=np.float64).reshape(-1, 2)
         self._areas = np.ascontiguousarray(areas, dtype=np.float64)
         self._row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint32)
@@ -133,7 +143,8 @@ class TerrainModel2D:
 
     @classmethod
     def from_workload(cls, m):
-        return cls(m["sites"], m["areas"], m["row_ptr"], m["col"], m["dist"], m["default_outlets"])
+        return cls(m["sites"], m["areas"], m["row_ptr"], m["col"], m["dist"], m["default_outlets"],
+                   triangles=m.get("triangles"))
 
     def num(self):  # model.rs:42-44: graph.order()
         return self._row_ptr.size - 1
@@ -150,15 +161,73 @@ class TerrainModel2D:
     def graph(self):
         return self._row_ptr, self._col, self._dist
 
-    def create_terrain_from_result(self, elevations):  # model.rs:62-68
-        return Terrain2D(self._sites.copy(), np.array(elevations, dtype=np.float64, copy=True))
+    def create_terrain_from_result(self, elevations, device=0, lib_path=None):  # model.rs:62-68
+        sites = self._sites.copy()
+        return Terrain2D(sites, np.array(elevations, dtype=np.float64, copy=True),
+                         TerrainInterpolator2D(sites, self._triangulation, device, lib_path))
+
+
+class TerrainInterpolator2D:
+    """interpolator.rs:6-28.  `new(sites)` is lazy: the reference triangulates the sites a second time inside
+    generate() (model.rs:62-68); here the device interpolator is created on the first query, from the builder's
+    triangulation when the model carries one, else from a host Delaunay of the sites (triangulation.py)."""
+
+    def __init__(self, sites, triangulation=None, device=0, lib_path=None):
+        self._sites = np.ascontiguousarray(sites, dtype=np.float64).reshape(-1, 2)
+        self._triangulation = triangulation
+        self._device, self._lib_path = device, lib_path
+        self._native = None
+        self._values_of = None
+
+    @classmethod
+    def new(cls, sites):
+        return cls(sites)
+
+    def _handle(self, elevations):
+        if self._native is None:
+            if self._triangulation is None:
+                from . import triangulation as _tr
+                self._triangulation = _tr.delaunay(self._sites)
+            tri, he = self._triangulation
+            self._native = _native.Interpolator(self._sites, tri, he, self._device, self._lib_path)
+        if self._values_of is not elevations:
+            self._native.set_values(elevations)
+            self._values_of = elevations
+        return self._native
+
+    def interpolate(self, elevations, site):  # interpolator.rs:17-27
+        z = self._handle(elevations).points(np.array([[site.x, site.y]], dtype=np.float64))[0]
+        return None if z != z else float(z)
+
+    def interpolate_many(self, elevations, points_xy):
+        """One call for many sites: (k, 2) array -> k values, NaN where the reference returns None."""
+        return self._handle(elevations).points(points_xy)
+
+    def raster(self, elevations, width, height, x0, y0, span_x, span_y, pixel_offset=0.0, row_begin=0, row_end=None,
+               device_ptr=None):
+        h = self._handle(elevations)
+        desc = h.raster_desc(width, height, x0, y0, span_x, span_y, pixel_offset, row_begin, row_end)
+        if device_ptr is not None:
+            h.raster_device(desc, device_ptr)
+            return None
+        return h.raster(desc)
+
+    def stats(self):
+        return None if self._native is None else self._native.stats()
+
+    def close(self):
+        if self._native is not None:
+            self._native.close()
+            self._native = None
+            self._values_of = None
 
 
 class Terrain2D:
     """terrain.rs:8-39."""
 
-    def __init__(self, sites, elevations):
+    def __init__(self, sites, elevations, interpolator=None):
         self._sites, self._elevations = sites, elevations
+        self._interpolator = interpolator if interpolator is not None else TerrainInterpolator2D(sites)
 
     def sites(self):
         return self._sites
@@ -167,8 +236,19 @@ class Terrain2D:
         return self._elevations
 
     def get_elevation(self, site):
-        raise NotImplementedError("natural-neighbour interpolation (terrain.rs:36-38) is outside the generate() path; "
-                                  "see DESIGN.md, scope row f1")
+        """terrain.rs:36-38: interpolated elevation at `site`, None outside the convex hull of the sites."""
+        return self._interpolator.interpolate(self._elevations, site)
+
+    def get_elevations(self, points_xy):
+        """get_elevation for an array of points (k, 2) in one device call; NaN = None."""
+        return self._interpolator.interpolate_many(self._elevations, points_xy)
+
+    def raster(self, width, height, x0, y0, span_x, span_y, pixel_offset=0.0, row_begin=0, row_end=None,
+               device_ptr=None):
+        """The per-pixel get_elevation loop of the examples as one device call (include/fastlem_b200.h,
+        fastlem_interp_raster): rows [row_begin, row_end) of a width x height image, NaN = None."""
+        return self._interpolator.raster(self._elevations, width, height, x0, y0, span_x, span_y, pixel_offset,
+                                         row_begin, row_end, device_ptr)
 
 
 class TerrainGenerator:
@@ -228,4 +308,4 @@ class TerrainGenerator:
             elevations, it = ctx.generate(self._max_iteration)
             self.last_stats = ctx.stats()
             self.last_iterations = it
-        return model.create_terrain_from_result(elevations)  # generator.rs:212
+        return model.create_terrain_from_result(elevations, self.device, self._lib_path)  # generator.rs:212

@@ -4,6 +4,10 @@ A single terrain's receiver forest is global, so one terrain = one GPU ("replica
 (different seeds / erodibility fields / outlet masks) shards trivially: member t runs on rank t mod world,
 every rank owns one fastlem context per member it runs, there is no collective on the data path, and the
 elevations are gathered once at the end (NCCL all_gather over NVLink on GPUs, gloo in the CPU tests).
+
+The `get_elevation` raster of one terrain partitions the other way: sites, elevations and triangulation are
+replicated (every rank builds the same interpolator), the image is cut into contiguous row blocks, one per rank,
+and the blocks are gathered once at the end.
 """
 import numpy as np
 
@@ -53,4 +57,44 @@ def gather_elevations(local, n_members, n_sites, rank, world, device="cpu"):
         g = gathered[r].cpu().numpy()
         for k, t in enumerate(members_of_rank(n_members, r, world)):
             out[t] = g[k]
+    return out
+
+
+def rows_of_rank(height, rank, world):
+    """Contiguous row block [begin, end) of a `height`-row raster for `rank`: sizes differ by at most one row."""
+    base, extra = divmod(height, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def raster_partitioned(interpolator, desc_args, rank, world, device="cpu"):
+    """Every rank rasterises its own row block and all ranks end up with the full (height, width) image.
+
+    interpolator: fastlem_b200._native.Interpolator with values set (replicated on every rank)
+    desc_args   : dict(width, height, x0, y0, span_x, span_y, pixel_offset)
+    On GPUs (`device` = "cuda:k") the block is written straight into the torch tensor that NCCL gathers
+    (fastlem_interp_raster_device, no host round trip); with gloo the block goes through the host.
+    """
+    import torch
+    width, height = int(desc_args["width"]), int(desc_args["height"])
+    r0, r1 = rows_of_rank(height, rank, world)
+    max_rows = rows_of_rank(height, 0, world)[1]
+    buf = torch.zeros((max_rows, width), dtype=torch.float64, device=device)
+    desc = interpolator.raster_desc(width, height, desc_args["x0"], desc_args["y0"], desc_args["span_x"],
+                                    desc_args["span_y"], desc_args.get("pixel_offset", 0.0), r0, r1)
+    if r1 > r0:
+        if buf.is_cuda:
+            interpolator.raster_device(desc, buf.data_ptr())
+        else:
+            buf[:r1 - r0].copy_(torch.from_numpy(interpolator.raster(desc)))
+    if world == 1:
+        gathered = [buf]
+    else:
+        import torch.distributed as dist
+        gathered = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(gathered, buf)
+    out = np.empty((height, width), dtype=np.float64)
+    for r in range(world):
+        a, b = rows_of_rank(height, r, world)
+        out[a:b] = gathered[r][:b - a].cpu().numpy()
     return out

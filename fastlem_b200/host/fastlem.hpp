@@ -10,7 +10,9 @@
 //   models::surface::sites::Site2D (sites.rs)                Site2D
 //   models::surface::model::TerrainModel2D (model.rs:18-69)  TerrainModel2D (built from a finished graph; the
 //                                                            Delaunay/Lloyd builder stays outside this path)
-//   models::surface::terrain::Terrain2D (terrain.rs:8-39)    Terrain2D (get_elevation: not on this path)
+//   models::surface::terrain::Terrain2D (terrain.rs:8-39)    Terrain2D (get_elevation on the device; + raster())
+//   models::surface::interpolator::TerrainInterpolator2D     TerrainInterpolator2D (interpolator.rs:6-28; built lazily
+//                                                            from the builder's Delaunay triangulation)
 //   lem::generator::GenerationError (generator.rs:18-26)     GenerationError
 //   lem::generator::TerrainGenerator (generator.rs:36-213)   TerrainGenerator<M, T>
 //
@@ -21,7 +23,9 @@
 #include <cmath>
 #include <cstdint>
 #include <limits>
+#include <memory>
 #include <optional>
+#include <stdexcept>
 #include <string>
 #include <utility>
 #include <vector>
@@ -69,35 +73,110 @@ struct Graph {
     std::size_t order() const { return row_ptr.empty() ? 0 : row_ptr.size() - 1; }
 };
 
+// The builder's Delaunay triangulation in delaunator's layout (what `delaunator::triangulate` returns in the crate):
+// half-edge e = 3t+k runs triangles[e] -> triangles[3t+(k+1)%3]; halfedges[e] = opposite half-edge or 0xFFFFFFFF.
+struct Triangulation {
+    std::vector<std::uint32_t> triangles;
+    std::vector<std::uint32_t> halfedges;
+    bool empty() const { return triangles.empty(); }
+};
+
+// src/models/surface/interpolator.rs:6-28.  The reference triangulates the sites again inside `new`; here the
+// builder's triangulation is reused and the device interpolator is created on the first query.
+class TerrainInterpolator2D {
+  public:
+    TerrainInterpolator2D() = default;
+    TerrainInterpolator2D(const std::vector<Site2D>& sites, Triangulation tri, int device = 0)
+        : state_(std::make_shared<State>()) {
+        state_->xy.reserve(2 * sites.size());
+        for (const Site2D& s : sites) { state_->xy.push_back(s.x); state_->xy.push_back(s.y); }
+        state_->tri = std::move(tri);
+        state_->device = device;
+    }
+
+    // interpolator.rs:17-27: None outside the convex hull of the sites
+    std::optional<Elevation> interpolate(const std::vector<Elevation>& elevations, const Site2D& site) const {
+        const double q[2] = {site.x, site.y};
+        double z = 0.0;
+        check(fastlem_interp_points(handle(elevations), 1, q, &z));
+        if (z != z) return std::nullopt;
+        return z;
+    }
+
+    // rows [row_begin, row_end) of the examples' per-pixel loop in one call; NaN = None
+    std::vector<Elevation> raster(const std::vector<Elevation>& elevations, const fastlem_raster& r) const {
+        std::vector<Elevation> out((std::size_t)(r.row_end - r.row_begin) * r.width);
+        check(fastlem_interp_raster(handle(elevations), &r, out.data()));
+        return out;
+    }
+
+  private:
+    struct State {
+        std::vector<double> xy;
+        Triangulation tri;
+        int device = 0;
+        fastlem_interp* h = nullptr;
+        const double* values_of = nullptr;
+        ~State() { fastlem_interp_destroy(h); }
+    };
+    fastlem_interp* handle(const std::vector<Elevation>& elevations) const {
+        if (!state_ || state_->tri.empty())
+            throw std::runtime_error("TerrainInterpolator2D: the model carries no triangulation");
+        State& s = *state_;
+        if (!s.h) {
+            if (fastlem_interp_create(&s.h, s.device, (std::uint32_t)(s.xy.size() / 2), s.xy.data(),
+                                      (std::uint32_t)(s.tri.triangles.size() / 3), s.tri.triangles.data(),
+                                      s.tri.halfedges.data()) != FASTLEM_OK)
+                throw std::runtime_error("fastlem_interp_create failed (invalid triangulation or no CUDA device; "
+                                         "there is no CPU fallback)");
+        }
+        if (s.values_of != elevations.data()) {
+            if (elevations.size() != s.xy.size() / 2) throw std::runtime_error("interpolate: one elevation per site");
+            check(fastlem_interp_set_values(s.h, elevations.data()));
+            s.values_of = elevations.data();
+        }
+        return s.h;
+    }
+    void check(int rc) const {
+        if (rc != FASTLEM_OK) throw std::runtime_error(fastlem_interp_last_error(state_ ? state_->h : nullptr));
+    }
+    std::shared_ptr<State> state_;  // Terrain2D is Clone in the reference: copies share the device interpolator
+};
+
 // src/models/surface/terrain.rs:8-39
 class Terrain2D {
   public:
-    Terrain2D(std::vector<Site2D> sites, std::vector<Elevation> elevations)
-        : sites_(std::move(sites)), elevations_(std::move(elevations)) {}
+    Terrain2D(std::vector<Site2D> sites, std::vector<Elevation> elevations,
+              TerrainInterpolator2D interpolator = TerrainInterpolator2D())
+        : sites_(std::move(sites)), elevations_(std::move(elevations)), interpolator_(std::move(interpolator)) {}
     const std::vector<Site2D>& sites() const { return sites_; }
     const std::vector<Elevation>& elevations() const { return elevations_; }
-    // natural-neighbour interpolation is not part of the generate() path (scope row f1)
-    std::optional<Elevation> get_elevation(const Site2D&) const { return std::nullopt; }
+    // terrain.rs:36-38
+    std::optional<Elevation> get_elevation(const Site2D& site) const {
+        return interpolator_.interpolate(elevations_, site);
+    }
+    std::vector<Elevation> raster(const fastlem_raster& r) const { return interpolator_.raster(elevations_, r); }
 
   private:
     std::vector<Site2D> sites_;
     std::vector<Elevation> elevations_;
+    TerrainInterpolator2D interpolator_;
 };
 
 // src/models/surface/model.rs:18-69
 class TerrainModel2D {
   public:
     TerrainModel2D(std::vector<Site2D> sites, std::vector<Area> areas, Graph graph,
-                   std::vector<std::uint32_t> default_outlets)
+                   std::vector<std::uint32_t> default_outlets, Triangulation triangulation = Triangulation())
         : sites_(std::move(sites)), areas_(std::move(areas)), graph_(std::move(graph)),
-          default_outlets_(std::move(default_outlets)) {}
+          default_outlets_(std::move(default_outlets)), triangulation_(std::move(triangulation)) {}
     std::size_t num() const { return graph_.order(); }  // model.rs:42-44
     const std::vector<Site2D>& sites() const { return sites_; }
     const std::vector<Area>& areas() const { return areas_; }
     const std::vector<std::uint32_t>& default_outlets() const { return default_outlets_; }
     const Graph& graph() const { return graph_; }
     Terrain2D create_terrain_from_result(const std::vector<Elevation>& elevations) const {  // model.rs:62-68
-        return Terrain2D(sites_, elevations);
+        return Terrain2D(sites_, elevations, TerrainInterpolator2D(sites_, triangulation_));
     }
 
   private:
@@ -105,6 +184,7 @@ class TerrainModel2D {
     std::vector<Area> areas_;
     Graph graph_;
     std::vector<std::uint32_t> default_outlets_;
+    Triangulation triangulation_;
 };
 
 // src/lem/generator.rs:18-26 (+ DeviceError)

@@ -34,6 +34,67 @@ def _worker(rank, world, port, emu_lib, out_dir):
     dist.destroy_process_group()
 
 
+def _raster_worker(rank, world, port, emu_lib, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from fastlem_b200 import _native, ensemble
+    from tools import workloads as W
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sites, tri, he, values = _raster_inputs()
+    with _native.Interpolator(sites, tri, he, lib_path=emu_lib) as it:
+        it.set_values(values)
+        img = ensemble.raster_partitioned(it, RASTER, rank, world)
+    np.save(os.path.join(out_dir, f"raster_{rank}.npy"), img)
+    dist.destroy_process_group()
+
+
+RASTER = dict(width=45, height=37, x0=0.0, y0=0.0, span_x=100.0, span_y=100.0, pixel_offset=0.5)
+
+
+def _raster_inputs():
+    from tools import workloads as W
+    m = W.delaunay_model(W.random_sites(900, seed=8))
+    sites, tri, he = W.triangulation_of(m)
+    return sites, tri, he, 20.0 + 10.0 * W.value_noise(sites, 0.07, seed=2, octaves=3)
+
+
+def test_rows_of_rank_partition():
+    from fastlem_b200 import ensemble
+    for height in (1, 7, 37, 4096):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [ensemble.rows_of_rank(height, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == height
+            assert all(blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1 and sizes[0] == max(sizes)
+
+
+def test_raster_two_ranks_gloo(tmp_path, emu_lib, oracle):
+    """The get_elevation raster partitioned by row blocks over 2 ranks equals the single-rank image and the oracle."""
+    import torch.multiprocessing as mp
+    from fastlem_b200 import _native
+    port = 30500 + (os.getpid() % 1000)
+    mp.spawn(_raster_worker, args=(2, port, emu_lib, str(tmp_path)), nprocs=2, join=True)
+    a = np.load(tmp_path / "raster_0.npy")
+    b = np.load(tmp_path / "raster_1.npy")
+    assert np.array_equal(a, b, equal_nan=True)
+    sites, tri, he, values = _raster_inputs()
+    with _native.Interpolator(sites, tri, he, lib_path=emu_lib) as it:
+        it.set_values(values)
+        single = it.raster(it.raster_desc(RASTER["width"], RASTER["height"], 0.0, 0.0, 100.0, 100.0, 0.5))
+    assert np.array_equal(a, single, equal_nan=True)
+    cols, rows = np.meshgrid(np.arange(RASTER["width"]), np.arange(RASTER["height"]))
+    q = np.stack([100.0 * ((cols.reshape(-1) + 0.5) / RASTER["width"]),
+                  100.0 * ((rows.reshape(-1) + 0.5) / RASTER["height"])], axis=1)
+    ref = oracle.nn_interpolate(sites, tri, values, q).reshape(a.shape)
+    assert np.array_equal(np.isnan(a), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert (np.abs(a[ok] - ref[ok]) <= 1e-9 * np.maximum(1.0, np.abs(ref[ok]))).all()
+
+
 def test_members_of_rank_partition():
     from fastlem_b200 import ensemble
     for world in (1, 2, 4, 8):

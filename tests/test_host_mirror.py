@@ -62,3 +62,52 @@ def test_noise_is_the_reference_stream(emu_lib, oracle):
     from fastlem_b200 import _native
     base = np.linspace(-1.0, 1.0, 257)
     assert np.array_equal(_native.host_initial_elevations(base, emu_lib), oracle.initial_elevations(base))
+
+
+def test_get_elevation_render_loop(emu_lib, oracle):
+    """examples/landscape_evolution.rs:36-62: generate(), then get_elevation per pixel (`if let Some(e)`), against the
+    oracle's interpolation of the oracle's elevations; the one-call raster gives the same image."""
+    from tools import workloads as W
+    m = W.delaunay_model(W.random_sites(700, seed=5), lloyd=1, bound_min=(0, 0), bound_max=(100, 100))
+    model = fl.TerrainModel2D.from_workload(m)
+    num = model.num()
+    terrain = _generator(emu_lib).set_model(model).set_parameters(
+        [fl.TopographicalParameters.default() for _ in range(num)]).generate()
+    bound_max = fl.Site2D(100.0, 100.0)
+    img_width = img_height = 24
+    image = np.full((img_height, img_width), np.nan)
+    for imgx in range(img_width):
+        for imgy in range(img_height):
+            x = bound_max.x * (imgx / img_width)
+            y = bound_max.y * (imgy / img_height)
+            e = terrain.get_elevation(fl.Site2D(x, y))
+            if e is not None:
+                image[imgy, imgx] = e
+    raster = terrain.raster(img_width, img_height, 0.0, 0.0, bound_max.x, bound_max.y)
+    assert np.array_equal(image, raster, equal_nan=True)
+    sites, tri, _ = W.triangulation_of(m)
+    cols, rows = np.meshgrid(np.arange(img_width), np.arange(img_height))
+    q = np.stack([100.0 * (cols.reshape(-1) / img_width), 100.0 * (rows.reshape(-1) / img_height)], axis=1)
+    ref = oracle.nn_interpolate(sites, tri, terrain.elevations(), q).reshape(img_height, img_width)
+    assert np.array_equal(np.isnan(ref), np.isnan(raster))
+    ok = ~np.isnan(ref)
+    assert ok.sum() > 400 and np.isnan(ref[0, 0])  # the corner pixel (0, 0) lies outside the hull of random sites
+    assert (np.abs(raster[ok] - ref[ok]) <= 1e-9 * np.maximum(1.0, np.abs(ref[ok]))).all()
+    assert terrain.get_elevation(fl.Site2D(-1.0, 50.0)) is None
+
+
+def test_interpolator_triangulates_on_demand(emu_lib, oracle):
+    """TerrainInterpolator2D::new(sites) without a builder triangulation: a host Delaunay of the sites on first use."""
+    from fastlem_b200 import triangulation
+    rng = np.random.default_rng(3)
+    sites = rng.random((300, 2)) * 50.0
+    values = sites[:, 0] * 0.1 + np.sin(sites[:, 1])
+    it = fl.TerrainInterpolator2D(sites, lib_path=emu_lib)
+    assert it.stats() is None  # nothing built yet
+    q = 10.0 + rng.random((50, 2)) * 30.0
+    out = it.interpolate_many(values, q)
+    tri, he = triangulation.delaunay(sites)
+    ref = oracle.nn_interpolate(sites, tri, values, q)
+    assert (np.abs(out - ref) <= 1e-9 * np.maximum(1.0, np.abs(ref))).all()
+    assert it.interpolate(values, fl.Site2D(q[0, 0], q[0, 1])) == out[0]
+    it.close()

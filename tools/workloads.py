@@ -81,21 +81,9 @@ def _hull_cycle(pts, tri):
 
 
 def halfedges_from_triangles(tri, n):
-    """delaunator's `halfedges` for CCW triangles `tri` (T x 3): for half-edge e = 3t+k (tri[t,k] -> tri[t,(k+1)%3])
-    the index of the opposite half-edge, 0xFFFFFFFF on the hull.  (What the Rust shim gets from
-    `delaunator::triangulate`; rebuilt here because scipy reports neighbours per opposite vertex.)"""
-    tri = np.asarray(tri, dtype=np.int64)
-    frm = tri.reshape(-1)
-    to = tri[:, [1, 2, 0]].reshape(-1)
-    key = frm * np.int64(n) + to
-    rkey = to * np.int64(n) + frm
-    order = np.argsort(key, kind="stable")
-    pos = np.searchsorted(key[order], rkey)
-    pos_c = np.minimum(pos, key.size - 1)
-    hit = key[order][pos_c] == rkey
-    he = np.full(key.size, 0xFFFFFFFF, dtype=np.uint32)
-    he[hit] = order[pos_c[hit]].astype(np.uint32)
-    return he
+    """delaunator's `halfedges` (see fastlem_b200/triangulation.py)."""
+    from fastlem_b200.triangulation import halfedges_from_triangles as f
+    return f(tri, n)
 
 
 def triangulation_of(model):
