@@ -16,6 +16,7 @@
 // Deliberately written differently from the device code (fastlem_b200/csrc/fl_interp.cuh): brute-force point
 // location, visited-set BFS with the determinant in-circle predicate, explicit ordered polygons with the shoelace
 // sum about v_i, adjacency rebuilt from the triangles alone, long double arithmetic.
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -52,6 +53,7 @@ struct Mesh {
     std::vector<Pt> pts;
     std::vector<uint32_t> tri;                      // counter-clockwise after normalisation
     std::unordered_map<uint64_t, uint32_t> edge_tri;  // directed edge (a -> b) -> triangle having it
+    std::vector<uint32_t> nbr;                      // nbr[3t+k] = triangle across edge k of t (from edge_tri)
     uint64_t key(uint32_t a, uint32_t b) const { return ((uint64_t)a << 32) | b; }
     uint32_t tri_of(uint32_t a, uint32_t b) const {
         auto it = edge_tri.find(key(a, b));
@@ -71,17 +73,47 @@ Mesh build_mesh(uint32_t n, const double* xy, uint32_t nt, const uint32_t* tri) 
         if (cross(m.pts[v[0]], m.pts[v[1]], m.pts[v[2]]) < 0) { uint32_t s = v[1]; v[1] = v[2]; v[2] = s; }
         for (int k = 0; k < 3; ++k) m.edge_tri[m.key(v[k], v[(k + 1) % 3])] = t;
     }
+    m.nbr.resize(3 * (size_t)nt);
+    for (uint32_t t = 0; t < nt; ++t)
+        for (int k = 0; k < 3; ++k) m.nbr[3 * (size_t)t + k] = m.tri_of(m.tri[3 * (size_t)t + (k + 1) % 3], m.tri[3 * (size_t)t + k]);
     return m;
 }
 
+double g_mesh_seconds = 0.0;
+
+// Point location for the timed CPU baseline (bench.py): visibility walk from the previous query's triangle, the way a
+// CPU implementation scanning an image would do it.  Returns NONE when the walk leaves the hull or does not settle.
+uint32_t walk_locate(const Mesh& m, Pt p, uint32_t start) {
+    uint32_t t = start < m.nt ? start : 0;
+    for (uint32_t steps = 0; steps < 4 * m.nt + 16; ++steps) {
+        const uint32_t* v = &m.tri[3 * (size_t)t];
+        int worst = -1;
+        real wv = 0;
+        for (int k = 0; k < 3; ++k) {
+            const real o = cross(m.pts[v[k]], m.pts[v[(k + 1) % 3]], p);
+            if (o < wv) { wv = o; worst = k; }
+        }
+        if (worst < 0) return t;
+        const uint32_t t2 = m.nbr[3 * (size_t)t + worst];
+        if (t2 == 0xFFFFFFFFu) return 0xFFFFFFFFu;
+        t = t2;
+    }
+    return 0xFFFFFFFFu;
+}
+
 // weights of one query; returns false for None.  ids/w receive the natural neighbours and their weights.
-bool query(const Mesh& m, Pt p, std::vector<uint32_t>* ids, std::vector<real>* w) {
+// `hint`: null = brute-force location; else walk from *hint and store the triangle found.
+bool query(const Mesh& m, Pt p, std::vector<uint32_t>* ids, std::vector<real>* w, uint32_t* hint = nullptr) {
     ids->clear();
     w->clear();
     if (!(p.x == p.x) || !(p.y == p.y)) return false;
     // 1. brute-force location: first triangle (in index order) with p inside or on its boundary
     uint32_t t0 = 0xFFFFFFFFu;
-    for (uint32_t t = 0; t < m.nt && t0 == 0xFFFFFFFFu; ++t) {
+    if (hint) {
+        t0 = walk_locate(m, p, *hint);
+        if (t0 != 0xFFFFFFFFu) *hint = t0;
+    }
+    for (uint32_t t = 0; !hint && t < m.nt && t0 == 0xFFFFFFFFu; ++t) {
         const uint32_t* v = &m.tri[3 * (size_t)t];
         if (cross(m.pts[v[0]], m.pts[v[1]], p) >= 0 && cross(m.pts[v[1]], m.pts[v[2]], p) >= 0 &&
             cross(m.pts[v[2]], m.pts[v[0]], p) >= 0)
@@ -96,9 +128,8 @@ bool query(const Mesh& m, Pt p, std::vector<uint32_t>* ids, std::vector<real>* w
     std::vector<uint32_t> cav{t0};
     std::unordered_map<uint32_t, bool> in_cav{{t0, true}};
     for (size_t h = 0; h < cav.size(); ++h) {
-        const uint32_t* v = &m.tri[3 * (size_t)cav[h]];
         for (int k = 0; k < 3; ++k) {
-            const uint32_t t2 = m.tri_of(v[(k + 1) % 3], v[k]);
+            const uint32_t t2 = m.nbr[3 * (size_t)cav[h] + k];
             if (t2 == 0xFFFFFFFFu || in_cav.count(t2)) continue;
             const uint32_t* u = &m.tri[3 * (size_t)t2];
             const bool in = incircle(m.pts[u[0]], m.pts[u[1]], m.pts[u[2]], p) > 0;
@@ -183,6 +214,25 @@ void fo_nn_interpolate(uint32_t n, const double* xy, uint32_t nt, const uint32_t
         out[i] = (double)z;
     }
 }
+
+// Same values with walk-based point location (CPU baseline of bench.py's raster leg; consecutive queries should be
+// close to each other).  The time spent building the mesh is kept apart: fo_nn_last_mesh_seconds().
+void fo_nn_interpolate_walk(uint32_t n, const double* xy, uint32_t nt, const uint32_t* tri, const double* values,
+                            uint32_t nq, const double* qxy, double* out) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const Mesh m = build_mesh(n, xy, nt, tri);
+    g_mesh_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::vector<uint32_t> ids;
+    std::vector<real> w;
+    uint32_t hint = 0;
+    for (uint32_t i = 0; i < nq; ++i) {
+        if (!query(m, Pt{(real)qxy[2 * i], (real)qxy[2 * i + 1]}, &ids, &w, &hint)) { out[i] = std::nan(""); continue; }
+        real z = 0;
+        for (size_t k = 0; k < ids.size(); ++k) z += w[k] * (real)values[ids[k]];
+        out[i] = (double)z;
+    }
+}
+double fo_nn_last_mesh_seconds(void) { return g_mesh_seconds; }
 
 // Natural neighbours and weights of ONE query; returns their number (0 = None), at most `cap` are written.
 uint32_t fo_nn_weights(uint32_t n, const double* xy, uint32_t nt, const uint32_t* tri, double qx, double qy,

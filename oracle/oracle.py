@@ -38,6 +38,7 @@ def lib():
         _lib.fo_generate.restype = ctypes.c_uint32
         _lib.fo_iterate_once.restype = ctypes.c_int
         _lib.fo_nn_weights.restype = ctypes.c_uint32
+        _lib.fo_nn_last_mesh_seconds.restype = ctypes.c_double
     return _lib
 
 
@@ -157,11 +158,17 @@ def generate(m, erodibility, uplift_rate, max_slope, outlets, initial, max_itera
 # ------------------------------------------------------------------------------------------------
 # Terrain2D::get_elevation (nn_oracle.cpp)
 # ------------------------------------------------------------------------------------------------
-def nn_interpolate(sites, triangles, values, queries):
-    """terrain.rs:36-38 / interpolator.rs:17-27 for a batch of points; NaN = None."""
+def nn_last_mesh_seconds():
+    return float(lib().fo_nn_last_mesh_seconds())
+
+
+def nn_interpolate(sites, triangles, values, queries, walk=False):
+    """terrain.rs:36-38 / interpolator.rs:17-27 for a batch of points; NaN = None.
+    walk=True: point location by walking from the previous query's triangle instead of brute force (same values)."""
     xy, tri, v, q = _f64(sites).reshape(-1), _u32(triangles).reshape(-1), _f64(values), _f64(queries).reshape(-1)
     out = np.empty(q.size // 2, dtype=np.float64)
-    lib().fo_nn_interpolate(ctypes.c_uint32(xy.size // 2), _p(xy, _f64p), ctypes.c_uint32(tri.size // 3), _p(tri, _u32p),
+    f = lib().fo_nn_interpolate_walk if walk else lib().fo_nn_interpolate
+    f(ctypes.c_uint32(xy.size // 2), _p(xy, _f64p), ctypes.c_uint32(tri.size // 3), _p(tri, _u32p),
                             _p(v, _f64p), ctypes.c_uint32(out.size), _p(q, _f64p), _p(out, _f64p))
     return out
 

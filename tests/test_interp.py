@@ -60,6 +60,18 @@ def test_oracle_weights_are_sibson_coordinates(oracle):
         assert np.abs((w[:, None] * sites[ids]).sum(axis=0) - q).max() < 1e-10
 
 
+def test_oracle_walk_location_gives_the_same_values(oracle):
+    """The walk-located variant timed by bench.py's CPU baseline is the same interpolation."""
+    _, sites, tri, _, values = make_case(2000, 13)
+    cols, rows = np.meshgrid(np.arange(64.0), np.arange(8.0))
+    q = np.stack([100.0 * cols.reshape(-1) / 64.0, 40.0 + rows.reshape(-1)], axis=1)
+    a = oracle.nn_interpolate(sites, tri, values, q)
+    b = oracle.nn_interpolate(sites, tri, values, q, walk=True)
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and (~np.isnan(a)).sum() > 400
+    ok = ~np.isnan(a)
+    assert rel_err(b[ok], a[ok]).max() <= 1e-12
+
+
 def test_pyref_definition_matches_oracle(oracle):
     from oracle import pyref
     _, sites, tri, _, values = make_case(120, 12)
