@@ -162,6 +162,7 @@ def raster_leg(args, ctx, m, rank, world, local_rank, barrier):
     blk = torch.zeros((max_rows, size), dtype=torch.float64, device="cuda")
     gathered = [torch.empty_like(blk) for _ in range(world)] if world > 1 else None
     desc = it.raster_desc(size, size, 0.0, 0.0, 100.0, 100.0, 0.0, r0, r1)
+    torch.cuda.synchronize()  # the interpolator runs on its own stream: torch's fills of blk must have finished
 
     def step():
         it.raster_device(desc, blk.data_ptr())

@@ -84,6 +84,7 @@ def raster_partitioned(interpolator, desc_args, rank, world, device="cpu"):
                                     desc_args["span_y"], desc_args.get("pixel_offset", 0.0), r0, r1)
     if r1 > r0:
         if buf.is_cuda:
+            torch.cuda.synchronize(buf.device)  # the interpolator has its own stream: wait for torch's fill of buf
             interpolator.raster_device(desc, buf.data_ptr())
         else:
             buf[:r1 - r0].copy_(torch.from_numpy(interpolator.raster(desc)))

@@ -111,3 +111,33 @@ def test_interpolator_triangulates_on_demand(emu_lib, oracle):
     assert (np.abs(out - ref) <= 1e-9 * np.maximum(1.0, np.abs(ref))).all()
     assert it.interpolate(values, fl.Site2D(q[0, 0], q[0, 1])) == out[0]
     it.close()
+
+
+def test_advanced_example_render(emu_lib, oracle):
+    """examples/terrain_generation_advanced.rs:285-315 (two displaced get_elevation calls per pixel) through
+    examples/terrain_generation_advanced.py, against per-pixel oracle queries at the example's coordinates."""
+    import importlib.util
+    import math
+    import os
+    from scenarios import ROOT
+    from tools import workloads as W
+    spec = importlib.util.spec_from_file_location("adv", os.path.join(ROOT, "examples", "terrain_generation_advanced.py"))
+    adv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(adv)
+    size = 20
+    terrain, elevation, brightness = adv.main(1500, size, None, lib_path=emu_lib)
+    m = W.delaunay_model(W.random_sites(1500, (0.0, 0.0), (100.0, 100.0), seed=0), lloyd=1, bound_min=(0.0, 0.0),
+                         bound_max=(100.0, 100.0))
+    sites, tri, _ = W.triangulation_of(m)
+    sdx, sdy = 0.3 * math.cos(3.14 * 0.25), 0.3 * math.sin(3.14 * 0.25)
+    for imgx, imgy in ((3, 4), (10, 10), (19, 0), (0, 19), (7, 15)):
+        x = (100.0 - sdx) * ((imgx + 0.5) / size) + 0.0
+        y = (100.0 - sdy) * ((imgy + 0.5) / size) + 0.0
+        e1, e2 = oracle.nn_interpolate(sites, tri, terrain.elevations(), np.array([[x, y], [x + sdx, y + sdy]]))
+        if np.isnan(e1) or np.isnan(e2):
+            assert np.isnan(elevation[imgy, imgx]) and np.isnan(brightness[imgy, imgx])
+            continue
+        assert abs(elevation[imgy, imgx] - e1) <= 1e-9 * max(1.0, abs(e1))
+        want = 1.0 - math.sin(math.atan((e1 - e2) / 50.0))
+        assert abs(brightness[imgy, imgx] - want) <= 1e-9
+    assert np.isfinite(elevation).mean() > 0.8
