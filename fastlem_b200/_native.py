@@ -24,7 +24,7 @@ _STAGE_DTYPE = {0: np.uint32, 1: np.uint32, 2: np.uint32, 3: np.uint32, 4: np.ui
 SYMBOLS = ["fastlem_create", "fastlem_destroy", "fastlem_last_error", "fastlem_set_graph",
            "fastlem_set_parameters", "fastlem_generate", "fastlem_run", "fastlem_download", "fastlem_download_to_device",
            "fastlem_set_option", "fastlem_get_stats", "fastlem_debug_fetch", "fastlem_version",
-           "fastlem_host_initial_elevations",
+           "fastlem_host_initial_elevations", "fastlem_host_graph_from_triangles",
            "fastlem_interp_create", "fastlem_interp_destroy", "fastlem_interp_last_error", "fastlem_interp_set_values",
            "fastlem_interp_set_values_device", "fastlem_interp_set_values_from", "fastlem_interp_points",
            "fastlem_interp_raster", "fastlem_interp_raster_device", "fastlem_interp_get_stats"]
@@ -100,6 +100,8 @@ def load(path=None):
     lib.fastlem_version.restype = ctypes.c_char_p
     lib.fastlem_host_initial_elevations.argtypes = [u32, f64p, f64p]
     lib.fastlem_host_initial_elevations.restype = None
+    lib.fastlem_host_graph_from_triangles.argtypes = [u32, f64p, u32, u32p, u32p, u32p, f64p, ctypes.c_uint64,
+                                                      ctypes.POINTER(ctypes.c_uint64)]
     lib.fastlem_interp_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, u32, f64p, u32, u32p, u32p]
     lib.fastlem_interp_destroy.argtypes = [vp]
     lib.fastlem_interp_destroy.restype = None
@@ -304,3 +306,25 @@ def host_initial_elevations(base_elevation, lib_path=None):
     out = np.empty_like(base)
     load(lib_path).fastlem_host_initial_elevations(base.size, _p(base, ctypes.c_double), _p(out, ctypes.c_double))
     return out
+
+
+def host_graph_from_triangles(sites, triangles, lib_path=None):
+    """builder.rs:252-268 on the host: (row_ptr, col, dist) in the boundary format of set_graph, rows in
+    neighbors_of order, from the builder's triangle array (3T site indices)."""
+    lib = load(lib_path)
+    xy, tri = _f64(sites).reshape(-1), _u32(triangles).reshape(-1)
+    n, nt = xy.size // 2, tri.size // 3
+    row_ptr = np.empty(n + 1, dtype=np.uint32)
+    nnz = ctypes.c_uint64(0)
+    rc = lib.fastlem_host_graph_from_triangles(n, _p(xy, ctypes.c_double), nt, _p(tri, ctypes.c_uint32),
+                                               _p(row_ptr, ctypes.c_uint32), None, None, 0, ctypes.byref(nnz))
+    if rc != OK:
+        raise FastlemError(rc, "graph_from_triangles: invalid triangulation")
+    col = np.empty(nnz.value, dtype=np.uint32)
+    dist = np.empty(nnz.value, dtype=np.float64)
+    rc = lib.fastlem_host_graph_from_triangles(n, _p(xy, ctypes.c_double), nt, _p(tri, ctypes.c_uint32),
+                                               _p(row_ptr, ctypes.c_uint32), _p(col, ctypes.c_uint32),
+                                               _p(dist, ctypes.c_double), nnz.value, ctypes.byref(nnz))
+    if rc != OK:
+        raise FastlemError(rc, "graph_from_triangles failed")
+    return row_ptr, col, dist

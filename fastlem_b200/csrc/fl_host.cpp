@@ -6,8 +6,10 @@
 //   rng = StdRng::seed_from_u64(0); elevations[i] = base[i] + rng.gen::<f64>() * f64::EPSILON
 // StdRng (rand 0.8.5) is ChaCha with 12 rounds; seed_from_u64 (rand_core 0.6) expands the u64 with
 // a PCG32 generator; gen::<f64>() keeps the top 53 bits of next_u64().
+#include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <vector>
 
 #include "../../include/fastlem_b200.h"
 
@@ -77,4 +79,46 @@ extern "C" void fastlem_host_initial_elevations(uint32_t n, const double* base_e
         double u = (double)(rng.next_u64() >> 11) * scale;
         out[i] = base_elevation[i] + u * eps;
     }
+}
+
+// The graph build of TerrainModel2DBulider::build (reference src/models/surface/builder.rs:252-268), straight into the
+// boundary format of fastlem_set_graph: for every triangle (a, b, c) of the builder's triangulation, in order, the
+// half-edges a->b, b->c, c->a with from < to become edges; add_edge(u, v, w) appends (v, w) to u's list and (u, w) to
+// v's list (terrain-graph), w = Site2D::distance (sites.rs:27-29).  Row i of the CSR is therefore
+// graph.neighbors_of(i) in iteration order, without building the Vec<Vec<..>> graph and walking it again.
+extern "C" int fastlem_host_graph_from_triangles(uint32_t n_sites, const double* sites_xy, uint32_t n_triangles,
+                                                 const uint32_t* triangles, uint32_t* row_ptr, uint32_t* col,
+                                                 double* dist, uint64_t capacity, uint64_t* nnz_out) {
+    if ((n_sites && !sites_xy) || (n_triangles && !triangles) || !row_ptr) return FASTLEM_E_INVALID;
+    // pass 1: degrees
+    for (uint32_t i = 0; i <= n_sites; ++i) row_ptr[i] = 0;
+    uint64_t nnz = 0;
+    for (uint32_t t = 0; t < n_triangles; ++t) {
+        const uint32_t* v = triangles + 3 * (size_t)t;
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t a = v[k], b = v[(k + 1) % 3];
+            if (a >= n_sites || b >= n_sites) return FASTLEM_E_INVALID;
+            if (a < b) { ++row_ptr[a + 1]; ++row_ptr[b + 1]; nnz += 2; }
+        }
+    }
+    if (nnz >= 0xFFFFFFFFull) return FASTLEM_E_INVALID;  // CSR offsets are uint32
+    if (nnz_out) *nnz_out = nnz;
+    for (uint32_t i = 0; i < n_sites; ++i) row_ptr[i + 1] += row_ptr[i];
+    if (!col && !dist) return FASTLEM_OK;  // size query
+    if (!col || !dist || capacity < nnz) return FASTLEM_E_INVALID;
+    // pass 2: fill in insertion order
+    std::vector<uint32_t> cursor(row_ptr, row_ptr + n_sites);
+    for (uint32_t t = 0; t < n_triangles; ++t) {
+        const uint32_t* v = triangles + 3 * (size_t)t;
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t a = v[k], b = v[(k + 1) % 3];
+            if (!(a < b)) continue;
+            const double dx = sites_xy[2 * (size_t)a] - sites_xy[2 * (size_t)b];
+            const double dy = sites_xy[2 * (size_t)a + 1] - sites_xy[2 * (size_t)b + 1];
+            const double w = std::sqrt(dx * dx + dy * dy);
+            col[cursor[a]] = b; dist[cursor[a]++] = w;
+            col[cursor[b]] = a; dist[cursor[b]++] = w;
+        }
+    }
+    return FASTLEM_OK;
 }

@@ -137,6 +137,17 @@ int fastlem_debug_fetch(fastlem_ctx* ctx, int stage, void* out, size_t bytes);
  * using the `rand` crate): generator.rs:134-138, out[i] = base[i] + StdRng::seed_from_u64(0).gen::<f64>() * EPSILON. */
 void fastlem_host_initial_elevations(uint32_t n, const double* base_elevation, double* out);
 
+/* Host utility: the graph build of TerrainModel2DBulider::build, builder.rs:252-268, written
+ * straight into the boundary format of fastlem_set_graph -- for every triangle (a, b, c) of the builder's
+ * triangulation, in order, the half-edges a->b, b->c, c->a with from < to become edges of length
+ * Site2D::distance (sites.rs:27-29), appended to both endpoints' rows (terrain-graph's add_edge).  The shim calls it on
+ * `voronoi.triangulation().triangles` instead of building the Vec<Vec<..>> graph and re-walking neighbors_of.
+ * Two calls: with col = dist = NULL it fills row_ptr (n_sites + 1) and *nnz_out; with buffers of `capacity` >= nnz
+ * entries it fills everything.  Pure host code, no device needed. */
+int fastlem_host_graph_from_triangles(uint32_t n_sites, const double* sites_xy, uint32_t n_triangles,
+                                      const uint32_t* triangles, uint32_t* row_ptr, uint32_t* col, double* dist,
+                                      uint64_t capacity, uint64_t* nnz_out);
+
 /* ------------------------------------------------------------------------------------------------
  * Terrain2D::get_elevation  
  *

@@ -128,3 +128,23 @@ def test_non_simple_graphs_are_rejected(emu_lib):
                 ctx.set_graph(g["row_ptr"], g["col"], g["dist"], np.ones(3))
             assert ei.value.code == _native.E_INVALID, what
             assert what.split()[0] in str(ei.value), what
+
+
+def test_host_graph_from_triangles_matches_builder_rule(product_lib):
+    """fastlem_host_graph_from_triangles (scope row f4) = builder.rs:252-268: edge filter from < to per half-edge in
+    triangle order, add_edge appends to both rows, Euclidean lengths -- against the numpy restatement in
+    tools/workloads.py, bit for bit; pure host code, so it runs from the product library without a device."""
+    from fastlem_b200 import _native
+    from tools import workloads as W
+    for n, seed in ((4, 1), (300, 2), (20000, 3)):
+        m = W.delaunay_model(W.random_sites(n, seed=seed))
+        rp, col, dist = _native.host_graph_from_triangles(m["sites"], m["triangles"].reshape(-1), product_lib)
+        assert np.array_equal(rp, m["row_ptr"]) and np.array_equal(col, m["col"]) and np.array_equal(dist, m["dist"])
+    # hand-made: two triangles (0,1,2), (2,1,3): half-edges 0->1, 1->2 | 1->3 are kept (2->0, 2->1, 3->2 are not)
+    sites = np.array([[0.0, 0.0], [3.0, 0.0], [0.0, 4.0], [3.0, 4.0]])
+    rp, col, dist = _native.host_graph_from_triangles(sites, np.array([0, 1, 2, 2, 1, 3], dtype=np.uint32), product_lib)
+    assert rp.tolist() == [0, 1, 4, 5, 6]
+    assert col.tolist() == [1, 0, 2, 3, 1, 1]
+    assert dist.tolist() == [3.0, 3.0, 5.0, 4.0, 5.0, 4.0]
+    with pytest.raises(_native.FastlemError):
+        _native.host_graph_from_triangles(sites, np.array([0, 1, 7], dtype=np.uint32), product_lib)

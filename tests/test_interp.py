@@ -243,7 +243,31 @@ def check_values_from_solver(lib, O):
     assert rel_err(np.array([a[32, 32], a[48, 8]]), ref).max() <= NN_TOL
 
 
+def check_cocircular_lattice(lib, O):
+    """Regular grid sites: four cocircular sites per cell (degenerate Delaunay, coincident Voronoi vertices), queries on
+    grid lines, cell centres (on circumcircles), sites and hull edges."""
+    from fastlem_b200 import _native, triangulation
+    gx, gy = np.meshgrid(np.arange(30.0), np.arange(20.0))
+    sites = np.stack([gx.reshape(-1) * 3.0, gy.reshape(-1) * 5.0], axis=1)
+    tri, he = triangulation.delaunay(sites)
+    rng = np.random.default_rng(0)
+    values = rng.random(sites.shape[0]) * 10.0
+    q = np.concatenate([np.stack([rng.random(3000) * 87.0, rng.random(3000) * 95.0], axis=1),
+                        np.stack([np.repeat(np.arange(0.0, 87.0, 1.5), 10), np.tile(np.arange(0.0, 95.0, 9.5), 58)], axis=1)])
+    with _native.Interpolator(sites, tri, he, lib_path=lib) as it:
+        it.set_values(values)
+        out = it.points(q)
+    ref = O.nn_interpolate(sites, tri, values, q)
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert ok.sum() > 3000 and rel_err(out[ok], ref[ok]).max() <= NN_TOL
+
+
 # ---- CPU tier: emulation build -------------------------------------------------------------------
+def test_emu_cocircular_lattice(oracle, emu_lib):
+    check_cocircular_lattice(emu_lib, oracle)
+
+
 @pytest.mark.parametrize("path", helpers.nn_golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
 def test_emu_matches_golden(emu_lib, path):
     check_golden(emu_lib, path)
@@ -313,6 +337,11 @@ def test_gpu_matches_golden(gpu_lib, path):
                                                  (20000, 5, (100.0, 100.0), 1)])
 def test_gpu_matches_oracle(oracle, gpu_lib, n, seed, bound, lloyd):
     check_against_oracle(gpu_lib, oracle, n, seed, 3000, bound, lloyd)
+
+
+@pytest.mark.gpu
+def test_gpu_cocircular_lattice(oracle, gpu_lib):
+    check_cocircular_lattice(gpu_lib, oracle)
 
 
 @pytest.mark.gpu
