@@ -263,7 +263,37 @@ def check_cocircular_lattice(lib, O):
     assert ok.sum() > 3000 and rel_err(out[ok], ref[ok]).max() <= NN_TOL
 
 
+def check_sites_on_a_circle(lib, O):
+    """All sites on one circle: every triangle shares the circumcircle, the cavity of the centre is the whole
+    triangulation and the interpolant at the centre is the mean.  Beyond FLI_MAX_CAVITY (512) triangles the call fails
+    loudly instead of returning a truncated sum."""
+    from fastlem_b200 import _native, triangulation
+    q = np.array([[50.0, 50.0], [55.0, 48.0]])
+    for n in (12, 200):
+        th = np.linspace(0.0, 2.0 * np.pi, n, endpoint=False)
+        sites = np.stack([50.0 + 30.0 * np.cos(th), 50.0 + 30.0 * np.sin(th)], axis=1)
+        tri, he = triangulation.delaunay(sites)
+        values = np.random.default_rng(n).random(n) * 10.0
+        with _native.Interpolator(sites, tri, he, lib_path=lib) as it:
+            it.set_values(values)
+            out = it.points(q)
+        assert abs(out[0] - values.mean()) < 1e-9
+        assert rel_err(out, O.nn_interpolate(sites, tri, values, q)).max() <= NN_TOL
+    th = np.linspace(0.0, 2.0 * np.pi, 700, endpoint=False)
+    sites = np.stack([50.0 + 30.0 * np.cos(th), 50.0 + 30.0 * np.sin(th)], axis=1)
+    tri, he = triangulation.delaunay(sites)
+    with _native.Interpolator(sites, tri, he, lib_path=lib) as it:
+        it.set_values(np.zeros(700))
+        with pytest.raises(_native.FastlemError) as e:
+            it.points(q)
+        assert e.value.code == _native.E_INVALID
+
+
 # ---- CPU tier: emulation build -------------------------------------------------------------------
+def test_emu_sites_on_a_circle(oracle, emu_lib):
+    check_sites_on_a_circle(emu_lib, oracle)
+
+
 def test_emu_cocircular_lattice(oracle, emu_lib):
     check_cocircular_lattice(emu_lib, oracle)
 
@@ -337,6 +367,11 @@ def test_gpu_matches_golden(gpu_lib, path):
                                                  (20000, 5, (100.0, 100.0), 1)])
 def test_gpu_matches_oracle(oracle, gpu_lib, n, seed, bound, lloyd):
     check_against_oracle(gpu_lib, oracle, n, seed, 3000, bound, lloyd)
+
+
+@pytest.mark.gpu
+def test_gpu_sites_on_a_circle(oracle, gpu_lib):
+    check_sites_on_a_circle(gpu_lib, oracle)
 
 
 @pytest.mark.gpu
