@@ -24,6 +24,7 @@ struct fastlem_interp {
     FliTri* d_tri = nullptr;
     FliNbr* d_nbr = nullptr;
     FliCirc* d_circ = nullptr;
+    FliGeo* d_geo = nullptr;  // FLI_DENORM builds only
     uint32_t* d_cell = nullptr;
     uint32_t* d_cell2 = nullptr;
     double* d_value = nullptr;
@@ -89,6 +90,7 @@ FliModel model_of(const fastlem_interp* c) {
     M.tri = c->d_tri;
     M.nbr = c->d_nbr;
     M.circ = c->d_circ;
+    M.geo = c->d_geo;
     M.cell = c->d_cell;
     M.value = c->d_value;
     M.grid = c->grid;
@@ -160,7 +162,7 @@ extern "C" {
 void fastlem_interp_destroy(fastlem_interp* c) {
     if (!c) return;
     fl_set_device(c->device);
-    void* ptrs[] = {c->d_site, c->d_tri, c->d_nbr, c->d_circ, c->d_cell, c->d_cell2, c->d_value, c->d_flags, c->d_out,
+    void* ptrs[] = {c->d_site, c->d_tri, c->d_nbr, c->d_circ, c->d_geo, c->d_cell, c->d_cell2, c->d_value, c->d_flags, c->d_out,
                     c->d_query};
     for (void* p : ptrs)
         if (p) fl_free(p);
@@ -185,6 +187,9 @@ static int interp_setup(fastlem_interp* c, const double* sites_xy, const uint32_
     FLI_CK(ialloc(c->d_tri, nt));
     FLI_CK(ialloc(c->d_nbr, nt));
     FLI_CK(ialloc(c->d_circ, nt));
+#if FLI_DENORM
+    FLI_CK(ialloc(c->d_geo, nt));
+#endif
     FLI_CK(ialloc(c->d_value, n));
     // the raw delaunator arrays are only needed by k_nn_prepare
     uint32_t *d_triangles = nullptr, *d_halfedges = nullptr;
@@ -200,7 +205,7 @@ static int interp_setup(fastlem_interp* c, const double* sites_xy, const uint32_
         if (e != cudaSuccess) { rc = fail(c, FASTLEM_E_CUDA, std::string("upload: ") + cudaGetErrorString(e)); break; }
         if (nt) {
             FL_LAUNCH(k_nn_prepare, blocks_for(nt), 256, c->stream, n, nt, c->d_site, d_triangles, d_halfedges, c->d_tri,
-                      c->d_nbr, c->d_circ, c->d_flags);
+                      c->d_nbr, c->d_circ, c->d_geo, c->d_flags);
             c->stats.kernel_launches++;
         }
         rc = read_flags(c);

@@ -26,7 +26,39 @@
 #include "fl_rt.h"
 
 #define FLI_NONE 0xFFFFFFFFu
+// Build-time variants of the query kernel, kept for A/B runs on the device (tools/ab_raster.py).  The defaults are the
+// fastest combination measured on a B200 (profiles/r1c_ab_raster*.txt: 4096^2 pixels over 1M sites, 2.83 ms with
+// everything off -> 2.02 ms):
+//   FLI_MINBLOCKS n : __launch_bounds__(256, n) on the query kernels (0 = ptxas' choice: 80 registers, 3 CTAs per SM;
+//                     4 = 64 registers with ~100 B of spills, +12 %; 5 and 6 lose to their spills)
+//   FLI_RECIP 1     : one reciprocal per (p, boundary edge) circumcentre instead of two divisions (+12 %)
+//   FLI_UNIFIED 1   : interior and boundary edges share the code of the first term (+6 % on top of FLI_RECIP)
+//   FLI_WARP_8X4 1  : raster lanes cover 8 x 4 pixels instead of 16 x 2 (+2 %)
+#ifndef FLI_MINBLOCKS
+#define FLI_MINBLOCKS 4
+#endif
+#ifndef FLI_RECIP
+#define FLI_RECIP 1
+#endif
+#ifndef FLI_UNIFIED
+#define FLI_UNIFIED 1
+#endif
+#ifndef FLI_WARP_8X4
+#define FLI_WARP_8X4 1
+#endif
+//   FLI_DENORM 1    : vertex coordinates stored per triangle (48 B more per triangle): the loads of a triangle's record
+//                     no longer wait for its vertex ids (+3 %)
+#ifndef FLI_DENORM
+#define FLI_DENORM 1
+#endif
+#if FLI_MINBLOCKS > 0 && !defined(FL_EMU)
+#define FLI_QUERY_BOUNDS __launch_bounds__(256, FLI_MINBLOCKS)
+#else
+#define FLI_QUERY_BOUNDS __launch_bounds__(256)
+#endif
+#ifndef FLI_STACK
 #define FLI_STACK 48      // depth-first stack of the cavity walk (pending triangles)
+#endif
 #define FLI_MAX_CAVITY 512  // triangles visited per query before the walk is declared broken
 
 // flag words
@@ -38,6 +70,7 @@ struct alignas(16) FliPt { double x, y; };
 struct alignas(16) FliTri { uint32_t v[3]; uint32_t pad; };   // vertices; edge k runs v[k] -> v[(k+1)%3]
 struct alignas(16) FliNbr { uint32_t t[3]; uint32_t pad; };   // triangle across edge k, FLI_NONE on the hull
 struct alignas(16) FliCirc { double x, y, r2, pad; };         // circumcentre and squared circumradius
+struct alignas(16) FliGeo { FliPt p[3]; };                    // FLI_DENORM: the three vertices' coordinates
 
 struct FliGrid {
     double x0, y0, inv_cell_x, inv_cell_y;
@@ -65,6 +98,22 @@ __device__ __forceinline__ bool fli_circumcentre(double ax, double ay, double bx
     return d != 0.0;
 }
 
+// circumcentre of (p, a, b) relative to p for the query kernels
+__device__ __forceinline__ bool fli_circumcentre_q(double ax, double ay, double bx, double by, double cx, double cy,
+                                                   double* ux, double* uy) {
+#if FLI_RECIP
+    const double ex = bx - ax, ey = by - ay, fx = cx - ax, fy = cy - ay;
+    const double d = 2.0 * (ex * fy - ey * fx);
+    const double e2 = ex * ex + ey * ey, f2 = fx * fx + fy * fy;
+    const double inv = 1.0 / d;
+    *ux = (fy * e2 - ey * f2) * inv;
+    *uy = (ex * f2 - fx * e2) * inv;
+    return d != 0.0;
+#else
+    return fli_circumcentre(ax, ay, bx, by, cx, cy, ux, uy);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // set-up kernels (once per triangulation)
 // ------------------------------------------------------------------------------------------------
@@ -74,7 +123,7 @@ __global__ void __launch_bounds__(256) k_nn_prepare(uint32_t n_sites, uint32_t n
                                                     const uint32_t* __restrict__ triangles,
                                                     const uint32_t* __restrict__ halfedges, FliTri* __restrict__ tri,
                                                     FliNbr* __restrict__ nbr, FliCirc* __restrict__ circ,
-                                                    uint32_t* __restrict__ flags) {
+                                                    FliGeo* __restrict__ geo, uint32_t* __restrict__ flags) {
     const uint32_t t = FLI_TID;
     if (t >= n_tri) return;
     FliTri T;
@@ -110,6 +159,11 @@ __global__ void __launch_bounds__(256) k_nn_prepare(uint32_t n_sites, uint32_t n
         return;
     }
     const FliPt a = site[T.v[0]], b = site[T.v[1]], c = site[T.v[2]];
+    if (geo) {
+        FliGeo G;
+        G.p[0] = a; G.p[1] = b; G.p[2] = c;
+        geo[t] = G;
+    }
     const double o = fli_cross(b.x - a.x, b.y - a.y, c.x - a.x, c.y - a.y);
     if (o > 0.0) atomicOr(&flags[FLI_F_POS], 1u);
     else if (o < 0.0) atomicOr(&flags[FLI_F_NEG], 1u);
@@ -198,6 +252,7 @@ struct FliModel {
     const FliTri* tri;
     const FliNbr* nbr;
     const FliCirc* circ;
+    const FliGeo* geo;  // FLI_DENORM only
     const uint32_t* cell;
     const double* value;
     FliGrid grid;
@@ -220,9 +275,13 @@ __device__ __forceinline__ double fli_query(const FliModel& M, const double px, 
     for (;;) {
         T = M.tri[t];
         N = M.nbr[t];
+#if FLI_DENORM
+        { const FliGeo G = M.geo[t]; P[0] = G.p[0]; P[1] = G.p[1]; P[2] = G.p[2]; }
+#else
         P[0] = M.site[T.v[0]];
         P[1] = M.site[T.v[1]];
         P[2] = M.site[T.v[2]];
+#endif
         double worst = 0.0;
         int kw = -1;
         for (int k = 0; k < 3; ++k) {
@@ -271,6 +330,30 @@ __device__ __forceinline__ double fli_query(const FliModel& M, const double px, 
                 }
             }
             const double max_ = 0.5 * (px + a.x), may = 0.5 * (py + a.y);
+#if FLI_UNIFIED
+            // X = the other end of the Voronoi edge piece that starts at C: the neighbour's circumcentre (interior edge)
+            // or g = circumcentre of (p, a, b) (boundary edge of the cavity)
+            double Xx = C2.x, Xy = C2.y;
+            if (!inside) {
+                double ux, uy;
+                if (!fli_circumcentre_q(px, py, a.x, a.y, b.x, b.y, &ux, &uy)) {
+                    const double ex = b.x - a.x, ey = b.y - a.y;
+                    const double s = ((px - a.x) * ex + (py - a.y) * ey) / (ex * ex + ey * ey);
+                    return M.value[T.v[k]] + s * (M.value[T.v[k1]] - M.value[T.v[k]]);
+                }
+                Xx = px + ux;
+                Xy = py + uy;
+            }
+            const double ta = fli_cross(Xx - max_, Xy - may, C.x - max_, C.y - may);
+            num += ta * M.value[T.v[k]];
+            den += ta;
+            if (!inside) {
+                const double mbx = 0.5 * (px + b.x), mby = 0.5 * (py + b.y);
+                const double tb = fli_cross(C.x - mbx, C.y - mby, Xx - mbx, Xy - mby);
+                num += tb * M.value[T.v[k1]];
+                den += tb;
+            }
+#else
             if (inside) {
                 // interior edge a -> b (t on its left, t2 on its right): around a, t2 precedes t
                 const double term = fli_cross(C2.x - max_, C2.y - may, C.x - max_, C.y - may);
@@ -279,7 +362,7 @@ __device__ __forceinline__ double fli_query(const FliModel& M, const double px, 
             } else {
                 // boundary edge of the cavity: t is the first triangle of a's fan and the last of b's
                 double ux, uy;
-                if (!fli_circumcentre(px, py, a.x, a.y, b.x, b.y, &ux, &uy)) {
+                if (!fli_circumcentre_q(px, py, a.x, a.y, b.x, b.y, &ux, &uy)) {
                     // p on the line through a, b: only possible on a hull edge -> linear along the edge
                     const double ex = b.x - a.x, ey = b.y - a.y;
                     const double s = ((px - a.x) * ex + (py - a.y) * ey) / (ex * ex + ey * ey);
@@ -294,6 +377,7 @@ __device__ __forceinline__ double fli_query(const FliModel& M, const double px, 
                 num += tb * M.value[T.v[k1]];
                 den += tb;
             }
+#endif
         }
         if (sp == 0) break;
         if (++visited > FLI_MAX_CAVITY) {
@@ -305,15 +389,19 @@ __device__ __forceinline__ double fli_query(const FliModel& M, const double px, 
         from = st_from[sp];
         T = M.tri[t];
         N = M.nbr[t];
+#if FLI_DENORM
+        { const FliGeo G = M.geo[t]; P[0] = G.p[0]; P[1] = G.p[1]; P[2] = G.p[2]; }
+#else
         P[0] = M.site[T.v[0]];
         P[1] = M.site[T.v[1]];
         P[2] = M.site[T.v[2]];
+#endif
     }
     return num / den;
 }
 
 // arbitrary points (Terrain2D::get_elevation, one call per point in the reference)
-__global__ void __launch_bounds__(256) k_nn_points(FliModel M, uint32_t nq, const FliPt* __restrict__ q,
+__global__ void FLI_QUERY_BOUNDS k_nn_points(FliModel M, uint32_t nq, const FliPt* __restrict__ q,
                                                    double* __restrict__ out, uint32_t* __restrict__ flags) {
     const uint32_t i = FLI_TID;
     if (i >= nq) return;
@@ -329,12 +417,19 @@ struct FliRaster {
     uint32_t width, height, row_begin, row_end;
 };
 
-__global__ void __launch_bounds__(256) k_nn_raster(FliModel M, FliRaster R, double* __restrict__ out,
+__global__ void FLI_QUERY_BOUNDS k_nn_raster(FliModel M, FliRaster R, double* __restrict__ out,
                                                    uint32_t* __restrict__ flags) {
     const uint32_t tiles_x = (R.width + 15u) / 16u;
     const uint32_t tile = blockIdx.x;
-    const uint32_t col = (tile % tiles_x) * 16u + (threadIdx.x & 15u);
-    const uint32_t row = R.row_begin + (tile / tiles_x) * 16u + (threadIdx.x >> 4);
+#if FLI_WARP_8X4
+    // lanes 0..31 of a warp: 8 columns x 4 rows; warps 0..7 of the CTA: 2 x 4 such blocks
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t lx = (warp & 1u) * 8u + (lane & 7u), ly = (warp >> 1) * 4u + (lane >> 3);
+#else
+    const uint32_t lx = threadIdx.x & 15u, ly = threadIdx.x >> 4;
+#endif
+    const uint32_t col = (tile % tiles_x) * 16u + lx;
+    const uint32_t row = R.row_begin + (tile / tiles_x) * 16u + ly;
     if (col >= R.width || row >= R.row_end) return;
     const double x = R.span_x * (((double)col + R.offset) / (double)R.width) + R.x0;
     const double y = R.span_y * (((double)row + R.offset) / (double)R.height) + R.y0;
