@@ -101,3 +101,37 @@ def check_against_golden(ctx, path):
     assert it == int(g["iterations"])
     assert_close(e, g["final"], "golden final elevations")
     assert np.array_equal(e, g["final"], equal_nan=True), "golden final elevations (bit-exact)"
+
+
+def check_converged_properties(ctx, O, m, p, outlets, initial, first_iterations=3):
+    """Size-independent checks for workloads the oracle cannot run to convergence: the first iterations against the
+    oracle, then properties of the converged device result (determinism, a forest draining to the outlets, elevations
+    increasing upstream, outlets untouched, conservation of drainage area, fixed point under one oracle iteration)."""
+    n = m["n"]
+    load_ctx(ctx, m, p, outlets, initial)
+    check_first_iteration(ctx, O, m, p, outlets, initial)
+    if first_iterations:
+        assert check_generate(ctx, O, m, p, outlets, initial, first_iterations)
+    e, it = ctx.generate()
+    recv = ctx.fetch("receivers").astype(np.int64)
+    A = ctx.fetch("drainage_area")
+    depth = ctx.fetch("depth")
+    labels = ctx.fetch("labels").astype(np.int64)
+    e2, it2 = ctx.generate()
+    assert it == it2 and np.array_equal(e, e2), "deterministic"
+    is_outlet = np.zeros(n, dtype=bool)
+    is_outlet[outlets] = True
+    # converged forest: every site drains to an outlet, elevation strictly increases upstream (positive uplift)
+    assert (depth != 0xFFFFFFFF).all()
+    assert is_outlet[labels].all()
+    non_out = ~is_outlet
+    assert (recv[non_out] != np.arange(n)[non_out]).all()
+    assert (e[non_out] > e[recv[non_out]]).all()
+    assert np.array_equal(e[is_outlet], initial[is_outlet]), "outlets keep base + noise (generator.rs:177-179)"
+    # conservation: the outlets' drainage areas add up to the total cell area
+    assert abs(A[is_outlet].sum() - m["areas"].sum()) <= 1e-9 * m["areas"].sum()
+    # fixed point: one more body from the converged field changes nothing (checked with the oracle)
+    nxt = O.iterate_once(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, e)
+    assert not nxt["changed"]
+    assert np.array_equal(nxt["next"], recv)
+    return e, it

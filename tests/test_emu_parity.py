@@ -190,3 +190,14 @@ def test_first_iteration_levels_vs_flow(oracle, emu_lib, name):
         with _ctx(emu_lib, sweep=3, first_flow=first_flow) as ctx:
             helpers.load_ctx(ctx, m, p, outlets, initial)
             assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
+
+
+@pytest.mark.parametrize("name,n", [("uniform", 2500), ("advanced", 4000), ("max_slope", 2000)])
+def test_converged_properties_helper(oracle, emu_lib, name, n):
+    """The size-independent property checks used by the full-size GPU tests (C2 at 1M, C3 at 4M sites), run here at a
+    size where the oracle also converges, so the helper itself is known to hold on a correct result."""
+    m, p, outlets, initial, _ = scenario(name, n)
+    with _ctx(emu_lib) as ctx:
+        e, it = helpers.check_converged_properties(ctx, oracle, m, p, outlets, initial)
+    ref, ref_it = oracle.generate(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, initial)
+    assert it == ref_it and np.array_equal(e, ref)
