@@ -182,22 +182,6 @@ def test_c2_one_million_sites(oracle, gpu_ctx_factory):
         helpers.check_converged_properties(ctx, oracle, m, p, outlets, initial)
 
 
-def test_c3_four_million_sites_advanced(oracle, gpu_ctx_factory):
-    """BASELINE config C3 at full size: 4M sites, noise-driven erodibility, ocean-mask outlets flood-filled from the rim
-    (examples/terrain_generation_advanced.rs:136-210).  The graph is the jittered 2000 x 2000 lattice (a 4M-site
-    Delaunay build alone takes minutes on the host; the lattice is the same stand-in DESIGN.md uses for C4).  Every
-    stage of iteration 1 against the oracle, then the size-independent properties of the converged result."""
-    from tools import workloads as W
-    m = W.lattice_model(2000, 2000, jitter=0.35, seed=21)
-    p = W.advanced_params(m, seed=3, ocean_level=-0.25)
-    outlets = W.outlets_for(m, p)
-    assert m["n"] == 4000000 and outlets.size > m["default_outlets"].size, "explicit ocean outlets, not the rim default"
-    initial = oracle.initial_elevations(p["base"])
-    with gpu_ctx_factory() as ctx:
-        _, it = helpers.check_converged_properties(ctx, oracle, m, p, outlets, initial, first_iterations=0)
-        assert it > 100
-
-
 def test_host_mirror_on_gpu(oracle, product_lib):
     import fastlem_b200 as fl
     m, p, outlets, initial, _ = scenario("max_slope")
