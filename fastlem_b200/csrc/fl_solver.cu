@@ -11,6 +11,7 @@
 //   2  as 1, and paths of >= FL_LONG_PATH sites are walked by a whole warp (default)
 #include "../../include/fastlem_b200.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <new>
@@ -1358,8 +1359,11 @@ int fastlem_set_parameters(fastlem_ctx* c, const double* initial_elevation, cons
     for (uint32_t k = 0; k < n_outlets; ++k) table[outlets[k]] = 1;
     FL_CK(fl_h2d(c->orig.is_outlet, table.data(), n, c->stream));
     FL_CK(fl_stream_sync(c->stream));
+    // the flood order of lake removal is a function of (graph, outlets) only: keep it when an ensemble member changes
+    // nothing but the per-site parameters
+    const bool same_outlets = c->outlets.size() == n_outlets && std::equal(c->outlets.begin(), c->outlets.end(), outlets);
     c->outlets.assign(outlets, outlets + n_outlets);
-    c->rank_ready = false;
+    c->rank_ready = c->rank_ready && same_outlets;
     c->has_params = true;
     c->stats.ms_upload += wall_ms() - t0;
     return FASTLEM_OK;

@@ -34,6 +34,24 @@ def run_members(member_inputs, make_context, max_iteration=None):
     return out
 
 
+def run_members_shared_graph(graph, member_params, make_context, max_iteration=None):
+    """Ensemble members that share one model (same sites and graph) and differ in their parameters only (seeds of the
+    erodibility / uplift fields, outlet masks): one context, the graph is uploaded once, every member is one
+    set_parameters + generate.  The flood order of lake removal is kept as long as the outlets do not change.
+
+    graph        : dict with row_ptr, col, dist, areas
+    member_params: list of dicts with initial, erodibility, uplift, tan_max_slope (optional), outlets
+    returns      : list of (elevations, iterations)
+    """
+    out = []
+    with make_context() as ctx:
+        ctx.set_graph(graph["row_ptr"], graph["col"], graph["dist"], graph["areas"])
+        for m in member_params:
+            ctx.set_parameters(m["initial"], m["erodibility"], m["uplift"], m.get("tan_max_slope"), m["outlets"])
+            out.append(ctx.generate(max_iteration))
+    return out
+
+
 def gather_elevations(local, n_members, n_sites, rank, world, device="cpu"):
     """All-gather the members' elevations: returns an (n_members, n_sites) float64 array on every rank.
 

@@ -201,3 +201,30 @@ def test_converged_properties_helper(oracle, emu_lib, name, n):
         e, it = helpers.check_converged_properties(ctx, oracle, m, p, outlets, initial)
     ref, ref_it = oracle.generate(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, initial)
     assert it == ref_it and np.array_equal(e, ref)
+
+
+def test_ensemble_members_on_one_shared_graph(oracle, emu_lib):
+    """C5-style ensemble on one model: members differ in erodibility, uplift, max_slope and (one of them) outlets; one
+    context, one graph upload (fastlem_b200.ensemble.run_members_shared_graph).  The flood order survives a parameter
+    change with the same outlets and is recomputed when the outlets change."""
+    from fastlem_b200 import _native, ensemble
+    from tools import workloads as W
+    m, p, outlets, initial, _ = scenario("uniform", 2500)
+    n = m["n"]
+    rng = np.random.default_rng(4)
+    other_outlets = np.unique(np.concatenate([outlets[::2], rng.integers(0, n, 5).astype(np.uint32)])).astype(np.uint32)
+    members = [
+        dict(initial=initial, erodibility=p["erodibility"], uplift=p["uplift"], outlets=outlets),
+        dict(initial=initial, erodibility=0.5 + rng.random(n), uplift=p["uplift"], outlets=outlets),
+        dict(initial=initial, erodibility=p["erodibility"], uplift=1.1 + 0.9 * W.value_noise(m["sites"], 0.05, seed=3, octaves=2),
+             outlets=outlets),
+        dict(initial=initial, erodibility=0.5 + rng.random(n), uplift=p["uplift"], outlets=other_outlets),
+        dict(initial=initial, erodibility=p["erodibility"], uplift=p["uplift"], outlets=outlets,
+             tan_max_slope=helpers.tan_of(np.full(n, 0.3))),
+    ]
+    res = ensemble.run_members_shared_graph(m, members, lambda: _native.Context(0, emu_lib), max_iteration=40)
+    for k, (mem, (e, it)) in enumerate(zip(members, res)):
+        ms = None if "tan_max_slope" not in mem else np.full(n, 0.3)
+        ref, ref_it = oracle.generate(m, mem["erodibility"], mem["uplift"], ms, mem["outlets"], mem["initial"], 40)
+        assert it == ref_it, k
+        assert np.array_equal(e, ref), f"member {k}"

@@ -1,4 +1,5 @@
-"""GPU tier, run last (file name): BASELINE configurations at their full sizes, checked through size-independent
+"""GPU tier, run last (file name): tests added without a GPU at hand in the session that wrote them, and BASELINE
+configurations at their full sizes, checked through size-independent
 properties because the oracle cannot run them to convergence in test time (tests/helpers.py,
 check_converged_properties; the helper itself is validated on the CPU tier in test_emu_parity.py).
 C2 at 1M sites lives in test_gpu_parity.py::test_c2_one_million_sites."""
@@ -23,3 +24,27 @@ def test_c3_four_million_sites_advanced(oracle, gpu_ctx_factory):
     with gpu_ctx_factory() as ctx:
         _, it = helpers.check_converged_properties(ctx, oracle, m, p, outlets, initial, first_iterations=0)
         assert it > 100
+
+
+def test_ensemble_members_on_one_shared_graph_gpu(oracle, product_lib):
+    """The shared-graph ensemble runner on the device (same checks as tests/test_emu_parity.py)."""
+    import numpy as np
+    from fastlem_b200 import _native, ensemble
+    from scenarios import scenario
+    m, p, outlets, initial, _ = scenario("uniform", 30000)
+    n = m["n"]
+    rng = np.random.default_rng(4)
+    other_outlets = np.unique(np.concatenate([outlets[::2], rng.integers(0, n, 5).astype(np.uint32)])).astype(np.uint32)
+    members = [
+        dict(initial=initial, erodibility=p["erodibility"], uplift=p["uplift"], outlets=outlets),
+        dict(initial=initial, erodibility=0.5 + rng.random(n), uplift=p["uplift"], outlets=outlets),
+        dict(initial=initial, erodibility=0.5 + rng.random(n), uplift=p["uplift"], outlets=other_outlets),
+        dict(initial=initial, erodibility=p["erodibility"], uplift=p["uplift"], outlets=outlets,
+             tan_max_slope=helpers.tan_of(np.full(n, 0.3))),
+    ]
+    res = ensemble.run_members_shared_graph(m, members, lambda: _native.Context(0, product_lib), max_iteration=60)
+    for k, (mem, (e, it)) in enumerate(zip(members, res)):
+        ms = None if "tan_max_slope" not in mem else np.full(n, 0.3)
+        ref, ref_it = oracle.generate(m, mem["erodibility"], mem["uplift"], ms, mem["outlets"], mem["initial"], 60)
+        assert it == ref_it, k
+        assert np.array_equal(e, ref), f"member {k}"
