@@ -58,7 +58,24 @@ __global__ void __launch_bounds__(256) k_rev_slots(uint32_t n, const uint32_t* _
 // set in its child mask, so parents can later enumerate children in adjacency order without rescanning
 // their neighbours.  Rows longer than 32 ignore the mask and rescan (fl_children_rev).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_receivers_mask(uint32_t n, const uint32_t* __restrict__ row_ptr,
+// Build-time variants for A/B runs on the device (tools/ab_k1.py): FL_K1_MINBLOCKS n = __launch_bounds__(256, n)
+// (0 = ptxas' choice), FL_K1_BATCH = neighbours whose loads are issued together.  Measured on a B200 at 1M sites
+// (profiles/r1c_ab_k1_1.txt, _2.txt; results bit-identical): batches of 8 (78 registers, 3 CTAs per SM) 60.5 us per
+// launch; 6: 50.3; 4: 51.1; 3 (48 registers, 5 CTAs per SM): 46.6; 2: 50.1; forcing more CTAs per SM through
+// __launch_bounds__ only adds spills (batch 8: 60.9 / 69.3 / 70.7 / 82.0 us for 4 / 5 / 6 / 8 CTAs).  With a mean
+// degree of 6 a row is two batches of 3.
+#ifndef FL_K1_MINBLOCKS
+#define FL_K1_MINBLOCKS 0
+#endif
+#ifndef FL_K1_BATCH
+#define FL_K1_BATCH 3
+#endif
+#if FL_K1_MINBLOCKS > 0 && !defined(FL_EMU)
+#define FL_K1_BOUNDS __launch_bounds__(256, FL_K1_MINBLOCKS)
+#else
+#define FL_K1_BOUNDS __launch_bounds__(256)
+#endif
+__global__ void FL_K1_BOUNDS k_receivers_mask(uint32_t n, const uint32_t* __restrict__ row_ptr,
                                                          const uint32_t* __restrict__ col,
                                                          const double* __restrict__ dist,
                                                          const uint8_t* __restrict__ rev,
@@ -76,22 +93,22 @@ __global__ void __launch_bounds__(256) k_receivers_mask(uint32_t n, const uint32
         const double ei = elev[i];
         double steepest = 0.0;
         const uint32_t s0 = row_ptr[i], s1 = row_ptr[i + 1];
-        // eight neighbours at a time: their ids and edge lengths first, then the elevation gathers -- all loads of a
-        // batch are in flight together; the comparisons then run in adjacency order (first slot wins ties)
-        for (uint32_t sb = s0; sb < s1; sb += 8u) {
-            uint32_t j[8];
-            double d[8], ej[8];
+        // FL_K1_BATCH neighbours at a time: their ids and edge lengths first, then the elevation gathers -- all loads of
+        // a batch are in flight together; the comparisons then run in adjacency order (first slot wins ties)
+        for (uint32_t sb = s0; sb < s1; sb += (uint32_t)FL_K1_BATCH) {
+            uint32_t j[FL_K1_BATCH];
+            double d[FL_K1_BATCH], ej[FL_K1_BATCH];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < FL_K1_BATCH; ++k) {
                 const uint32_t s = sb + (uint32_t)k;
                 const bool ok = s < s1;
                 j[k] = ok ? col[s] : i;  // padding: the site itself (never lower than itself)
                 d[k] = ok ? dist[s] : 1.0;
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) ej[k] = elev[j[k]];
+            for (int k = 0; k < FL_K1_BATCH; ++k) ej[k] = elev[j[k]];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < FL_K1_BATCH; ++k) {
                 if (ei > ej[k]) {
                     const double slope = (ei - ej[k]) / d[k];
                     if (slope > steepest) {
