@@ -21,7 +21,7 @@ _STAGE_DTYPE = {0: np.uint32, 1: np.uint32, 2: np.uint32, 3: np.uint32, 4: np.ui
                 6: np.float64, 7: np.float64, 8: np.uint32}
 
 # every symbol include/fastlem_b200.h declares
-SYMBOLS = ["fastlem_create", "fastlem_destroy", "fastlem_last_error", "fastlem_set_graph",
+SYMBOLS = ["fastlem_create", "fastlem_destroy", "fastlem_last_error", "fastlem_get_device", "fastlem_set_graph",
            "fastlem_set_parameters", "fastlem_generate", "fastlem_run", "fastlem_download", "fastlem_download_to_device",
            "fastlem_set_option", "fastlem_get_stats", "fastlem_debug_fetch", "fastlem_version",
            "fastlem_host_initial_elevations", "fastlem_host_graph_from_triangles",
@@ -88,6 +88,7 @@ def load(path=None):
     lib.fastlem_destroy.restype = None
     lib.fastlem_last_error.argtypes = [vp]
     lib.fastlem_last_error.restype = ctypes.c_char_p
+    lib.fastlem_get_device.argtypes = [vp]
     lib.fastlem_set_graph.argtypes = [vp, u32, u32p, u32p, f64p, f64p]
     lib.fastlem_set_parameters.argtypes = [vp, f64p, f64p, f64p, f64p, u32p, u32]
     lib.fastlem_generate.argtypes = [vp, u32, f64p, u32p]

@@ -338,6 +338,8 @@ int fastlem_interp_set_values_device(fastlem_interp* c, const double* device_val
 
 int fastlem_interp_set_values_from(fastlem_interp* c, fastlem_ctx* solver) {
     if (!c || !solver) return FASTLEM_E_INVALID;
+    if (fastlem_get_device(solver) != c->device)
+        return fail(c, FASTLEM_E_INVALID, "set_values_from: the solver context lives on another device");
     FLI_CK(fl_set_device(c->device));
     // the solver writes its elevations (caller's numbering) straight into the interpolator's value array
     int rc = fastlem_download_to_device(solver, c->d_value);

@@ -1196,6 +1196,8 @@ void fastlem_destroy(fastlem_ctx* c) {
 
 const char* fastlem_last_error(const fastlem_ctx* c) { return c ? c->err.c_str() : "null context"; }
 
+int fastlem_get_device(const fastlem_ctx* c) { return c ? c->device : -1; }
+
 int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
     if (!c || !name) return FASTLEM_E_INVALID;
     std::string s(name);

@@ -45,6 +45,8 @@ enum {
 int fastlem_create(fastlem_ctx** out, int device_ordinal);
 void fastlem_destroy(fastlem_ctx* ctx);
 const char* fastlem_last_error(const fastlem_ctx* ctx);
+/* CUDA device ordinal the context lives on (-1 for a null context). */
+int fastlem_get_device(const fastlem_ctx* ctx);
 
 /* The model, as `generate()` reads it through trait Model (src/core/traits.rs:13-20):
  *   n        = model.num()                                   (generator.rs:99-105)
