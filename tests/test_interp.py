@@ -289,7 +289,33 @@ def check_sites_on_a_circle(lib, O):
         assert e.value.code == _native.E_INVALID
 
 
+def check_empty_and_tiny(lib):
+    """No triangles at all (0, 1, 2 sites): every query is None; empty query batches and empty row ranges are fine; a
+    single triangle reproduces the plane through its vertices (inside, on an edge, on a vertex) and is None outside."""
+    from fastlem_b200 import _native
+    none = np.zeros(0, dtype=np.uint32)
+    for n in (0, 1, 2):
+        sites = np.arange(2 * n, dtype=np.float64).reshape(n, 2)
+        with _native.Interpolator(sites, none, none, lib_path=lib) as it:
+            it.set_values(np.ones(n))
+            assert np.isnan(it.points(np.array([[0.5, 0.5], [0.0, 1.0]]))).all()
+            assert it.points(np.zeros((0, 2))).shape == (0,)
+            assert np.isnan(it.raster(it.raster_desc(3, 2, 0.0, 0.0, 1.0, 1.0))).all()
+            assert it.raster(it.raster_desc(3, 2, 0.0, 0.0, 1.0, 1.0, 0.0, 1, 1)).shape == (0, 3)
+    sites = np.array([[0.0, 0.0], [4.0, 0.0], [0.0, 4.0]])
+    with _native.Interpolator(sites, np.array([0, 1, 2], dtype=np.uint32), np.full(3, 0xFFFFFFFF, dtype=np.uint32),
+                              lib_path=lib) as it:
+        it.set_values(np.array([1.0, 2.0, 3.0]))  # z = 1 + x/4 + y/2
+        out = it.points(np.array([[1.0, 1.0], [2.0, 2.0], [0.0, 0.0], [2.0, 0.0], [5.0, 5.0], [-1.0, 1.0]]))
+    assert np.allclose(out[:4], [1.75, 2.5, 1.0, 1.5], rtol=0, atol=1e-12)
+    assert np.isnan(out[4:]).all()
+
+
 # ---- CPU tier: emulation build -------------------------------------------------------------------
+def test_emu_empty_and_tiny(emu_lib):
+    check_empty_and_tiny(emu_lib)
+
+
 def test_emu_sites_on_a_circle(oracle, emu_lib):
     check_sites_on_a_circle(emu_lib, oracle)
 
@@ -367,6 +393,11 @@ def test_gpu_matches_golden(gpu_lib, path):
                                                  (20000, 5, (100.0, 100.0), 1)])
 def test_gpu_matches_oracle(oracle, gpu_lib, n, seed, bound, lloyd):
     check_against_oracle(gpu_lib, oracle, n, seed, 3000, bound, lloyd)
+
+
+@pytest.mark.gpu
+def test_gpu_empty_and_tiny(gpu_lib):
+    check_empty_and_tiny(gpu_lib)
 
 
 @pytest.mark.gpu
