@@ -41,10 +41,17 @@ NCU_TRAFFIC_NOTE = {"receivers": "ncu: 99.1 MB read + 8.5 MB written per launch 
                             "full pass; the incremental pass touches 3-10 % of the sites)"}
 
 
+WORKLOAD = "delaunay"  # --workload lattice: jittered lattice (stand-in for the relaxed Delaunay graph of C4 at 16M sites)
+
+
 def build_workload(n_sites, seed):
     from tools import workloads as W
     t0 = time.time()
-    m = W.delaunay_model(W.random_sites(n_sites, (0.0, 0.0), (100.0, 100.0), seed=seed))
+    if WORKLOAD == "lattice":
+        side = max(2, int(round(n_sites ** 0.5)))
+        m = W.lattice_model(side, side, jitter=0.35, seed=seed)
+    else:
+        m = W.delaunay_model(W.random_sites(n_sites, (0.0, 0.0), (100.0, 100.0), seed=seed))
     p = W.uniform_params(m["n"])
     outlets = W.outlets_for(m, p)
     return m, p, outlets, time.time() - t0
@@ -128,7 +135,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C2: {n} random sites, Delaunay graph, uniform erodibility, hull outlets",
+            "config": {"workload": (f"C2: {n} random sites, Delaunay graph, uniform erodibility, hull outlets"
+                                    if WORKLOAD == "delaunay" else f"C4 stand-in: jittered lattice of {n} sites, uniform "
+                                    f"erodibility, rim outlets"),
                        "sites": n, "iterations_per_step": iters},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -236,6 +245,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--sites", type=int, default=1000000)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="delaunay", choices=["delaunay", "lattice"],
+                    help="lattice: jittered lattice of ~--sites sites (C4 stand-in; builds in seconds at 16M); the raster leg "
+                         "needs a Delaunay triangulation and is skipped")
     ap.add_argument("--ref-iters", type=int, default=5, help="iterations per step of the CPU arm")
     ap.add_argument("--cpu-baseline-iters", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -245,6 +257,10 @@ def main():
                     help="profiling aid: stop every generate() after this many iterations (the metric is then NOT the "
                          "benchmark's; used for ncu launch lists of the same command)")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
+    if WORKLOAD == "lattice":
+        args.raster = 0
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -408,8 +424,11 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * wall_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"C2: {n} random sites in [0,100]^2, Delaunay graph (boundary format), uniform "
-                                       f"erodibility 1.0, hull outlets; step = generate() to convergence",
+                "config": {"workload": (f"C2: {n} random sites in [0,100]^2, Delaunay graph (boundary format), uniform "
+                                        f"erodibility 1.0, hull outlets; step = generate() to convergence"
+                                        if WORKLOAD == "delaunay" else
+                                        f"C4 stand-in: jittered lattice of {n} sites in [0,100]^2 (each cell split along a random "
+                                        f"diagonal), uniform erodibility 1.0, rim outlets; step = generate() to convergence"),
                            "sites": n, "directed_edges": int(m["col"].size),
                            "iterations_per_step": iters_total / args.steps,
                            "l2": "working set ~170 MB per iteration > 126 MB L2; hundreds of iterations per step, no flush",
