@@ -91,10 +91,12 @@ int fastlem_download(fastlem_ctx* ctx, double* elevations_out);
  * (used to hand an ensemble member's result to an NCCL gather without a host round trip). */
 int fastlem_download_to_device(fastlem_ctx* ctx, double* device_elevations_out);
 
-/* Options (all default 0): "profile" = 1 records CUDA events around every stage and fills the ms_*
- * fields of fastlem_stats; "keep_stages" = 1 keeps the pre-lake-removal receivers/labels of the last
- * iteration for fastlem_debug_fetch; "sweep" selects the tree-sweep implementation: 0 = one launch per
- * tree level, 1 = path-decomposed (default). */
+/* Options.  "profile" = 1 (default 0) records CUDA events around every stage and fills the ms_* fields of
+ * fastlem_stats; "keep_stages" = 1 (default 0) keeps the pre-lake-removal receivers/labels of the last iteration for
+ * fastlem_debug_fetch.  The rest select between implementations that give bit-identical results:
+ * "sweep" 0 = one launch per tree level, 1 / 2 = path-decomposed (thread / warp per path), 3 = dataflow sweeps
+ * (default); "incremental" (1), "incr_div" (16), "first_flow" (1), "fuse_levels" (1), "fuse_k4" (0), "flood_device" (1),
+ * "park_after" (8), "key_base", "rebuild_every" (0 = adaptive), "rebuild_growth" (4), "rebuild_height" (150). */
 int fastlem_set_option(fastlem_ctx* ctx, const char* name, int64_t value);
 
 typedef struct fastlem_stats {
@@ -110,7 +112,7 @@ typedef struct fastlem_stats {
     /* "profile"=1 only: summed over the iterations of the last run */
     double ms_receivers, ms_labels, ms_lakes, ms_order, ms_area, ms_elevation;
     uint64_t n_receivers, n_labels, n_lakes, n_order, n_area, n_elevation; /* launches per stage */
-    /* "sweep"=1: path layout of the last iteration */
+    /* "sweep" >= 1: path / segment layout of the last iteration */
     uint32_t rebuilds;    /* layout rebuilds (site renumberings) during the last run */
     uint32_t path_levels; /* nesting depth of the path decomposition = rounds per sweep */
     uint32_t paths;       /* number of paths */
