@@ -37,6 +37,7 @@ struct fastlem_interp {
     bool has_values = false;
     FliGrid grid{};
     double sgn = 1.0;
+    double origin[2] = {0.0, 0.0};  // lower corner of the sites' bounding box, subtracted from every coordinate
     uint32_t max_walk = 0;
     cudaEvent_t ev[2] = {};
     fastlem_interp_stats stats{};
@@ -97,6 +98,8 @@ FliModel model_of(const fastlem_interp* c) {
     M.n_tri = c->n_tri;
     M.max_walk = c->max_walk;
     M.sgn = c->sgn;
+    M.ox = c->origin[0];
+    M.oy = c->origin[1];
     return M;
 }
 
@@ -178,6 +181,19 @@ const char* fastlem_interp_last_error(const fastlem_interp* c) { return c ? c->e
 static int interp_setup(fastlem_interp* c, const double* sites_xy, const uint32_t* triangles, const uint32_t* halfedges) {
     const uint32_t n = c->n_sites, nt = c->n_tri;
     const double t0 = wall_ms();
+    // bounding box of the sites; its lower corner becomes the origin of all device-side coordinates, so that data given
+    // in large absolute coordinates (map projections) keeps its precision in the circumcentre / area arithmetic
+    double lo[2] = {INFINITY, INFINITY}, hi[2] = {-INFINITY, -INFINITY};
+    for (uint32_t i = 0; i < n; ++i)
+        for (int k = 0; k < 2; ++k) {
+            const double v = sites_xy[2 * (size_t)i + k];
+            if (!(v == v) || std::isinf(v)) return fail(c, FASTLEM_E_INVALID, "interpolator: non-finite site coordinate");
+            lo[k] = v < lo[k] ? v : lo[k];
+            hi[k] = v > hi[k] ? v : hi[k];
+        }
+    if (n == 0) lo[0] = lo[1] = hi[0] = hi[1] = 0.0;
+    c->origin[0] = lo[0];
+    c->origin[1] = lo[1];
     void* hf = nullptr;
     FLI_CK(fl_malloc_host(&hf, sizeof(uint32_t) * FLI_N_FLAGS));
     c->h_flags = (uint32_t*)hf;
@@ -203,6 +219,10 @@ static int interp_setup(fastlem_interp* c, const double* sites_xy, const uint32_
         if (e == cudaSuccess) e = fl_h2d(d_halfedges, halfedges, sizeof(uint32_t) * 3 * (size_t)nt, c->stream);
         if (e == cudaSuccess) e = fl_memset(c->d_flags, 0, sizeof(uint32_t) * FLI_N_FLAGS, c->stream);
         if (e != cudaSuccess) { rc = fail(c, FASTLEM_E_CUDA, std::string("upload: ") + cudaGetErrorString(e)); break; }
+        if (n) {
+            FL_LAUNCH(k_nn_translate, blocks_for(n), 256, c->stream, n, c->d_site, c->origin[0], c->origin[1]);
+            c->stats.kernel_launches++;
+        }
         if (nt) {
             FL_LAUNCH(k_nn_prepare, blocks_for(nt), 256, c->stream, n, nt, c->d_site, d_triangles, d_halfedges, c->d_tri,
                       c->d_nbr, c->d_circ, c->d_geo, c->d_flags);
@@ -231,16 +251,7 @@ static int interp_setup(fastlem_interp* c, const double* sites_xy, const uint32_
                                               std::to_string(c->h_flags[FLI_F_NOT_DELAUNAY]) +
                                               " opposite vertices inside a circumcircle)");
 
-    // hint grid over the bounding box of the sites: ~2 triangle centroids per cell
-    double lo[2] = {INFINITY, INFINITY}, hi[2] = {-INFINITY, -INFINITY};
-    for (uint32_t i = 0; i < n; ++i)
-        for (int k = 0; k < 2; ++k) {
-            const double v = sites_xy[2 * (size_t)i + k];
-            if (!(v == v) || std::isinf(v)) return fail(c, FASTLEM_E_INVALID, "interpolator: non-finite site coordinate");
-            lo[k] = v < lo[k] ? v : lo[k];
-            hi[k] = v > hi[k] ? v : hi[k];
-        }
-    if (n == 0) lo[0] = lo[1] = hi[0] = hi[1] = 0.0;
+    // hint grid over the bounding box of the (translated) sites: ~2 triangle centroids per cell
     const double w = hi[0] - lo[0], h = hi[1] - lo[1];
     double cells = nt / 2.0;
     if (cells < 1.0) cells = 1.0;
@@ -256,8 +267,8 @@ static int interp_setup(fastlem_interp* c, const double* sites_xy, const uint32_
     if (gy > 16384.0) gy = 16384.0;
     c->grid.gx = (uint32_t)gx;
     c->grid.gy = (uint32_t)gy;
-    c->grid.x0 = lo[0];
-    c->grid.y0 = lo[1];
+    c->grid.x0 = 0.0;  // device coordinates are relative to the lower corner of the bounding box
+    c->grid.y0 = 0.0;
     c->grid.inv_cell_x = w > 0.0 ? gx / w : 0.0;
     c->grid.inv_cell_y = h > 0.0 ? gy / h : 0.0;
     const size_t nc = (size_t)c->grid.gx * c->grid.gy;

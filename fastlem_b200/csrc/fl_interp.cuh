@@ -117,6 +117,16 @@ __device__ __forceinline__ bool fli_circumcentre_q(double ax, double ay, double 
 // ------------------------------------------------------------------------------------------------
 // set-up kernels (once per triangulation)
 // ------------------------------------------------------------------------------------------------
+// sites relative to the lower corner of their bounding box (exact when the offset is large against the extent)
+__global__ void __launch_bounds__(256) k_nn_translate(uint32_t n, FliPt* __restrict__ site, double ox, double oy) {
+    const uint32_t i = FLI_TID;
+    if (i >= n) return;
+    FliPt p = site[i];
+    p.x -= ox;
+    p.y -= oy;
+    site[i] = p;
+}
+
 // delaunator's arrays (triangles[3T], halfedges[3T]; usize::MAX = no opposite half-edge) -> FliTri / FliNbr,
 // circumcircles, orientation census.
 __global__ void __launch_bounds__(256) k_nn_prepare(uint32_t n_sites, uint32_t n_tri, const FliPt* __restrict__ site,
@@ -261,13 +271,15 @@ struct FliModel {
     uint32_t n_tri;
     uint32_t max_walk;
     double sgn;  // +1: triangles counter-clockwise, -1: clockwise
+    double ox, oy;  // origin of the device-side coordinates (lower corner of the sites' bounding box)
 };
 
 // Returns the interpolated value, or NaN for `None` (outside the convex hull; NaN coordinates).
-__device__ __forceinline__ double fli_query(const FliModel& M, const double px, const double py,
+__device__ __forceinline__ double fli_query(const FliModel& M, const double qx, const double qy,
                                             uint32_t* __restrict__ flags) {
     const double nan = fli_nan();
-    if (!(px == px) || !(py == py) || M.n_tri == 0u) return nan;
+    if (!(qx == qx) || !(qy == qy) || M.n_tri == 0u) return nan;
+    const double px = qx - M.ox, py = qy - M.oy;  // same translation as the sites (k_nn_translate)
     // ---- 1. locate -------------------------------------------------------------------------------
     uint32_t t = M.cell[fli_cell(M.grid, px, py)];
     FliTri T;

@@ -43,5 +43,8 @@ def delaunay(sites):
     """(triangles[3T] uint32, halfedges[3T] uint32) of the Delaunay triangulation of `sites` (n x 2)."""
     from scipy.spatial import Delaunay
     pts = np.ascontiguousarray(sites, dtype=np.float64).reshape(-1, 2)
-    tri = orient_ccw(pts, Delaunay(pts).simplices)
+    # Qhull lifts to x^2 + y^2 in double precision: centre the points first, or data in large absolute coordinates
+    # comes back with in-circle decisions that are off by far more than rounding
+    centred = pts - pts.mean(axis=0) if pts.shape[0] else pts
+    tri = orient_ccw(pts, Delaunay(centred).simplices)
     return tri.reshape(-1).astype(np.uint32), halfedges_from_triangles(tri, pts.shape[0])

@@ -311,7 +311,33 @@ def check_empty_and_tiny(lib):
     assert np.isnan(out[4:]).all()
 
 
+def check_large_offsets(lib, O):
+    """Sites in large absolute coordinates (map projections): device coordinates are taken relative to the bounding box,
+    so the accuracy does not degrade with the offset; values on the sites stay exact."""
+    from fastlem_b200 import _native, triangulation
+    rng = np.random.default_rng(0)
+    base = rng.random((4000, 2)) * 100.0
+    values = rng.random(4000) * 100.0
+    q0 = 5.0 + rng.random((2000, 2)) * 90.0
+    for off in (1.0e3, 5.0e5, 1.0e7):
+        sites, q = base + off, q0 + off
+        tri, he = triangulation.delaunay(sites)
+        with _native.Interpolator(sites, tri, he, lib_path=lib) as it:
+            it.set_values(values)
+            out = it.points(q)
+            assert np.array_equal(it.points(sites[:200]), values[:200])
+            img = it.raster(it.raster_desc(16, 16, off, off, 100.0, 100.0, 0.5))
+        ref = O.nn_interpolate(sites, tri, values, q)
+        assert not np.isnan(ref).any() and not np.isnan(out).any()
+        assert rel_err(out, ref).max() <= NN_TOL
+        assert np.isfinite(img).mean() > 0.9
+
+
 # ---- CPU tier: emulation build -------------------------------------------------------------------
+def test_emu_large_offsets(oracle, emu_lib):
+    check_large_offsets(emu_lib, oracle)
+
+
 def test_emu_empty_and_tiny(emu_lib):
     check_empty_and_tiny(emu_lib)
 
@@ -393,6 +419,11 @@ def test_gpu_matches_golden(gpu_lib, path):
                                                  (20000, 5, (100.0, 100.0), 1)])
 def test_gpu_matches_oracle(oracle, gpu_lib, n, seed, bound, lloyd):
     check_against_oracle(gpu_lib, oracle, n, seed, 3000, bound, lloyd)
+
+
+@pytest.mark.gpu
+def test_gpu_large_offsets(oracle, gpu_lib):
+    check_large_offsets(gpu_lib, oracle)
 
 
 @pytest.mark.gpu
