@@ -50,6 +50,7 @@ inline real incircle(Pt a, Pt b, Pt c, Pt p) {
 
 struct Mesh {
     uint32_t n = 0, nt = 0;
+    Pt origin{0, 0};  // first site: all coordinates are taken relative to it (exact in long double)
     std::vector<Pt> pts;
     std::vector<uint32_t> tri;                      // counter-clockwise after normalisation
     std::unordered_map<uint64_t, uint32_t> edge_tri;  // directed edge (a -> b) -> triangle having it
@@ -66,7 +67,8 @@ Mesh build_mesh(uint32_t n, const double* xy, uint32_t nt, const uint32_t* tri) 
     m.n = n;
     m.nt = nt;
     m.pts.resize(n);
-    for (uint32_t i = 0; i < n; ++i) m.pts[i] = Pt{(real)xy[2 * i], (real)xy[2 * i + 1]};
+    if (n) m.origin = Pt{(real)xy[0], (real)xy[1]};
+    for (uint32_t i = 0; i < n; ++i) m.pts[i] = Pt{(real)xy[2 * i] - m.origin.x, (real)xy[2 * i + 1] - m.origin.y};
     m.tri.assign(tri, tri + 3 * (size_t)nt);
     for (uint32_t t = 0; t < nt; ++t) {
         uint32_t* v = &m.tri[3 * (size_t)t];
@@ -208,7 +210,10 @@ void fo_nn_interpolate(uint32_t n, const double* xy, uint32_t nt, const uint32_t
     std::vector<uint32_t> ids;
     std::vector<real> w;
     for (uint32_t i = 0; i < nq; ++i) {
-        if (!query(m, Pt{(real)qxy[2 * i], (real)qxy[2 * i + 1]}, &ids, &w)) { out[i] = std::nan(""); continue; }
+        if (!query(m, Pt{(real)qxy[2 * i] - m.origin.x, (real)qxy[2 * i + 1] - m.origin.y}, &ids, &w)) {
+            out[i] = std::nan("");
+            continue;
+        }
         real z = 0;
         for (size_t k = 0; k < ids.size(); ++k) z += w[k] * (real)values[ids[k]];
         out[i] = (double)z;
@@ -226,7 +231,10 @@ void fo_nn_interpolate_walk(uint32_t n, const double* xy, uint32_t nt, const uin
     std::vector<real> w;
     uint32_t hint = 0;
     for (uint32_t i = 0; i < nq; ++i) {
-        if (!query(m, Pt{(real)qxy[2 * i], (real)qxy[2 * i + 1]}, &ids, &w, &hint)) { out[i] = std::nan(""); continue; }
+        if (!query(m, Pt{(real)qxy[2 * i] - m.origin.x, (real)qxy[2 * i + 1] - m.origin.y}, &ids, &w, &hint)) {
+            out[i] = std::nan("");
+            continue;
+        }
         real z = 0;
         for (size_t k = 0; k < ids.size(); ++k) z += w[k] * (real)values[ids[k]];
         out[i] = (double)z;
@@ -240,7 +248,7 @@ uint32_t fo_nn_weights(uint32_t n, const double* xy, uint32_t nt, const uint32_t
     const Mesh m = build_mesh(n, xy, nt, tri);
     std::vector<uint32_t> ids;
     std::vector<real> w;
-    if (!query(m, Pt{(real)qx, (real)qy}, &ids, &w)) return 0;
+    if (!query(m, Pt{(real)qx - m.origin.x, (real)qy - m.origin.y}, &ids, &w)) return 0;
     for (size_t k = 0; k < ids.size() && k < cap; ++k) { ids_out[k] = ids[k]; w_out[k] = (double)w[k]; }
     return (uint32_t)ids.size();
 }
