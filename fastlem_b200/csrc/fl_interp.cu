@@ -137,7 +137,10 @@ int launch_raster(fastlem_interp* c, const fastlem_raster* r, double* d_out) {
     R.x0 = r->x0; R.y0 = r->y0; R.span_x = r->span_x; R.span_y = r->span_y; R.offset = r->pixel_offset;
     R.width = r->width; R.height = r->height; R.row_begin = r->row_begin; R.row_end = r->row_end;
     const uint32_t rows = r->row_end - r->row_begin;
-    const uint32_t tiles = ((r->width + 15u) / 16u) * ((rows + 15u) / 16u);
+    const uint64_t tiles64 = (uint64_t)((r->width + 15u) / 16u) * (uint64_t)((rows + 15u) / 16u);
+    if (tiles64 > 0x7FFFFFFFull)
+        return fail(c, FASTLEM_E_INVALID, "raster: too many pixels for one call, split the row range");
+    const uint32_t tiles = (uint32_t)tiles64;
     FLI_CK(fl_memset(c->d_flags, 0, sizeof(uint32_t) * FLI_N_FLAGS, c->stream));
     FLI_CK(fl_event_record(c->ev[0], c->stream));
     if (tiles) {
