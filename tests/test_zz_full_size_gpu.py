@@ -48,3 +48,27 @@ def test_ensemble_members_on_one_shared_graph_gpu(oracle, product_lib):
         ref, ref_it = oracle.generate(m, mem["erodibility"], mem["uplift"], ms, mem["outlets"], mem["initial"], 60)
         assert it == ref_it, k
         assert np.array_equal(e, ref), f"member {k}"
+
+
+def test_random_graphs_bit_exact_gpu(oracle, product_lib):
+    """The differential fuzz of tests/test_fuzz.py on the device: random small graphs (ties, several components, random
+    outlets, mixed max_slope), every sweep implementation, bit-exact against the oracle."""
+    import numpy as np
+    from fastlem_b200 import _native
+    from tools.fuzz_solver import random_case
+    done = 0
+    for seed in range(200, 280):
+        case = random_case(seed, oracle)
+        if case is None:
+            continue
+        m, p, outlets, initial, max_iteration = case
+        ref, ref_it = oracle.generate(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, initial, max_iteration)
+        for sweep in (0, 1, 2, 3):
+            with _native.Context(0, product_lib) as ctx:
+                ctx.set_option("sweep", sweep)
+                helpers.load_ctx(ctx, m, p, outlets, initial)
+                e, it = ctx.generate(max_iteration)
+            assert it == ref_it, (seed, sweep)
+            assert np.array_equal(e, ref, equal_nan=True), (seed, sweep)
+        done += 1
+    assert done >= 40
