@@ -333,7 +333,48 @@ def check_large_offsets(lib, O):
         assert np.isfinite(img).mean() > 0.9
 
 
+def check_fuzz(lib, O, seeds):
+    """Random triangulations that stress the geometry: 1000:1 anisotropic boxes, Gaussian clouds, dense clumps inside a
+    sparse field, tiny extents at large offsets; random queries, queries next to sites and on edge midpoints."""
+    from fastlem_b200 import _native, triangulation
+    for seed in seeds:
+        rng = np.random.default_rng(1000 + seed)
+        n = int(rng.integers(4, 500))
+        kind, off = seed % 4, [0.0, 1.0e4, -3.0e5, 7.0e6][(seed // 4) % 4]
+        if kind == 0:
+            sites = rng.random((n, 2)) * [1000.0, 1.0]
+        elif kind == 1:
+            sites = rng.normal(0.0, 1.0, (n, 2)) * [5.0, 50.0]
+        elif kind == 2:
+            sites = np.concatenate([rng.random((n, 2)) * 100.0, rng.random((n // 3 + 1, 2)) * 0.01 + 50.0])
+        else:
+            sites = rng.random((n, 2)) * 1.0e-3
+        sites = sites + off
+        tri, he = triangulation.delaunay(sites)
+        values = rng.random(sites.shape[0]) * 100.0
+        lo, hi = sites.min(axis=0), sites.max(axis=0)
+        T = tri.reshape(-1, 3)
+        k = rng.integers(0, T.shape[0], 50)
+        q = np.concatenate([lo + rng.random((300, 2)) * (hi - lo),
+                            sites[rng.integers(0, sites.shape[0], 50)] + rng.normal(0.0, 1e-9, (50, 2)) * (hi - lo),
+                            0.5 * (sites[T[k, 0]] + sites[T[k, 1]])])
+        with _native.Interpolator(sites, tri, he, lib_path=lib) as it:
+            it.set_values(values)
+            out = it.points(q)
+        ref = O.nn_interpolate(sites, tri, values, q)
+        # hull-edge midpoints may fall on either side of the hull in double / long double arithmetic
+        assert (np.isnan(out) != np.isnan(ref)).sum() <= 3, seed
+        ok = ~np.isnan(out) & ~np.isnan(ref)
+        # stolen regions bounded by the far-away circumcentres of hull slivers (1000:1 boxes, queries next to a hull
+        # site) are ill-conditioned in any formulation: a looser bar than NN_TOL here
+        assert ok.sum() > 100 and rel_err(out[ok], ref[ok]).max() <= 1e-6, seed
+
+
 # ---- CPU tier: emulation build -------------------------------------------------------------------
+def test_emu_fuzz(oracle, emu_lib):
+    check_fuzz(emu_lib, oracle, range(48))
+
+
 def test_emu_large_offsets(oracle, emu_lib):
     check_large_offsets(emu_lib, oracle)
 
@@ -419,6 +460,11 @@ def test_gpu_matches_golden(gpu_lib, path):
                                                  (20000, 5, (100.0, 100.0), 1)])
 def test_gpu_matches_oracle(oracle, gpu_lib, n, seed, bound, lloyd):
     check_against_oracle(gpu_lib, oracle, n, seed, 3000, bound, lloyd)
+
+
+@pytest.mark.gpu
+def test_gpu_fuzz(oracle, gpu_lib):
+    check_fuzz(gpu_lib, oracle, range(48, 96))
 
 
 @pytest.mark.gpu
