@@ -1,6 +1,9 @@
 """Differential fuzz of the solver against the oracle on random graphs (CPU: host emulation build; with --gpu the
 product library on cuda:0).
-    python tools/fuzz_solver.py [--gpu] [first_seed] [count] [min_n] [max_n]
+    python tools/fuzz_solver.py [--gpu] [--options] [first_seed] [count] [min_n] [max_n]
+--options: instead of looping over the sweep implementations, every case runs the default sweep with a random combination
+of the solver options (incremental, incr_div, rebuild_*, park_after, key_base, fuse_levels, first_flow, flood_device),
+twice on the same context.
 """
 import os
 import sys
@@ -67,7 +70,8 @@ def main():
     import helpers
     from fastlem_b200 import _native, build
     from oracle import oracle as O
-    args = [a for a in sys.argv[1:] if a != "--gpu"]
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    with_options = "--options" in sys.argv
     lib = _native.LIB_PATH if "--gpu" in sys.argv else build.build_emu()
     first, count = (int(args[0]) if args else 0), (int(args[1]) if len(args) > 1 else 400)
     min_n, max_n = (int(args[2]) if len(args) > 2 else 2), (int(args[3]) if len(args) > 3 else 80)
@@ -78,6 +82,22 @@ def main():
             continue
         m, p, outlets, initial, mi = case
         ref, ref_it = O.generate(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, initial, mi)
+        if with_options:
+            rng = np.random.default_rng(seed + 77)
+            opts = dict(incremental=int(rng.integers(0, 2)), incr_div=int(rng.choice([1, 2, 16, 64])),
+                        rebuild_every=int(rng.choice([0, 0, 1, 2, 5, 1000])), park_after=int(rng.choice([0, 4, 8, 64])),
+                        key_base=int(rng.choice([1, 2, 3, 254])), fuse_levels=int(rng.integers(0, 2)),
+                        first_flow=int(rng.integers(0, 2)), flood_device=int(rng.integers(0, 2)),
+                        rebuild_growth=int(rng.choice([1, 4, 50])), rebuild_height=int(rng.choice([100, 150, 400])))
+            with _native.Context(0, lib) as ctx:
+                for k, v in opts.items():
+                    ctx.set_option(k, v)
+                helpers.load_ctx(ctx, m, p, outlets, initial)
+                runs = [ctx.generate(mi), ctx.generate(mi)]
+            if any(it != ref_it or not np.array_equal(e, ref, equal_nan=True) for e, it in runs):
+                print("MISMATCH seed", seed, "n", m["n"], opts)
+                bad += 1
+            continue
         for sweep in (0, 1, 2, 3):
             with _native.Context(0, lib) as ctx:
                 ctx.set_option("sweep", sweep)
