@@ -418,6 +418,23 @@ def test_emu_values_from_solver(oracle, emu_lib):
     check_values_from_solver(emu_lib, oracle)
 
 
+def test_emu_device_pointer_entry_points(emu_lib):
+    """fastlem_interp_set_values_device / fastlem_interp_raster_device: in the emulation build "device" memory is host
+    memory, so numpy buffers stand in for the tensors bench.py and ensemble.raster_partitioned pass on the GPU."""
+    from fastlem_b200 import _native
+    _, sites, tri, he, values = make_case(1200, 81)
+    with _native.Interpolator(sites, tri, he, lib_path=emu_lib) as it:
+        it.set_values(values)
+        desc = it.raster_desc(40, 30, 0.0, 0.0, 100.0, 100.0, 0.5, 5, 25)
+        want = it.raster(desc)
+        it.set_values(np.zeros_like(values))
+        dev_values = np.ascontiguousarray(values)
+        it.set_values_device(dev_values.ctypes.data)
+        out = np.full((20, 40), -1.0)
+        it.raster_device(desc, out.ctypes.data)
+    assert np.array_equal(out, want, equal_nan=True)
+
+
 def test_emu_clustered_sites(oracle, emu_lib):
     """Strongly non-uniform sites: most hint cells are empty (several dilation passes) and walks are long."""
     from fastlem_b200 import _native
