@@ -918,7 +918,9 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
             return fail(c, FASTLEM_E_STATE, "K4: the fused pass waited for parked work too long (internal error)");
         maxh = c->h_flags[FL_FLAG_K4MAXH];
         if (incr && c->prev_maxh > maxh) maxh = c->prev_maxh;
-        if (!(c->h_flags[FL_FLAG_BROKEN] & 4u)) break;
+        // redo with the exact base when a key overflowed the fixed base, or when the bound carried over from the
+        // previous iteration (incremental passes only see the heights of the dirty segments) lies above it
+        if (!(c->h_flags[FL_FLAG_BROKEN] & 4u) && maxh <= key_base) break;
         if (attempt) return fail(c, FASTLEM_E_STATE, "flow: height bookkeeping broke (keys)");
         key_base = maxh;  // deeper than the fixed base: exact base, more key bits, the large host buffer
         FL_RC(ensure_h_offs(c));

@@ -92,11 +92,16 @@ def main():
                         key_base=int(rng.choice([1, 2, 3, 254])), fuse_levels=int(rng.integers(0, 2)),
                         first_flow=int(rng.integers(0, 2)), flood_device=int(rng.integers(0, 2)),
                         rebuild_growth=int(rng.choice([1, 4, 50])), rebuild_height=int(rng.choice([100, 150, 400])))
-            with _native.Context(0, lib) as ctx:
-                for k, v in opts.items():
-                    ctx.set_option(k, v)
-                helpers.load_ctx(ctx, m, p, outlets, initial)
-                runs = [ctx.generate(mi), ctx.generate(mi)]
+            try:
+                with _native.Context(0, lib) as ctx:
+                    for k, v in opts.items():
+                        ctx.set_option(k, v)
+                    helpers.load_ctx(ctx, m, p, outlets, initial)
+                    runs = [ctx.generate(mi), ctx.generate(mi)]
+            except _native.FastlemError as ex:
+                print("ERROR seed", seed, "n", m["n"], opts, ex)
+                bad += 1
+                continue
             if any(it != ref_it or not np.array_equal(e, ref, equal_nan=True) for e, it in runs):
                 print("MISMATCH seed", seed, "n", m["n"], opts)
                 bad += 1
