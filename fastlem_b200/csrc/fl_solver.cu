@@ -586,7 +586,7 @@ int iterate_levels(fastlem_ctx* c, bool first, bool* changed_out) {
         for (uint32_t lv = 0; lv <= maxd; ++lv) {  // K5: roots first
             const uint32_t b = c->h_offs[lv], cnt = c->h_offs[lv + 1] - b;
             LAUNCH_N(k_elev_level, cnt, b, cnt, (int)lv, c->d_order, L.recv, c->d_label, L.drecv, c->d_A, L.erod,
-                     L.uplift, L.tan, L.elev, c->d_rt, c->d_flags);
+                     L.uplift, c->has_tan ? L.tan : nullptr, L.elev, c->d_rt, c->d_flags);
         }
         c->stats.n_elevation += maxd + 1;
     } else {

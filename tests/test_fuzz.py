@@ -49,3 +49,38 @@ def test_height_bound_above_key_base_regression(oracle, emu_lib, seed, opts):
         helpers.load_ctx(ctx, m, p, outlets, initial)
         e, it = ctx.generate(mi)
     assert it == ref_it and np.array_equal(e, ref, equal_nan=True)
+
+
+def test_context_reuse_sequences(oracle, emu_lib):
+    """One context through random sequences of set_graph / set_parameters / set_option('sweep') / generate: graphs of
+    different sizes, outlets that change, max_slope present in one run and absent in the next (this used to leave the
+    level-synchronous path clamping with the previous run's slopes), plateaus; every run bit-exact against the oracle."""
+    from fastlem_b200 import _native
+    from tools.fuzz_solver import random_graph
+    for seed in range(25):
+        rng = np.random.default_rng(seed)
+        graphs = [random_graph(rng, 5, 200) for _ in range(2)]
+        with _native.Context(0, emu_lib) as ctx:
+            m = outlets = None
+            for step in range(8):
+                if step == 0 or rng.random() < 0.25:
+                    m = graphs[int(rng.integers(0, 2))]
+                    n = m["n"]
+                    ctx.set_graph(m["row_ptr"], m["col"], m["dist"], m["areas"])
+                    outlets = None
+                if outlets is None or rng.random() < 0.4:
+                    outlets = np.sort(rng.choice(n, int(rng.integers(1, max(2, n // 6))), replace=False)).astype(np.uint32)
+                ms = None
+                if rng.random() < 0.4:
+                    ms = 0.05 + rng.random(n) * 0.8
+                    ms[rng.random(n) < 0.3] = np.nan
+                k = 0.2 + rng.random(n) * 2
+                u = np.ones(n) if rng.random() < 0.5 else 0.5 + rng.random(n)
+                initial = oracle.initial_elevations(np.zeros(n) if rng.random() < 0.7 else rng.random(n))
+                mi = int(rng.integers(1, 50))
+                if rng.random() < 0.3:
+                    ctx.set_option("sweep", int(rng.integers(0, 4)))
+                ctx.set_parameters(initial, k, u, helpers.tan_of(ms), outlets)
+                e, it = ctx.generate(mi)
+                ref, ref_it = oracle.generate(m, k, u, ms, outlets, initial, mi)
+                assert it == ref_it and np.array_equal(e, ref, equal_nan=True), (seed, step)
