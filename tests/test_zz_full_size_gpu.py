@@ -72,3 +72,37 @@ def test_random_graphs_bit_exact_gpu(oracle, product_lib):
             assert np.array_equal(e, ref, equal_nan=True), (seed, sweep)
         done += 1
     assert done >= 40
+
+
+def test_context_reuse_sequences_gpu(oracle, product_lib):
+    """tests/test_fuzz.py::test_context_reuse_sequences on the device (other seeds)."""
+    import numpy as np
+    from fastlem_b200 import _native
+    from tools.fuzz_solver import random_graph
+    for seed in range(100, 120):
+        rng = np.random.default_rng(seed)
+        graphs = [random_graph(rng, 5, 200) for _ in range(2)]
+        with _native.Context(0, product_lib) as ctx:
+            m = outlets = None
+            for step in range(8):
+                if step == 0 or rng.random() < 0.25:
+                    m = graphs[int(rng.integers(0, 2))]
+                    n = m["n"]
+                    ctx.set_graph(m["row_ptr"], m["col"], m["dist"], m["areas"])
+                    outlets = None
+                if outlets is None or rng.random() < 0.4:
+                    outlets = np.sort(rng.choice(n, int(rng.integers(1, max(2, n // 6))), replace=False)).astype(np.uint32)
+                ms = None
+                if rng.random() < 0.4:
+                    ms = 0.05 + rng.random(n) * 0.8
+                    ms[rng.random(n) < 0.3] = np.nan
+                k = 0.2 + rng.random(n) * 2
+                u = np.ones(n) if rng.random() < 0.5 else 0.5 + rng.random(n)
+                initial = oracle.initial_elevations(np.zeros(n) if rng.random() < 0.7 else rng.random(n))
+                mi = int(rng.integers(1, 50))
+                if rng.random() < 0.3:
+                    ctx.set_option("sweep", int(rng.integers(0, 4)))
+                ctx.set_parameters(initial, k, u, helpers.tan_of(ms), outlets)
+                e, it = ctx.generate(mi)
+                ref, ref_it = oracle.generate(m, k, u, ms, outlets, initial, mi)
+                assert it == ref_it and np.array_equal(e, ref, equal_nan=True), (seed, step)
