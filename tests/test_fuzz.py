@@ -84,3 +84,42 @@ def test_context_reuse_sequences(oracle, emu_lib):
                 e, it = ctx.generate(mi)
                 ref, ref_it = oracle.generate(m, k, u, ms, outlets, initial, mi)
                 assert it == ref_it and np.array_equal(e, ref, equal_nan=True), (seed, step)
+
+
+def check_special_parameter_values(lib, oracle, seeds):
+    """Zero, negative, infinite and denormal-range erodibility / uplift on a tenth of the sites: infinities and NaNs
+    appear in response times and elevations and must propagate exactly as in the oracle (f64::max semantics of
+    generator.rs:179, IEEE division), for the level-synchronous and the dataflow sweeps."""
+    from fastlem_b200 import _native
+    for seed in seeds:
+        m, p, outlets, initial, mi = random_case(seed, oracle, 2, 120, (1, 30))
+        rng = np.random.default_rng(seed + 9)
+        n = m["n"]
+        k, u = p["erodibility"].copy(), p["uplift"].copy()
+        idx = rng.choice(n, max(1, n // 10), replace=False)
+        kind = seed % 6
+        if kind == 0:
+            k[idx] = 0.0
+        elif kind == 1:
+            k[idx] = 1e300
+        elif kind == 2:
+            u[idx] = 0.0
+        elif kind == 3:
+            u[idx] = -1.0
+        elif kind == 4:
+            k[idx] = np.inf
+        else:
+            u[idx] = 1e-300
+            k[idx] = 1e-300
+        ref, ref_it = oracle.generate(m, k, u, p["max_slope"], outlets, initial, mi)
+        for sweep in (0, 3):
+            with _native.Context(0, lib) as ctx:
+                ctx.set_option("sweep", sweep)
+                ctx.set_graph(m["row_ptr"], m["col"], m["dist"], m["areas"])
+                ctx.set_parameters(initial, k, u, helpers.tan_of(p["max_slope"]), outlets)
+                e, it = ctx.generate(mi)
+            assert it == ref_it and np.array_equal(e, ref, equal_nan=True), (seed, kind, sweep)
+
+
+def test_special_parameter_values(oracle, emu_lib):
+    check_special_parameter_values(emu_lib, oracle, range(60))

@@ -106,3 +106,9 @@ def test_context_reuse_sequences_gpu(oracle, product_lib):
                 e, it = ctx.generate(mi)
                 ref, ref_it = oracle.generate(m, k, u, ms, outlets, initial, mi)
                 assert it == ref_it and np.array_equal(e, ref, equal_nan=True), (seed, step)
+
+
+def test_special_parameter_values_gpu(oracle, product_lib):
+    """tests/test_fuzz.py::check_special_parameter_values on the device (inf / NaN propagation, other seeds)."""
+    from test_fuzz import check_special_parameter_values
+    check_special_parameter_values(product_lib, oracle, range(60, 120))
