@@ -14,8 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = [os.path.join(CSRC, f) for f in ("fl_solver.cu", "fl_interp.cu", "fl_flood.cpp", "fl_host.cpp")]
-HEADERS = [os.path.join(CSRC, f) for f in ("fl_rt.h", "fl_kernels.cuh", "fl_paths.cuh", "fl_flow.cuh", "fl_floodgpu.cuh",
-                                                 "fl_interp.cuh", "fl_flood.h")] + \
+HEADERS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".hpp"))) + \
           [os.path.join(ROOT, "include", "fastlem_b200.h")]
 LIB = os.path.join(HERE, "_lib", "libfastlem_b200.so")
 EMU_LIB = os.path.join(ROOT, "tests", "_emu", "libfastlem_emu.so")

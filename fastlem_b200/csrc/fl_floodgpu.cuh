@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(256) k_flg_sizes(FlFloodG g) {
         atomicAdd(&g.size[p], sz);
         __threadfence();
         if (atomicSub(&g.cnt[p], 1u) != 2u) return;  // somebody else arrives last (counts are biased by one)
+        __threadfence();  // acquire side: the other children's additions to size[p]
         sz = atomicAdd(&g.size[p], 0u);
         v = p;
     }

@@ -63,10 +63,22 @@ __device__ __forceinline__ unsigned long long fl_gtime() {
 #define FL_TLOG(f, site, slot) ((void)0)
 #endif
 
+// Hand-offs between threads of one launch follow the PTX memory model's release / acquire patterns at gpu scope:
+//   producer:  plain stores ... fence.acq_rel.gpu ; atomic (relaxed)        -- release pattern
+//   consumer:  atomic (relaxed) or ld.acquire.gpu ... fence.acq_rel.gpu ; plain loads   -- acquire pattern
+// The consumer-side fence sits on the WINNER path only (the last reporter / last publisher / the waiter whose flag
+// came up), so the common "somebody else arrives last" path pays nothing.  -DFL_RELAXED_READERS=1 builds the
+// round-1 variant without the consumer-side fences (ordering by an address dependency on the atomic's result only;
+// not covered by the memory model) for A/B timing: tools/ab_acquire.py, profiles/r2_ab_acquire.txt.
+#ifndef FL_RELAXED_READERS
+#define FL_RELAXED_READERS 0
+#endif
 #ifdef FL_EMU
 template <class T> __device__ __forceinline__ T fl_ld_cg(const T* p) { return *p; }
 __device__ __forceinline__ uint32_t fl_ld_relaxed(const uint32_t* p) { return *p; }
+__device__ __forceinline__ uint32_t fl_ld_acquire(const uint32_t* p) { return *p; }
 __device__ __forceinline__ uint32_t fl_dep0(uint32_t) { return 0u; }
+__device__ __forceinline__ void fl_fence_acquire() {}
 #else
 template <class T> __device__ __forceinline__ T fl_ld_cg(const T* p) { return __ldcg(p); }
 // relaxed gpu-scope load of a flag word (served by L2, pipelinable)
@@ -75,14 +87,26 @@ __device__ __forceinline__ uint32_t fl_ld_relaxed(const uint32_t* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// An opaque zero derived from v.  Adding it to an index makes the following loads ADDRESS-DEPENDENT on the
-// atomic result v, so they are issued only after v has arrived and are served by L2 after the writers'
-// fence + atomic: the reader side needs no fence of its own.
+#if FL_RELAXED_READERS
+__device__ __forceinline__ uint32_t fl_ld_acquire(const uint32_t* p) { return fl_ld_relaxed(p); }
+__device__ __forceinline__ void fl_fence_acquire() {}
+// An opaque zero derived from v: makes the following loads ADDRESS-DEPENDENT on the atomic result v (A/B variant only)
 __device__ __forceinline__ uint32_t fl_dep0(uint32_t v) {
     uint32_t z;
     asm volatile("and.b32 %0, %1, 0;" : "=r"(z) : "r"(v));
     return z;
 }
+#else
+// acquire load of a flag word at gpu scope: loads that follow it in program order see everything the writer released
+__device__ __forceinline__ uint32_t fl_ld_acquire(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// acquire side of a hand-off decided by a relaxed atomic: fence after the atomic, before the dependent loads
+__device__ __forceinline__ void fl_fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ uint32_t fl_dep0(uint32_t) { return 0u; }
+#endif
 #endif
 
 __device__ __forceinline__ uint32_t fl_st_publish(uint32_t np, uint32_t hp) {
@@ -265,7 +289,8 @@ __device__ __forceinline__ uint32_t fl_gather_store(const FlFlow& f, uint32_t p,
 // that the round trips overlap.
 __device__ __forceinline__ uint32_t fl_report(const FlFlow& f, uint32_t h, uint32_t p, bool fenced, uint32_t* dep_out) {
     (void)h;
-    if (!fenced) fl_fence_release();  // publish A[h], hgt[h]
+    if (!fenced) fl_fence_release();  // publish A[h], hgt[h] (and, by cumulativity, what the caller's warp stored
+                                      // before its __syncwarp())
     const uint32_t prev = atomicAdd(&f.state[p], 1u);
     const uint32_t nw = f.nwait[p] & FL_NW_COUNT;
     const uint32_t sh = f.seg_head[p];
@@ -273,10 +298,12 @@ __device__ __forceinline__ uint32_t fl_report(const FlFlow& f, uint32_t h, uint3
     if ((prev & FL_ST_COUNT_MASK) + 1u < nw) return FL_NONE;
     // last reporter at p: gather and publish p's partial sums
     const uint32_t swait = f.seg_wait[sh];
+    fl_fence_acquire();  // the other reporters' A / hgt: acquire side of their fence + atomic on state[p]
     f.state[p] = fl_gather_store(f, p, p_has_chain, fl_dep0(prev));  // no report can follow the last one: a plain store
     fl_fence_release();  // publish the partial sums before the segment counter moves
     const uint32_t done = atomicAdd(&f.seg_done[sh], 1u) + 1u;
     if (done < swait) return FL_NONE;
+    fl_fence_acquire();  // the other publishers' partial sums: acquire side of their fence + atomic on seg_done[sh]
     *dep_out = fl_dep0(done);
     return fl_seg_start(f, sh);  // every waiting site of the segment is published: climb it
 }
@@ -649,10 +676,10 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
         }
         uint32_t next_tail = FL_NONE, dep = 0u;
         const long long t_rep = FL_CLOCK();
-        fl_fence_release();  // every lane publishes its own stores (A, hgt) before lane 0 reports
-        __syncwarp();
-        if (lane == 0) next_tail = fl_report(f, h, p, true, &dep);
+        __syncwarp();  // the lanes' stores (A, hsuf, hgt) happen before lane 0's release fence inside fl_report
+        if (lane == 0) next_tail = fl_report(f, h, p, false, &dep);
         next_tail = __shfl_sync(FL_FULL, next_tail, 0);
+        __syncwarp();  // lane 0's acquire fence happens before the other lanes' loads of the next segment
         if (lane == 0) FL_COUNT(f, FLS_W_CYC_REPORT, FL_CLOCK() - t_rep);
         if (next_tail == FL_NONE) return;
         if (lane == 0) FL_COUNT(f, FLS_W_SEGSTART, 1);
@@ -809,7 +836,7 @@ __global__ void __launch_bounds__(256, 2) k_incr_flow(FlFlow f) {
             idx = atomicAdd(&f.counters[1], 1u);
             uint32_t spins = 0u;
             for (;;) {
-                if (fl_ld_relaxed(&f.ready[idx]) != 0u) { what = 1u; break; }
+                if (fl_ld_acquire(&f.ready[idx]) != 0u) { what = 1u; break; }
                 if ((spins & 3u) == 0u && fl_ld_relaxed(f.remaining) == 0u) { what = 2u; break; }
                 __nanosleep(200);
                 if (++spins > (1u << 21)) { atomicOr(&f.flags[FL_FLAG_BROKEN], 8u); what = 2u; break; }
@@ -817,6 +844,7 @@ __global__ void __launch_bounds__(256, 2) k_incr_flow(FlFlow f) {
         }
         idx = __shfl_sync(FL_FULL, idx, 0);
         what = __shfl_sync(FL_FULL, what, 0);
+        __syncwarp();  // lane 0's acquire load happens before the other lanes' loads of the parked climb
         if (what == 2u) return;
         const uint32_t cur = fl_ld_cg(&f.parked[idx]);
         if (lane == 0) { FL_COUNT(f, FLS_W_FLOWS, 1); FL_TLOG(f, cur, 2); }
@@ -852,6 +880,7 @@ __global__ void __launch_bounds__(256) k_subtree_sweep(uint32_t n, const uint32_
         atomicAdd(&size[p], sz);
         __threadfence();
         if (atomicSub(&pend[p], 1u) != 2u) return;  // somebody else arrives last
+        __threadfence();  // acquire side: the other children's additions to size[p]
         sz = atomicAdd(&size[p], 0u);
         v = p;
     }
@@ -1271,14 +1300,12 @@ __global__ void __launch_bounds__(128) k_elev_flow_fused(FlFused u, FlElev e) {
         e.lvl_value = u.lvl_of[i];
         if (!is_root) {  // wait for the receiver's segment
             const uint32_t j = u.ticket_of[u.seg_head[p]];
-            if (lane == 0) {
-                uint32_t spins = 0u;
-                while (fl_ld_relaxed(&u.done[j]) == 0u) {
-                    __nanosleep(40);
-                    if (++spins > (1u << 24)) { atomicOr(&e.flags[FL_FLAG_BROKEN], 2u); break; }
-                }
+            // every lane runs its own acquire load of the flag (one broadcast transaction per round)
+            uint32_t spins = 0u;
+            while (!__all_sync(FL_FULL, fl_ld_acquire(&u.done[j]) != 0u)) {
+                __nanosleep(40);
+                if (++spins > (1u << 24)) { if (lane == 0) atomicOr(&e.flags[FL_FLAG_BROKEN], 2u); break; }
             }
-            __syncwarp();
         }
         uint32_t root;
         double rt_prev, z_prev, e_out, rt_out;
@@ -1316,9 +1343,8 @@ __global__ void __launch_bounds__(128) k_elev_flow_fused(FlFused u, FlElev e) {
                 changed |= fl_elev_warp(e, h + 1u, root, rt_prev, z_prev, e_out, rt_out, sm);
             if (changed && lane == 0) e.flags[FL_FLAG_CHANGED] = 1u;
         }
-        fl_fence_release();  // every lane publishes its own stores before the ticket is marked done
-        __syncwarp();
-        if (lane == 0) atomicExch(&u.done[i], 1u);
+        __syncwarp();  // the lanes' stores happen before lane 0's release fence
+        if (lane == 0) { fl_fence_release(); atomicExch(&u.done[i], 1u); }
     }
 #endif
 }

@@ -342,6 +342,13 @@ __global__ void __launch_bounds__(256) k_rank_inverse(uint32_t n, const uint32_t
     if (t != FL_NONE) rank_to_node[t] = q;
 }
 
+// a[k] <- newpos[a[k]]  (a list of site ids follows a renumbering)
+__global__ void __launch_bounds__(256) k_map_list(uint32_t count, const uint32_t* __restrict__ newpos,
+                                                   uint32_t* __restrict__ a) {
+    uint32_t k = FL_TID;
+    if (k < count) a[k] = newpos[a[k]];
+}
+
 __global__ void __launch_bounds__(256) k_iota(uint32_t n, uint32_t* __restrict__ a) {
     uint32_t q = FL_TID;
     if (q < n) a[q] = q;

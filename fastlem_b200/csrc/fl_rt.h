@@ -58,6 +58,7 @@ inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
 inline int __ffsll(long long x) { return __builtin_ffsll(x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
 
 template <class F> inline void fl_emu_launch(unsigned grid, unsigned block, F&& f) {
     gridDim = fl_dim3(grid);

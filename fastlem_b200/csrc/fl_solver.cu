@@ -22,6 +22,7 @@
 #include "fl_flood.h"
 #include "fl_kernels.cuh"
 #include "fl_flow.cuh"
+#include "fl_elev.cuh"
 #include "fl_floodgpu.cuh"
 #include "fl_paths.cuh"
 
@@ -136,6 +137,16 @@ struct fastlem_ctx {
     int incr_flow_blocks = 0;         // resident blocks of k_incr_flow (0 = not available)
     int64_t opt_fuse_k4 = 0;     // measured no faster than two launches: kept as an option
     int64_t opt_first_flow = 1;  // the first iteration also uses the dataflow sweeps (layout by subtree sizes)
+    // K5 as one launch (fl_elev.cuh): queues of segment heads, the outlets as seeds
+    unsigned long long* d_queue = nullptr;
+    unsigned long long* d_lqueue = nullptr;
+    uint32_t lqueue_cap = 0;
+    uint32_t* d_seeds_orig = nullptr;  // the outlets, caller's numbering
+    uint32_t* d_seeds = nullptr;       // current numbering
+    uint32_t n_seeds = 0;
+    uint32_t push_epoch = 0;
+    int push_blocks = 0;
+    int64_t opt_k5_push = 1;
     uint32_t* d_ticket_of = nullptr;  // fused sparse levels of K5
     uint32_t* d_fdone = nullptr;
     uint32_t* d_flvl = nullptr;
@@ -654,6 +665,7 @@ int rebuild_layout(fastlem_ctx* c, const double* weight) {
     a.lvl = nullptr; a.lvl_n = nullptr;
     LAUNCH_N(k_permute_nodes, n, n, c->d_newpos, a);
     c->cur ^= 1;
+    LAUNCH_N(k_map_list, c->n_seeds, c->n_seeds, c->d_newpos, c->d_seeds);
     if (c->rank_ready) LAUNCH_N(k_rank_inverse, n, n, M.rank, c->d_rank_to_node);
     FL_CK(fl_stream_sync(c->stream));  // h_offs
     for (uint32_t g = c->n_groups; g-- > 0;)  // keys that do not occur (e.g. a level without long paths)
@@ -769,6 +781,7 @@ int rebuild_layout_flow(fastlem_ctx* c, const double* weight) {
     a.lvl = L.lvl; a.lvl_n = M.lvl;
     LAUNCH_N(k_permute_nodes, n, n, c->d_newpos, a);
     c->cur ^= 1;
+    LAUNCH_N(k_map_list, c->n_seeds, c->n_seeds, c->d_newpos, c->d_seeds);
     if (c->rank_ready) LAUNCH_N(k_rank_inverse, n, n, M.rank, c->d_rank_to_node);
     c->stats.n_order += 10;
     c->stats.rebuilds++;
@@ -886,117 +899,165 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     }
     FL_RC(stage_mark(c, 8));  // end of K4
 
-    // order the segment heads by descending nesting height (exact for the current forest; an upper bound of the
-    // largest height after incremental passes -- heights that no longer occur are empty levels)
-    // Keys are base - height with a fixed base, so the sort does not have to wait for the host to learn the largest
-    // height: one read-back after the level offsets brings everything.  Only when segments nest deeper than the fixed
-    // base (stale numbering in the first iterations) the ordering is redone with the exact height as base.
-    uint32_t key_base = (uint32_t)c->opt_key_base;
-    uint32_t* hbuf = c->h_offs_k;
-    uint32_t maxh = 0;
-    for (int attempt = 0;; ++attempt) {
-        int bits = 8;
-        if (attempt || key_base != FL_KEY_BASE) {
-            bits = 1;
-            while (bits < 32 && (1ull << bits) <= (unsigned long long)key_base + 1ull) ++bits;
-        }
-        if (attempt) {
-            FL_CK(fl_memset(c->d_flags + FL_FLAG_BROKEN, 0, sizeof(uint32_t), c->stream));
-            FL_CK(fl_d2d(c->d_flags + FL_FLAG_MAXDEPTH, c->d_flags + FL_FLAG_K4MAXH, sizeof(uint32_t), c->stream));
-        }
-        LAUNCH_N(k_flow_sort_keys, n, n, c->d_hgt, key_base, c->d_depth, c->d_flags);
-        FL_CK(fl_sort_pairs(c->d_tmp, c->tmp_bytes, c->d_depth, c->d_sorted, c->d_iota, c->d_order, n, bits, c->stream,
-                            false));
-        FL_CK(fl_memset(c->d_flags + FL_FLAG_MAXDEPTH, 0xFF, sizeof(uint32_t), c->stream));
-        FL_CK(fl_memset(c->d_offs, 0xFF, sizeof(uint32_t) * ((size_t)key_base + 2), c->stream));
-        LAUNCH_N(k_level_offsets, n, n, c->d_sorted, c->d_offs, c->d_flags);
-        FL_CK(fl_d2h(hbuf, c->d_offs, sizeof(uint32_t) * ((size_t)key_base + 2), c->stream));
-        FL_RC(read_flags(c));
-        if (c->h_flags[FL_FLAG_BROKEN] & 1u)
-            return fail(c, FASTLEM_E_STATE, "K4: a climb met an unpublished site (internal error)");
-        if (c->h_flags[FL_FLAG_BROKEN] & 8u)
-            return fail(c, FASTLEM_E_STATE, "K4: the fused pass waited for parked work too long (internal error)");
-        maxh = c->h_flags[FL_FLAG_K4MAXH];
-        if (incr && c->prev_maxh > maxh) maxh = c->prev_maxh;
-        // redo with the exact base when a key overflowed the fixed base, or when the bound carried over from the
-        // previous iteration (incremental passes only see the heights of the dirty segments) lies above it
-        if (!(c->h_flags[FL_FLAG_BROKEN] & 4u) && maxh <= key_base) break;
-        if (attempt) return fail(c, FASTLEM_E_STATE, "flow: height bookkeeping broke (keys)");
-        key_base = maxh;  // deeper than the fixed base: exact base, more key bits, the large host buffer
-        FL_RC(ensure_h_offs(c));
-        hbuf = c->h_offs;
-    }
-    uint32_t* const hoffs = hbuf + (key_base - maxh);  // hoffs[g]: first head of height maxh - g
-    const uint32_t last_abs = c->h_flags[FL_FLAG_MAXDEPTH];  // = key_base - (smallest height that occurs)
-    if (last_abs == FL_NONE || last_abs < key_base - maxh || last_abs > key_base || (!incr && last_abs != key_base))
-        return fail(c, FASTLEM_E_STATE, "flow: height bookkeeping broke");
-    const uint32_t last_key = last_abs - (key_base - maxh);
-    const uint32_t n_heads = c->h_flags[FL_FLAG_REACHED];
-    for (uint32_t g = last_key + 2; g <= maxh + 1; ++g) hoffs[g] = n_heads;
-    for (uint32_t g = maxh + 1; g-- > 0;)
-        if (hoffs[g] == FL_NONE) hoffs[g] = hoffs[g + 1];
-    if (hoffs[0] == FL_NONE) hoffs[0] = 0;
-    c->stats.n_order += 3;
-    c->stats.path_levels = maxh + 1;
-    c->stats.paths = n_heads;
-    c->prev_maxh = maxh;
-    if (rebuilt) { c->segs_at_rebuild = n_heads; c->maxh_at_rebuild = maxh; }
-    else if (c->opt_rebuild_every == 0 &&
-             ((unsigned long long)n_heads * 100ull >
-                  (unsigned long long)c->segs_at_rebuild * (100ull + (unsigned long long)c->opt_rebuild_growth) ||
-              (unsigned long long)maxh * 100ull >
-                  (unsigned long long)c->maxh_at_rebuild * (unsigned long long)c->opt_rebuild_height + 200ull))
-        c->need_rebuild = true;  // the numbering has degraded: renumber in the next iteration
-    if (c->trace_iters && it < 400u)
-        std::fprintf(stderr, "[fastlem trace] it %u: chg %u incr %d rebuilt %d heads %u maxh %u next_rebuild %d\n", it, n_chg,
-                     (int)incr, (int)rebuilt, n_heads, maxh, (int)c->need_rebuild);
-    FL_RC(stage_mark(c, 5));  // end of the head ordering
-
-    // K5: one launch per nesting height, outermost segments first
-    FlElev e;
-    LAUNCH_N(k_celerity_term, n, n, L.erod, c->d_A, L.drecv, c->d_tcel);
-    e.n = n; e.recv = L.recv; e.drecv = L.drecv; e.tcel = c->d_tcel; e.uplift = L.uplift;
-    e.tan_slope = c->has_tan ? L.tan : nullptr; e.is_outlet = L.is_outlet; e.elev = L.elev; e.rt = c->d_rt;
-    e.root_of = c->d_root_of; e.flags = c->d_flags; e.lvl = L.lvl; e.lvl_value = 0;
     uint32_t launched = 0;
-    // the sparse levels at the top of the forest go out as ONE launch (ticket order = level order)
-    uint32_t g_first = 0;
-    if (c->opt_fuse_levels) {
-        uint32_t gf = 0;
-        while (gf <= maxh && hoffs[gf + 1] - hoffs[gf] <= FL_WARP_LEVEL_MAX) ++gf;
-        const uint32_t total = hoffs[gf];
-        if (gf >= 2 && total > 0) {
-            FlFused u;
-            u.count = total; u.heads = c->d_order; u.seg_head = c->d_sg_head; u.ticket_of = c->d_ticket_of;
-            u.done = c->d_fdone; u.next_ticket = c->d_flags + FL_FLAG_TICKET; u.lvl_of = c->d_flvl;
-            LAUNCH_N(k_fused_index, total, total, c->d_order, c->d_hgt, c->d_ticket_of, c->d_flvl, c->d_fdone);
+    if (c->opt_k5_push) {
+        // K5 as one launch (fl_elev.cuh): no ordering of the segment heads, nothing read back before the sweep
+        FL_RC(stage_mark(c, 5));
+        FlPush e;
+        e.n = n; e.row_ptr = L.row_ptr; e.col = L.col; e.recv = L.recv; e.cmask = L.cmask; e.drecv = L.drecv;
+        e.erod = L.erod; e.A = c->d_A; e.uplift = L.uplift; e.tan_slope = c->has_tan ? L.tan : nullptr;
+        e.elev = L.elev; e.rt = c->d_rt; e.root_of = c->d_root_of; e.queue = c->d_queue; e.lqueue = c->d_lqueue;
+        e.lcap = c->lqueue_cap; e.epoch = ++c->push_epoch; e.seeds = c->d_seeds; e.n_seeds = c->n_seeds;
+        e.flags = c->d_flags;
+        FL_LAUNCH(k_push_seed, blocks_for(c->n_seeds ? c->n_seeds : 1u), 256, c->stream, e);
 #ifdef FL_EMU
-            const unsigned blocks = blocks_for(total, 128);  // emulation: one thread per ticket, in ticket order
+        FL_LAUNCH(k_elev_push, 1, 1, c->stream, e);
 #else
-            unsigned blocks = blocks_for(total * 32u, 128);
-            const unsigned cap = (unsigned)c->sm_count * 8u;
-            if (blocks > cap) blocks = cap;
+        FL_LAUNCH(k_elev_push, (unsigned)c->push_blocks, 256, c->stream, e);
 #endif
-            FL_LAUNCH(k_elev_flow_fused, blocks, 128, c->stream, u, e);
-            launched += 1;
-            g_first = gf;
+        launched = 2;
+    } else {
+        // order the segment heads by descending nesting height (exact for the current forest; an upper bound of the
+        // largest height after incremental passes -- heights that no longer occur are empty levels)
+        // Keys are base - height with a fixed base, so the sort does not have to wait for the host to learn the largest
+        // height: one read-back after the level offsets brings everything.  Only when segments nest deeper than the fixed
+        // base (stale numbering in the first iterations) the ordering is redone with the exact height as base.
+        uint32_t key_base = (uint32_t)c->opt_key_base;
+        uint32_t* hbuf = c->h_offs_k;
+        uint32_t maxh = 0;
+        for (int attempt = 0;; ++attempt) {
+            int bits = 8;
+            if (attempt || key_base != FL_KEY_BASE) {
+                bits = 1;
+                while (bits < 32 && (1ull << bits) <= (unsigned long long)key_base + 1ull) ++bits;
+            }
+            if (attempt) {
+                FL_CK(fl_memset(c->d_flags + FL_FLAG_BROKEN, 0, sizeof(uint32_t), c->stream));
+                FL_CK(fl_d2d(c->d_flags + FL_FLAG_MAXDEPTH, c->d_flags + FL_FLAG_K4MAXH, sizeof(uint32_t), c->stream));
+            }
+            LAUNCH_N(k_flow_sort_keys, n, n, c->d_hgt, key_base, c->d_depth, c->d_flags);
+            FL_CK(fl_sort_pairs(c->d_tmp, c->tmp_bytes, c->d_depth, c->d_sorted, c->d_iota, c->d_order, n, bits, c->stream,
+                                false));
+            FL_CK(fl_memset(c->d_flags + FL_FLAG_MAXDEPTH, 0xFF, sizeof(uint32_t), c->stream));
+            FL_CK(fl_memset(c->d_offs, 0xFF, sizeof(uint32_t) * ((size_t)key_base + 2), c->stream));
+            LAUNCH_N(k_level_offsets, n, n, c->d_sorted, c->d_offs, c->d_flags);
+            FL_CK(fl_d2h(hbuf, c->d_offs, sizeof(uint32_t) * ((size_t)key_base + 2), c->stream));
+            FL_RC(read_flags(c));
+            if (c->h_flags[FL_FLAG_BROKEN] & 1u)
+                return fail(c, FASTLEM_E_STATE, "K4: a climb met an unpublished site (internal error)");
+            if (c->h_flags[FL_FLAG_BROKEN] & 8u)
+                return fail(c, FASTLEM_E_STATE, "K4: the fused pass waited for parked work too long (internal error)");
+            maxh = c->h_flags[FL_FLAG_K4MAXH];
+            if (incr && c->prev_maxh > maxh) maxh = c->prev_maxh;
+            // redo with the exact base when a key overflowed the fixed base, or when the bound carried over from the
+            // previous iteration (incremental passes only see the heights of the dirty segments) lies above it
+            if (!(c->h_flags[FL_FLAG_BROKEN] & 4u) && maxh <= key_base) break;
+            if (attempt) return fail(c, FASTLEM_E_STATE, "flow: height bookkeeping broke (keys)");
+            key_base = maxh;  // deeper than the fixed base: exact base, more key bits, the large host buffer
+            FL_RC(ensure_h_offs(c));
+            hbuf = c->h_offs;
         }
-    }
-    for (uint32_t g = g_first; g <= maxh; ++g) {
-        const uint32_t b = hoffs[g], cnt = hoffs[g + 1] - b;
-        if (!cnt) continue;
-        ++launched;
-        e.lvl_value = maxh - g;
-        if (cnt <= FL_WARP_LEVEL_MAX)  // few segments: a warp each
-            FL_LAUNCH(k_elev_flow_warps, blocks_for(cnt * 32u, 128), 128, c->stream, b, cnt, c->d_order, e);
-        else
-            FL_LAUNCH(k_elev_flow, blocks_for(cnt, 128), 128, c->stream, b, cnt, c->d_order, e);
+        uint32_t* const hoffs = hbuf + (key_base - maxh);  // hoffs[g]: first head of height maxh - g
+        const uint32_t last_abs = c->h_flags[FL_FLAG_MAXDEPTH];  // = key_base - (smallest height that occurs)
+        if (last_abs == FL_NONE || last_abs < key_base - maxh || last_abs > key_base || (!incr && last_abs != key_base))
+            return fail(c, FASTLEM_E_STATE, "flow: height bookkeeping broke");
+        const uint32_t last_key = last_abs - (key_base - maxh);
+        const uint32_t n_heads = c->h_flags[FL_FLAG_REACHED];
+        for (uint32_t g = last_key + 2; g <= maxh + 1; ++g) hoffs[g] = n_heads;
+        for (uint32_t g = maxh + 1; g-- > 0;)
+            if (hoffs[g] == FL_NONE) hoffs[g] = hoffs[g + 1];
+        if (hoffs[0] == FL_NONE) hoffs[0] = 0;
+        c->stats.n_order += 3;
+        c->stats.path_levels = maxh + 1;
+        c->stats.paths = n_heads;
+        c->prev_maxh = maxh;
+        if (rebuilt) { c->segs_at_rebuild = n_heads; c->maxh_at_rebuild = maxh; }
+        else if (c->opt_rebuild_every == 0 &&
+                 ((unsigned long long)n_heads * 100ull >
+                      (unsigned long long)c->segs_at_rebuild * (100ull + (unsigned long long)c->opt_rebuild_growth) ||
+                  (unsigned long long)maxh * 100ull >
+                      (unsigned long long)c->maxh_at_rebuild * (unsigned long long)c->opt_rebuild_height + 200ull))
+            c->need_rebuild = true;  // the numbering has degraded: renumber in the next iteration
+        if (c->trace_iters && it < 400u)
+            std::fprintf(stderr, "[fastlem trace] it %u: chg %u incr %d rebuilt %d heads %u maxh %u next_rebuild %d\n", it, n_chg,
+                         (int)incr, (int)rebuilt, n_heads, maxh, (int)c->need_rebuild);
+        FL_RC(stage_mark(c, 5));  // end of the head ordering
+
+        // K5: one launch per nesting height, outermost segments first
+        FlElev e;
+        LAUNCH_N(k_celerity_term, n, n, L.erod, c->d_A, L.drecv, c->d_tcel);
+        e.n = n; e.recv = L.recv; e.drecv = L.drecv; e.tcel = c->d_tcel; e.uplift = L.uplift;
+        e.tan_slope = c->has_tan ? L.tan : nullptr; e.is_outlet = L.is_outlet; e.elev = L.elev; e.rt = c->d_rt;
+        e.root_of = c->d_root_of; e.flags = c->d_flags; e.lvl = L.lvl; e.lvl_value = 0;
+        // the sparse levels at the top of the forest go out as ONE launch (ticket order = level order)
+        uint32_t g_first = 0;
+        if (c->opt_fuse_levels) {
+            uint32_t gf = 0;
+            while (gf <= maxh && hoffs[gf + 1] - hoffs[gf] <= FL_WARP_LEVEL_MAX) ++gf;
+            const uint32_t total = hoffs[gf];
+            if (gf >= 2 && total > 0) {
+                FlFused u;
+                u.count = total; u.heads = c->d_order; u.seg_head = c->d_sg_head; u.ticket_of = c->d_ticket_of;
+                u.done = c->d_fdone; u.next_ticket = c->d_flags + FL_FLAG_TICKET; u.lvl_of = c->d_flvl;
+                LAUNCH_N(k_fused_index, total, total, c->d_order, c->d_hgt, c->d_ticket_of, c->d_flvl, c->d_fdone);
+    #ifdef FL_EMU
+                const unsigned blocks = blocks_for(total, 128);  // emulation: one thread per ticket, in ticket order
+    #else
+                unsigned blocks = blocks_for(total * 32u, 128);
+                const unsigned cap = (unsigned)c->sm_count * 8u;
+                if (blocks > cap) blocks = cap;
+    #endif
+                FL_LAUNCH(k_elev_flow_fused, blocks, 128, c->stream, u, e);
+                launched += 1;
+                g_first = gf;
+            }
+        }
+        for (uint32_t g = g_first; g <= maxh; ++g) {
+            const uint32_t b = hoffs[g], cnt = hoffs[g + 1] - b;
+            if (!cnt) continue;
+            ++launched;
+            e.lvl_value = maxh - g;
+            if (cnt <= FL_WARP_LEVEL_MAX)  // few segments: a warp each
+                FL_LAUNCH(k_elev_flow_warps, blocks_for(cnt * 32u, 128), 128, c->stream, b, cnt, c->d_order, e);
+            else
+                FL_LAUNCH(k_elev_flow, blocks_for(cnt, 128), 128, c->stream, b, cnt, c->d_order, e);
+        }
     }
     c->stats.kernel_launches += launched; c->stats.n_elevation += launched;
     FL_RC(stage_mark(c, 6));
     FL_RC(read_flags(c));
     FL_CK(fl_last_error());
-    if (c->h_flags[FL_FLAG_BROKEN]) return fail(c, FASTLEM_E_STATE, "K5: a segment waited for its receiver's segment too long (internal error)");
+    if (c->opt_k5_push) {
+        if (c->h_flags[FL_FLAG_BROKEN] & 1u)
+            return fail(c, FASTLEM_E_STATE, "K4: a climb met an unpublished site (internal error)");
+        if (c->h_flags[FL_FLAG_BROKEN] & 8u)
+            return fail(c, FASTLEM_E_STATE, "K4: the fused pass waited for parked work too long (internal error)");
+        if (c->h_flags[FL_FLAG_BROKEN])
+            return fail(c, FASTLEM_E_STATE,
+                        "K5: the segment queue broke (internal error; flags " + std::to_string(c->h_flags[FL_FLAG_BROKEN]) +
+                            " tail " + std::to_string(c->h_flags[FLQ_TAIL]) + " head " + std::to_string(c->h_flags[FLQ_HEAD]) +
+                            " ltail " + std::to_string(c->h_flags[FLQ_LTAIL]) + " lhead " +
+                            std::to_string(c->h_flags[FLQ_LHEAD]) + " pending " + std::to_string(c->h_flags[FLQ_PENDING]) +
+                            " seeds " + std::to_string(c->n_seeds) + " iteration " + std::to_string(it) + ")");
+        // bookkeeping of the numbering: nesting height met by K4 (at the roots it finished), segments the sweep visited
+        uint32_t maxh = c->h_flags[FL_FLAG_MAXDEPTH];
+        if (incr && c->prev_maxh > maxh) maxh = c->prev_maxh;
+        const uint32_t n_heads = c->h_flags[FLQ_TAIL];
+        c->stats.path_levels = maxh + 1;
+        c->stats.paths = n_heads;
+        c->prev_maxh = maxh;
+        if (rebuilt) { c->segs_at_rebuild = n_heads; c->maxh_at_rebuild = maxh; }
+        else if (c->opt_rebuild_every == 0 &&
+                 ((unsigned long long)n_heads * 100ull >
+                      (unsigned long long)c->segs_at_rebuild * (100ull + (unsigned long long)c->opt_rebuild_growth) ||
+                  (unsigned long long)maxh * 100ull >
+                      (unsigned long long)c->maxh_at_rebuild * (unsigned long long)c->opt_rebuild_height + 200ull))
+            c->need_rebuild = true;
+        if (c->trace_iters && it < 400u)
+            std::fprintf(stderr, "[fastlem trace] it %u: chg %u incr %d rebuilt %d heads %u maxh %u next_rebuild %d\n", it,
+                         n_chg, (int)incr, (int)rebuilt, n_heads, maxh, (int)c->need_rebuild);
+    } else if (c->h_flags[FL_FLAG_BROKEN])
+        return fail(c, FASTLEM_E_STATE, "K5: a segment waited for its receiver's segment too long (internal error)");
     *changed_out = c->h_flags[FL_FLAG_CHANGED] != 0;
     if (c->opt_profile) {  // receivers | flags | lakes | rebuild + ordering | K4 | K5
         const int from[7] = {0, 1, 2, 3, 8, 7, 5}, to[7] = {1, 2, 3, 7, 5, 8, 6};
@@ -1031,6 +1092,7 @@ int reset_layout(fastlem_ctx* c) {
     FL_CK(fl_d2d(L.elev, c->d_init, sizeof(double) * n, c->stream));
     LAUNCH_N(k_iota, n, n, L.orig_of);
     FL_CK(fl_memset(L.lvl, 0, sizeof(uint32_t) * n, c->stream));
+    if (c->n_seeds) FL_CK(fl_d2d(c->d_seeds, c->d_seeds_orig, sizeof(uint32_t) * c->n_seeds, c->stream));
     c->prev_maxh = 0;
     c->k4_valid = false;
     c->k4_last_full = true;
@@ -1105,6 +1167,11 @@ int alloc_graph_buffers(fastlem_ctx* c, uint32_t n, uint32_t nnz) {
     FL_CK(dalloc(c, c->d_sg_wait, n));
     FL_CK(dalloc(c, c->d_sg_done, n));
     FL_CK(dalloc(c, c->d_ready, (size_t)n + 65536));
+    c->lqueue_cap = n / 8u + 64u;
+    FL_CK(dalloc(c, c->d_queue, n));
+    FL_CK(dalloc(c, c->d_lqueue, c->lqueue_cap));
+    FL_CK(dalloc(c, c->d_seeds_orig, n));
+    FL_CK(dalloc(c, c->d_seeds, n));
     FL_CK(dalloc(c, c->d_ticket_of, n));
     FL_CK(dalloc(c, c->d_fdone, n));
     FL_CK(dalloc(c, c->d_flvl, n));
@@ -1228,6 +1295,8 @@ int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
     } else if (s == "key_base") {
         if (value < 1 || value > (int64_t)FL_KEY_BASE) return fail(c, FASTLEM_E_INVALID, "option key_base: 1..254");
         c->opt_key_base = value;
+    } else if (s == "k5_push") {
+        c->opt_k5_push = value != 0;
     } else if (s == "fuse_levels") {
         c->opt_fuse_levels = value != 0;
     } else if (s == "rebuild_height") {
@@ -1287,7 +1356,17 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     LAUNCH_N(k_rev_slots, n, n, c->orig.row_ptr, c->orig.col, c->orig.dist, c->orig.rev, c->d_flags);
     FL_CK(fl_d2h(c->h_flags, c->d_flags, sizeof(uint32_t), c->stream));
     FL_CK(fl_memset(c->d_ready, 0, sizeof(uint32_t) * ((size_t)n + 65536), c->stream));
+    FL_CK(fl_memset(c->d_queue, 0, sizeof(unsigned long long) * n, c->stream));
+    FL_CK(fl_memset(c->d_lqueue, 0, sizeof(unsigned long long) * c->lqueue_cap, c->stream));
+    c->push_epoch = 0;
+    c->n_seeds = 0;
 #ifndef FL_EMU
+    {
+        int occ = 0;
+        c->push_blocks = fl_sm_count();
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elev_push, 256, 0) == cudaSuccess && occ > 0)
+            c->push_blocks = occ * fl_sm_count();
+    }
     {
         int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_incr_flow, 256, 0) == cudaSuccess && occ > 0)
@@ -1342,8 +1421,16 @@ int fastlem_set_parameters(fastlem_ctx* c, const double* initial_elevation, cons
     if (!initial_elevation || !erodibility || !uplift_rate || (n_outlets && !outlets))
         return fail(c, FASTLEM_E_INVALID, "set_parameters: null pointer");
     const uint32_t n = c->n;
-    for (uint32_t k = 0; k < n_outlets; ++k)
+    // stream_tree.rs:101-107 outlet table (static across iterations, so built once).  An outlet listed twice would be
+    // traversed twice by the reference (generator.rs:149: its basin's areas and response times accumulate twice); the
+    // crate's own outlet lists (ascending is_outlet indices / the hull cycle, generator.rs:120-132) never repeat a
+    // site, so duplicates are rejected instead of silently changing the result.
+    std::vector<uint8_t> table(n, 0);
+    for (uint32_t k = 0; k < n_outlets; ++k) {
         if (outlets[k] >= n) return fail(c, FASTLEM_E_INVALID, "set_parameters: outlet index out of range");
+        if (table[outlets[k]]) return fail(c, FASTLEM_E_INVALID, "set_parameters: an outlet is listed twice");
+        table[outlets[k]] = 1;
+    }
     FL_CK(fl_set_device(c->device));
     double t0 = wall_ms();
     FL_CK(fl_h2d(c->d_init, initial_elevation, sizeof(double) * n, c->stream));
@@ -1358,9 +1445,8 @@ int fastlem_set_parameters(fastlem_ctx* c, const double* initial_elevation, cons
         }
         FL_CK(fl_h2d(c->orig.tan, tan_max_slope, sizeof(double) * n, c->stream));
     }
-    // stream_tree.rs:101-107 outlet table (static across iterations, so built once)
-    std::vector<uint8_t> table(n, 0);
-    for (uint32_t k = 0; k < n_outlets; ++k) table[outlets[k]] = 1;
+    c->n_seeds = n_outlets;  // the seeds of the top-down sweep (fl_elev.cuh)
+    if (n_outlets) FL_CK(fl_h2d(c->d_seeds_orig, outlets, sizeof(uint32_t) * n_outlets, c->stream));
     FL_CK(fl_h2d(c->orig.is_outlet, table.data(), n, c->stream));
     FL_CK(fl_stream_sync(c->stream));
     // the flood order of lake removal is a function of (graph, outlets) only: keep it when an ensemble member changes

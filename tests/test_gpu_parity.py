@@ -145,7 +145,7 @@ def test_c7_nonuniform_uplift_lakes_every_iteration(oracle, gpu_ctx_factory):
 
 
 @pytest.mark.parametrize("opts", [dict(key_base=1), dict(fuse_levels=0), dict(incremental=0), dict(incr_div=1),
-                                  dict(flood_device=0), dict(fuse_k4=1), dict(first_flow=0)])
+                                  dict(flood_device=0), dict(fuse_k4=1), dict(first_flow=0), dict(k5_push=0)])
 @pytest.mark.parametrize("name,n", [("uniform", 30000), ("advanced", 20000), ("max_slope", 20000)])
 def test_solver_options_do_not_change_results(oracle, gpu_ctx_factory, name, n, opts):
     """Every scheduling option (deep-nesting ordering path, per-level K5 launches, full K4 every iteration, incremental
