@@ -300,7 +300,8 @@ class TerrainGenerator:
             outlets = model.default_outlets()
         # generator.rs:134-138
         initial = _native.host_initial_elevations(p.base_elevation, self._lib_path)
-        tan = None if p.max_slope is None else np.tan(p.max_slope)  # generator.rs:194, NaN stays NaN
+        # generator.rs:194 `max_slope.tan()`: libm's tan (np.tan's SIMD path differs by an ulp for ~0.5 % of the inputs)
+        tan = None if p.max_slope is None else _native.host_tan_max_slope(p.max_slope, self._lib_path)
         row_ptr, col, dist = model.graph()
         with _native.Context(self.device, self._lib_path) as ctx:
             ctx.set_graph(row_ptr, col, dist, model.areas())

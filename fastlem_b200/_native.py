@@ -24,7 +24,7 @@ _STAGE_DTYPE = {0: np.uint32, 1: np.uint32, 2: np.uint32, 3: np.uint32, 4: np.ui
 SYMBOLS = ["fastlem_create", "fastlem_destroy", "fastlem_last_error", "fastlem_get_device", "fastlem_set_graph",
            "fastlem_set_parameters", "fastlem_generate", "fastlem_run", "fastlem_download", "fastlem_download_to_device",
            "fastlem_set_option", "fastlem_get_stats", "fastlem_debug_fetch", "fastlem_version",
-           "fastlem_host_initial_elevations", "fastlem_host_graph_from_triangles",
+           "fastlem_host_initial_elevations", "fastlem_host_tan_max_slope", "fastlem_host_graph_from_triangles",
            "fastlem_interp_create", "fastlem_interp_destroy", "fastlem_interp_last_error", "fastlem_interp_set_values",
            "fastlem_interp_set_values_device", "fastlem_interp_set_values_from", "fastlem_interp_points",
            "fastlem_interp_raster", "fastlem_interp_raster_device", "fastlem_interp_get_stats"]
@@ -101,6 +101,8 @@ def load(path=None):
     lib.fastlem_version.restype = ctypes.c_char_p
     lib.fastlem_host_initial_elevations.argtypes = [u32, f64p, f64p]
     lib.fastlem_host_initial_elevations.restype = None
+    lib.fastlem_host_tan_max_slope.argtypes = [u32, f64p, f64p]
+    lib.fastlem_host_tan_max_slope.restype = None
     lib.fastlem_host_graph_from_triangles.argtypes = [u32, f64p, u32, u32p, u32p, u32p, f64p, ctypes.c_uint64,
                                                       ctypes.POINTER(ctypes.c_uint64)]
     lib.fastlem_interp_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, u32, f64p, u32, u32p, u32p]
@@ -306,6 +308,14 @@ def host_initial_elevations(base_elevation, lib_path=None):
     base = _f64(base_elevation)
     out = np.empty_like(base)
     load(lib_path).fastlem_host_initial_elevations(base.size, _p(base, ctypes.c_double), _p(out, ctypes.c_double))
+    return out
+
+
+def host_tan_max_slope(max_slope, lib_path=None):
+    """generator.rs:194 on the host: tan(max_slope) with libm (what Rust's f64::tan calls); NaN (None) stays NaN."""
+    ms = _f64(max_slope)
+    out = np.empty_like(ms)
+    load(lib_path).fastlem_host_tan_max_slope(ms.size, _p(ms, ctypes.c_double), _p(out, ctypes.c_double))
     return out
 
 

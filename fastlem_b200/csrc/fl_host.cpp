@@ -81,6 +81,11 @@ extern "C" void fastlem_host_initial_elevations(uint32_t n, const double* base_e
     }
 }
 
+// generator.rs:194: `max_slope.tan()` -- Rust's f64::tan is libm's tan
+extern "C" void fastlem_host_tan_max_slope(uint32_t n, const double* max_slope, double* out) {
+    for (uint32_t i = 0; i < n; ++i) out[i] = std::tan(max_slope[i]);
+}
+
 // The graph build of TerrainModel2DBulider::build (reference src/models/surface/builder.rs:252-268), straight into the
 // boundary format of fastlem_set_graph: for every triangle (a, b, c) of the builder's triangulation, in order, the
 // half-edges a->b, b->c, c->a with from < to become edges; add_edge(u, v, w) appends (v, w) to u's list and (u, w) to

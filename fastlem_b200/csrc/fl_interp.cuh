@@ -285,7 +285,7 @@ __device__ __forceinline__ double fli_query(const FliModel& M, const double qx, 
     FliTri T;
     FliNbr N;
     FliPt P[3];
-    uint32_t steps = 0;
+    uint32_t steps = 0, came_from = FLI_NONE;
     for (;;) {
         T = M.tri[t];
         N = M.nbr[t];
@@ -296,16 +296,21 @@ __device__ __forceinline__ double fli_query(const FliModel& M, const double qx, 
         P[1] = M.site[T.v[1]];
         P[2] = M.site[T.v[2]];
 #endif
+        // The walk never steps straight back over the edge it came through: the two triangles evaluate their shared
+        // edge from different base vertices, so for a query on that edge within rounding BOTH can see a tiny negative
+        // orientation and the walk would bounce between them until max_walk.  In exact arithmetic a step back is
+        // impossible (the edge was crossed because p lies strictly beyond it), so that edge is not a candidate.
         double worst = 0.0;
         int kw = -1;
         for (int k = 0; k < 3; ++k) {
             const FliPt a = P[k], b = P[(k + 1) % 3];
             const double o = M.sgn * fli_cross(b.x - a.x, b.y - a.y, px - a.x, py - a.y);
-            if (o < worst) { worst = o; kw = k; }
+            if (o < worst && !(came_from != FLI_NONE && N.t[k] == came_from)) { worst = o; kw = k; }
         }
         if (kw < 0) break;  // inside or on the boundary of t
         const uint32_t t2 = N.t[kw];
         if (t2 == FLI_NONE) return nan;  // beyond a hull edge: outside the convex hull
+        came_from = t;
         t = t2;
         if (++steps > M.max_walk) {
             atomicOr(&flags[FLI_F_WALK_OVERFLOW], 1u);

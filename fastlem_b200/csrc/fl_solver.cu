@@ -146,7 +146,7 @@ struct fastlem_ctx {
     uint32_t n_seeds = 0;
     uint32_t push_epoch = 0;
     int push_blocks = 0;
-    int64_t opt_k5_push = 1;
+    int64_t opt_k5_push = 0;  // 1: all segments through the push queue (fl_elev.cuh); measured slower than the level sweep (profiles/r2a_*)
     uint32_t* d_ticket_of = nullptr;  // fused sparse levels of K5
     uint32_t* d_fdone = nullptr;
     uint32_t* d_flvl = nullptr;

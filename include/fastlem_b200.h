@@ -141,6 +141,11 @@ int fastlem_debug_fetch(fastlem_ctx* ctx, int stage, void* out, size_t bytes);
  * using the `rand` crate): generator.rs:134-138, out[i] = base[i] + StdRng::seed_from_u64(0).gen::<f64>() * EPSILON. */
 void fastlem_host_initial_elevations(uint32_t n, const double* base_elevation, double* out);
 
+/* Host utility for the mirrors: generator.rs:194 compares the slope with `max_slope.tan()`; Rust's f64::tan is the
+ * platform libm's tan.  out[i] = tan(max_slope[i]) with libm (NaN = None stays NaN), so that every mirror hands
+ * fastlem_set_parameters bit-identical `tan_max_slope` values (a SIMD tan such as numpy's may differ by an ulp). */
+void fastlem_host_tan_max_slope(uint32_t n, const double* max_slope, double* out);
+
 /* Host utility: the graph build of TerrainModel2DBulider::build, builder.rs:252-268, written
  * straight into the boundary format of fastlem_set_graph -- for every triangle (a, b, c) of the builder's
  * triangulation, in order, the half-edges a->b, b->c, c->a with from < to become edges of length

@@ -49,6 +49,33 @@ def test_landscape_evolution_test_scenario(emu_lib, oracle):
     assert np.array_equal(terrain.elevations(), ref)
 
 
+def test_tan_of_max_slope_is_libm(emu_lib):
+    """generator.rs:194 `max_slope.tan()`: the mirror's tan is libm's (math.tan), bit for bit, NaN (None) kept."""
+    import math
+    from fastlem_b200 import _native
+    rng = np.random.default_rng(3)
+    ms = rng.uniform(-1.6, 1.6, 200000)
+    ms[::97] = np.nan
+    got = _native.host_tan_max_slope(ms, emu_lib)
+    want = np.array([math.tan(v) if v == v else np.nan for v in ms])
+    assert np.array_equal(got, want, equal_nan=True)
+
+
+def test_random_per_site_max_slope_is_bit_exact(emu_lib, oracle):
+    """Per-site Some(max_slope) with random angles (round-1 advisor finding: np.tan differs from libm's tan by an ulp
+    for ~0.5 % of the inputs, and one ulp in tan breaks bit-exactness of every clamped site)."""
+    m, p, outlets, initial, _ = scenario("uniform", 1500)
+    rng = np.random.default_rng(11)
+    ms = rng.uniform(0.02, 1.2, m["n"])
+    ms[rng.random(m["n"]) < 0.2] = np.nan  # None
+    arrays = fl.ParameterArrays(p["base"], p["erodibility"], p["uplift"], np.zeros(m["n"], dtype=bool), max_slope=ms)
+    gen = _generator(emu_lib).set_model(fl.TerrainModel2D.from_workload(m)).set_parameters(arrays).set_max_iteration(40)
+    terrain = gen.generate()
+    ref, ref_it = oracle.generate(m, p["erodibility"], p["uplift"], ms, outlets, initial, 40)
+    assert gen.last_iterations == ref_it
+    assert np.array_equal(terrain.elevations(), ref)
+
+
 def test_explicit_outlets_override_default(emu_lib, oracle):
     m, p, outlets, initial, _ = scenario("interior_outlets")
     arrays = fl.ParameterArrays(p["base"], p["erodibility"], p["uplift"], p["is_outlet"])

@@ -142,6 +142,36 @@ def check_properties(lib):
         assert np.isnan(it.points(np.array([[np.nan, 1.0], [1.0, np.nan]]))).all()
 
 
+def check_queries_on_shared_edges(lib, O):
+    """Queries on an interior triangle edge within rounding (midpoints and other points of every edge): the two
+    triangles evaluate the shared edge from different base vertices, so both can see a tiny negative orientation --
+    the visibility walk must not bounce between them (round-1 advisor finding: one such pixel failed the whole call
+    with E_INVALID).  The reference answers these points like any other."""
+    from fastlem_b200 import _native
+    for n, seed in ((300, 0), (300, 1), (2000, 2)):
+        rng = np.random.default_rng(seed)
+        sites = rng.random((n, 2)) * 100.0
+        m = W.delaunay_model(sites)
+        sites, tri, he = W.triangulation_of(m)
+        values = 30.0 + 25.0 * W.value_noise(sites, 0.08, seed=seed, octaves=3) + rng.random(n)
+        t3 = np.asarray(tri).reshape(-1, 3)
+        interior = np.asarray(he).reshape(-1, 3) != 0xFFFFFFFF  # delaunator: no opposite half-edge on the hull
+        qs = []
+        for k in range(3):
+            a, b = sites[t3[:, k]][interior[:, k]], sites[t3[:, (k + 1) % 3]][interior[:, k]]
+            for s in (0.5, 0.25, 1.0 / 3.0, 0.9):
+                qs.append(a + s * (b - a))
+        q = np.concatenate(qs)
+        with _native.Interpolator(sites, tri, he, lib_path=lib) as it:
+            it.set_values(values)
+            out = it.points(q)  # raises on a walk overflow
+        assert not np.isnan(out).any()
+        sub = rng.choice(q.shape[0], 400, replace=False)
+        ref = O.nn_interpolate(sites, tri, values, q[sub])
+        assert not np.isnan(ref).any()
+        assert rel_err(out[sub], ref).max() <= NN_TOL
+
+
 def check_raster(lib, O):
     """The raster entry point equals per-pixel point queries with the examples' coordinate formula, for both pixel
     offsets, any row block, and is independent of how the rows are partitioned."""
@@ -375,6 +405,10 @@ def test_emu_fuzz(oracle, emu_lib):
     check_fuzz(emu_lib, oracle, range(48))
 
 
+def test_emu_queries_on_shared_edges(oracle, emu_lib):
+    check_queries_on_shared_edges(emu_lib, oracle)
+
+
 def test_emu_large_offsets(oracle, emu_lib):
     check_large_offsets(emu_lib, oracle)
 
@@ -477,6 +511,11 @@ def test_gpu_matches_golden(gpu_lib, path):
                                                  (20000, 5, (100.0, 100.0), 1)])
 def test_gpu_matches_oracle(oracle, gpu_lib, n, seed, bound, lloyd):
     check_against_oracle(gpu_lib, oracle, n, seed, 3000, bound, lloyd)
+
+
+@pytest.mark.gpu
+def test_gpu_queries_on_shared_edges(oracle, gpu_lib):
+    check_queries_on_shared_edges(gpu_lib, oracle)
 
 
 @pytest.mark.gpu
