@@ -3,18 +3,28 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--sites S] [--impl reference]
 
-A *step* is one complete `generate()` to convergence (reference src/lem/generator.rs:140-210) on the
-BASELINE config C2 workload: 1M random sites in [0,100]^2, Delaunay adjacency in the boundary format,
-uniform erodibility 1.0, uplift 1.0, hull ("border") outlets.  metric = sites x iterations / seconds.
+N = 1.  A *step* is one complete `generate()` to convergence (reference src/lem/generator.rs:140-210) on the BASELINE
+config C2 workload: 1M random sites in [0,100]^2, Delaunay adjacency in the boundary format, uniform erodibility 1.0,
+uplift 1.0, hull ("border") outlets.  metric = sites x iterations / seconds.
   value : device-resident (graph + parameters already in HBM, fastlem_run only; CUDA events)
   e2e   : the same through the C ABI with HOST buffers every step: fastlem_set_graph + set_parameters
           (H2D copies, flood-order prep) + fastlem_generate (D2H of the elevations)
-N > 1 (torchrun): one independent terrain per rank (an ensemble member with its own seed), no data-path
-collective, one final NCCL all_gather of the elevations per step; "scaling": "weak".
-Extra key "raster" (not part of the metric): the `Terrain2D::get_elevation` loop of the examples as a --raster^2
-image (default 4096) of rank 0's terrain, rows partitioned over the ranks, one NCCL all_gather of the row blocks.
---impl reference: the CPU oracle (single-threaded restatement of the reference; the crate itself is Rust and
-cannot be built in this image) on the same workload, each step bounded to the first few iterations.
+Extra keys on the N = 1 line (not part of the metric):
+  c4_16M   : BASELINE config C4, a 16M-site generate() to convergence (jittered-lattice stand-in for the relaxed Delaunay
+             graph, which takes minutes to build on the host): 1 warm + 2 timed runs, stage times, roofline fractions,
+             the CPU port on the first iterations of the same workload
+  window   : the first --ref-iters iterations of the C2 generate() (fresh context, host buffers) -- the same window the
+             CPU arm (--impl reference) times, for a like-for-like ratio
+  ensemble : members of a parameter ensemble on the C2 graph through 1 and 2 contexts of one GPU
+  raster   : the `Terrain2D::get_elevation` loop of the examples as a --raster^2 image (default 4096)
+N > 1 (torchrun).  BASELINE config C5 style: an ensemble of independent terrains on one shared graph (every rank
+builds the same C2 model and uploads it once), members differ in their noise-driven erodibility field (seed = member
+index), --members-per-rank members per rank and step.  Members are handed out first come first served through the
+process group's store (fastlem_b200/ensemble.py), no collective on the data path, results stay on the device, ONE NCCL
+gather at the end of the timed region; "scaling": "weak".  The raster leg partitions the image rows over the ranks
+and gathers the blocks on rank 0.
+--impl reference: the CPU oracle (single-threaded restatement of the reference; the crate itself is Rust and cannot be
+built in this image) on the C2 workload, each step = the first --ref-iters iterations (iteration 1 timed apart).
 """
 import argparse
 import json
@@ -22,6 +32,7 @@ import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 import numpy as np
@@ -31,30 +42,49 @@ sys.path.insert(0, ROOT)
 
 METRIC = "sites_per_sec_per_generate_iteration"
 UNIT = "sites/s"
-# algorithmic bytes per site per iteration (DESIGN.md "Roofline")
+# algorithmic (compulsory) bytes per site per iteration, SURVEY.md 8(d) / DESIGN.md section 4
 STAGE_BYTES = {"receivers": 88.125, "labels": 8.0, "area": 20.0, "elevation": 64.0}
-# dram__bytes_read.sum + dram__bytes_write.sum per pass at 1M sites from one `ncu --set full` capture of a late iteration
-# (profiles/r1b_ncu_kernels.txt): K1 = k_receivers_mask; K4 = the two flow kernels of an incremental pass
-NCU_TRAFFIC = {"receivers": 107.6e6, "area": 11.0e6}
-NCU_TRAFFIC_NOTE = {"receivers": "ncu: 99.1 MB read + 8.5 MB written per launch (88.1 MB algorithmic)",
-                    "area": "ncu: k_incr_start 6.8 MB + k_area_flow_long 4.1 MB per incremental pass (20 MB algorithmic for a "
-                            "full pass; the incremental pass touches 3-10 % of the sites)"}
+ITER_BYTES = 180.0
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of THIS build, written by
+# tools/ncu_traffic.py (absent kernel / size -> traffic null)
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+KERNEL_STAGE = {"k_receivers_mask": "receivers", "k_area_flow": "area", "k_incr_start": "area", "k_area_flow_long": "area",
+                "k_elev_plan": "elevation", "k_elev_top": "elevation", "k_elev_low": "elevation"}
 
 
-WORKLOAD = "delaunay"  # --workload lattice: jittered lattice (stand-in for the relaxed Delaunay graph of C4 at 16M sites)
-
-
-def build_workload(n_sites, seed):
+def delaunay_workload(n_sites, seed):
     from tools import workloads as W
     t0 = time.time()
-    if WORKLOAD == "lattice":
-        side = max(2, int(round(n_sites ** 0.5)))
-        m = W.lattice_model(side, side, jitter=0.35, seed=seed)
-    else:
-        m = W.delaunay_model(W.random_sites(n_sites, (0.0, 0.0), (100.0, 100.0), seed=seed))
+    m = W.delaunay_model(W.random_sites(n_sites, (0.0, 0.0), (100.0, 100.0), seed=seed))
     p = W.uniform_params(m["n"])
-    outlets = W.outlets_for(m, p)
-    return m, p, outlets, time.time() - t0
+    return m, p, W.outlets_for(m, p), time.time() - t0
+
+
+def lattice_workload(n_sites, seed):
+    from tools import workloads as W
+    t0 = time.time()
+    side = max(2, int(round(n_sites ** 0.5)))
+    m = W.lattice_model(side, side, jitter=0.35, seed=seed)
+    p = W.uniform_params(m["n"])
+    return m, p, W.outlets_for(m, p), time.time() - t0
+
+
+def build_workload(kind, n_sites, seed):
+    return lattice_workload(n_sites, seed) if kind == "lattice" else delaunay_workload(n_sites, seed)
+
+
+def workload_name(kind, n):
+    if kind == "lattice":
+        return (f"C4 stand-in: jittered lattice of {n} sites in [0,100]^2 (each cell split along a random diagonal), uniform "
+                f"erodibility 1.0, rim outlets; step = generate() to convergence")
+    return (f"C2: {n} random sites in [0,100]^2, Delaunay graph (boundary format), uniform erodibility 1.0, hull outlets; "
+            f"step = generate() to convergence")
+
+
+def member_erodibility(sites, t):
+    """Erodibility field of ensemble member t (terrain_generation_advanced.rs:136-160 style: |fbm noise| * 4 + 0.1)."""
+    from tools import workloads as W
+    return np.abs(W.value_noise(sites, 8.0 / 75.0, seed=1000 + int(t), octaves=3)) * 4.0 + 0.1
 
 
 def peaks():
@@ -65,6 +95,13 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel, n):
+    try:
+        return json.load(open(TRAFFIC_FILE)).get(f"{kernel}@{n}")
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -109,59 +146,251 @@ class ClockSampler:
         return out
 
 
-def run_reference(args, rank, world):
-    """CPU arm: the oracle port, one thread, each step = the first `ref_iters` iterations of the workload."""
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank):
+    """CPU arm: the oracle port, one thread; each step = the first `ref_iters` iterations of the C2 workload.
+    Iteration 1 (whose lake removal runs the heap flood) is also timed on its own, so that the steady iterations can be
+    read off the line."""
     if rank != 0:
         return
     from oracle import oracle as O
-    m, p, outlets, _ = build_workload(args.sites, seed=1)
+    m, p, outlets, _ = build_workload(args.workload, args.sites, seed=1)
     initial = O.initial_elevations(p["base"])
     n = m["n"]
     iters = args.ref_iters
 
-    def step():
+    def step(k):
         t0 = time.perf_counter()
-        _, it = O.generate(m, p["erodibility"], p["uplift"], None, outlets, initial, iters)
+        _, it = O.generate(m, p["erodibility"], p["uplift"], None, outlets, initial, k)
         return time.perf_counter() - t0, it
+    t_first, _ = step(1)
     for _ in range(args.warmup):
-        step()
+        step(iters)
     tot, tot_it = 0.0, 0
     for _ in range(args.steps):
-        dt, it = step()
+        dt, it = step(iters)
         tot += dt
         tot_it += it
     value = n * tot_it / tot
-    sample = f"first {iters} iterations of generate() on the {n}-site workload per step (incl. the heap flood of iteration 1)"
+    per_step = tot / args.steps
+    steady = (per_step - t_first) / max(tot_it / args.steps - 1, 1)
+    sample = (f"first {iters} iterations of generate() on the {n}-site workload per step, 1 thread (nproc={os.cpu_count()}); "
+              f"iteration 1 alone {t_first:.3f} s (heap flood of lake removal), later iterations {steady:.3f} s each")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": (f"C2: {n} random sites, Delaunay graph, uniform erodibility, hull outlets"
-                                    if WORKLOAD == "delaunay" else f"C4 stand-in: jittered lattice of {n} sites, uniform "
-                                    f"erodibility, rim outlets"),
-                       "sites": n, "iterations_per_step": iters},
+            "config": {"workload": workload_name(args.workload, n), "sites": n, "iterations_per_step": tot_it / args.steps,
+                       "window": f"first {iters} iterations"},
+            "first_iteration_seconds": t_first, "steady_iteration_seconds": steady,
+            "steady_value": n / steady if steady > 0 else None,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def raster_leg(args, ctx, m, rank, world, local_rank, barrier):
-    """Terrain2D::get_elevation for every pixel of a size x size image of rank 0's terrain (terrain.rs:36-38; pixel
+# ------------------------------------------------------------------------------------------------------------------
+# roofline of one profiled run
+# ------------------------------------------------------------------------------------------------------------------
+STAGES = ("receivers", "labels", "lakes", "order", "area", "elevation")
+
+
+def roofline_of(st, n, iters, dev_ms):
+    """st: stats of runs with "profile" >= 1 summed by the caller (stage ms), st["kernels"] from a "profile" = 2 run.
+    The kernel the line is about is the single kernel with the largest share of the device time; `achieved` =
+    algorithmic bytes of its stage per iteration / its device time per iteration."""
+    peak, peak_src = peaks()
+    stage_ms = {k: st["ms_" + k] for k in STAGES}
+    kern = {k: v for k, v in st.get("kernels", {}).items() if v["launches"] and k in KERNEL_STAGE}
+    per_it = {k: v["ms"] / max(st["kernel_iterations"], 1) for k, v in kern.items()}
+    dom = max(per_it, key=per_it.get) if per_it else "k_receivers_mask"
+    stage = KERNEL_STAGE[dom]
+    alg = STAGE_BYTES[stage] * n
+    ms_it = per_it.get(dom, stage_ms[stage] / max(iters, 1))
+    achieved = alg / (ms_it / 1e3) / 1e9 if ms_it > 0 else 0.0
+    k1_ms = per_it.get("k_receivers_mask", stage_ms["receivers"] / max(iters, 1))
+    k1 = STAGE_BYTES["receivers"] * n / (k1_ms / 1e3) / 1e9 if k1_ms > 0 else 0.0
+    whole = ITER_BYTES * n * iters / (dev_ms / 1e3) / 1e9 if dev_ms > 0 else 0.0
+    kernels = {}
+    for k, v in kern.items():
+        kernels[k] = {"ms_per_iteration": per_it[k], "ms_per_launch": v["ms"] / v["launches"],
+                      "launches_per_iteration": v["launches"] / max(st["kernel_iterations"], 1),
+                      "stage": KERNEL_STAGE[k],
+                      "share_of_iteration": per_it[k] / (dev_ms / max(iters, 1)) if dev_ms > 0 else None,
+                      "traffic": ncu_traffic(k, n)}
+    return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": ncu_traffic(dom, n), "peak_source": peak_src,
+            "bytes_per_launch": alg, "ms_per_launch": ms_it,
+            "what": f"{dom}: the {stage} stage's algorithmic bytes per iteration ({STAGE_BYTES[stage]} B x {n} sites) over the "
+                    f"kernel's device time per iteration (CUDA events around every launch, \"profile\"=2 run of the same "
+                    f"workload inside this process; the timed steps themselves run with stage events only)",
+            "receivers_kernel": {"kernel": "k_receivers_mask", "achieved": k1, "frac": k1 / peak, "ms_per_launch": k1_ms,
+                                 "bytes_per_launch": STAGE_BYTES["receivers"] * n,
+                                 "traffic": ncu_traffic("k_receivers_mask", n)},
+            "whole_iteration": {"achieved": whole, "frac": whole / peak, "bytes": ITER_BYTES * n,
+                                "ms": dev_ms / max(iters, 1)},
+            "stage_ms_per_iteration": {k: v / max(iters, 1) for k, v in stage_ms.items()},
+            "kernels": kernels}
+
+
+def profiled_runs(ctx, steps, max_iter):
+    """`steps` runs with stage events, then one run with per-kernel events; returns (iters, dev_ms, launches, stats)."""
+    iters, dev_ms, launches = 0, 0.0, 0
+    acc = {"ms_" + k: 0.0 for k in STAGES}
+    acc.update({"n_" + k: 0 for k in STAGES})
+    last = None
+    for _ in range(steps):
+        it = ctx.run(max_iter)
+        st = ctx.stats()
+        iters += it
+        dev_ms += st["ms_run"]
+        launches += st["kernel_launches"]
+        for k in acc:
+            acc[k] += st[k]
+        last = st
+    return iters, dev_ms, launches, acc, last
+
+
+def kernel_profile(ctx, max_iter):
+    ctx.set_option("profile", 2)
+    it = ctx.run(max_iter)
+    st = ctx.stats()
+    ctx.set_option("profile", 1)
+    return st["kernels"], it
+
+
+def pinned(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# extra legs of the N = 1 line
+# ------------------------------------------------------------------------------------------------------------------
+def c4_leg(args, local_rank):
+    """BASELINE config C4: 16M sites to convergence on one B200."""
+    from fastlem_b200 import _native
+    m, p, outlets, t_build = lattice_workload(args.c4_sites, seed=1)
+    n = m["n"]
+    initial = _native.host_initial_elevations(p["base"])
+    out = {"workload": workload_name("lattice", n), "sites": n, "directed_edges": int(m["col"].size),
+           "workload_build_s": t_build}
+    with _native.Context(local_rank) as ctx:
+        ctx.set_option("profile", 1)
+        t0 = time.perf_counter()
+        ctx.set_graph(m["row_ptr"], m["col"], m["dist"], m["areas"])
+        ctx.set_parameters(initial, p["erodibility"], p["uplift"], None, outlets)
+        t_up = time.perf_counter() - t0
+        ctx.run(args.c4_max_iter)  # warm (also computes the flood order)
+        warm = ctx.stats()
+        t1 = time.perf_counter()
+        iters, dev_ms, launches, acc, last = profiled_runs(ctx, 2, args.c4_max_iter)
+        wall = time.perf_counter() - t1
+        acc["kernels"], acc["kernel_iterations"] = kernel_profile(ctx, 200 if args.c4_max_iter is None else min(200, args.c4_max_iter))
+        e = ctx.download()
+    out.update({"runs": "1 warm + 2 timed generate() (device-resident inputs), then 200 iterations with per-kernel events",
+                "iterations_per_run": iters / 2, "generate_seconds": wall / 2, "device_ms_per_run": dev_ms / 2,
+                "value": n * iters / wall, "unit": UNIT, "upload_seconds": t_up, "flood_rank_ms": warm["ms_flood_rank"],
+                "flood_rank_on_device": bool(warm["flood_on_device"]), "gpu_launches": launches,
+                "incremental_area_iterations": last["incremental_iterations"],
+                "layout": {"rebuilds_per_run": last["rebuilds"], "nesting_levels": last["path_levels"],
+                           "segments": last["paths"]},
+                "roofline": roofline_of(acc, n, iters, dev_ms),
+                "elevation_range": [float(e.min()), float(e.max())]})
+    if not args.no_cpu_baseline:
+        from oracle import oracle as O
+        tc = time.perf_counter()
+        _, itc = O.generate(m, p["erodibility"], p["uplift"], None, outlets, initial, args.c4_cpu_iters)
+        tc = time.perf_counter() - tc
+        out["cpu_baseline"] = {"value": n * itc / tc, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"first {itc} iterations of the same {n}-site generate() ({tc:.1f} s, 1 thread; "
+                                         f"nproc={os.cpu_count()})"}
+    return out
+
+
+def window_leg(args, local_rank, hm, hp, n):
+    """The first --ref-iters iterations of the C2 generate(), fresh context and host buffers every step: the window
+    the CPU arm times (iteration 1 with lake removal and its flood order included)."""
+    from fastlem_b200 import _native
+    out = pinned(np.empty(n))
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        with _native.Context(local_rank) as c2:
+            c2.set_graph(hm["row_ptr"], hm["col"], hm["dist"], hm["areas"])
+            c2.set_parameters(hp["initial"], hp["erodibility"], hp["uplift"], None, hp["outlets"])
+            _, it = c2.generate(args.ref_iters, out=out)
+        ts.append(time.perf_counter() - t0)
+    t = float(np.median(ts))
+    return {"iterations": it, "seconds": t, "value": n * it / t, "unit": UNIT,
+            "what": f"first {args.ref_iters} iterations of the C2 generate() through the C ABI with host buffers, context "
+                    f"creation and destruction included (median of 3) -- the window `--impl reference` times"}
+
+
+def ensemble_leg(args, local_rank, m, p, outlets, initial):
+    """Members of a parameter ensemble on the C2 graph through 1 and 2 contexts (streams) of one GPU: the sweeps of one
+    terrain are latency-bound, so two members in flight share the GPU almost for free."""
+    from fastlem_b200 import _native, ensemble
+    n = m["n"]
+    members = args.ensemble_members
+    prm = [dict(initial=initial, erodibility=member_erodibility(m["sites"], t), uplift=p["uplift"], outlets=outlets)
+           for t in range(members)]
+    out = {"members": members, "sites": n, "what": "noise-driven erodibility per member (seed = member index), shared graph, "
+                                                   "hull outlets; each member = set_parameters (host buffers) + run to convergence"}
+    for n_ctx in (1, 2):
+        ctxs = []
+        for _ in range(n_ctx):
+            c = _native.Context(local_rank)
+            c.set_graph(m["row_ptr"], m["col"], m["dist"], m["areas"])
+            ctxs.append(c)
+        # warm: flood order + allocations
+        for c in ctxs:
+            c.set_parameters(prm[0]["initial"], prm[0]["erodibility"], prm[0]["uplift"], None, prm[0]["outlets"])
+            c.run(3)
+        pool = ensemble.MemberPool(members)
+        work = [0]
+        lock = threading.Lock()
+
+        def on_result(t, it, ctx):
+            with lock:
+                work[0] += it
+
+        def drive(c):
+            ensemble.run_pool(c, pool, lambda t: prm[t], on_result)
+        t0 = time.perf_counter()
+        ths = [threading.Thread(target=drive, args=(c,)) for c in ctxs]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        dt = time.perf_counter() - t0
+        for c in ctxs:
+            c.close()
+        out[f"contexts_{n_ctx}"] = {"seconds": dt, "iterations": work[0], "value": n * work[0] / dt, "unit": UNIT}
+    out["speedup_2_contexts"] = out["contexts_2"]["value"] / out["contexts_1"]["value"]
+    return out
+
+
+def raster_leg(args, ctx_or_elev, m, rank, world, local_rank, barrier):
+    """Terrain2D::get_elevation for every pixel of a size x size image of one terrain (terrain.rs:36-38; pixel
     coordinates as in examples/landscape_evolution.rs:49-50).  Sites, triangulation and elevations are replicated,
-    rows are partitioned over the ranks (fastlem_b200/ensemble.py), the row blocks are gathered once over NCCL."""
+    rows are partitioned over the ranks (fastlem_b200/ensemble.py), the row blocks are gathered on rank 0 over NCCL."""
     import torch
     import torch.distributed as dist
     from fastlem_b200 import _native, ensemble
     from tools import workloads as W
     size = args.raster
-    if world > 1 and rank != 0:
-        m = build_workload(args.sites, seed=1)[0]  # replicate rank 0's model (host-side graph build)
     sites, tri, he = W.triangulation_of(m)
     n = sites.shape[0]
     elev = torch.empty(n, dtype=torch.float64, device="cuda")
     it = _native.Interpolator(sites, tri, he, device=local_rank)
     if rank == 0:
-        ctx.download_to_device(elev.data_ptr())
+        if isinstance(ctx_or_elev, torch.Tensor):
+            elev.copy_(ctx_or_elev)
+        else:
+            ctx_or_elev.download_to_device(elev.data_ptr())
     if world > 1:
         dist.broadcast(elev, src=0)
     torch.cuda.synchronize()
@@ -169,14 +398,14 @@ def raster_leg(args, ctx, m, rank, world, local_rank, barrier):
     r0, r1 = ensemble.rows_of_rank(size, rank, world)
     max_rows = ensemble.rows_of_rank(size, 0, world)[1]
     blk = torch.zeros((max_rows, size), dtype=torch.float64, device="cuda")
-    gathered = [torch.empty_like(blk) for _ in range(world)] if world > 1 else None
+    gathered = [torch.empty_like(blk) for _ in range(world)] if (world > 1 and rank == 0) else None
     desc = it.raster_desc(size, size, 0.0, 0.0, 100.0, 100.0, 0.0, r0, r1)
     torch.cuda.synchronize()  # the interpolator runs on its own stream: torch's fills of blk must have finished
 
     def step():
         it.raster_device(desc, blk.data_ptr())
         if world > 1:
-            dist.all_gather(gathered, blk)
+            dist.gather(blk, gathered, dst=0)
             torch.cuda.synchronize()
         return it.stats()["ms_query_kernel"]
     for _ in range(2):
@@ -205,19 +434,22 @@ def raster_leg(args, ctx, m, rank, world, local_rank, barrier):
     it.close()
     if rank != 0:
         return None
+    peak, _ = peaks()
     pixels = size * size
     n_tri = tri.size // 3
     # compulsory traffic of one raster: triangulation (vertices 16, neighbours 16, circumcircle 32 bytes per triangle),
     # sites 16 + values 8 bytes per site, hint grid 4 bytes per cell, 8 bytes written per pixel
     alg = 64.0 * n_tri + 24.0 * n + 4.0 * st["grid_x"] * st["grid_y"] + 8.0 * pixels
     out = {"what": f"{size}x{size} get_elevation raster of the {n}-site terrain (natural-neighbour interpolation), "
-                   f"rows partitioned over {world} GPU(s)",
+                   f"rows partitioned over {world} GPU(s), row blocks gathered on rank 0",
            "pixels": pixels, "pixels_per_s": pixels / float(t[0]), "ms_per_raster": 1e3 * float(t[0]),
            "ms_kernel_max_over_ranks": float(t[2]), "ms_per_raster_host_output": 1e3 * float(t[1]),
            "d2h_bytes_per_raster": 8 * pixels, "ms_interpolator_setup": st["ms_setup"],
            "hint_grid": [st["grid_x"], st["grid_y"]], "fraction_inside_hull_rank0_rows": inside,
            "algorithmic_bytes": alg, "achieved_gbs": alg / world / (float(t[2]) / 1e3) / 1e9 if float(t[2]) > 0 else None,
            "kernel": "k_nn_raster", "launches_per_raster": 1}
+    if out["achieved_gbs"]:
+        out["frac_of_hbm_peak"] = out["achieved_gbs"] / peak
     if not args.no_cpu_baseline:
         from oracle import oracle as O
         rows = 16  # bounded sample: sixteen image rows through the CPU oracle (walk-located variant)
@@ -238,48 +470,13 @@ def raster_leg(args, ctx, m, rank, world, local_rank, barrier):
     return out
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--sites", type=int, default=1000000)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="delaunay", choices=["delaunay", "lattice"],
-                    help="lattice: jittered lattice of ~--sites sites (C4 stand-in; builds in seconds at 16M); the raster leg "
-                         "needs a Delaunay triangulation and is skipped")
-    ap.add_argument("--ref-iters", type=int, default=5, help="iterations per step of the CPU arm")
-    ap.add_argument("--cpu-baseline-iters", type=int, default=20)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--raster", type=int, default=4096, help="side of the get_elevation raster leg (0 = skip)")
-    ap.add_argument("--sweep", type=int, default=None, help="solver option 'sweep' (DESIGN.md)")
-    ap.add_argument("--max-iter", type=int, default=None,
-                    help="profiling aid: stop every generate() after this many iterations (the metric is then NOT the "
-                         "benchmark's; used for ncu launch lists of the same command)")
-    args = ap.parse_args()
-    global WORKLOAD
-    WORKLOAD = args.workload
-    if WORKLOAD == "lattice":
-        args.raster = 0
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-
+# ------------------------------------------------------------------------------------------------------------------
+# N = 1: one terrain (C2)
+# ------------------------------------------------------------------------------------------------------------------
+def single_gpu(args, local_rank):
     import torch
-    import torch.distributed as dist
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
     from fastlem_b200 import _native
-    m, p, outlets, t_build = build_workload(args.sites, seed=1 + rank)
+    m, p, outlets, t_build = build_workload(args.workload, args.sites, seed=1)
     n = m["n"]
     initial = _native.host_initial_elevations(p["base"])
     graph_bytes = m["row_ptr"].nbytes + m["col"].nbytes + m["dist"].nbytes + m["areas"].nbytes
@@ -291,65 +488,27 @@ def main():
         ctx.set_option("sweep", args.sweep)
     ctx.set_graph(m["row_ptr"], m["col"], m["dist"], m["areas"])
     ctx.set_parameters(initial, p["erodibility"], p["uplift"], None, outlets)
-    gathered = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
-    mine = torch.empty(n, dtype=torch.float64, device="cuda")
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def resident_step():
-        it = ctx.run(args.max_iter)
-        if world > 1:
-            ctx.download_to_device(mine.data_ptr())
-            dist.all_gather(gathered, mine)
-            torch.cuda.synchronize()
-        return it, ctx.stats()
-
     for _ in range(args.warmup):
-        resident_step()
+        ctx.run(args.max_iter)
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
+    sampler = ClockSampler(local_rank)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    iters_total, dev_ms, launches = 0, 0.0, 0
-    stage_ms = {"receivers": 0.0, "labels": 0.0, "lakes": 0.0, "order": 0.0, "area": 0.0, "elevation": 0.0}
-    stage_n = dict.fromkeys(stage_ms, 0)
-    last = None
-    for _ in range(args.steps):
-        it, st = resident_step()
-        iters_total += it
-        dev_ms += st["ms_run"]
-        launches += st["kernel_launches"]
-        for k in stage_ms:
-            stage_ms[k] += st["ms_" + k]
-            stage_n[k] += st["n_" + k]
-        last = st
-    barrier()
+    iters_total, dev_ms, launches, acc, last = profiled_runs(ctx, args.steps, args.max_iter)
+    torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop()
+    value = n * iters_total / wall
+    acc["kernels"], acc["kernel_iterations"] = kernel_profile(ctx, args.max_iter)
 
-    # max over ranks of the bracketed time; sum of site-iterations over ranks
-    t = torch.tensor([wall, dev_ms / 1e3], dtype=torch.float64, device="cuda")
-    w = torch.tensor([float(n) * iters_total, float(launches)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(w, op=dist.ReduceOp.SUM)
-    wall_max, dev_max = float(t[0]), float(t[1])
-    work, launches_all = float(w[0]), int(w[1])
-    value = work / wall_max
-
-    # e2e through the C ABI with host buffers (same steps, fresh context each time); the host buffers are
-    # pinned copies of the model (torch.pin_memory), handed to the C ABI as plain pointers
-    def pinned(a):
-        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    # e2e through the C ABI with host buffers (same steps, fresh context each time); the host buffers are pinned copies of
+    # the model (torch.pin_memory), handed to the C ABI as plain pointers
     hm = {k: pinned(m[k]) for k in ("row_ptr", "col", "dist", "areas")}
     hp = {"initial": pinned(initial), "erodibility": pinned(p["erodibility"]), "uplift": pinned(p["uplift"]),
           "outlets": pinned(outlets)}
-    e2e_iters, e2e_t = 0, 0.0
-    out = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
-    barrier()
+    e2e_iters = 0
+    out = pinned(np.empty(n))
+    torch.cuda.synchronize()
     t1 = time.perf_counter()
     e2e_parts = {"create": 0.0, "set_graph": 0.0, "set_parameters": 0.0, "generate": 0.0, "destroy": 0.0}
     for _ in range(args.steps):
@@ -370,89 +529,229 @@ def main():
         tf = time.perf_counter()
         for k, v in zip(e2e_parts, (tb - ta, tc - tb, td - tc, te_ - td, tf - te_)):
             e2e_parts[k] += v / args.steps
-    barrier()
+    torch.cuda.synchronize()
     e2e_t = time.perf_counter() - t1
-    te = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
-    we = torch.tensor([float(n) * e2e_iters], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dist.all_reduce(we, op=dist.ReduceOp.SUM)
-    e2e_value = float(we[0]) / float(te[0])
+    e2e_value = n * e2e_iters / e2e_t
+
+    def extra(fn, *a):
+        try:
+            return fn(*a)
+        except Exception as ex:  # the extras never cost the headline line
+            return {"error": f"{type(ex).__name__}: {ex}"}
+
+    window = extra(window_leg, args, local_rank, hm, hp, n)
+    raster = None
+    if args.raster > 0 and args.workload == "delaunay":
+        raster = extra(raster_leg, args, ctx, m, 0, 1, local_rank, torch.cuda.synchronize)
+    ens = extra(ensemble_leg, args, local_rank, m, p, outlets, initial) if args.ensemble_members > 0 and args.workload == "delaunay" else None
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle as O
+        tc = time.perf_counter()
+        _, itc = O.generate(m, p["erodibility"], p["uplift"], None, outlets, initial, args.cpu_baseline_iters)
+        tc = time.perf_counter() - tc
+        cpu = {"value": n * itc / tc, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"first {itc} iterations of the same {n}-site generate() ({tc:.1f} s, 1 thread; nproc={os.cpu_count()})"}
+    ctx.close()
+    c4 = extra(c4_leg, args, local_rank) if args.c4_sites > 0 else None
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, n), "sites": n, "directed_edges": int(m["col"].size),
+                       "iterations_per_step": iters_total / args.steps,
+                       "l2": "working set ~170 MB per iteration > 126 MB L2; hundreds of iterations per step, no flush",
+                       "max_iteration": args.max_iter, "parallelism": "single GPU", "sweep": args.sweep},
+            "generate_seconds": wall / args.steps, "device_ms_per_step": dev_ms / args.steps,
+            "incremental_area_iterations": last["incremental_iterations"],
+            "layout": {"rebuilds_per_step": last["rebuilds"], "nesting_levels": last["path_levels"], "segments": last["paths"]},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(graph_bytes + param_bytes),
+                    "d2h_bytes_per_step": int(8 * n), "seconds_per_step": e2e_t / args.steps,
+                    "flood_rank_ms": e2e_stats["ms_flood_rank"], "flood_rank_on_device": bool(e2e_stats["flood_on_device"]),
+                    "upload_ms": e2e_stats["ms_upload"], "seconds_by_call": e2e_parts,
+                    "device_ms_in_generate": e2e_stats["ms_run"],
+                    "host_buffers": "pinned host arrays handed to the C ABI as plain pointers"},
+            "gpu_launches": int(launches), "roofline": roofline_of(acc, n, iters_total, dev_ms), "cpu_baseline": cpu,
+            "clocks": clocks, "workload_build_s": t_build, "window": window, "c4_16M": c4, "ensemble": ens,
+            "raster": raster}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# N > 1: an ensemble on one shared graph, members handed out dynamically
+# ------------------------------------------------------------------------------------------------------------------
+def multi_gpu(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from fastlem_b200 import _native, ensemble
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    m, p, outlets, t_build = build_workload(args.workload, args.sites, seed=1)  # the same model on every rank
+    n = m["n"]
+    initial = _native.host_initial_elevations(p["base"])
+    per_step = args.members_per_rank * world
+    graph_bytes = m["row_ptr"].nbytes + m["col"].nbytes + m["dist"].nbytes + m["areas"].nbytes
+    hp_shared = {"initial": pinned(initial), "uplift": pinned(p["uplift"]), "outlets": pinned(outlets)}
+
+    def make_params(t):  # host side, on the helper thread of run_pool: overlaps the previous member's solve
+        return dict(initial=hp_shared["initial"], erodibility=pinned(member_erodibility(m["sites"], t)),
+                    uplift=hp_shared["uplift"], outlets=hp_shared["outlets"])
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    cap = args.members_per_rank * args.steps * 2 + 4  # device buffer for this rank's results
+    results = torch.zeros((cap, n), dtype=torch.float64, device="cuda")
+    counters = {"iters": 0, "launches": 0, "dev_ms": 0.0, "members": []}
+
+    def on_device(t, it, ctx):
+        k = len(counters["members"])
+        if k < cap:
+            ctx.download_to_device(results[k].data_ptr())
+        st = ctx.stats()
+        counters["iters"] += it
+        counters["launches"] += st["kernel_launches"]
+        counters["dev_ms"] += st["ms_run"]
+        counters["members"].append(t)
+
+    ctx = _native.Context(local_rank)
+    ctx.set_graph(m["row_ptr"], m["col"], m["dist"], m["areas"])
+    # warm-up: W steps of the same shape (members from their own pool), untimed
+    warm_pool = ensemble.MemberPool.for_process_group(args.warmup * per_step, "fastlem_warm")
+    ensemble.run_pool(ctx, warm_pool, make_params, lambda t, it, c: None, args.max_iter)
+    counters.update({"iters": 0, "launches": 0, "dev_ms": 0.0, "members": []})
+
+    # timed region: K steps' worth of members in ONE pool (no barrier between steps), one gather at the end
+    total = args.steps * per_step
+    pool = ensemble.MemberPool.for_process_group(total, "fastlem_timed")
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    t0 = time.perf_counter()
+    ensemble.run_pool(ctx, pool, make_params, on_device, args.max_iter)
+    torch.cuda.synchronize()
+    t_own = time.perf_counter() - t0
+    mine = len(counters["members"])
+    sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([mine], dtype=torch.int64, device="cuda"))
+    most = int(max(int(s) for s in sizes))
+    gathered = [torch.empty((most, n), dtype=torch.float64, device="cuda") for _ in range(world)] if rank == 0 else None
+    dist.gather(results[:most].contiguous(), gathered, dst=0)  # the final NCCL gather of the ensemble's elevations
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([wall, t_own, counters["dev_ms"] / 1e3], dtype=torch.float64, device="cuda")
+    w = torch.tensor([float(n) * counters["iters"], float(counters["launches"]), float(mine)], dtype=torch.float64, device="cuda")
+    tmin = torch.tensor([t_own], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+    value = float(w[0]) / float(t[0])
+    ctx.close()
+
+    # e2e: the same ensemble through the C ABI with host buffers -- the graph uploaded inside the timed region (once per
+    # rank), every member = set_parameters from pinned host arrays + generate with the elevations copied to the host
+    pool2 = ensemble.MemberPool.for_process_group(total, "fastlem_e2e")
+    host_out = pinned(np.empty(n))
+    hm = {k: pinned(m[k]) for k in ("row_ptr", "col", "dist", "areas")}
+    e2e = {"iters": 0, "members": 0}
+
+    def on_host(t_, it, c):
+        c.download(out=host_out)
+        e2e["iters"] += it
+        e2e["members"] += 1
+    barrier()
+    t1 = time.perf_counter()
+    with _native.Context(local_rank) as c2:
+        c2.set_graph(hm["row_ptr"], hm["col"], hm["dist"], hm["areas"])
+        ensemble.run_pool(c2, pool2, make_params, on_host, args.max_iter)
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device="cuda")
+    e2e_w = torch.tensor([float(n) * e2e["iters"], float(e2e["members"])], dtype=torch.float64, device="cuda")
+    dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(e2e_w, op=dist.ReduceOp.SUM)
 
     raster = None
-    if args.raster > 0:
+    if args.raster > 0 and args.workload == "delaunay":
         try:
-            raster = raster_leg(args, ctx, m, rank, world, local_rank, barrier)
-        except Exception as ex:  # the raster is an extra: never lose the headline line over it
+            raster = raster_leg(args, results[0], m, rank, world, local_rank, barrier)
+        except Exception as ex:
             raster = {"error": f"{type(ex).__name__}: {ex}"}
 
     if rank == 0:
+        members_total = int(w[2])
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * float(t[0]) / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"C5 style: ensemble of {per_step} members per step ({args.members_per_rank} per GPU) x {n} sites "
+                                       f"on the C2 graph (shared, uploaded once per rank), noise-driven erodibility per member, hull "
+                                       f"outlets; each member = generate() to convergence; members handed out first come first "
+                                       f"served over the {world} ranks, one NCCL gather of the elevations at the end",
+                           "sites": n, "members_per_step": per_step, "members_timed": members_total,
+                           "iterations_per_member": float(w[0]) / n / max(members_total, 1),
+                           "l2": "working set ~170 MB per iteration > 126 MB L2; hundreds of iterations per member, no flush",
+                           "max_iteration": args.max_iter, "parallelism": f"{world} GPUs, one process each, 1 member at a time per GPU"},
+                "balance": {"slowest_rank_s": float(t[1]), "fastest_rank_s": float(tmin[0]),
+                            "gather_and_barrier_s": float(t[0]) - float(t[1])},
+                "e2e": {"value": float(e2e_w[0]) / float(e2e_t[0]), "unit": UNIT,
+                        "h2d_bytes_per_step": int(graph_bytes * world / args.steps + per_step * (3 * 8 * n + outlets.nbytes)),
+                        "d2h_bytes_per_step": int(per_step * 8 * n), "seconds_per_step": float(e2e_t[0]) / args.steps,
+                        "members": int(e2e_w[1]),
+                        "host_buffers": "pinned host arrays handed to the C ABI as plain pointers; graph upload inside the timed "
+                                        "region (once per rank)"},
+                "gpu_launches": int(w[1]), "device_seconds_max_over_ranks": float(t[2]),
+                "roofline": None, "cpu_baseline": None, "clocks": clocks, "workload_build_s": t_build, "raster": raster}
         peak, peak_src = peaks()
-        dom = max(("receivers", "area", "elevation"), key=lambda k: stage_ms[k])
-        # one "launch" of a stage = one pass of that stage over all n sites (= one iteration's worth)
-        passes = iters_total
-        alg_bytes = STAGE_BYTES[dom] * n
-        achieved = alg_bytes * passes / (stage_ms[dom] / 1e3) / 1e9 if stage_ms[dom] > 0 else 0.0
-        k1 = STAGE_BYTES["receivers"] * n * passes / (stage_ms["receivers"] / 1e3) / 1e9 if stage_ms["receivers"] else 0.0
-        iter_bytes = 180.0 * n
-        whole = iter_bytes * passes / (dev_ms / 1e3) / 1e9
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(dom) if n == 1000000 else None,
-                    "peak_source": peak_src,
-                    "bytes_per_pass": alg_bytes, "ms_per_pass": stage_ms[dom] / max(passes, 1),
-                    "kernel_launches_per_pass": stage_n[dom] / max(passes, 1),
-                    "kernel_names": {"receivers": "k_receivers_mask",
-                                     "area": "incremental pass (9 of 10 iterations): k_seg_keys+scan+k_incr_mark+k_incr_prepare+"
-                                             "k_incr_start+k_area_flow_long+k_incr_cleanup; full pass: k_count_waits+k_seg_keys+scan+"
-                                             "k_seg_prepare+k_area_flow+k_area_flow_long",
-                                     "elevation": "k_celerity_term+k_fused_index+k_elev_flow_fused+k_elev_flow"}[dom],
-                    "traffic_note": NCU_TRAFFIC_NOTE.get(dom),
-                    "receivers_kernel": {"achieved": k1, "frac": k1 / peak,
-                                         "ms_per_launch": stage_ms["receivers"] / max(stage_n["receivers"], 1)},
-                    "whole_iteration": {"achieved": whole, "frac": whole / peak, "bytes": iter_bytes},
-                    "stage_ms_per_iteration": {k: v / max(passes, 1) for k, v in stage_ms.items()}}
-        cpu = None
-        if not args.no_cpu_baseline:
-            from oracle import oracle as O
-            k_it = args.cpu_baseline_iters
-            tc = time.perf_counter()
-            _, itc = O.generate(m, p["erodibility"], p["uplift"], None, outlets, initial, k_it)
-            tc = time.perf_counter() - tc
-            cpu = {"value": n * itc / tc, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": f"first {itc} iterations of the same {n}-site generate() ({tc:.1f} s, 1 thread; "
-                             f"nproc={os.cpu_count()})"}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1e3 * wall_max / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": (f"C2: {n} random sites in [0,100]^2, Delaunay graph (boundary format), uniform "
-                                        f"erodibility 1.0, hull outlets; step = generate() to convergence"
-                                        if WORKLOAD == "delaunay" else
-                                        f"C4 stand-in: jittered lattice of {n} sites in [0,100]^2 (each cell split along a random "
-                                        f"diagonal), uniform erodibility 1.0, rim outlets; step = generate() to convergence"),
-                           "sites": n, "directed_edges": int(m["col"].size),
-                           "iterations_per_step": iters_total / args.steps,
-                           "l2": "working set ~170 MB per iteration > 126 MB L2; hundreds of iterations per step, no flush",
-                           "max_iteration": args.max_iter,
-                           "parallelism": "1 terrain per GPU" if world > 1 else "single GPU",
-                           "sweep": args.sweep},
-                "generate_seconds": wall_max / args.steps, "device_ms_per_step": 1e3 * dev_max / args.steps,
-                "first_iteration_nesting_levels_or_tree_depth": last["depth_first"] or None,
-                "incremental_area_iterations": last["incremental_iterations"],
-                "layout": {"rebuilds_per_step": last["rebuilds"], "nesting_levels": last["path_levels"],
-                           "segments": last["paths"]},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(graph_bytes + param_bytes),
-                        "d2h_bytes_per_step": int(8 * n), "seconds_per_step": float(te[0]) / args.steps,
-                        "flood_rank_ms": e2e_stats["ms_flood_rank"], "flood_rank_on_device": bool(e2e_stats["flood_on_device"]), "upload_ms": e2e_stats["ms_upload"],
-                        "seconds_by_call": e2e_parts, "device_ms_in_generate": e2e_stats["ms_run"],
-                        "host_buffers": "pinned host arrays handed to the C ABI as plain pointers"},
-                "gpu_launches": launches_all, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-                "workload_build_s": t_build, "raster": raster}
-        if raster and "achieved_gbs" in raster:
-            raster["frac_of_hbm_peak"] = raster["achieved_gbs"] / peak
+        whole = ITER_BYTES * float(w[0]) / float(t[0]) / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": "whole iteration (all ranks)", "achieved": whole, "peak": peak * world,
+                            "unit": "GB/s", "frac": whole / (peak * world), "traffic": None, "peak_source": peak_src,
+                            "what": "180 B x sites x iterations of all members over the wall time, against N x the measured "
+                                    "copy peak; the per-kernel figures are on the N = 1 line"}
         print(json.dumps(line), flush=True)
-    ctx.close()
+    dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--sites", type=int, default=1000000)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="delaunay", choices=["delaunay", "lattice"],
+                    help="lattice: jittered lattice of ~--sites sites (C4 stand-in; builds in seconds at 16M); the raster and "
+                         "ensemble legs need the Delaunay model and are skipped")
+    ap.add_argument("--ref-iters", type=int, default=50, help="iterations per step of the CPU arm (and of the `window` leg)")
+    ap.add_argument("--cpu-baseline-iters", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--raster", type=int, default=4096, help="side of the get_elevation raster leg (0 = skip)")
+    ap.add_argument("--c4-sites", type=int, default=16000000, help="sites of the C4 leg of the N = 1 line (0 = skip)")
+    ap.add_argument("--c4-max-iter", type=int, default=None)
+    ap.add_argument("--c4-cpu-iters", type=int, default=5)
+    ap.add_argument("--ensemble-members", type=int, default=8, help="members of the N = 1 ensemble leg (0 = skip)")
+    ap.add_argument("--members-per-rank", type=int, default=4, help="N > 1: ensemble members per rank and step")
+    ap.add_argument("--sweep", type=int, default=None, help="solver option 'sweep' (DESIGN.md)")
+    ap.add_argument("--max-iter", type=int, default=None,
+                    help="profiling aid: stop every generate() after this many iterations (the metric is then NOT the "
+                         "benchmark's; used for ncu launch lists of the same command)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.destroy_process_group()
+        multi_gpu(args, rank, local_rank, world)
+    else:
+        single_gpu(args, local_rank)
 
 
 if __name__ == "__main__":

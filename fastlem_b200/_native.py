@@ -41,10 +41,17 @@ class Stats(ctypes.Structure):
                 ("n_order", ctypes.c_uint64), ("n_area", ctypes.c_uint64), ("n_elevation", ctypes.c_uint64),
                 ("rebuilds", ctypes.c_uint32), ("path_levels", ctypes.c_uint32), ("paths", ctypes.c_uint32),
                 ("incremental_iterations", ctypes.c_uint32),
-                ("flood_on_device", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+                ("flood_on_device", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
+                ("ms_kernel", ctypes.c_double * 8), ("n_kernel", ctypes.c_uint64 * 8)]
+
+    KERNELS = ("k_receivers_mask", "k_area_flow", "k_incr_start", "k_area_flow_long", "k_elev_plan", "k_elev_top",
+               "k_elev_low", "rebuild")  # FASTLEM_K_*
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("ms_kernel", "n_kernel")}
+        d["kernels"] = {name: {"ms": self.ms_kernel[i], "launches": int(self.n_kernel[i])}
+                        for i, name in enumerate(self.KERNELS)}
+        return d
 
 
 class InterpStats(ctypes.Structure):

@@ -1,132 +1,141 @@
-// fl_elev.cuh -- K5, response time + elevation + max_slope clamp + `changed` (generator.rs:162-203), as ONE launch.
+// fl_elev.cuh -- K5, response time + elevation + max_slope clamp + `changed` (generator.rs:162-203), split by the
+// nesting height of the segments (a segment = a run of positions q, q+1, ... with recv[q+1] == q, fl_flow.cuh; its
+// nesting height hgt = longest chain of segment-to-segment hand-offs below it, left at every segment head by K4).
 //
-// The sweep runs outlet -> upstream.  A site needs nothing but its receiver's new values, so the work is handed
-// DOWN the forest through a queue of segment heads (a segment = a run of positions q, q+1, ... with recv[q+1] == q,
-// fl_flow.cuh): whoever has written site p pushes every child of p that starts a segment of its own.  No ordering of
-// the segments by nesting height, no launch per level, no level offsets on the host -- the queue order IS a
-// topological order.  Every floating-point operation is the reference's, in the reference's order:
+// The sweep runs outlet -> upstream; a site needs nothing but its receiver's NEW values.  The forest has two very
+// different parts: a sparse TOP (few, long segments: trunks and their tributaries; a long chain of dependent
+// hand-offs) and a populous BOTTOM (most segments are one to three sites long and have no or only leaf children).
+//
+//   k_elev_plan  one pass over hgt[]: level histogram (the host picks the cut height from it for the next iteration);
+//                every head with hgt >= cut registers itself in its receiver's push mask `pmask` (bit = its slot in the
+//                receiver's row); roots with hgt >= cut are computed right here and seed the queue.
+//   k_elev_top   segments with hgt >= cut, ONE persistent launch, dataflow: a queue of segment starts whose entries
+//                carry the receiver's new values (root, rt, z), so a consumer needs no gather from the producer's
+//                arrays.  One warp per entry: 32-site windows (coalesced loads, FL_PDEPTH windows prefetched, the
+//                serial additions staged through shared memory and run identically by every lane); the children
+//                registered in pmask are pushed window by window, i.e. a tributary starts as soon as the site it
+//                joins is written, not when the whole trunk is done.  Queue order is a topological order (an entry is
+//                appended by the segment that holds its receiver), tickets are handed out in queue order to resident
+//                warps, so a waiting warp only ever waits for warps that are running.
+//   k_elev_low   heights cut-1 ... 0, one launch per height over ALL positions (a thread whose site heads a segment of
+//                that height walks it; the warp finishes the rare long ones together): no sorting, no lists, loads stay
+//                in position order; the receiver's values are complete because its segment is strictly higher.
+//
+// Every floating-point operation is the reference's, in the reference's order:
 //     celerity = k_i * A_i^0.5 ;  rt_i = 0.0 + (rt_recv + 1.0 / celerity * d_i)                 generator.rs:162-174
 //     z = e_outlet + u_i * max(rt_i - rt_outlet, 0.0) ; clamp against the receiver's NEW elevation   :177-203
+// Trees whose root is not an outlet are never visited (generator.rs:149): their sites get root_of = FL_NONE and keep
+// their elevation.
 //
-// Queues (entries are (epoch << 32 | site); epoch = number of this launch, so the arrays are never cleared):
-//   short queue : segment heads.  Lanes of the "short" warps hold one ticket (slot number) each, poll their slot,
-//                 walk up to FL_PSHORT sites of the segment alone and push the children of those sites;
-//   long queue  : the rest of a segment that went on beyond FL_PSHORT sites.  "Long" warps take one ticket per warp
-//                 and walk the rest in 32-site windows (coalesced loads, FL_PDEPTH windows prefetched, the serial
-//                 additions staged through shared memory), pushing the children window by window.
-// Seeds are the outlets (an outlet is its own receiver, hence always a segment head; trees without an outlet are
-// never visited: generator.rs:149).  `pending` = entries pushed and not yet finished; a warp that finds nothing
-// ready leaves when it reads pending == 0.
-// Ordering between threads: producer = result stores, fence.acq_rel.gpu, st.relaxed entry; consumer = ld.relaxed
-// entry, fence.acq_rel.gpu, loads (fl_flow.cuh, release / acquire patterns of the PTX memory model).
+// Ordering between threads of k_elev_top: producer = payload stores, st.release.gpu of the entry's flag word;
+// consumer = ld.acquire.gpu of the flag word, then the payload loads (PTX memory model, release / acquire pattern).
 #pragma once
 #include "fl_flow.cuh"
 
 #define FL_PB 4       // sites per thread-level batch (loads issued together)
-#define FL_PSHORT 8   // sites a lane walks alone before the rest of the segment goes to the long queue
-#define FL_PDEPTH 3   // windows of a long segment kept in flight
+#define FL_PSHORT 8   // k_elev_low: sites a thread walks alone before the warp finishes the segment together
+#ifndef FL_PDEPTH
+#define FL_PDEPTH 3   // windows of a segment kept in flight
+#endif
+#define FL_CUT_MAX 8u  // largest cut height (= most k_elev_low launches per iteration)
 
-enum { FLQ_TAIL = 16, FLQ_HEAD = 17, FLQ_LTAIL = 18, FLQ_LHEAD = 19, FLQ_PENDING = 20 };  // words of d_flags
+// words of d_flags
+// (the three queue counters sit on cache lines of their own: producers hit tail, consumers head, finishers done)
+enum { FLQ_HIST = 24 /* 32 bins: heads per nesting height (31 = 31+) */, FLQ_TAIL = 64, FLQ_HEAD = 96, FLQ_DONE = 128 };
 
-struct FlPush {
+struct FlQEntry {  // 32 bytes = one sector
+    unsigned long long flag;  // (epoch << 32) | first site of the run; written last (release)
+    uint32_t root;            // tree root (an outlet), FL_NONE = tree without outlet
+    uint32_t pad;
+    double rt_p;              // response time of the run's receiver
+    double z_p;               // NEW elevation of the run's receiver
+};
+
+struct FlSplit {
     uint32_t n;
     const uint32_t* row_ptr;
     const uint32_t* col;
+    const uint8_t* rev;
     const uint32_t* recv;
     const uint32_t* cmask;
+    const uint8_t* is_outlet;
+    const uint32_t* hgt;
     const double* drecv;
     const double* erod;
     const double* A;
     const double* uplift;
     const double* tan_slope;  // may be null
+    double* tcel;      // 1.0 / (k * A^0.5) * d per site: written by k_elev_plan, read by the sweeps
     double* elev;
     double* rt;
     uint32_t* root_of;
-    unsigned long long* queue;   // n entries
-    unsigned long long* lqueue;  // lcap entries
-    uint32_t lcap;
-    uint32_t epoch;
-    const uint32_t* seeds;  // the outlets in the current numbering
-    uint32_t n_seeds;
+    uint32_t* pmask;   // per site: children that start a queue entry (consumed and cleared by k_elev_top)
+    FlQEntry* queue;   // n entries
+    uint32_t epoch;    // number of this sweep: entries of earlier sweeps never match, the queue is never cleared
+    uint32_t cut;      // segments with hgt >= cut go through the queue
     uint32_t* flags;
 };
 
-__device__ __forceinline__ unsigned long long flq_entry(uint32_t epoch, uint32_t site) {
+__device__ __forceinline__ unsigned long long flq_flag(uint32_t epoch, uint32_t site) {
     return ((unsigned long long)epoch << 32) | (unsigned long long)site;
 }
 #ifdef FL_EMU
-__device__ __forceinline__ unsigned long long flq_ld(const unsigned long long* p) { return *p; }
-__device__ __forceinline__ void flq_st(unsigned long long* p, unsigned long long v) { *p = v; }
+__device__ __forceinline__ unsigned long long flq_ld_acquire(const unsigned long long* p) { return *p; }
+__device__ __forceinline__ void flq_st_release(unsigned long long* p, unsigned long long v) { *p = v; }
 #else
-__device__ __forceinline__ unsigned long long flq_ld(const unsigned long long* p) {
+__device__ __forceinline__ unsigned long long flq_ld_acquire(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void flq_st(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void flq_st_release(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 #endif
 
-// seeds + counters (before the sweep; one small launch)
-__global__ void __launch_bounds__(256) k_push_seed(FlPush e) {
-    const uint32_t k = FL_TID;
-    if (k == 0u) {
-        e.flags[FLQ_TAIL] = e.n_seeds;
-        e.flags[FLQ_PENDING] = e.n_seeds;
-        e.flags[FLQ_HEAD] = 0u; e.flags[FLQ_LTAIL] = 0u; e.flags[FLQ_LHEAD] = 0u;
-    }
-    if (k < e.n_seeds) e.queue[k] = flq_entry(e.epoch, e.seeds[k]);
+// append a run start; `release`: other threads of the SAME launch consume it (k_elev_top), else the next launch does
+__device__ __forceinline__ void flq_put(const FlSplit& e, uint32_t slot, uint32_t site, uint32_t root, double rt_p,
+                                        double z_p, bool release) {
+    FlQEntry* q = &e.queue[slot];
+    q->root = root;
+    q->rt_p = rt_p;
+    q->z_p = z_p;
+    if (release) flq_st_release(&q->flag, flq_flag(e.epoch, site));
+    else q->flag = flq_flag(e.epoch, site);
 }
 
-// what a segment starts from: the values of the head's receiver (another segment, already written) or, for a
-// tree root (an outlet), the root's own old elevation
+// what a run starts from
 struct FlSegStart {
     uint32_t root;
     double rt_prev, z_prev, e_out, rt_out;
-    bool is_root;
 };
-__device__ __forceinline__ FlSegStart fl_push_start(const FlPush& e, uint32_t h) {
-    FlSegStart s;
-    const uint32_t p = e.recv[h];
-    s.is_root = (p == h);
-    if (s.is_root) {
-        s.root = h;
-        s.rt_prev = 0.0;
-        s.z_prev = e.elev[h];  // has_edge(i,i) is false: the clamp compares with the site's own old elevation
-        s.e_out = s.z_prev;
-        s.rt_out = 0.0;
-    } else {  // written by another thread of this launch: read through L2
-        s.root = fl_ld_cg(&e.root_of[p]);
-        s.rt_prev = fl_ld_cg(&e.rt[p]);
-        s.z_prev = fl_ld_cg(&e.elev[p]);  // the receiver already holds its NEW elevation
-        s.e_out = fl_ld_cg(&e.elev[s.root]);
-        s.rt_out = fl_ld_cg(&e.rt[s.root]);
-    }
-    return s;
+
+// generator.rs:172-173 for one site
+__device__ __forceinline__ double fl_celerity_term(const FlSplit& e, uint32_t i, double d) {
+    const double celerity = e.erod[i] * sqrt(e.A[i]);
+    return 1.0 / celerity * d;
 }
 
-// up to B sites of one segment by one thread, starting at q; returns true when the segment ended inside the batch.
-// nchild counts the children that start segments of their own (every child except the chain child q+1).
+// up to B sites of one run by one thread, starting at q (q is NOT a tree root: roots are handled by fl_root_site);
+// returns true when the run ended inside the batch.  A dead run (root == FL_NONE) only marks its sites.
 template <int B>
-__device__ __forceinline__ bool fl_push_batch(const FlPush& e, uint32_t& q, uint32_t h, FlSegStart& s, bool& changed,
-                                              uint32_t& nchild) {
+__device__ __forceinline__ bool fl_run_batch(const FlSplit& e, uint32_t& q, FlSegStart& s, bool& changed) {
     const uint32_t nb = e.n - q < (uint32_t)B ? e.n - q : (uint32_t)B;
+    const bool live = s.root != FL_NONE;
     double d[B], t[B], up[B], eo[B], ms[B];
-    uint32_t nx[B], cm[B];
+    uint32_t nx[B];
 #pragma unroll
     for (int k = 0; k < B; ++k) {
-        d[k] = 1.0; t[k] = 0.0; up[k] = 0.0; eo[k] = 0.0; ms[k] = 0.0; nx[k] = FL_NONE; cm[k] = 0u;
+        d[k] = 1.0; t[k] = 0.0; up[k] = 0.0; eo[k] = 0.0; ms[k] = 0.0; nx[k] = FL_NONE;
         if ((uint32_t)k < nb) {
             const uint32_t i = q + k;
-            d[k] = e.drecv[i];
-            const double celerity = e.erod[i] * sqrt(e.A[i]);
-            t[k] = 1.0 / celerity * d[k];
-            up[k] = e.uplift[i];
-            eo[k] = e.elev[i];
-            if (e.tan_slope) ms[k] = e.tan_slope[i];
             nx[k] = (i + 1u < e.n) ? e.recv[i + 1u] : FL_NONE;
-            cm[k] = e.cmask[i];
+            if (live) {
+                t[k] = e.tcel[i];
+                up[k] = e.uplift[i];
+                eo[k] = e.elev[i];
+                if (e.tan_slope) { ms[k] = e.tan_slope[i]; d[k] = e.drecv[i]; }
+            }
         }
     }
     bool ended = false;
@@ -136,185 +145,188 @@ __device__ __forceinline__ bool fl_push_batch(const FlPush& e, uint32_t& q, uint
         if (!ended && (uint32_t)k < nb) {
             const uint32_t i = q + k;
             ++walked;
-            const double rti = 0.0 + (s.rt_prev + t[k]);
-            if (s.is_root && i == h) s.rt_out = rti;
-            double z = s.e_out + up[k] * fmax(rti - s.rt_out, 0.0);
-            if (e.tan_slope) {
-                if (ms[k] == ms[k]) {  // not NaN: Some(max_slope)
-                    const double slope = (z - s.z_prev) / d[k];
-                    if (slope > ms[k]) z = s.z_prev + ms[k] * d[k];
+            if (live) {
+                const double rti = 0.0 + (s.rt_prev + t[k]);
+                double z = s.e_out + up[k] * fmax(rti - s.rt_out, 0.0);
+                if (e.tan_slope) {
+                    if (ms[k] == ms[k]) {  // not NaN: Some(max_slope)
+                        const double slope = (z - s.z_prev) / d[k];
+                        if (slope > ms[k]) z = s.z_prev + ms[k] * d[k];
+                    }
                 }
+                changed |= (z != eo[k]);
+                e.elev[i] = z;
+                e.rt[i] = rti;
+                s.rt_prev = rti;
+                s.z_prev = z;
             }
-            changed |= (z != eo[k]);
-            if (s.is_root && i == h) s.e_out = z;  // later sites read elevations[outlet] after the outlet's own update
-            e.elev[i] = z;
-            e.rt[i] = rti;
             e.root_of[i] = s.root;
-            s.rt_prev = rti;
-            s.z_prev = z;
-            const bool chain = nx[k] == i;
-            nchild += (uint32_t)__popc(cm[k]) - (chain ? 1u : 0u);
-            if (!chain) ended = true;
+            if (nx[k] != i) ended = true;
         }
     }
     q += walked;  // one past the last site written
     return ended || q >= e.n;
 }
 
-// entries for the children of the sites [first, end) that start segments of their own, written from slot `at` on
-template <class F>
-__device__ __forceinline__ void fl_push_children(const FlPush& e, uint32_t first, uint32_t end, F&& put) {
-    for (uint32_t i = first; i < end; ++i) {
-        uint32_t m = e.cmask[i];
-        if (!m) continue;
-        const uint32_t s0 = e.row_ptr[i];
-        const bool chain = (i + 1u < e.n) && (e.recv[i + 1u] == i);
-        while (m) {
-            const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
-            m &= m - 1u;
-            const uint32_t c = e.col[s0 + b];
-            if (chain && c == i + 1u) continue;
-            put(c);
+// A tree root h (recv[h] == h).  An outlet: rt = 0.0 + (0.0 + term), the elevation formula with e_outlet = its own
+// old elevation and rt_outlet = its own new rt, the clamp against its own old elevation (has_edge(i,i) is false);
+// sites after it read elevations[outlet] AFTER this update.  Not an outlet: the tree is never visited.
+__device__ __forceinline__ FlSegStart fl_root_site(const FlSplit& e, uint32_t h, double t, bool& changed) {
+    FlSegStart s;
+    s.root = e.is_outlet[h] ? h : FL_NONE;
+    s.rt_prev = 0.0; s.z_prev = 0.0; s.e_out = 0.0; s.rt_out = 0.0;
+    if (s.root == FL_NONE) { e.root_of[h] = FL_NONE; return s; }
+    const double eold = e.elev[h];
+    const double rti = 0.0 + (0.0 + t);
+    double z = eold + e.uplift[h] * fmax(rti - rti, 0.0);
+    if (e.tan_slope) {
+        const double ms = e.tan_slope[h];
+        if (ms == ms) {
+            const double d = e.drecv[h];
+            const double slope = (z - eold) / d;
+            if (slope > ms) z = eold + ms * d;
         }
     }
+    changed |= (z != eold);
+    e.elev[h] = z;
+    e.rt[h] = rti;
+    e.root_of[h] = h;
+    s.rt_prev = rti; s.z_prev = z; s.e_out = z; s.rt_out = rti;
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan: histogram, push masks, the roots of the top trees
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_elev_plan(FlSplit e) {
+#ifndef FL_EMU
+    __shared__ uint32_t hist[32];
+    if (threadIdx.x < 32u) hist[threadIdx.x] = 0u;
+    __syncthreads();
+#endif
+    const uint32_t q = FL_TID;
+    bool changed = false;
+    if (q < e.n) {
+        const double tq = fl_celerity_term(e, q, e.drecv[q]);  // (fully parallel: the division and the square root stay
+        e.tcel[q] = tq;                                        //  out of the serial chains)
+        const uint32_t h = e.hgt[q];
+        if (h != FL_NONE) {  // q heads a segment
+#ifdef FL_EMU
+            atomicAdd(&e.flags[FLQ_HIST + (h < 31u ? h : 31u)], 1u);
+#else
+            atomicAdd(&hist[h < 31u ? h : 31u], 1u);
+#endif
+            if (h >= e.cut) {
+                const uint32_t p = e.recv[q];
+                if (p == q) {
+                    // a top tree: the root site itself, then the run behind it and its top children as queue entries
+                    const FlSegStart s = fl_root_site(e, q, tq, changed);
+                    const bool chain = (q + 1u < e.n) && (e.recv[q + 1u] == q);
+                    if (chain) flq_put(e, atomicAdd(&e.flags[FLQ_TAIL], 1u), q + 1u, s.root, s.rt_prev, s.z_prev, false);
+                    const uint32_t s0 = e.row_ptr[q];
+                    uint32_t m = e.cmask[q];
+                    while (m) {
+                        const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+                        m &= m - 1u;
+                        const uint32_t c = e.col[s0 + b];
+                        if (chain && c == q + 1u) continue;
+                        const uint32_t hc = e.hgt[c];
+                        if (hc != FL_NONE && hc >= e.cut)
+                            flq_put(e, atomicAdd(&e.flags[FLQ_TAIL], 1u), c, s.root, s.rt_prev, s.z_prev, false);
+                    }
+                } else if (e.recv[p] != p) {  // (a root pushes its own top children, above)
+                    uint32_t bit = 32u;
+                    for (uint32_t sl = e.row_ptr[q]; sl < e.row_ptr[q + 1u]; ++sl)
+                        if (e.col[sl] == p) { bit = e.rev[sl]; break; }
+                    if (bit < 32u) atomicOr(&e.pmask[p], 1u << bit);
+                    else atomicOr(&e.flags[FL_FLAG_BROKEN], 16u);
+                }
+            }
+        }
+    }
+    if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
+#ifndef FL_EMU
+    __syncthreads();
+    if (threadIdx.x < 32u && hist[threadIdx.x]) atomicAdd(&e.flags[FLQ_HIST + threadIdx.x], hist[threadIdx.x]);
+#endif
+}
+
+// children of site i registered in its push mask -> queue entries carrying i's new values; clears the mask
+template <class F>
+__device__ __forceinline__ void fl_push_masked(const FlSplit& e, uint32_t i, uint32_t s0, uint32_t m, F&& put) {
+    while (m) {
+        const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+        m &= m - 1u;
+        put(e.col[s0 + b]);
+    }
+    e.pmask[i] = 0u;
 }
 
 #ifdef FL_EMU
-// host emulation: one thread drains the queue in FIFO order (parents before children)
-__global__ void k_elev_push(FlPush e) {
+// host emulation: one thread drains the queue in FIFO order (receivers before their children)
+__global__ void k_elev_top(FlSplit e) {
     if (FL_TID != 0u) return;
     uint32_t head = 0, tail = e.flags[FLQ_TAIL];
     bool changed = false;
     while (head < tail) {
-        const unsigned long long ent = e.queue[head++];
-        if ((uint32_t)(ent >> 32) != e.epoch) { atomicOr(&e.flags[FL_FLAG_BROKEN], 2u); return; }
-        const uint32_t h = (uint32_t)ent;
-        FlSegStart s = fl_push_start(e, h);
-        uint32_t q = h, nchild = 0;
-        while (!fl_push_batch<FL_PB>(e, q, h, s, changed, nchild)) {}
-        uint32_t pushed = 0;  // the segment's sites are [h, q)
-        fl_push_children(e, h, q, [&](uint32_t c) { e.queue[tail++] = flq_entry(e.epoch, c); ++pushed; });
-        if (pushed != nchild) { atomicOr(&e.flags[FL_FLAG_BROKEN], 2u); return; }
+        const FlQEntry ent = e.queue[head++];
+        if ((uint32_t)(ent.flag >> 32) != e.epoch) { atomicOr(&e.flags[FL_FLAG_BROKEN], 2u); return; }
+        uint32_t q = (uint32_t)ent.flag;
+        FlSegStart s;
+        s.root = ent.root; s.rt_prev = ent.rt_p; s.z_prev = ent.z_p;
+        s.e_out = s.root != FL_NONE ? e.elev[s.root] : 0.0;
+        s.rt_out = s.root != FL_NONE ? e.rt[s.root] : 0.0;
+        for (bool ended = false; !ended;) {
+            const uint32_t first = q;
+            ended = fl_run_batch<FL_PB>(e, q, s, changed);
+            for (uint32_t i = first; i < q; ++i) {
+                const uint32_t m = e.pmask[i];
+                if (!m) continue;
+                const double rt_i = s.root != FL_NONE ? e.rt[i] : 0.0, z_i = s.root != FL_NONE ? e.elev[i] : 0.0;
+                fl_push_masked(e, i, e.row_ptr[i], m, [&](uint32_t c) {
+                    if (tail >= e.n) { atomicOr(&e.flags[FL_FLAG_BROKEN], 2u); return; }
+                    flq_put(e, tail++, c, s.root, rt_i, z_i, false);
+                });
+            }
+        }
     }
     e.flags[FLQ_TAIL] = tail;
     e.flags[FLQ_HEAD] = head;
-    e.flags[FLQ_PENDING] = 0u;
+    e.flags[FLQ_DONE] = tail;
     if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
 }
 #else
 
 // ------------------------------------------------------------------------------------------------
-// short warps: one ticket per lane
+// 32-site windows of a run: lane l holds site base + l
 // ------------------------------------------------------------------------------------------------
-__device__ void fl_push_short_warp(const FlPush& e) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t my = FL_NONE;
-    bool changed = false;
-    uint32_t idle = 0u;
-    for (;;) {
-        const uint32_t need = __ballot_sync(FL_FULL, my == FL_NONE);
-        if (need) {
-            uint32_t base = 0u;
-            if (lane == 0) base = atomicAdd(&e.flags[FLQ_HEAD], (uint32_t)__popc(need));
-            base = __shfl_sync(FL_FULL, base, 0);
-            if (my == FL_NONE) my = base + (uint32_t)__popc(need & lt_mask);
-        }
-        unsigned long long ent = 0ull;
-        if (my < e.n) ent = flq_ld(&e.queue[my]);
-        const bool ready = (uint32_t)(ent >> 32) == e.epoch;
-        const uint32_t rmask = __ballot_sync(FL_FULL, ready);
-        if (!rmask) {
-            uint32_t pend = 1u;
-            if (lane == 0) pend = fl_ld_relaxed(&e.flags[FLQ_PENDING]);
-            pend = __shfl_sync(FL_FULL, pend, 0);
-            if (pend == 0u) break;
-            const uint32_t ns = 64u << (idle < 5u ? idle : 5u);
-            __nanosleep(ns);
-            ++idle;
-            if (idle > (1u << 22)) { if (lane == 0) atomicOr(&e.flags[FL_FLAG_BROKEN], 2u); break; }
-            continue;
-        }
-        idle = 0u;
-        fl_fence_acquire();  // acquire side of the producers' fence + entry store
-        uint32_t nchild = 0u, cont = FL_NONE, h = 0u, q = 0u;
-        if (ready) {
-            h = (uint32_t)ent;
-            q = h;
-            FlSegStart s = fl_push_start(e, h);
-            bool ended = fl_push_batch<FL_PB>(e, q, h, s, changed, nchild);
-#pragma unroll
-            for (int r = 1; r < FL_PSHORT / FL_PB; ++r)
-                if (!ended) ended = fl_push_batch<FL_PB>(e, q, h, s, changed, nchild);
-            if (!ended) cont = q;  // the rest of a long segment: a warp continues from q (its receiver is q - 1)
-        }
-        // one reservation per warp and round
-        uint32_t off = nchild;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t w = __shfl_up_sync(FL_FULL, off, o);
-            if (lane >= o) off += w;
-        }
-        const uint32_t total = __shfl_sync(FL_FULL, off, 31);
-        off -= nchild;
-        const uint32_t lmask = __ballot_sync(FL_FULL, cont != FL_NONE);
-        const uint32_t ltotal = (uint32_t)__popc(lmask);
-        if (total | ltotal) {
-            uint32_t sbase = 0u, lbase = 0u;
-            if (lane == 0) {
-                atomicAdd(&e.flags[FLQ_PENDING], total + ltotal);  // before the entries can be seen
-                if (total) sbase = atomicAdd(&e.flags[FLQ_TAIL], total);
-                if (ltotal) lbase = atomicAdd(&e.flags[FLQ_LTAIL], ltotal);
-            }
-            sbase = __shfl_sync(FL_FULL, sbase, 0);
-            lbase = __shfl_sync(FL_FULL, lbase, 0);
-            __syncwarp();         // lane 0's increment of `pending` happens before every lane's fence
-            fl_fence_release();   // each lane: its results (and, by cumulativity, the increment) before its entries
-            if (ready) {
-                uint32_t at = sbase + off;
-                fl_push_children(e, h, q, [&](uint32_t c) { flq_st(&e.queue[at++], flq_entry(e.epoch, c)); });
-                if (cont != FL_NONE) {
-                    const uint32_t slot = lbase + (uint32_t)__popc(lmask & lt_mask);
-                    if (slot < e.lcap) flq_st(&e.lqueue[slot], flq_entry(e.epoch, cont));
-                    else atomicOr(&e.flags[FL_FLAG_BROKEN], 2u);
-                }
-            }
-        }
-        if (lane == 0) atomicAdd(&e.flags[FLQ_PENDING], 0u - (uint32_t)__popc(rmask));
-        if (ready) my = FL_NONE;
-    }
-    if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
-}
-
-// ------------------------------------------------------------------------------------------------
-// long warps: one ticket per warp; the segment from q on in 32-site windows
-// ------------------------------------------------------------------------------------------------
-struct FlPWin {  // one window: lane l holds site base + l
+struct FlPWin {
     double t, up, eold, ms, d;
-    uint32_t nx, cm, s0;
+    uint32_t nx, pm, s0;
     bool valid;
 };
 
-__device__ __forceinline__ FlPWin fl_pwin_load(const FlPush& e, uint32_t base, int lane) {
+template <bool PUSH>
+__device__ __forceinline__ FlPWin fl_pwin_load(const FlSplit& e, uint32_t base, int lane, bool live) {
     FlPWin w;
-    w.t = 0.0; w.up = 0.0; w.eold = 0.0; w.ms = 0.0; w.d = 1.0; w.nx = FL_NONE; w.cm = 0u; w.s0 = 0u;
+    w.t = 0.0; w.up = 0.0; w.eold = 0.0; w.ms = 0.0; w.d = 1.0; w.nx = FL_NONE; w.pm = 0u; w.s0 = 0u;
     const unsigned long long i64 = (unsigned long long)base + (unsigned)lane;
     w.valid = i64 < e.n;
     if (w.valid) {
         const uint32_t i = (uint32_t)i64;
-        w.d = e.drecv[i];
-        const double celerity = e.erod[i] * sqrt(e.A[i]);
-        w.t = 1.0 / celerity * w.d;
-        w.up = e.uplift[i];
-        w.eold = e.elev[i];
         w.nx = (i + 1u < e.n) ? e.recv[i + 1u] : FL_NONE;
-        w.cm = e.cmask[i];
-        w.s0 = e.row_ptr[i];
-        if (e.tan_slope) w.ms = e.tan_slope[i];
+        if (PUSH) { w.pm = e.pmask[i]; w.s0 = e.row_ptr[i]; }
+        if (live) {
+            w.t = e.tcel[i];
+            w.up = e.uplift[i];
+            w.eold = e.elev[i];
+            if (e.tan_slope) { w.ms = e.tan_slope[i]; w.d = e.drecv[i]; }
+        }
     }
     return w;
 }
 
+// sites of the window that belong to the run (it ends at the first site whose successor is not chained to it)
 __device__ __forceinline__ uint32_t fl_pwin_nproc(const FlPWin& w, uint32_t q, int lane, uint32_t& endmask) {
     const uint32_t i = q + (uint32_t)lane;
     endmask = __ballot_sync(FL_FULL, !w.valid || w.nx != i);
@@ -325,10 +337,12 @@ __device__ __forceinline__ uint32_t fl_pwin_nproc(const FlPWin& w, uint32_t q, i
 }
 
 // the two serial chains of a window (response time; clamp if max_slope): per-lane terms staged in shared memory,
-// every lane runs the identical chain over broadcast reads (8 terms fetched together, then 8 dependent additions)
-__device__ __forceinline__ void fl_pwin_compute(const FlPush& e, const FlPWin& w, uint32_t q, uint32_t nproc, int lane,
+// every lane runs the identical chain over broadcast reads (8 terms fetched together, then 8 dependent additions).
+// Leaves the lane's own results in my_rt / my_z.
+__device__ __forceinline__ void fl_pwin_compute(const FlSplit& e, const FlPWin& w, uint32_t q, uint32_t nproc, int lane,
                                                 uint32_t root, double& rt_prev, double& z_prev, double e_out,
-                                                double rt_out, bool& changed, FlChainSmem& sm) {
+                                                double rt_out, bool& changed, FlChainSmem& sm, double& my_rt,
+                                                double& my_z) {
     __syncwarp();
     sm.in[lane] = ((uint32_t)lane < nproc) ? w.t : 0.0;  // padding: 0.0 + (r + 0.0) == r (r >= +0.0)
     __syncwarp();
@@ -348,7 +362,7 @@ __device__ __forceinline__ void fl_pwin_compute(const FlPush& e, const FlPWin& w
         rt_prev = r;
     }
     __syncwarp();
-    const double my_rt = sm.out[lane];
+    my_rt = sm.out[lane];
     double z = e_out + w.up * fmax(my_rt - rt_out, 0.0);
     if (e.tan_slope) {
         __syncwarp();
@@ -374,6 +388,7 @@ __device__ __forceinline__ void fl_pwin_compute(const FlPush& e, const FlPWin& w
     } else {
         z_prev = __shfl_sync(FL_FULL, z, (int)nproc - 1);
     }
+    my_z = z;
     if ((uint32_t)lane < nproc) {
         const uint32_t i = q + (uint32_t)lane;
         changed |= (z != w.eold);
@@ -383,12 +398,11 @@ __device__ __forceinline__ void fl_pwin_compute(const FlPush& e, const FlPWin& w
     }
 }
 
-// children of a window's sites: one reservation per window
-__device__ __forceinline__ void fl_pwin_push(const FlPush& e, const FlPWin& w, uint32_t q, uint32_t nproc, int lane) {
-    const uint32_t i = q + (uint32_t)lane;
-    const bool inwin = (uint32_t)lane < nproc;
-    const bool chain = inwin && w.nx == i;
-    const uint32_t cnt = inwin ? (uint32_t)__popc(w.cm) - (chain ? 1u : 0u) : 0u;
+// queue entries for the registered children of a window's sites: one reservation per window
+__device__ __forceinline__ void fl_pwin_push(const FlSplit& e, const FlPWin& w, uint32_t q, uint32_t nproc, int lane,
+                                             uint32_t root, double my_rt, double my_z) {
+    const uint32_t m = ((uint32_t)lane < nproc) ? w.pm : 0u;
+    const uint32_t cnt = (uint32_t)__popc(m);
     uint32_t off = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -398,98 +412,190 @@ __device__ __forceinline__ void fl_pwin_push(const FlPush& e, const FlPWin& w, u
     const uint32_t total = __shfl_sync(FL_FULL, off, 31);
     if (!total) return;
     off -= cnt;
-    // the children's ids first (independent loads), while the reservation is under way
-    uint32_t kid[4];
-    uint32_t m = w.cm;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        kid[k] = FL_NONE;
-        if (cnt && m) {
-            const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
-            m &= m - 1u;
-            kid[k] = e.col[w.s0 + b];
-        }
-    }
     uint32_t sbase = 0u;
-    if (lane == 0) {
-        atomicAdd(&e.flags[FLQ_PENDING], total);
-        sbase = atomicAdd(&e.flags[FLQ_TAIL], total);
-    }
+    if (lane == 0) sbase = atomicAdd(&e.flags[FLQ_TAIL], total);
     sbase = __shfl_sync(FL_FULL, sbase, 0);
-    __syncwarp();
-    fl_fence_release();
     if (cnt) {
         uint32_t at = sbase + off;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (kid[k] != FL_NONE && !(chain && kid[k] == i + 1u)) flq_st(&e.queue[at++], flq_entry(e.epoch, kid[k]));
-        while (m) {  // more than four children
-            const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
-            m &= m - 1u;
-            const uint32_t c = e.col[w.s0 + b];
-            if (chain && c == i + 1u) continue;
-            flq_st(&e.queue[at++], flq_entry(e.epoch, c));
-        }
+        fl_push_masked(e, q + (uint32_t)lane, w.s0, m, [&](uint32_t c) {
+            if (at < e.n) flq_put(e, at, c, root, my_rt, my_z, true);
+            else atomicOr(&e.flags[FL_FLAG_BROKEN], 2u);
+            ++at;
+        });
     }
 }
 
-__device__ void fl_push_long_warp(const FlPush& e, FlChainSmem& sm) {
+// a run from q on, by the whole warp; PUSH: registered children become queue entries (k_elev_top)
+template <bool PUSH, int DEPTH>
+__device__ __forceinline__ void fl_run_warp(const FlSplit& e, uint32_t q, const FlSegStart& s, bool& changed,
+                                            FlChainSmem& sm) {
+    const int lane = threadIdx.x & 31;
+    const bool live = s.root != FL_NONE;
+    double rt_prev = s.rt_prev, z_prev = s.z_prev;
+    FlPWin ring[DEPTH];
+    ring[0] = fl_pwin_load<PUSH>(e, q, lane, live);
+    uint32_t endmask;
+    uint32_t nproc = fl_pwin_nproc(ring[0], q, lane, endmask);
+    if (!endmask) {  // the run goes on beyond the first window: keep DEPTH windows in flight
+#pragma unroll
+        for (int j = 1; j < DEPTH; ++j) ring[j] = fl_pwin_load<PUSH>(e, q + 32u * (uint32_t)j, lane, live);
+    }
+    for (;;) {
+        const FlPWin cur = ring[0];
+        if (!endmask) {
+#pragma unroll
+            for (int j = 0; j + 1 < DEPTH; ++j) ring[j] = ring[j + 1];
+            ring[DEPTH - 1] = fl_pwin_load<PUSH>(e, q + 32u * (uint32_t)DEPTH, lane, live);
+        }
+        double my_rt = 0.0, my_z = 0.0;
+        if (live) fl_pwin_compute(e, cur, q, nproc, lane, s.root, rt_prev, z_prev, s.e_out, s.rt_out, changed, sm, my_rt, my_z);
+        else if ((uint32_t)lane < nproc) e.root_of[q + (uint32_t)lane] = FL_NONE;
+        if (PUSH) fl_pwin_push(e, cur, q, nproc, lane, s.root, my_rt, my_z);
+        if (endmask) break;
+        q += 32u;
+        nproc = fl_pwin_nproc(ring[0], q, lane, endmask);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// top: one warp per queue entry
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_elev_top(FlSplit e) {
+    __shared__ FlChainSmem chain_smem[8];
+    FlChainSmem& sm = chain_smem[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     bool changed = false;
     for (;;) {
+        // Tickets are handed out in queue order; the warp waits for the entry with its number.  A waiting warp polls
+        // nothing but its own entry's flag word (its own address: no hot spot), and looks at the shared counters only
+        // once in a while -- done / tail are the words every producer's atomics go to.
         uint32_t t = 0u;
-        if (lane == 0) t = atomicAdd(&e.flags[FLQ_LHEAD], 1u);
+        if (lane == 0) t = atomicAdd(&e.flags[FLQ_HEAD], 1u);
         t = __shfl_sync(FL_FULL, t, 0);
+        if (t >= e.n) break;  // more tickets than entries can ever exist
         uint32_t q = FL_NONE, idle = 0u;
         for (;;) {
-            uint32_t got = FL_NONE, pend = 1u;
-            if (lane == 0) {
-                if (t < e.lcap) {
-                    const unsigned long long ent = flq_ld(&e.lqueue[t]);
-                    if ((uint32_t)(ent >> 32) == e.epoch) got = (uint32_t)ent;
-                }
-                if (got == FL_NONE) pend = fl_ld_relaxed(&e.flags[FLQ_PENDING]);
-            }
-            got = __shfl_sync(FL_FULL, got, 0);
-            pend = __shfl_sync(FL_FULL, pend, 0);
-            if (got != FL_NONE) { q = got; break; }
-            if (pend == 0u) break;
-            const uint32_t ns = 64u << (idle < 5u ? idle : 5u);
-            __nanosleep(ns);
+            // every lane runs its own acquire load of the flag word (one broadcast transaction)
+            const unsigned long long f = flq_ld_acquire(&e.queue[t].flag);
+            if ((uint32_t)(f >> 32) == e.epoch) { q = (uint32_t)f; break; }
             ++idle;
-            if (idle > (1u << 22)) { if (lane == 0) atomicOr(&e.flags[FL_FLAG_BROKEN], 2u); break; }
+            if ((idle & 31u) == 0u) {
+                // All work is done when every entry ever appended has been finished: an entry is appended only by an
+                // unfinished one, so done == tail (done read first) is final.
+                uint32_t fin = 0u;
+                if (lane == 0) {
+                    const uint32_t done = fl_ld_relaxed(&e.flags[FLQ_DONE]);
+                    const uint32_t tail = fl_ld_relaxed(&e.flags[FLQ_TAIL]);
+                    fin = (done == tail && t >= tail) ? 1u : 0u;
+                }
+                if (__shfl_sync(FL_FULL, fin, 0)) break;
+                if (idle > (1u << 24)) { if (lane == 0) atomicOr(&e.flags[FL_FLAG_BROKEN], 2u); break; }
+            }
+            __nanosleep(idle < 8u ? 32u : 100u);
         }
         if (q == FL_NONE) break;
-        fl_fence_acquire();  // every lane: acquire side of the producer's fence + entry store (lane 0 read the entry;
-        __syncwarp();        // its fence and this barrier order the other lanes' loads behind it)
-        // q continues a segment: its receiver q - 1 holds the running values
-        FlSegStart s = fl_push_start(e, q);
-        double rt_prev = s.rt_prev, z_prev = s.z_prev;
-        FlPWin ring[FL_PDEPTH];
-#pragma unroll
-        for (int j = 0; j < FL_PDEPTH; ++j) ring[j] = fl_pwin_load(e, q + 32u * (uint32_t)j, lane);
-        for (;;) {
-            uint32_t endmask;
-            const uint32_t nproc = fl_pwin_nproc(ring[0], q, lane, endmask);
-            const FlPWin cur = ring[0];
-#pragma unroll
-            for (int j = 0; j + 1 < FL_PDEPTH; ++j) ring[j] = ring[j + 1];
-            if (!endmask) ring[FL_PDEPTH - 1] = fl_pwin_load(e, q + 32u * (uint32_t)FL_PDEPTH, lane);
-            fl_pwin_compute(e, cur, q, nproc, lane, s.root, rt_prev, z_prev, s.e_out, s.rt_out, changed, sm);
-            fl_pwin_push(e, cur, q, nproc, lane);
-            if (endmask) break;
-            q += 32u;
-        }
-        if (lane == 0) atomicAdd(&e.flags[FLQ_PENDING], 0u - 1u);
+        FlSegStart s;
+        s.root = e.queue[t].root;
+        s.rt_prev = e.queue[t].rt_p;
+        s.z_prev = e.queue[t].z_p;
+        // the root's values were written by k_elev_plan (an earlier launch)
+        s.e_out = s.root != FL_NONE ? e.elev[s.root] : 0.0;
+        s.rt_out = s.root != FL_NONE ? e.rt[s.root] : 0.0;
+        fl_run_warp<true, FL_PDEPTH>(e, q, s, changed, sm);
+        if (lane == 0) atomicAdd(&e.flags[FLQ_DONE], 1u);
     }
     if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
 }
-
-// warps 0..3 of a block serve the short queue, warps 4..7 the long queue
-__global__ void __launch_bounds__(256) k_elev_push(FlPush e) {
-    __shared__ FlChainSmem chain_smem[4];
-    const uint32_t w = threadIdx.x >> 5;
-    if (w < 4u) fl_push_short_warp(e);
-    else fl_push_long_warp(e, chain_smem[w - 4u]);
-}
 #endif
+
+// ------------------------------------------------------------------------------------------------
+// low: all segments of ONE nesting height below the cut, one thread per position
+// ------------------------------------------------------------------------------------------------
+#define FL_LOW_CHUNK 2048u  // positions scanned by one block of k_elev_low
+__global__ void __launch_bounds__(256) k_elev_low(FlSplit e, uint32_t level) {
+#ifdef FL_EMU
+    // emulation: one thread per position
+    const uint32_t h = FL_TID;
+    if (h >= e.n || e.hgt[h] != level) return;
+    const bool active = true;
+    {
+#else
+    // The heads of this height among the block's FL_LOW_CHUNK positions are first compacted into shared memory (in
+    // position order within a warp's 32 positions), then walked by dense warps.
+    __shared__ uint32_t list[FL_LOW_CHUNK];
+    __shared__ uint32_t count;
+    __shared__ FlChainSmem chain_smem[8];
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0u) count = 0u;
+    __syncthreads();
+    const unsigned long long base = (unsigned long long)blockIdx.x * FL_LOW_CHUNK;
+#pragma unroll
+    for (uint32_t j = 0; j < FL_LOW_CHUNK / 256u; ++j) {
+        const unsigned long long site = base + j * 256u + threadIdx.x;
+        const bool is_head = site < e.n && e.hgt[site] == level;
+        const uint32_t bal = __ballot_sync(FL_FULL, is_head);
+        uint32_t off = 0u;
+        if (lane == 0 && bal) off = atomicAdd(&count, (uint32_t)__popc(bal));
+        off = __shfl_sync(FL_FULL, off, 0);
+        if (is_head) list[off + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = (uint32_t)site;
+    }
+    __syncthreads();
+    const uint32_t total = count;
+    bool changed_any = false;
+    for (uint32_t k0 = 0; k0 < total; k0 += 256u) {  // uniform trip count: whole warps stay together
+    const bool active = k0 + threadIdx.x < total;
+    const uint32_t h = active ? list[k0 + threadIdx.x] : 0u;
+#endif
+    bool changed = false, longseg = false;
+    uint32_t q = 0;
+    FlSegStart s;
+    s.root = FL_NONE; s.rt_prev = 0.0; s.z_prev = 0.0; s.e_out = 0.0; s.rt_out = 0.0;
+    if (active) {
+        const uint32_t p = e.recv[h];
+        bool ended = false;
+        q = h;
+        if (p == h) {
+            s = fl_root_site(e, h, e.tcel[h], changed);
+            q = h + 1u;
+            ended = !(q < e.n && e.recv[q] == h);
+        } else {  // the receiver's segment is strictly higher: finished by an earlier launch
+            s.root = e.root_of[p];
+            if (s.root != FL_NONE) {
+                s.rt_prev = e.rt[p];
+                s.z_prev = e.elev[p];  // the receiver already holds its NEW elevation
+                s.e_out = e.elev[s.root];
+                s.rt_out = e.rt[s.root];
+            }
+        }
+#pragma unroll 1
+        for (int r = 0; r < FL_PSHORT / FL_PB && !ended; ++r) ended = fl_run_batch<FL_PB>(e, q, s, changed);
+#ifdef FL_EMU
+        while (!ended) ended = fl_run_batch<FL_PB>(e, q, s, changed);
+#endif
+        longseg = !ended;
+    }
+#ifdef FL_EMU
+    (void)longseg;
+    if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
+    }
+#else
+    uint32_t todo = __ballot_sync(FL_FULL, longseg);
+    while (todo) {  // the rare long segments of the warp, one after the other, by all lanes together
+        const int src = __ffs((int)todo) - 1;
+        todo &= todo - 1u;
+        FlSegStart w;
+        w.root = __shfl_sync(FL_FULL, s.root, src);
+        w.rt_prev = fl_shfl(s.rt_prev, src);
+        w.z_prev = fl_shfl(s.z_prev, src);
+        w.e_out = fl_shfl(s.e_out, src);
+        w.rt_out = fl_shfl(s.rt_out, src);
+        const uint32_t q_s = __shfl_sync(FL_FULL, q, src);
+        bool ch = false;
+        fl_run_warp<false, 1>(e, q_s, w, ch, chain_smem[threadIdx.x >> 5]);  // (rare: one window ahead is enough)
+        changed |= ch;
+    }
+    changed_any |= changed;
+    }
+    if (changed_any) e.flags[FL_FLAG_CHANGED] = 1u;
+#endif
+}

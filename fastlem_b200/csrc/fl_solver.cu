@@ -137,16 +137,17 @@ struct fastlem_ctx {
     int incr_flow_blocks = 0;         // resident blocks of k_incr_flow (0 = not available)
     int64_t opt_fuse_k4 = 0;     // measured no faster than two launches: kept as an option
     int64_t opt_first_flow = 1;  // the first iteration also uses the dataflow sweeps (layout by subtree sizes)
-    // K5 as one launch (fl_elev.cuh): queues of segment heads, the outlets as seeds
-    unsigned long long* d_queue = nullptr;
-    unsigned long long* d_lqueue = nullptr;
-    uint32_t lqueue_cap = 0;
-    uint32_t* d_seeds_orig = nullptr;  // the outlets, caller's numbering
-    uint32_t* d_seeds = nullptr;       // current numbering
-    uint32_t n_seeds = 0;
+    // K5 split by nesting height (fl_elev.cuh): queue of run starts for the top of the forest, push masks
+    FlQEntry* d_queue = nullptr;   // n entries
+    uint32_t* d_pmask = nullptr;   // zero between sweeps (k_elev_top clears what k_elev_plan sets)
     uint32_t push_epoch = 0;
-    int push_blocks = 0;
-    int64_t opt_k5_push = 0;  // 1: all segments through the push queue (fl_elev.cuh); measured slower than the level sweep (profiles/r2a_*)
+    int top_blocks = 0;            // the most blocks of k_elev_top that can be resident
+    int64_t opt_k5_split = 1;      // 0: the round-1 sweep (heads sorted by height, one launch per height)
+    int64_t opt_k5_cut = -1;       // cut height: -1 = chosen from the previous iteration's level histogram
+    int64_t opt_k5_top_cap = 12288;  // auto cut: at most this many segments go through the queue
+    int64_t opt_k5_top_blocks = 0;   // 0 = one block per SM
+    uint32_t k5_cut = 0;           // the cut of the next sweep
+    bool k5_cut_known = false;
     uint32_t* d_ticket_of = nullptr;  // fused sparse levels of K5
     uint32_t* d_fdone = nullptr;
     uint32_t* d_flvl = nullptr;
@@ -191,12 +192,14 @@ struct fastlem_ctx {
     void* d_tmp = nullptr;        // CUB temp storage (sort / scan)
     size_t tmp_bytes = 0;
 
-    bool opt_profile = false, opt_keep = false;
+    int opt_profile = 0;  // 1: stage times (events, no extra synchronisation); 2: + per-kernel times (synchronises)
+    bool opt_keep = false;
     int64_t opt_sweep = 3;
 
     fastlem_stats stats{};
     cudaEvent_t ev[ST_COUNT + 3] = {};
     cudaEvent_t ev_run[2] = {};
+    cudaEvent_t ev_k[2] = {};  // "profile"=2: brackets one kernel
 };
 
 namespace {
@@ -274,6 +277,22 @@ inline Layout& L_(fastlem_ctx* c) { return c->lay[c->cur]; }
 
 int stage_mark(fastlem_ctx* c, int k) {
     if (c->opt_profile) FL_CK(fl_event_record(c->ev[k], c->stream));
+    return FASTLEM_OK;
+}
+
+// "profile"=2: device time of single kernels (fastlem_stats.ms_kernel); k_begin before the launch, k_end after it
+int k_begin(fastlem_ctx* c) {
+    if (c->opt_profile >= 2) FL_CK(fl_event_record(c->ev_k[0], c->stream));
+    return FASTLEM_OK;
+}
+int k_end(fastlem_ctx* c, int id) {
+    if (c->opt_profile < 2) return FASTLEM_OK;
+    FL_CK(fl_event_record(c->ev_k[1], c->stream));
+    FL_CK(fl_event_sync(c->ev_k[1]));
+    float ms = 0.f;
+    FL_CK(fl_event_elapsed(&ms, c->ev_k[0], c->ev_k[1]));
+    c->stats.ms_kernel[id] += ms;
+    c->stats.n_kernel[id] += 1;
     return FASTLEM_OK;
 }
 
@@ -665,7 +684,6 @@ int rebuild_layout(fastlem_ctx* c, const double* weight) {
     a.lvl = nullptr; a.lvl_n = nullptr;
     LAUNCH_N(k_permute_nodes, n, n, c->d_newpos, a);
     c->cur ^= 1;
-    LAUNCH_N(k_map_list, c->n_seeds, c->n_seeds, c->d_newpos, c->d_seeds);
     if (c->rank_ready) LAUNCH_N(k_rank_inverse, n, n, M.rank, c->d_rank_to_node);
     FL_CK(fl_stream_sync(c->stream));  // h_offs
     for (uint32_t g = c->n_groups; g-- > 0;)  // keys that do not occur (e.g. a level without long paths)
@@ -781,7 +799,6 @@ int rebuild_layout_flow(fastlem_ctx* c, const double* weight) {
     a.lvl = L.lvl; a.lvl_n = M.lvl;
     LAUNCH_N(k_permute_nodes, n, n, c->d_newpos, a);
     c->cur ^= 1;
-    LAUNCH_N(k_map_list, c->n_seeds, c->n_seeds, c->d_newpos, c->d_seeds);
     if (c->rank_ready) LAUNCH_N(k_rank_inverse, n, n, M.rank, c->d_rank_to_node);
     c->stats.n_order += 10;
     c->stats.rebuilds++;
@@ -797,8 +814,10 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     const bool track = c->opt_incremental != 0 && c->k4_valid && !c->need_rebuild && c->opt_rebuild_every != 1;
     {
         Layout& L = L_(c);
+        FL_RC(k_begin(c));
         LAUNCH_N(k_receivers_mask, n, n, L.row_ptr, L.col, L.dist, L.rev, L.elev, L.is_outlet, L.recv, L.drecv, L.cmask,
                  c->d_flags, track ? c->d_chg_node : (uint32_t*)nullptr, track ? c->d_chg_old : (uint32_t*)nullptr);
+        FL_RC(k_end(c, FASTLEM_K_RECEIVERS));
         c->stats.n_receivers++;
     }
     FL_RC(stage_mark(c, 1));
@@ -826,7 +845,9 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
             LAUNCH_N(k_subtree_weight, n, n, c->d_state, c->d_A);
             c->stats.n_order += 3;
         }
+        FL_RC(k_begin(c));
         FL_RC(rebuild_layout_flow(c, c->d_A));
+        FL_RC(k_end(c, FASTLEM_K_REBUILD));
     }
     c->need_rebuild = false;
     FL_RC(stage_mark(c, 7));  // end of the layout rebuild
@@ -853,9 +874,13 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
         LAUNCH_N(k_seg_keys, n, n, L.recv, c->d_depth);
         FL_CK(fl_inclusive_max(c->d_tmp, c->tmp_bytes, c->d_depth, c->d_sg_head, n, c->stream, false));
         LAUNCH_N(k_seg_prepare, n, f, c->d_sg_tail, c->d_sg_wait);
+        FL_RC(k_begin(c));
         LAUNCH_N(k_area_flow, n, f);
+        FL_RC(k_end(c, FASTLEM_K_AREA_FLOW));
         if (f.park_after) {  // the parked (long) climbs, one warp each (persistent grid)
+            FL_RC(k_begin(c));
             FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 4u, 256, c->stream, f);
+            FL_RC(k_end(c, FASTLEM_K_AREA_FLOW_LONG));
             c->stats.kernel_launches++;
         }
         c->stats.n_area += 6;
@@ -887,8 +912,14 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
             }
 #endif
             if (!fused) {
+                FL_RC(k_begin(c));
                 FL_LAUNCH(k_incr_start, wide * 2u, 64, c->stream, f);
-                if (f.park_after) FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 4u, 256, c->stream, f);
+                FL_RC(k_end(c, FASTLEM_K_INCR_START));
+                if (f.park_after) {
+                    FL_RC(k_begin(c));
+                    FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 4u, 256, c->stream, f);
+                    FL_RC(k_end(c, FASTLEM_K_AREA_FLOW_LONG));
+                }
             }
             FL_LAUNCH(k_incr_cleanup, wide, 256, c->stream, f);
             const uint64_t nl = fused ? 6 : (f.park_after ? 7 : 6);
@@ -900,22 +931,50 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     FL_RC(stage_mark(c, 8));  // end of K4
 
     uint32_t launched = 0;
-    if (c->opt_k5_push) {
-        // K5 as one launch (fl_elev.cuh): no ordering of the segment heads, nothing read back before the sweep
+    if (c->opt_k5_split) {
+        // K5 split by nesting height (fl_elev.cuh): nothing is sorted, nothing is read back before the sweep
         FL_RC(stage_mark(c, 5));
-        FlPush e;
-        e.n = n; e.row_ptr = L.row_ptr; e.col = L.col; e.recv = L.recv; e.cmask = L.cmask; e.drecv = L.drecv;
-        e.erod = L.erod; e.A = c->d_A; e.uplift = L.uplift; e.tan_slope = c->has_tan ? L.tan : nullptr;
-        e.elev = L.elev; e.rt = c->d_rt; e.root_of = c->d_root_of; e.queue = c->d_queue; e.lqueue = c->d_lqueue;
-        e.lcap = c->lqueue_cap; e.epoch = ++c->push_epoch; e.seeds = c->d_seeds; e.n_seeds = c->n_seeds;
+        uint32_t cut = c->opt_k5_cut >= 0 ? (uint32_t)c->opt_k5_cut : c->k5_cut;
+        if (c->opt_k5_cut < 0 && !c->k5_cut_known) cut = n <= (uint32_t)c->opt_k5_top_cap ? 0u : 4u;
+        if (cut > FL_CUT_MAX) cut = FL_CUT_MAX;
+        FlSplit e;
+        e.n = n; e.row_ptr = L.row_ptr; e.col = L.col; e.rev = L.rev; e.recv = L.recv; e.cmask = L.cmask;
+        e.is_outlet = L.is_outlet; e.hgt = c->d_hgt; e.drecv = L.drecv; e.erod = L.erod; e.A = c->d_A;
+        e.uplift = L.uplift; e.tan_slope = c->has_tan ? L.tan : nullptr; e.tcel = c->d_tcel; e.elev = L.elev; e.rt = c->d_rt;
+        e.root_of = c->d_root_of; e.pmask = c->d_pmask; e.queue = c->d_queue; e.epoch = ++c->push_epoch; e.cut = cut;
         e.flags = c->d_flags;
-        FL_LAUNCH(k_push_seed, blocks_for(c->n_seeds ? c->n_seeds : 1u), 256, c->stream, e);
+        FL_RC(k_begin(c));
+        LAUNCH_N(k_elev_plan, n, e);
+        FL_RC(k_end(c, FASTLEM_K_ELEV_PLAN));
+        FL_RC(k_begin(c));
 #ifdef FL_EMU
-        FL_LAUNCH(k_elev_push, 1, 1, c->stream, e);
+        FL_LAUNCH(k_elev_top, 1, 1, c->stream, e);
 #else
-        FL_LAUNCH(k_elev_push, (unsigned)c->push_blocks, 256, c->stream, e);
+        {
+            int64_t blocks = c->opt_k5_top_blocks > 0 ? c->opt_k5_top_blocks : (int64_t)c->sm_count;
+            if (blocks > (int64_t)c->top_blocks) blocks = c->top_blocks;
+            FL_LAUNCH(k_elev_top, (unsigned)blocks, 256, c->stream, e);
+        }
 #endif
-        launched = 2;
+        FL_RC(k_end(c, FASTLEM_K_ELEV_TOP));
+        c->stats.kernel_launches++;
+        for (uint32_t lv = cut; lv-- > 0;) {
+            FL_RC(k_begin(c));
+#ifdef FL_EMU
+            LAUNCH_N(k_elev_low, n, e, lv);
+#else
+            FL_LAUNCH(k_elev_low, (n + FL_LOW_CHUNK - 1u) / FL_LOW_CHUNK, 256, c->stream, e, lv);
+            c->stats.kernel_launches++;
+#endif
+            FL_RC(k_end(c, FASTLEM_K_ELEV_LOW));
+        }
+        c->stats.n_elevation += 2 + cut;
+#ifdef FL_EMU
+        // emulation only: every push mask must have been consumed (a mask left behind = a segment at or above the cut
+        // whose receiver's segment lies below it, i.e. the nesting heights are not strictly decreasing downwards)
+        for (uint32_t i = 0; i < n; ++i)
+            if (c->d_pmask[i]) return fail(c, FASTLEM_E_STATE, "K5: a push mask was not consumed (nesting heights inconsistent)");
+#endif
     } else {
         // order the segment heads by descending nesting height (exact for the current forest; an upper bound of the
         // largest height after incremental passes -- heights that no longer occur are empty levels)
@@ -1027,22 +1086,30 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     FL_RC(stage_mark(c, 6));
     FL_RC(read_flags(c));
     FL_CK(fl_last_error());
-    if (c->opt_k5_push) {
+    if (c->opt_k5_split) {
         if (c->h_flags[FL_FLAG_BROKEN] & 1u)
             return fail(c, FASTLEM_E_STATE, "K4: a climb met an unpublished site (internal error)");
         if (c->h_flags[FL_FLAG_BROKEN] & 8u)
             return fail(c, FASTLEM_E_STATE, "K4: the fused pass waited for parked work too long (internal error)");
         if (c->h_flags[FL_FLAG_BROKEN])
             return fail(c, FASTLEM_E_STATE,
-                        "K5: the segment queue broke (internal error; flags " + std::to_string(c->h_flags[FL_FLAG_BROKEN]) +
+                        "K5: the run queue broke (internal error; flags " + std::to_string(c->h_flags[FL_FLAG_BROKEN]) +
                             " tail " + std::to_string(c->h_flags[FLQ_TAIL]) + " head " + std::to_string(c->h_flags[FLQ_HEAD]) +
-                            " ltail " + std::to_string(c->h_flags[FLQ_LTAIL]) + " lhead " +
-                            std::to_string(c->h_flags[FLQ_LHEAD]) + " pending " + std::to_string(c->h_flags[FLQ_PENDING]) +
-                            " seeds " + std::to_string(c->n_seeds) + " iteration " + std::to_string(it) + ")");
-        // bookkeeping of the numbering: nesting height met by K4 (at the roots it finished), segments the sweep visited
+                            " done " + std::to_string(c->h_flags[FLQ_DONE]) + " iteration " + std::to_string(it) + ")");
+        // bookkeeping of the numbering: nesting height met by K4 (at the roots it finished), segments of the forest
         uint32_t maxh = c->h_flags[FL_FLAG_MAXDEPTH];
         if (incr && c->prev_maxh > maxh) maxh = c->prev_maxh;
-        const uint32_t n_heads = c->h_flags[FLQ_TAIL];
+        const uint32_t* hist = c->h_flags + FLQ_HIST;
+        uint32_t n_heads = 0;
+        for (int b = 0; b < 32; ++b) n_heads += hist[b];
+        // cut height of the next sweep: the smallest one that leaves at most top_cap segments to the queue
+        {
+            uint32_t above = 0, cut = FL_CUT_MAX;
+            for (int b = 31; b >= (int)FL_CUT_MAX; --b) above += hist[b];
+            while (cut > 0u && above + hist[cut - 1u] <= (uint32_t)c->opt_k5_top_cap) { above += hist[cut - 1u]; --cut; }
+            c->k5_cut = cut;
+            c->k5_cut_known = true;
+        }
         c->stats.path_levels = maxh + 1;
         c->stats.paths = n_heads;
         c->prev_maxh = maxh;
@@ -1054,8 +1121,9 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
                       (unsigned long long)c->maxh_at_rebuild * (unsigned long long)c->opt_rebuild_height + 200ull))
             c->need_rebuild = true;
         if (c->trace_iters && it < 400u)
-            std::fprintf(stderr, "[fastlem trace] it %u: chg %u incr %d rebuilt %d heads %u maxh %u next_rebuild %d\n", it,
-                         n_chg, (int)incr, (int)rebuilt, n_heads, maxh, (int)c->need_rebuild);
+            std::fprintf(stderr, "[fastlem trace] it %u: chg %u incr %d rebuilt %d heads %u maxh %u cut %u top %u next_rebuild %d\n",
+                         it, n_chg, (int)incr, (int)rebuilt, n_heads, maxh, c->k5_cut, c->h_flags[FLQ_TAIL],
+                         (int)c->need_rebuild);
     } else if (c->h_flags[FL_FLAG_BROKEN])
         return fail(c, FASTLEM_E_STATE, "K5: a segment waited for its receiver's segment too long (internal error)");
     *changed_out = c->h_flags[FL_FLAG_CHANGED] != 0;
@@ -1092,7 +1160,8 @@ int reset_layout(fastlem_ctx* c) {
     FL_CK(fl_d2d(L.elev, c->d_init, sizeof(double) * n, c->stream));
     LAUNCH_N(k_iota, n, n, L.orig_of);
     FL_CK(fl_memset(L.lvl, 0, sizeof(uint32_t) * n, c->stream));
-    if (c->n_seeds) FL_CK(fl_d2d(c->d_seeds, c->d_seeds_orig, sizeof(uint32_t) * c->n_seeds, c->stream));
+    FL_CK(fl_memset(c->d_pmask, 0, sizeof(uint32_t) * n, c->stream));
+    c->k5_cut_known = false;
     c->prev_maxh = 0;
     c->k4_valid = false;
     c->k4_last_full = true;
@@ -1167,11 +1236,8 @@ int alloc_graph_buffers(fastlem_ctx* c, uint32_t n, uint32_t nnz) {
     FL_CK(dalloc(c, c->d_sg_wait, n));
     FL_CK(dalloc(c, c->d_sg_done, n));
     FL_CK(dalloc(c, c->d_ready, (size_t)n + 65536));
-    c->lqueue_cap = n / 8u + 64u;
     FL_CK(dalloc(c, c->d_queue, n));
-    FL_CK(dalloc(c, c->d_lqueue, c->lqueue_cap));
-    FL_CK(dalloc(c, c->d_seeds_orig, n));
-    FL_CK(dalloc(c, c->d_seeds, n));
+    FL_CK(dalloc(c, c->d_pmask, n));
     FL_CK(dalloc(c, c->d_ticket_of, n));
     FL_CK(dalloc(c, c->d_fdone, n));
     FL_CK(dalloc(c, c->d_flvl, n));
@@ -1234,6 +1300,7 @@ int fastlem_create(fastlem_ctx** out, int device_ordinal) {
     bool ok = true;
     for (int k = 0; k < ST_COUNT + 3; ++k) ok = ok && fl_event_create(&c->ev[k]) == cudaSuccess;
     for (int k = 0; k < 2; ++k) ok = ok && fl_event_create(&c->ev_run[k]) == cudaSuccess;
+    for (int k = 0; k < 2; ++k) ok = ok && fl_event_create(&c->ev_k[k]) == cudaSuccess;
     void* fl = nullptr;
     ok = ok && fl_malloc(&fl, sizeof(uint32_t) * FL_N_FLAGS) == cudaSuccess;
     c->d_flags = (uint32_t*)fl;
@@ -1259,6 +1326,8 @@ void fastlem_destroy(fastlem_ctx* c) {
         if (c->ev[k]) fl_event_destroy(c->ev[k]);
     for (int k = 0; k < 2; ++k)
         if (c->ev_run[k]) fl_event_destroy(c->ev_run[k]);
+    for (int k = 0; k < 2; ++k)
+        if (c->ev_k[k]) fl_event_destroy(c->ev_k[k]);
     if (c->stream_ok) fl_stream_destroy(c->stream);
     delete c;
 }
@@ -1270,7 +1339,7 @@ int fastlem_get_device(const fastlem_ctx* c) { return c ? c->device : -1; }
 int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
     if (!c || !name) return FASTLEM_E_INVALID;
     std::string s(name);
-    if (s == "profile") c->opt_profile = value != 0;
+    if (s == "profile") c->opt_profile = value < 0 ? 0 : (value > 2 ? 2 : (int)value);
     else if (s == "keep_stages") c->opt_keep = value != 0;
     else if (s == "sweep") {
         if (value < 0 || value > 3)
@@ -1295,8 +1364,17 @@ int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
     } else if (s == "key_base") {
         if (value < 1 || value > (int64_t)FL_KEY_BASE) return fail(c, FASTLEM_E_INVALID, "option key_base: 1..254");
         c->opt_key_base = value;
-    } else if (s == "k5_push") {
-        c->opt_k5_push = value != 0;
+    } else if (s == "k5_split") {
+        c->opt_k5_split = value != 0;
+    } else if (s == "k5_cut") {
+        if (value < -1 || value > (int64_t)FL_CUT_MAX) return fail(c, FASTLEM_E_INVALID, "option k5_cut: -1 (auto) or 0..8");
+        c->opt_k5_cut = value;
+    } else if (s == "k5_top_cap") {
+        if (value < 0) return fail(c, FASTLEM_E_INVALID, "option k5_top_cap: >= 0");
+        c->opt_k5_top_cap = value;
+    } else if (s == "k5_top_blocks") {
+        if (value < 0) return fail(c, FASTLEM_E_INVALID, "option k5_top_blocks: 0 (one per SM) or a block count");
+        c->opt_k5_top_blocks = value;
     } else if (s == "fuse_levels") {
         c->opt_fuse_levels = value != 0;
     } else if (s == "rebuild_height") {
@@ -1356,16 +1434,16 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     LAUNCH_N(k_rev_slots, n, n, c->orig.row_ptr, c->orig.col, c->orig.dist, c->orig.rev, c->d_flags);
     FL_CK(fl_d2h(c->h_flags, c->d_flags, sizeof(uint32_t), c->stream));
     FL_CK(fl_memset(c->d_ready, 0, sizeof(uint32_t) * ((size_t)n + 65536), c->stream));
-    FL_CK(fl_memset(c->d_queue, 0, sizeof(unsigned long long) * n, c->stream));
-    FL_CK(fl_memset(c->d_lqueue, 0, sizeof(unsigned long long) * c->lqueue_cap, c->stream));
+    FL_CK(fl_memset(c->d_queue, 0, sizeof(FlQEntry) * n, c->stream));
     c->push_epoch = 0;
-    c->n_seeds = 0;
 #ifndef FL_EMU
     {
+        // k_elev_top waits on queue entries: every block must be resident
         int occ = 0;
-        c->push_blocks = fl_sm_count();
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elev_push, 256, 0) == cudaSuccess && occ > 0)
-            c->push_blocks = occ * fl_sm_count();
+        c->top_blocks = fl_sm_count();
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elev_top, 256, 0) != cudaSuccess || occ < 1)
+            return fail(c, FASTLEM_E_CUDA, "set_graph: k_elev_top does not fit on an SM");
+        c->top_blocks = occ * fl_sm_count();  // the most that can be resident
     }
     {
         int occ = 0;
@@ -1445,8 +1523,6 @@ int fastlem_set_parameters(fastlem_ctx* c, const double* initial_elevation, cons
         }
         FL_CK(fl_h2d(c->orig.tan, tan_max_slope, sizeof(double) * n, c->stream));
     }
-    c->n_seeds = n_outlets;  // the seeds of the top-down sweep (fl_elev.cuh)
-    if (n_outlets) FL_CK(fl_h2d(c->d_seeds_orig, outlets, sizeof(uint32_t) * n_outlets, c->stream));
     FL_CK(fl_h2d(c->orig.is_outlet, table.data(), n, c->stream));
     FL_CK(fl_stream_sync(c->stream));
     // the flood order of lake removal is a function of (graph, outlets) only: keep it when an ensemble member changes

@@ -52,6 +52,86 @@ def run_members_shared_graph(graph, member_params, make_context, max_iteration=N
     return out
 
 
+class MemberPool:
+    """A pool of ensemble members handed out one at a time, first come first served, to whichever rank is free
+    (members differ in their iteration counts by +-20 %, so a static `t mod world` split leaves ranks idle).
+    The shared counter lives in the process group's store (the TCPStore torchrun sets up: one `add` round trip per
+    member, nothing on the data path); with a single rank it is a local counter."""
+
+    def __init__(self, n_members, key="fastlem_pool", store=None):
+        import threading
+        self.n_members = int(n_members)
+        self.key = key
+        self.store = store
+        self._next = 0
+        self._lock = threading.Lock()
+
+    @classmethod
+    def for_process_group(cls, n_members, key):
+        import torch.distributed as dist
+        store = None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            store = dist.distributed_c10d._get_default_store()
+        return cls(n_members, key, store)
+
+    def take(self):
+        """Next member index, or None when the pool is empty."""
+        if self.store is not None:
+            t = int(self.store.add(self.key, 1)) - 1
+        else:
+            with self._lock:
+                t = self._next
+                self._next += 1
+        return t if t < self.n_members else None
+
+
+def run_pool(ctx, pool, make_params, on_result, max_iteration=None):
+    """Run members from `pool` on one context that already holds the shared graph (set_graph done once).
+
+    make_params(t) -> dict(initial, erodibility, uplift, tan_max_slope (optional), outlets): host arrays of member t.
+                      It runs on a helper thread while the previous member is being solved (one member ahead, so the
+                      host-side preparation and the next set_parameters never wait for each other).
+    on_result(t, iterations, ctx): called after member t's run, before the next set_parameters (the caller downloads
+                      the elevations to the host or to a device buffer there).
+    Returns the list of members this context ran.
+    """
+    import queue
+    import threading
+    ready = queue.Queue()
+    go = threading.Semaphore(1)  # one member is prepared ahead of the one being solved
+    failure = []
+
+    def producer():
+        try:
+            while True:
+                go.acquire()
+                t = pool.take()
+                if t is None:
+                    break
+                ready.put((t, make_params(t)))
+        except BaseException as ex:  # surfaced on the consumer side
+            failure.append(ex)
+        ready.put(None)
+
+    th = threading.Thread(target=producer, daemon=True)
+    th.start()
+    done = []
+    while True:
+        item = ready.get()
+        if item is None:
+            break
+        t, prm = item
+        ctx.set_parameters(prm["initial"], prm["erodibility"], prm["uplift"], prm.get("tan_max_slope"), prm["outlets"])
+        go.release()  # the next member may be prepared while this one is solved
+        it = ctx.run(max_iteration)
+        on_result(t, it, ctx)
+        done.append(t)
+    th.join()
+    if failure:
+        raise failure[0]
+    return done
+
+
 def gather_elevations(local, n_members, n_sites, rank, world, device="cpu"):
     """All-gather the members' elevations: returns an (n_members, n_sites) float64 array on every rank.
 

@@ -119,7 +119,21 @@ typedef struct fastlem_stats {
     uint32_t incremental_iterations; /* iterations whose drainage areas were updated incrementally */
     uint32_t flood_on_device; /* 1: the flood order was computed on the device, 0: exact host replay (ties) */
     uint32_t reserved;
+    /* "profile"=2 only (synchronises after every bracketed kernel: a diagnostic mode): device time and launch count
+     * of single kernels of the default path, summed over the last run; index = FASTLEM_K_* */
+    double ms_kernel[8];
+    uint64_t n_kernel[8];
 } fastlem_stats;
+enum {
+    FASTLEM_K_RECEIVERS = 0,      /* k_receivers_mask (K1) */
+    FASTLEM_K_AREA_FLOW = 1,      /* k_area_flow: thread-level climbs of a full K4 pass */
+    FASTLEM_K_INCR_START = 2,     /* k_incr_start: thread-level climbs of an incremental K4 pass */
+    FASTLEM_K_AREA_FLOW_LONG = 3, /* k_area_flow_long: warp-level climbs of the long segments (K4) */
+    FASTLEM_K_ELEV_PLAN = 4,      /* k_elev_plan (K5) */
+    FASTLEM_K_ELEV_TOP = 5,       /* k_elev_top (K5: the run queue) */
+    FASTLEM_K_ELEV_LOW = 6,       /* k_elev_low (K5: one launch per nesting height below the cut) */
+    FASTLEM_K_REBUILD = 7         /* every kernel of a site renumbering */
+};
 int fastlem_get_stats(const fastlem_ctx* ctx, fastlem_stats* out);
 
 /* Stage dumps of the LAST iteration executed, for parity tests.  `bytes` must equal the size of the

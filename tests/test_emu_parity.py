@@ -177,7 +177,22 @@ def test_head_ordering_deep_nesting_path(oracle, emu_lib, name):
     """The head ordering of sweep 3 sorts on a fixed key base; segments nesting deeper than the base take a second
     pass with the exact base.  key_base=1 forces that path on small inputs."""
     m, p, outlets, initial, max_iteration = scenario(name)
-    with _ctx(emu_lib, sweep=3, key_base=1) as ctx:
+    with _ctx(emu_lib, sweep=3, k5_split=0, key_base=1) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
+
+
+@pytest.mark.parametrize("opts", [dict(k5_cut=0), dict(k5_cut=1), dict(k5_cut=2), dict(k5_cut=4), dict(k5_cut=8),
+                                  dict(k5_top_cap=0), dict(k5_top_cap=40), dict(k5_split=0)],
+                         ids=lambda o: ",".join(f"{k}={v}" for k, v in o.items()))
+@pytest.mark.parametrize("name", ["uniform", "advanced", "uplift", "max_slope", "mixed_slope", "plateau", "disconnected",
+                                  "interior_outlets", "single_outlet", "lattice"])
+def test_k5_split_by_nesting_height(oracle, emu_lib, name, opts):
+    """K5 split at any cut height (everything through the run queue ... everything by per-height launches; the cut
+    chosen from the level histogram with a tiny / zero queue budget) gives the oracle's bits; trees without an outlet
+    stay unvisited."""
+    m, p, outlets, initial, max_iteration = scenario(name)
+    with _ctx(emu_lib, sweep=3, **opts) as ctx:
         helpers.load_ctx(ctx, m, p, outlets, initial)
         assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
 

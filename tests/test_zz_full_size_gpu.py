@@ -26,6 +26,27 @@ def test_c3_four_million_sites_advanced(oracle, gpu_ctx_factory):
         assert it > 100
 
 
+def test_c4_sixteen_million_sites(oracle, gpu_ctx_factory):
+    """BASELINE config C4 at full size: 16M sites, uniform erodibility, rim outlets, generate() to convergence on one
+    B200 (the loop of src/lem/generator.rs:140-210).  The graph is the jittered 4000 x 4000 lattice (planar
+    triangulation, degree 6 on average; a 16M-site Delaunay build takes several minutes on the host).  Iteration 1 stage
+    by stage against the oracle (receivers, labels, lake connection, areas, response times, elevations: bit-exact),
+    then the size-independent properties of the converged result: determinism over two runs, a forest draining to the
+    outlets with elevations increasing upstream, conservation of the drainage area, and the oracle's own iteration
+    finding the device result to be a fixed point with the same receivers."""
+    from tools import workloads as W
+    m = W.lattice_model(4000, 4000, jitter=0.35, seed=1)
+    p = W.uniform_params(m["n"])
+    outlets = W.outlets_for(m, p)
+    assert m["n"] == 16000000
+    initial = oracle.initial_elevations(p["base"])
+    with gpu_ctx_factory() as ctx:
+        _, it = helpers.check_converged_properties(ctx, oracle, m, p, outlets, initial, first_iterations=0)
+        st = ctx.stats()
+        assert it > 1000
+        assert st["flood_on_device"] == 1
+
+
 def test_ensemble_members_on_one_shared_graph_gpu(oracle, product_lib):
     """The shared-graph ensemble runner on the device (same checks as tests/test_emu_parity.py)."""
     import numpy as np

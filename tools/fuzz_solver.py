@@ -90,7 +90,7 @@ def main():
             opts = dict(incremental=int(rng.integers(0, 2)), incr_div=int(rng.choice([1, 2, 16, 64])),
                         rebuild_every=int(rng.choice([0, 0, 1, 2, 5, 1000])), park_after=int(rng.choice([0, 4, 8, 64])),
                         key_base=int(rng.choice([1, 2, 3, 254])), fuse_levels=int(rng.integers(0, 2)),
-                        first_flow=int(rng.integers(0, 2)), flood_device=int(rng.integers(0, 2)), k5_push=int(rng.integers(0, 2)),
+                        first_flow=int(rng.integers(0, 2)), flood_device=int(rng.integers(0, 2)), k5_split=int(rng.integers(0, 4) != 0), k5_cut=int(rng.integers(-1, 9)), k5_top_cap=int(rng.choice([0, 10, 200, 12288])),
                         rebuild_growth=int(rng.choice([1, 4, 50])), rebuild_height=int(rng.choice([100, 150, 400])))
             try:
                 with _native.Context(0, lib) as ctx:
