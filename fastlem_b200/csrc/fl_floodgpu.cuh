@@ -54,13 +54,21 @@ __device__ __forceinline__ unsigned long long flg_bits(double d) { return (unsig
 
 // undirected edge lengths (each edge once, from its lower endpoint) as sortable keys; flags[3] on a non-positive or
 // non-finite length.  Slots that are not the lower endpoint get FLG_KEY_NONE (sorted last).
+// Edges between two outlets take no part: they are self-loops of the contracted source.  In the heap flood they only
+// ever produce entries for sites that are already in the heap with key 0.0 and are popped (visited) before any
+// positive key, i.e. stale entries that are skipped when they surface -- so their lengths may tie freely.  This is
+// the case of the reference's own `add_edge_sites` rim (equally spaced boundary sites, builder.rs:115-122) under an
+// ocean mask (examples/terrain_generation_advanced.rs:178-182).
 __global__ void __launch_bounds__(256) k_flg_edge_keys(FlFloodG g, unsigned long long* keys) {
     const uint32_t i = FL_TID;
     if (i >= g.n) return;
+    const bool out_i = g.is_outlet[i] != 0;
     for (uint32_t s = g.row_ptr[i]; s < g.row_ptr[i + 1]; ++s) {
         const double d = g.dist[s];
-        if (!(d > 0.0) || !(d < 1.7976931348623157e308)) g.flags[3] = 1u;
-        keys[s] = (g.col[s] > i) ? flg_bits(d) : FLG_KEY_NONE;
+        const uint32_t j = g.col[s];
+        const bool inner = out_i && g.is_outlet[j] != 0;
+        if (!inner && (!(d > 0.0) || !(d < 1.7976931348623157e308))) g.flags[3] = 1u;
+        keys[s] = (j > i && !inner) ? flg_bits(d) : FLG_KEY_NONE;
     }
 }
 __global__ void __launch_bounds__(256) k_flg_dup_check(uint32_t m, const unsigned long long* __restrict__ sorted,

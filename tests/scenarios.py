@@ -67,6 +67,22 @@ def scenario(name, n=None):
         p = W.uniform_params(m["n"])
         p["base"] = 2.0 + W.value_noise(m["sites"], 0.08, seed=9, octaves=3)
         return _finish(m, p)
+    if name in ("edge_sites_ocean", "edge_sites_partial"):
+        # terrain_generation_advanced.rs:36-42,178-182: relaxed random sites + add_edge_sites(None, None) (equally spaced
+        # rim sites), outlets = ocean flood-filled from the rim.
+        # _ocean: the whole rim is ocean (every tied edge joins two outlets); _partial: parts of the rim are land
+        nn = n or 3000
+        pts = W.random_sites(nn, seed=23)
+        from scipy.spatial import Delaunay
+        pts = W._lloyd_step(pts, Delaunay(pts), (0.0, 0.0), (100.0, 100.0))
+        # 64 sites per side: spacing 100/64 is exact in binary, so ALL rim edges have the same length bit for bit (with the
+        # default count the lerp's rounding makes most of them differ in the last place)
+        m = W.delaunay_model_with_rim(W.add_edge_sites(pts, edge_num_x=64, edge_num_y=64), nn)
+        p = W.uniform_params(m["n"])
+        p["erodibility"] = np.abs(W.value_noise(m["sites"], 8.0 / 75.0, seed=4, octaves=3)) * 4.0 + 0.1
+        p["is_outlet"] = W.ocean_rim_outlets(m, nn, band=3.0 if name == "edge_sites_ocean" else None, seed=5)
+        assert p["is_outlet"].any()
+        return _finish(m, p)
     if name == "lattice":  # equal rim edge lengths: exact key ties in the flood heap
         m = W.lattice_model(40, 30, jitter=0.3, seed=4)
         return _finish(m, W.uniform_params(m["n"]))

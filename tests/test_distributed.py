@@ -51,6 +51,62 @@ def _raster_worker(rank, world, port, emu_lib, out_dir):
     dist.destroy_process_group()
 
 
+def _pool_worker(rank, world, port, emu_lib, out_dir):
+    """The dynamic ensemble pool (bench.py --gpus N): one shared graph per rank, members taken first come first served
+    through the process group's store, results gathered at the end (variable number of members per rank)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from fastlem_b200 import _native, ensemble
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m, p, outlets, initial, _ = scenario("uniform", 500)
+    n = m["n"]
+    n_members = 7
+    pool = ensemble.MemberPool.for_process_group(n_members, "pool_test")
+    mine = {}
+
+    def make_params(t):
+        return dict(initial=initial, erodibility=_pool_erodibility(n, t), uplift=p["uplift"], outlets=outlets)
+
+    def on_result(t, it, ctx):
+        mine[t] = (ctx.download(), it)
+    with _native.Context(0, emu_lib) as ctx:
+        ctx.set_graph(m["row_ptr"], m["col"], m["dist"], m["areas"])
+        done = ensemble.run_pool(ctx, pool, make_params, on_result)
+    assert sorted(done) == sorted(mine)
+    # gather: member ids and elevations, padded to the largest count
+    counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([len(done)], dtype=torch.int64))
+    most = int(max(int(c) for c in counts))
+    ids = torch.full((most,), -1, dtype=torch.int64)
+    vals = torch.zeros((most, n), dtype=torch.float64)
+    for k, t in enumerate(done):
+        ids[k] = t
+        vals[k] = torch.from_numpy(mine[t][0])
+    all_ids = [torch.empty_like(ids) for _ in range(world)]
+    all_vals = [torch.empty_like(vals) for _ in range(world)]
+    dist.all_gather(all_ids, ids)
+    dist.all_gather(all_vals, vals)
+    if rank == 0:
+        out = {}
+        for r in range(world):
+            for k in range(most):
+                t = int(all_ids[r][k])
+                if t >= 0:
+                    assert t not in out, "a member ran twice"
+                    out[t] = all_vals[r][k].numpy()
+        assert sorted(out) == list(range(n_members)), "every member ran exactly once"
+        np.save(os.path.join(out_dir, "pool.npy"), np.stack([out[t] for t in range(n_members)]))
+    dist.destroy_process_group()
+
+
+def _pool_erodibility(n, t):
+    return 0.5 + np.random.default_rng(100 + t).random(n)
+
+
 RASTER = dict(width=45, height=37, x0=0.0, y0=0.0, span_x=100.0, span_y=100.0, pixel_offset=0.5)
 
 
@@ -116,3 +172,21 @@ def test_ensemble_two_ranks_gloo(tmp_path, emu_lib, oracle):
         inp, m, p = _member("uniform", 600, sc)
         ref, _ = oracle.generate(m, inp["erodibility"], inp["uplift"], None, inp["outlets"], inp["initial"])
         assert np.array_equal(a[t], ref), f"member {t}"
+
+
+def test_member_pool_single_process():
+    from fastlem_b200 import ensemble
+    pool = ensemble.MemberPool(5)
+    assert [pool.take() for _ in range(7)] == [0, 1, 2, 3, 4, None, None]
+
+
+def test_ensemble_pool_two_ranks_gloo(tmp_path, emu_lib, oracle):
+    """Dynamic member assignment over 2 ranks: every member exactly once, each bit-identical to the oracle."""
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 1000)
+    mp.spawn(_pool_worker, args=(2, port, emu_lib, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / "pool.npy")
+    m, p, outlets, initial, _ = scenario("uniform", 500)
+    for t in range(got.shape[0]):
+        ref, _ = oracle.generate(m, _pool_erodibility(m["n"], t), p["uplift"], None, outlets, initial)
+        assert np.array_equal(got[t], ref), f"member {t}"

@@ -125,6 +125,21 @@ def test_flood_rank_device_larger(oracle, emu_lib, name, n):
         assert ctx.stats()["flood_on_device"] == 1
 
 
+@pytest.mark.parametrize("name,on_device", [("edge_sites_ocean", 1), ("edge_sites_partial", 0)])
+def test_flood_rank_with_add_edge_sites_rim(oracle, emu_lib, name, on_device):
+    """The reference's own `add_edge_sites` rim (builder.rs:54-131: equally spaced boundary sites, exact edge-length ties)
+    under an ocean mask flood-filled from the rim (terrain_generation_advanced.rs:178-182).  When the whole rim is ocean
+    every tied edge joins two outlets -- a self-loop of the contracted source that only ever yields stale heap entries --
+    and the flood order is computed on the device; a rim that is partly land keeps real ties and takes the host replay.
+    Either way the order and the whole generate() equal the oracle's."""
+    m, p, outlets, initial, max_iteration = scenario(name)
+    with _ctx(emu_lib) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert np.array_equal(ctx.fetch("flood_rank"), oracle.flood_order(m, outlets))
+        assert ctx.stats()["flood_on_device"] == on_device
+        assert helpers.check_generate(ctx, oracle, m, p, outlets, initial, max_iteration)
+
+
 def test_rerun_restarts_from_initial(emu_lib):
     m, p, outlets, initial, _ = scenario("uniform", 800)
     with _ctx(emu_lib) as ctx:

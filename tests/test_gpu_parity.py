@@ -158,7 +158,8 @@ def test_solver_options_do_not_change_results(oracle, gpu_ctx_factory, name, n, 
 
 @pytest.mark.parametrize("name,n", [("uniform", 3000), ("advanced", 5000), ("lattice", None), ("lattice_regular", None),
                                     ("disconnected", None), ("interior_outlets", 8000), ("single_outlet", 6000),
-                                    ("uniform", 200000), ("advanced", 200000), ("uniform", 1000000)])
+                                    ("uniform", 200000), ("advanced", 200000), ("uniform", 1000000),
+                                    ("edge_sites_ocean", 3000), ("edge_sites_ocean", 100000), ("edge_sites_partial", 3000)])
 def test_flood_order_on_device(oracle, gpu_ctx_factory, name, n):
     """fl_floodgpu.cuh: pop order of the lake flood from the minimum spanning tree, against the oracle's heap replay."""
     m, p, outlets, initial, _ = scenario(name, n) if n else scenario(name)
@@ -166,7 +167,7 @@ def test_flood_order_on_device(oracle, gpu_ctx_factory, name, n):
     with gpu_ctx_factory() as ctx:
         helpers.load_ctx(ctx, m, p, outlets, initial)
         assert np.array_equal(ctx.fetch("flood_rank"), ref)
-        assert ctx.stats()["flood_on_device"] == (0 if name == "lattice_regular" else 1)
+        assert ctx.stats()["flood_on_device"] == (0 if name in ("lattice_regular", "edge_sites_partial") else 1)
     with gpu_ctx_factory(flood_device=0) as ctx:
         helpers.load_ctx(ctx, m, p, outlets, initial)
         assert np.array_equal(ctx.fetch("flood_rank"), ref)

@@ -30,11 +30,15 @@ def _orient_ccw(pts, tri):
     return tri, np.abs(cross) * 0.5
 
 
-def model_from_triangles(pts, tri, hull_cycle=None, dedupe=False):
-    """Boundary-format model from CCW triangles, following builder.rs:249-270."""
+def model_from_triangles(pts, tri, hull_cycle=None, dedupe=False, clockwise=False):
+    """Boundary-format model from CCW triangles, following builder.rs:249-270.  clockwise: orient the triangles the
+    other way round before the half-edge pass (the rule `from < to` drops a hull edge whose only half-edge runs from the
+    larger to the smaller index, so the orientation decides WHICH hull edges exist)."""
     pts = np.ascontiguousarray(pts, dtype=np.float64)
     n = pts.shape[0]
     tri, tri_area = _orient_ccw(pts, np.asarray(tri, dtype=np.int64))
+    if clockwise:
+        tri = np.ascontiguousarray(tri[:, [0, 2, 1]])
     # half-edges in (triangle, k) order: (a,b), (b,c), (c,a); keep from < to
     frm = tri[:, [0, 1, 2]].reshape(-1)
     to = tri[:, [1, 2, 0]].reshape(-1)
@@ -144,6 +148,74 @@ def _lloyd_step(pts, dl, bound_min, bound_max):
     out = pts.copy()
     ok = (~on_hull) & (acc_a > 0)
     out[ok] = acc_c[ok] / acc_a[ok, None]
+    return out
+
+
+def add_edge_sites(pts, bound_min=(0.0, 0.0), bound_max=(100.0, 100.0), edge_num_x=None, edge_num_y=None):
+    """TerrainModel2DBulider::add_edge_sites (builder.rs:54-131): equally spaced sites along the bounding box, appended
+    after the given sites, corner order (min,min) -> (min,max) -> (max,max) -> (max,min), edge i from corner i towards
+    corner i+1 at t = j / edge_num, j = 0 .. edge_num-1."""
+    pts = np.asarray(pts, dtype=np.float64)
+    n = pts.shape[0]
+    (x0, y0), (x1, y1) = bound_min, bound_max
+    corners = [(x0, y0), (x0, y1), (x1, y1), (x1, y0)]
+    out = []
+    for i, c in enumerate(corners):
+        nxt = corners[(i + 1) % 4]
+        if i % 2 == 1:
+            num = edge_num_x if edge_num_x is not None else int(np.sqrt(n / (y1 - y0) * (x1 - x0)))
+        else:
+            num = edge_num_y if edge_num_y is not None else int(np.sqrt(n / (x1 - x0) * (y1 - y0)))
+        for j in range(num):
+            t = j / num
+            out.append((c[0] * (1.0 - t) + nxt[0] * t, c[1] * (1.0 - t) + nxt[1] * t))
+    return np.concatenate([pts, np.array(out, dtype=np.float64).reshape(-1, 2)])
+
+
+def delaunay_model_with_rim(pts, n_inner, bound_min=(0.0, 0.0), bound_max=(100.0, 100.0)):
+    """Delaunay model of sites whose tail (indices >= n_inner) lies exactly ON the bounding box (add_edge_sites).  Qhull
+    drops collinear hull points from the triangulation; delaunator (the crate's triangulator, exact predicates) keeps
+    them: every pair of consecutive rim sites is joined through a triangle with an interior apex.  That topology is the
+    Delaunay triangulation of the sites with the rim bulged outwards by a hair (strictly convex position); lengths and
+    areas are then taken from the TRUE coordinates."""
+    from scipy.spatial import Delaunay
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    lo, hi = np.asarray(bound_min, float), np.asarray(bound_max, float)
+    mid, half = 0.5 * (lo + hi), 0.5 * (hi - lo)
+    bulged = pts.copy()
+    rim = bulged[n_inner:]
+    u = (rim - mid) / half  # in [-1, 1]^2, on the boundary of the square
+    # push every rim site outwards along its edge's normal by eps * (1 - s^2), s = position along the edge in [-1, 1]
+    eps = 1e-6 * half.max()
+    on_x = np.abs(np.abs(u[:, 0]) - 1.0) < 1e-12
+    on_y = np.abs(np.abs(u[:, 1]) - 1.0) < 1e-12
+    rim[on_x, 0] += np.sign(u[on_x, 0]) * eps * (1.0 - u[on_x, 1] ** 2)
+    rim[on_y, 1] += np.sign(u[on_y, 1]) * eps * (1.0 - u[on_y, 0] ** 2)
+    # clockwise triangles: the half-edges along the rim then run in the order add_edge_sites appends the rim sites, so the
+    # rule `from < to` (builder.rs:255-263) KEEPS the rim edges -- the case in which their equal lengths matter
+    return model_from_triangles(pts, Delaunay(bulged).simplices, clockwise=True)
+
+
+def ocean_rim_outlets(model, n_inner, band=None, seed=0):
+    """Outlet mask in the manner of examples/terrain_generation_advanced.rs:178-182,343-371: the `add_edge_sites` rim
+    sites (indices >= n_inner) that are "ocean" seed a flood fill through neighbouring ocean sites.  Ocean = a noise field
+    below a threshold, plus (band) everything within `band` of the bounding box, so the whole rim is ocean."""
+    pts, n = model["sites"], model["n"]
+    sea = value_noise(pts, 4.0 / 75.0, seed=seed + 7) < -0.2
+    if band is not None:
+        lo, hi = pts.min(axis=0), pts.max(axis=0)
+        sea |= ((pts - lo) < band).any(axis=1) | ((hi - pts) < band).any(axis=1)
+    rp, col = model["row_ptr"].astype(np.int64), model["col"]
+    out = np.zeros(n, dtype=bool)
+    stack = [i for i in range(n_inner, n) if sea[i]]
+    while stack:
+        i = stack.pop()
+        if out[i]:
+            continue
+        out[i] = True
+        for j in col[rp[i]:rp[i + 1]]:
+            if not out[j] and sea[j]:
+                stack.append(int(j))
     return out
 
 
