@@ -339,7 +339,7 @@ def ensemble_leg(args, local_rank, m, p, outlets, initial):
            for t in range(members)]
     out = {"members": members, "sites": n, "what": "noise-driven erodibility per member (seed = member index), shared graph, "
                                                    "hull outlets; each member = set_parameters (host buffers) + run to convergence"}
-    for n_ctx in (1, 2):
+    for n_ctx in (1, 2, 3, 4):
         ctxs = []
         for _ in range(n_ctx):
             c = _native.Context(local_rank)
@@ -356,20 +356,15 @@ def ensemble_leg(args, local_rank, m, p, outlets, initial):
         def on_result(t, it, ctx):
             with lock:
                 work[0] += it
-
-        def drive(c):
-            ensemble.run_pool(c, pool, lambda t: prm[t], on_result)
         t0 = time.perf_counter()
-        ths = [threading.Thread(target=drive, args=(c,)) for c in ctxs]
-        for th in ths:
-            th.start()
-        for th in ths:
-            th.join()
+        ensemble.run_pool_concurrent(ctxs, pool, lambda t: prm[t], on_result)
         dt = time.perf_counter() - t0
         for c in ctxs:
             c.close()
         out[f"contexts_{n_ctx}"] = {"seconds": dt, "iterations": work[0], "value": n * work[0] / dt, "unit": UNIT}
     out["speedup_2_contexts"] = out["contexts_2"]["value"] / out["contexts_1"]["value"]
+    out["like_for_like"] = (f"contexts_{args.contexts_per_gpu} is the one-GPU figure of the workload the N > 1 lines run "
+                            f"({args.contexts_per_gpu} members in flight per GPU)")
     return out
 
 
@@ -605,21 +600,29 @@ def multi_gpu(args, rank, local_rank, world):
     results = torch.zeros((cap, n), dtype=torch.float64, device="cuda")
     counters = {"iters": 0, "launches": 0, "dev_ms": 0.0, "members": []}
 
-    def on_device(t, it, ctx):
-        k = len(counters["members"])
+    lock = threading.Lock()
+
+    def on_device(t, it, ctx):  # (called from the context's own thread)
+        with lock:
+            k = len(counters["members"])
+            counters["members"].append(t)
         if k < cap:
             ctx.download_to_device(results[k].data_ptr())
         st = ctx.stats()
-        counters["iters"] += it
-        counters["launches"] += st["kernel_launches"]
-        counters["dev_ms"] += st["ms_run"]
-        counters["members"].append(t)
+        with lock:
+            counters["iters"] += it
+            counters["launches"] += st["kernel_launches"]
+            counters["dev_ms"] += st["ms_run"]
 
-    ctx = _native.Context(local_rank)
-    ctx.set_graph(m["row_ptr"], m["col"], m["dist"], m["areas"])
+    # `contexts_per_gpu` members in flight per GPU: one context (own stream, own copy of the graph) and host thread each
+    ctxs = []
+    for _ in range(max(1, args.contexts_per_gpu)):
+        c = _native.Context(local_rank)
+        c.set_graph(m["row_ptr"], m["col"], m["dist"], m["areas"])
+        ctxs.append(c)
     # warm-up: W steps of the same shape (members from their own pool), untimed
     warm_pool = ensemble.MemberPool.for_process_group(args.warmup * per_step, "fastlem_warm")
-    ensemble.run_pool(ctx, warm_pool, make_params, lambda t, it, c: None, args.max_iter)
+    ensemble.run_pool_concurrent(ctxs, warm_pool, make_params, lambda t, it, c: None, args.max_iter)
     counters.update({"iters": 0, "launches": 0, "dev_ms": 0.0, "members": []})
 
     # timed region: K steps' worth of members in ONE pool (no barrier between steps), one gather at the end
@@ -628,7 +631,7 @@ def multi_gpu(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     t0 = time.perf_counter()
-    ensemble.run_pool(ctx, pool, make_params, on_device, args.max_iter)
+    ensemble.run_pool_concurrent(ctxs, pool, make_params, on_device, args.max_iter)
     torch.cuda.synchronize()
     t_own = time.perf_counter() - t0
     mine = len(counters["members"])
@@ -647,24 +650,33 @@ def multi_gpu(args, rank, local_rank, world):
     dist.all_reduce(w, op=dist.ReduceOp.SUM)
     dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
     value = float(w[0]) / float(t[0])
-    ctx.close()
+    for c in ctxs:
+        c.close()
 
     # e2e: the same ensemble through the C ABI with host buffers -- the graph uploaded inside the timed region (once per
     # rank), every member = set_parameters from pinned host arrays + generate with the elevations copied to the host
     pool2 = ensemble.MemberPool.for_process_group(total, "fastlem_e2e")
-    host_out = pinned(np.empty(n))
+    n_ctx = max(1, args.contexts_per_gpu)
+    host_out = {}
     hm = {k: pinned(m[k]) for k in ("row_ptr", "col", "dist", "areas")}
     e2e = {"iters": 0, "members": 0}
 
     def on_host(t_, it, c):
-        c.download(out=host_out)
-        e2e["iters"] += it
-        e2e["members"] += 1
+        c.download(out=host_out[id(c)])
+        with lock:
+            e2e["iters"] += it
+            e2e["members"] += 1
     barrier()
     t1 = time.perf_counter()
-    with _native.Context(local_rank) as c2:
+    c2s = []
+    for _ in range(n_ctx):
+        c2 = _native.Context(local_rank)
         c2.set_graph(hm["row_ptr"], hm["col"], hm["dist"], hm["areas"])
-        ensemble.run_pool(c2, pool2, make_params, on_host, args.max_iter)
+        host_out[id(c2)] = pinned(np.empty(n))
+        c2s.append(c2)
+    ensemble.run_pool_concurrent(c2s, pool2, make_params, on_host, args.max_iter)
+    for c2 in c2s:
+        c2.close()
     barrier()
     e2e_t = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device="cuda")
     e2e_w = torch.tensor([float(n) * e2e["iters"], float(e2e["members"])], dtype=torch.float64, device="cuda")
@@ -684,21 +696,24 @@ def multi_gpu(args, rank, local_rank, world):
                 "ms_per_step": 1e3 * float(t[0]) / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"C5 style: ensemble of {per_step} members per step ({args.members_per_rank} per GPU) x {n} sites "
-                                       f"on the C2 graph (shared, uploaded once per rank), noise-driven erodibility per member, hull "
+                                       f"on the C2 graph (shared by the members, uploaded once per context), noise-driven erodibility per member, hull "
                                        f"outlets; each member = generate() to convergence; members handed out first come first "
                                        f"served over the {world} ranks, one NCCL gather of the elevations at the end",
                            "sites": n, "members_per_step": per_step, "members_timed": members_total,
                            "iterations_per_member": float(w[0]) / n / max(members_total, 1),
                            "l2": "working set ~170 MB per iteration > 126 MB L2; hundreds of iterations per member, no flush",
-                           "max_iteration": args.max_iter, "parallelism": f"{world} GPUs, one process each, 1 member at a time per GPU"},
+                           "max_iteration": args.max_iter, "parallelism": f"{world} GPUs, one process each, {n_ctx} members in flight per GPU (one context and "
+                                          f"stream each)",
+                           "like_for_like_n1": f"`ensemble.contexts_{n_ctx}` of the N = 1 line is this workload on one GPU (the "
+                                               f"N = 1 `value` is ONE C2 terrain, which cannot use more than one stream)"},
                 "balance": {"slowest_rank_s": float(t[1]), "fastest_rank_s": float(tmin[0]),
                             "gather_and_barrier_s": float(t[0]) - float(t[1])},
                 "e2e": {"value": float(e2e_w[0]) / float(e2e_t[0]), "unit": UNIT,
-                        "h2d_bytes_per_step": int(graph_bytes * world / args.steps + per_step * (3 * 8 * n + outlets.nbytes)),
+                        "h2d_bytes_per_step": int(graph_bytes * world * n_ctx / args.steps + per_step * (3 * 8 * n + outlets.nbytes)),
                         "d2h_bytes_per_step": int(per_step * 8 * n), "seconds_per_step": float(e2e_t[0]) / args.steps,
                         "members": int(e2e_w[1]),
                         "host_buffers": "pinned host arrays handed to the C ABI as plain pointers; graph upload inside the timed "
-                                        "region (once per rank)"},
+                                        "region (once per context)"},
                 "gpu_launches": int(w[1]), "device_seconds_max_over_ranks": float(t[2]),
                 "roofline": None, "cpu_baseline": None, "clocks": clocks, "workload_build_s": t_build, "raster": raster}
         peak, peak_src = peaks()
@@ -730,6 +745,8 @@ def main():
     ap.add_argument("--c4-cpu-iters", type=int, default=5)
     ap.add_argument("--ensemble-members", type=int, default=8, help="members of the N = 1 ensemble leg (0 = skip)")
     ap.add_argument("--members-per-rank", type=int, default=4, help="N > 1: ensemble members per rank and step")
+    ap.add_argument("--contexts-per-gpu", type=int, default=2,
+                    help="N > 1: ensemble members in flight per GPU (one context + host thread each)")
     ap.add_argument("--sweep", type=int, default=None, help="solver option 'sweep' (DESIGN.md)")
     ap.add_argument("--max-iter", type=int, default=None,
                     help="profiling aid: stop every generate() after this many iterations (the metric is then NOT the "

@@ -41,7 +41,7 @@ class Stats(ctypes.Structure):
                 ("n_order", ctypes.c_uint64), ("n_area", ctypes.c_uint64), ("n_elevation", ctypes.c_uint64),
                 ("rebuilds", ctypes.c_uint32), ("path_levels", ctypes.c_uint32), ("paths", ctypes.c_uint32),
                 ("incremental_iterations", ctypes.c_uint32),
-                ("flood_on_device", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
+                ("flood_on_device", ctypes.c_uint32), ("outlet_ranks_on_device", ctypes.c_uint32),
                 ("ms_kernel", ctypes.c_double * 8), ("n_kernel", ctypes.c_uint64 * 8)]
 
     KERNELS = ("k_receivers_mask", "k_area_flow", "k_incr_start", "k_area_flow_long", "k_elev_plan", "k_elev_top",
@@ -141,7 +141,7 @@ def _p(a, t):
 
 
 class Context:
-    """One fastlem_ctx.  Keeps the numpy arrays it handed to the library alive (the C ABI borrows the graph)."""
+    """One fastlem_ctx (the C ABI copies everything it is handed; no array has to outlive the call)."""
 
     def __init__(self, device=0, lib_path=None):
         self._lib = load(lib_path)

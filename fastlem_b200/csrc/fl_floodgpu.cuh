@@ -18,9 +18,11 @@
 //   tree, pointer walks for nga, a counting sweep for |B|, two radix sorts + scans for the sibling prefix, and
 //   pointer jumping for the final sums.
 //
-// The outlets' own ranks depend on the heap's behaviour at equal keys (all 0.0); the host replays just that prefix
-// (fl_flood_rank_prefix).  Graphs with equal or non-positive edge lengths fall back to the full host replay
-// (fl_flood.cpp), which reproduces Rust's BinaryHeap at ties.
+// The outlets' own ranks depend on the heap's behaviour at equal keys (all 0.0) and have a closed form (k_flg_outlet_*,
+// below): the first outlet, then the node-right-left pre-order of the array-embedded heap left by the first pop.  Its
+// validity condition is checked on the device; when it fails the host replays just that prefix (fl_flood_rank_prefix).
+// Graphs with equal or non-positive edge lengths fall back to the full host replay (fl_flood.cpp), which reproduces
+// Rust's BinaryHeap at ties.
 #pragma once
 #include "fl_kernels.cuh"
 
@@ -47,7 +49,8 @@ struct FlFloodG {
     uint32_t* nga;                // n+1
     uint32_t* cnt;                // n+1: nga children still to report
     uint32_t* size;               // n+1: |B|
-    uint32_t* flags;              // [0] any component hooked, [1] next frontier size, [2] work left, [3] bad edge length
+    uint32_t* flags;              // [0] any component hooked, [1] next frontier size, [2] work left, [3] bad edge length,
+                                  // [4..6] counters of the rooting walk, [7] closed form of the outlets' ranks not valid
 };
 
 __device__ __forceinline__ unsigned long long flg_bits(double d) { return (unsigned long long)__double_as_longlong(d); }
@@ -67,7 +70,8 @@ __global__ void __launch_bounds__(256) k_flg_edge_keys(FlFloodG g, unsigned long
         const double d = g.dist[s];
         const uint32_t j = g.col[s];
         const bool inner = out_i && g.is_outlet[j] != 0;
-        if (!inner && (!(d > 0.0) || !(d < 1.7976931348623157e308))) g.flags[3] = 1u;
+        const bool bad = !(d > 0.0) || !(d < 1.7976931348623157e308);
+        if (bad) g.flags[inner ? 7 : 3] = 1u;  // [7]: only the closed form of the outlets' ranks needs these positive
         keys[s] = (j > i && !inner) ? flg_bits(d) : FLG_KEY_NONE;
     }
 }
@@ -77,6 +81,94 @@ __global__ void __launch_bounds__(256) k_flg_dup_check(uint32_t m, const unsigne
     if (i + 1u >= m) return;
     const unsigned long long a = sorted[i];
     if (a != FLG_KEY_NONE && a == sorted[i + 1u]) flags[3] = 1u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The outlets' own ranks (stream_tree.rs:184-197 push every outlet with key 0.0; Rust's BinaryHeap decides their order).
+// Equal keys never move in sift_up (`<=`), so after the pushes the heap array is the outlet list itself.  The first pop
+// returns outlets[0]; sift_down_to_bottom follows the RIGHT child at equal keys, so the hole runs down the right spine
+// 0, 2, 6, 14, ... and the last outlet lands at its end.  From then on every pop takes the root and promotes, level by
+// level, the right child if both children have key 0.0, else the one that has (a positive key never beats 0.0) -- the
+// 0.0 entries leave in node-right-left pre-order of that array, PROVIDED the element moved from the tail by each of
+// these pops has a positive key (then it never rises above a 0.0 entry).  Sufficient: before the pop number k >= 1 at
+// least k entries have been pushed (the array is then longer than the K - 1 slots the 0.0 entries live in).  Pushes of
+// a pop = its neighbours not yet visited = non-outlets and outlets of a later (or its own) rank.
+struct FlOutletPrefix {
+    uint32_t count;       // K = number of outlets
+    uint32_t right_steps; // moves of the first pop's hole along the right spine
+    uint32_t final_left;  // 1: one more move into a last, single (left) child
+    uint32_t spine_end;   // position reached by the right moves
+    uint32_t last_pos;    // where the last outlet lands
+};
+inline FlOutletPrefix flg_outlet_prefix(uint32_t count) {
+    FlOutletPrefix p;
+    p.count = count; p.right_steps = 0u; p.final_left = 0u; p.spine_end = 0u; p.last_pos = 0u;
+    if (count < 2u) return p;
+    const unsigned long long len = (unsigned long long)count - 1ull, bound = len >= 2ull ? len - 2ull : 0ull;
+    unsigned long long at = 0ull, kid = 1ull;
+    while (kid <= bound) { at = kid + 1ull; kid = 2ull * at + 1ull; ++p.right_steps; }
+    p.spine_end = (uint32_t)at;
+    if (kid == len - 1ull) { p.final_left = 1u; at = kid; }
+    p.last_pos = (uint32_t)at;
+    return p;
+}
+// nodes of the subtree of r in the array-embedded complete binary tree of m nodes
+__device__ __forceinline__ uint32_t flg_heap_subtree(uint32_t r, uint32_t m) {
+    unsigned long long lo = r, hi = r, s = 0ull;
+    while (lo < m) {
+        s += (hi < m ? hi : (unsigned long long)m - 1ull) - lo + 1ull;
+        lo = 2ull * lo + 1ull;
+        hi = 2ull * hi + 2ull;
+    }
+    return (uint32_t)s;
+}
+// index of position p in the node-right-left pre-order of that tree
+__device__ __forceinline__ uint32_t flg_nrl_index(uint32_t p, uint32_t m) {
+    uint32_t before = 0u;
+    while (p > 0u) {
+        before += 1u;                                                           // the parent itself
+        if ((p & 1u) && p + 1u < m) before += flg_heap_subtree(p + 1u, m);      // a left child: the right sibling's subtree
+        p = (p - 1u) >> 1;
+    }
+    return before;
+}
+// rank of every outlet (outlet_rank: n words, preset to FL_NONE)
+__global__ void __launch_bounds__(256) k_flg_outlet_rank(FlOutletPrefix f, const uint32_t* __restrict__ outlets,
+                                                          uint32_t* outlet_rank) {
+    const uint32_t a = FL_TID;
+    if (a >= f.count) return;
+    uint32_t r = 0u;
+    if (a > 0u) {
+        uint32_t pos = a;  // position in the array after the first pop
+        if (a == f.count - 1u) pos = f.last_pos;
+        else {
+            const uint32_t d = 31u - (uint32_t)__clz((int)(a + 2u));  // a + 2 == 2^d: a lies on the right spine
+            if (a + 2u == (1u << d) && d >= 2u && d <= f.right_steps + 1u) pos = (1u << (d - 1u)) - 2u;
+            else if (f.final_left && a == 2u * f.spine_end + 1u) pos = f.spine_end;
+        }
+        r = 1u + flg_nrl_index(pos, f.count - 1u);
+    }
+    outlet_rank[outlets[a]] = r;
+}
+// pushes made while outlet number `rank` is popped
+__global__ void __launch_bounds__(256) k_flg_outlet_pushes(FlFloodG g, uint32_t count, const uint32_t* __restrict__ outlets,
+                                                            const uint32_t* __restrict__ outlet_rank, uint32_t* pushes) {
+    const uint32_t a = FL_TID;
+    if (a >= count) return;
+    const uint32_t o = outlets[a], r = outlet_rank[o];
+    uint32_t c = 0u;
+    for (uint32_t s = g.row_ptr[o]; s < g.row_ptr[o + 1u]; ++s) {
+        const uint32_t rj = outlet_rank[g.col[s]];
+        if (rj == FL_NONE || rj >= r) ++c;
+    }
+    pushes[r] = c;
+}
+// before[k] = pushes of the pops 0 .. k-1
+__global__ void __launch_bounds__(256) k_flg_outlet_check(uint32_t count, const uint32_t* __restrict__ before,
+                                                           uint32_t* flags) {
+    const uint32_t k = FL_TID;
+    if (k == 0u || k >= count) return;
+    if (before[k] < k) flags[7] = 1u;
 }
 
 __global__ void __launch_bounds__(256) k_flg_init(FlFloodG g) {

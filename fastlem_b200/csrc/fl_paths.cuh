@@ -81,7 +81,8 @@ __global__ void FL_K1_BOUNDS k_receivers_mask(uint32_t n, const uint32_t* __rest
                                                          const uint8_t* __restrict__ rev,
                                                          const double* __restrict__ elev,
                                                          const uint8_t* __restrict__ is_outlet,
-                                                         uint32_t* __restrict__ recv, double* __restrict__ drecv,
+                                                         const uint32_t* recv_prev, uint32_t* recv,
+                                                         double* __restrict__ drecv,
                                                          uint32_t* cmask, uint32_t* __restrict__ flags,
                                                          uint32_t* __restrict__ chg_node,
                                                          uint32_t* __restrict__ chg_old) {
@@ -123,7 +124,7 @@ __global__ void FL_K1_BOUNDS k_receivers_mask(uint32_t n, const uint32_t* __rest
         if (best == i) atomicOr(&flags[FL_FLAG_LAKE], 1u);
     }
     if (chg_node) {  // incremental K4: sites whose receiver differs from the previous iteration's (final) one
-        const uint32_t old = recv[i];
+        const uint32_t old = recv_prev[i];  // (recv_prev may be recv itself)
         if (old != best) {
             const uint32_t k = atomicAdd(&flags[FL_FLAG_NCHG], 1u);
             chg_node[k] = i;
@@ -137,6 +138,180 @@ __global__ void FL_K1_BOUNDS k_receivers_mask(uint32_t n, const uint32_t* __rest
         if (r < 32u) atomicOr(&cmask[best], 1u << r);
     }
 }
+
+#ifndef FL_EMU
+// ------------------------------------------------------------------------------------------------
+// K1 with the CSR stream staged through shared memory by the bulk-copy engine (cp.async.bulk + mbarrier; SASS: UBLKCP).
+//
+// The thread-per-row kernel above is bound by dependent round trips, not by bytes: row_ptr -> col / dist of a batch ->
+// the elevation gathers -> the next batch (5-6 latencies in a row per thread, 1280 threads per SM).  Here a persistent
+// CTA walks tiles of FL_K1B_ROWS consecutive rows; the tile's contiguous col / dist span (rows are contiguous in CSR) is
+// copied global -> shared by ONE bulk copy each, issued one tile ahead into the other stage, so when a tile starts its
+// neighbour ids are a shared-memory read away and a thread issues ALL its elevation gathers at once: one exposed
+// round trip per row.  Same comparisons, same order (stream_tree.rs:109-137): results are bit-identical.
+// A span longer than a stage (FL_K1B_CAP slots; mean degree 6 -> 1536) is read from global memory directly.
+// ------------------------------------------------------------------------------------------------
+#define FL_K1B_ROWS 256u
+#define FL_K1B_CAP 2048u
+#define FL_K1B_GATHER 8
+#define FL_K1B_STAGE_BYTES (FL_K1B_CAP * 12u)
+#define FL_K1B_SMEM (2u * FL_K1B_STAGE_BYTES + 64u)
+
+__device__ __forceinline__ uint32_t fl_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fl_mbar_init(void* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fl_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fl_mbar_expect_tx(void* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fl_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fl_mbar_arrive(void* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fl_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fl_mbar_wait(void* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(fl_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fl_bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fl_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(fl_smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(256) k_receivers_bulk(uint32_t n, uint32_t n_tiles, const uint32_t* __restrict__ row_ptr,
+                                                         const uint32_t* __restrict__ col,
+                                                         const double* __restrict__ dist,
+                                                         const uint8_t* __restrict__ rev,
+                                                         const double* __restrict__ elev,
+                                                         const uint8_t* __restrict__ is_outlet,
+                                                         const uint32_t* recv_prev, uint32_t* recv,
+                                                         double* __restrict__ drecv,
+                                                         uint32_t* cmask, uint32_t* __restrict__ flags,
+                                                         uint32_t* __restrict__ chg_node,
+                                                         uint32_t* __restrict__ chg_old) {
+    extern __shared__ __align__(128) unsigned char k1b_smem[];
+    // stage s: dist at s * STAGE_BYTES (CAP doubles), col right behind it (CAP words); then 2 barriers, 2 x (start, ok)
+    unsigned long long* bars = (unsigned long long*)(k1b_smem + 2u * FL_K1B_STAGE_BYTES);
+    uint32_t* meta = (uint32_t*)(k1b_smem + 2u * FL_K1B_STAGE_BYTES + 16u);
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0u) {
+        fl_mbar_init(&bars[0], 1u);
+        fl_mbar_init(&bars[1], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // thread 0: the span of the tile to be copied next (loaded one iteration before it is needed)
+    uint32_t nb = 0u, ne = 0u;
+    auto bounds = [&](uint32_t tile) {
+        const unsigned long long t0 = (unsigned long long)tile * FL_K1B_ROWS;
+        const unsigned long long t1 = t0 + FL_K1B_ROWS < n ? t0 + FL_K1B_ROWS : n;
+        nb = row_ptr[t0];
+        ne = row_ptr[t1];
+    };
+    auto issue = [&](uint32_t stage) {  // spans [nb, ne) -> stage; start aligned down to 16 slots (16 B for every array)
+        const uint32_t start = nb & ~15u;
+        const uint32_t cnt = (ne - start + 15u) & ~15u;
+        const bool ok = cnt > 0u && cnt <= FL_K1B_CAP;
+        meta[2u * stage] = start;
+        meta[2u * stage + 1u] = ok ? 1u : 0u;
+        unsigned char* base = k1b_smem + stage * FL_K1B_STAGE_BYTES;
+        if (ok) {
+            fl_mbar_expect_tx(&bars[stage], cnt * 12u);
+            fl_bulk_g2s(base, dist + start, cnt * 8u, &bars[stage]);
+            fl_bulk_g2s(base + FL_K1B_CAP * 8u, col + start, cnt * 4u, &bars[stage]);
+        } else {
+            fl_mbar_arrive(&bars[stage]);
+        }
+    };
+    uint32_t tile = blockIdx.x;
+    if (tid == 0u && tile < n_tiles) {
+        bounds(tile);
+        issue(0u);
+        if (tile + gridDim.x < n_tiles) bounds(tile + gridDim.x);
+    }
+    uint32_t parity0 = 0u, parity1 = 0u, stage = 0u;
+    bool lake = false;
+    for (; tile < n_tiles; tile += gridDim.x, stage ^= 1u) {
+        if (tid == 0u && tile + gridDim.x < n_tiles) {  // (the other stage was released by the barrier that ended the previous tile)
+            issue(stage ^ 1u);
+            const unsigned long long after = (unsigned long long)tile + 2ull * gridDim.x;
+            if (after < n_tiles) bounds((uint32_t)after);
+        }
+        const unsigned long long i64 = (unsigned long long)tile * FL_K1B_ROWS + tid;
+        const bool active = i64 < n;
+        const uint32_t i = (uint32_t)i64;
+        uint32_t s0 = 0u, s1 = 0u, old = 0u;
+        bool outlet = true;
+        double ei = 0.0;
+        if (active) {
+            s0 = row_ptr[i];
+            s1 = row_ptr[i + 1u];
+            outlet = is_outlet[i] != 0;
+            ei = elev[i];
+            if (chg_node) old = recv_prev[i];
+        }
+        fl_mbar_wait(&bars[stage], stage ? parity1 : parity0);
+        if (stage) parity1 ^= 1u; else parity0 ^= 1u;
+        const uint32_t start = meta[2u * stage];
+        const bool staged = meta[2u * stage + 1u] != 0u;
+        uint32_t best = i, best_s = FL_NONE;
+        double best_d = 1.0;
+        if (active && !outlet) {
+            const double* sd = (const double*)(k1b_smem + stage * FL_K1B_STAGE_BYTES) + (s0 - start);
+            const uint32_t* sc = (const uint32_t*)(k1b_smem + stage * FL_K1B_STAGE_BYTES + FL_K1B_CAP * 8u) + (s0 - start);
+            const uint32_t deg = s1 - s0;
+            double steepest = 0.0;
+            for (uint32_t sb = 0u; sb < deg; sb += (uint32_t)FL_K1B_GATHER) {
+                uint32_t j[FL_K1B_GATHER];
+                double ej[FL_K1B_GATHER];
+#pragma unroll
+                for (int k = 0; k < FL_K1B_GATHER; ++k) {
+                    const uint32_t o = sb + (uint32_t)k;
+                    j[k] = o < deg ? (staged ? sc[o] : col[s0 + o]) : i;  // padding: the site itself (never lower than itself)
+                }
+#pragma unroll
+                for (int k = 0; k < FL_K1B_GATHER; ++k) ej[k] = elev[j[k]];
+#pragma unroll
+                for (int k = 0; k < FL_K1B_GATHER; ++k) {
+                    if (ei > ej[k]) {
+                        const uint32_t o = sb + (uint32_t)k;
+                        const double d = staged ? sd[o] : dist[s0 + o];
+                        const double slope = (ei - ej[k]) / d;
+                        if (slope > steepest) {
+                            steepest = slope;
+                            best = j[k];
+                            best_d = d;
+                            best_s = s0 + o;
+                        }
+                    }
+                }
+            }
+            if (best == i) lake = true;
+        }
+        if (active) {
+            if (chg_node && old != best) {  // incremental K4: sites whose receiver differs from the previous iteration's
+                const uint32_t k = atomicAdd(&flags[FL_FLAG_NCHG], 1u);
+                chg_node[k] = i;
+                chg_old[k] = old;
+            }
+            recv[i] = best;
+            drecv[i] = best_d;
+            if (best_s != FL_NONE) {
+                const uint32_t r = rev[best_s];
+                if (r < 32u) atomicOr(&cmask[best], 1u << r);
+            }
+        }
+        __syncthreads();  // every read of this stage is done: it may be refilled
+    }
+    if (lake) atomicOr(&flags[FL_FLAG_LAKE], 1u);
+}
+#endif
 
 // child masks from scratch (after lake removal rewrote receivers)
 __global__ void __launch_bounds__(256) k_childmask(uint32_t n, const uint32_t* __restrict__ row_ptr,

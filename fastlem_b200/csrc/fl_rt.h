@@ -73,6 +73,7 @@ template <class F> inline void fl_emu_launch(unsigned grid, unsigned block, F&& 
 }
 #define FL_LAUNCH(kernel, grid, block, stream, ...) \
     do { (void)(stream); fl_emu_launch((grid), (block), [&] { kernel(__VA_ARGS__); }); } while (0)
+#define FL_RANGE(name) ((void)0)
 
 inline cudaError_t fl_set_device(int) { return 0; }
 inline cudaError_t fl_stream_create(cudaStream_t* s) { *s = 0; return 0; }
@@ -156,11 +157,21 @@ inline cudaError_t fl_exclusive_sum64(void*, size_t& temp_bytes, const unsigned 
 #else
 // ------------------------------------------------------------------------------------------------
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler (Nsight Systems / Compute) is attached
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #define FL_DEVICE_BUILD 1
 
 #define FL_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+
+// NVTX range over a scope: the API calls and the stages of an iteration show up named on a profiler's timeline
+struct FlRange {
+    explicit FlRange(const char* name) { nvtxRangePushA(name); }
+    ~FlRange() { nvtxRangePop(); }
+    FlRange(const FlRange&) = delete;
+    FlRange& operator=(const FlRange&) = delete;
+};
+#define FL_RANGE(name) FlRange fl_range_##__LINE__(name)
 
 inline cudaError_t fl_set_device(int d) { return cudaSetDevice(d); }
 inline cudaError_t fl_stream_create(cudaStream_t* s) { return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); }

@@ -79,9 +79,6 @@ struct fastlem_ctx {
     uint32_t n = 0, nnz = 0;
     bool has_graph = false, has_params = false, has_tan = false;
     // borrowed host pointers (flood order is computed from them on first use)
-    const uint32_t* h_row_ptr = nullptr;
-    const uint32_t* h_col = nullptr;
-    const double* h_dist = nullptr;
     std::vector<uint32_t> outlets;
 
     Layout orig;    // the caller's numbering: static inputs only (+ rank)
@@ -142,6 +139,16 @@ struct fastlem_ctx {
     uint32_t* d_pmask = nullptr;   // zero between sweeps (k_elev_top clears what k_elev_plan sets)
     uint32_t push_epoch = 0;
     int top_blocks = 0;            // the most blocks of k_elev_top that can be resident
+    // The next iteration's K1 is launched before the host has read this iteration's flags (iterate_flow): it writes into
+    // alternate receiver buffers that the next iteration swaps in, so a run that turns out to have ended keeps its state.
+    uint32_t* d_recv_alt = nullptr;
+    uint32_t* d_cmask_alt = nullptr;
+    double* d_drecv_alt = nullptr;
+    bool k1_pre = false;           // the alternate buffers hold the next iteration's K1 output
+    bool k1_pre_track = false;     // ... and it listed the re-routed sites
+    int64_t opt_overlap = 1;       // 0: the host waits for the flags before it launches anything else
+    int k1_bulk_blocks = 0;        // resident blocks of k_receivers_bulk (0 = not available)
+    int64_t opt_k1_bulk = 1;       // K1 with the CSR stream staged by the bulk-copy engine (fl_paths.cuh)
     int64_t opt_k5_split = 1;      // 0: the round-1 sweep (heads sorted by height, one launch per height)
     int64_t opt_k5_cut = -1;       // cut height: -1 = chosen from the previous iteration's level histogram
     int64_t opt_k5_top_cap = 12288;  // auto cut: at most this many segments go through the queue
@@ -163,6 +170,7 @@ struct fastlem_ctx {
     bool k4_valid = false;      // the arrays above and A/pre/post/state/hgt describe the forest of L.recv
     bool k4_last_full = true;   // the previous K4 was a full pass (its counters are not zeroed)
     int64_t opt_flood_device = 1;  // flood order on the device (fl_floodgpu.cuh) when the edge lengths allow it
+    int64_t opt_outlet_closed_form = 1;  // the outlets' own ranks by their closed form on the device (0: host replay of the prefix)
     int64_t opt_incremental = 1;
     int64_t opt_incr_div = 16;  // incremental pass when re-routed sites * incr_div <= n
     unsigned long long* d_flow_stats = nullptr;
@@ -197,7 +205,7 @@ struct fastlem_ctx {
     int64_t opt_sweep = 3;
 
     fastlem_stats stats{};
-    cudaEvent_t ev[ST_COUNT + 3] = {};
+    cudaEvent_t ev[ST_COUNT + 6] = {};  // [9], [10]: K1 of the NEXT iteration; [11]: flags copied
     cudaEvent_t ev_run[2] = {};
     cudaEvent_t ev_k[2] = {};  // "profile"=2: brackets one kernel
 };
@@ -296,6 +304,17 @@ int k_end(fastlem_ctx* c, int id) {
     return FASTLEM_OK;
 }
 
+// the flag words on their way to the host; the caller may launch more work before it waits for them
+int read_flags_begin(fastlem_ctx* c) {
+    FL_CK(fl_d2h(c->h_flags, c->d_flags, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
+    FL_CK(fl_event_record(c->ev[ST_COUNT + 5], c->stream));
+    return FASTLEM_OK;
+}
+int read_flags_end(fastlem_ctx* c) {
+    FL_CK(fl_event_sync(c->ev[ST_COUNT + 5]));
+    return FASTLEM_OK;
+}
+
 int read_flags(fastlem_ctx* c) {
     FL_CK(fl_d2h(c->h_flags, c->d_flags, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
     FL_CK(fl_stream_sync(c->stream));
@@ -362,10 +381,27 @@ struct FlTmpAlloc {
     }
 };
 
+// the graph back on the host, for the exact heap replay (fl_flood.cpp) that inputs with tied edge lengths need
+struct HostCsr {
+    std::vector<uint32_t> row_ptr, col;
+    std::vector<double> dist;
+};
+int download_csr(fastlem_ctx* c, HostCsr& h) {
+    h.row_ptr.resize((size_t)c->n + 1); h.col.resize(c->nnz); h.dist.resize(c->nnz);
+    FL_CK(fl_d2h(h.row_ptr.data(), c->orig.row_ptr, sizeof(uint32_t) * ((size_t)c->n + 1), c->stream));
+    if (c->nnz) {
+        FL_CK(fl_d2h(h.col.data(), c->orig.col, sizeof(uint32_t) * c->nnz, c->stream));
+        FL_CK(fl_d2h(h.dist.data(), c->orig.dist, sizeof(double) * c->nnz, c->stream));
+    }
+    FL_CK(fl_stream_sync(c->stream));
+    return FASTLEM_OK;
+}
+
 // flood order on the device (fl_floodgpu.cuh).  *done = false: the graph has equal / non-positive edge lengths (or
 // rows too long for the reverse-slot table) and the exact host replay must be used instead.
 int device_flood_rank(fastlem_ctx* c, bool* done) {
     *done = false;
+    FL_RANGE("fastlem flood order (device)");
     const uint32_t n = c->n, nnz = c->nnz;
     if (c->max_degree >= 255u || c->outlets.empty() || nnz == 0u) return FASTLEM_OK;
     FlTrace tr("flood");
@@ -408,20 +444,39 @@ int device_flood_rank(fastlem_ctx* c, bool* done) {
     if (hf[3]) return FASTLEM_OK;  // ties: the host replay reproduces the heap's behaviour
 
     tr.mark("distinct check");
-    // 2. the outlets' own ranks (equal keys 0.0: heap behaviour) -- exact replay of that prefix on the host
-    std::vector<uint32_t> orank(n);
-    uint32_t n_out = 0;  // distinct outlets = |S|
+    // 2. the outlets' own ranks (equal keys 0.0: heap behaviour): closed form + validity check on the device
+    //    (fl_floodgpu.cuh, k_flg_outlet_*); the exact host replay of that prefix only when the check fails
+    const uint32_t n_out = (uint32_t)c->outlets.size();  // distinct (fastlem_set_parameters rejects duplicates) = |S|
     {
-        std::vector<uint8_t> seen(n, 0);
-        for (uint32_t o : c->outlets)
-            if (!seen[o]) { seen[o] = 1; ++n_out; }
-        fl_flood_rank_prefix(n, c->h_row_ptr, c->h_col, c->h_dist, c->outlets.data(), (uint32_t)c->outlets.size(),
-                             orank.data(), n_out);
-        FL_CK(tmp.get(outlet_rank, n));
-        FL_CK(fl_h2d(outlet_rank, orank.data(), sizeof(uint32_t) * n, c->stream));
+        uint32_t *d_outlets = nullptr, *pushes = nullptr, *before = nullptr;
+        FL_CK(tmp.get(outlet_rank, n)); FL_CK(tmp.get(d_outlets, n_out)); FL_CK(tmp.get(pushes, n_out));
+        FL_CK(tmp.get(before, n_out));
+        FL_CK(fl_h2d(d_outlets, c->outlets.data(), sizeof(uint32_t) * n_out, c->stream));
+        FL_CK(fl_memset(outlet_rank, 0xFF, sizeof(uint32_t) * n, c->stream));
+        bool closed = c->opt_outlet_closed_form != 0 && !hf[7];
+        if (closed) {
+            const FlOutletPrefix f = flg_outlet_prefix(n_out);
+            LAUNCH_N(k_flg_outlet_rank, n_out, f, d_outlets, outlet_rank);
+            LAUNCH_N(k_flg_outlet_pushes, n_out, g, n_out, d_outlets, outlet_rank, pushes);
+            FL_CK(fl_exclusive_sum(cub_tmp, need, pushes, before, n_out, c->stream, false));
+            LAUNCH_N(k_flg_outlet_check, n_out, n_out, before, g.flags);
+            FL_CK(fl_d2h(hf, g.flags, sizeof(hf), c->stream));
+            FL_CK(fl_stream_sync(c->stream));
+            closed = !hf[7];
+        }
+        c->stats.outlet_ranks_on_device = closed ? 1u : 0u;
+        if (!closed) {
+            HostCsr h;
+            FL_RC(download_csr(c, h));
+            std::vector<uint32_t> orank(n);
+            fl_flood_rank_prefix(n, h.row_ptr.data(), h.col.data(), h.dist.data(), c->outlets.data(), n_out, orank.data(),
+                                 n_out);
+            FL_CK(fl_h2d(outlet_rank, orank.data(), sizeof(uint32_t) * n, c->stream));
+            FL_CK(fl_stream_sync(c->stream));
+        }
     }
 
-    tr.mark("outlet prefix (host)");
+    tr.mark("outlet prefix");
     // 3. Boruvka: minimum spanning forest of the graph with the outlets contracted
     LAUNCH_N(k_flg_init, n + 1, g);
     FL_CK(fl_memset(g.mst, 0, nnz, c->stream));
@@ -518,9 +573,13 @@ int ensure_rank(fastlem_ctx* c) {
     if (c->opt_flood_device) FL_RC(device_flood_rank(c, &done));
     c->stats.flood_on_device = done ? 1u : 0u;
     if (!done) {
+        c->stats.outlet_ranks_on_device = 0u;
         c->stats.kernel_launches = launches_before;
+        HostCsr h;  // (the graph lives in HBM; the caller's arrays are not kept)
+        FL_RC(download_csr(c, h));
         std::vector<uint32_t> rank(n);
-        fl_flood_rank(n, c->h_row_ptr, c->h_col, c->h_dist, c->outlets.data(), (uint32_t)c->outlets.size(), rank.data());
+        fl_flood_rank(n, h.row_ptr.data(), h.col.data(), h.dist.data(), c->outlets.data(), (uint32_t)c->outlets.size(),
+                      rank.data());
         FL_CK(fl_h2d(c->orig.rank, rank.data(), sizeof(uint32_t) * n, c->stream));
         FL_CK(fl_stream_sync(c->stream));
     }
@@ -537,6 +596,7 @@ int ensure_rank(fastlem_ctx* c) {
 
 // K3: connect every lake basin and reverse its in-basin path (labels must be in d_pd)
 int run_lakes(fastlem_ctx* c) {
+    FL_RANGE("fastlem K3 lake removal");
     const uint32_t n = c->n;
     Layout& L = L_(c);
     FL_RC(ensure_rank(c));
@@ -703,8 +763,8 @@ int iterate_paths(fastlem_ctx* c, bool* changed_out) {
     FL_RC(stage_mark(c, 0));
     {
         Layout& L = L_(c);
-        LAUNCH_N(k_receivers_mask, n, n, L.row_ptr, L.col, L.dist, L.rev, L.elev, L.is_outlet, L.recv, L.drecv, L.cmask,
-                 c->d_flags, (uint32_t*)nullptr, (uint32_t*)nullptr);
+        LAUNCH_N(k_receivers_mask, n, n, L.row_ptr, L.col, L.dist, L.rev, L.elev, L.is_outlet, L.recv, L.recv, L.drecv,
+                 L.cmask, c->d_flags, (uint32_t*)nullptr, (uint32_t*)nullptr);
         c->stats.n_receivers++;
     }
     FL_RC(stage_mark(c, 1));
@@ -773,6 +833,7 @@ int iterate_paths(fastlem_ctx* c, bool* changed_out) {
 // has degraded; segments are whatever chains are contiguous in the current numbering.
 // ------------------------------------------------------------------------------------------------
 int rebuild_layout_flow(fastlem_ctx* c, const double* weight) {
+    FL_RANGE("fastlem renumber sites");
     const uint32_t n = c->n;
     Layout& L = c->lay[c->cur];
     Layout& M = c->lay[c->cur ^ 1];
@@ -805,23 +866,69 @@ int rebuild_layout_flow(fastlem_ctx* c, const double* weight) {
     return FASTLEM_OK;
 }
 
-int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
+// K1 of the current layout: receivers from L.elev into (recv, drecv, cmask); `track`: lists the sites whose receiver
+// differs from recv_prev (the previous iteration's final receivers)
+int launch_receivers(fastlem_ctx* c, bool track, const uint32_t* recv_prev, uint32_t* recv, double* drecv, uint32_t* cmask) {
     const uint32_t n = c->n;
-    FL_CK(fl_memset(c->d_flags, 0, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
-    FL_CK(fl_memset(L_(c).cmask, 0, sizeof(uint32_t) * n, c->stream));
-    FL_RC(stage_mark(c, 0));
-    // K1 lists the re-routed sites when the K4 state of the previous iteration can be reused
-    const bool track = c->opt_incremental != 0 && c->k4_valid && !c->need_rebuild && c->opt_rebuild_every != 1;
-    {
-        Layout& L = L_(c);
-        FL_RC(k_begin(c));
-        LAUNCH_N(k_receivers_mask, n, n, L.row_ptr, L.col, L.dist, L.rev, L.elev, L.is_outlet, L.recv, L.drecv, L.cmask,
-                 c->d_flags, track ? c->d_chg_node : (uint32_t*)nullptr, track ? c->d_chg_old : (uint32_t*)nullptr);
-        FL_RC(k_end(c, FASTLEM_K_RECEIVERS));
-        c->stats.n_receivers++;
+    Layout& L = L_(c);
+    FL_RC(k_begin(c));
+    bool bulk = false;
+#ifndef FL_EMU
+    if (c->opt_k1_bulk && c->k1_bulk_blocks > 0 && n > 0u) {
+        // persistent CTAs over tiles of FL_K1B_ROWS rows, the CSR span of a tile bulk-copied one tile ahead
+        const uint32_t tiles = (uint32_t)(((unsigned long long)n + FL_K1B_ROWS - 1u) / FL_K1B_ROWS);
+        const uint32_t blocks = tiles < (uint32_t)c->k1_bulk_blocks ? tiles : (uint32_t)c->k1_bulk_blocks;
+        k_receivers_bulk<<<blocks, 256, FL_K1B_SMEM, c->stream>>>(
+            n, tiles, L.row_ptr, L.col, L.dist, L.rev, L.elev, L.is_outlet, recv_prev, recv, drecv, cmask, c->d_flags,
+            track ? c->d_chg_node : (uint32_t*)nullptr, track ? c->d_chg_old : (uint32_t*)nullptr);
+        c->stats.kernel_launches++;
+        bulk = true;
     }
-    FL_RC(stage_mark(c, 1));
-    FL_RC(read_flags(c));
+#endif
+    if (!bulk)
+        LAUNCH_N(k_receivers_mask, n, n, L.row_ptr, L.col, L.dist, L.rev, L.elev, L.is_outlet, recv_prev, recv, drecv, cmask,
+                 c->d_flags, track ? c->d_chg_node : (uint32_t*)nullptr, track ? c->d_chg_old : (uint32_t*)nullptr);
+    FL_RC(k_end(c, FASTLEM_K_RECEIVERS));
+    c->stats.n_receivers++;
+    return FASTLEM_OK;
+}
+
+// `may_continue`: another iteration may follow this one (the iteration cap has not been reached)
+int iterate_flow(fastlem_ctx* c, uint32_t it, bool may_continue, bool* changed_out) {
+    FL_RANGE("fastlem iteration");
+    const uint32_t n = c->n;
+    bool track;
+    if (c->k1_pre) {
+        // K1 ran at the end of the previous iteration (below), into the alternate buffers: swap them in
+        Layout& L = L_(c);
+        std::swap(L.recv, c->d_recv_alt);
+        std::swap(L.drecv, c->d_drecv_alt);
+        std::swap(L.cmask, c->d_cmask_alt);
+        std::swap(c->ev[0], c->ev[ST_COUNT + 3]);
+        std::swap(c->ev[1], c->ev[ST_COUNT + 4]);
+        c->k1_pre = false;
+        track = c->k1_pre_track && !c->need_rebuild;
+    } else {
+        FL_CK(fl_memset(c->d_flags, 0, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
+        FL_CK(fl_memset(L_(c).cmask, 0, sizeof(uint32_t) * n, c->stream));
+        FL_RC(stage_mark(c, 0));
+        // K1 lists the re-routed sites when the K4 state of the previous iteration can be reused
+        track = c->opt_incremental != 0 && c->k4_valid && !c->need_rebuild && c->opt_rebuild_every != 1;
+        Layout& L = L_(c);
+        FL_RC(launch_receivers(c, track, L.recv, L.recv, L.drecv, L.cmask));
+        FL_RC(stage_mark(c, 1));
+    }
+    // While the flags travel to the host: the segment keys of the forest K1 left (k_seg_keys + scan, needed by either
+    // form of K4; redone below if lake removal or a renumbering changes the forest / the numbering first)
+    const bool overlap = c->opt_overlap != 0 && c->opt_profile < 2;
+    bool keys_ready = false;
+    FL_RC(read_flags_begin(c));
+    if (overlap && !c->need_rebuild) {
+        LAUNCH_N(k_seg_keys, n, n, L_(c).recv, c->d_depth);
+        FL_CK(fl_inclusive_max(c->d_tmp, c->tmp_bytes, c->d_depth, c->d_sg_head, n, c->stream, false));
+        keys_ready = true;
+    }
+    FL_RC(read_flags_end(c));
     const bool has_lake = c->h_flags[FL_FLAG_LAKE] != 0;
     const uint32_t n_chg = c->h_flags[FL_FLAG_NCHG];
     FL_RC(stage_mark(c, 2));
@@ -850,6 +957,7 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
         FL_RC(k_end(c, FASTLEM_K_REBUILD));
     }
     c->need_rebuild = false;
+    if (has_lake || rebuilt) keys_ready = false;  // the forest / the numbering changed after the keys were taken
     FL_RC(stage_mark(c, 7));  // end of the layout rebuild
     Layout& L = L_(c);
     const bool incr = track && !has_lake && !rebuilt &&
@@ -871,8 +979,10 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
         FL_CK(fl_memset(c->d_sg_wait, 0, sizeof(uint32_t) * n, c->stream));
         FL_CK(fl_memset(c->d_sg_done, 0, sizeof(uint32_t) * n, c->stream));
         LAUNCH_N(k_count_waits, n, n, L.recv, L.cmask, L.areas, c->d_nwait, c->d_A, c->d_hgt, c->d_hsuf);
-        LAUNCH_N(k_seg_keys, n, n, L.recv, c->d_depth);
-        FL_CK(fl_inclusive_max(c->d_tmp, c->tmp_bytes, c->d_depth, c->d_sg_head, n, c->stream, false));
+        if (!keys_ready) {
+            LAUNCH_N(k_seg_keys, n, n, L.recv, c->d_depth);
+            FL_CK(fl_inclusive_max(c->d_tmp, c->tmp_bytes, c->d_depth, c->d_sg_head, n, c->stream, false));
+        }
         LAUNCH_N(k_seg_prepare, n, f, c->d_sg_tail, c->d_sg_wait);
         FL_RC(k_begin(c));
         LAUNCH_N(k_area_flow, n, f);
@@ -896,8 +1006,10 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
         }
         if (n_chg) {
             f.dirty_from = c->d_dirty_from;
-            LAUNCH_N(k_seg_keys, n, n, L.recv, c->d_depth);
-            FL_CK(fl_inclusive_max(c->d_tmp, c->tmp_bytes, c->d_depth, c->d_sg_head, n, c->stream, false));
+            if (!keys_ready) {
+                LAUNCH_N(k_seg_keys, n, n, L.recv, c->d_depth);
+                FL_CK(fl_inclusive_max(c->d_tmp, c->tmp_bytes, c->d_depth, c->d_sg_head, n, c->stream, false));
+            }
             FL_LAUNCH(k_incr_mark, blocks_for(n_chg, 128), 128, c->stream, f, n_chg, c->d_chg_node, c->d_chg_old);
             const unsigned wide = (unsigned)c->sm_count * 8u;
             FL_LAUNCH(k_incr_prepare, wide, 128, c->stream, f);
@@ -1084,7 +1196,21 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool* changed_out) {
     }
     c->stats.kernel_launches += launched; c->stats.n_elevation += launched;
     FL_RC(stage_mark(c, 6));
-    FL_RC(read_flags(c));
+    FL_RC(read_flags_begin(c));
+    if (overlap && may_continue && c->opt_k5_split) {
+        // While the flags travel to the host, the NEXT iteration's K1 is already running (the elevations it reads are
+        // final).  It writes the alternate receiver buffers, so if this iteration turns out to be the last one
+        // (`changed` clear) nothing of the run's state has been touched; the next iteration swaps the buffers in.
+        const bool track_next = c->opt_incremental != 0 && c->opt_rebuild_every != 1;  // (k4_valid holds from here on)
+        FL_CK(fl_memset(c->d_flags, 0, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
+        FL_CK(fl_memset(c->d_cmask_alt, 0, sizeof(uint32_t) * n, c->stream));
+        if (c->opt_profile) FL_CK(fl_event_record(c->ev[ST_COUNT + 3], c->stream));
+        FL_RC(launch_receivers(c, track_next, L.recv, c->d_recv_alt, c->d_drecv_alt, c->d_cmask_alt));
+        if (c->opt_profile) FL_CK(fl_event_record(c->ev[ST_COUNT + 4], c->stream));
+        c->k1_pre = true;
+        c->k1_pre_track = track_next;
+    }
+    FL_RC(read_flags_end(c));
     FL_CK(fl_last_error());
     if (c->opt_k5_split) {
         if (c->h_flags[FL_FLAG_BROKEN] & 1u)
@@ -1198,6 +1324,9 @@ int alloc_graph_buffers(fastlem_ctx* c, uint32_t n, uint32_t nnz) {
         FL_CK(dalloc(c, S.cmask, n));
         FL_CK(dalloc(c, S.lvl, n));
     }
+    FL_CK(dalloc(c, c->d_recv_alt, n));
+    FL_CK(dalloc(c, c->d_cmask_alt, n));
+    FL_CK(dalloc(c, c->d_drecv_alt, n));
     FL_CK(dalloc(c, c->d_init, n));
     FL_CK(dalloc(c, c->d_rank_to_node, n));
     FL_CK(dalloc(c, c->d_pd, n));
@@ -1298,7 +1427,7 @@ int fastlem_create(fastlem_ctx** out, int device_ordinal) {
     c->h_offs_k = c->h_flags + FL_N_FLAGS;
     c->h_rounds = c->h_offs_k + (FL_KEY_BASE + 2);
     bool ok = true;
-    for (int k = 0; k < ST_COUNT + 3; ++k) ok = ok && fl_event_create(&c->ev[k]) == cudaSuccess;
+    for (int k = 0; k < ST_COUNT + 6; ++k) ok = ok && fl_event_create(&c->ev[k]) == cudaSuccess;
     for (int k = 0; k < 2; ++k) ok = ok && fl_event_create(&c->ev_run[k]) == cudaSuccess;
     for (int k = 0; k < 2; ++k) ok = ok && fl_event_create(&c->ev_k[k]) == cudaSuccess;
     void* fl = nullptr;
@@ -1322,7 +1451,7 @@ void fastlem_destroy(fastlem_ctx* c) {
     if (c->d_flags) fl_free(c->d_flags);
     if (c->h_flags) fl_free_host(c->h_flags);
 
-    for (int k = 0; k < ST_COUNT + 3; ++k)
+    for (int k = 0; k < ST_COUNT + 6; ++k)
         if (c->ev[k]) fl_event_destroy(c->ev[k]);
     for (int k = 0; k < 2; ++k)
         if (c->ev_run[k]) fl_event_destroy(c->ev_run[k]);
@@ -1351,6 +1480,13 @@ int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
         c->opt_park_after = value;
     } else if (s == "flood_device") {
         c->opt_flood_device = value != 0;
+        c->rank_ready = false;
+    } else if (s == "overlap") {
+        c->opt_overlap = value != 0;
+    } else if (s == "k1_bulk") {
+        c->opt_k1_bulk = value != 0;
+    } else if (s == "outlet_closed_form") {
+        c->opt_outlet_closed_form = value != 0;
         c->rank_ready = false;
     } else if (s == "incremental") {
         c->opt_incremental = value != 0;
@@ -1409,7 +1545,6 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     tr.mark("free previous");
     c->n = n;
     c->nnz = nnz;
-    c->h_row_ptr = row_ptr; c->h_col = col; c->h_dist = dist;
     const size_t n1 = (size_t)n + 1;
     c->slab_dry = true;  // sizes first, then one allocation, then the same calls carve it up
     c->slab_need = 0;
@@ -1449,6 +1584,13 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
         int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_incr_flow, 256, 0) == cudaSuccess && occ > 0)
             c->incr_flow_blocks = occ * fl_sm_count();
+    }
+    {
+        int occ = 0;
+        c->k1_bulk_blocks = 0;
+        if (cudaFuncSetAttribute(k_receivers_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL_K1B_SMEM) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_receivers_bulk, 256, FL_K1B_SMEM) == cudaSuccess && occ > 0)
+            c->k1_bulk_blocks = occ * fl_sm_count();
     }
 #endif
 #ifdef FL_FLOW_STATS
@@ -1542,14 +1684,16 @@ int fastlem_run(fastlem_ctx* c, uint32_t max_iteration, uint32_t* iterations_don
     FL_CK(fl_set_device(c->device));
     // reset per-run stats, keep the one-off ones
     double up = c->stats.ms_upload, fr = c->stats.ms_flood_rank;
-    const uint32_t fd = c->stats.flood_on_device;
+    const uint32_t fd = c->stats.flood_on_device, od = c->stats.outlet_ranks_on_device;
     c->stats = fastlem_stats{};
     c->stats.ms_upload = up;
     c->stats.ms_flood_rank = fr;
     c->stats.flood_on_device = fd;
+    c->stats.outlet_ranks_on_device = od;
     FL_CK(fl_event_record(c->ev_run[0], c->stream));
     FL_RC(reset_layout(c));
     c->need_rebuild = true;
+    c->k1_pre = false;
     uint32_t it = 0;
     while (it < max_iteration) {
         bool changed = false;
@@ -1557,7 +1701,7 @@ int fastlem_run(fastlem_ctx* c, uint32_t max_iteration, uint32_t* iterations_don
         // children of the path layout from the second body on.
         const bool flow_ok = c->opt_sweep == 3 && c->max_degree <= 32;
         if (c->opt_sweep == 0 || (it == 0 && !(flow_ok && c->opt_first_flow))) FL_RC(iterate_levels(c, it == 0, &changed));
-        else if (flow_ok) FL_RC(iterate_flow(c, it, &changed));
+        else if (flow_ok) FL_RC(iterate_flow(c, it, it + 1u < max_iteration, &changed));
         else FL_RC(iterate_paths(c, &changed));
         ++it;
         if (!changed) break;

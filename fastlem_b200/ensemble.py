@@ -132,6 +132,34 @@ def run_pool(ctx, pool, make_params, on_result, max_iteration=None):
     return done
 
 
+def run_pool_concurrent(contexts, pool, make_params, on_result, max_iteration=None):
+    """`run_pool` on several contexts of ONE device at once, one host thread per context, all drawing from the same pool.
+
+    The solver's sweeps are latency-bound chains: a single terrain leaves most of the GPU idle, and
+    the kernels of independent members interleave on the SMs (each context has its own stream; the library calls release
+    the GIL).  `on_result(t, iterations, ctx)` is called from the context's thread -- guard shared state with a lock.
+    Returns the list of members run, per context."""
+    import threading
+    done = [None] * len(contexts)
+    failure = []
+
+    def work(k):
+        try:
+            done[k] = run_pool(contexts[k], pool, make_params, on_result, max_iteration)
+        except BaseException as ex:
+            failure.append(ex)
+
+    threads = [threading.Thread(target=work, args=(k,), daemon=True) for k in range(1, len(contexts))]
+    for th in threads:
+        th.start()
+    work(0)
+    for th in threads:
+        th.join()
+    if failure:
+        raise failure[0]
+    return done
+
+
 def gather_elevations(local, n_members, n_sites, rank, world, device="cpu"):
     """All-gather the members' elevations: returns an (n_members, n_sites) float64 array on every rank.
 

@@ -56,9 +56,8 @@ int fastlem_get_device(const fastlem_ctx* ctx);
  *   col/dist = neighbour index and edge attribute (length) per slot
  *   areas    = model.areas()
  * The graph must be simple and symmetric with equal lengths in both directions (what
- * terrain-graph's add_edge produces).  The arrays are copied to HBM before this returns, but the
- * pointers must stay valid until the ctx is destroyed or the graph is replaced: the flood order of
- * lake removal (a function of graph + outlets only) is computed from them on first use.
+ * terrain-graph's add_edge produces).  The arrays are copied to HBM before this returns and the
+ * pointers are not kept: the caller may free or reuse them at once.
  */
 int fastlem_set_graph(fastlem_ctx* ctx, uint32_t n, const uint32_t* row_ptr, const uint32_t* col,
                       const double* dist, const double* areas);
@@ -95,7 +94,7 @@ int fastlem_download_to_device(fastlem_ctx* ctx, double* device_elevations_out);
  * fastlem_stats; "keep_stages" = 1 (default 0) keeps the pre-lake-removal receivers/labels of the last iteration for
  * fastlem_debug_fetch.  The rest select between implementations that give bit-identical results:
  * "sweep" 0 = one launch per tree level, 1 / 2 = path-decomposed (thread / warp per path), 3 = dataflow sweeps
- * (default); "incremental" (1), "incr_div" (16), "first_flow" (1), "fuse_levels" (1), "fuse_k4" (0), "flood_device" (1),
+ * (default); "incremental" (1), "incr_div" (16), "first_flow" (1), "fuse_levels" (1), "fuse_k4" (0), "flood_device" (1), "outlet_closed_form" (1),
  * "park_after" (8), "key_base", "rebuild_every" (0 = adaptive), "rebuild_growth" (4), "rebuild_height" (150). */
 int fastlem_set_option(fastlem_ctx* ctx, const char* name, int64_t value);
 
@@ -118,7 +117,8 @@ typedef struct fastlem_stats {
     uint32_t paths;       /* number of paths */
     uint32_t incremental_iterations; /* iterations whose drainage areas were updated incrementally */
     uint32_t flood_on_device; /* 1: the flood order was computed on the device, 0: exact host replay (ties) */
-    uint32_t reserved;
+    uint32_t outlet_ranks_on_device; /* 1: the outlets' own ranks came from their closed form on the device, 0: host replay
+                                      * of that prefix (an outlet without unvisited neighbours early in the order) */
     /* "profile"=2 only (synchronises after every bracketed kernel: a diagnostic mode): device time and launch count
      * of single kernels of the default path, summed over the last run; index = FASTLEM_K_* */
     double ms_kernel[8];

@@ -51,7 +51,7 @@ def _raster_worker(rank, world, port, emu_lib, out_dir):
     dist.destroy_process_group()
 
 
-def _pool_worker(rank, world, port, emu_lib, out_dir):
+def _pool_worker(rank, world, port, emu_lib, out_dir, n_contexts=1):
     """The dynamic ensemble pool (bench.py --gpus N): one shared graph per rank, members taken first come first served
     through the process group's store, results gathered at the end (variable number of members per rank)."""
     sys.path.insert(0, ROOT)
@@ -71,12 +71,22 @@ def _pool_worker(rank, world, port, emu_lib, out_dir):
     def make_params(t):
         return dict(initial=initial, erodibility=_pool_erodibility(n, t), uplift=p["uplift"], outlets=outlets)
 
+    import threading
+    lock = threading.Lock()
+
     def on_result(t, it, ctx):
-        mine[t] = (ctx.download(), it)
-    with _native.Context(0, emu_lib) as ctx:
+        e = ctx.download()
+        with lock:
+            mine[t] = (e, it)
+    ctxs = []
+    for _ in range(n_contexts):  # members in flight per rank: one context and host thread each (bench.py --contexts-per-gpu)
+        ctx = _native.Context(0, emu_lib)
         ctx.set_graph(m["row_ptr"], m["col"], m["dist"], m["areas"])
-        done = ensemble.run_pool(ctx, pool, make_params, on_result)
-    assert sorted(done) == sorted(mine)
+        ctxs.append(ctx)
+    done = [t for part in ensemble.run_pool_concurrent(ctxs, pool, make_params, on_result) for t in part]
+    for ctx in ctxs:
+        ctx.close()
+    assert sorted(done) == sorted(mine) and len(done) == len(set(done))
     # gather: member ids and elevations, padded to the largest count
     counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(counts, torch.tensor([len(done)], dtype=torch.int64))
@@ -180,11 +190,13 @@ def test_member_pool_single_process():
     assert [pool.take() for _ in range(7)] == [0, 1, 2, 3, 4, None, None]
 
 
-def test_ensemble_pool_two_ranks_gloo(tmp_path, emu_lib, oracle):
-    """Dynamic member assignment over 2 ranks: every member exactly once, each bit-identical to the oracle."""
+@pytest.mark.parametrize("n_contexts", [1, 2])
+def test_ensemble_pool_two_ranks_gloo(tmp_path, emu_lib, oracle, n_contexts):
+    """Dynamic member assignment over 2 ranks (and 1 or 2 members in flight per rank): every member exactly once, each
+    bit-identical to the oracle."""
     import torch.multiprocessing as mp
-    port = 31500 + (os.getpid() % 1000)
-    mp.spawn(_pool_worker, args=(2, port, emu_lib, str(tmp_path)), nprocs=2, join=True)
+    port = 31500 + (os.getpid() % 1000) + 1000 * n_contexts
+    mp.spawn(_pool_worker, args=(2, port, emu_lib, str(tmp_path), n_contexts), nprocs=2, join=True)
     got = np.load(tmp_path / "pool.npy")
     m, p, outlets, initial, _ = scenario("uniform", 500)
     for t in range(got.shape[0]):

@@ -113,6 +113,45 @@ def test_flood_rank_matches_oracle(oracle, emu_lib, name, device):
         assert np.array_equal(ctx.fetch("flood_rank"), oracle.flood_order(m, outlets)), name
         on_device = ctx.stats()["flood_on_device"]
         assert on_device == (1 if device and name not in ("lattice_regular",) else 0)
+        assert ctx.stats()["outlet_ranks_on_device"] == on_device  # closed form of the outlets' own ranks
+    if device:  # the same with the outlets' prefix replayed on the host
+        with _ctx(emu_lib, outlet_closed_form=0) as ctx:
+            helpers.load_ctx(ctx, m, p, outlets, initial)
+            assert np.array_equal(ctx.fetch("flood_rank"), oracle.flood_order(m, outlets)), name
+            assert ctx.stats()["outlet_ranks_on_device"] == 0
+
+
+@pytest.mark.parametrize("count", list(range(1, 41)) + [63, 64, 65, 127, 128, 129, 1000])
+def test_outlet_ranks_closed_form_every_count(oracle, emu_lib, count):
+    """The outlets' own ranks (BinaryHeap at equal keys 0.0, stream_tree.rs:184-197) from their closed form on the device
+    (fl_floodgpu.cuh, k_flg_outlet_*), for every small number of outlets (every shape of the heap's last level) and a
+    few larger ones, outlets in a shuffled order."""
+    m, p, _, initial, _ = scenario("uniform", 2500)
+    rng = np.random.default_rng(count)
+    outlets = rng.choice(m["n"], count, replace=False).astype(np.uint32)  # unsorted: user-supplied default_outlets order
+    with _ctx(emu_lib) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert np.array_equal(ctx.fetch("flood_rank"), oracle.flood_order(m, outlets))
+        st = ctx.stats()
+        assert st["flood_on_device"] == 1 and st["outlet_ranks_on_device"] == 1
+
+
+def test_outlet_ranks_closed_form_refused(oracle, emu_lib):
+    """An outlet without neighbours at the front of the order: its pop pushes nothing, the next pop moves a 0.0 entry from
+    the tail and the closed form does not hold -- the validity check must send the prefix to the host replay."""
+    m, p, outlets, initial, _ = scenario("uniform", 1500)
+    n = m["n"] + 3  # three sites without any edge, placed at the front of the outlet list
+    m2 = dict(m, n=n, row_ptr=np.concatenate([m["row_ptr"], np.full(3, m["row_ptr"][-1], np.uint32)]).astype(np.uint32),
+              areas=np.concatenate([m["areas"], np.ones(3)]))
+    p2 = dict(erodibility=np.ones(n), uplift=np.ones(n), max_slope=None)
+    outlets2 = np.concatenate([np.arange(n - 3, n, dtype=np.uint32), outlets]).astype(np.uint32)
+    initial2 = oracle.initial_elevations(np.zeros(n))
+    with _ctx(emu_lib) as ctx:
+        helpers.load_ctx(ctx, m2, p2, outlets2, initial2)
+        assert np.array_equal(ctx.fetch("flood_rank"), oracle.flood_order(m2, outlets2))
+        st = ctx.stats()
+        assert st["flood_on_device"] == 1 and st["outlet_ranks_on_device"] == 0
+        assert helpers.check_generate(ctx, oracle, m2, p2, outlets2, initial2, 30)
 
 
 @pytest.mark.parametrize("name,n", [("uniform", 20000), ("advanced", 30000), ("interior_outlets", 8000),
@@ -258,3 +297,22 @@ def test_ensemble_members_on_one_shared_graph(oracle, emu_lib):
         ref, ref_it = oracle.generate(m, mem["erodibility"], mem["uplift"], ms, mem["outlets"], mem["initial"], 40)
         assert it == ref_it, k
         assert np.array_equal(e, ref), f"member {k}"
+
+
+def test_graph_arrays_are_not_borrowed(oracle, emu_lib):
+    """fastlem_set_graph copies its arrays (include/fastlem_b200.h): the caller may overwrite them right after the call,
+    even when the flood order needs the exact host replay later on (tied edge lengths: the graph is read back from the
+    device for it)."""
+    m, p, outlets, initial, max_iteration = scenario("lattice_regular")
+    with _ctx(emu_lib) as ctx:
+        rp, col, dist, areas = (m[k].copy() for k in ("row_ptr", "col", "dist", "areas"))
+        ctx.set_graph(rp, col, dist, areas)
+        for a in ctx._keep["graph"]:
+            a[...] = 0
+        rp[...] = 0; col[...] = 0; dist[...] = 0; areas[...] = 0
+        ctx.set_parameters(initial, p["erodibility"], p["uplift"], helpers.tan_of(p["max_slope"]), outlets)
+        assert np.array_equal(ctx.fetch("flood_rank"), oracle.flood_order(m, outlets))
+        assert ctx.stats()["flood_on_device"] == 0
+        e, it = ctx.generate(max_iteration)
+        ref, ref_it = oracle.generate(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, initial, max_iteration)
+        assert it == ref_it and np.array_equal(e, ref)

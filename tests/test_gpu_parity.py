@@ -167,7 +167,9 @@ def test_flood_order_on_device(oracle, gpu_ctx_factory, name, n):
     with gpu_ctx_factory() as ctx:
         helpers.load_ctx(ctx, m, p, outlets, initial)
         assert np.array_equal(ctx.fetch("flood_rank"), ref)
-        assert ctx.stats()["flood_on_device"] == (0 if name in ("lattice_regular", "edge_sites_partial") else 1)
+        st = ctx.stats()
+        assert st["flood_on_device"] == (0 if name in ("lattice_regular", "edge_sites_partial") else 1)
+        assert st["outlet_ranks_on_device"] == st["flood_on_device"]  # closed form of the outlets' own ranks
     with gpu_ctx_factory(flood_device=0) as ctx:
         helpers.load_ctx(ctx, m, p, outlets, initial)
         assert np.array_equal(ctx.fetch("flood_rank"), ref)

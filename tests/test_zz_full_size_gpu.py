@@ -3,6 +3,7 @@ configurations at their full sizes, checked through size-independent
 properties because the oracle cannot run them to convergence in test time (tests/helpers.py,
 check_converged_properties; the helper itself is validated on the CPU tier in test_emu_parity.py).
 C2 at 1M sites lives in test_gpu_parity.py::test_c2_one_million_sites."""
+import numpy as np
 import pytest
 
 import helpers
@@ -41,10 +42,30 @@ def test_c4_sixteen_million_sites(oracle, gpu_ctx_factory):
     assert m["n"] == 16000000
     initial = oracle.initial_elevations(p["base"])
     with gpu_ctx_factory() as ctx:
-        _, it = helpers.check_converged_properties(ctx, oracle, m, p, outlets, initial, first_iterations=0)
+        e, it = helpers.check_converged_properties(ctx, oracle, m, p, outlets, initial, first_iterations=0)
         st = ctx.stats()
         assert it > 1000
         assert st["flood_on_device"] == 1
+        # the lock-free hand-offs of K4 / K5 under load: a third run of the whole thing, identical bits
+        e3, it3 = ctx.generate()
+        assert it3 == it and np.array_equal(e3, e)
+
+
+def test_stress_two_hundred_generates_one_million_sites(product_lib):
+    """The sweeps of K4 and K5 hand work between warps without locks (release / acquire through L2, fl_flow.cuh,
+    fl_elev.cuh): 200 back-to-back generate() of the C2 terrain (1M sites, about a thousand iterations each, 2e5
+    launches of the dataflow kernels) must give identical bits and identical iteration counts every time."""
+    import hashlib
+    from fastlem_b200 import _native
+    from scenarios import scenario
+    m, p, outlets, initial, _ = scenario("uniform", 1000000)
+    with _native.Context(0, product_lib) as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        seen = set()
+        for _ in range(200):
+            e, it = ctx.generate()
+            seen.add((it, hashlib.sha1(e.tobytes()).hexdigest()))
+        assert len(seen) == 1, f"{len(seen)} different results in 200 runs"
 
 
 def test_ensemble_members_on_one_shared_graph_gpu(oracle, product_lib):

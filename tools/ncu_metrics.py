@@ -23,7 +23,8 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
 
 def main():
     rep = sys.argv[1]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    raw = open(rep).read() if rep.endswith(".csv") else \
+        subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     names, units = rows[hdr], rows[hdr + 1]
