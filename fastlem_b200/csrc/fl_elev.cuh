@@ -38,10 +38,14 @@
 #define FL_PDEPTH 3   // windows of a segment kept in flight
 #endif
 #define FL_CUT_MAX 8u  // largest cut height (= most k_elev_low launches per iteration)
+#ifndef FL_TOP_EARLY_WINDOW
+#define FL_TOP_EARLY_WINDOW 1  // build-time A/B switch: k_elev_top requests a run's first window with the entry's payload
+#endif
 
 // words of d_flags
 // (the three queue counters sit on cache lines of their own: producers hit tail, consumers head, finishers done)
-enum { FLQ_HIST = 24 /* 32 bins: heads per nesting height (31 = 31+) */, FLQ_TAIL = 64, FLQ_HEAD = 96, FLQ_DONE = 128 };
+enum { FLQ_HIST = 24 /* 32 bins: heads per nesting height (31 = 31+) */, FLQ_TAIL = 64, FLQ_HEAD = 96, FLQ_DONE = 128,
+       FLQ_LOW = 160 /* FL_CUT_MAX words: heads listed per height below the cut */ };
 
 struct FlQEntry {  // 32 bytes = one sector
     unsigned long long flag;  // (epoch << 32) | first site of the run; written last (release)
@@ -74,7 +78,17 @@ struct FlSplit {
     uint32_t epoch;    // number of this sweep: entries of earlier sweeps never match, the queue is never cleared
     uint32_t cut;      // segments with hgt >= cut go through the queue
     uint32_t* flags;
+    // the heads below the cut as (head, receiver) pairs, one list per height, filled by k_elev_plan (flags[FLQ_LOW + l] =
+    // length).  A segment of height l has a chain of l segments below it and segments are disjoint, so there are at
+    // most n / (l + 1) heads of height l: the lists lie behind each other in low_list at fl_low_region(n, l).
+    uint2* low_list;
 };
+#define FL_LOW_CHUNK 2048u  // positions per block of k_elev_plan
+__host__ __device__ inline size_t fl_low_region(uint32_t n, uint32_t level) {
+    size_t at = 0;
+    for (uint32_t l = 0; l < level; ++l) at += (size_t)n / (l + 1u) + 1u;
+    return at;
+}
 
 __device__ __forceinline__ unsigned long long flq_flag(uint32_t epoch, uint32_t site) {
     return ((unsigned long long)epoch << 32) | (unsigned long long)site;
@@ -119,53 +133,71 @@ __device__ __forceinline__ double fl_celerity_term(const FlSplit& e, uint32_t i,
 // up to B sites of one run by one thread, starting at q (q is NOT a tree root: roots are handled by fl_root_site);
 // returns true when the run ended inside the batch.  A dead run (root == FL_NONE) only marks its sites.
 template <int B>
-__device__ __forceinline__ bool fl_run_batch(const FlSplit& e, uint32_t& q, FlSegStart& s, bool& changed) {
-    const uint32_t nb = e.n - q < (uint32_t)B ? e.n - q : (uint32_t)B;
-    const bool live = s.root != FL_NONE;
+struct FlBatch {
     double d[B], t[B], up[B], eo[B], ms[B];
     uint32_t nx[B];
+    uint32_t nb;
+};
+// the loads of a batch: they depend on nothing but the position, so a caller may issue them before it knows what the
+// run starts from (`live` = false skips the values of a dead run when that is already known)
+template <int B>
+__device__ __forceinline__ void fl_batch_load(const FlSplit& e, uint32_t q, bool live, FlBatch<B>& b) {
+    b.nb = e.n - q < (uint32_t)B ? e.n - q : (uint32_t)B;
 #pragma unroll
     for (int k = 0; k < B; ++k) {
-        d[k] = 1.0; t[k] = 0.0; up[k] = 0.0; eo[k] = 0.0; ms[k] = 0.0; nx[k] = FL_NONE;
-        if ((uint32_t)k < nb) {
+        b.d[k] = 1.0; b.t[k] = 0.0; b.up[k] = 0.0; b.eo[k] = 0.0; b.ms[k] = 0.0; b.nx[k] = FL_NONE;
+        if ((uint32_t)k < b.nb) {
             const uint32_t i = q + k;
-            nx[k] = (i + 1u < e.n) ? e.recv[i + 1u] : FL_NONE;
+            b.nx[k] = (i + 1u < e.n) ? e.recv[i + 1u] : FL_NONE;
             if (live) {
-                t[k] = e.tcel[i];
-                up[k] = e.uplift[i];
-                eo[k] = e.elev[i];
-                if (e.tan_slope) { ms[k] = e.tan_slope[i]; d[k] = e.drecv[i]; }
+                b.t[k] = e.tcel[i];
+                b.up[k] = e.uplift[i];
+                b.eo[k] = e.elev[i];
+                if (e.tan_slope) { b.ms[k] = e.tan_slope[i]; b.d[k] = e.drecv[i]; }
             }
         }
     }
+}
+template <int B>
+__device__ __forceinline__ bool fl_batch_compute(const FlSplit& e, uint32_t& q, FlSegStart& s, bool& changed,
+                                                 const FlBatch<B>& b) {
+    const bool live = s.root != FL_NONE;
     bool ended = false;
     uint32_t walked = 0u;
 #pragma unroll
     for (int k = 0; k < B; ++k) {
-        if (!ended && (uint32_t)k < nb) {
+        if (!ended && (uint32_t)k < b.nb) {
             const uint32_t i = q + k;
             ++walked;
             if (live) {
-                const double rti = 0.0 + (s.rt_prev + t[k]);
-                double z = s.e_out + up[k] * fmax(rti - s.rt_out, 0.0);
+                const double rti = 0.0 + (s.rt_prev + b.t[k]);
+                double z = s.e_out + b.up[k] * fmax(rti - s.rt_out, 0.0);
                 if (e.tan_slope) {
-                    if (ms[k] == ms[k]) {  // not NaN: Some(max_slope)
-                        const double slope = (z - s.z_prev) / d[k];
-                        if (slope > ms[k]) z = s.z_prev + ms[k] * d[k];
+                    if (b.ms[k] == b.ms[k]) {  // not NaN: Some(max_slope)
+                        const double slope = (z - s.z_prev) / b.d[k];
+                        if (slope > b.ms[k]) z = s.z_prev + b.ms[k] * b.d[k];
                     }
                 }
-                changed |= (z != eo[k]);
+                changed |= (z != b.eo[k]);
                 e.elev[i] = z;
                 e.rt[i] = rti;
                 s.rt_prev = rti;
                 s.z_prev = z;
             }
             e.root_of[i] = s.root;
-            if (nx[k] != i) ended = true;
+            if (b.nx[k] != i) ended = true;
         }
     }
     q += walked;  // one past the last site written
     return ended || q >= e.n;
+}
+// up to B sites of one run by one thread, starting at q (q is NOT a tree root: roots are handled by fl_root_site);
+// returns true when the run ended inside the batch.  A dead run (root == FL_NONE) only marks its sites.
+template <int B>
+__device__ __forceinline__ bool fl_run_batch(const FlSplit& e, uint32_t& q, FlSegStart& s, bool& changed) {
+    FlBatch<B> b;
+    fl_batch_load<B>(e, q, s.root != FL_NONE, b);
+    return fl_batch_compute<B>(e, q, s, changed, b);
 }
 
 // A tree root h (recv[h] == h).  An outlet: rt = 0.0 + (0.0 + term), the elevation formula with e_outlet = its own
@@ -198,58 +230,104 @@ __device__ __forceinline__ FlSegStart fl_root_site(const FlSplit& e, uint32_t h,
 // ------------------------------------------------------------------------------------------------
 // plan: histogram, push masks, the roots of the top trees
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_elev_plan(FlSplit e) {
-#ifndef FL_EMU
-    __shared__ uint32_t hist[32];
-    if (threadIdx.x < 32u) hist[threadIdx.x] = 0u;
-    __syncthreads();
-#endif
-    const uint32_t q = FL_TID;
-    bool changed = false;
-    if (q < e.n) {
-        const double tq = fl_celerity_term(e, q, e.drecv[q]);  // (fully parallel: the division and the square root stay
-        e.tcel[q] = tq;                                        //  out of the serial chains)
-        const uint32_t h = e.hgt[q];
-        if (h != FL_NONE) {  // q heads a segment
-#ifdef FL_EMU
-            atomicAdd(&e.flags[FLQ_HIST + (h < 31u ? h : 31u)], 1u);
-#else
-            atomicAdd(&hist[h < 31u ? h : 31u], 1u);
-#endif
-            if (h >= e.cut) {
-                const uint32_t p = e.recv[q];
-                if (p == q) {
-                    // a top tree: the root site itself, then the run behind it and its top children as queue entries
-                    const FlSegStart s = fl_root_site(e, q, tq, changed);
-                    const bool chain = (q + 1u < e.n) && (e.recv[q + 1u] == q);
-                    if (chain) flq_put(e, atomicAdd(&e.flags[FLQ_TAIL], 1u), q + 1u, s.root, s.rt_prev, s.z_prev, false);
-                    const uint32_t s0 = e.row_ptr[q];
-                    uint32_t m = e.cmask[q];
-                    while (m) {
-                        const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
-                        m &= m - 1u;
-                        const uint32_t c = e.col[s0 + b];
-                        if (chain && c == q + 1u) continue;
-                        const uint32_t hc = e.hgt[c];
-                        if (hc != FL_NONE && hc >= e.cut)
-                            flq_put(e, atomicAdd(&e.flags[FLQ_TAIL], 1u), c, s.root, s.rt_prev, s.z_prev, false);
-                    }
-                } else if (e.recv[p] != p) {  // (a root pushes its own top children, above)
-                    uint32_t bit = 32u;
-                    for (uint32_t sl = e.row_ptr[q]; sl < e.row_ptr[q + 1u]; ++sl)
-                        if (e.col[sl] == p) { bit = e.rev[sl]; break; }
-                    if (bit < 32u) atomicOr(&e.pmask[p], 1u << bit);
-                    else atomicOr(&e.flags[FL_FLAG_BROKEN], 16u);
-                }
+// one site of the plan pass; returns its nesting height if it heads a segment (FL_NONE otherwise)
+template <class H>
+__device__ __forceinline__ uint32_t fl_plan_site(const FlSplit& e, uint32_t q, bool& changed, H&& count_head) {
+    const double tq = fl_celerity_term(e, q, e.drecv[q]);  // (fully parallel: the division and the square root stay
+    e.tcel[q] = tq;                                        //  out of the serial chains)
+    const uint32_t h = e.hgt[q];
+    if (h == FL_NONE) return FL_NONE;  // q does not head a segment
+    count_head(h < 31u ? h : 31u);
+    if (h >= e.cut) {
+        const uint32_t p = e.recv[q];
+        if (p == q) {
+            // a top tree: the root site itself, then the run behind it and its top children as queue entries
+            const FlSegStart s = fl_root_site(e, q, tq, changed);
+            const bool chain = (q + 1u < e.n) && (e.recv[q + 1u] == q);
+            if (chain) flq_put(e, atomicAdd(&e.flags[FLQ_TAIL], 1u), q + 1u, s.root, s.rt_prev, s.z_prev, false);
+            const uint32_t s0 = e.row_ptr[q];
+            uint32_t m = e.cmask[q];
+            while (m) {
+                const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+                m &= m - 1u;
+                const uint32_t c = e.col[s0 + b];
+                if (chain && c == q + 1u) continue;
+                const uint32_t hc = e.hgt[c];
+                if (hc != FL_NONE && hc >= e.cut)
+                    flq_put(e, atomicAdd(&e.flags[FLQ_TAIL], 1u), c, s.root, s.rt_prev, s.z_prev, false);
             }
+        } else if (e.recv[p] != p) {  // (a root pushes its own top children, above)
+            uint32_t bit = 32u;
+            for (uint32_t sl = e.row_ptr[q]; sl < e.row_ptr[q + 1u]; ++sl)
+                if (e.col[sl] == p) { bit = e.rev[sl]; break; }
+            if (bit < 32u) atomicOr(&e.pmask[p], 1u << bit);
+            else atomicOr(&e.flags[FL_FLAG_BROKEN], 16u);
         }
     }
-    if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
-#ifndef FL_EMU
-    __syncthreads();
-    if (threadIdx.x < 32u && hist[threadIdx.x]) atomicAdd(&e.flags[FLQ_HIST + threadIdx.x], hist[threadIdx.x]);
-#endif
+    return h;
 }
+
+#ifdef FL_EMU
+__global__ void __launch_bounds__(256) k_elev_plan(FlSplit e) {
+    const uint32_t q = FL_TID;
+    bool changed = false;
+    if (q < e.n) fl_plan_site(e, q, changed, [&](uint32_t bin) { atomicAdd(&e.flags[FLQ_HIST + bin], 1u); });
+    if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
+}
+#else
+// One block per chunk of FL_LOW_CHUNK positions.  Besides the per-site work, the block appends its heads below the
+// cut to the per-height lists (one reservation per block and height; position order inside a warp's 32 positions), so
+// that the per-height launches of k_elev_low neither scan the heights again nor run half-empty warps -- the sparse
+// heights above 0 would otherwise leave a handful of active threads per block.
+__global__ void __launch_bounds__(256) k_elev_plan(FlSplit e) {
+    __shared__ uint32_t hist[32];
+    __shared__ uint32_t lcount[FL_CUT_MAX];
+    __shared__ uint32_t lbase[FL_CUT_MAX];
+    if (threadIdx.x < 32u) hist[threadIdx.x] = 0u;
+    if (threadIdx.x < FL_CUT_MAX) lcount[threadIdx.x] = 0u;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const unsigned long long base = (unsigned long long)blockIdx.x * FL_LOW_CHUNK;
+    bool changed = false;
+    uint32_t slot[FL_LOW_CHUNK / 256u];  // (height << 16 | rank among the block's heads of that height), FL_NONE = none
+    uint32_t rcv[FL_LOW_CHUNK / 256u];   // receiver of such a head (k_elev_low starts from its values)
+#pragma unroll
+    for (uint32_t j = 0; j < FL_LOW_CHUNK / 256u; ++j) {
+        const unsigned long long q64 = base + j * 256u + threadIdx.x;
+        uint32_t h = FL_NONE;
+        if (q64 < e.n) h = fl_plan_site(e, (uint32_t)q64, changed, [&](uint32_t bin) { atomicAdd(&hist[bin], 1u); });
+        const bool low = h != FL_NONE && h < e.cut;
+        rcv[j] = low ? e.recv[(uint32_t)q64] : 0u;
+        // lanes whose heads have the same height reserve their places together (one shared-memory atomic per group)
+        const uint32_t key = low ? h : FL_CUT_MAX;
+        const uint32_t peers = __match_any_sync(FL_FULL, key);
+        const int leader = __ffs((int)peers) - 1;
+        uint32_t first = 0u;
+        if (low && lane == leader) first = atomicAdd(&lcount[h], (uint32_t)__popc(peers));
+        first = __shfl_sync(FL_FULL, first, leader);
+        slot[j] = low ? ((h << 16) | (first + (uint32_t)__popc(peers & ((1u << lane) - 1u)))) : FL_NONE;
+    }
+    __syncthreads();
+    // one reservation per block and height in the global lists
+    if (threadIdx.x < FL_CUT_MAX) {
+        const uint32_t cnt = lcount[threadIdx.x];
+        lbase[threadIdx.x] = cnt ? atomicAdd(&e.flags[FLQ_LOW + threadIdx.x], cnt) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t j = 0; j < FL_LOW_CHUNK / 256u; ++j)
+        if (slot[j] != FL_NONE) {
+            const uint32_t l = slot[j] >> 16;
+            const size_t at = (size_t)lbase[l] + (slot[j] & 0xFFFFu);
+            if (at <= (size_t)e.n / (l + 1u))
+                e.low_list[fl_low_region(e.n, l) + at] = make_uint2((uint32_t)(base + j * 256u + threadIdx.x), rcv[j]);
+            else
+                atomicOr(&e.flags[FL_FLAG_BROKEN], 64u);  // cannot happen: more heads of a height than sites allow
+        }
+    if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
+    if (threadIdx.x < 32u && hist[threadIdx.x]) atomicAdd(&e.flags[FLQ_HIST + threadIdx.x], hist[threadIdx.x]);
+}
+#endif
 
 // children of site i registered in its push mask -> queue entries carrying i's new values; clears the mask
 template <class F>
@@ -398,48 +476,65 @@ __device__ __forceinline__ void fl_pwin_compute(const FlSplit& e, const FlPWin& 
     }
 }
 
-// queue entries for the registered children of a window's sites: one reservation per window
-__device__ __forceinline__ void fl_pwin_push(const FlSplit& e, const FlPWin& w, uint32_t q, uint32_t nproc, int lane,
-                                             uint32_t root, double my_rt, double my_z) {
-    const uint32_t m = ((uint32_t)lane < nproc) ? w.pm : 0u;
-    const uint32_t cnt = (uint32_t)__popc(m);
-    uint32_t off = cnt;
+// queue entries for the registered children of a window's sites: one reservation per window.  The reservation (an atomic
+// on the queue tail, ~1 us round trip) is ISSUED when the window has been written and CONSUMED one window later
+// (fl_push_finish), so the chain of windows of a long run does not wait for it.
+#ifndef FL_PUSH_PIPELINE
+#define FL_PUSH_PIPELINE 1  // build-time A/B switch (tools/ab_build.py); 0: reserve and fill at once
+#endif
+struct FlPush {
+    uint32_t total, cnt, off, m, s0, site, sbase;
+    double rt, z;
+};
+__device__ __forceinline__ void fl_push_begin(const FlSplit& e, const FlPWin& w, uint32_t q, uint32_t nproc, int lane,
+                                              double my_rt, double my_z, FlPush& p) {
+    p.m = ((uint32_t)lane < nproc) ? w.pm : 0u;
+    p.cnt = (uint32_t)__popc(p.m);
+    uint32_t off = p.cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t v = __shfl_up_sync(FL_FULL, off, o);
         if (lane >= o) off += v;
     }
-    const uint32_t total = __shfl_sync(FL_FULL, off, 31);
-    if (!total) return;
-    off -= cnt;
-    uint32_t sbase = 0u;
-    if (lane == 0) sbase = atomicAdd(&e.flags[FLQ_TAIL], total);
-    sbase = __shfl_sync(FL_FULL, sbase, 0);
-    if (cnt) {
-        uint32_t at = sbase + off;
-        fl_push_masked(e, q + (uint32_t)lane, w.s0, m, [&](uint32_t c) {
-            if (at < e.n) flq_put(e, at, c, root, my_rt, my_z, true);
+    p.total = __shfl_sync(FL_FULL, off, 31);
+    p.off = off - p.cnt;
+    p.s0 = w.s0; p.site = q + (uint32_t)lane; p.rt = my_rt; p.z = my_z;
+    p.sbase = 0u;
+    if (p.total && lane == 0) p.sbase = atomicAdd(&e.flags[FLQ_TAIL], p.total);  // (the result is not needed yet)
+}
+__device__ __forceinline__ void fl_push_finish(const FlSplit& e, FlPush& p, uint32_t root) {
+    if (!p.total) return;
+    const uint32_t sbase = __shfl_sync(FL_FULL, p.sbase, 0);
+    if (p.cnt) {
+        uint32_t at = sbase + p.off;
+        fl_push_masked(e, p.site, p.s0, p.m, [&](uint32_t c) {
+            if (at < e.n) flq_put(e, at, c, root, p.rt, p.z, true);
             else atomicOr(&e.flags[FL_FLAG_BROKEN], 2u);
             ++at;
         });
     }
+    p.total = 0u;
 }
 
 // a run from q on, by the whole warp; PUSH: registered children become queue entries (k_elev_top)
 template <bool PUSH, int DEPTH>
 __device__ __forceinline__ void fl_run_warp(const FlSplit& e, uint32_t q, const FlSegStart& s, bool& changed,
-                                            FlChainSmem& sm) {
+                                            FlChainSmem& sm, const FlPWin* first = nullptr) {
     const int lane = threadIdx.x & 31;
     const bool live = s.root != FL_NONE;
     double rt_prev = s.rt_prev, z_prev = s.z_prev;
     FlPWin ring[DEPTH];
-    ring[0] = fl_pwin_load<PUSH>(e, q, lane, live);
+    // (`first`: the caller requested the first window before it knew what the run starts from)
+    ring[0] = first ? *first : fl_pwin_load<PUSH>(e, q, lane, live);
     uint32_t endmask;
     uint32_t nproc = fl_pwin_nproc(ring[0], q, lane, endmask);
     if (!endmask) {  // the run goes on beyond the first window: keep DEPTH windows in flight
 #pragma unroll
         for (int j = 1; j < DEPTH; ++j) ring[j] = fl_pwin_load<PUSH>(e, q + 32u * (uint32_t)j, lane, live);
     }
+    FlPush pend;
+    pend.total = 0u; pend.cnt = 0u; pend.off = 0u; pend.m = 0u; pend.s0 = 0u; pend.site = 0u; pend.sbase = 0u;
+    pend.rt = 0.0; pend.z = 0.0;
     for (;;) {
         const FlPWin cur = ring[0];
         if (!endmask) {
@@ -450,11 +545,16 @@ __device__ __forceinline__ void fl_run_warp(const FlSplit& e, uint32_t q, const 
         double my_rt = 0.0, my_z = 0.0;
         if (live) fl_pwin_compute(e, cur, q, nproc, lane, s.root, rt_prev, z_prev, s.e_out, s.rt_out, changed, sm, my_rt, my_z);
         else if ((uint32_t)lane < nproc) e.root_of[q + (uint32_t)lane] = FL_NONE;
-        if (PUSH) fl_pwin_push(e, cur, q, nproc, lane, s.root, my_rt, my_z);
+        if (PUSH) {
+            fl_push_finish(e, pend, s.root);  // the previous window's children (its reservation has arrived by now)
+            fl_push_begin(e, cur, q, nproc, lane, my_rt, my_z, pend);
+            if (!FL_PUSH_PIPELINE) fl_push_finish(e, pend, s.root);
+        }
         if (endmask) break;
         q += 32u;
         nproc = fl_pwin_nproc(ring[0], q, lane, endmask);
     }
+    if (PUSH) fl_push_finish(e, pend, s.root);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -494,6 +594,8 @@ __global__ void __launch_bounds__(256) k_elev_top(FlSplit e) {
             __nanosleep(idle < 8u ? 32u : 100u);
         }
         if (q == FL_NONE) break;
+        // the run's first window is requested together with the entry's payload (one round trip less per hand-off)
+        const FlPWin w0 = fl_pwin_load<true>(e, q, lane, true);
         FlSegStart s;
         s.root = e.queue[t].root;
         s.rt_prev = e.queue[t].rt_p;
@@ -501,7 +603,7 @@ __global__ void __launch_bounds__(256) k_elev_top(FlSplit e) {
         // the root's values were written by k_elev_plan (an earlier launch)
         s.e_out = s.root != FL_NONE ? e.elev[s.root] : 0.0;
         s.rt_out = s.root != FL_NONE ? e.rt[s.root] : 0.0;
-        fl_run_warp<true, FL_PDEPTH>(e, q, s, changed, sm);
+        fl_run_warp<true, FL_PDEPTH>(e, q, s, changed, sm, FL_TOP_EARLY_WINDOW ? &w0 : nullptr);
         if (lane == 0) atomicAdd(&e.flags[FLQ_DONE], 1u);
     }
     if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
@@ -511,91 +613,98 @@ __global__ void __launch_bounds__(256) k_elev_top(FlSplit e) {
 // ------------------------------------------------------------------------------------------------
 // low: all segments of ONE nesting height below the cut, one thread per position
 // ------------------------------------------------------------------------------------------------
-#define FL_LOW_CHUNK 2048u  // positions scanned by one block of k_elev_low
-__global__ void __launch_bounds__(256) k_elev_low(FlSplit e, uint32_t level) {
 #ifdef FL_EMU
+__global__ void __launch_bounds__(256) k_elev_low(FlSplit e, uint32_t level) {
     // emulation: one thread per position
     const uint32_t h = FL_TID;
     if (h >= e.n || e.hgt[h] != level) return;
-    const bool active = true;
-    {
-#else
-    // The heads of this height among the block's FL_LOW_CHUNK positions are first compacted into shared memory (in
-    // position order within a warp's 32 positions), then walked by dense warps.
-    __shared__ uint32_t list[FL_LOW_CHUNK];
-    __shared__ uint32_t count;
-    __shared__ FlChainSmem chain_smem[8];
-    const int lane = threadIdx.x & 31;
-    if (threadIdx.x == 0u) count = 0u;
-    __syncthreads();
-    const unsigned long long base = (unsigned long long)blockIdx.x * FL_LOW_CHUNK;
-#pragma unroll
-    for (uint32_t j = 0; j < FL_LOW_CHUNK / 256u; ++j) {
-        const unsigned long long site = base + j * 256u + threadIdx.x;
-        const bool is_head = site < e.n && e.hgt[site] == level;
-        const uint32_t bal = __ballot_sync(FL_FULL, is_head);
-        uint32_t off = 0u;
-        if (lane == 0 && bal) off = atomicAdd(&count, (uint32_t)__popc(bal));
-        off = __shfl_sync(FL_FULL, off, 0);
-        if (is_head) list[off + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = (uint32_t)site;
-    }
-    __syncthreads();
-    const uint32_t total = count;
-    bool changed_any = false;
-    for (uint32_t k0 = 0; k0 < total; k0 += 256u) {  // uniform trip count: whole warps stay together
-    const bool active = k0 + threadIdx.x < total;
-    const uint32_t h = active ? list[k0 + threadIdx.x] : 0u;
-#endif
-    bool changed = false, longseg = false;
-    uint32_t q = 0;
+    bool changed = false;
+    uint32_t q = h;
     FlSegStart s;
     s.root = FL_NONE; s.rt_prev = 0.0; s.z_prev = 0.0; s.e_out = 0.0; s.rt_out = 0.0;
-    if (active) {
-        const uint32_t p = e.recv[h];
-        bool ended = false;
-        q = h;
-        if (p == h) {
-            s = fl_root_site(e, h, e.tcel[h], changed);
-            q = h + 1u;
-            ended = !(q < e.n && e.recv[q] == h);
-        } else {  // the receiver's segment is strictly higher: finished by an earlier launch
-            s.root = e.root_of[p];
-            if (s.root != FL_NONE) {
-                s.rt_prev = e.rt[p];
-                s.z_prev = e.elev[p];  // the receiver already holds its NEW elevation
-                s.e_out = e.elev[s.root];
-                s.rt_out = e.rt[s.root];
+    const uint32_t p = e.recv[h];
+    bool ended = false;
+    if (p == h) {
+        s = fl_root_site(e, h, e.tcel[h], changed);
+        q = h + 1u;
+        ended = !(q < e.n && e.recv[q] == h);
+    } else {  // the receiver's segment is strictly higher: finished by an earlier launch
+        s.root = e.root_of[p];
+        if (s.root != FL_NONE) {
+            s.rt_prev = e.rt[p];
+            s.z_prev = e.elev[p];  // the receiver already holds its NEW elevation
+            s.e_out = e.elev[s.root];
+            s.rt_out = e.rt[s.root];
+        }
+    }
+    while (!ended) ended = fl_run_batch<FL_PB>(e, q, s, changed);
+    if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
+}
+#else
+// The heads of this height were listed by k_elev_plan together with their receivers; a persistent grid walks the list
+// 256 heads per block at a time.  Phase 1, one thread per head: the first batch's loads and the receiver's values are
+// requested together (three dependent round trips per head: list -> receiver + sites -> tree root), runs of up to
+// FL_PSHORT sites are finished by the thread.  Longer ones go to a list in shared memory and are walked by whole warps
+// in phase 2 -- kept apart so that the window machinery does not sit inside the thread-per-head loop.
+#ifndef FL_LOW_MINBLOCKS
+#define FL_LOW_MINBLOCKS 3  // resident blocks per SM the register allocation aims at (measured: 3 beats 2 and 4, r2k_ab.txt)
+#endif
+struct FlLongRun { uint32_t q, root; double rt_prev, z_prev, e_out, rt_out; };
+__global__ void __launch_bounds__(256, FL_LOW_MINBLOCKS) k_elev_low(FlSplit e, uint32_t level) {
+    __shared__ FlChainSmem chain_smem[8];
+    __shared__ FlLongRun longs[256];
+    __shared__ uint32_t n_long;
+    const uint32_t total = e.flags[FLQ_LOW + level];
+    const uint2* __restrict__ list = e.low_list + fl_low_region(e.n, level);
+    bool changed = false;
+    for (unsigned long long g0 = (unsigned long long)blockIdx.x * 256u; g0 < total; g0 += (unsigned long long)gridDim.x * 256u) {
+        if (threadIdx.x == 0u) n_long = 0u;
+        __syncthreads();
+        const unsigned long long k = g0 + threadIdx.x;
+        if (k < total) {
+            const uint2 hp = list[k];
+            const uint32_t h = hp.x, p = hp.y;
+            uint32_t q = h;
+            FlSegStart s;
+            s.root = FL_NONE; s.rt_prev = 0.0; s.z_prev = 0.0; s.e_out = 0.0; s.rt_out = 0.0;
+            bool ended = false;
+            if (p == h) {  // a tree root below the cut (small trees)
+                s = fl_root_site(e, h, e.tcel[h], changed);
+                q = h + 1u;
+                ended = !(q < e.n && e.recv[q] == h);
+                if (!ended) ended = fl_run_batch<FL_PB>(e, q, s, changed);
+            } else {  // the receiver's segment is strictly higher: finished by an earlier launch
+                FlBatch<FL_PB> b;
+                fl_batch_load<FL_PB>(e, q, true, b);
+                const uint32_t root_p = e.root_of[p];
+                const double rt_p = e.rt[p];    // (rt of a tree without outlet is never used)
+                const double z_p = e.elev[p];   // the receiver already holds its NEW elevation
+                s.root = root_p;
+                if (root_p != FL_NONE) {
+                    s.rt_prev = rt_p;
+                    s.z_prev = z_p;
+                    s.e_out = e.elev[root_p];
+                    s.rt_out = e.rt[root_p];
+                }
+                ended = fl_batch_compute<FL_PB>(e, q, s, changed, b);
+            }
+#pragma unroll 1
+            for (int r = 1; r < FL_PSHORT / FL_PB && !ended; ++r) ended = fl_run_batch<FL_PB>(e, q, s, changed);
+            if (!ended) {
+                FlLongRun& r = longs[atomicAdd(&n_long, 1u)];  // (at most one per thread of the block)
+                r.q = q; r.root = s.root; r.rt_prev = s.rt_prev; r.z_prev = s.z_prev; r.e_out = s.e_out; r.rt_out = s.rt_out;
             }
         }
-#pragma unroll 1
-        for (int r = 0; r < FL_PSHORT / FL_PB && !ended; ++r) ended = fl_run_batch<FL_PB>(e, q, s, changed);
-#ifdef FL_EMU
-        while (!ended) ended = fl_run_batch<FL_PB>(e, q, s, changed);
-#endif
-        longseg = !ended;
+        __syncthreads();
+        const uint32_t nl = n_long;
+        for (uint32_t j = threadIdx.x >> 5; j < nl; j += 8u) {  // phase 2: a warp per long run
+            FlSegStart w;
+            w.root = longs[j].root; w.rt_prev = longs[j].rt_prev; w.z_prev = longs[j].z_prev;
+            w.e_out = longs[j].e_out; w.rt_out = longs[j].rt_out;
+            fl_run_warp<false, 1>(e, longs[j].q, w, changed, chain_smem[threadIdx.x >> 5]);  // (rare: one window ahead is enough)
+        }
+        __syncthreads();
     }
-#ifdef FL_EMU
-    (void)longseg;
     if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
-    }
-#else
-    uint32_t todo = __ballot_sync(FL_FULL, longseg);
-    while (todo) {  // the rare long segments of the warp, one after the other, by all lanes together
-        const int src = __ffs((int)todo) - 1;
-        todo &= todo - 1u;
-        FlSegStart w;
-        w.root = __shfl_sync(FL_FULL, s.root, src);
-        w.rt_prev = fl_shfl(s.rt_prev, src);
-        w.z_prev = fl_shfl(s.z_prev, src);
-        w.e_out = fl_shfl(s.e_out, src);
-        w.rt_out = fl_shfl(s.rt_out, src);
-        const uint32_t q_s = __shfl_sync(FL_FULL, q, src);
-        bool ch = false;
-        fl_run_warp<false, 1>(e, q_s, w, ch, chain_smem[threadIdx.x >> 5]);  // (rare: one window ahead is enough)
-        changed |= ch;
-    }
-    changed_any |= changed;
-    }
-    if (changed_any) e.flags[FL_FLAG_CHANGED] = 1u;
-#endif
 }
+#endif

@@ -287,23 +287,60 @@ __device__ __forceinline__ uint32_t fl_gather_store(const FlFlow& f, uint32_t p,
 // opaque zero that orders the next climb's loads after the deciding atomic.  `fenced`: the caller has already
 // fenced its stores.  The static data of p (counts, row, child mask) is requested right behind the atomic so
 // that the round trips overlap.
+// Ordering (FL_ATOMIC_ORDERING, the default): the two deciding atomics are themselves the release / acquire
+// operations -- atom.acq_rel.gpu = MEMBAR.ALL.GPU ; ATOMG ; CCTL.IVALL in SASS, i.e. ONE memory barrier per atomic
+// (release side) and an L1 invalidation (acquire side).  The fence form, fence.acq_rel.gpu before and after a relaxed
+// atomic, is the same thing to the memory model but costs two barriers per atomic: ncu put 25 % of the warp kernel's
+// stall samples on those MEMBARs (profiles/r2i_src_k_area_flow_long.txt).  -DFL_ATOMIC_ORDERING=0 builds the fence form.
+#ifndef FL_ATOMIC_ORDERING
+#define FL_ATOMIC_ORDERING 1
+#endif
+#if defined(FL_EMU) || !FL_ATOMIC_ORDERING || FL_RELAXED_READERS
+#define FL_QUALIFIED_ATOMICS 0
+#else
+#define FL_QUALIFIED_ATOMICS 1
+__device__ __forceinline__ uint32_t fl_atom_add_acq_rel(uint32_t* p, uint32_t v) {
+    uint32_t o;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory");
+    return o;
+}
+__device__ __forceinline__ uint32_t fl_atom_add_acquire(uint32_t* p, uint32_t v) {
+    uint32_t o;
+    asm volatile("atom.acquire.gpu.global.add.u32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory");
+    return o;
+}
+#endif
 __device__ __forceinline__ uint32_t fl_report(const FlFlow& f, uint32_t h, uint32_t p, bool fenced, uint32_t* dep_out) {
     (void)h;
+#if FL_QUALIFIED_ATOMICS
+    // release: publishes A[h], hgt[h] (and, by cumulativity, what the caller's warp stored before its __syncwarp());
+    // acquire: the last reporter sees the other reporters' A / hgt
+    const uint32_t prev = fenced ? fl_atom_add_acquire(&f.state[p], 1u) : fl_atom_add_acq_rel(&f.state[p], 1u);
+#else
     if (!fenced) fl_fence_release();  // publish A[h], hgt[h] (and, by cumulativity, what the caller's warp stored
                                       // before its __syncwarp())
     const uint32_t prev = atomicAdd(&f.state[p], 1u);
+#endif
     const uint32_t nw = f.nwait[p] & FL_NW_COUNT;
     const uint32_t sh = f.seg_head[p];
     const bool p_has_chain = (p + 1u < f.n) && (f.recv[p + 1u] == p);
     if ((prev & FL_ST_COUNT_MASK) + 1u < nw) return FL_NONE;
     // last reporter at p: gather and publish p's partial sums
     const uint32_t swait = f.seg_wait[sh];
+#if FL_QUALIFIED_ATOMICS
+    f.state[p] = fl_gather_store(f, p, p_has_chain, 0u);  // no report can follow the last one: a plain store
+    // release: the partial sums are published before the segment counter moves; acquire: the last publisher sees the
+    // other publishers' partial sums
+    const uint32_t done = fl_atom_add_acq_rel(&f.seg_done[sh], 1u) + 1u;
+    if (done < swait) return FL_NONE;
+#else
     fl_fence_acquire();  // the other reporters' A / hgt: acquire side of their fence + atomic on state[p]
     f.state[p] = fl_gather_store(f, p, p_has_chain, fl_dep0(prev));  // no report can follow the last one: a plain store
     fl_fence_release();  // publish the partial sums before the segment counter moves
     const uint32_t done = atomicAdd(&f.seg_done[sh], 1u) + 1u;
     if (done < swait) return FL_NONE;
     fl_fence_acquire();  // the other publishers' partial sums: acquire side of their fence + atomic on seg_done[sh]
+#endif
     *dep_out = fl_dep0(done);
     return fl_seg_start(f, sh);  // every waiting site of the segment is published: climb it
 }
@@ -509,6 +546,10 @@ __device__ __forceinline__ FlWin fl_win_load(const FlFlow& f, uint32_t base, int
 }
 
 #define FL_WDEPTH 3  // windows kept in flight on a long chain
+#ifndef FL_XPOST_PREFETCH
+#define FL_XPOST_PREFETCH 0  // build-time A/B switch (tools/ab_build.py): xpost of the next window requested one window
+                             // ahead -- measured SLOWER (K4 0.319 vs 0.300 ms per iteration at 1M sites, profiles/r2j_ab.txt)
+#endif
 
 __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t hrun, bool has_chain, FlAreaSmem& sm) {
     const int lane = threadIdx.x & 31;
@@ -517,6 +558,10 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
     uint32_t nring = 0;
 #pragma unroll
     for (int j = 0; j < FL_WDEPTH; ++j) { ring[j].cm = 0u; ring[j].rc = FL_NONE; ring[j].st = 0u; ring[j].ar = 0.0; ring[j].pre = 0.0; ring[j].p1 = 0.0; ring[j].p2 = 0.0; }
+    double xnext[FL_XPOST];  // xpost of the window after the current one (valid while the chain goes on)
+    bool xnext_valid = false;
+#pragma unroll
+    for (int j = 0; j < FL_XPOST; ++j) xnext[j] = 0.0;
     for (;;) {
         const long long t_win = FL_CLOCK();
         const bool first_win = nring == 0u;
@@ -564,19 +609,33 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
         bool slow = false;
         double xv[FL_XPOST];
 #pragma unroll
-        for (int j = 0; j < FL_XPOST; ++j) xv[j] = 0.0;
+        for (int j = 0; j < FL_XPOST; ++j) xv[j] = xnext[j];  // (requested while the previous window was climbed)
         if (inwin) {
             nterm = 1u;
             if (lit) {
                 if (npk == 15u) slow = true;
                 else {
                     nterm += npk;
-                    if (npk > 2u) {
+                    if (npk > 2u && !xnext_valid) {
 #pragma unroll
                         for (int j = 0; j < FL_XPOST; ++j)
                             if ((uint32_t)j + 2u < npk) xv[j] = fl_ld_cg(&f.xpost[(size_t)idx * FL_XPOST + j]);
                     }
                 }
+            }
+        }
+        // The 3rd.. children of the NEXT window's sites: requested now, used one window later.  Every site of a segment
+        // is published before its climb starts, so what the ring holds of the next window is final.
+        xnext_valid = false;
+        if (FL_XPOST_PREFETCH && goes_on && nring >= 2u) {
+            xnext_valid = true;
+            const long long li1 = (long long)cur - 32 - lane;
+            const uint32_t st1 = ring[1].st, np1 = fl_st_np(st1);
+#pragma unroll
+            for (int j = 0; j < FL_XPOST; ++j) {
+                xnext[j] = 0.0;
+                if (li1 >= 0 && (st1 & FL_ST_PRE_READY) && np1 != 15u && (uint32_t)j + 2u < np1)
+                    xnext[j] = fl_ld_cg(&f.xpost[(size_t)li1 * FL_XPOST + j]);
             }
         }
         const uint32_t slowmask = __ballot_sync(FL_FULL, slow);

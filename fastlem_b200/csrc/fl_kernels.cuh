@@ -16,7 +16,8 @@ enum { FL_FLAG_LAKE = 0, FL_FLAG_CHANGED = 1, FL_FLAG_JUMP = 2, FL_FLAG_MAXDEPTH
        FL_FLAG_NCHG = 8 /* receivers changed by K1 */, FL_FLAG_NREGATHER = 9, FL_FLAG_NDIRTY = 10 /* incremental K4 lists */,
        FL_FLAG_TICKET = 11 /* fused K5 launch */, FL_FLAG_K4MAXH = 12 /* largest nesting height met by K4 */,
        FL_FLAG_NROOTS = 13 /* fused incremental K4: dirty tree roots still to finish */,
-       FL_N_FLAGS = 160 /* 24..55: level histogram, 64 / 96 / 128: queue counters of the split K5 sweep (fl_elev.cuh) */ };
+       FL_N_FLAGS = 192 /* 24..55: level histogram, 64 / 96 / 128: queue counters, 160..167: heads per height below the cut
+                           (split K5 sweep, fl_elev.cuh) */ };
 
 #define FL_TID (blockIdx.x * blockDim.x + threadIdx.x)
 

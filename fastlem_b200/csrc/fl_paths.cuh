@@ -154,7 +154,14 @@ __global__ void FL_K1_BOUNDS k_receivers_mask(uint32_t n, const uint32_t* __rest
 #define FL_K1B_ROWS 256u
 #define FL_K1B_CAP 2048u
 #define FL_K1B_GATHER 8
-#define FL_K1B_STAGE_BYTES (FL_K1B_CAP * 12u)
+// one stage: dist | col | rev of the tile's span, then the tile's own rows: row_ptr (257 used), elev, is_outlet, recv_prev
+#define FL_K1B_OFF_COL (FL_K1B_CAP * 8u)
+#define FL_K1B_OFF_REV (FL_K1B_OFF_COL + FL_K1B_CAP * 4u)
+#define FL_K1B_OFF_ROWP (FL_K1B_OFF_REV + FL_K1B_CAP)
+#define FL_K1B_OFF_ELEV (FL_K1B_OFF_ROWP + 272u * 4u)
+#define FL_K1B_OFF_OUTLET (FL_K1B_OFF_ELEV + FL_K1B_ROWS * 8u)
+#define FL_K1B_OFF_PREV (FL_K1B_OFF_OUTLET + FL_K1B_ROWS)
+#define FL_K1B_STAGE_BYTES (FL_K1B_OFF_PREV + FL_K1B_ROWS * 4u)
 #define FL_K1B_SMEM (2u * FL_K1B_STAGE_BYTES + 64u)
 
 __device__ __forceinline__ uint32_t fl_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -163,9 +170,6 @@ __device__ __forceinline__ void fl_mbar_init(void* bar, uint32_t count) {
 }
 __device__ __forceinline__ void fl_mbar_expect_tx(void* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fl_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void fl_mbar_arrive(void* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fl_smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fl_mbar_wait(void* bar, uint32_t parity) {
     asm volatile(
@@ -196,9 +200,8 @@ __global__ void __launch_bounds__(256) k_receivers_bulk(uint32_t n, uint32_t n_t
                                                          uint32_t* __restrict__ chg_node,
                                                          uint32_t* __restrict__ chg_old) {
     extern __shared__ __align__(128) unsigned char k1b_smem[];
-    // stage s: dist at s * STAGE_BYTES (CAP doubles), col right behind it (CAP words); then 2 barriers, 2 x (start, ok)
     unsigned long long* bars = (unsigned long long*)(k1b_smem + 2u * FL_K1B_STAGE_BYTES);
-    uint32_t* meta = (uint32_t*)(k1b_smem + 2u * FL_K1B_STAGE_BYTES + 16u);
+    uint32_t* meta = (uint32_t*)(k1b_smem + 2u * FL_K1B_STAGE_BYTES + 16u);  // per stage: span start, span staged?
     const uint32_t tid = threadIdx.x;
     if (tid == 0u) {
         fl_mbar_init(&bars[0], 1u);
@@ -214,98 +217,105 @@ __global__ void __launch_bounds__(256) k_receivers_bulk(uint32_t n, uint32_t n_t
         nb = row_ptr[t0];
         ne = row_ptr[t1];
     };
-    auto issue = [&](uint32_t stage) {  // spans [nb, ne) -> stage; start aligned down to 16 slots (16 B for every array)
+    // everything a tile reads except the neighbours' elevations, by the copy engine: its own rows (row_ptr, elev,
+    // is_outlet, previous receivers) and its CSR span [nb, ne), the span's start aligned down to 16 slots (16 bytes in
+    // every array).  Sizes are multiples of 16 bytes; what they read beyond the tile lies inside the same allocation.
+    auto issue = [&](uint32_t tile, uint32_t stage) {
+        const unsigned long long t0 = (unsigned long long)tile * FL_K1B_ROWS;
+        const uint32_t rows = (uint32_t)(t0 + FL_K1B_ROWS < n ? FL_K1B_ROWS : n - t0);
         const uint32_t start = nb & ~15u;
         const uint32_t cnt = (ne - start + 15u) & ~15u;
         const bool ok = cnt > 0u && cnt <= FL_K1B_CAP;
         meta[2u * stage] = start;
         meta[2u * stage + 1u] = ok ? 1u : 0u;
         unsigned char* base = k1b_smem + stage * FL_K1B_STAGE_BYTES;
+        const uint32_t b_rowp = ((rows + 1u) * 4u + 15u) & ~15u, b_elev = (rows * 8u + 15u) & ~15u,
+                       b_out = (rows + 15u) & ~15u, b_prev = (rows * 4u + 15u) & ~15u;
+        fl_mbar_expect_tx(&bars[stage], b_rowp + b_elev + b_out + (chg_node ? b_prev : 0u) + (ok ? cnt * 13u : 0u));
+        fl_bulk_g2s(base + FL_K1B_OFF_ROWP, row_ptr + t0, b_rowp, &bars[stage]);
+        fl_bulk_g2s(base + FL_K1B_OFF_ELEV, elev + t0, b_elev, &bars[stage]);
+        fl_bulk_g2s(base + FL_K1B_OFF_OUTLET, is_outlet + t0, b_out, &bars[stage]);
+        if (chg_node) fl_bulk_g2s(base + FL_K1B_OFF_PREV, recv_prev + t0, b_prev, &bars[stage]);
         if (ok) {
-            fl_mbar_expect_tx(&bars[stage], cnt * 12u);
             fl_bulk_g2s(base, dist + start, cnt * 8u, &bars[stage]);
-            fl_bulk_g2s(base + FL_K1B_CAP * 8u, col + start, cnt * 4u, &bars[stage]);
-        } else {
-            fl_mbar_arrive(&bars[stage]);
+            fl_bulk_g2s(base + FL_K1B_OFF_COL, col + start, cnt * 4u, &bars[stage]);
+            fl_bulk_g2s(base + FL_K1B_OFF_REV, rev + start, cnt, &bars[stage]);
         }
     };
     uint32_t tile = blockIdx.x;
     if (tid == 0u && tile < n_tiles) {
         bounds(tile);
-        issue(0u);
+        issue(tile, 0u);
         if (tile + gridDim.x < n_tiles) bounds(tile + gridDim.x);
     }
     uint32_t parity0 = 0u, parity1 = 0u, stage = 0u;
     bool lake = false;
     for (; tile < n_tiles; tile += gridDim.x, stage ^= 1u) {
         if (tid == 0u && tile + gridDim.x < n_tiles) {  // (the other stage was released by the barrier that ended the previous tile)
-            issue(stage ^ 1u);
+            issue(tile + gridDim.x, stage ^ 1u);
             const unsigned long long after = (unsigned long long)tile + 2ull * gridDim.x;
             if (after < n_tiles) bounds((uint32_t)after);
         }
         const unsigned long long i64 = (unsigned long long)tile * FL_K1B_ROWS + tid;
         const bool active = i64 < n;
         const uint32_t i = (uint32_t)i64;
-        uint32_t s0 = 0u, s1 = 0u, old = 0u;
-        bool outlet = true;
-        double ei = 0.0;
-        if (active) {
-            s0 = row_ptr[i];
-            s1 = row_ptr[i + 1u];
-            outlet = is_outlet[i] != 0;
-            ei = elev[i];
-            if (chg_node) old = recv_prev[i];
-        }
         fl_mbar_wait(&bars[stage], stage ? parity1 : parity0);
         if (stage) parity1 ^= 1u; else parity0 ^= 1u;
+        const unsigned char* base = k1b_smem + stage * FL_K1B_STAGE_BYTES;
         const uint32_t start = meta[2u * stage];
         const bool staged = meta[2u * stage + 1u] != 0u;
-        uint32_t best = i, best_s = FL_NONE;
+        uint32_t best = i, best_s = FL_NONE, best_r = 0xFFu;
         double best_d = 1.0;
-        if (active && !outlet) {
-            const double* sd = (const double*)(k1b_smem + stage * FL_K1B_STAGE_BYTES) + (s0 - start);
-            const uint32_t* sc = (const uint32_t*)(k1b_smem + stage * FL_K1B_STAGE_BYTES + FL_K1B_CAP * 8u) + (s0 - start);
-            const uint32_t deg = s1 - s0;
-            double steepest = 0.0;
-            for (uint32_t sb = 0u; sb < deg; sb += (uint32_t)FL_K1B_GATHER) {
-                uint32_t j[FL_K1B_GATHER];
-                double ej[FL_K1B_GATHER];
+        if (active) {
+            const uint32_t s0 = ((const uint32_t*)(base + FL_K1B_OFF_ROWP))[tid];
+            const uint32_t s1 = ((const uint32_t*)(base + FL_K1B_OFF_ROWP))[tid + 1u];
+            const bool outlet = (base + FL_K1B_OFF_OUTLET)[tid] != 0;
+            const double ei = ((const double*)(base + FL_K1B_OFF_ELEV))[tid];
+            if (!outlet) {
+                const double* sd = (const double*)base + (s0 - start);
+                const uint32_t* sc = (const uint32_t*)(base + FL_K1B_OFF_COL) + (s0 - start);
+                const uint32_t deg = s1 - s0;
+                double steepest = 0.0;
+                for (uint32_t sb = 0u; sb < deg; sb += (uint32_t)FL_K1B_GATHER) {
+                    uint32_t j[FL_K1B_GATHER];
+                    double ej[FL_K1B_GATHER];
 #pragma unroll
-                for (int k = 0; k < FL_K1B_GATHER; ++k) {
-                    const uint32_t o = sb + (uint32_t)k;
-                    j[k] = o < deg ? (staged ? sc[o] : col[s0 + o]) : i;  // padding: the site itself (never lower than itself)
-                }
-#pragma unroll
-                for (int k = 0; k < FL_K1B_GATHER; ++k) ej[k] = elev[j[k]];
-#pragma unroll
-                for (int k = 0; k < FL_K1B_GATHER; ++k) {
-                    if (ei > ej[k]) {
+                    for (int k = 0; k < FL_K1B_GATHER; ++k) {
                         const uint32_t o = sb + (uint32_t)k;
-                        const double d = staged ? sd[o] : dist[s0 + o];
-                        const double slope = (ei - ej[k]) / d;
-                        if (slope > steepest) {
-                            steepest = slope;
-                            best = j[k];
-                            best_d = d;
-                            best_s = s0 + o;
+                        j[k] = o < deg ? (staged ? sc[o] : col[s0 + o]) : i;
+                    }
+#pragma unroll
+                    for (int k = 0; k < FL_K1B_GATHER; ++k)  // all gathers of the row in flight together
+                        ej[k] = (sb + (uint32_t)k < deg) ? elev[j[k]] : ei;  // padding: never lower than the site itself
+#pragma unroll
+                    for (int k = 0; k < FL_K1B_GATHER; ++k) {
+                        if (ei > ej[k]) {
+                            const uint32_t o = sb + (uint32_t)k;
+                            const double d = staged ? sd[o] : dist[s0 + o];
+                            const double slope = (ei - ej[k]) / d;
+                            if (slope > steepest) {
+                                steepest = slope;
+                                best = j[k];
+                                best_d = d;
+                                best_s = s0 + o;
+                            }
                         }
                     }
                 }
+                if (best == i) lake = true;
+                else best_r = staged ? (base + FL_K1B_OFF_REV)[best_s - start] : rev[best_s];
             }
-            if (best == i) lake = true;
-        }
-        if (active) {
-            if (chg_node && old != best) {  // incremental K4: sites whose receiver differs from the previous iteration's
-                const uint32_t k = atomicAdd(&flags[FL_FLAG_NCHG], 1u);
-                chg_node[k] = i;
-                chg_old[k] = old;
+            if (chg_node) {  // incremental K4: sites whose receiver differs from the previous iteration's
+                const uint32_t old = ((const uint32_t*)(base + FL_K1B_OFF_PREV))[tid];
+                if (old != best) {
+                    const uint32_t k = atomicAdd(&flags[FL_FLAG_NCHG], 1u);
+                    chg_node[k] = i;
+                    chg_old[k] = old;
+                }
             }
             recv[i] = best;
             drecv[i] = best_d;
-            if (best_s != FL_NONE) {
-                const uint32_t r = rev[best_s];
-                if (r < 32u) atomicOr(&cmask[best], 1u << r);
-            }
+            if (best_r < 32u) atomicOr(&cmask[best], 1u << best_r);
         }
         __syncthreads();  // every read of this stage is done: it may be refilled
     }

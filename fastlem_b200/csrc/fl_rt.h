@@ -36,6 +36,8 @@ struct fl_dim3 {
 typedef fl_dim3 dim3;
 extern thread_local fl_dim3 threadIdx, blockIdx, blockDim, gridDim;
 
+struct uint2 { unsigned x, y; };
+inline uint2 make_uint2(unsigned x, unsigned y) { uint2 v; v.x = x; v.y = y; return v; }
 typedef int cudaStream_t;
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };

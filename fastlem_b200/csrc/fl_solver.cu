@@ -135,6 +135,8 @@ struct fastlem_ctx {
     int64_t opt_fuse_k4 = 0;     // measured no faster than two launches: kept as an option
     int64_t opt_first_flow = 1;  // the first iteration also uses the dataflow sweeps (layout by subtree sizes)
     // K5 split by nesting height (fl_elev.cuh): queue of run starts for the top of the forest, push masks
+    uint2* d_low_list = nullptr;     // K5: (head, receiver) pairs per height below the cut (k_elev_plan -> k_elev_low)
+    int low_blocks = 0;              // resident blocks of k_elev_low
     FlQEntry* d_queue = nullptr;   // n entries
     uint32_t* d_pmask = nullptr;   // zero between sweeps (k_elev_top clears what k_elev_plan sets)
     uint32_t push_epoch = 0;
@@ -1054,9 +1056,14 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool may_continue, bool* changed_o
         e.is_outlet = L.is_outlet; e.hgt = c->d_hgt; e.drecv = L.drecv; e.erod = L.erod; e.A = c->d_A;
         e.uplift = L.uplift; e.tan_slope = c->has_tan ? L.tan : nullptr; e.tcel = c->d_tcel; e.elev = L.elev; e.rt = c->d_rt;
         e.root_of = c->d_root_of; e.pmask = c->d_pmask; e.queue = c->d_queue; e.epoch = ++c->push_epoch; e.cut = cut;
-        e.flags = c->d_flags;
+        e.flags = c->d_flags; e.low_list = c->d_low_list;
         FL_RC(k_begin(c));
+#ifdef FL_EMU
         LAUNCH_N(k_elev_plan, n, e);
+#else
+        FL_LAUNCH(k_elev_plan, (n + FL_LOW_CHUNK - 1u) / FL_LOW_CHUNK, 256, c->stream, e);
+        c->stats.kernel_launches++;
+#endif
         FL_RC(k_end(c, FASTLEM_K_ELEV_PLAN));
         FL_RC(k_begin(c));
 #ifdef FL_EMU
@@ -1075,7 +1082,11 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool may_continue, bool* changed_o
 #ifdef FL_EMU
             LAUNCH_N(k_elev_low, n, e, lv);
 #else
-            FL_LAUNCH(k_elev_low, (n + FL_LOW_CHUNK - 1u) / FL_LOW_CHUNK, 256, c->stream, e, lv);
+            {   // persistent grid over the height's list; never more blocks than the list can have groups of 256 heads
+                const size_t most = ((size_t)n / (lv + 1u) + 256u) / 256u;
+                const unsigned blocks = (unsigned)(most < (size_t)c->low_blocks ? most : (size_t)c->low_blocks);
+                FL_LAUNCH(k_elev_low, blocks, 256, c->stream, e, lv);
+            }
             c->stats.kernel_launches++;
 #endif
             FL_RC(k_end(c, FASTLEM_K_ELEV_LOW));
@@ -1365,6 +1376,7 @@ int alloc_graph_buffers(fastlem_ctx* c, uint32_t n, uint32_t nnz) {
     FL_CK(dalloc(c, c->d_sg_wait, n));
     FL_CK(dalloc(c, c->d_sg_done, n));
     FL_CK(dalloc(c, c->d_ready, (size_t)n + 65536));
+    FL_CK(dalloc(c, c->d_low_list, fl_low_region(n, FL_CUT_MAX)));
     FL_CK(dalloc(c, c->d_queue, n));
     FL_CK(dalloc(c, c->d_pmask, n));
     FL_CK(dalloc(c, c->d_ticket_of, n));
@@ -1570,6 +1582,17 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     FL_CK(fl_d2h(c->h_flags, c->d_flags, sizeof(uint32_t), c->stream));
     FL_CK(fl_memset(c->d_ready, 0, sizeof(uint32_t) * ((size_t)n + 65536), c->stream));
     FL_CK(fl_memset(c->d_queue, 0, sizeof(FlQEntry) * n, c->stream));
+    FL_CK(fl_memset(c->d_rt, 0, sizeof(double) * n, c->stream));  // (read, never used, for sites of trees without outlet)
+    // the climbs of K4 request a batch's / a window's partial sums before they know which of its sites have any: sites that
+    // never publish are read (and ignored) too -- defined values keep compute-sanitizer's initcheck clean
+    FL_CK(fl_memset(c->d_pre, 0, sizeof(double) * n, c->stream));
+    FL_CK(fl_memset(c->d_post1, 0, sizeof(double) * n, c->stream));
+    FL_CK(fl_memset(c->d_post2, 0, sizeof(double) * n, c->stream));
+    FL_CK(fl_memset(c->d_xpost, 0, sizeof(double) * n * FL_XPOST, c->stream));
+    FL_CK(fl_memset(c->d_xbuf, 0, sizeof(double) * n, c->stream));
+    FL_CK(fl_memset(c->d_hbuf, 0, sizeof(uint32_t) * n, c->stream));
+    FL_CK(fl_memset(c->d_hpre, 0, sizeof(uint32_t) * n, c->stream));
+    FL_CK(fl_memset(c->d_hsuf, 0, sizeof(uint32_t) * n, c->stream));
     c->push_epoch = 0;
 #ifndef FL_EMU
     {
@@ -1584,6 +1607,11 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
         int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_incr_flow, 256, 0) == cudaSuccess && occ > 0)
             c->incr_flow_blocks = occ * fl_sm_count();
+    }
+    {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elev_low, 256, 0) != cudaSuccess || occ < 1) occ = 1;
+        c->low_blocks = occ * fl_sm_count();
     }
     {
         int occ = 0;

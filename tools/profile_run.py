@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--max-slope", type=float, default=None)
     ap.add_argument("--park-after", type=int, default=None)
     ap.add_argument("--brief", action="store_true")
+    ap.add_argument("--lib", default=None, help="path of a variant build of the library (tools/ab_build.py)")
     ap.add_argument("--opt", action="append", default=[], help="solver option name=value (repeatable)")
     args = ap.parse_args()
     cache = f"/tmp/fl_workload_{args.sites}_{int(args.lattice)}.npz"
@@ -44,7 +45,7 @@ def main():
     p = W.uniform_params(n)
     initial = _native.host_initial_elevations(p["base"])
     tan = None if args.max_slope is None else np.full(n, np.tan(args.max_slope))
-    with _native.Context(0) as ctx:
+    with _native.Context(0, args.lib) as ctx:
         ctx.set_option("profile", 1)
         if args.sweep is not None:
             ctx.set_option("sweep", args.sweep)
@@ -68,7 +69,7 @@ def main():
             st["ms_per_iter"] = 1e3 * dt / max(it, 1)
             if args.brief:
                 it_ = max(it, 1)
-                print(f"sites={n} opts={args.opt} incr={st['incremental_iterations']} iters={it} ms/iter={st['ms_per_iter']:.3f} K1={st['ms_receivers']/it_:.3f} "
+                print(f"{os.path.basename(args.lib) + ' ' if args.lib else ''}sites={n} opts={args.opt} incr={st['incremental_iterations']} iters={it} ms/iter={st['ms_per_iter']:.3f} K1={st['ms_receivers']/it_:.3f} "
                       f"order={st['ms_order']/it_:.3f} K4={st['ms_area']/it_:.3f} K5={st['ms_elevation']/it_:.3f} rebuilds={st['rebuilds']} "
                       f"levels={st['path_levels']} segs={st['paths']}")
             else:
