@@ -163,8 +163,9 @@ class TerrainModel2D:
 
     def create_terrain_from_result(self, elevations, device=0, lib_path=None):  # model.rs:62-68
         sites = self._sites.copy()
-        return Terrain2D(sites, np.array(elevations, dtype=np.float64, copy=True),
-                         TerrainInterpolator2D(sites, self._triangulation, device, lib_path))
+        own = np.array(elevations, dtype=np.float64, copy=True)
+        own.setflags(write=False)  # (the reference's Terrain2D owns its elevations; the interpolator caches the upload)
+        return Terrain2D(sites, own, TerrainInterpolator2D(sites, self._triangulation, device, lib_path))
 
 
 class TerrainInterpolator2D:
@@ -178,6 +179,7 @@ class TerrainInterpolator2D:
         self._device, self._lib_path = device, lib_path
         self._native = None
         self._values_of = None
+        self._has_nan = False
 
     @classmethod
     def new(cls, sites):
@@ -190,14 +192,29 @@ class TerrainInterpolator2D:
                 self._triangulation = _tr.delaunay(self._sites)
             tri, he = self._triangulation
             self._native = _native.Interpolator(self._sites, tri, he, self._device, self._lib_path)
-        if self._values_of is not elevations:
+        # The reference reads the slice on every call.  The uploaded copy is reused only for an array that cannot have
+        # changed in between: the same object, not writeable (Terrain2D's own elevations are made read-only).
+        e = np.asarray(elevations)
+        if self._values_of is not elevations or e.flags.writeable:
             self._native.set_values(elevations)
             self._values_of = elevations
+            self._has_nan = bool(np.isnan(e).any())
         return self._native
 
+    def _inside_hull(self, points_xy):
+        """True where the reference returns Some(..): the same query over a constant field (NaN only outside the hull)."""
+        h = self._native
+        h.set_values(np.ones(self._sites.shape[0]))
+        inside = ~np.isnan(h.points(points_xy))
+        self._values_of = None  # the next query uploads its elevations again
+        return inside
+
     def interpolate(self, elevations, site):  # interpolator.rs:17-27
-        z = self._handle(elevations).points(np.array([[site.x, site.y]], dtype=np.float64))[0]
-        return None if z != z else float(z)
+        xy = np.array([[site.x, site.y]], dtype=np.float64)
+        z = self._handle(elevations).points(xy)[0]
+        if z != z:  # None outside the hull -- or Some(NaN) when the elevations themselves hold a NaN
+            return float(z) if self._has_nan and self._inside_hull(xy)[0] else None
+        return float(z)
 
     def interpolate_many(self, elevations, points_xy):
         """One call for many sites: (k, 2) array -> k values, NaN where the reference returns None."""

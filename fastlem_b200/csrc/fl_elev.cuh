@@ -83,7 +83,9 @@ struct FlSplit {
     // most n / (l + 1) heads of height l: the lists lie behind each other in low_list at fl_low_region(n, l).
     uint2* low_list;
 };
-#define FL_LOW_CHUNK 2048u  // positions per block of k_elev_plan
+#ifndef FL_LOW_CHUNK
+#define FL_LOW_CHUNK 512u  // positions per block of k_elev_plan (build-time A/B switch; 512 measured best at 1M sites, no difference at 16M: profiles/r2n_ab.txt)
+#endif
 __host__ __device__ inline size_t fl_low_region(uint32_t n, uint32_t level) {
     size_t at = 0;
     for (uint32_t l = 0; l < level; ++l) at += (size_t)n / (l + 1u) + 1u;
@@ -230,99 +232,119 @@ __device__ __forceinline__ FlSegStart fl_root_site(const FlSplit& e, uint32_t h,
 // ------------------------------------------------------------------------------------------------
 // plan: histogram, push masks, the roots of the top trees
 // ------------------------------------------------------------------------------------------------
-// one site of the plan pass; returns its nesting height if it heads a segment (FL_NONE otherwise)
-template <class H>
-__device__ __forceinline__ uint32_t fl_plan_site(const FlSplit& e, uint32_t q, bool& changed, H&& count_head) {
-    const double tq = fl_celerity_term(e, q, e.drecv[q]);  // (fully parallel: the division and the square root stay
-    e.tcel[q] = tq;                                        //  out of the serial chains)
-    const uint32_t h = e.hgt[q];
-    if (h == FL_NONE) return FL_NONE;  // q does not head a segment
-    count_head(h < 31u ? h : 31u);
-    if (h >= e.cut) {
-        const uint32_t p = e.recv[q];
-        if (p == q) {
-            // a top tree: the root site itself, then the run behind it and its top children as queue entries
-            const FlSegStart s = fl_root_site(e, q, tq, changed);
-            const bool chain = (q + 1u < e.n) && (e.recv[q + 1u] == q);
-            if (chain) flq_put(e, atomicAdd(&e.flags[FLQ_TAIL], 1u), q + 1u, s.root, s.rt_prev, s.z_prev, false);
-            const uint32_t s0 = e.row_ptr[q];
-            uint32_t m = e.cmask[q];
-            while (m) {
-                const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
-                m &= m - 1u;
-                const uint32_t c = e.col[s0 + b];
-                if (chain && c == q + 1u) continue;
-                const uint32_t hc = e.hgt[c];
-                if (hc != FL_NONE && hc >= e.cut)
-                    flq_put(e, atomicAdd(&e.flags[FLQ_TAIL], 1u), c, s.root, s.rt_prev, s.z_prev, false);
-            }
-        } else if (e.recv[p] != p) {  // (a root pushes its own top children, above)
-            uint32_t bit = 32u;
-            for (uint32_t sl = e.row_ptr[q]; sl < e.row_ptr[q + 1u]; ++sl)
-                if (e.col[sl] == p) { bit = e.rev[sl]; break; }
-            if (bit < 32u) atomicOr(&e.pmask[p], 1u << bit);
-            else atomicOr(&e.flags[FL_FLAG_BROKEN], 16u);
+// a head q of height h >= cut (receiver p, celerity term tq) in the plan pass: a root is computed here and seeds the
+// queue with the run behind it and its top children; any other head registers in its receiver's push mask
+__device__ __forceinline__ void fl_plan_top_head(const FlSplit& e, uint32_t q, uint32_t p, double tq, bool& changed) {
+    if (p == q) {
+        // a top tree: the root site itself, then the run behind it and its top children as queue entries
+        const FlSegStart s = fl_root_site(e, q, tq, changed);
+        const bool chain = (q + 1u < e.n) && (e.recv[q + 1u] == q);
+        if (chain) flq_put(e, atomicAdd(&e.flags[FLQ_TAIL], 1u), q + 1u, s.root, s.rt_prev, s.z_prev, false);
+        const uint32_t s0 = e.row_ptr[q];
+        uint32_t m = e.cmask[q];
+        while (m) {
+            const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+            m &= m - 1u;
+            const uint32_t c = e.col[s0 + b];
+            if (chain && c == q + 1u) continue;
+            const uint32_t hc = e.hgt[c];
+            if (hc != FL_NONE && hc >= e.cut)
+                flq_put(e, atomicAdd(&e.flags[FLQ_TAIL], 1u), c, s.root, s.rt_prev, s.z_prev, false);
         }
+    } else if (e.recv[p] != p) {  // (a root pushes its own top children, above)
+        uint32_t bit = 32u;
+        for (uint32_t sl = e.row_ptr[q]; sl < e.row_ptr[q + 1u]; ++sl)
+            if (e.col[sl] == p) { bit = e.rev[sl]; break; }
+        if (bit < 32u) atomicOr(&e.pmask[p], 1u << bit);
+        else atomicOr(&e.flags[FL_FLAG_BROKEN], 16u);
     }
-    return h;
 }
 
 #ifdef FL_EMU
 __global__ void __launch_bounds__(256) k_elev_plan(FlSplit e) {
     const uint32_t q = FL_TID;
+    if (q >= e.n) return;
     bool changed = false;
-    if (q < e.n) fl_plan_site(e, q, changed, [&](uint32_t bin) { atomicAdd(&e.flags[FLQ_HIST + bin], 1u); });
+    const double tq = fl_celerity_term(e, q, e.drecv[q]);  // (fully parallel: the division and the square root stay
+    e.tcel[q] = tq;                                        //  out of the serial chains)
+    const uint32_t h = e.hgt[q];
+    if (h != FL_NONE) {  // q heads a segment
+        atomicAdd(&e.flags[FLQ_HIST + (h < 31u ? h : 31u)], 1u);
+        if (h >= e.cut) fl_plan_top_head(e, q, e.recv[q], tq, changed);
+    }
     if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
 }
 #else
-// One block per chunk of FL_LOW_CHUNK positions.  Besides the per-site work, the block appends its heads below the
-// cut to the per-height lists (one reservation per block and height; position order inside a warp's 32 positions), so
-// that the per-height launches of k_elev_low neither scan the heights again nor run half-empty warps -- the sparse
-// heights above 0 would otherwise leave a handful of active threads per block.
+// One block per chunk of FL_LOW_CHUNK positions, FL_PLAN_PER_THREAD per thread.  All loads of a thread's sites go out
+// first; then the celerity terms (the division and the square root stay out of the serial chains), the rare heads at or
+// above the cut, and finally the heads below the cut are appended to the per-height lists: per warp one ballot per
+// height (position order inside a warp's 32 positions), per block ONE reservation per height in the global list -- so
+// the per-height launches of k_elev_low neither scan the heights again nor run half-empty warps.
+#define FL_PLAN_PER_THREAD (FL_LOW_CHUNK / 256u)
 __global__ void __launch_bounds__(256) k_elev_plan(FlSplit e) {
     __shared__ uint32_t hist[32];
     __shared__ uint32_t lcount[FL_CUT_MAX];
-    __shared__ uint32_t lbase[FL_CUT_MAX];
+    __shared__ unsigned long long gbase[FL_CUT_MAX];
     if (threadIdx.x < 32u) hist[threadIdx.x] = 0u;
     if (threadIdx.x < FL_CUT_MAX) lcount[threadIdx.x] = 0u;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const unsigned long long base = (unsigned long long)blockIdx.x * FL_LOW_CHUNK;
     bool changed = false;
-    uint32_t slot[FL_LOW_CHUNK / 256u];  // (height << 16 | rank among the block's heads of that height), FL_NONE = none
-    uint32_t rcv[FL_LOW_CHUNK / 256u];   // receiver of such a head (k_elev_low starts from its values)
+    double dq[FL_PLAN_PER_THREAD], kq[FL_PLAN_PER_THREAD], aq[FL_PLAN_PER_THREAD];
+    uint32_t hq[FL_PLAN_PER_THREAD], rcv[FL_PLAN_PER_THREAD];
 #pragma unroll
-    for (uint32_t j = 0; j < FL_LOW_CHUNK / 256u; ++j) {
+    for (uint32_t j = 0; j < FL_PLAN_PER_THREAD; ++j) {
         const unsigned long long q64 = base + j * 256u + threadIdx.x;
-        uint32_t h = FL_NONE;
-        if (q64 < e.n) h = fl_plan_site(e, (uint32_t)q64, changed, [&](uint32_t bin) { atomicAdd(&hist[bin], 1u); });
-        const bool low = h != FL_NONE && h < e.cut;
-        rcv[j] = low ? e.recv[(uint32_t)q64] : 0u;
-        // lanes whose heads have the same height reserve their places together (one shared-memory atomic per group)
-        const uint32_t key = low ? h : FL_CUT_MAX;
-        const uint32_t peers = __match_any_sync(FL_FULL, key);
-        const int leader = __ffs((int)peers) - 1;
-        uint32_t first = 0u;
-        if (low && lane == leader) first = atomicAdd(&lcount[h], (uint32_t)__popc(peers));
-        first = __shfl_sync(FL_FULL, first, leader);
-        slot[j] = low ? ((h << 16) | (first + (uint32_t)__popc(peers & ((1u << lane) - 1u)))) : FL_NONE;
+        dq[j] = 1.0; kq[j] = 1.0; aq[j] = 1.0; hq[j] = FL_NONE; rcv[j] = 0u;
+        if (q64 < e.n) {
+            const uint32_t q = (uint32_t)q64;
+            dq[j] = e.drecv[q]; kq[j] = e.erod[q]; aq[j] = e.A[q]; hq[j] = e.hgt[q]; rcv[j] = e.recv[q];
+        }
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < FL_PLAN_PER_THREAD; ++j) {
+        const unsigned long long q64 = base + j * 256u + threadIdx.x;
+        if (q64 < e.n) {
+            const double celerity = kq[j] * sqrt(aq[j]);  // generator.rs:172-173
+            const double tq = 1.0 / celerity * dq[j];
+            e.tcel[(uint32_t)q64] = tq;
+            if (hq[j] != FL_NONE && hq[j] >= e.cut) {
+                atomicAdd(&hist[hq[j] < 31u ? hq[j] : 31u], 1u);
+                fl_plan_top_head(e, (uint32_t)q64, rcv[j], tq, changed);
+            }
+        }
+    }
+    uint32_t slot[FL_PLAN_PER_THREAD];  // rank among the block's heads of the same height (below the cut)
+#pragma unroll
+    for (uint32_t j = 0; j < FL_PLAN_PER_THREAD; ++j) {
+        slot[j] = 0u;
+        for (uint32_t l = 0; l < e.cut; ++l) {
+            const uint32_t peers = __ballot_sync(FL_FULL, hq[j] == l);
+            if (!peers) continue;
+            const int leader = __ffs((int)peers) - 1;
+            uint32_t first = 0u;
+            if (lane == leader) first = atomicAdd(&lcount[l], (uint32_t)__popc(peers));
+            first = __shfl_sync(FL_FULL, first, leader);
+            if (hq[j] == l) slot[j] = first + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        }
     }
     __syncthreads();
     // one reservation per block and height in the global lists
     if (threadIdx.x < FL_CUT_MAX) {
-        const uint32_t cnt = lcount[threadIdx.x];
-        lbase[threadIdx.x] = cnt ? atomicAdd(&e.flags[FLQ_LOW + threadIdx.x], cnt) : 0u;
+        const uint32_t l = threadIdx.x, cnt = lcount[l];
+        const uint32_t first = cnt ? atomicAdd(&e.flags[FLQ_LOW + l], cnt) : 0u;
+        gbase[l] = (unsigned long long)fl_low_region(e.n, l) + first;
+        // cannot happen: more heads of a height than sites allow (the list would run into the next height's)
+        if ((unsigned long long)first + cnt > (unsigned long long)e.n / (l + 1u) + 1ull) { gbase[l] = ~0ull; atomicOr(&e.flags[FL_FLAG_BROKEN], 64u); }
+        if (cnt) atomicAdd(&e.flags[FLQ_HIST + l], cnt);
     }
     __syncthreads();
 #pragma unroll
-    for (uint32_t j = 0; j < FL_LOW_CHUNK / 256u; ++j)
-        if (slot[j] != FL_NONE) {
-            const uint32_t l = slot[j] >> 16;
-            const size_t at = (size_t)lbase[l] + (slot[j] & 0xFFFFu);
-            if (at <= (size_t)e.n / (l + 1u))
-                e.low_list[fl_low_region(e.n, l) + at] = make_uint2((uint32_t)(base + j * 256u + threadIdx.x), rcv[j]);
-            else
-                atomicOr(&e.flags[FL_FLAG_BROKEN], 64u);  // cannot happen: more heads of a height than sites allow
+    for (uint32_t j = 0; j < FL_PLAN_PER_THREAD; ++j)
+        if (hq[j] < e.cut) {  // (FL_NONE is not)
+            const unsigned long long g = gbase[hq[j]];
+            if (g != ~0ull) e.low_list[g + slot[j]] = make_uint2((uint32_t)(base + j * 256u + threadIdx.x), rcv[j]);
         }
     if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
     if (threadIdx.x < 32u && hist[threadIdx.x]) atomicAdd(&e.flags[FLQ_HIST + threadIdx.x], hist[threadIdx.x]);
@@ -647,15 +669,18 @@ __global__ void __launch_bounds__(256) k_elev_low(FlSplit e, uint32_t level) {
 // FL_PSHORT sites are finished by the thread.  Longer ones go to a list in shared memory and are walked by whole warps
 // in phase 2 -- kept apart so that the window machinery does not sit inside the thread-per-head loop.
 #ifndef FL_LOW_MINBLOCKS
-#define FL_LOW_MINBLOCKS 3  // resident blocks per SM the register allocation aims at (measured: 3 beats 2 and 4, r2k_ab.txt)
+#define FL_LOW_MINBLOCKS 4  // resident blocks per SM the register allocation aims at
+#endif
+#ifndef FL_PB_LOW
+#define FL_PB_LOW 2  // sites per batch of a thread of k_elev_low (measured: 2 with 4 resident blocks beats 4 with 3, r2m_ab.txt)
 #endif
 struct FlLongRun { uint32_t q, root; double rt_prev, z_prev, e_out, rt_out; };
-__global__ void __launch_bounds__(256, FL_LOW_MINBLOCKS) k_elev_low(FlSplit e, uint32_t level) {
+__global__ void __launch_bounds__(256, FL_LOW_MINBLOCKS) k_elev_low(FlSplit e, uint32_t level, size_t region) {
     __shared__ FlChainSmem chain_smem[8];
     __shared__ FlLongRun longs[256];
     __shared__ uint32_t n_long;
     const uint32_t total = e.flags[FLQ_LOW + level];
-    const uint2* __restrict__ list = e.low_list + fl_low_region(e.n, level);
+    const uint2* __restrict__ list = e.low_list + region;  // = fl_low_region(e.n, level)
     bool changed = false;
     for (unsigned long long g0 = (unsigned long long)blockIdx.x * 256u; g0 < total; g0 += (unsigned long long)gridDim.x * 256u) {
         if (threadIdx.x == 0u) n_long = 0u;
@@ -672,10 +697,10 @@ __global__ void __launch_bounds__(256, FL_LOW_MINBLOCKS) k_elev_low(FlSplit e, u
                 s = fl_root_site(e, h, e.tcel[h], changed);
                 q = h + 1u;
                 ended = !(q < e.n && e.recv[q] == h);
-                if (!ended) ended = fl_run_batch<FL_PB>(e, q, s, changed);
+                if (!ended) ended = fl_run_batch<FL_PB_LOW>(e, q, s, changed);
             } else {  // the receiver's segment is strictly higher: finished by an earlier launch
-                FlBatch<FL_PB> b;
-                fl_batch_load<FL_PB>(e, q, true, b);
+                FlBatch<FL_PB_LOW> b;
+                fl_batch_load<FL_PB_LOW>(e, q, true, b);
                 const uint32_t root_p = e.root_of[p];
                 const double rt_p = e.rt[p];    // (rt of a tree without outlet is never used)
                 const double z_p = e.elev[p];   // the receiver already holds its NEW elevation
@@ -686,10 +711,10 @@ __global__ void __launch_bounds__(256, FL_LOW_MINBLOCKS) k_elev_low(FlSplit e, u
                     s.e_out = e.elev[root_p];
                     s.rt_out = e.rt[root_p];
                 }
-                ended = fl_batch_compute<FL_PB>(e, q, s, changed, b);
+                ended = fl_batch_compute<FL_PB_LOW>(e, q, s, changed, b);
             }
 #pragma unroll 1
-            for (int r = 1; r < FL_PSHORT / FL_PB && !ended; ++r) ended = fl_run_batch<FL_PB>(e, q, s, changed);
+            for (int r = 1; r < FL_PSHORT / FL_PB_LOW && !ended; ++r) ended = fl_run_batch<FL_PB_LOW>(e, q, s, changed);
             if (!ended) {
                 FlLongRun& r = longs[atomicAdd(&n_long, 1u)];  // (at most one per thread of the block)
                 r.q = q; r.root = s.root; r.rt_prev = s.rt_prev; r.z_prev = s.z_prev; r.e_out = s.e_out; r.rt_out = s.rt_out;

@@ -792,13 +792,15 @@ __global__ void __launch_bounds__(256, 2) k_area_flow_long(FlFlow f) {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fl_mark_up(const FlFlow& f, uint32_t p) {
     for (;;) {
+        // two dependent round trips per step up the forest: {flag, segment head} then {dirty mark, the head's receiver};
+        // the results are looked at only after everything has been requested
         const uint32_t old = atomicOr(&f.nwait[p], FL_NW_RFLAG);
-        if (!(old & FL_NW_RFLAG)) f.rlist[atomicAdd(&f.flags[FL_FLAG_NREGATHER], 1u)] = p;
         const uint32_t sh = f.seg_head[p];
         const uint32_t prev = atomicMax(&f.dirty_from[sh], p + 1u);
+        const uint32_t pp = f.recv[sh];
+        if (!(old & FL_NW_RFLAG)) f.rlist[atomicAdd(&f.flags[FL_FLAG_NREGATHER], 1u)] = p;
         if (prev != 0u) return;  // the segment is already dirty: whoever marked it first walks on from its head
         f.slist[atomicAdd(&f.flags[FL_FLAG_NDIRTY], 1u)] = sh;
-        const uint32_t pp = f.recv[sh];
         if (pp == sh) {  // tree root: the fused launch ends when every dirty root is finished
             atomicAdd(&f.flags[FL_FLAG_NROOTS], 1u);
             return;

@@ -185,8 +185,12 @@ struct fastlem_ctx {
     uint32_t segs_at_rebuild = 0, maxh_at_rebuild = 0;
     bool need_rebuild = true;
     int64_t opt_rebuild_every = 0;  // 0 = adaptive
-    int64_t opt_rebuild_height = 150;  // adaptive: ... or when the nesting height exceeds this many percent of its value + 2
-    int64_t opt_rebuild_growth = 4;  // adaptive: renumber when the segment count grew by this many percent
+    // adaptive renumbering: when the segment count grew by `growth` percent, or the nesting height exceeds `height` percent
+    // of its value after the last renumbering + 2.  0 = by the number of sites: a renumbering (and the full K4 pass it
+    // forces) costs about 0.8 iterations at 1M sites but 2 at 16M, so large models renumber later -- 4 / 150 up to 1M
+    // sites, 8 / 250 from 16M on (measured optima, profiles/r2l_rebuild_sweep_*.txt, r2m_*), in between by log2(n)
+    int64_t opt_rebuild_height = 0;
+    int64_t opt_rebuild_growth = 0;
     // scratch in the caller's numbering (download, debug fetch, kept stages)
     double* d_out_f64 = nullptr;
     uint32_t* d_out_u32 = nullptr;
@@ -868,6 +872,20 @@ int rebuild_layout_flow(fastlem_ctx* c, const double* weight) {
     return FASTLEM_OK;
 }
 
+// thresholds of the adaptive renumbering (see fastlem_ctx::opt_rebuild_height)
+static inline double rebuild_scale(uint32_t n) {
+    double t = n > 1000000u ? std::log2((double)n / 1.0e6) / 4.0 : 0.0;
+    return t > 1.0 ? 1.0 : t;
+}
+static inline unsigned long long rebuild_growth_of(const fastlem_ctx* c) {
+    return c->opt_rebuild_growth > 0 ? (unsigned long long)c->opt_rebuild_growth
+                                     : (unsigned long long)(4.0 + 4.0 * rebuild_scale(c->n) + 0.5);
+}
+static inline unsigned long long rebuild_height_of(const fastlem_ctx* c) {
+    return c->opt_rebuild_height > 0 ? (unsigned long long)c->opt_rebuild_height
+                                     : (unsigned long long)(150.0 + 100.0 * rebuild_scale(c->n) + 0.5);
+}
+
 // K1 of the current layout: receivers from L.elev into (recv, drecv, cmask); `track`: lists the sites whose receiver
 // differs from recv_prev (the previous iteration's final receivers)
 int launch_receivers(fastlem_ctx* c, bool track, const uint32_t* recv_prev, uint32_t* recv, double* drecv, uint32_t* cmask) {
@@ -1085,7 +1103,7 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool may_continue, bool* changed_o
             {   // persistent grid over the height's list; never more blocks than the list can have groups of 256 heads
                 const size_t most = ((size_t)n / (lv + 1u) + 256u) / 256u;
                 const unsigned blocks = (unsigned)(most < (size_t)c->low_blocks ? most : (size_t)c->low_blocks);
-                FL_LAUNCH(k_elev_low, blocks, 256, c->stream, e, lv);
+                FL_LAUNCH(k_elev_low, blocks, 256, c->stream, e, lv, fl_low_region(n, lv));
             }
             c->stats.kernel_launches++;
 #endif
@@ -1156,9 +1174,9 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool may_continue, bool* changed_o
         if (rebuilt) { c->segs_at_rebuild = n_heads; c->maxh_at_rebuild = maxh; }
         else if (c->opt_rebuild_every == 0 &&
                  ((unsigned long long)n_heads * 100ull >
-                      (unsigned long long)c->segs_at_rebuild * (100ull + (unsigned long long)c->opt_rebuild_growth) ||
+                      (unsigned long long)c->segs_at_rebuild * (100ull + rebuild_growth_of(c)) ||
                   (unsigned long long)maxh * 100ull >
-                      (unsigned long long)c->maxh_at_rebuild * (unsigned long long)c->opt_rebuild_height + 200ull))
+                      (unsigned long long)c->maxh_at_rebuild * rebuild_height_of(c) + 200ull))
             c->need_rebuild = true;  // the numbering has degraded: renumber in the next iteration
         if (c->trace_iters && it < 400u)
             std::fprintf(stderr, "[fastlem trace] it %u: chg %u incr %d rebuilt %d heads %u maxh %u next_rebuild %d\n", it, n_chg,
@@ -1253,9 +1271,9 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool may_continue, bool* changed_o
         if (rebuilt) { c->segs_at_rebuild = n_heads; c->maxh_at_rebuild = maxh; }
         else if (c->opt_rebuild_every == 0 &&
                  ((unsigned long long)n_heads * 100ull >
-                      (unsigned long long)c->segs_at_rebuild * (100ull + (unsigned long long)c->opt_rebuild_growth) ||
+                      (unsigned long long)c->segs_at_rebuild * (100ull + rebuild_growth_of(c)) ||
                   (unsigned long long)maxh * 100ull >
-                      (unsigned long long)c->maxh_at_rebuild * (unsigned long long)c->opt_rebuild_height + 200ull))
+                      (unsigned long long)c->maxh_at_rebuild * rebuild_height_of(c) + 200ull))
             c->need_rebuild = true;
         if (c->trace_iters && it < 400u)
             std::fprintf(stderr, "[fastlem trace] it %u: chg %u incr %d rebuilt %d heads %u maxh %u cut %u top %u next_rebuild %d\n",
@@ -1526,10 +1544,10 @@ int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
     } else if (s == "fuse_levels") {
         c->opt_fuse_levels = value != 0;
     } else if (s == "rebuild_height") {
-        if (value < 100) return fail(c, FASTLEM_E_INVALID, "option rebuild_height: percent >= 100");
+        if (value != 0 && value < 100) return fail(c, FASTLEM_E_INVALID, "option rebuild_height: 0 (by model size) or percent >= 100");
         c->opt_rebuild_height = value;
     } else if (s == "rebuild_growth") {
-        if (value < 1) return fail(c, FASTLEM_E_INVALID, "option rebuild_growth: percent >= 1");
+        if (value < 0) return fail(c, FASTLEM_E_INVALID, "option rebuild_growth: 0 (by model size) or percent >= 1");
         c->opt_rebuild_growth = value;
     } else if (s == "rebuild_every") {
         if (value < 0) return fail(c, FASTLEM_E_INVALID, "option rebuild_every: 0 (adaptive) or a positive period");

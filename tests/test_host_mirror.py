@@ -168,3 +168,26 @@ def test_advanced_example_render(emu_lib, oracle):
         want = 1.0 - math.sin(math.atan((e1 - e2) / 50.0))
         assert abs(brightness[imgy, imgx] - want) <= 1e-9
     assert np.isfinite(elevation).mean() > 0.8
+
+
+def test_interpolator_reads_the_slice_on_every_call(emu_lib):
+    """interpolator.rs:17-27 reads `elevations` on every call: values changed in place must be seen (the upload is only
+    reused for arrays that cannot change), and a NaN elevation gives Some(NaN), not the None of a query outside the hull."""
+    rng = np.random.default_rng(5)
+    sites = rng.random((200, 2)) * 50.0
+    values = np.full(200, 2.0)
+    it = fl.TerrainInterpolator2D(sites, lib_path=emu_lib)
+    inside, outside = fl.Site2D(25.0, 25.0), fl.Site2D(-5.0, 25.0)
+    assert abs(it.interpolate(values, inside) - 2.0) < 1e-12
+    values[:] = 7.0  # same object, new contents
+    assert abs(it.interpolate(values, inside) - 7.0) < 1e-12
+    assert it.interpolate(values, outside) is None
+    values[:] = np.nan
+    z = it.interpolate(values, inside)
+    assert z is not None and z != z  # Some(NaN)
+    assert it.interpolate(values, outside) is None
+    frozen = np.full(200, 3.0)
+    frozen.setflags(write=False)
+    assert abs(it.interpolate(frozen, inside) - 3.0) < 1e-12
+    assert abs(it.interpolate(frozen, inside) - 3.0) < 1e-12  # (served from the uploaded copy)
+    it.close()
