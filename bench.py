@@ -48,7 +48,7 @@ ITER_BYTES = 180.0
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of THIS build, written by
 # tools/ncu_traffic.py (absent kernel / size -> traffic null)
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-KERNEL_STAGE = {"k_receivers_mask": "receivers", "k_area_flow": "area", "k_incr_start": "area", "k_area_flow_long": "area",
+KERNEL_STAGE = {"k_receivers_bulk": "receivers", "k_area_flow": "area", "k_incr_start": "area", "k_area_flow_long": "area",
                 "k_elev_plan": "elevation", "k_elev_top": "elevation", "k_elev_low": "elevation"}
 
 
@@ -81,10 +81,21 @@ def workload_name(kind, n):
             f"step = generate() to convergence")
 
 
-def member_erodibility(sites, t):
-    """Erodibility field of ensemble member t (terrain_generation_advanced.rs:136-160 style: |fbm noise| * 4 + 0.1)."""
+def erodibility_basis(sites):
+    """Four independent noise fields over the sites (terrain_generation_advanced.rs:136-160 style fbm noise), built once per
+    process; every ensemble member mixes two of them with its own angle (member_erodibility)."""
     from tools import workloads as W
-    return np.abs(W.value_noise(sites, 8.0 / 75.0, seed=1000 + int(t), octaves=3)) * 4.0 + 0.1
+    return [W.value_noise(sites, 8.0 / 75.0, seed=1000 + k, octaves=3) for k in range(4)]
+
+
+def member_erodibility(basis, t):
+    """Erodibility field of ensemble member t: |noise| * 4 + 0.1 with noise = a rotation by the member's own angle in the
+    plane of two basis fields -- a different field for every t at the cost of one pass over the sites (the parameter
+    synthesis is the caller's business, not the solver's: it must not be what the pool waits for)."""
+    t = int(t)
+    a = 0.61803398875 * (t + 1) * np.pi
+    f = basis[t % 4] * np.cos(a) + basis[(t // 4 + 1 + t % 4) % 4] * np.sin(a)
+    return np.abs(f) * 4.0 + 0.1
 
 
 def peaks():
@@ -205,12 +216,14 @@ def roofline_of(st, n, iters, dev_ms):
     stage_ms = {k: st["ms_" + k] for k in STAGES}
     kern = {k: v for k, v in st.get("kernels", {}).items() if v["launches"] and k in KERNEL_STAGE}
     per_it = {k: v["ms"] / max(st["kernel_iterations"], 1) for k, v in kern.items()}
-    dom = max(per_it, key=per_it.get) if per_it else "k_receivers_mask"
+    dom = max(per_it, key=per_it.get) if per_it else "k_receivers_bulk"
     stage = KERNEL_STAGE[dom]
     alg = STAGE_BYTES[stage] * n
     ms_it = per_it.get(dom, stage_ms[stage] / max(iters, 1))
     achieved = alg / (ms_it / 1e3) / 1e9 if ms_it > 0 else 0.0
-    k1_ms = per_it.get("k_receivers_mask", stage_ms["receivers"] / max(iters, 1))
+    # K1: the stage events of the timed runs bracket exactly the K1 launch (plus the two small memsets before it), over
+    # ALL iterations; the "profile"=2 figure is a sample of the first iterations with a synchronisation after every kernel
+    k1_ms = stage_ms["receivers"] / max(iters, 1)
     k1 = STAGE_BYTES["receivers"] * n / (k1_ms / 1e3) / 1e9 if k1_ms > 0 else 0.0
     whole = ITER_BYTES * n * iters / (dev_ms / 1e3) / 1e9 if dev_ms > 0 else 0.0
     kernels = {}
@@ -226,9 +239,11 @@ def roofline_of(st, n, iters, dev_ms):
             "what": f"{dom}: the {stage} stage's algorithmic bytes per iteration ({STAGE_BYTES[stage]} B x {n} sites) over the "
                     f"kernel's device time per iteration (CUDA events around every launch, \"profile\"=2 run of the same "
                     f"workload inside this process; the timed steps themselves run with stage events only)",
-            "receivers_kernel": {"kernel": "k_receivers_mask", "achieved": k1, "frac": k1 / peak, "ms_per_launch": k1_ms,
+            "receivers_kernel": {"kernel": "k_receivers_bulk", "achieved": k1, "frac": k1 / peak, "ms_per_launch": k1_ms,
+                                 "timing": "CUDA events around the K1 stage of every iteration of the timed runs",
+                                 "ms_per_launch_profile2_sample": per_it.get("k_receivers_bulk"),
                                  "bytes_per_launch": STAGE_BYTES["receivers"] * n,
-                                 "traffic": ncu_traffic("k_receivers_mask", n)},
+                                 "traffic": ncu_traffic("k_receivers_bulk", n)},
             "whole_iteration": {"achieved": whole, "frac": whole / peak, "bytes": ITER_BYTES * n,
                                 "ms": dev_ms / max(iters, 1)},
             "stage_ms_per_iteration": {k: v / max(iters, 1) for k, v in stage_ms.items()},
@@ -335,11 +350,12 @@ def ensemble_leg(args, local_rank, m, p, outlets, initial):
     from fastlem_b200 import _native, ensemble
     n = m["n"]
     members = args.ensemble_members
-    prm = [dict(initial=initial, erodibility=member_erodibility(m["sites"], t), uplift=p["uplift"], outlets=outlets)
+    basis = erodibility_basis(m["sites"])
+    prm = [dict(initial=initial, erodibility=member_erodibility(basis, t), uplift=p["uplift"], outlets=outlets)
            for t in range(members)]
     out = {"members": members, "sites": n, "what": "noise-driven erodibility per member (seed = member index), shared graph, "
                                                    "hull outlets; each member = set_parameters (host buffers) + run to convergence"}
-    for n_ctx in (1, 2, 3, 4):
+    for n_ctx in (1, 2, 3, 4, 6, 8):
         ctxs = []
         for _ in range(n_ctx):
             c = _native.Context(local_rank)
@@ -581,15 +597,18 @@ def multi_gpu(args, rank, local_rank, world):
     import torch.distributed as dist
     from fastlem_b200 import _native, ensemble
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    m, p, outlets, t_build = build_workload(args.workload, args.sites, seed=1)  # the same model on every rank
+    # BASELINE config C5: members of 4M sites (`--ensemble-sites`; `--sites` if given explicitly); the same model on every rank
+    sites_arg = args.sites if args.sites != 1000000 else args.ensemble_sites
+    m, p, outlets, t_build = build_workload(args.workload, sites_arg, seed=1)
     n = m["n"]
     initial = _native.host_initial_elevations(p["base"])
     per_step = args.members_per_rank * world
     graph_bytes = m["row_ptr"].nbytes + m["col"].nbytes + m["dist"].nbytes + m["areas"].nbytes
     hp_shared = {"initial": pinned(initial), "uplift": pinned(p["uplift"]), "outlets": pinned(outlets)}
+    basis = erodibility_basis(m["sites"])
 
     def make_params(t):  # host side, on the helper thread of run_pool: overlaps the previous member's solve
-        return dict(initial=hp_shared["initial"], erodibility=pinned(member_erodibility(m["sites"], t)),
+        return dict(initial=hp_shared["initial"], erodibility=member_erodibility(basis, t),
                     uplift=hp_shared["uplift"], outlets=hp_shared["outlets"])
 
     def barrier():
@@ -625,6 +644,12 @@ def multi_gpu(args, rank, local_rank, world):
     ensemble.run_pool_concurrent(ctxs, warm_pool, make_params, lambda t, it, c: None, args.max_iter)
     counters.update({"iters": 0, "launches": 0, "dev_ms": 0.0, "members": []})
 
+    # the collectives of the timed region once, untimed: NCCL sets up its send / receive channels on first use (1.4 s here)
+    warm = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    dist.all_gather(warm, torch.zeros(1, dtype=torch.int64, device="cuda"))
+    warm_out = [torch.empty((1, n), dtype=torch.float64, device="cuda") for _ in range(world)] if rank == 0 else None
+    dist.gather(results[:1].contiguous(), warm_out, dst=0)
+    del warm_out
     # timed region: K steps' worth of members in ONE pool (no barrier between steps), one gather at the end
     total = args.steps * per_step
     pool = ensemble.MemberPool.for_process_group(total, "fastlem_timed")
@@ -655,7 +680,8 @@ def multi_gpu(args, rank, local_rank, world):
 
     # e2e: the same ensemble through the C ABI with host buffers -- the graph uploaded inside the timed region (once per
     # rank), every member = set_parameters from pinned host arrays + generate with the elevations copied to the host
-    pool2 = ensemble.MemberPool.for_process_group(total, "fastlem_e2e")
+    total_e2e = min(total, 2 * per_step)  # (a shorter run of the same thing: at most two steps' worth of members)
+    pool2 = ensemble.MemberPool.for_process_group(total_e2e, "fastlem_e2e")
     n_ctx = max(1, args.contexts_per_gpu)
     host_out = {}
     hm = {k: pinned(m[k]) for k in ("row_ptr", "col", "dist", "areas")}
@@ -674,9 +700,12 @@ def multi_gpu(args, rank, local_rank, world):
         c2.set_graph(hm["row_ptr"], hm["col"], hm["dist"], hm["areas"])
         host_out[id(c2)] = pinned(np.empty(n))
         c2s.append(c2)
+    t_up = time.perf_counter() - t1
     ensemble.run_pool_concurrent(c2s, pool2, make_params, on_host, args.max_iter)
+    t_pool = time.perf_counter() - t1 - t_up
     for c2 in c2s:
         c2.close()
+    t_close = time.perf_counter() - t1 - t_up - t_pool
     barrier()
     e2e_t = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device="cuda")
     e2e_w = torch.tensor([float(n) * e2e["iters"], float(e2e["members"])], dtype=torch.float64, device="cuda")
@@ -695,13 +724,13 @@ def multi_gpu(args, rank, local_rank, world):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * float(t[0]) / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"C5 style: ensemble of {per_step} members per step ({args.members_per_rank} per GPU) x {n} sites "
-                                       f"on the C2 graph (shared by the members, uploaded once per context), noise-driven erodibility per member, hull "
+                "config": {"workload": f"C5: ensemble of {per_step} members per step ({args.members_per_rank} per GPU) x {n} sites "
+                                       f"on one Delaunay graph of random sites (shared by the members, uploaded once per context), noise-driven erodibility per member, hull "
                                        f"outlets; each member = generate() to convergence; members handed out first come first "
                                        f"served over the {world} ranks, one NCCL gather of the elevations at the end",
                            "sites": n, "members_per_step": per_step, "members_timed": members_total,
                            "iterations_per_member": float(w[0]) / n / max(members_total, 1),
-                           "l2": "working set ~170 MB per iteration > 126 MB L2; hundreds of iterations per member, no flush",
+                           "l2": f"working set ~{170 * n // 1000000} MB per member and iteration > 126 MB L2; hundreds of iterations per member, no flush",
                            "max_iteration": args.max_iter, "parallelism": f"{world} GPUs, one process each, {n_ctx} members in flight per GPU (one context and "
                                           f"stream each)",
                            "like_for_like_n1": f"`ensemble.contexts_{n_ctx}` of the N = 1 line is this workload on one GPU (the "
@@ -709,9 +738,10 @@ def multi_gpu(args, rank, local_rank, world):
                 "balance": {"slowest_rank_s": float(t[1]), "fastest_rank_s": float(tmin[0]),
                             "gather_and_barrier_s": float(t[0]) - float(t[1])},
                 "e2e": {"value": float(e2e_w[0]) / float(e2e_t[0]), "unit": UNIT,
-                        "h2d_bytes_per_step": int(graph_bytes * world * n_ctx / args.steps + per_step * (3 * 8 * n + outlets.nbytes)),
-                        "d2h_bytes_per_step": int(per_step * 8 * n), "seconds_per_step": float(e2e_t[0]) / args.steps,
+                        "h2d_bytes_per_step": int(graph_bytes * world * n_ctx * per_step / total_e2e + per_step * (3 * 8 * n + outlets.nbytes)),
+                        "d2h_bytes_per_step": int(per_step * 8 * n), "seconds_per_step": float(e2e_t[0]) * per_step / total_e2e,
                         "members": int(e2e_w[1]),
+                        "seconds_rank0": {"create_and_set_graph": t_up, "members": t_pool, "destroy": t_close},
                         "host_buffers": "pinned host arrays handed to the C ABI as plain pointers; graph upload inside the timed "
                                         "region (once per context)"},
                 "gpu_launches": int(w[1]), "device_seconds_max_over_ranks": float(t[2]),
@@ -743,9 +773,11 @@ def main():
     ap.add_argument("--c4-sites", type=int, default=16000000, help="sites of the C4 leg of the N = 1 line (0 = skip)")
     ap.add_argument("--c4-max-iter", type=int, default=None)
     ap.add_argument("--c4-cpu-iters", type=int, default=5)
-    ap.add_argument("--ensemble-members", type=int, default=8, help="members of the N = 1 ensemble leg (0 = skip)")
-    ap.add_argument("--members-per-rank", type=int, default=4, help="N > 1: ensemble members per rank and step")
-    ap.add_argument("--contexts-per-gpu", type=int, default=2,
+    ap.add_argument("--ensemble-members", type=int, default=16, help="members of the N = 1 ensemble leg (0 = skip)")
+    ap.add_argument("--members-per-rank", type=int, default=8, help="N > 1: ensemble members per rank and step")
+    ap.add_argument("--ensemble-sites", type=int, default=4000000,
+                    help="N > 1: sites of the ensemble's model (BASELINE config C5: 4M-site terrains)")
+    ap.add_argument("--contexts-per-gpu", type=int, default=4,
                     help="N > 1: ensemble members in flight per GPU (one context + host thread each)")
     ap.add_argument("--sweep", type=int, default=None, help="solver option 'sweep' (DESIGN.md)")
     ap.add_argument("--max-iter", type=int, default=None,

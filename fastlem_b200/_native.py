@@ -44,7 +44,7 @@ class Stats(ctypes.Structure):
                 ("flood_on_device", ctypes.c_uint32), ("outlet_ranks_on_device", ctypes.c_uint32),
                 ("ms_kernel", ctypes.c_double * 8), ("n_kernel", ctypes.c_uint64 * 8)]
 
-    KERNELS = ("k_receivers_mask", "k_area_flow", "k_incr_start", "k_area_flow_long", "k_elev_plan", "k_elev_top",
+    KERNELS = ("k_receivers_bulk", "k_area_flow", "k_incr_start", "k_area_flow_long", "k_elev_plan", "k_elev_top",
                "k_elev_low", "rebuild")  # FASTLEM_K_*
 
     def as_dict(self):

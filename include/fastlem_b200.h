@@ -126,7 +126,7 @@ typedef struct fastlem_stats {
     uint64_t n_kernel[8];
 } fastlem_stats;
 enum {
-    FASTLEM_K_RECEIVERS = 0,      /* k_receivers_mask (K1) */
+    FASTLEM_K_RECEIVERS = 0,      /* k_receivers_bulk (K1; k_receivers_mask with "k1_bulk" = 0) */
     FASTLEM_K_AREA_FLOW = 1,      /* k_area_flow: thread-level climbs of a full K4 pass */
     FASTLEM_K_INCR_START = 2,     /* k_incr_start: thread-level climbs of an incremental K4 pass */
     FASTLEM_K_AREA_FLOW_LONG = 3, /* k_area_flow_long: warp-level climbs of the long segments (K4) */
