@@ -23,7 +23,7 @@ _STAGE_DTYPE = {0: np.uint32, 1: np.uint32, 2: np.uint32, 3: np.uint32, 4: np.ui
 # every symbol include/fastlem_b200.h declares
 SYMBOLS = ["fastlem_create", "fastlem_destroy", "fastlem_last_error", "fastlem_get_device", "fastlem_set_graph",
            "fastlem_set_parameters", "fastlem_generate", "fastlem_run", "fastlem_download", "fastlem_download_to_device",
-           "fastlem_set_option", "fastlem_get_stats", "fastlem_debug_fetch", "fastlem_version",
+           "fastlem_set_option", "fastlem_get_stats", "fastlem_debug_fetch", "fastlem_version", "fastlem_trim_memory",
            "fastlem_host_initial_elevations", "fastlem_host_tan_max_slope", "fastlem_host_graph_from_triangles",
            "fastlem_interp_create", "fastlem_interp_destroy", "fastlem_interp_last_error", "fastlem_interp_set_values",
            "fastlem_interp_set_values_device", "fastlem_interp_set_values_from", "fastlem_interp_points",
@@ -106,6 +106,8 @@ def load(path=None):
     lib.fastlem_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.fastlem_debug_fetch.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t]
     lib.fastlem_version.restype = ctypes.c_char_p
+    lib.fastlem_trim_memory.argtypes = [ctypes.c_int]
+    lib.fastlem_trim_memory.restype = ctypes.c_int
     lib.fastlem_host_initial_elevations.argtypes = [u32, f64p, f64p]
     lib.fastlem_host_initial_elevations.restype = None
     lib.fastlem_host_tan_max_slope.argtypes = [u32, f64p, f64p]

@@ -116,7 +116,7 @@ int check_query_flags(fastlem_interp* c) {
 
 int ensure_out(fastlem_interp* c, size_t count) {
     if (count <= c->out_cap) return FASTLEM_OK;
-    if (c->d_out) fl_free(c->d_out);
+    if (c->d_out) fl_free(c->d_out, c->stream);
     c->d_out = nullptr;
     c->out_cap = 0;
     FLI_CK(ialloc(c->d_out, count));
@@ -171,7 +171,7 @@ void fastlem_interp_destroy(fastlem_interp* c) {
     void* ptrs[] = {c->d_site, c->d_tri, c->d_nbr, c->d_circ, c->d_geo, c->d_cell, c->d_cell2, c->d_value, c->d_flags, c->d_out,
                     c->d_query};
     for (void* p : ptrs)
-        if (p) fl_free(p);
+        if (p) fl_free(p, c->stream);
     if (c->h_flags) fl_free_host(c->h_flags);
     for (int k = 0; k < 2; ++k)
         if (c->ev[k]) fl_event_destroy(c->ev[k]);
@@ -214,7 +214,7 @@ static int interp_setup(fastlem_interp* c, const double* sites_xy, const uint32_
     uint32_t *d_triangles = nullptr, *d_halfedges = nullptr;
     FLI_CK(ialloc(d_triangles, 3 * (size_t)nt));
     cudaError_t e = ialloc(d_halfedges, 3 * (size_t)nt);
-    if (e != cudaSuccess) { fl_free(d_triangles); FLI_CK(e); }
+    if (e != cudaSuccess) { fl_free(d_triangles, c->stream); FLI_CK(e); }
     int rc = FASTLEM_OK;
     do {
         e = fl_h2d(c->d_site, sites_xy, sizeof(double) * 2 * (size_t)n, c->stream);
@@ -233,8 +233,8 @@ static int interp_setup(fastlem_interp* c, const double* sites_xy, const uint32_
         }
         rc = read_flags(c);
     } while (0);
-    fl_free(d_triangles);
-    fl_free(d_halfedges);
+    fl_free(d_triangles, c->stream);
+    fl_free(d_halfedges, c->stream);
     if (rc) return rc;
     const uint32_t* f = c->h_flags;
     if (f[FLI_F_BAD_INDEX]) return fail(c, FASTLEM_E_INVALID, "interpolator: triangle vertex index out of range");
@@ -295,7 +295,7 @@ static int interp_setup(fastlem_interp* c, const double* sites_xy, const uint32_
         if (passes > c->grid.gx + c->grid.gy) return fail(c, FASTLEM_E_INVALID, "interpolator: hint grid could not be filled");
     }
     c->stats.grid_passes = passes;
-    fl_free(c->d_cell2);
+    fl_free(c->d_cell2, c->stream);
     c->d_cell2 = nullptr;
     c->stats.ms_setup = wall_ms() - t0;
     return FASTLEM_OK;
@@ -370,7 +370,7 @@ int fastlem_interp_points(fastlem_interp* c, uint32_t n_points, const double* po
     int rc = ensure_out(c, n_points);
     if (rc) return rc;
     if (n_points > c->query_cap) {
-        if (c->d_query) fl_free(c->d_query);
+        if (c->d_query) fl_free(c->d_query, c->stream);
         c->d_query = nullptr;
         c->query_cap = 0;
         FLI_CK(ialloc(c->d_query, n_points));

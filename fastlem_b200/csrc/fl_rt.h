@@ -82,7 +82,8 @@ inline cudaError_t fl_stream_create(cudaStream_t* s) { *s = 0; return 0; }
 inline cudaError_t fl_stream_destroy(cudaStream_t) { return 0; }
 inline cudaError_t fl_stream_sync(cudaStream_t) { return 0; }
 inline cudaError_t fl_malloc(void** p, size_t bytes) { *p = std::malloc(bytes ? bytes : 1); return *p ? 0 : 2; }
-inline cudaError_t fl_free(void* p) { std::free(p); return 0; }
+inline cudaError_t fl_free(void* p, cudaStream_t = 0) { std::free(p); return 0; }
+inline cudaError_t fl_trim_pool() { return 0; }
 inline cudaError_t fl_malloc_host(void** p, size_t bytes) { *p = std::malloc(bytes ? bytes : 1); return *p ? 0 : 2; }
 inline cudaError_t fl_free_host(void* p) { std::free(p); return 0; }
 inline cudaError_t fl_h2d(void* d, const void* h, size_t bytes, cudaStream_t) { std::memcpy(d, h, bytes); return 0; }
@@ -159,6 +160,7 @@ inline cudaError_t fl_exclusive_sum64(void*, size_t& temp_bytes, const unsigned 
 #else
 // ------------------------------------------------------------------------------------------------
 #include <cuda_runtime.h>
+#include <mutex>
 #include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler (Nsight Systems / Compute) is attached
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -179,8 +181,65 @@ inline cudaError_t fl_set_device(int d) { return cudaSetDevice(d); }
 inline cudaError_t fl_stream_create(cudaStream_t* s) { return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); }
 inline cudaError_t fl_stream_destroy(cudaStream_t s) { return cudaStreamDestroy(s); }
 inline cudaError_t fl_stream_sync(cudaStream_t s) { return cudaStreamSynchronize(s); }
-inline cudaError_t fl_malloc(void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 1); }
-inline cudaError_t fl_free(void* p) { return cudaFree(p); }
+// Device memory comes from a stream-ordered pool the library keeps per device (cudaMemPool, release threshold = never):
+// a context's buffers go back to the pool when it is destroyed and the next context (the next `generate()` of a caller
+// that creates one per call, as the Rust shim does) gets them back without a trip to the driver.  cudaMalloc / cudaFree
+// of the ~0.5 GB slab of a 1M-site model were measured at up to 0.3 s EACH on some boxes (profiles/r2s_bench_1M.json:
+// destroy 0.32 s) against 0.62 s for the whole solve.  fastlem_trim_memory() returns the cached memory to the driver;
+// FASTLEM_NO_POOL=1 goes back to cudaMalloc / cudaFree.  A buffer is freed in the order of its owner's stream
+// (cudaFreeAsync), so it is never handed out again while a kernel still uses it.
+struct FlPool {
+    cudaMemPool_t pool = nullptr;
+    cudaStream_t stream = nullptr;
+    int state = 0;  // 0 = not tried, 1 = in use, -1 = unavailable
+};
+inline FlPool* fl_pool() {
+    static std::mutex mu;
+    static FlPool pools[64];
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    FlPool& P = pools[d];
+    if (P.state == 0) {
+        P.state = -1;
+        const char* off = std::getenv("FASTLEM_NO_POOL");
+        if (!(off && off[0] == '1')) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = d;
+            unsigned long long keep = ~0ull;
+            if (cudaMemPoolCreate(&P.pool, &props) == cudaSuccess &&
+                cudaMemPoolSetAttribute(P.pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&P.stream, cudaStreamNonBlocking) == cudaSuccess)
+                P.state = 1;
+            else
+                (void)cudaGetLastError();
+        }
+    }
+    return P.state == 1 ? &P : nullptr;
+}
+inline cudaError_t fl_malloc(void** p, size_t bytes) {
+    if (FlPool* P = fl_pool()) {
+        cudaError_t e = cudaMallocFromPoolAsync(p, bytes ? bytes : 1, P->pool, P->stream);
+        if (e != cudaSuccess) return e;
+        return cudaStreamSynchronize(P->stream);
+    }
+    return cudaMalloc(p, bytes ? bytes : 1);
+}
+// `owner`: the stream whose work last used the buffer -- the free is ordered behind that work
+inline cudaError_t fl_free(void* p, cudaStream_t owner) {
+    if (fl_pool()) return cudaFreeAsync(p, owner);
+    return cudaFree(p);
+}
+inline cudaError_t fl_trim_pool() {
+    if (FlPool* P = fl_pool()) {
+        cudaError_t e = cudaStreamSynchronize(P->stream);
+        return e != cudaSuccess ? e : cudaMemPoolTrimTo(P->pool, 0);
+    }
+    return cudaSuccess;
+}
 inline cudaError_t fl_malloc_host(void** p, size_t bytes) { return cudaMallocHost(p, bytes ? bytes : 1); }
 inline cudaError_t fl_free_host(void* p) { return cudaFreeHost(p); }
 inline cudaError_t fl_h2d(void* d, const void* h, size_t bytes, cudaStream_t s) {

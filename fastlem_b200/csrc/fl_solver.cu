@@ -244,7 +244,7 @@ template <class T> cudaError_t dalloc(fastlem_ctx* c, T*& p, size_t count) {
         c->slab_ptrs.push_back((void**)&p);
         return cudaSuccess;
     }
-    if (p) { fl_free(p); p = nullptr; }
+    if (p) { fl_free(p, c->stream); p = nullptr; }
     void* v = nullptr;
     cudaError_t e = fl_malloc(&v, count * sizeof(T));
     p = (T*)v;
@@ -256,11 +256,11 @@ template <class T> cudaError_t dalloc(fastlem_ctx* c, T*& p, size_t count) {
 
 void free_all(fastlem_ctx* c) {
     for (void** q : c->owned)
-        if (*q) { fl_free(*q); *q = nullptr; }
+        if (*q) { fl_free(*q, c->stream); *q = nullptr; }
     c->owned.clear();
     for (void** q : c->slab_ptrs) *q = nullptr;
     c->slab_ptrs.clear();
-    if (c->slab) fl_free(c->slab);
+    if (c->slab) fl_free(c->slab, c->stream);
     c->slab = nullptr;
     c->slab_size = c->slab_used = c->slab_need = 0;
     if (c->h_offs) fl_free_host(c->h_offs);
@@ -369,7 +369,9 @@ struct FlTmpAlloc {
     std::vector<void*> p;
     unsigned char* slab = nullptr;
     size_t size = 0, used = 0;
-    ~FlTmpAlloc() { for (void* q : p) fl_free(q); }
+    cudaStream_t stream;
+    explicit FlTmpAlloc(cudaStream_t s) : stream(s) {}
+    ~FlTmpAlloc() { for (void* q : p) fl_free(q, stream); }
     cudaError_t reserve(size_t bytes) {  // one allocation for everything that fits
         void* v = nullptr;
         cudaError_t e = fl_malloc(&v, bytes);
@@ -411,7 +413,7 @@ int device_flood_rank(fastlem_ctx* c, bool* done) {
     const uint32_t n = c->n, nnz = c->nnz;
     if (c->max_degree >= 255u || c->outlets.empty() || nnz == 0u) return FASTLEM_OK;
     FlTrace tr("flood");
-    FlTmpAlloc tmp;
+    FlTmpAlloc tmp(c->stream);
     const size_t n1 = (size_t)n + 1;
     // everything below comes out of one allocation: 17 bytes per slot (tree flags, two key arrays) and ~150 per site
     FL_CK(tmp.reserve((size_t)nnz * 17 + n1 * 160 + ((size_t)1 << 20) + 2 * c->tmp_bytes));
@@ -1422,6 +1424,11 @@ int alloc_graph_buffers(fastlem_ctx* c, uint32_t n, uint32_t nnz) {
 
 extern "C" {
 
+int fastlem_trim_memory(int device_ordinal) {
+    if (fl_set_device(device_ordinal) != cudaSuccess) return FASTLEM_E_CUDA;
+    return fl_trim_pool() == cudaSuccess ? FASTLEM_OK : FASTLEM_E_CUDA;
+}
+
 const char* fastlem_version(void) {
 #ifdef FL_EMU
     return "fastlem_b200 0.2.0 emu";
@@ -1477,8 +1484,8 @@ void fastlem_destroy(fastlem_ctx* c) {
     FlTrace tr("destroy");
     free_all(c);
     tr.mark("free_all");
-    if (c->d_tmp) fl_free(c->d_tmp);
-    if (c->d_flags) fl_free(c->d_flags);
+    if (c->d_tmp) fl_free(c->d_tmp, c->stream);
+    if (c->d_flags) fl_free(c->d_flags, c->stream);
     if (c->h_flags) fl_free_host(c->h_flags);
 
     for (int k = 0; k < ST_COUNT + 6; ++k)
@@ -1657,7 +1664,7 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     size_t max_bytes = 0;
     FL_CK(fl_inclusive_max(nullptr, max_bytes, c->d_deg_new, c->d_sg_head, n, c->stream, true));
     if (max_bytes > scan_bytes) scan_bytes = max_bytes;
-    if (c->d_tmp) { fl_free(c->d_tmp); c->d_tmp = nullptr; }
+    if (c->d_tmp) { fl_free(c->d_tmp, c->stream); c->d_tmp = nullptr; }
     c->tmp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
     FL_CK(fl_malloc(&c->d_tmp, c->tmp_bytes));
     tr.mark("work allocations");

@@ -44,6 +44,12 @@ enum {
 /* Creates a context on CUDA device `device_ordinal`. */
 int fastlem_create(fastlem_ctx** out, int device_ordinal);
 void fastlem_destroy(fastlem_ctx* ctx);
+
+/* Device memory is taken from a pool the library keeps per device: the buffers of a destroyed context are reused by
+ * the next one (a caller that creates a context per generate(), as the Rust shim does, pays the driver's allocation
+ * cost once, not per call).  This returns what the pool holds and no live context uses to the driver.  The environment
+ * variable FASTLEM_NO_POOL=1 disables the pool (plain cudaMalloc / cudaFree). */
+int fastlem_trim_memory(int device_ordinal);
 const char* fastlem_last_error(const fastlem_ctx* ctx);
 /* CUDA device ordinal the context lives on (-1 for a null context). */
 int fastlem_get_device(const fastlem_ctx* ctx);

@@ -316,3 +316,31 @@ def test_graph_arrays_are_not_borrowed(oracle, emu_lib):
         e, it = ctx.generate(max_iteration)
         ref, ref_it = oracle.generate(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, initial, max_iteration)
         assert it == ref_it and np.array_equal(e, ref)
+
+
+@pytest.mark.parametrize("overlap", [0, 1])
+@pytest.mark.parametrize("name", ["uniform", "uplift", "advanced"])
+def test_speculative_receivers_leave_the_state_alone(oracle, emu_lib, name, overlap):
+    """iterate_flow launches the NEXT iteration's K1 before the host has seen this iteration's flags (option `overlap`),
+    into alternate buffers: after a run that stopped at its iteration cap or converged, the receivers, areas and
+    response times that can be fetched are still those of the LAST iteration that counts."""
+    m, p, outlets, initial, _ = scenario(name)
+    for k in (2, 3, 6):
+        before, _ = oracle.generate(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, initial, k - 1)
+        ref = oracle.iterate_once(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, before)
+        with _ctx(emu_lib, overlap=overlap) as ctx:
+            helpers.load_ctx(ctx, m, p, outlets, initial)
+            e, it = ctx.generate(k)
+            assert it == k and np.array_equal(e, ref["elevations"])
+            assert np.array_equal(ctx.fetch("receivers"), ref["next"])
+            assert np.array_equal(ctx.fetch("drainage_area"), ref["drainage"])
+            assert np.array_equal(ctx.fetch("response_time"), ref["response"])
+    # ... and after convergence (the speculative K1 of the iteration that never runs has been launched)
+    full, its = oracle.generate(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, initial, 400)
+    if its < 400:
+        last = oracle.iterate_once(m, p["erodibility"], p["uplift"], p["max_slope"], outlets, full)
+        with _ctx(emu_lib, overlap=overlap) as ctx:
+            helpers.load_ctx(ctx, m, p, outlets, initial)
+            e, it = ctx.generate(400)
+            assert it == its and np.array_equal(e, full)
+            assert np.array_equal(ctx.fetch("receivers"), last["next"])
