@@ -27,6 +27,24 @@ def test_c3_four_million_sites_advanced(oracle, gpu_ctx_factory):
         assert it > 100
 
 
+def test_c3_one_million_sites_delaunay_rim_under_ocean_mask(oracle, gpu_ctx_factory):
+    """BASELINE config C3 on the real thing at 1M sites: relaxed random sites + the reference's own `add_edge_sites` rim
+    (equally spaced boundary sites: every rim edge has the same length, builder.rs:54-131) on a Delaunay graph, outlets =
+    the ocean flood-filled from the rim (terrain_generation_advanced.rs:36-42,178-182), noise-driven erodibility.  The
+    flood order -- tied rim edges and ~1e5 outlets included -- must come from the device and equal the oracle's heap
+    replay; then the size-independent properties of the converged result."""
+    from scenarios import scenario
+    m, p, outlets, initial, _ = scenario("edge_sites_ocean", 1000000)
+    assert outlets.size > 10000
+    with gpu_ctx_factory() as ctx:
+        helpers.load_ctx(ctx, m, p, outlets, initial)
+        assert np.array_equal(ctx.fetch("flood_rank"), oracle.flood_order(m, outlets))
+        st = ctx.stats()
+        assert st["flood_on_device"] == 1 and st["outlet_ranks_on_device"] == 1
+        _, it = helpers.check_converged_properties(ctx, oracle, m, p, outlets, initial, first_iterations=1)
+        assert it > 50
+
+
 def test_c4_sixteen_million_sites(oracle, gpu_ctx_factory):
     """BASELINE config C4 at full size: 16M sites, uniform erodibility, rim outlets, generate() to convergence on one
     B200 (the loop of src/lem/generator.rs:140-210).  The graph is the jittered 4000 x 4000 lattice (planar
