@@ -160,6 +160,15 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # CPU arm
 # ------------------------------------------------------------------------------------------------------------------
+def ref_window_iters(args, n):
+    """Iterations per step of the CPU arm (and of the GPU arm's `window` leg, which times the same window): `--ref-iters`,
+    cut down so that steps + warmup of them stay near 100 s of single-thread CPU work (about 0.19 s per iteration and
+    million sites, 1 s per million sites for iteration 1 with its heap flood), never below 2."""
+    per_step = 100.0 / max(args.steps + args.warmup, 1)
+    fit = int((per_step - 1.0e-6 * n) / (0.19e-6 * n))
+    return max(2, min(args.ref_iters, fit))
+
+
 def run_reference(args, rank):
     """CPU arm: the oracle port, one thread; each step = the first `ref_iters` iterations of the C2 workload.
     Iteration 1 (whose lake removal runs the heap flood) is also timed on its own, so that the steady iterations can be
@@ -177,7 +186,7 @@ def run_reference(args, rank):
         m, p, outlets, _ = build_workload(args.workload, args.sites, seed=1)
     initial = O.initial_elevations(p["base"])
     n = m["n"]
-    iters = args.ref_iters if n <= 1000000 else max(5, int(args.ref_iters * 1000000 // n))
+    iters = ref_window_iters(args, n)
 
     def step(k):
         t0 = time.perf_counter()
@@ -346,11 +355,11 @@ def window_leg(args, local_rank, hm, hp, n):
         with _native.Context(local_rank) as c2:
             c2.set_graph(hm["row_ptr"], hm["col"], hm["dist"], hm["areas"])
             c2.set_parameters(hp["initial"], hp["erodibility"], hp["uplift"], None, hp["outlets"])
-            _, it = c2.generate(args.ref_iters, out=out)
+            _, it = c2.generate(ref_window_iters(args, n), out=out)
         ts.append(time.perf_counter() - t0)
     t = float(np.median(ts))
     return {"iterations": it, "seconds": t, "value": n * it / t, "unit": UNIT,
-            "what": f"first {args.ref_iters} iterations of the C2 generate() through the C ABI with host buffers, context "
+            "what": f"first {ref_window_iters(args, n)} iterations of the C2 generate() through the C ABI with host buffers, context "
                     f"creation and destruction included (median of 3) -- the window `--impl reference` times"}
 
 
@@ -694,7 +703,7 @@ def multi_gpu(args, rank, local_rank, world):
 
     # e2e: the same ensemble through the C ABI with host buffers -- the graph uploaded inside the timed region (once per
     # rank), every member = set_parameters from pinned host arrays + generate with the elevations copied to the host
-    total_e2e = min(total, 2 * per_step)  # (a shorter run of the same thing: at most two steps' worth of members)
+    total_e2e = min(total, per_step)  # (a shorter run of the same thing: one step's worth of members)
     pool2 = ensemble.MemberPool.for_process_group(total_e2e, "fastlem_e2e")
     n_ctx = max(1, args.contexts_per_gpu)
     host_out = {}
@@ -727,7 +736,9 @@ def multi_gpu(args, rank, local_rank, world):
     dist.all_reduce(e2e_w, op=dist.ReduceOp.SUM)
 
     raster = None
-    if args.raster > 0 and args.workload == "delaunay":
+    # (the raster leg needs a second pass over the triangulation on the host: only for models up to 2M sites, where it
+    # costs seconds; profiles/r2p_bench_*gpu.json hold the 1M-site raster over 2 / 4 / 8 GPUs)
+    if args.raster > 0 and args.workload == "delaunay" and n <= 2000000:
         try:
             raster = raster_leg(args, results[0], m, rank, world, local_rank, barrier)
         except Exception as ex:
