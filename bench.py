@@ -703,7 +703,7 @@ def multi_gpu(args, rank, local_rank, world):
 
     # e2e: the same ensemble through the C ABI with host buffers -- the graph uploaded inside the timed region (once per
     # rank), every member = set_parameters from pinned host arrays + generate with the elevations copied to the host
-    total_e2e = min(total, per_step)  # (a shorter run of the same thing: one step's worth of members)
+    total_e2e = min(total, 2 * per_step)  # (a shorter run of the same thing: at most two steps' worth of members)
     pool2 = ensemble.MemberPool.for_process_group(total_e2e, "fastlem_e2e")
     n_ctx = max(1, args.contexts_per_gpu)
     host_out = {}
