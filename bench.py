@@ -620,7 +620,7 @@ def multi_gpu(args, rank, local_rank, world):
     import torch.distributed as dist
     from fastlem_b200 import _native, ensemble
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    # BASELINE config C5: members of 4M sites (`--ensemble-sites`; `--sites` if given explicitly); the same model on every rank
+    # the ensemble's model (`--ensemble-sites`; `--sites` if given explicitly); the same model on every rank
     sites_arg = args.sites if args.sites != 1000000 else args.ensemble_sites
     m, p, outlets, t_build = build_workload(args.workload, sites_arg, seed=1)
     n = m["n"]
@@ -800,8 +800,10 @@ def main():
     ap.add_argument("--c4-cpu-iters", type=int, default=5)
     ap.add_argument("--ensemble-members", type=int, default=16, help="members of the N = 1 ensemble leg (0 = skip)")
     ap.add_argument("--members-per-rank", type=int, default=8, help="N > 1: ensemble members per rank and step")
-    ap.add_argument("--ensemble-sites", type=int, default=4000000,
-                    help="N > 1: sites of the ensemble's model (BASELINE config C5: 4M-site terrains)")
+    ap.add_argument("--ensemble-sites", type=int, default=1000000,
+                    help="N > 1: sites of the ensemble's model.  BASELINE config C5 has 4M-site members: "
+                         "`--ensemble-sites 4000000 --workload lattice` (profiles/r2r_bench_8gpu_c5_4M.json); the default "
+                         "Delaunay model of 4M sites costs minutes of Qhull per rank")
     ap.add_argument("--contexts-per-gpu", type=int, default=4,
                     help="N > 1: ensemble members in flight per GPU (one context + host thread each)")
     ap.add_argument("--sweep", type=int, default=None, help="solver option 'sweep' (DESIGN.md)")

@@ -38,6 +38,13 @@
 #define FL_PDEPTH 3   // windows of a segment kept in flight
 #endif
 #define FL_CUT_MAX 8u  // largest cut height (= most k_elev_low launches per iteration)
+#ifndef FL_TOP_WAIT_LIMIT_NS
+// how long a warp of k_elev_top polls for its queue entry before the sweep is declared broken.  A guard against hanging,
+// not a schedule: idle warps wait as long as the kernel runs, so the limit bounds the kernel's run time.  It used to be
+// a poll count (2^24, a few seconds) and fired in a two-process run with four contexts per GPU on 4M-site models
+// (profiles/r2v_bench_2gpu_failed.err) although the same members pass in one process; wall clock, and generous, now.
+#define FL_TOP_WAIT_LIMIT_NS 120000000000ull
+#endif
 #ifndef FL_TOP_EARLY_WINDOW
 #define FL_TOP_EARLY_WINDOW 1  // build-time A/B switch: k_elev_top requests a run's first window with the entry's payload
 #endif
@@ -596,6 +603,7 @@ __global__ void __launch_bounds__(256) k_elev_top(FlSplit e) {
         t = __shfl_sync(FL_FULL, t, 0);
         if (t >= e.n) break;  // more tickets than entries can ever exist
         uint32_t q = FL_NONE, idle = 0u;
+        unsigned long long wait_from = 0ull;
         for (;;) {
             // every lane runs its own acquire load of the flag word (one broadcast transaction)
             const unsigned long long f = flq_ld_acquire(&e.queue[t].flag);
@@ -611,7 +619,13 @@ __global__ void __launch_bounds__(256) k_elev_top(FlSplit e) {
                     fin = (done == tail && t >= tail) ? 1u : 0u;
                 }
                 if (__shfl_sync(FL_FULL, fin, 0)) break;
-                if (idle > (1u << 24)) { if (lane == 0) atomicOr(&e.flags[FL_FLAG_BROKEN], 2u); break; }
+                if ((idle & 1023u) == 0u) {  // (the wall clock once per ~1000 polls)
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    now = __shfl_sync(FL_FULL, now, 0);
+                    if (wait_from == 0ull) wait_from = now;
+                    else if (now - wait_from > FL_TOP_WAIT_LIMIT_NS) { if (lane == 0) atomicOr(&e.flags[FL_FLAG_BROKEN], 2u); break; }
+                }
             }
             __nanosleep(idle < 8u ? 32u : 100u);
         }
