@@ -611,10 +611,15 @@ __global__ void __launch_bounds__(256) k_elev_top(FlSplit e) {
             ++idle;
             if ((idle & 31u) == 0u) {
                 // All work is done when every entry ever appended has been finished: an entry is appended only by an
-                // unfinished one, so done == tail (done read first) is final.
+                // unfinished one, so done == tail is final -- PROVIDED the tail read is not older than the done read and
+                // counts every entry the finished ones appended.  Hence: `done` is read with acquire (the tail load
+                // cannot be served before it) and incremented with release (a finisher's reservations on `tail` are
+                // visible before its increment of `done`).  Two relaxed loads let a warp pair a NEW done with an OLD tail
+                // (different L2 slices), leave with a ticket whose entry was about to be written, and orphan that entry:
+                // the sweep then waited for it until the limit (profiles/r2v_bench_2gpu_failed.err: tail 278, done 277).
                 uint32_t fin = 0u;
                 if (lane == 0) {
-                    const uint32_t done = fl_ld_relaxed(&e.flags[FLQ_DONE]);
+                    const uint32_t done = fl_ld_acquire(&e.flags[FLQ_DONE]);
                     const uint32_t tail = fl_ld_relaxed(&e.flags[FLQ_TAIL]);
                     fin = (done == tail && t >= tail) ? 1u : 0u;
                 }
@@ -640,7 +645,9 @@ __global__ void __launch_bounds__(256) k_elev_top(FlSplit e) {
         s.e_out = s.root != FL_NONE ? e.elev[s.root] : 0.0;
         s.rt_out = s.root != FL_NONE ? e.rt[s.root] : 0.0;
         fl_run_warp<true, FL_PDEPTH>(e, q, s, changed, sm, FL_TOP_EARLY_WINDOW ? &w0 : nullptr);
-        if (lane == 0) atomicAdd(&e.flags[FLQ_DONE], 1u);
+        __syncwarp();
+        if (lane == 0)  // release: this entry's reservations on the queue tail are visible before it counts as done
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&e.flags[FLQ_DONE]) : "memory");
     }
     if (changed) e.flags[FL_FLAG_CHANGED] = 1u;
 }
