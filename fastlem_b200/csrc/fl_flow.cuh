@@ -150,8 +150,6 @@ struct FlFlow {
     uint32_t* flags;
     uint32_t* parked;    // sites where a long climb was parked for the warp-level pass
     uint32_t* counters;  // [0] = number of parked climbs, [1] = next one to take
-    uint32_t* ready;     // per parked slot: the entry is complete (fused launch: warps wait on their ticket's slot)
-    uint32_t* remaining; // fused launch: dirty tree roots not yet finished (0 = all work done); null otherwise
     uint32_t park_after; // a thread parks its climb after this many sites (0 = never)
     unsigned long long* stats;
     unsigned long long* tlog;  // FL_FLOW_STATS builds: 4 time stamps per segment head
@@ -428,10 +426,6 @@ __device__ void fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t
                 f.hbuf[cur] = hrun;
                 const uint32_t slot = atomicAdd(&f.counters[0], 1u);
                 f.parked[slot] = cur;
-                if (f.remaining) {  // fused launch: a warp may already be waiting for this slot
-                    fl_fence_release();
-                    atomicExch(&f.ready[slot], 1u);
-                }
                 return;
             }
             continue;
@@ -442,7 +436,6 @@ __device__ void fl_flow_thread(const FlFlow& f, uint32_t cur, double x, uint32_t
         f.hgt[cur] = hrun;
         if (p == cur) {  // tree root: its segment has the largest nesting height of the tree
             if (hrun > 0u) atomicMax(&f.flags[FL_FLAG_MAXDEPTH], hrun);
-            if (f.remaining) atomicSub(f.remaining, 1u);
             return;
         }
         uint32_t dep = 0u;
@@ -730,7 +723,6 @@ __device__ void fl_flow_warp(const FlFlow& f, uint32_t cur, double x, uint32_t h
         if (lane == 0) { f.hgt[h] = hrun; FL_COUNT(f, FLS_W_HEADS, 1); FL_TLOG(f, h, 3); }
         if (p == h) {
             if (lane == 0 && hrun > 0u) atomicMax(&f.flags[FL_FLAG_MAXDEPTH], hrun);
-            if (lane == 0 && f.remaining) atomicSub(f.remaining, 1u);
             return;
         }
         uint32_t next_tail = FL_NONE, dep = 0u;
@@ -801,10 +793,7 @@ __device__ __forceinline__ void fl_mark_up(const FlFlow& f, uint32_t p) {
         if (!(old & FL_NW_RFLAG)) f.rlist[atomicAdd(&f.flags[FL_FLAG_NREGATHER], 1u)] = p;
         if (prev != 0u) return;  // the segment is already dirty: whoever marked it first walks on from its head
         f.slist[atomicAdd(&f.flags[FL_FLAG_NDIRTY], 1u)] = sh;
-        if (pp == sh) {  // tree root: the fused launch ends when every dirty root is finished
-            atomicAdd(&f.flags[FL_FLAG_NROOTS], 1u);
-            return;
-        }
+        if (pp == sh) return;  // tree root
         atomicAdd(&f.nwait[pp], 1u);  // the dirty head sh will report to pp
         p = pp;
     }
@@ -862,57 +851,7 @@ __global__ void __launch_bounds__(256) k_incr_cleanup(FlFlow f) {
         f.seg_wait[sh] = 0u;
         f.seg_done[sh] = 0u;
     }
-    const uint32_t np = f.counters[0];
-    for (uint32_t k = FL_TID; k < np; k += gridDim.x * blockDim.x) f.ready[k] = 0u;
 }
-
-#ifndef FL_EMU
-// Fused incremental pass: the thread-level starts and the warp-level continuation of the long climbs in ONE launch
-// whose blocks are all resident.  Phase A: the dirty segments that wait for nobody are started, one thread each.
-// Phase B: every warp takes a ticket and waits for the parked climb with that number -- or for the end of all work
-// (every dirty tree root finished).  A parked climb thus continues as soon as some warp is free instead of waiting for
-// the next launch.
-__global__ void __launch_bounds__(256, 2) k_incr_flow(FlFlow f) {
-    __shared__ FlAreaSmem chain_smem[8];
-    FlAreaSmem& sm = chain_smem[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
-    if (threadIdx.x < 128u) {  // phase A in the first four warps of a block; the other four serve parked climbs at once
-        const uint32_t cnt = f.flags[FL_FLAG_NDIRTY];
-        for (uint32_t k = blockIdx.x * 128u + threadIdx.x; k < cnt; k += gridDim.x * 128u) {
-            const uint32_t sh = f.slist[k];
-            if (f.seg_wait[sh] != 0u) continue;
-            const uint32_t cur = fl_seg_start(f, sh);
-            double x;
-            uint32_t hrun;
-            bool has_chain;
-            fl_seg_entry(f, cur, x, hrun, has_chain);
-            FL_COUNT(f, FLS_T_CLIMBS, 1);
-            fl_flow_thread(f, cur, x, hrun, has_chain, true);
-        }
-    }
-    __syncwarp();
-    for (;;) {
-        uint32_t idx = 0u, what = 0u;  // what: 1 = my parked climb is there, 2 = all work is done
-        if (lane == 0) {
-            idx = atomicAdd(&f.counters[1], 1u);
-            uint32_t spins = 0u;
-            for (;;) {
-                if (fl_ld_acquire(&f.ready[idx]) != 0u) { what = 1u; break; }
-                if ((spins & 3u) == 0u && fl_ld_relaxed(f.remaining) == 0u) { what = 2u; break; }
-                __nanosleep(200);
-                if (++spins > (1u << 21)) { atomicOr(&f.flags[FL_FLAG_BROKEN], 8u); what = 2u; break; }
-            }
-        }
-        idx = __shfl_sync(FL_FULL, idx, 0);
-        what = __shfl_sync(FL_FULL, what, 0);
-        __syncwarp();  // lane 0's acquire load happens before the other lanes' loads of the parked climb
-        if (what == 2u) return;
-        const uint32_t cur = fl_ld_cg(&f.parked[idx]);
-        if (lane == 0) { FL_COUNT(f, FLS_W_FLOWS, 1); FL_TLOG(f, cur, 2); }
-        fl_flow_warp(f, cur, fl_ld_cg(&f.xbuf[cur]), fl_ld_cg(&f.hbuf[cur]), true, sm);
-    }
-}
-#endif
 
 // ------------------------------------------------------------------------------------------------
 // First iteration: there are no previous drainage areas to choose heavy children by, so the layout is built from

@@ -130,9 +130,6 @@ struct fastlem_ctx {
     uint32_t* d_sg_wait = nullptr;
     uint32_t* d_sg_done = nullptr;
     // incremental K4 (fl_flow.cuh): state kept between iterations + per-iteration work lists
-    uint32_t* d_ready = nullptr;      // fused incremental K4: per parked slot
-    int incr_flow_blocks = 0;         // resident blocks of k_incr_flow (0 = not available)
-    int64_t opt_fuse_k4 = 0;     // measured no faster than two launches: kept as an option
     int64_t opt_first_flow = 1;  // the first iteration also uses the dataflow sweeps (layout by subtree sizes)
     // K5 split by nesting height (fl_elev.cuh): queue of run starts for the top of the forest, push masks
     uint2* d_low_list = nullptr;     // K5: (head, receiver) pairs per height below the cut (k_elev_plan -> k_elev_low)
@@ -994,7 +991,6 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool may_continue, bool* changed_o
     f.hgt = c->d_hgt; f.flags = c->d_flags; f.parked = c->d_parked; f.counters = c->d_flags + FL_FLAG_PARKED;
     f.park_after = (uint32_t)c->opt_park_after; f.stats = c->d_flow_stats; f.tlog = c->d_tlog;
     f.hsuf = c->d_hsuf; f.dirty_from = nullptr; f.rlist = c->d_rlist; f.slist = c->d_slist;
-    f.ready = c->d_ready; f.remaining = nullptr;
     if (!incr) {
         FL_CK(fl_memset(c->d_state, 0, sizeof(uint32_t) * n, c->stream));
         FL_CK(fl_memset(c->d_nwait, 0, sizeof(uint32_t) * n, c->stream));
@@ -1035,28 +1031,16 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool may_continue, bool* changed_o
             FL_LAUNCH(k_incr_mark, blocks_for(n_chg, 128), 128, c->stream, f, n_chg, c->d_chg_node, c->d_chg_old);
             const unsigned wide = (unsigned)c->sm_count * 8u;
             FL_LAUNCH(k_incr_prepare, wide, 128, c->stream, f);
-            bool fused = false;
-#ifndef FL_EMU
-            if (c->opt_fuse_k4 && f.park_after && c->incr_flow_blocks > 0) {
-                // one launch for the thread-level starts and the warp-level continuation (all blocks resident)
-                f.remaining = c->d_flags + FL_FLAG_NROOTS;
-                FL_LAUNCH(k_incr_flow, (unsigned)c->incr_flow_blocks, 256, c->stream, f);
-                f.remaining = nullptr;
-                fused = true;
-            }
-#endif
-            if (!fused) {
+            FL_RC(k_begin(c));
+            FL_LAUNCH(k_incr_start, wide * 2u, 64, c->stream, f);
+            FL_RC(k_end(c, FASTLEM_K_INCR_START));
+            if (f.park_after) {
                 FL_RC(k_begin(c));
-                FL_LAUNCH(k_incr_start, wide * 2u, 64, c->stream, f);
-                FL_RC(k_end(c, FASTLEM_K_INCR_START));
-                if (f.park_after) {
-                    FL_RC(k_begin(c));
-                    FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 4u, 256, c->stream, f);
-                    FL_RC(k_end(c, FASTLEM_K_AREA_FLOW_LONG));
-                }
+                FL_LAUNCH(k_area_flow_long, (unsigned)c->sm_count * 4u, 256, c->stream, f);
+                FL_RC(k_end(c, FASTLEM_K_AREA_FLOW_LONG));
             }
             FL_LAUNCH(k_incr_cleanup, wide, 256, c->stream, f);
-            const uint64_t nl = fused ? 6 : (f.park_after ? 7 : 6);
+            const uint64_t nl = f.park_after ? 7 : 6;
             c->stats.kernel_launches += nl;
             c->stats.n_area += nl;
         }
@@ -1147,8 +1131,6 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool may_continue, bool* changed_o
             FL_RC(read_flags(c));
             if (c->h_flags[FL_FLAG_BROKEN] & 1u)
                 return fail(c, FASTLEM_E_STATE, "K4: a climb met an unpublished site (internal error)");
-            if (c->h_flags[FL_FLAG_BROKEN] & 8u)
-                return fail(c, FASTLEM_E_STATE, "K4: the fused pass waited for parked work too long (internal error)");
             maxh = c->h_flags[FL_FLAG_K4MAXH];
             if (incr && c->prev_maxh > maxh) maxh = c->prev_maxh;
             // redo with the exact base when a key overflowed the fixed base, or when the bound carried over from the
@@ -1246,8 +1228,6 @@ int iterate_flow(fastlem_ctx* c, uint32_t it, bool may_continue, bool* changed_o
     if (c->opt_k5_split) {
         if (c->h_flags[FL_FLAG_BROKEN] & 1u)
             return fail(c, FASTLEM_E_STATE, "K4: a climb met an unpublished site (internal error)");
-        if (c->h_flags[FL_FLAG_BROKEN] & 8u)
-            return fail(c, FASTLEM_E_STATE, "K4: the fused pass waited for parked work too long (internal error)");
         if (c->h_flags[FL_FLAG_BROKEN])
             return fail(c, FASTLEM_E_STATE,
                         "K5: the run queue broke (internal error; flags " + std::to_string(c->h_flags[FL_FLAG_BROKEN]) +
@@ -1395,7 +1375,6 @@ int alloc_graph_buffers(fastlem_ctx* c, uint32_t n, uint32_t nnz) {
     FL_CK(dalloc(c, c->d_sg_tail, n));
     FL_CK(dalloc(c, c->d_sg_wait, n));
     FL_CK(dalloc(c, c->d_sg_done, n));
-    FL_CK(dalloc(c, c->d_ready, (size_t)n + 65536));
     FL_CK(dalloc(c, c->d_low_list, fl_low_region(n, FL_CUT_MAX)));
     FL_CK(dalloc(c, c->d_queue, n));
     FL_CK(dalloc(c, c->d_pmask, n));
@@ -1532,8 +1511,6 @@ int fastlem_set_option(fastlem_ctx* c, const char* name, int64_t value) {
         c->opt_incr_div = value;
     } else if (s == "first_flow") {
         c->opt_first_flow = value != 0;
-    } else if (s == "fuse_k4") {
-        c->opt_fuse_k4 = value != 0;
     } else if (s == "key_base") {
         if (value < 1 || value > (int64_t)FL_KEY_BASE) return fail(c, FASTLEM_E_INVALID, "option key_base: 1..254");
         c->opt_key_base = value;
@@ -1605,7 +1582,6 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
     FL_CK(fl_memset(c->d_flags, 0, sizeof(uint32_t) * FL_N_FLAGS, c->stream));
     LAUNCH_N(k_rev_slots, n, n, c->orig.row_ptr, c->orig.col, c->orig.dist, c->orig.rev, c->d_flags);
     FL_CK(fl_d2h(c->h_flags, c->d_flags, sizeof(uint32_t), c->stream));
-    FL_CK(fl_memset(c->d_ready, 0, sizeof(uint32_t) * ((size_t)n + 65536), c->stream));
     FL_CK(fl_memset(c->d_queue, 0, sizeof(FlQEntry) * n, c->stream));
     FL_CK(fl_memset(c->d_rt, 0, sizeof(double) * n, c->stream));  // (read, never used, for sites of trees without outlet)
     // the climbs of K4 request a batch's / a window's partial sums before they know which of its sites have any: sites that
@@ -1627,11 +1603,6 @@ int fastlem_set_graph(fastlem_ctx* c, uint32_t n, const uint32_t* row_ptr, const
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elev_top, 256, 0) != cudaSuccess || occ < 1)
             return fail(c, FASTLEM_E_CUDA, "set_graph: k_elev_top does not fit on an SM");
         c->top_blocks = occ * fl_sm_count();  // the most that can be resident
-    }
-    {
-        int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_incr_flow, 256, 0) == cudaSuccess && occ > 0)
-            c->incr_flow_blocks = occ * fl_sm_count();
     }
     {
         int occ = 0;

@@ -100,7 +100,7 @@ int fastlem_download_to_device(fastlem_ctx* ctx, double* device_elevations_out);
  * fastlem_stats; "keep_stages" = 1 (default 0) keeps the pre-lake-removal receivers/labels of the last iteration for
  * fastlem_debug_fetch.  The rest select between implementations that give bit-identical results:
  * "sweep" 0 = one launch per tree level, 1 / 2 = path-decomposed (thread / warp per path), 3 = dataflow sweeps
- * (default); "incremental" (1), "incr_div" (16), "first_flow" (1), "fuse_levels" (1), "fuse_k4" (0), "flood_device" (1), "outlet_closed_form" (1),
+ * (default); "incremental" (1), "incr_div" (16), "first_flow" (1), "fuse_levels" (1), "flood_device" (1), "outlet_closed_form" (1),
  * "park_after" (8), "key_base", "rebuild_every" (0 = adaptive), "rebuild_growth" / "rebuild_height" (0 = by model size: 4 / 150 percent up to 1M sites,
  * 8 / 250 from 16M sites on), "k1_bulk" (1), "overlap" (1), "outlet_closed_form" (1). */
 int fastlem_set_option(fastlem_ctx* ctx, const char* name, int64_t value);

@@ -145,7 +145,7 @@ def test_c7_nonuniform_uplift_lakes_every_iteration(oracle, gpu_ctx_factory):
 
 
 @pytest.mark.parametrize("opts", [dict(k5_split=0, key_base=1), dict(k5_split=0, fuse_levels=0), dict(incremental=0), dict(incr_div=1),
-                                  dict(flood_device=0), dict(fuse_k4=1), dict(first_flow=0), dict(k5_split=0), dict(k5_cut=0), dict(k5_cut=1), dict(k5_cut=3), dict(k5_cut=8), dict(k5_top_cap=50),
+                                  dict(flood_device=0), dict(first_flow=0), dict(k5_split=0), dict(k5_cut=0), dict(k5_cut=1), dict(k5_cut=3), dict(k5_cut=8), dict(k5_top_cap=50),
                                   dict(k1_bulk=0), dict(overlap=0), dict(outlet_closed_form=0), dict(k1_bulk=0, overlap=0, k5_cut=2),
                                   dict(rebuild_growth=1, rebuild_height=100), dict(rebuild_growth=50, rebuild_height=400)])
 @pytest.mark.parametrize("name,n", [("uniform", 30000), ("advanced", 20000), ("max_slope", 20000)])
