@@ -148,3 +148,13 @@ def test_host_graph_from_triangles_matches_builder_rule(product_lib):
     assert dist.tolist() == [3.0, 3.0, 5.0, 4.0, 5.0, 4.0]
     with pytest.raises(_native.FastlemError):
         _native.host_graph_from_triangles(sites, np.array([0, 1, 7], dtype=np.uint32), product_lib)
+
+
+def test_trim_memory_is_exported_and_harmless(emu_lib):
+    """fastlem_trim_memory (include/fastlem_b200.h): returns the library's cached device memory to the driver; the host
+    emulation has no pool and reports success."""
+    import ctypes
+    lib = ctypes.CDLL(emu_lib)
+    lib.fastlem_trim_memory.argtypes = [ctypes.c_int]
+    lib.fastlem_trim_memory.restype = ctypes.c_int
+    assert lib.fastlem_trim_memory(0) == 0
